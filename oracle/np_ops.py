@@ -1,0 +1,194 @@
+"""numpy restatement of lele's indexing / shape / element-wise operators.
+TEST INFRASTRUCTURE ONLY (see oracle/lele_oracle.h).  Citations: /root/reference paths.
+
+These ops are bit-exact copies or single IEEE operations, so numpy float32 arithmetic
+reproduces the reference exactly (no accumulation order is involved except reductions).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+f32 = np.float32
+
+
+def _a(x):
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+# ---- manipulation.rs ----
+def concat(xs, axis):  # manipulation.rs:108-207 (empty inputs skipped)
+    xs = [_a(x) for x in xs if np.asarray(x).size > 0]
+    return np.concatenate(xs, axis=axis)
+
+
+def _slice_bounds(dim, start, end, step):  # manipulation.rs:268-330
+    I64MAX, I64MIN = 2**63 - 1, -2**63
+    end_max = end > I64MAX // 2
+    end_min = end < I64MIN // 2
+    s = dim if start > dim else (-dim if start < -dim else start)
+    if end_max: e = dim
+    elif end_min: e = -dim
+    elif end > dim: e = dim
+    elif end < -dim: e = -dim
+    else: e = end
+    ns = s + dim if s < 0 else s
+    if end_max: ne = dim if step > 0 else -1
+    elif end_min: ne = 0 if step > 0 else -1
+    elif e < 0: ne = e + dim
+    else: ne = e
+    if step > 0:
+        return min(max(ns, 0), dim), min(max(ne, 0), dim)
+    return min(max(ns, 0), dim - 1), min(max(ne, -1), dim - 1)
+
+
+def slice_(x, starts, ends, axes=(), steps=()):  # manipulation.rs:209-381
+    x = _a(x)
+    idx = [np.arange(d) for d in x.shape]
+    for i in range(len(starts)):
+        ax = i if len(axes) == 0 else (axes[i] + x.ndim if axes[i] < 0 else axes[i])
+        step = steps[i] if i < len(steps) else 1
+        s, e = _slice_bounds(x.shape[ax], int(starts[i]), int(ends[i]), step)
+        idx[ax] = np.arange(s, e, step)
+    return x[np.ix_(*idx)]
+
+
+def pad(x, pads, value=0.0, mode="constant"):  # manipulation.rs:382-588
+    x = _a(x)
+    r = x.ndim
+    p = [max(int(v), 0) for v in pads]
+    if len(p) < 2 * r:
+        half = len(p) // 2
+        miss = r - half
+        full = [0] * (2 * r)
+        for i in range(half):
+            full[miss + i] = p[i]
+            full[r + miss + i] = p[half + i]
+        p = full
+    widths = [(p[i], p[i + r]) for i in range(r)]
+    if mode == "constant":
+        return np.pad(x, widths, mode="constant", constant_values=f32(value))
+    return np.pad(x, widths, mode=mode)  # "edge" / "reflect" match numpy's definitions
+
+
+def gather(x, indices, axis=0):  # manipulation.rs:589-640
+    x = _a(x)
+    idx = np.asarray(indices).astype(np.int64)
+    ax = axis + x.ndim if axis < 0 else axis
+    idx = np.where(idx < 0, idx + x.shape[ax], idx)
+    return np.take(x, idx, axis=ax)
+
+
+def transpose(x, perm=()):  # manipulation.rs:644-1080 (empty perm = reverse)
+    x = _a(x)
+    return np.ascontiguousarray(np.transpose(x, perm if len(perm) else None))
+
+
+def split(x, axis, splits):  # manipulation.rs:1091-1213
+    x = _a(x)
+    ax = axis + x.ndim if axis < 0 else axis
+    outs, o = [], 0
+    for s in splits:
+        sl = [slice(None)] * x.ndim
+        sl[ax] = slice(o, o + int(s))
+        outs.append(np.ascontiguousarray(x[tuple(sl)]))
+        o += int(s)
+    return outs
+
+
+def where_op(cond, x, y):  # manipulation.rs:1215-1399 (non-zero = true)
+    return np.where(np.asarray(cond) != 0, _a(x), _a(y)).astype(np.float32)
+
+
+def expand(x, shape):  # math.rs:2168-2248
+    x = _a(x)
+    tgt = np.broadcast_shapes(x.shape, tuple(int(s) for s in shape))
+    return np.ascontiguousarray(np.broadcast_to(x, tgt))
+
+
+def tile(x, repeats):  # math.rs:2249-2300
+    return np.tile(_a(x), tuple(int(r) for r in repeats))
+
+
+def reshape(x, shape):  # shape.rs:2-93 (0 = copy dim, -1 = infer)
+    x = _a(x)
+    shp = [x.shape[i] if (s == 0 and i < x.ndim) else int(s) for i, s in enumerate(shape)]
+    return x.reshape(shp)
+
+
+def topk(x, k):  # conv2d.rs:1385-1437: last axis, stable, indices as f32
+    x = _a(x)
+    k = min(int(k), x.shape[-1])
+    order = np.argsort(-x, axis=-1, kind="stable")[..., :k]
+    return np.take_along_axis(x, order, axis=-1), order.astype(np.float32)
+
+
+def gather_elements(x, indices, axis):  # conv2d.rs:1438-1506: f32 indices, negative wrap
+    x = _a(x)
+    ax = axis + x.ndim if axis < 0 else axis
+    idx = np.asarray(indices).astype(np.int64)
+    idx = np.where(idx < 0, idx + x.shape[ax], idx)
+    return np.take_along_axis(x, idx, axis=ax)
+
+
+def resize_nearest(x, scales=None, sizes=None, mode="asymmetric"):  # conv2d.rs:1261-1384
+    x = _a(x)
+    n, c, h, w = x.shape
+    if sizes is not None:
+        oh, ow = int(sizes[2]), int(sizes[3])
+    else:
+        sh = scales[2] if len(scales) >= 3 else 1.0
+        sw = scales[3] if len(scales) >= 4 else 1.0
+        oh, ow = int(np.float64(h) * np.float64(f32(sh))), int(np.float64(w) * np.float64(f32(sw)))
+    hs, ws = f32(h) / f32(oh), f32(w) / f32(ow)
+
+    def src(o, scale, lim):
+        o = np.arange(o, dtype=np.float32)
+        if mode == "asymmetric":
+            v = np.minimum(np.floor(o * scale), f32(lim - 1))
+        else:
+            t = (o + f32(0.5)) * scale - f32(0.5)
+            v = np.sign(t) * np.floor(np.abs(t) + f32(0.5))  # f32::round = half away from zero
+            v = np.minimum(np.maximum(v, f32(0.0)), f32(lim - 1))
+        return v.astype(np.int64)
+
+    ih, iw = src(oh, hs, h), src(ow, ws, w)
+    return np.ascontiguousarray(x[:, :, ih][:, :, :, iw])
+
+
+# ---- math.rs element-wise (NumPy broadcasting, utils.rs:107) ----
+def add(a, b): return (_a(a) + _a(b)).astype(np.float32)           # math.rs:414
+def sub(a, b): return (_a(a) - _a(b)).astype(np.float32)           # math.rs:838
+def mul(a, b): return (_a(a) * _a(b)).astype(np.float32)           # math.rs:611
+def div(a, b): return (_a(a) / _a(b)).astype(np.float32)           # math.rs:1106
+def maximum(a, b): return np.maximum(_a(a), _a(b))                 # math.rs:1922
+def neg(x): return -_a(x)                                          # math.rs:2142
+def sqrt(x): return np.sqrt(_a(x))                                 # math.rs:1460
+def reciprocal(x): return (f32(1.0) / _a(x)).astype(np.float32)    # math.rs:893
+def clip(x, lo, hi): return np.minimum(np.maximum(_a(x), f32(lo)), f32(hi))  # math.rs:1984
+
+
+def mod_f32(a, b):  # math.rs:1163-1192 : a - b*floor(a/b), 0 when b == 0
+    a, b = _a(a), np.broadcast_to(_a(b), np.shape(a))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = a - b * np.floor(a / b)
+    return np.where(b == 0, f32(0), r).astype(np.float32)
+
+
+def prelu(x, slope):  # math.rs:2012
+    x = _a(x)
+    return np.where(x < 0, x * _a(slope), x).astype(np.float32)
+
+
+def reduce(x, axes, keepdims, kind):  # math.rs:1527-1921
+    x = _a(x)
+    axes = tuple(a + x.ndim if a < 0 else a for a in axes) if len(axes) else tuple(range(x.ndim))
+    if kind == "sum":
+        return np.add.reduce(x, axis=axes, keepdims=keepdims, dtype=np.float32)
+    if kind == "mean":
+        cnt = int(np.prod([x.shape[a] for a in axes]))
+        return (np.add.reduce(x, axis=axes, keepdims=keepdims, dtype=np.float32) * (f32(1.0) / f32(cnt))).astype(np.float32)
+    if kind == "max":
+        return np.max(x, axis=axes, keepdims=keepdims)
+    if kind == "l2":
+        return np.sqrt(np.add.reduce(x * x, axis=axes, keepdims=keepdims, dtype=np.float32)).astype(np.float32)
+    raise ValueError(kind)

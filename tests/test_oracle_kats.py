@@ -1,0 +1,219 @@
+"""Pins the CPU oracle against every known-answer vector the reference's own tests hold for
+the hot path, plus independent cross-checks (numpy / torch CPU)."""
+import numpy as np
+import pytest
+
+from oracle import reference_api as R
+from tests.kat_runner import KATS, kat_id, run_kat
+
+
+@pytest.mark.parametrize("k", KATS, ids=kat_id)
+def test_reference_kat(k):
+    run_kat(R, k)
+
+
+def test_layer_norm_mean_std():  # tests/kernel_accuracy.rs:100-132
+    out = R.layer_norm(np.array([[1, 2, 3], [4, 5, 6]], np.float32), np.ones(3), np.zeros(3), -1, 1e-5)
+    row = out[0]
+    assert abs(row.mean()) < 1e-5
+    var = 2.0 / 3.0
+    assert abs(row.std() - np.sqrt(var / (var + 1e-5))) < 1e-5
+
+
+def test_dql_dequant_error():  # tests/kernel_accuracy.rs:205-247
+    x = np.arange(1, 9, dtype=np.float32).reshape(2, 4)
+    q, s, z = R.dynamic_quantize_linear(x)
+    assert np.abs((q - z) * s - x).max() < s + 0.1
+    assert z == 0.0 and abs(s - 8.0 / 255.0) < 1e-7
+
+
+def test_silu_erf_vs_libm():  # tests/kernel_accuracy.rs:377-408 (17/19 elems hit the SIMD tail)
+    x = np.arange(-8, 9, dtype=np.float32) * 0.5
+    np.testing.assert_allclose(R.silu(x), x / (1 + np.exp(-x.astype(np.float64))), atol=1e-5)
+    import math
+    x = np.arange(-9, 10, dtype=np.float32) * 0.5
+    np.testing.assert_allclose(R.erf(x), [math.erf(v) for v in x], atol=2e-6)
+
+
+def _lcg_inputs(n, state):  # src/kernels/fft.rs:302-307
+    out = []
+    for _ in range(n):
+        state = (state * 1103515245 + 12345) & 0xFFFFFFFF
+        out.append(np.float32(state) / np.float32(0xFFFFFFFF) * 2.0 - 1.0)
+    return np.array(out, np.float32), state
+
+
+def test_rfft_vs_numpy_lcg():  # src/kernels/fft.rs:302-351 sizes and seed
+    st = 12345
+    for log_n in range(3, 11):
+        x, st = _lcg_inputs(1 << log_n, st)
+        re, im = R.rfft(x)
+        ref = np.fft.rfft(x.astype(np.float64))
+        np.testing.assert_allclose(re, ref.real, atol=1e-4)
+        np.testing.assert_allclose(im, ref.imag, atol=1e-4)
+
+
+def test_fft_parseval_linearity():  # tests/regression_kernels.rs:524-596
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(256).astype(np.float32)
+    y = rng.standard_normal(256).astype(np.float32)
+    rx, ix = R.rfft(x); ry, iy = R.rfft(y); rs, is_ = R.rfft(x + y)
+    np.testing.assert_allclose(rs, rx + ry, atol=1e-3)
+    np.testing.assert_allclose(is_, ix + iy, atol=1e-3)
+    full = np.concatenate([rx**2 + ix**2, (rx**2 + ix**2)[1:-1]])
+    assert abs(full.sum() / 256 - (x.astype(np.float64) ** 2).sum()) < 1e-4 * (x**2).sum() + 1e-2
+
+
+def test_mel_filterbank_shape_and_cmvn():  # verify_features.rs:66-80, features/cmvn.rs:98-110
+    w = R.mel_filterbank(16000.0, 512, 10, 0.0)
+    assert w.shape == (10, 257) and w.sum() > 0
+    out = R.cmvn(np.array([[1, 10], [2, 20], [3, 30]], np.float32))
+    assert abs(out[:, 0].mean()) < 1e-5 and out[0, 0] < 0 and abs(out[1, 0]) < 1e-5 and out[2, 0] > 0
+
+
+def test_stft_reference_properties():  # tests/regression_kernels.rs:426-517
+    p = R.stft(np.ones(512, np.float32), 256, 64, 256, power=True)
+    assert (p[:, 0] > 1000).all() and (p[:, 2:] < 1.0).all()
+    sig = np.sin(np.arange(800, dtype=np.float32) * np.float32(0.01))
+    c = R.stft(sig, 256, 128, 256); p = R.stft(sig, 256, 128, 256, power=True)
+    np.testing.assert_allclose(c[..., 0] ** 2 + c[..., 1] ** 2, p, atol=1e-3)
+    t = np.arange(1600, dtype=np.float32)
+    s = np.sin(np.float32(2 * np.pi) * 1000.0 * t / 16000.0).astype(np.float32)
+    p = R.stft(s, 256, 160, 256, power=True)
+    mid = p[p.shape[0] // 2]
+    other = np.concatenate([mid[:5], mid[-4:]])
+    assert mid[16] > 5 * other.max()
+
+
+def _ref_gru(x, w, r, bw, br, hs):  # tests/regression_kernels.rs:602-633 (f64 restatement)
+    h = np.zeros(hs); ys = []
+    sig = lambda v: 1 / (1 + np.exp(-v))
+    for xt in x:
+        wc = w @ xt; rc = r @ h
+        z = sig(wc[:hs] + rc[:hs] + bw[:hs] + br[:hs])
+        rg = sig(wc[hs:2 * hs] + rc[hs:2 * hs] + bw[hs:2 * hs] + br[hs:2 * hs])
+        hg = np.tanh(wc[2 * hs:] + bw[2 * hs:] + rg * (rc[2 * hs:] + br[2 * hs:]))
+        h = (1 - z) * hg + z * h
+        ys.append(h.copy())
+    return np.array(ys), h
+
+
+GRU_CASES = [  # tests/regression_kernels.rs:636-737
+    dict(sl=1, is_=4, hs=8, x=[0.1, 0.2, -0.1, 0.3], w=lambda i: i * 0.01 - 0.1, r=lambda i: i * 0.02 - 0.2, b=lambda i: i * 0.005 - 0.05, tol=1e-4),
+    dict(sl=5, is_=3, hs=6, x=lambda i: ((i * 7 + 3) % 20) * 0.1 - 0.5, w=lambda i: i * 0.03 - 0.2, r=lambda i: i * 0.01 - 0.1, b=lambda i: 0.1 + 0 * i, tol=1e-3),
+    dict(sl=3, is_=4, hs=8, x=lambda i: i * 0.15 - 0.3, w=lambda i: i * 0.01, r=lambda i: i * 0.02 - 0.1, b=lambda i: 0.05 + 0 * i, tol=1e-3),
+    dict(sl=2, is_=3, hs=4, x=[0.5, -0.3, 0.1, -0.2, 0.4, 0.6], w=lambda i: i * 0.05, r=lambda i: i * 0.03, b=None, tol=1e-4),
+]
+
+
+def gru_case(c):
+    sl, is_, hs = c["sl"], c["is_"], c["hs"]
+    gen = lambda f, n: np.array(f, np.float32) if isinstance(f, list) else f(np.arange(n, dtype=np.float32)).astype(np.float32)
+    x = gen(c["x"], sl * is_).reshape(sl, 1, is_)
+    w = gen(c["w"], 3 * hs * is_).reshape(1, 3 * hs, is_)
+    r = gen(c["r"], 3 * hs * hs).reshape(1, 3 * hs, hs)
+    b = None if c["b"] is None else gen(c["b"], 6 * hs).reshape(1, 6 * hs)
+    return x, w, r, b
+
+
+@pytest.mark.parametrize("c", GRU_CASES)
+def test_gru_vs_ref_gru_step(c):
+    x, w, r, b = gru_case(c)
+    hs = c["hs"]
+    y, h = R.gru(x, w, r, b)
+    bz = np.zeros(6 * hs) if b is None else b.reshape(-1).astype(np.float64)
+    yr, hr = _ref_gru(x[:, 0].astype(np.float64), w[0].astype(np.float64), r[0].astype(np.float64), bz[:3 * hs], bz[3 * hs:], hs)
+    np.testing.assert_allclose(y.reshape(-1, hs), yr, atol=c["tol"])
+    np.testing.assert_allclose(h.reshape(-1), hr, atol=c["tol"])
+
+
+def test_lstm_shape_finite():  # tests/regression_kernels.rs:972-997
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((4, 1, 8)).astype(np.float32)
+    w = (0.1 * rng.standard_normal((1, 64, 8))).astype(np.float32)
+    r = (0.1 * rng.standard_normal((1, 64, 16))).astype(np.float32)
+    y, h, c = R.lstm(x, w, r, None)
+    assert y.shape == (4, 1, 1, 16) and np.isfinite(y).all() and np.isfinite(c).all()
+
+
+def test_conv_vs_torch():  # tests/regression_kernels.rs:76-252 shapes; torch CPU as independent check
+    torch = pytest.importorskip("torch")
+    F = torch.nn.functional
+    rng = np.random.default_rng(2)
+    for (ic, oc, k, s, p, g) in [(3, 8, 3, 1, 1, 1), (4, 8, 3, 2, 1, 1), (4, 4, 3, 1, 1, 4), (8, 16, 1, 1, 0, 1)]:
+        x = rng.standard_normal((2, ic, 9, 11)).astype(np.float32)
+        w = rng.standard_normal((oc, ic // g, k, k)).astype(np.float32)
+        b = rng.standard_normal(oc).astype(np.float32)
+        for act in (0, 1, 2):
+            got = R.conv2d(x, w, b, (1, 1), g, (p, p, p, p), (s, s), act)
+            ref = F.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=s, padding=p, groups=g)
+            ref = ref if act == 0 else (F.relu(ref) if act == 1 else F.silu(ref))
+            np.testing.assert_allclose(got, ref.numpy(), atol=1e-3)
+    x = rng.standard_normal((1, 6, 5, 7)).astype(np.float32)
+    w = rng.standard_normal((6, 4, 3, 3)).astype(np.float32)
+    b = rng.standard_normal(4).astype(np.float32)
+    got = R.conv_transpose(x, w, b, (1, 1), (1, 1, 1, 1), (2, 2))
+    ref = F.conv_transpose2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=2, padding=1)
+    np.testing.assert_allclose(got, ref.numpy(), atol=1e-3)
+    assert R.conv_transpose(np.zeros((1, 8, 10, 10), np.float32), np.ones((8, 8, 2, 2), np.float32), None, (1, 1), (0, 0, 0, 0), (2, 2)).shape == (1, 8, 20, 20)  # conv2d.rs:3391
+    x = rng.standard_normal((2, 6, 40)).astype(np.float32)
+    w = rng.standard_normal((6, 1, 11)).astype(np.float32)
+    got = R.conv1d(x, w, None, (1,), 6, (5, 5), (1,))
+    ref = F.conv1d(torch.from_numpy(x), torch.from_numpy(w), padding=5, groups=6)
+    np.testing.assert_allclose(got, ref.numpy(), atol=1e-4)
+
+
+def test_int8_linear_matches_unfused_and_wasm_bench_shapes():
+    """fused_quantized_linear == DQL -> MatMulInteger -> scale -> bias (patterns.rs:122-190),
+    on the shapes src/bin/wasm_bench.rs:293-317 benchmarks (tol k*0.01 there; exact here)."""
+    rng = np.random.default_rng(3)
+    for (m, k, n) in [(93, 512, 1536), (93, 512, 512), (17, 560, 512), (5, 2048, 512), (3, 20, 9)]:
+        x = ((np.arange(m * k, dtype=np.float32) * 0.01) % 2.0 - 1.0).reshape(1, m, k)  # wasm_bench.rs:765
+        w = rng.integers(0, 256, (k, n), dtype=np.uint8)
+        ws = rng.uniform(0.002, 0.006, n).astype(np.float32)
+        b = rng.standard_normal(n).astype(np.float32)
+        fused = R.fused_quantized_linear(x, w, ws, 128, b, True)
+        q, s, z = R.dynamic_quantize_linear(x)
+        unf = R.mat_mul_integer(q, w.astype(np.float32), z, 128.0, (s * ws).astype(np.float32), b, True)
+        if k % 8 == 0:
+            np.testing.assert_array_equal(fused, unf)
+        else:  # row tail takes the scalar rounding in the fused kernel (avx/quantization.rs:208)
+            np.testing.assert_allclose(fused, unf, atol=float(s * ws.max() * 255 * 2))
+        # integer core exactness vs int64 numpy
+        acc = (q[0].astype(np.int64) - int(z)) @ (w.astype(np.int64) - 128)
+        ref = np.maximum(acc.astype(np.float32) * (s * ws) + b, 0)
+        np.testing.assert_array_equal(unf[0], ref.astype(np.float32))
+
+
+def test_indexing_ops_numpy_semantics():
+    x = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    np.testing.assert_array_equal(R.slice(x, [1], [2**63 - 1], [2], []), x[:, :, 1:])
+    np.testing.assert_array_equal(R.slice(x, [-1], [-(2**63)], [1], [-1]), x[:, ::-1])
+    np.testing.assert_array_equal(R.slice(x, [0], [1], [0], []), x[:1])
+    np.testing.assert_array_equal(R.pad(x[0], [1, 2], 0.0, "constant").shape, (3, 7))  # short pads -> trailing dims
+    np.testing.assert_array_equal(R.pad(x[0], [0, 1, 0, 1], mode="reflect"), np.pad(x[0], ((0, 0), (1, 1)), mode="reflect"))
+    v, i = R.topk(np.array([[1, 3, 3, 2]], np.float32), 2)
+    np.testing.assert_array_equal(i, [[1, 2]])  # stable: lower index first on ties (conv2d.rs:1385)
+    np.testing.assert_array_equal(R.gather(x, np.array([-1], np.float32), 1), x[:, [2]])
+    r = R.resize_nearest(np.array([[[[1, 2], [3, 4]]]], np.float32), scales=[1, 1, 2, 2])
+    np.testing.assert_array_equal(r[0, 0], [[1, 1, 2, 2], [1, 1, 2, 2], [3, 3, 4, 4], [3, 3, 4, 4]])  # conv2d.rs:3520
+
+
+def test_frontend_shapes_and_edges():
+    """SenseVoiceFrontend::compute (pipeline.rs:67): zh.wav-sized and 16 s clips."""
+    from lele_b200.sensevoice_weights import synth_pcm
+    assert R.frontend(np.zeros(399, np.float32)).shape == (0, 560)       # shorter than a frame -> empty
+    mel, out = R.frontend(synth_pcm(0, 89472), want_mel=True)            # fixtures/zh.wav length
+    assert mel.shape == (557, 80) and out.shape == (93, 560)
+    np.testing.assert_array_equal(out[0, :80], mel[0]); np.testing.assert_array_equal(out[0, 240:320], mel[0])
+    np.testing.assert_array_equal(out[1, :80], mel[3]); np.testing.assert_array_equal(out[92, 480:], mel[555])
+    assert np.isfinite(out).all() and out.min() >= np.log(np.float32(1e-5)) - 1e-6
+    # independent f64 check of one frame
+    pcm = synth_pcm(1, 4000).astype(np.float64) * 32768.0
+    fr = pcm[160:560].copy(); fr -= fr.mean(); fr[1:] -= 0.97 * fr[:-1]
+    fr *= 0.5 * (1 - np.cos(2 * np.pi * np.arange(400) / 399))
+    pw = np.abs(np.fft.rfft(fr, 512)) ** 2
+    wts = R.mel_filterbank(16000.0, 512, 80, 20.0).astype(np.float64)
+    ref = np.log(np.maximum(wts @ pw, 1e-5))
+    mel = R.frontend(synth_pcm(1, 4000), want_mel=True)[0]
+    np.testing.assert_allclose(mel[1], ref, rtol=2e-4, atol=2e-4)
