@@ -1,0 +1,141 @@
+// common.cuh -- shared device/host helpers for the lele_b200 CUDA back-end (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <unordered_map>
+
+#include "../../include/lele_b200.h"
+
+// ----------------------------------------------------------------------------
+// context: one per (device, stream).  Mirrors what the Rust shim would hold per model
+// instance (SURVEY 8b "Threading": re-entrant per (device, stream) handle).
+// ----------------------------------------------------------------------------
+struct lele_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    // grow-only scratch (the analogue of lele's thread_local SCRATCH_A/RS/CS, avx/quantization.rs:90-95)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // arena: host Vec base pointer -> device mirror (src/tensor.rs static buffer arena mapped to HBM)
+    struct Mirror { void* dptr; size_t bytes; };
+    std::unordered_map<const void*, Mirror> arena;
+    unsigned long long launches = 0;   // kernels launched through this ctx (bench "gpu_launches")
+    // cached device constants (FFT twiddles per n, Hann window, sparse mel bank ...)
+    std::unordered_map<std::string, void*> tables;
+};
+// returns the cached device copy of a host table, uploading it on first use
+int lb_table(lele_b200_ctx* ctx, const std::string& key, const void* host, size_t bytes, void** out);
+
+void lb_set_error(const char* fmt, ...);
+int lb_scratch(lele_b200_ctx* ctx, size_t bytes, void** out);
+
+#define LB_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            lb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return LELE_B200_ERR_CUDA;                                                       \
+        }                                                                                    \
+    } while (0)
+
+#define LB_REQUIRE(cond, ...)                                                                \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            lb_set_error(__VA_ARGS__);                                                       \
+            return LELE_B200_ERR_ARG;                                                        \
+        }                                                                                    \
+    } while (0)
+
+#define LB_LAUNCH_CHECK(ctx)                                                                 \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            lb_set_error("%s:%d: launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return LELE_B200_ERR_CUDA;                                                       \
+        }                                                                                    \
+    } while (0)
+
+static inline int lb_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ----------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float lb_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float lb_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float lb_warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int lb_warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// order-preserving float <-> uint key, so per-clip min/max can use integer atomics
+__device__ __forceinline__ unsigned lb_fkey(float f) {
+    unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float lb_fkey_inv(unsigned k) {
+    unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+#define LB_KEY_MIN_INIT 0xffffffffu /* identity for atomicMin over keys */
+#define LB_KEY_MAX_INIT 0x00000000u /* identity for atomicMax over keys */
+
+// Polynomial expf used by lele's x86 SIMD bodies (avx/math.rs:11-66): clamp, rint(x*log2e),
+// two-step ln2 reduction, degree-7 FMA Horner, 2^n through the exponent bits.
+__device__ __forceinline__ float lb_cephes_expf(float x) {
+    x = fmaxf(x, -87.33654f);
+    x = fminf(x, 88.72284f);
+    float fx = rintf(__fmul_rn(x, 1.44269504088896341f));
+    x = __fmaf_rn(-fx, 0.693359375f, x);
+    x = __fmaf_rn(-fx, -2.12194440e-4f, x);
+    float y = __fmaf_rn(0.000198712018891638893f, x, 0.00139712726883569741f);
+    y = __fmaf_rn(y, x, 0.00833345670066840443f);
+    y = __fmaf_rn(y, x, 0.0416657844442129135f);
+    y = __fmaf_rn(y, x, 0.166666671633720398f);
+    y = __fmaf_rn(y, x, 0.5f);
+    y = __fmaf_rn(y, x, 1.0f);
+    y = __fmaf_rn(y, x, 1.0f);
+    int e = ((int)fx + 127) << 23;
+    return __fmul_rn(y, __int_as_float(e));
+}
+__device__ __forceinline__ float lb_sigmoid_simd(float x) {  // avx/math.rs:69
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_cephes_expf(-x)));
+}
+__device__ __forceinline__ float lb_tanh_simd(float x) {  // avx/math.rs:81-97
+    float e = lb_cephes_expf(__fmul_rn(-x, 2.0f));
+    float r = fabsf(__fdiv_rn(__fsub_rn(1.0f, e), __fadd_rn(1.0f, e)));
+    return copysignf(r, x);
+}
+__device__ __forceinline__ float lb_erf_simd(float x) {  // avx/math.rs:113-150
+    float ax = fabsf(x);
+    float t = __fdiv_rn(1.0f, __fmaf_rn(0.3275911f, ax, 1.0f));
+    float poly = __fmaf_rn(1.061405429f, t, -1.453152027f);
+    poly = __fmaf_rn(poly, t, 1.421413741f);
+    poly = __fmaf_rn(poly, t, -0.284496736f);
+    poly = __fmaf_rn(poly, t, 0.254829592f);
+    float ev = lb_cephes_expf(-__fmul_rn(ax, ax));
+    float r = __fmaf_rn(-__fmul_rn(poly, t), ev, 1.0f);
+    return __uint_as_float(__float_as_uint(r) | (__float_as_uint(x) & 0x80000000u));
+}
+#endif  // __CUDACC__

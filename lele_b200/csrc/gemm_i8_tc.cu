@@ -1,0 +1,368 @@
+// gemm_i8_tc.cu -- the dominant kernel: exact u8 x u8 -> s32 GEMM on the 5th-gen tensor cores
+// (tcgen05.mma kind::i8, accumulators in TMEM, operands staged by TMA with 128B swizzle) with
+// lele's quantised-linear epilogue fused (zero-point corrections, per-slice activation scale x
+// per-channel weight scale, bias, ReLU, optional residual adds / min-max / argmax).
+//
+// Replaces fused_dq_gemm_avx2 + gemm_2rows_avx2 (src/kernels/avx/quantization.rs:225,1603) --
+// not a port: those are VPMADDUBSW row kernels; this is a persistent warp-specialised
+// TMA -> tcgen05 -> TMEM -> epilogue pipeline.  Integer core is exact (the AVX2 i16 saturation,
+// avx/quantization.rs:1597-1600, is not reproduced: the documented formula :926-936 is the contract):
+//    acc[i,j] = sum_k a[i,k] w[k,j]                      (tcgen05, s32)
+//    int      = acc - w_zp*rowsum[i] - a_zp[i]*colsum[j] + K*a_zp[i]*w_zp
+//    y        = f32(int) * (a_scale[i] * w_scale[j]) + bias[j]   (separate mul / add, :1417-1423)
+//
+// Tiling: CTA tile 128 x 256 x 128B-K, 4 smem stages (48 KB each), 2 TMEM accumulator stages
+// (2 x 256 columns = all 512), 384 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM
+// allocator, warps 4-11 epilogue (TMEM lane quadrant = warp%4, column half = (warp-4)/4).
+// Persistent: grid = #SMs, tiles walked n-fastest so concurrently running CTAs share A rows in L2.
+#include "gemm_i8_tc.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 128;          // BK in bytes == elements (u8)
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK;               // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK;               // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 384;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int UMMA_K = 32;                           // bytes per tcgen05.mma for 8-bit operands
+
+// ---- PTX wrappers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) { printf("lele_b200 gemm_i8_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (SM100 UMMA; cute/arch/mma_sm100_desc.hpp):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D=S32 (c_format 2 @4), A=U8 (0 @7), B=U8 (0 @10), K-major both,
+// N>>3 @17, M>>4 @24
+constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct KernelArgs {
+    int M, N, K;
+    int num_m_blocks, num_n_blocks, num_k_blocks;
+    LbI8Epilogue ep;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const KernelArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024 B alignment
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]       epilogue -> MMA
+    uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {   // whole warp: allocate all 512 TMEM columns (1 CTA/SM by construction)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
+                for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < args.num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);            // TMA bytes landed
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance along K inside the 128B swizzle atom: +32 B == +2 in the (>>4) address field
+                        umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
+                                (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                // frees the smem slot when the MMAs retire
+                    if (kb == args.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (8 warps) =====================
+        const int ew = warp - 4;
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;           // which 128-column half of the tile
+        const LbI8Epilogue& ep = args.ep;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
+            const int row = m_blk * BM + quad * 32 + lane;
+            const bool row_ok = row < args.M;
+            int rs = 0, zpa = 0; float sa = 0.0f;
+            if (row_ok) { rs = __ldg(ep.rowsum + row); zpa = __ldg(ep.row_zp + row); sa = __ldg(ep.row_scale + row); }
+            const int row_corr = args.K * zpa * ep.w_zp - ep.w_zp * rs;
+            float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+            unsigned long long best = 0ull;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int chunk = 0; chunk < 4; ++chunk) {
+                const int col0 = half * 128 + chunk * 32;             // column inside the tile
+                const int gcol0 = n_blk * BN + col0;                  // global column
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), r);
+                if (row_ok && gcol0 < args.N) {
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int4 cs = __ldg(reinterpret_cast<const int4*>(ep.colsum + gcol0) + q);
+                        const float4 ws = __ldg(reinterpret_cast<const float4*>(ep.w_scale + gcol0) + q);
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol0) + q);
+                        const int csv[4] = {cs.x, cs.y, cs.z, cs.w};
+                        const float wsv[4] = {ws.x, ws.y, ws.z, ws.w};
+                        const float biv[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int acci = (int)r[q * 4 + e] + row_corr - zpa * csv[e];
+                            float t = __fmul_rn((float)acci, __fmul_rn(sa, wsv[e]));
+                            if (ep.has_bias) t = __fadd_rn(t, biv[e]);
+                            if (ep.relu) t = fmaxf(t, 0.0f);
+                            v[q * 4 + e] = t;
+                        }
+                    }
+                    const long long obase = (long long)row * args.N + gcol0;
+                    const int ncols = min(32, args.N - gcol0);
+                    if (ep.add1) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (e < ncols) v[e] = __fadd_rn(v[e], __ldg(ep.add1 + obase + e));
+                    }
+                    if (ep.add2) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (e < ncols) v[e] = __fadd_rn(__ldg(ep.add2 + obase + e), v[e]);
+                    }
+                    if (ep.minmax_keys) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (e < ncols) { vmin = fminf(vmin, v[e]); vmax = fmaxf(vmax, v[e]); }
+                    }
+                    if (ep.argmax_keys) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (e < ncols) {
+                            unsigned long long key = ((unsigned long long)lb_fkey(v[e]) << 32) | (unsigned)(gcol0 + e);
+                            best = key > best ? key : best;
+                        }
+                    }
+                    if (ep.out) {
+                        float* o = ep.out + obase;
+                        if (ncols == 32 && ((args.N & 3) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) if (e < ncols) o[e] = v[e];
+                        }
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+            if (ep.minmax_keys) {
+                const int first_row = m_blk * BM + quad * 32;
+                const int last_row = min(first_row + 31, args.M - 1);
+                if (first_row < args.M) {
+                    if (first_row / ep.rows_per_slice == last_row / ep.rows_per_slice) {
+                        vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
+                        if (lane == 0) {
+                            int sl = first_row / ep.rows_per_slice;
+                            atomicMin(ep.minmax_keys + 2 * sl, lb_fkey(vmin));
+                            atomicMax(ep.minmax_keys + 2 * sl + 1, lb_fkey(vmax));
+                        }
+                    } else if (row_ok && vmin <= vmax) {
+                        int sl = row / ep.rows_per_slice;
+                        atomicMin(ep.minmax_keys + 2 * sl, lb_fkey(vmin));
+                        atomicMax(ep.minmax_keys + 2 * sl + 1, lb_fkey(vmax));
+                    }
+                }
+            }
+            if (ep.argmax_keys && row_ok && best != 0ull) atomicMax(ep.argmax_keys + row, best);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// u8 [rows, cols] row-major, box = [box_rows, 128 B], 128B swizzle, OOB -> zero fill
+int make_tmap_u8(CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return LELE_B200_ERR_CUDA; }
+    return LELE_B200_OK;
+}
+
+}  // namespace
+
+int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep) {
+    LB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_i8_tc: empty problem");
+    LB_REQUIRE(K % 16 == 0, "gemm_i8_tc: K=%d must be a multiple of 16 (TMA row pitch)", K);
+    LB_REQUIRE((((uintptr_t)A | (uintptr_t)Wt) & 15) == 0, "gemm_i8_tc: operands must be 16-byte aligned");
+    CUtensorMap ta, tb;
+    int rc = make_tmap_u8(&ta, A, M, K, BM);
+    if (rc) return rc;
+    rc = make_tmap_u8(&tb, Wt, N, K, BN);
+    if (rc) return rc;
+    KernelArgs args;
+    args.M = M; args.N = N; args.K = K;
+    args.num_m_blocks = lb_ceil_div(M, BM);
+    args.num_n_blocks = lb_ceil_div(N, BN);
+    args.num_k_blocks = lb_ceil_div(K, BK);
+    args.ep = ep;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    int tiles = args.num_m_blocks * args.num_n_blocks;
+    int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    gemm_i8_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, args);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}

@@ -1,0 +1,48 @@
+// gemm_i8_tc.cuh -- interface of the tcgen05 (kind::i8) u8 x u8 -> s32 GEMM with the fused
+// lele quantised-linear epilogue.  See gemm_i8_tc.cu.
+#pragma once
+#include "common.cuh"
+
+struct LbI8Epilogue {
+    // per output row (filled by the activation quantiser, quant.cu)
+    const int32_t* rowsum;     // [M] sum_k a_q[row,k]
+    const float* row_scale;    // [M] dynamic scale of the row's slice
+    const int32_t* row_zp;     // [M] activation zero point of the row's slice
+    // per output column (filled once by lele_b200_prepare_weights), padded to a multiple of 256
+    const int32_t* colsum;     // sum_k w[k,col]
+    const float* w_scale;      // per-channel weight scale (scalar scales are expanded)
+    const float* bias;         // zeros when absent
+    int w_zp;
+    int has_bias;
+    int relu;
+    // optional fusions used by the SenseVoice runner (all NULL for the plain operator)
+    const float* add1;         // out = (v + add1)            e.g. + fsmn memory
+    const float* add2;         // out = add2 + (v [+ add1])   e.g. residual stream
+    unsigned* minmax_keys;     // per-slice min/max keys of `out` ([n_slices][2])
+    int rows_per_slice;
+    unsigned long long* argmax_keys;  // [M] max over columns of (fkey(out) << 32 | col)
+    float* out;                // [M, N]; may be NULL when only argmax_keys is wanted
+};
+
+// A: u8 [M, K] row-major (K-major); Wt: u8 [N, K] row-major (K-major).  K % 16 == 0.
+int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K,
+                  const LbI8Epilogue& ep);
+
+// ---- shared between quant.cu and the graph runner (sensevoice.cu) ----
+struct lele_b200_qweights {
+    uint8_t* wt = nullptr;      // [n, k]  K-major copy of the u8 weight (lele's b_t, quantization.rs:206)
+    int32_t* colsum = nullptr;  // [n_pad]
+    float* w_scale = nullptr;   // [n_pad] (scalar scales expanded)
+    float* bias = nullptr;      // [n_pad] zeros when absent
+    int k = 0, n = 0, n_pad = 0, w_zp = 0, has_bias = 0;
+};
+struct LbQuantScratch { uint8_t* a_u8; int32_t* rowsum; float* row_scale; int32_t* row_zp; };
+size_t lb_quant_scratch_bytes(long long M, int K);
+LbQuantScratch lb_quant_scratch_carve(void* base, long long M, int K);
+int lb_minmax_init(lele_b200_ctx* ctx, unsigned* keys, int n_slices);
+int lb_slice_minmax(lele_b200_ctx* ctx, const float* x, int n_slices, long long slice_len, unsigned* keys);
+int lb_quantize_rows(lele_b200_ctx* ctx, const float* x, const unsigned* keys, long long M, int rows_per_slice, int K,
+                     uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp);
+// dispatches to the tcgen05 kernel (K % 16 == 0) or the CUDA-core kernel
+int lb_gemm_i8(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep);
+void lb_fill_weight_fields(LbI8Epilogue& ep, const lele_b200_qweights* w, const LbQuantScratch& s);

@@ -1,0 +1,318 @@
+// indexing.cu -- bit-exact copy / index operators (src/kernels/manipulation.rs, shape.rs,
+// conv2d.rs:1051-1506): strided gather (transpose / slice / expand / split), concat, pad,
+// gather, gather_elements, tile, topk, argmax, resize_nearest, max_pool2d.
+// reshape / flatten / squeeze / unsqueeze stay zero-copy views on the host side (shape.rs).
+#include "common.cuh"
+
+namespace {
+constexpr int MAXR = 8;
+struct StridedArgs { int rank; long long shape[MAXR]; long long stride[MAXR]; long long total; long long offset; };
+int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
+
+__global__ void strided_copy_kernel(const float* __restrict__ in, StridedArgs a, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (long long)gridDim.x * blockDim.x) {
+        long long rem = i, off = a.offset;
+        for (int d = a.rank - 1; d >= 0; --d) { long long c = rem % a.shape[d]; rem /= a.shape[d]; off += c * a.stride[d]; }
+        out[i] = in[off];
+    }
+}
+// 32x32 tiled transpose of the two innermost output dims when the innermost INPUT stride is not 1
+// but some other output dim has input stride 1: covers [0,2,1,3]/[0,2,3,1]/2-D transposes
+// (manipulation.rs:644-1080 fast paths) with coalesced reads and writes.
+__global__ void __launch_bounds__(256)
+transpose_tiled_kernel(const float* __restrict__ in, long long in_off, long long batch_in_stride, long long rows, long long cols,
+                       long long in_row_stride /*stride of out-row index in input*/, long long in_col_stride /*stride of out-col index*/,
+                       float* __restrict__ out) {
+    // here in_row_stride == 1 (input contiguous along the output ROW index)
+    __shared__ float tile[32][33];
+    const long long b = blockIdx.z;
+    const float* src = in + in_off + b * batch_in_stride;
+    float* dst = out + b * rows * cols;
+    const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {   // read: fast index = row (unit stride in input)
+        long long r = r0 + tx, c = c0 + j;
+        if (r < rows && c < cols) tile[j][tx] = src[r * in_row_stride + c * in_col_stride];
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {   // write: fast index = col
+        long long r = r0 + j, c = c0 + tx;
+        if (r < rows && c < cols) dst[r * cols + c] = tile[tx][j];
+    }
+}
+
+struct ConcatArgs { const float* in[16]; long long axis_len[16]; long long axis_off[16]; int n; };
+__global__ void concat_kernel(ConcatArgs a, long long outer, long long inner, long long total_axis, float* __restrict__ out) {
+    const long long total = outer * total_axis * inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long in_i = i % inner, ax = (i / inner) % total_axis, o = i / (inner * total_axis);
+        int s = 0;
+        while (s + 1 < a.n && ax >= a.axis_off[s + 1]) ++s;
+        out[i] = a.in[s][(o * a.axis_len[s] + (ax - a.axis_off[s])) * inner + in_i];
+    }
+}
+
+struct PadArgs { int rank; long long in_shape[MAXR]; long long out_shape[MAXR]; long long begin[MAXR]; long long total; int mode; float value; };
+__global__ void pad_kernel(const float* __restrict__ in, PadArgs a, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (long long)gridDim.x * blockDim.x) {
+        long long rem = i, off = 0, mul = 1;
+        bool inside = true;
+        for (int d = a.rank - 1; d >= 0; --d) {
+            long long c = rem % a.out_shape[d] - a.begin[d]; rem /= a.out_shape[d];
+            long long n = a.in_shape[d];
+            if (c < 0 || c >= n) {
+                if (a.mode == 0) inside = false;
+                else if (a.mode == 1) c = c < 0 ? 0 : n - 1;                       // edge  (manipulation.rs:484)
+                else { if (n == 1) c = 0; else { long long p = 2 * (n - 1); c = ((c % p) + p) % p; if (c >= n) c = p - c; } }  // reflect (:486)
+            }
+            off += c * mul; mul *= n;
+        }
+        out[i] = inside ? in[off] : a.value;
+    }
+}
+
+__global__ void gather_kernel(const float* __restrict__ data, long long outer, int axis_dim, long long inner,
+                              const float* __restrict__ indices, long long n_idx, float* __restrict__ out) {
+    const long long total = outer * n_idx * inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long k = i % inner, q = (i / inner) % n_idx, o = i / (inner * n_idx);
+        long long idx = (long long)indices[q];
+        if (idx < 0) idx += axis_dim;
+        out[i] = data[(o * axis_dim + idx) * inner + k];
+    }
+}
+__global__ void gather_elements_kernel(const float* __restrict__ data, const float* __restrict__ indices, long long outer,
+                                       int axis_dim, int idx_dim, long long inner, float* __restrict__ out) {
+    const long long total = outer * idx_dim * inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long k = i % inner, o = i / (inner * idx_dim);
+        long long idx = (long long)indices[i];
+        if (idx < 0) idx += axis_dim;
+        out[i] = data[(o * axis_dim + idx) * inner + k];
+    }
+}
+struct TileArgs { int rank; long long in_shape[MAXR]; long long out_shape[MAXR]; long long total; };
+__global__ void tile_kernel(const float* __restrict__ in, TileArgs a, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total; i += (long long)gridDim.x * blockDim.x) {
+        long long rem = i, off = 0, mul = 1;
+        for (int d = a.rank - 1; d >= 0; --d) {
+            long long c = (rem % a.out_shape[d]) % a.in_shape[d]; rem /= a.out_shape[d];
+            off += c * mul; mul *= a.in_shape[d];
+        }
+        out[i] = in[off];
+    }
+}
+
+// top-k of each row: one warp per row, k rounds of (max value, lowest index) selection.
+// Stable sort_by(partial_cmp) descending => ties keep the lower index first (conv2d.rs:1385-1437).
+__global__ void __launch_bounds__(256)
+topk_kernel(const float* __restrict__ x, long long outer, int n, int k, float* __restrict__ values, float* __restrict__ indices) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= outer) return;
+    const float* xr = x + row * n;
+    float last_v = INFINITY; int last_i = -1;
+    for (int t = 0; t < k; ++t) {
+        // candidate ordering: (value desc, index asc); must come strictly after (last_v, last_i)
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int j = lane; j < n; j += 32) {
+            float v = xr[j];
+            bool after = (v < last_v) || (v == last_v && j > last_i);
+            if (after && (v > bv || (v == bv && j < bi))) { bv = v; bi = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { values[row * k + t] = bv; indices[row * k + t] = (float)bi; }
+        last_v = bv; last_i = bi;
+    }
+}
+// argmax with LAST-max tie rule (Iterator::max_by)
+__global__ void __launch_bounds__(256)
+argmax_last_kernel(const float* __restrict__ x, long long outer, int n, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= outer) return;
+    const float* xr = x + row * n;
+    unsigned long long best = 0ull;
+    for (int j = lane; j < n; j += 32) {
+        unsigned long long key = ((unsigned long long)lb_fkey(xr[j]) << 32) | (unsigned)j;
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o); best = ok > best ? ok : best; }
+    if (lane == 0) out[row] = (int32_t)(best & 0xffffffffu);
+}
+__global__ void argmax_keys_to_ids_kernel(const unsigned long long* __restrict__ keys, long long n, int32_t* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)(keys[i] & 0xffffffffu);
+}
+
+__global__ void resize_nearest_kernel(const float* __restrict__ x, long long nc, int h, int w, int oh, int ow, int mode,
+                                      float* __restrict__ out) {
+    const float hs = __fdiv_rn((float)h, (float)oh), ws = __fdiv_rn((float)w, (float)ow);
+    const long long total = nc * oh * ow;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ox = (int)(i % ow), oy = (int)((i / ow) % oh); long long c = i / ((long long)ow * oh);
+        int iy, ix;
+        if (mode == 0) {
+            iy = (int)fminf(floorf(__fmul_rn((float)oy, hs)), (float)(h - 1));
+            ix = (int)fminf(floorf(__fmul_rn((float)ox, ws)), (float)(w - 1));
+        } else {
+            iy = (int)fminf(fmaxf(roundf(__fsub_rn(__fmul_rn(__fadd_rn((float)oy, 0.5f), hs), 0.5f)), 0.0f), (float)(h - 1));
+            ix = (int)fminf(fmaxf(roundf(__fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), ws), 0.5f)), 0.0f), (float)(w - 1));
+        }
+        out[i] = x[(c * h + iy) * w + ix];
+    }
+}
+struct PoolArgs { int h, w, oh, ow, kh, kw, pt, pl, sh, sw, dh, dw; };
+__global__ void max_pool2d_kernel(const float* __restrict__ x, long long nc, PoolArgs a, float* __restrict__ out) {
+    const long long total = nc * a.oh * a.ow;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ox = (int)(i % a.ow), oy = (int)((i / a.ow) % a.oh); long long c = i / ((long long)a.ow * a.oh);
+        float m = -INFINITY;
+        for (int ky = 0; ky < a.kh; ++ky) {
+            int iy = oy * a.sh + ky * a.dh - a.pt;
+            if (iy < 0 || iy >= a.h) continue;
+            for (int kx = 0; kx < a.kw; ++kx) {
+                int ix = ox * a.sw + kx * a.dw - a.pl;
+                if (ix < 0 || ix >= a.w) continue;
+                m = fmaxf(m, x[(c * a.h + iy) * a.w + ix]);
+            }
+        }
+        out[i] = m;
+    }
+}
+}  // namespace
+
+int lb_argmax_keys_to_ids(lele_b200_ctx* ctx, const unsigned long long* keys, long long n, int32_t* out) {
+    argmax_keys_to_ids_kernel<<<lb_ceil_div(n, 256), 256, 0, ctx->stream>>>(keys, n, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_strided_copy(lele_b200_ctx* ctx, const float* in, long long in_offset, const long long* out_shape,
+                                      const long long* in_strides, int rank, float* out) {
+    LB_REQUIRE(ctx && in && out && rank >= 0 && rank <= MAXR, "strided_copy: bad arguments");
+    StridedArgs a; a.rank = rank; a.total = 1; a.offset = in_offset;
+    for (int i = 0; i < rank; ++i) { a.shape[i] = out_shape[i]; a.stride[i] = in_strides[i]; a.total *= out_shape[i]; }
+    if (a.total == 0) return LELE_B200_OK;
+    // tiled path: innermost two output dims (rows, cols) where the input is contiguous along rows
+    if (rank >= 2 && in_strides[rank - 2] == 1 && in_strides[rank - 1] != 1 && out_shape[rank - 1] >= 8 && out_shape[rank - 2] >= 8) {
+        long long batch = 1; bool regular = true; long long bstride = 0;
+        // leading dims must collapse to a single batch stride
+        if (rank > 2) {
+            for (int i = 0; i < rank - 2; ++i) batch *= out_shape[i];
+            bstride = in_strides[rank - 3];
+            long long expect = bstride;
+            for (int i = rank - 3; i >= 0; --i) { if (out_shape[i] != 1 && in_strides[i] != expect) regular = false; expect *= out_shape[i]; }
+        }
+        if (regular && batch <= 65535 && lb_ceil_div(out_shape[rank - 2], 32) <= 65535) {
+            dim3 grid(lb_ceil_div(out_shape[rank - 1], 32), lb_ceil_div(out_shape[rank - 2], 32), (unsigned)batch);
+            transpose_tiled_kernel<<<grid, 256, 0, ctx->stream>>>(in, in_offset, bstride, out_shape[rank - 2], out_shape[rank - 1], 1,
+                                                                 in_strides[rank - 1], out);
+            LB_LAUNCH_CHECK(ctx);
+            return LELE_B200_OK;
+        }
+    }
+    strided_copy_kernel<<<grid_for(a.total), 256, 0, ctx->stream>>>(in, a, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_concat(lele_b200_ctx* ctx, const float* const* inputs, const long long* axis_lens, int n_inputs,
+                                long long outer, long long inner, float* out) {
+    LB_REQUIRE(ctx && inputs && axis_lens && out, "concat: NULL argument");
+    LB_REQUIRE(n_inputs >= 1 && n_inputs <= 16, "concat: %d inputs (supported: 1..16 per call)", n_inputs);
+    ConcatArgs a; a.n = 0; long long off = 0;
+    for (int i = 0; i < n_inputs; ++i) {
+        if (axis_lens[i] == 0) continue;   // empty inputs skipped (manipulation.rs:120)
+        a.in[a.n] = inputs[i]; a.axis_len[a.n] = axis_lens[i]; a.axis_off[a.n] = off; off += axis_lens[i]; ++a.n;
+    }
+    if (a.n == 0 || outer * off * inner == 0) return LELE_B200_OK;
+    concat_kernel<<<grid_for(outer * off * inner), 256, 0, ctx->stream>>>(a, outer, inner, off, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_pad(lele_b200_ctx* ctx, const float* in, const long long* shape, int rank, const long long* pads, int mode,
+                             float value, float* out) {
+    LB_REQUIRE(ctx && in && out && rank >= 1 && rank <= MAXR && mode >= 0 && mode <= 2, "pad: bad arguments");
+    PadArgs a; a.rank = rank; a.total = 1; a.mode = mode; a.value = value;
+    for (int i = 0; i < rank; ++i) {
+        long long b = pads[i] < 0 ? 0 : pads[i], e = pads[i + rank] < 0 ? 0 : pads[i + rank];   // negatives clamp to 0 (manipulation.rs:390)
+        a.in_shape[i] = shape[i]; a.begin[i] = b; a.out_shape[i] = shape[i] + b + e; a.total *= a.out_shape[i];
+    }
+    if (a.total == 0) return LELE_B200_OK;
+    pad_kernel<<<grid_for(a.total), 256, 0, ctx->stream>>>(in, a, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_gather(lele_b200_ctx* ctx, const float* data, long long outer, int axis_dim, long long inner,
+                                const float* indices, long long n_indices, float* out) {
+    LB_REQUIRE(ctx && data && indices && out, "gather: NULL argument");
+    if (outer * n_indices * inner == 0) return LELE_B200_OK;
+    gather_kernel<<<grid_for(outer * n_indices * inner), 256, 0, ctx->stream>>>(data, outer, axis_dim, inner, indices, n_indices, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_gather_elements(lele_b200_ctx* ctx, const float* data, const float* indices, long long outer, int axis_dim,
+                                         int idx_dim, long long inner, float* out) {
+    LB_REQUIRE(ctx && data && indices && out, "gather_elements: NULL argument");
+    if (outer * idx_dim * inner == 0) return LELE_B200_OK;
+    gather_elements_kernel<<<grid_for(outer * idx_dim * inner), 256, 0, ctx->stream>>>(data, indices, outer, axis_dim, idx_dim, inner, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_tile(lele_b200_ctx* ctx, const float* in, const long long* shape, const long long* repeats, int rank,
+                              float* out) {
+    LB_REQUIRE(ctx && in && out && rank >= 1 && rank <= MAXR, "tile: bad arguments");
+    TileArgs a; a.rank = rank; a.total = 1;
+    for (int i = 0; i < rank; ++i) { a.in_shape[i] = shape[i]; a.out_shape[i] = shape[i] * repeats[i]; a.total *= a.out_shape[i]; }
+    if (a.total == 0) return LELE_B200_OK;
+    tile_kernel<<<grid_for(a.total), 256, 0, ctx->stream>>>(in, a, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_topk(lele_b200_ctx* ctx, const float* x, long long outer, int n, int k, float* values, float* indices) {
+    LB_REQUIRE(ctx && x && values && indices && n > 0, "topk: bad arguments");
+    LB_REQUIRE(k >= 0 && k <= n, "topk: k=%d must be in [0, n=%d] (caller applies k=min(k,last), conv2d.rs:1396)", k, n);
+    if (outer == 0 || k == 0) return LELE_B200_OK;
+    topk_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, outer, n, k, values, indices);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_argmax_last(lele_b200_ctx* ctx, const float* x, long long outer, int n, int32_t* out) {
+    LB_REQUIRE(ctx && x && out && n > 0, "argmax_last: bad arguments");
+    if (outer == 0) return LELE_B200_OK;
+    argmax_last_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, outer, n, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_resize_nearest(lele_b200_ctx* ctx, const float* x, int nb, int c, int h, int w, int oh, int ow, int mode,
+                                        float* out) {
+    LB_REQUIRE(ctx && x && out, "resize_nearest: NULL argument");
+    LB_REQUIRE(oh > 0 && ow > 0, "Resize: output dimensions must be positive, got out_h=%d out_w=%d (conv2d.rs:1321)", oh, ow);
+    long long total = (long long)nb * c * oh * ow;
+    if (total == 0) return LELE_B200_OK;
+    resize_nearest_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(x, (long long)nb * c, h, w, oh, ow, mode, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_max_pool2d(lele_b200_ctx* ctx, const float* x, int nb, int c, int h, int w, int kh, int kw, const int* pads,
+                                    const int* strides, const int* dils, int ceil_mode, float* out) {
+    LB_REQUIRE(ctx && x && out && pads && strides && dils, "max_pool2d: NULL argument");
+    PoolArgs a;
+    a.h = h; a.w = w; a.kh = kh; a.kw = kw; a.pt = pads[0]; a.pl = pads[1]; a.sh = strides[0]; a.sw = strides[1]; a.dh = dils[0]; a.dw = dils[1];
+    int nh = h + pads[0] + pads[2] - a.dh * (kh - 1) - 1, nw = w + pads[1] + pads[3] - a.dw * (kw - 1) - 1;
+    a.oh = (ceil_mode ? (nh + a.sh - 1) / a.sh : nh / a.sh) + 1;
+    a.ow = (ceil_mode ? (nw + a.sw - 1) / a.sw : nw / a.sw) + 1;
+    long long total = (long long)nb * c * a.oh * a.ow;
+    if (total <= 0) return LELE_B200_OK;
+    max_pool2d_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(x, (long long)nb * c, a, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}

@@ -1,0 +1,181 @@
+// norm.cu -- LayerNorm / Softmax / BatchNorm / RMSNorm (src/kernels/norm.rs + avx/norm.rs).
+// HBM-bound row kernels: one warp per row, 128-bit loads, warp-shuffle reductions.
+#include "common.cuh"
+
+// LayerNorm: mean = sum*(1/n); var = sumsq*(1/n) - mean^2 (not clamped); inv = 1/sqrt(var+eps);
+// y = fma((x-mean)*inv, gamma, beta) on the x86 SIMD body (first n/8*8 columns), plain
+// mul+add on the scalar tail (avx/norm.rs:84-133).  Optional fused per-slice min/max of the
+// output (keys, see common.cuh) feeds the dynamic quantiser of the next int8 linear.
+template <int kMaxVec>  // row cached in registers when n <= kMaxVec*128 and n % 4 == 0
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  long long outer, int n, float eps, float* __restrict__ out,
+                  unsigned* __restrict__ minmax_keys /*[n_slices][2] or NULL*/, int rows_per_slice) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= outer) return;
+    const float* xr = x + row * n;
+    float* o = out + row * n;
+    const float inv_n = __fdiv_rn(1.0f, (float)n);
+    const int simd_end = (n / 8) * 8;
+    float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+    const bool vec = kMaxVec > 0 && (n % 4 == 0) && n <= kMaxVec * 128 &&
+                     ((((uintptr_t)xr | (uintptr_t)o | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0);
+    if (vec) {
+        float4 v[kMaxVec > 0 ? kMaxVec : 1];
+        const int nv = n >> 2;
+        float s = 0.0f, sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i) {
+            int c = lane + 32 * i;
+            if (c < nv) {
+                v[i] = __ldg(reinterpret_cast<const float4*>(xr) + c);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                sq = fmaf(v[i].x, v[i].x, sq); sq = fmaf(v[i].y, v[i].y, sq);
+                sq = fmaf(v[i].z, v[i].z, sq); sq = fmaf(v[i].w, v[i].w, sq);
+            }
+        }
+        s = lb_warp_sum(s); sq = lb_warp_sum(sq);
+        const float mean = __fmul_rn(s, inv_n);
+        const float var = __fsub_rn(__fmul_rn(sq, inv_n), __fmul_rn(mean, mean));
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+#pragma unroll
+        for (int i = 0; i < kMaxVec; ++i) {
+            int c = lane + 32 * i;
+            if (c < nv) {
+                float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+                float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+                float in[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w}, r[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float sc = __fmul_rn(__fsub_rn(in[q], mean), inv);
+                    r[q] = (4 * c + q) < simd_end ? __fmaf_rn(sc, gg[q], bb[q]) : __fadd_rn(__fmul_rn(sc, gg[q]), bb[q]);
+                    vmin = fminf(vmin, r[q]); vmax = fmaxf(vmax, r[q]);
+                }
+                reinterpret_cast<float4*>(o)[c] = make_float4(r[0], r[1], r[2], r[3]);
+            }
+        }
+    } else {
+        float s = 0.0f, sq = 0.0f;
+        for (int j = lane; j < n; j += 32) { float t = xr[j]; s += t; sq = fmaf(t, t, sq); }
+        s = lb_warp_sum(s); sq = lb_warp_sum(sq);
+        const float mean = __fmul_rn(s, inv_n);
+        const float var = __fsub_rn(__fmul_rn(sq, inv_n), __fmul_rn(mean, mean));
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+        for (int j = lane; j < n; j += 32) {
+            float g = gamma ? gamma[j] : 1.0f, b = beta ? beta[j] : 0.0f;
+            float sc = __fmul_rn(__fsub_rn(xr[j], mean), inv);
+            float r = j < simd_end ? __fmaf_rn(sc, g, b) : __fadd_rn(__fmul_rn(sc, g), b);
+            vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
+            o[j] = r;
+        }
+    }
+    if (minmax_keys) {
+        vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
+        if (lane == 0) {
+            long long slice = row / rows_per_slice;
+            atomicMin(minmax_keys + 2 * slice, lb_fkey(vmin));
+            atomicMax(minmax_keys + 2 * slice + 1, lb_fkey(vmax));
+        }
+    }
+}
+
+int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer,
+                         int n, float eps, float* out, unsigned* minmax_keys, int rows_per_slice) {
+    if (outer == 0) return LELE_B200_OK;
+    const int warps = 8;
+    int grid = lb_ceil_div(outer, warps);
+    if (gamma && beta && n % 4 == 0 && n <= 8 * 128)
+        layer_norm_kernel<8><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
+    else
+        layer_norm_kernel<0><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_layer_norm(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta,
+                                    long long outer, int n, float eps, float* out) {
+    LB_REQUIRE(ctx && x && out && n > 0 && outer >= 0, "layer_norm: bad arguments");
+    return lb_layer_norm_minmax(ctx, x, gamma, beta, outer, n, eps, out, nullptr, 1);
+}
+
+// Softmax over the last axis (norm.rs:8-224 inner_size==1 -> avx/norm.rs:139-229):
+// max, exp(x-max) with the polynomial exp on the SIMD body / libm expf on the n%8 tail,
+// multiply by 1/sum.
+__global__ void __launch_bounds__(256)
+softmax_kernel(const float* __restrict__ x, long long outer, int n, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= outer) return;
+    const float* xr = x + row * n;
+    float* o = out + row * n;
+    const int simd_end = (n / 8) * 8;
+    float mx = -3.402823466e+38f;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, xr[j]);
+    mx = lb_warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < n; j += 32) {
+        float d = __fsub_rn(xr[j], mx);
+        float e = j < simd_end ? lb_cephes_expf(d) : expf(d);
+        o[j] = e;
+        sum += e;
+    }
+    sum = lb_warp_sum(sum);
+    const float inv = __fdiv_rn(1.0f, sum);
+    for (int j = lane; j < n; j += 32) o[j] = __fmul_rn(o[j], inv);
+}
+
+extern "C" int lele_b200_softmax(lele_b200_ctx* ctx, const float* x, long long outer, int n, float* out) {
+    LB_REQUIRE(ctx && x && out && n > 0 && outer >= 0, "softmax: bad arguments");
+    if (outer == 0) return LELE_B200_OK;
+    softmax_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, outer, n, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+// BatchNorm (norm.rs:313-419): y = x*s + (bias - mean*s), s = scale / sqrt(var+eps)
+__global__ void batch_norm_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ bias,
+                                  const float* __restrict__ mean, const float* __restrict__ var, int c, long long inner,
+                                  float eps, long long total, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ch = (int)((i / inner) % c);
+        float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[ch], eps)));
+        float s = __fmul_rn(scale[ch], inv);
+        float sh = __fsub_rn(bias[ch], __fmul_rn(mean[ch], s));
+        out[i] = __fadd_rn(__fmul_rn(x[i], s), sh);
+    }
+}
+extern "C" int lele_b200_batch_norm(lele_b200_ctx* ctx, const float* x, const float* scale, const float* bias,
+                                    const float* mean, const float* var, int nb, int c, long long inner, float eps,
+                                    float* out) {
+    LB_REQUIRE(ctx && x && scale && bias && mean && var && out, "batch_norm: NULL argument");
+    long long total = (long long)nb * c * inner;
+    if (total == 0) return LELE_B200_OK;
+    batch_norm_kernel<<<min(lb_ceil_div(total, 256), 148 * 16), 256, 0, ctx->stream>>>(x, scale, bias, mean, var, c, inner, eps, total, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+// RMSNorm (norm.rs:420-506): x * w / sqrt(mean(x^2) + eps)
+__global__ void __launch_bounds__(256)
+rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, long long outer, int n, float eps,
+                float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= outer) return;
+    const float* xr = x + row * n;
+    float sq = 0.0f;
+    for (int j = lane; j < n; j += 32) sq = fmaf(xr[j], xr[j], sq);
+    sq = lb_warp_sum(sq);
+    float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(sq, (float)n), eps)));
+    for (int j = lane; j < n; j += 32) out[row * n + j] = __fmul_rn(__fmul_rn(xr[j], inv), w ? w[j] : 1.0f);
+}
+extern "C" int lele_b200_rms_norm(lele_b200_ctx* ctx, const float* x, const float* w, long long outer, int n, float eps,
+                                  float* out) {
+    LB_REQUIRE(ctx && x && out && n > 0, "rms_norm: bad arguments");
+    if (outer == 0) return LELE_B200_OK;
+    rms_norm_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, w, outer, n, eps, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}

@@ -1,0 +1,408 @@
+// sensevoice.cu -- the graph runner for the SenseVoiceSmall-shaped network: the batched replay
+// of what a lele_gen-compiled model.rs does per clip (examples/sensevoice/src/main.rs:73-140;
+// layer composition src/bin/wasm_bench.rs:888-1113), with the weights blob resident in HBM
+// (src/compiler/mod.rs:1082 keeps a borrowed &[u8]; here blob_dev) and the workspace arena
+// (src/compiler/mod.rs:1057-1070) pre-sized for max_clips.
+//
+// The batch lives below the operator boundary: B clips are stacked along the row (M) dimension
+// of every GEMM, while everything the reference computes "per tensor" stays per clip
+// (dynamic-quantisation min/max/scale/zero-point, CMVN) -- SURVEY.md 7.2.
+//
+// Host-side C++ (the analogue of the generated straight-line run_chunk_k body); all math is in
+// the CUDA kernels of this directory.
+#include "gemm_i8_tc.cuh"
+#include <math.h>
+
+// ---- internal entry points from the other translation units ----
+int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n,
+                         float eps, float* out, unsigned* minmax_keys, int rows_per_slice);
+int lb_sgemm_strided_ldc(lele_b200_ctx* ctx, const float* A, long long rsa, long long csa, long long bsa, const float* B,
+                         long long rsb, long long csb, long long bsb, float* C, long long bsc, long long ldc, int batch, int m,
+                         int k, int n, float alpha);
+int lb_argmax_keys_to_ids(lele_b200_ctx* ctx, const unsigned long long* keys, long long n, int32_t* out);
+
+namespace {
+enum { SV_G_EMBED = 0, SV_G_POS, SV_G_AFTER_G, SV_G_AFTER_B, SV_G_TP_G, SV_G_TP_B, SV_G_CTC_W, SV_G_CTC_SCALE, SV_G_CTC_BIAS,
+       SV_G_CTC_ZP, SV_NUM_GLOBAL };
+enum { SV_L_LN1_G = 0, SV_L_LN1_B, SV_L_QKV_W, SV_L_QKV_SCALE, SV_L_QKV_BIAS, SV_L_QKV_ZP, SV_L_FSMN_W, SV_L_OUT_W, SV_L_OUT_SCALE,
+       SV_L_OUT_BIAS, SV_L_OUT_ZP, SV_L_LN2_G, SV_L_LN2_B, SV_L_FFN1_W, SV_L_FFN1_SCALE, SV_L_FFN1_BIAS, SV_L_FFN1_ZP, SV_L_FFN2_W,
+       SV_L_FFN2_SCALE, SV_L_FFN2_BIAS, SV_L_FFN2_ZP, SV_NUM_LAYER };
+
+enum ProfClass { P_FRONTEND = 0, P_CMVN, P_PREP, P_LAYERNORM, P_QUANTIZE, P_GEMM_I8, P_FSMN, P_ATTN_QK, P_SOFTMAX, P_ATTN_PV,
+                 P_MINMAX, P_ARGMAX, P_MISC, P_NUM };
+const char* kProfNames[P_NUM] = {"frontend_fbank_lfr", "cmvn", "prompt_scale_pos", "layer_norm", "quantize_rows", "gemm_i8_tcgen05",
+                                 "fsmn_dwconv", "attn_qk_sgemm", "softmax", "attn_pv_sgemm", "slice_minmax", "argmax", "misc"};
+
+// x0[b, r, :] = (r < 4 ? embed[id_r] : feats[b, r-4]) * sqrt(d) + pos[r]
+__global__ void prompt_scale_pos_kernel(const float* __restrict__ feats, const float* __restrict__ embed, const float* __restrict__ pos,
+                                        int4 ids, int n_clips, int t, int din, float sq, float* __restrict__ x0) {
+    const int T = t + 4;
+    const long long total = (long long)n_clips * T * din;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % din), r = (int)((i / din) % T), b = (int)(i / ((long long)din * T));
+        float v;
+        if (r < 4) { int id = r == 0 ? ids.x : (r == 1 ? ids.y : (r == 2 ? ids.z : ids.w)); v = embed[(long long)id * din + c]; }
+        else v = feats[((long long)b * t + (r - 4)) * din + c];
+        x0[i] = __fadd_rn(__fmul_rn(v, sq), pos[(long long)r * din + c]);
+    }
+}
+
+// FSMN memory block: depthwise conv1d over time (k taps, zero pad, no bias) on V + V.
+// v lives inside qkv [M, 3d] at column offset 2d.  Same tap order / unfused mul+add as the
+// reference conv1d then `add`.
+__global__ void __launch_bounds__(256)
+fsmn_kernel(const float* __restrict__ qkv, const float* __restrict__ w /*[d,1,k]*/, int n_clips, int T, int d, int k,
+            float* __restrict__ out /*[M,d]*/) {
+    const int pad = (k - 1) / 2;
+    const long long total = (long long)n_clips * T * d;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % d), tt = (int)((i / d) % T), b = (int)(i / ((long long)d * T));
+        const float* vb = qkv + ((long long)b * T) * 3 * d + 2 * d + c;
+        float s = 0.0f;
+        for (int kk = 0; kk < k; ++kk) {
+            int pos = tt + kk - pad;
+            if (pos >= 0 && pos < T) s = __fadd_rn(s, __fmul_rn(__ldg(w + (long long)c * k + kk), vb[(long long)pos * 3 * d]));
+        }
+        out[i] = __fadd_rn(s, vb[(long long)tt * 3 * d]);
+    }
+}
+
+__global__ void scale_copy_q_kernel(const float* __restrict__ qkv, long long M, int d, float qscale, float* __restrict__ q) {
+    const long long total = M * d;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / d; int c = (int)(i % d);
+        q[i] = __fmul_rn(qkv[r * 3 * d + c], qscale);
+    }
+}
+
+// softmax over score rows (same arithmetic as norm.cu softmax_kernel), in place
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ s, long long rows, int n) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* xr = s + row * n;
+    const int simd_end = (n / 8) * 8;
+    float mx = -3.402823466e+38f;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, xr[j]);
+    mx = lb_warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < n; j += 32) {
+        float dlt = __fsub_rn(xr[j], mx);
+        float e = j < simd_end ? lb_cephes_expf(dlt) : expf(dlt);
+        xr[j] = e; sum += e;
+    }
+    sum = lb_warp_sum(sum);
+    const float inv = __fdiv_rn(1.0f, sum);
+    for (int j = lane; j < n; j += 32) xr[j] = __fmul_rn(xr[j], inv);
+}
+
+__global__ void init_u64_kernel(unsigned long long* p, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0ull;
+}
+int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
+}  // namespace
+
+struct lele_b200_sensevoice {
+    int n_layers, d, d_in, ffn, heads, fsmn_k, vocab, n_embed, max_t, n_stage1, n_tensors;
+    const uint8_t* blob = nullptr;
+    std::vector<unsigned long long> table;       // (offset, nbytes) pairs
+    std::vector<lele_b200_qweights*> lin;         // 4 per layer + ctc
+    int max_clips = 0, max_samples = 0, max_T = 0;
+    // workspace arena
+    float *lfr = nullptr, *feats = nullptr, *x0 = nullptr, *x = nullptr, *h = nullptr, *qkv = nullptr, *qs = nullptr, *fsmn = nullptr,
+          *att = nullptr, *f1 = nullptr, *scores = nullptr, *pcm_stage = nullptr;
+    int32_t* ids_stage = nullptr;
+    unsigned* keys = nullptr;
+    unsigned long long* amax_keys = nullptr;
+    void* qscratch = nullptr;
+    // profiling
+    int profiling = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    float prof_ms[P_NUM] = {0};
+    int prof_calls[P_NUM] = {0};
+
+    const void* tensor(int idx) const { return blob + table[2 * idx]; }
+    const void* lt(int layer, int which) const { return tensor(SV_NUM_GLOBAL + layer * SV_NUM_LAYER + which); }
+};
+
+namespace {
+struct ProfScope {
+    lele_b200_sensevoice* m; lele_b200_ctx* ctx; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(lele_b200_sensevoice* m_, lele_b200_ctx* c_, int cls_) : m(m_), ctx(c_), cls(cls_) {
+        if (!m->profiling) return;
+        auto next = [&]() { if (m->ev_used == m->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); m->ev_pool.push_back(e); } return m->ev_pool[m->ev_used++]; };
+        a = next(); b = next();
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~ProfScope() { if (m->profiling) { cudaEventRecord(b, ctx->stream); m->spans.push_back({cls, a, b}); } }
+};
+#define SV_RUN(cls, expr) do { ProfScope _ps(m, ctx, cls); int _rc = (expr); if (_rc) return _rc; } while (0)
+
+#define SV_LINEAR(...) do { int _rc = sv_linear(__VA_ARGS__); if (_rc) return _rc; } while (0)
+
+// quantise the activation rows (per-clip keys already hold min/max) then the tcgen05 GEMM;
+// profiled as two classes so the GEMM's own duration feeds the roofline.
+int sv_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const unsigned* keys, long long M, int T,
+              const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep) {
+    SV_RUN(P_QUANTIZE, lb_quantize_rows(ctx, x, keys, M, T, w->k, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp));
+    lb_fill_weight_fields(ep, w, qs);
+    SV_RUN(P_GEMM_I8, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+    return LELE_B200_OK;
+}
+
+int sv_alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) { lb_set_error("sensevoice: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return LELE_B200_ERR_CUDA; }
+    return LELE_B200_OK;
+}
+}  // namespace
+
+extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* blob_dev, size_t nbytes, const uint8_t* hdr_host,
+                                           size_t header_bytes, int max_clips, int max_samples, lele_b200_sensevoice** out) {
+    LB_REQUIRE(ctx && blob_dev && hdr_host && out, "sensevoice_create: NULL argument");
+    LB_REQUIRE(header_bytes >= 256, "sensevoice_create: header too short");
+    const int32_t* hd = (const int32_t*)hdr_host;
+    LB_REQUIRE(hd[0] == 0x454C454C && hd[1] == 1, "sensevoice_create: bad blob magic/version");
+    lele_b200_sensevoice* m = new lele_b200_sensevoice();
+    m->n_layers = hd[2]; m->d = hd[3]; m->d_in = hd[4]; m->ffn = hd[5]; m->heads = hd[6]; m->fsmn_k = hd[7]; m->vocab = hd[8];
+    m->n_embed = hd[9]; m->max_t = hd[10]; m->n_stage1 = hd[11]; m->n_tensors = hd[12];
+    LB_REQUIRE(header_bytes >= 256 + 16 * (size_t)m->n_tensors, "sensevoice_create: header does not contain the tensor table");
+    LB_REQUIRE(m->n_tensors == SV_NUM_GLOBAL + m->n_layers * SV_NUM_LAYER, "sensevoice_create: tensor count mismatch");
+    LB_REQUIRE(m->d % m->heads == 0 && m->d % 4 == 0 && m->d_in % 4 == 0, "sensevoice_create: unsupported dims");
+    m->blob = blob_dev;
+    m->table.resize(2 * (size_t)m->n_tensors);
+    memcpy(m->table.data(), hdr_host + 256, 16 * (size_t)m->n_tensors);
+    for (int i = 0; i < m->n_tensors; ++i)
+        LB_REQUIRE(m->table[2 * i] + m->table[2 * i + 1] <= nbytes, "sensevoice_create: tensor %d out of blob bounds", i);
+    m->max_clips = max_clips; m->max_samples = max_samples;
+    int frames = lele_b200_frontend_num_frames(max_samples);
+    int t = (frames + 5) / 6;
+    m->max_T = t + 4;
+    LB_REQUIRE(m->max_T <= m->max_t, "sensevoice_create: %d rows exceed the positional table (%d)", m->max_T, m->max_t);
+
+    // one-time weight preparation (the analogue of B_WEIGHT_CACHE / prepare_weights)
+    auto prep = [&](const void* w, int k, int n, const void* sc, const void* zp_dev, const void* bias, lele_b200_qweights** q) -> int {
+        uint8_t zp_h = 0;
+        cudaError_t e = cudaMemcpyAsync(&zp_h, zp_dev, 1, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { lb_set_error("sensevoice_create: reading zero point: %s", cudaGetErrorString(e)); return LELE_B200_ERR_CUDA; }
+        return lele_b200_prepare_weights(ctx, (const uint8_t*)w, k, n, (const float*)sc, n, zp_h, (const float*)bias, q);
+    };
+    m->lin.assign((size_t)m->n_layers * 4 + 1, nullptr);
+    int rc = 0;
+    for (int l = 0; l < m->n_layers && !rc; ++l) {
+        int cur = l == 0 ? m->d_in : m->d;
+        rc = prep(m->lt(l, SV_L_QKV_W), cur, 3 * m->d, m->lt(l, SV_L_QKV_SCALE), m->lt(l, SV_L_QKV_ZP), m->lt(l, SV_L_QKV_BIAS), &m->lin[l * 4 + 0]);
+        if (!rc) rc = prep(m->lt(l, SV_L_OUT_W), m->d, m->d, m->lt(l, SV_L_OUT_SCALE), m->lt(l, SV_L_OUT_ZP), m->lt(l, SV_L_OUT_BIAS), &m->lin[l * 4 + 1]);
+        if (!rc) rc = prep(m->lt(l, SV_L_FFN1_W), m->d, m->ffn, m->lt(l, SV_L_FFN1_SCALE), m->lt(l, SV_L_FFN1_ZP), m->lt(l, SV_L_FFN1_BIAS), &m->lin[l * 4 + 2]);
+        if (!rc) rc = prep(m->lt(l, SV_L_FFN2_W), m->ffn, m->d, m->lt(l, SV_L_FFN2_SCALE), m->lt(l, SV_L_FFN2_ZP), m->lt(l, SV_L_FFN2_BIAS), &m->lin[l * 4 + 3]);
+    }
+    if (!rc) rc = prep(m->tensor(SV_G_CTC_W), m->d, m->vocab, m->tensor(SV_G_CTC_SCALE), m->tensor(SV_G_CTC_ZP), m->tensor(SV_G_CTC_BIAS), &m->lin[(size_t)m->n_layers * 4]);
+    if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
+
+    const size_t B = max_clips, M = B * m->max_T;
+    const int wide = m->d_in > m->d ? m->d_in : m->d;
+    const int kmax = m->ffn > wide ? m->ffn : wide;
+    rc = sv_alloc((void**)&m->lfr, sizeof(float) * B * t * m->d_in);
+    if (!rc) rc = sv_alloc((void**)&m->feats, sizeof(float) * B * t * m->d_in);
+    if (!rc) rc = sv_alloc((void**)&m->x0, sizeof(float) * M * m->d_in);
+    if (!rc) rc = sv_alloc((void**)&m->x, sizeof(float) * M * m->d);
+    if (!rc) rc = sv_alloc((void**)&m->h, sizeof(float) * M * wide);
+    if (!rc) rc = sv_alloc((void**)&m->qkv, sizeof(float) * M * 3 * m->d);
+    if (!rc) rc = sv_alloc((void**)&m->qs, sizeof(float) * M * m->d);
+    if (!rc) rc = sv_alloc((void**)&m->fsmn, sizeof(float) * M * m->d);
+    if (!rc) rc = sv_alloc((void**)&m->att, sizeof(float) * M * m->d);
+    if (!rc) rc = sv_alloc((void**)&m->f1, sizeof(float) * M * m->ffn);
+    if (!rc) rc = sv_alloc((void**)&m->scores, sizeof(float) * B * m->heads * m->max_T * m->max_T);
+    if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * B * ((size_t)m->n_layers * 4 + 1));
+    if (!rc) rc = sv_alloc((void**)&m->amax_keys, sizeof(unsigned long long) * M);
+    if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax));
+    if (!rc) rc = sv_alloc((void**)&m->pcm_stage, sizeof(float) * B * (size_t)max_samples);
+    if (!rc) rc = sv_alloc((void**)&m->ids_stage, sizeof(int32_t) * M);
+    if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
+    *out = m;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensevoice* m) {
+    if (!m) return LELE_B200_OK;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    for (auto* q : m->lin) lele_b200_qweights_destroy(nullptr, q);
+    void* bufs[] = {m->lfr, m->feats, m->x0, m->x, m->h, m->qkv, m->qs, m->fsmn, m->att, m->f1, m->scores, m->keys, m->amax_keys,
+                    m->qscratch, m->pcm_stage, m->ids_stage};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (auto e : m->ev_pool) cudaEventDestroy(e);
+    delete m;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_rows(const lele_b200_sensevoice* m, int n_samples) {
+    (void)m;
+    int frames = lele_b200_frontend_num_frames(n_samples);
+    return frames == 0 ? 0 : (frames + 5) / 6 + 4;
+}
+extern "C" int lele_b200_sensevoice_vocab(const lele_b200_sensevoice* m) { return m ? m->vocab : 0; }
+
+static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* feats, int B, int t, int lang, int textnorm,
+                      int n_layers_limit, int32_t* ids_dev, float* logits_opt) {
+    const int d = m->d, din = m->d_in, H = m->heads, dk = d / H, T = t + 4, ffn = m->ffn;
+    const long long M = (long long)B * T;
+    const int n_layers = (n_layers_limit >= 0 && n_layers_limit < m->n_layers) ? n_layers_limit : m->n_layers;
+    LB_REQUIRE(lang >= 0 && lang < m->n_embed && textnorm >= 0 && textnorm < m->n_embed, "sensevoice: prompt id out of range");
+    const int n_sites = m->n_layers * 4 + 1;
+    SV_RUN(P_MISC, lb_minmax_init(ctx, m->keys, n_sites * B));
+    auto site = [&](int s) { return m->keys + (size_t)2 * B * s; };
+    const LbQuantScratch qs = lb_quant_scratch_carve(m->qscratch, M, ffn > din ? ffn : din);
+
+    {   // gather(embed, prompt ids) ++ concat ++ mul sqrt(d) ++ add pos
+        ProfScope ps(m, ctx, P_PREP);
+        prompt_scale_pos_kernel<<<grid_for(M * din), 256, 0, ctx->stream>>>(feats, (const float*)m->tensor(SV_G_EMBED),
+            (const float*)m->tensor(SV_G_POS), make_int4(lang, 1, 2, textnorm), B, t, din, sqrtf((float)d), m->x0);
+        LB_LAUNCH_CHECK(ctx);
+    }
+    const float qscale = 1.0f / sqrtf((float)dk);
+    const float* xin = m->x0;
+    int cur = din;
+    for (int l = 0; l < n_layers; ++l) {
+        // ---- self-attention block ----
+        SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, xin, (const float*)m->lt(l, SV_L_LN1_G), (const float*)m->lt(l, SV_L_LN1_B), M, cur,
+                                                 1e-5f, m->h, site(l * 4 + 0), T));
+        {
+            LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
+            ep.out = m->qkv; ep.rows_per_slice = T;
+            SV_LINEAR(ctx, m,m->h, site(l * 4 + 0), M, T, m->lin[l * 4 + 0], qs, ep);
+        }
+        {
+            ProfScope ps(m, ctx, P_FSMN);
+            fsmn_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), B, T, d, m->fsmn_k, m->fsmn);
+            LB_LAUNCH_CHECK(ctx);
+            scale_copy_q_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, M, d, qscale, m->qs);
+            LB_LAUNCH_CHECK(ctx);
+        }
+        for (int hd = 0; hd < H; ++hd) {   // scores[b,hd] = (q*scale) k^T
+            SV_RUN(P_ATTN_QK, lb_sgemm_strided_ldc(ctx, m->qs + hd * dk, d, 1, (long long)T * d,
+                                                   m->qkv + d + hd * dk, 1, 3 * d, (long long)T * 3 * d,
+                                                   m->scores + (long long)hd * T * T, (long long)H * T * T, T, B, T, dk, T, 1.0f));
+        }
+        {
+            ProfScope ps(m, ctx, P_SOFTMAX);
+            softmax_rows_kernel<<<lb_ceil_div((long long)B * H * T, 8), 256, 0, ctx->stream>>>(m->scores, (long long)B * H * T, T);
+            LB_LAUNCH_CHECK(ctx);
+        }
+        for (int hd = 0; hd < H; ++hd) {   // att[b, :, hd*dk:(hd+1)*dk] = P v
+            SV_RUN(P_ATTN_PV, lb_sgemm_strided_ldc(ctx, m->scores + (long long)hd * T * T, T, 1, (long long)H * T * T,
+                                                   m->qkv + 2 * d + hd * dk, 3 * d, 1, (long long)T * 3 * d,
+                                                   m->att + hd * dk, (long long)T * d, d, B, T, T, dk, 1.0f));
+        }
+        SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->att, B, (long long)T * d, site(l * 4 + 1)));
+        {
+            LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
+            ep.out = m->x; ep.rows_per_slice = T; ep.add1 = m->fsmn; ep.add2 = (cur == d) ? xin : nullptr;   // x = x + (lin + fsmn)
+            SV_LINEAR(ctx, m,m->att, site(l * 4 + 1), M, T, m->lin[l * 4 + 1], qs, ep);
+        }
+        xin = m->x; cur = d;
+        // ---- feed-forward block ----
+        SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), M, d, 1e-5f,
+                                                 m->h, site(l * 4 + 2), T));
+        {
+            LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
+            ep.out = m->f1; ep.rows_per_slice = T; ep.relu = 1; ep.minmax_keys = site(l * 4 + 3);
+            SV_LINEAR(ctx, m,m->h, site(l * 4 + 2), M, T, m->lin[l * 4 + 2], qs, ep);
+        }
+        {
+            LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
+            ep.out = m->x; ep.rows_per_slice = T; ep.add2 = m->x;                                          // x = x + ffn
+            SV_LINEAR(ctx, m,m->f1, site(l * 4 + 3), M, T, m->lin[l * 4 + 3], qs, ep);
+        }
+        if (l == m->n_stage1 - 1) {   // after_norm (output replaces the residual stream)
+            SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, m->x, (const float*)m->tensor(SV_G_AFTER_G), (const float*)m->tensor(SV_G_AFTER_B), M, d,
+                                                     1e-5f, m->h, nullptr, T));
+            LB_CHECK_CUDA(cudaMemcpyAsync(m->x, m->h, sizeof(float) * M * d, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    if (n_layers < m->n_layers) {   // truncated run (tests): expose the hidden state
+        if (logits_opt) LB_CHECK_CUDA(cudaMemcpyAsync(logits_opt, xin, sizeof(float) * M * cur, cudaMemcpyDeviceToDevice, ctx->stream));
+        return LELE_B200_OK;
+    }
+    const int ctc_site = m->n_layers * 4;
+    SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, xin, (const float*)m->tensor(SV_G_TP_G), (const float*)m->tensor(SV_G_TP_B), M, cur, 1e-5f, m->h,
+                                             site(ctc_site), T));
+    if (ids_dev) {
+        ProfScope ps(m, ctx, P_ARGMAX);
+        init_u64_kernel<<<lb_ceil_div(M, 256), 256, 0, ctx->stream>>>(m->amax_keys, M);
+        LB_LAUNCH_CHECK(ctx);
+    }
+    {
+        LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
+        ep.out = logits_opt; ep.rows_per_slice = T; ep.argmax_keys = ids_dev ? m->amax_keys : nullptr;
+        SV_LINEAR(ctx, m,m->h, site(ctc_site), M, T, m->lin[(size_t)m->n_layers * 4], qs, ep);
+    }
+    if (ids_dev) SV_RUN(P_ARGMAX, lb_argmax_keys_to_ids(ctx, m->amax_keys, M, ids_dev));
+    return LELE_B200_OK;
+}
+
+static int sv_finish_profile(lele_b200_ctx* ctx, lele_b200_sensevoice* m) {
+    if (!m->profiling) return LELE_B200_OK;
+    LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < P_NUM; ++i) { m->prof_ms[i] = 0; m->prof_calls[i] = 0; }
+    for (auto& s : m->spans) { float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); m->prof_ms[s.cls] += ms; m->prof_calls[s.cls]++; }
+    m->spans.clear(); m->ev_used = 0;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_forward_features(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* feats_dev, int n_clips,
+                                                     int t, int lang, int textnorm, int n_layers_limit, int32_t* ids_dev,
+                                                     float* logits_dev_opt) {
+    LB_REQUIRE(ctx && m && feats_dev, "sensevoice_forward_features: NULL argument");
+    LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && t >= 1 && t + 4 <= m->max_T, "sensevoice_forward_features: batch/length exceeds workspace");
+    int rc = sv_encoder(ctx, m, feats_dev, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+    if (rc) return rc;
+    return sv_finish_profile(ctx, m);
+}
+
+extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_dev, int n_clips, int n_samples,
+                                            int lang, int textnorm, int n_layers_limit, int32_t* ids_dev, float* logits_dev_opt) {
+    LB_REQUIRE(ctx && m && pcm_dev, "sensevoice_forward: NULL argument");
+    LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && n_samples <= m->max_samples, "sensevoice_forward: batch/length exceeds workspace");
+    int frames = lele_b200_frontend_num_frames(n_samples);
+    LB_REQUIRE(frames > 0, "sensevoice_forward: clip shorter than one frame (400 samples)");
+    int t = (frames + 5) / 6;
+    SV_RUN(P_FRONTEND, lele_b200_frontend_compute(ctx, pcm_dev, n_clips, n_samples, n_samples, nullptr, m->lfr));
+    SV_RUN(P_CMVN, lele_b200_cmvn(ctx, m->lfr, n_clips, t, m->d_in, 1e-5f, m->feats));
+    int rc = sv_encoder(ctx, m, m->feats, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+    if (rc) return rc;
+    return sv_finish_profile(ctx, m);
+}
+
+extern "C" int lele_b200_sensevoice_transcribe_host(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_host, int n_clips,
+                                                    int n_samples, int lang, int textnorm, int32_t* ids_host) {
+    LB_REQUIRE(ctx && m && pcm_host && ids_host, "sensevoice_transcribe_host: NULL argument");
+    LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && n_samples <= m->max_samples, "sensevoice_transcribe_host: batch/length exceeds workspace");
+    int T = lele_b200_sensevoice_rows(m, n_samples);
+    LB_REQUIRE(T > 0, "sensevoice_transcribe_host: clip shorter than one frame");
+    LB_CHECK_CUDA(cudaMemcpyAsync(m->pcm_stage, pcm_host, sizeof(float) * (size_t)n_clips * n_samples, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = lele_b200_sensevoice_forward(ctx, m, m->pcm_stage, n_clips, n_samples, lang, textnorm, -1, m->ids_stage, nullptr);
+    if (rc) return rc;
+    LB_CHECK_CUDA(cudaMemcpyAsync(ids_host, m->ids_stage, sizeof(int32_t) * (size_t)n_clips * T, cudaMemcpyDeviceToHost, ctx->stream));
+    LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_set_profiling(lele_b200_sensevoice* m, int enable) {
+    LB_REQUIRE(m, "sensevoice_set_profiling: NULL model");
+    m->profiling = enable ? 1 : 0;
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_sensevoice_last_profile(lele_b200_sensevoice* m, const char** names, float* ms, int* calls, int cap,
+                                                 int* n_out) {
+    LB_REQUIRE(m && names && ms && calls && n_out, "sensevoice_last_profile: NULL argument");
+    int n = 0;
+    for (int i = 0; i < P_NUM && n < cap; ++i) { names[n] = kProfNames[i]; ms[n] = m->prof_ms[i]; calls[n] = m->prof_calls[i]; ++n; }
+    *n_out = n;
+    return LELE_B200_OK;
+}

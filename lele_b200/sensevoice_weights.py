@@ -101,6 +101,25 @@ def build_blob(cfg: SenseVoiceConfig = SenseVoiceConfig(), seed: int = 1234) -> 
     return blob
 
 
+def _tensor_nbytes(cfg: SenseVoiceConfig) -> list[int]:
+    d, din, v, f = cfg.d_model, cfg.d_in, cfg.vocab, cfg.ffn
+    lin = lambda k, n: [k * n, 4 * n, 4 * n, 1]            # w u8, scale f32, bias f32, zp u8
+    out = [4 * cfg.n_embed * din, 4 * cfg.max_t * din, 4 * d, 4 * d, 4 * d, 4 * d] + lin(d, v)
+    for l in range(cfg.n_layers):
+        cur = din if l == 0 else d
+        out += [4 * cur, 4 * cur] + lin(cur, 3 * d) + [4 * d * cfg.fsmn_k] + lin(d, d) + [4 * d, 4 * d] + lin(d, f) + lin(f, d)
+    return out
+
+
+def blob_nbytes(cfg: SenseVoiceConfig = SenseVoiceConfig()) -> int:
+    """Size of build_blob(cfg) without generating it (ranks that receive the NCCL broadcast)."""
+    sizes = _tensor_nbytes(cfg)
+    off = (256 + 16 * len(sizes) + ALIGN - 1) // ALIGN * ALIGN
+    for s in sizes:
+        off = (off + s + ALIGN - 1) // ALIGN * ALIGN
+    return off
+
+
 def synth_pcm(clip_id: int, n_samples: int = 256000) -> np.ndarray:
     """0.1*sin(2*pi*f_c*n/16000) + 0.01*u[n], f_c = 200+37*clip_id,
     u ~ uniform(-1,1) from a 64-bit LCG seeded 0x5EED0000+clip_id."""

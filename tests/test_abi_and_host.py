@@ -1,0 +1,140 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/lele_b200.h declares
+(no compute without a GPU), host logic (blob layout, synthetic PCM, shard plan), and the N>1
+path (weights broadcast + ids gather) under gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def so_path():
+    from lele_b200.build import build
+    return build()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "lele_b200.h")).read()
+    return sorted(set(re.findall(r"\b(lele_b200_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(so_path):
+    lib = ctypes.CDLL(so_path)
+    names = declared_symbols()
+    assert len(names) >= 60
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", so_path], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (lele_b200_[a-z0-9_]+)", out))
+    assert exported == set(names), (sorted(exported - set(names)), sorted(set(names) - exported))   # nothing undeclared leaks either
+
+
+def test_host_only_entry_points(so_path):
+    """hann_window / mel_filterbank / frame counting are host functions of the ABI: callable without a GPU
+    and identical to the oracle (same f32 libm arithmetic as the reference)."""
+    from lele_b200 import features as F
+    from oracle import reference_api as R
+    np.testing.assert_array_equal(F.hann_window(400), R.hann_window(400))
+    np.testing.assert_array_equal(F.mel_filterbank(16000.0, 512, 80, 20.0), R.mel_filterbank(16000.0, 512, 80, 20.0))
+    assert F.hann_window(1)[0] == 1.0 and F.hann_window(0).size == 0
+    lib = ctypes.CDLL(so_path)
+    assert lib.lele_b200_frontend_num_frames(256000) == 1598 and lib.lele_b200_frontend_out_rows(256000) == 267
+    assert lib.lele_b200_frontend_num_frames(399) == 0 and lib.lele_b200_frontend_num_frames(89472) == 557
+
+
+def test_compute_fails_loudly_without_gpu(so_path):
+    import lele_b200
+    if lele_b200.lib.lele_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(lele_b200.LeleB200Error):
+        lele_b200.kernels.add(np.ones(4, np.float32), np.ones(4, np.float32))
+    with pytest.raises(lele_b200.LeleB200Error):
+        lele_b200.features.SenseVoiceFrontend().compute(np.zeros(16000, np.float32))
+
+
+def test_product_never_imports_oracle():
+    """The product path may not route through the CPU oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "lele_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the CPU oracle", "").replace("oracle/sensevoice_ref.c", ""), f"{f} references the oracle"
+
+
+def test_blob_layout_and_synth():
+    from lele_b200.sensevoice_weights import SenseVoiceConfig, blob_nbytes, build_blob, synth_pcm
+    cfg = SenseVoiceConfig(n_layers=2, vocab=300, n_stage1=1, max_t=32)
+    blob = build_blob(cfg, seed=1)
+    assert blob.nbytes == blob_nbytes(cfg)
+    assert blob_nbytes(SenseVoiceConfig()) > 230e6            # ~233 MB u8 + f32 vectors
+    hdr = blob[:256].view(np.int32)
+    assert hdr[0] == 0x454C454C and hdr[12] == 10 + 2 * 21
+    table = blob[256:256 + 16 * int(hdr[12])].view(np.uint64).reshape(-1, 2)
+    assert (table[:, 0] % 256 == 0).all() and int(table[-1, 0] + table[-1, 1]) <= blob.nbytes
+    assert int(table[2 + 10, 1]) == 560 * 1536                 # layer-0 qkv weight is [560, 1536] u8
+    np.testing.assert_array_equal(build_blob(cfg, seed=1), blob)
+    a = synth_pcm(3, 4000)
+    np.testing.assert_array_equal(a, synth_pcm(3, 4000))
+    assert np.abs(a).max() < 0.111 and not np.array_equal(a, synth_pcm(4, 4000))
+    np.testing.assert_array_equal(synth_pcm(3, 8000)[:4000], a)   # LCG jump-ahead is prefix-stable
+    from oracle.binding import SenseVoiceRef
+    assert SenseVoiceRef(blob).vocab == 300
+
+
+def test_shard_range_partition():
+    from lele_b200.distributed import shard_range
+    for n, w in [(512, 8), (64, 1), (10, 4), (3, 8)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from lele_b200.distributed import broadcast_blob, gather_ids, shard_range, max_over_ranks
+from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob, blob_nbytes
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+cfg = SenseVoiceConfig(n_layers=1, vocab=64, n_stage1=1, max_t=16)
+nb = blob_nbytes(cfg)
+blob = torch.from_numpy(build_blob(cfg, seed=5)) if rank == 0 else torch.zeros(nb, dtype=torch.uint8)
+broadcast_blob(blob, 0)
+assert np.array_equal(blob.numpy(), build_blob(cfg, seed=5)), "broadcast mismatch"
+n_total, T = 7, 5                       # ragged: shards of 4 and 3 clips
+s, e = shard_range(n_total, rank, world)
+local = torch.arange(s * T, e * T, dtype=torch.int32).reshape(e - s, T)   # stands in for this rank's greedy ids
+allids = gather_ids(local, n_total, 0)
+if rank == 0:
+    assert allids.shape == (n_total, T) and torch.equal(allids.reshape(-1), torch.arange(n_total * T, dtype=torch.int32))
+else:
+    assert allids is None
+assert max_over_ranks(float(rank + 1)) == float(world)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_broadcast_and_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
+def test_bench_reference_arm_cli_contract():
+    """bench.py --impl reference must parse and (without running the 10 s/clip workload here) expose the flags."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "--impl" in r.stdout and "--gpus" in r.stdout and "--steps" in r.stdout and "--warmup" in r.stdout

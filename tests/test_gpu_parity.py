@@ -1,0 +1,271 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every operator of the CUDA product,
+called through the C ABI, against (1) the reference's own known-answer vectors and (2) the CPU
+oracle on the same seeded inputs.  Bars: bit-exact for integer / byte / index work; f32 within
+1e-4 relative (stated per test; GEMM-like sums are relative to the output magnitude, as the
+reference's own tests are absolute at 1e-5..1e-3)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import reference_api as R          # noqa: E402  (checker only)
+from tests import gpu_backend as G             # noqa: E402
+from tests.kat_runner import KATS, kat_id, run_kat  # noqa: E402
+from tests.test_oracle_kats import GRU_CASES, gru_case  # noqa: E402
+
+RTOL = 1e-4
+
+
+def close(got, ref, rtol=RTOL, atol_frac=RTOL):
+    """|got-ref| <= rtol*|ref| + atol_frac*max|ref| (normwise floor for cancellation-prone sums)"""
+    got = np.asarray(got, np.float32); ref = np.asarray(ref, np.float32)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    scale = float(np.abs(ref).max()) if ref.size else 0.0
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol_frac * scale + 1e-30)
+
+
+@pytest.mark.parametrize("k", KATS, ids=kat_id)
+def test_reference_kat_on_gpu(k):
+    run_kat(G, k)
+
+
+# ---------------------------------------------------------------- front-end
+def test_frontend_matches_oracle():
+    from lele_b200.sensevoice_weights import synth_batch
+    pcm = synth_batch(0, 3, 89472)                      # zh.wav-sized clips (557 frames -> 93 rows)
+    melg, outg = G.frontend(pcm, want_mel=True)
+    for c in range(3):
+        melr, outr = R.frontend(pcm[c], want_mel=True)
+        close(melg[c], melr)                              # log-mel, 1e-4
+        close(outg[c], outr)
+        # LFR is an exact copy of the GPU's own mel frames
+        np.testing.assert_array_equal(outg[c], R.lfr(melg[c]))
+    assert G.frontend(np.zeros(399, np.float32)).shape == (0, 560)      # empty clip
+    one = G.frontend(pcm[0][:400])                                       # exactly one frame
+    assert one.shape == (1, 560)
+    close(one, R.frontend(pcm[0][:400]))
+
+
+def test_cmvn_lfr_stft_rfft():
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((93, 560)) * 3 + 10).astype(np.float32)
+    close(G.cmvn(x), R.cmvn(x))
+    x = rng.standard_normal((11, 80)).astype(np.float32)
+    np.testing.assert_array_equal(G.lfr(x), R.lfr(x))
+    np.testing.assert_array_equal(G.lfr(x[:1]), R.lfr(x[:1]))
+    sig = np.sin(np.arange(800, dtype=np.float32) * np.float32(0.01))
+    close(G.stft(sig, 256, 128, 256), R.stft(sig, 256, 128, 256), atol_frac=1e-5)
+    close(G.stft(sig, 256, 128, 256, power=True), R.stft(sig, 256, 128, 256, power=True), atol_frac=1e-5)
+    close(G.stft(sig[:100], 256, 64, 256, power=True), R.stft(sig[:100], 256, 64, 256, power=True), atol_frac=1e-5)  # shorter than a window
+    for n in (8, 64, 512, 1024):
+        v = rng.standard_normal(n).astype(np.float32)
+        re, im = G.rfft(v); rr, ri = R.rfft(v)
+        close(re, rr, atol_frac=1e-5); close(im, ri, atol_frac=1e-5)
+
+
+# ---------------------------------------------------------------- norms / activations
+def test_layer_norm_softmax_norms():
+    rng = np.random.default_rng(1)
+    for shape in [(7, 512), (271, 560), (5, 19), (3, 4, 2048), (2, 1030)]:
+        x = (rng.standard_normal(shape) * 2 + 0.5).astype(np.float32)
+        g = (1 + 0.1 * rng.standard_normal(shape[-1])).astype(np.float32); b = (0.1 * rng.standard_normal(shape[-1])).astype(np.float32)
+        close(G.layer_norm(x, g, b, -1, 1e-5), R.layer_norm(x, g, b, -1, 1e-5), atol_frac=1e-6)
+    for shape in [(4, 271, 271), (9, 17), (3, 8), (2, 1000)]:
+        x = (rng.standard_normal(shape) * 3).astype(np.float32)
+        close(G.softmax(x, -1), R.softmax(x), atol_frac=1e-6)
+    x = rng.standard_normal((2, 5, 7, 3)).astype(np.float32)
+    sc, bi, mu = (rng.standard_normal(5).astype(np.float32) for _ in range(3)); var = rng.uniform(0.5, 2, 5).astype(np.float32)
+    close(G.batch_norm(x, sc, bi, mu, var), R.batch_norm(x, sc, bi, mu, var), atol_frac=1e-6)
+    w = rng.standard_normal(3).astype(np.float32)
+    close(G.rms_norm(x, w), R.rms_norm(x, w), atol_frac=1e-6)
+
+
+@pytest.mark.parametrize("name", ["relu", "sigmoid", "tanh", "silu", "erf", "gelu", "exp", "softplus"])
+def test_activations(name):
+    x = np.concatenate([np.linspace(-9, 9, 1003), [0.0, -0.0, 30.0, -30.0]]).astype(np.float32)  # 1007 elems: SIMD body + tail
+    close(getattr(G, name)(x), getattr(R, name)(x), rtol=1e-5, atol_frac=1e-7)
+
+
+def test_elementwise_and_reductions():
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal((3, 1, 5)).astype(np.float32); b = rng.standard_normal((4, 5)).astype(np.float32) + 3
+    for op in ("add", "sub", "mul", "div"):
+        np.testing.assert_array_equal(getattr(G, op)(a, b), getattr(R, op)(a, b))     # single IEEE ops: exact
+    np.testing.assert_array_equal(G.add(a, np.float32(2.5)), R.add(a, np.float32(2.5)))
+    big = rng.standard_normal(100003).astype(np.float32)
+    np.testing.assert_array_equal(G.mul(big, big), R.mul(big, big))
+    np.testing.assert_array_equal(G.maximum(a, b), R.maximum(a, b))
+    np.testing.assert_array_equal(G.clip(a, -0.5, 0.5), R.clip(a, -0.5, 0.5))
+    np.testing.assert_array_equal(G.mod_f32(a, b), R.mod_f32(a, b))
+    np.testing.assert_array_equal(G.neg(a), R.neg(a)); np.testing.assert_array_equal(G.sqrt(b), R.sqrt(b))
+    np.testing.assert_array_equal(G.reciprocal(b), R.reciprocal(b))
+    x = rng.standard_normal((3, 7, 5)).astype(np.float32)
+    for kind in ("sum", "mean", "max", "l2"):
+        close(G.reduce(x, [1], True, kind), R.reduce(x, [1], True, kind), atol_frac=1e-6)
+        close(G.reduce(x, [0, 2], False, kind), R.reduce(x, [0, 2], False, kind), atol_frac=1e-6)
+
+
+# ---------------------------------------------------------------- quantised path
+def test_dynamic_quantize_linear_exact():
+    rng = np.random.default_rng(3)
+    for shape in [(93, 512), (7, 13), (1, 5), (271, 2048)]:
+        x = (rng.standard_normal(shape) * 2).astype(np.float32)
+        qg, sg, zg = G.dynamic_quantize_linear(x); qr, sr, zr = R.dynamic_quantize_linear(x)
+        assert sg == sr and zg == zr
+        np.testing.assert_array_equal(qg, qr)             # integer result: bit-exact
+    x = np.abs(rng.standard_normal((4, 16))).astype(np.float32)   # all-positive -> zp 0
+    np.testing.assert_array_equal(G.dynamic_quantize_linear(x)[0], R.dynamic_quantize_linear(x)[0])
+
+
+def test_mat_mul_integer_exact():
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 256, (2, 37, 70)).astype(np.float32); b = rng.integers(0, 256, (70, 45)).astype(np.float32)
+    sc = rng.uniform(0.001, 0.01, 45).astype(np.float32); bi = rng.standard_normal(45).astype(np.float32)
+    np.testing.assert_array_equal(G.mat_mul_integer(a, b, 3.0, 128.0), R.mat_mul_integer(a, b, 3.0, 128.0))
+    np.testing.assert_array_equal(G.mat_mul_integer(a, b, 3.0, 128.0, sc, bi, True), R.mat_mul_integer(a, b, 3.0, 128.0, sc, bi, True))
+    np.testing.assert_array_equal(G.mat_mul_integer(a, b, 0.0, 0.0, sc[:1], None, False), R.mat_mul_integer(a, b, 0.0, 0.0, sc[:1], None, False))
+
+
+LINEAR_SHAPES = [  # (slices, m, k, n): SenseVoice shapes (wasm_bench.rs:293-317) + ragged / odd cases
+    (1, 93, 512, 1536), (1, 93, 512, 512), (1, 93, 512, 2048), (1, 93, 2048, 512), (1, 93, 560, 1536),
+    (3, 271, 512, 1536), (2, 271, 2048, 512), (1, 1, 16, 8), (2, 5, 48, 300), (1, 130, 144, 257), (1, 7, 20, 9),
+]
+
+
+@pytest.mark.parametrize("shape", LINEAR_SHAPES)
+def test_fused_quantized_linear_bit_exact(shape):
+    """Integer core exact on tcgen05 + identical f32 epilogue ops => bit-exact vs the oracle."""
+    s, m, k, n = shape
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    x = (rng.standard_normal((s, m, k)) * rng.uniform(0.5, 3, (s, 1, 1))).astype(np.float32)
+    w = rng.integers(0, 256, (k, n), dtype=np.uint8)
+    ws = rng.uniform(0.002, 0.006, n).astype(np.float32); b = rng.standard_normal(n).astype(np.float32)
+    for relu in (False, True):
+        np.testing.assert_array_equal(G.fused_quantized_linear(x, w, ws, 128, b, relu), R.fused_quantized_linear(x, w, ws, 128, b, relu))
+    np.testing.assert_array_equal(G.fused_quantized_linear(x, w, ws[:1], 7, None, False), R.fused_quantized_linear(x, w, ws[:1], 7, None, False))
+
+
+def test_fused_quantized_linear_extremes():
+    """max-magnitude integer sums (all 255 x 255 over K=2048) and a constant-zero input."""
+    k, n = 2048, 256
+    x = np.full((1, 130, k), 5.0, np.float32); x[0, 0, 0] = 0.0
+    w = np.full((k, n), 255, np.uint8)
+    np.testing.assert_array_equal(G.fused_quantized_linear(x, w, np.ones(n, np.float32), 0, None), R.fused_quantized_linear(x, w, np.ones(n, np.float32), 0, None))
+    z = np.zeros((1, 4, 64), np.float32)
+    w = np.arange(64 * 32, dtype=np.uint8).reshape(64, 32)
+    np.testing.assert_array_equal(G.fused_quantized_linear(z, w, np.ones(32, np.float32), 128, np.ones(32, np.float32)),
+                                  R.fused_quantized_linear(z, w, np.ones(32, np.float32), 128, np.ones(32, np.float32)))
+
+
+# ---------------------------------------------------------------- f32 GEMM / conv / rnn
+def test_matmul_family():
+    rng = np.random.default_rng(5)
+    for (ba, bb, m, k, n) in [(4, 4, 271, 128, 271), (4, 4, 271, 271, 128), (1, 1, 5, 7, 3), (3, 1, 65, 33, 70), (1, 2, 16, 16, 16)]:
+        a = rng.standard_normal((ba, m, k) if ba > 1 else (m, k)).astype(np.float32)
+        b = rng.standard_normal((bb, k, n) if bb > 1 else (k, n)).astype(np.float32)
+        close(G.matmul(a, b), R.matmul(a, b), atol_frac=1e-5)
+    a = rng.standard_normal((9, 20)).astype(np.float32); b = rng.standard_normal((20, 11)).astype(np.float32)
+    close(G.matmul_fused_add(a, b, np.arange(11, dtype=np.float32)), R.matmul_fused_add(a, b, np.arange(11, dtype=np.float32)), atol_frac=1e-5)
+    close(G.matmul_fused_add(a, b, np.arange(3, dtype=np.float32)), R.matmul_fused_add(a, b, np.arange(3, dtype=np.float32)), atol_frac=1e-5)
+    for ta in (False, True):
+        for tb in (False, True):
+            A = a.T.copy() if ta else a; B = b.T.copy() if tb else b
+            for c in (None, rng.standard_normal(11).astype(np.float32), rng.standard_normal((9, 11)).astype(np.float32), rng.standard_normal(9).astype(np.float32)[:, None] * np.ones((1, 1), np.float32)):
+                cc = None if c is None else np.asarray(c, np.float32).reshape(-1)
+                close(G.gemm(A, B, cc, 0.5, 2.0, ta, tb), R.gemm(A, B, cc, 0.5, 2.0, ta, tb), atol_frac=1e-5)
+
+
+def test_convs():
+    rng = np.random.default_rng(6)
+    for (ic, oc, k, s, p, g, d) in [(3, 8, 3, 1, 1, 1, 1), (4, 8, 3, 2, 1, 1, 1), (4, 4, 3, 1, 1, 4, 1), (64, 64, 3, 1, 1, 64, 1), (8, 16, 1, 1, 0, 1, 1), (16, 32, 3, 1, 2, 1, 2), (6, 4, 3, 1, 1, 2, 1)]:
+        x = rng.standard_normal((2, ic, 13, 17)).astype(np.float32)
+        w = (rng.standard_normal((oc, ic // g, k, k)) / np.sqrt(ic // g * k * k)).astype(np.float32)
+        b = rng.standard_normal(oc).astype(np.float32)
+        for act in (0, 1, 2):
+            close(G.conv2d(x, w, b, (d, d), g, (p, p, p, p), (s, s), act), R.conv2d(x, w, b, (d, d), g, (p, p, p, p), (s, s), act), atol_frac=1e-5)
+        close(G.conv2d(x, w, None, (d, d), g, (p, p, p, p), (s, s), 0), R.conv2d(x, w, None, (d, d), g, (p, p, p, p), (s, s), 0), atol_frac=1e-5)
+    x = rng.standard_normal((1, 6, 5, 7)).astype(np.float32); w = rng.standard_normal((6, 4, 3, 3)).astype(np.float32); b = rng.standard_normal(4).astype(np.float32)
+    close(G.conv_transpose(x, w, b, (1, 1), (1, 1, 1, 1), (2, 2)), R.conv_transpose(x, w, b, (1, 1), (1, 1, 1, 1), (2, 2)), atol_frac=1e-5)
+    x = rng.standard_normal((2, 16, 9, 9)).astype(np.float32); w = rng.standard_normal((16, 16, 2, 2)).astype(np.float32)
+    close(G.conv_transpose(x, w, None, (1, 1), (0, 0, 0, 0), (2, 2)), R.conv_transpose(x, w, None, (1, 1), (0, 0, 0, 0), (2, 2)), atol_frac=1e-5)   # Yolo shape class (k = stride)
+    for (ic, oc, k, g, pl, pr, s, d) in [(512, 512, 11, 512, 5, 5, 1, 1), (1, 258, 256, 1, 0, 0, 64, 1), (8, 12, 3, 1, 1, 1, 2, 1), (8, 8, 3, 2, 2, 2, 1, 2)]:
+        x = rng.standard_normal((2, ic, 300)).astype(np.float32); w = (rng.standard_normal((oc, ic // g, k)) / np.sqrt(k)).astype(np.float32)
+        b = rng.standard_normal(oc).astype(np.float32)
+        close(G.conv1d(x, w, b, (d,), g, (pl, pr), (s,), True), R.conv1d(x, w, b, (d,), g, (pl, pr), (s,), True), atol_frac=1e-5)
+    x = rng.standard_normal((2, 3, 10, 11)).astype(np.float32)
+    np.testing.assert_array_equal(G.max_pool2d(x, (5, 5), (2, 2, 2, 2), (1, 1)), R.max_pool2d(x, (5, 5), (2, 2, 2, 2), (1, 1)))
+    np.testing.assert_array_equal(G.max_pool2d(x, (3, 3), (0, 0, 0, 0), (2, 2), (1, 1), True), R.max_pool2d(x, (3, 3), (0, 0, 0, 0), (2, 2), (1, 1), True))
+    for mode in ("asymmetric", "half_pixel"):
+        np.testing.assert_array_equal(G.resize_nearest(x, scales=[1, 1, 2, 2], mode=mode), R.resize_nearest(x, scales=[1, 1, 2, 2], mode=mode))
+        np.testing.assert_array_equal(G.resize_nearest(x, sizes=[2, 3, 7, 5], mode=mode), R.resize_nearest(x, sizes=[2, 3, 7, 5], mode=mode))
+
+
+@pytest.mark.parametrize("c", GRU_CASES)
+def test_gru(c):
+    x, w, r, b = gru_case(c)
+    yg, hg = G.gru(x, w, r, b); yr, hr = R.gru(x, w, r, b)
+    close(yg, yr, atol_frac=1e-5); close(hg, hr, atol_frac=1e-5)
+
+
+def test_lstm_gru_larger():
+    rng = np.random.default_rng(7)
+    for hid, isz, seq in [(128, 64, 20), (20, 7, 5)]:
+        x = rng.standard_normal((seq, 1, isz)).astype(np.float32)
+        w = (rng.standard_normal((1, 4 * hid, isz)) / np.sqrt(isz)).astype(np.float32); r = (rng.standard_normal((1, 4 * hid, hid)) / np.sqrt(hid)).astype(np.float32)
+        b = (0.1 * rng.standard_normal((1, 8 * hid))).astype(np.float32)
+        h0 = rng.standard_normal((1, 1, hid)).astype(np.float32); c0 = rng.standard_normal((1, 1, hid)).astype(np.float32)
+        for got, ref in zip(G.lstm(x, w, r, b, h0, c0), R.lstm(x, w, r, b, h0, c0)):
+            close(got, ref, atol_frac=1e-4)
+        for got, ref in zip(G.lstm(x, w, r, None), R.lstm(x, w, r, None)):
+            close(got, ref, atol_frac=1e-4)
+        w3 = w[:, :3 * hid]; r3 = r[:, :3 * hid]; b3 = (0.1 * rng.standard_normal((1, 6 * hid))).astype(np.float32)
+        for got, ref in zip(G.gru(x, w3, r3, b3, h0), R.gru(x, w3, r3, b3, h0)):
+            close(got, ref, atol_frac=1e-4)
+
+
+# ---------------------------------------------------------------- indexing (bit-exact)
+def test_indexing_exact():
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((2, 3, 4, 5)).astype(np.float32)
+    for perm in [(0, 2, 1, 3), (0, 2, 3, 1), (3, 2, 1, 0), (1, 0, 2, 3), ()]:
+        np.testing.assert_array_equal(G.transpose(x, perm), R.transpose(x, perm))
+    big = rng.standard_normal((1, 271, 4, 128)).astype(np.float32)
+    np.testing.assert_array_equal(G.transpose(big, (0, 2, 1, 3)), R.transpose(big, (0, 2, 1, 3)))
+    m2 = rng.standard_normal((70, 45)).astype(np.float32)
+    np.testing.assert_array_equal(G.transpose(m2, (1, 0)), m2.T)
+    b3 = rng.standard_normal((3, 40, 50)).astype(np.float32)
+    np.testing.assert_array_equal(G.transpose(b3, (0, 2, 1)), np.transpose(b3, (0, 2, 1)))
+    np.testing.assert_array_equal(G.concat([x, x[:, :1], np.zeros((2, 0, 4, 5), np.float32)], 1), R.concat([x, x[:, :1], np.zeros((2, 0, 4, 5), np.float32)], 1))
+    for (st, en, ax, sp) in [([1], [3], [2], []), ([0], [2**63 - 1], [3], [2]), ([-1], [-(2**63)], [1], [-1]), ([1, 0], [3, 2], [0, 1], []), ([5], [9], [2], [])]:
+        np.testing.assert_array_equal(G.slice(x, st, en, ax, sp), R.slice(x, st, en, ax, sp))
+    for mode in ("constant", "edge", "reflect"):
+        np.testing.assert_array_equal(G.pad(x, [0, 0, 1, 2, 0, 0, 2, 1], 1.5, mode), R.pad(x, [0, 0, 1, 2, 0, 0, 2, 1], 1.5, mode))
+    np.testing.assert_array_equal(G.pad(x[0, 0], [1, 2], 0.0), R.pad(x[0, 0], [1, 2], 0.0))
+    np.testing.assert_array_equal(G.gather(x, np.array([[0, -1], [1, 1]], np.float32), 1), R.gather(x, np.array([[0, -1], [1, 1]], np.float32), 1))
+    idx = rng.integers(-3, 3, (2, 2, 4, 5)).astype(np.float32)
+    np.testing.assert_array_equal(G.gather_elements(x, idx, 1), R.gather_elements(x, idx, 1))
+    for got, ref in zip(G.split(x, 2, [1, 3]), R.split(x, 2, [1, 3])):
+        np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(G.expand(x[:, :1], [2, 3, 4, 5]), R.expand(x[:, :1], [2, 3, 4, 5]))
+    np.testing.assert_array_equal(G.tile(x[0, 0], [2, 3]), R.tile(x[0, 0], [2, 3]))
+    c = (rng.standard_normal((3, 1, 5)) > 0).astype(np.float32)
+    np.testing.assert_array_equal(G.where(c, x[0, :, :1], x[1, 0]), R.where(c, x[0, :, :1], x[1, 0]))
+    t = rng.integers(0, 6, (5, 40)).astype(np.float32)       # many ties
+    vg, ig = G.topk(t, 7); vr, ir = R.topk(t, 7)
+    np.testing.assert_array_equal(vg, vr); np.testing.assert_array_equal(ig, ir)
+    from lele_b200 import kernels as K
+    am = K.argmax_last(t)
+    np.testing.assert_array_equal(am, t.shape[1] - 1 - np.argmax(t[:, ::-1], axis=1))   # LAST max wins (Iterator::max_by)
+
+
+def test_error_behaviour_matches_reference_panics():
+    from lele_b200 import LeleB200Error
+    from lele_b200 import kernels as K
+    with pytest.raises(LeleB200Error):
+        K.lstm(np.zeros((2, 2, 4), np.float32), np.zeros((1, 8, 4), np.float32), np.zeros((1, 8, 2), np.float32))   # batch != 1 (rnn.rs:88)
+    with pytest.raises(LeleB200Error):
+        K.softmax(np.zeros((2, 3), np.float32), 0)                                                                      # norm.rs:218
+    with pytest.raises(LeleB200Error):
+        K.conv_transpose(np.zeros((1, 2, 3, 3), np.float32), np.zeros((2, 1, 2, 2), np.float32), group=2)              # conv2d.rs:3042
+    with pytest.raises(LeleB200Error):
+        K.matmul(np.zeros((2, 3), np.float32), np.zeros((4, 2), np.float32))

@@ -1,0 +1,110 @@
+"""GPU parity of the SenseVoice-shaped graph runner (csrc/sensevoice.cu) against the CPU oracle
+executing the reference's per-clip op-by-op sequence (oracle/sensevoice_ref.c), plus the
+size-independent properties used at BASELINE.json's full size (64 clips x 16 s)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from lele_b200 import SenseVoice                               # noqa: E402
+from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob, synth_batch  # noqa: E402
+from oracle import reference_api as R                            # noqa: E402  (checker only)
+
+SMALL = SenseVoiceConfig(n_layers=3, vocab=1000, n_stage1=2, max_t=128)
+
+
+def rel_err(got, ref):
+    return float(np.abs(got - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def small_model():
+    blob = build_blob(SMALL, seed=7)
+    m = SenseVoice(blob, max_clips=4, max_samples=89472)
+    yield blob, m
+    m.close()
+
+
+def test_forward_features_matches_oracle_per_layer(small_model):
+    """Hidden state after 0,1,2 layers and final logits; per-clip dynamic quantisation means each
+    clip of the batch must match its own single-clip oracle run."""
+    blob, m = small_model
+    ref = R.SenseVoiceRef(blob)
+    rng = np.random.default_rng(0)
+    feats = (rng.standard_normal((3, 40, 560)) * np.array([1.0, 2.5, 0.3])[:, None, None]).astype(np.float32)
+    for nl, tol in [(0, 1e-6), (1, 1e-4), (2, 2e-4), (-1, 5e-4)]:
+        got = m.forward(feats, 3, 0, n_layers=nl)
+        for c in range(3):
+            want = ref.forward(feats[c], 3, 0, n_layers=nl)
+            assert got[c].shape == want.shape
+            e = rel_err(got[c], want)
+            # f32 ops are within 1e-4; a quantiser rounding flip (|x*inv+zp - n.5| ~ 1e-6) moves one
+            # u8 by 1 LSB, so deeper prefixes get a proportionally looser, still normwise, bound
+            assert e < tol, (nl, c, e)
+
+
+def test_pcm_to_ids_matches_oracle(small_model):
+    blob, m = small_model
+    ref = R.SenseVoiceRef(blob)
+    pcm = synth_batch(0, 2, 89472)
+    ids, logits = m.transcribe(pcm, want_logits=True)
+    ids_host_path = m.transcribe(pcm)                          # host-buffer entry, fused-argmax epilogue (no logits written)
+    np.testing.assert_array_equal(ids, ids_host_path)
+    for c in range(2):
+        rids, rlog = ref.pcm_to_ids(pcm[c], want_logits=True)
+        assert rel_err(logits[c], rlog) < 1e-3
+        # greedy ids agree wherever the oracle's top-2 margin exceeds the logit tolerance
+        top2 = np.sort(rlog, axis=1)[:, -2:]
+        safe = (top2[:, 1] - top2[:, 0]) > 2e-3 * np.abs(rlog).max()
+        assert safe.mean() > 0.5
+        np.testing.assert_array_equal(ids[c][safe], rids[safe])
+        # and the GPU ids are the LAST-max argmax of the GPU logits (tokenizer.rs:55)
+        np.testing.assert_array_equal(ids[c], logits[c].shape[1] - 1 - np.argmax(logits[c][:, ::-1], axis=1))
+
+
+def test_prompt_ids_and_bounds(small_model):
+    blob, m = small_model
+    rng = np.random.default_rng(1)
+    f = rng.standard_normal((1, 10, 560)).astype(np.float32)
+    a = m.forward(f, 3, 0, n_layers=0); b = m.forward(f, 4, 1, n_layers=0)
+    assert not np.array_equal(a[0, 0], b[0, 0]) and np.array_equal(a[0, 1:3], b[0, 1:3]) and np.array_equal(a[0, 4:], b[0, 4:])
+    from lele_b200 import LeleB200Error
+    with pytest.raises(LeleB200Error):
+        m.forward(f, 99, 0)
+    with pytest.raises(LeleB200Error):
+        m.forward(np.zeros((5, 10, 560), np.float32))           # more clips than the workspace holds
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    blob = build_blob(SenseVoiceConfig(), seed=1234)
+    m = SenseVoice(blob, max_clips=64, max_samples=256000)
+    yield blob, m
+    m.close()
+
+
+def test_full_size_first_layers_vs_oracle(full_model):
+    """BASELINE config shapes (T'=271, d=512, ffn 2048): 2 layers of one 16 s clip vs the oracle."""
+    blob, m = full_model
+    ref = R.SenseVoiceRef(blob)
+    pcm = synth_batch(5, 1, 256000)
+    feats = R.cmvn(R.frontend(pcm[0]))
+    got = m.forward(feats[None], 3, 0, n_layers=2)[0]
+    want = ref.forward(feats, 3, 0, n_layers=2)
+    assert got.shape == (271, 512)
+    assert rel_err(got, want) < 2e-4
+
+
+def test_full_size_batch_properties(full_model):
+    """64 clips x 16 s: (1) deterministic, (2) batch-invariant bit-for-bit (clip c inside a batch of
+    64 == the same clip in a batch of 2: everything per-tensor is per clip), (3) ids are the
+    argmax of the logits, (4) host-buffer path == device path."""
+    blob, m = full_model
+    pcm = synth_batch(0, 64, 256000)
+    ids64 = m.transcribe(pcm)
+    assert ids64.shape == (64, 271)
+    np.testing.assert_array_equal(ids64, m.transcribe(pcm))
+    ids2, logits2 = m.transcribe(pcm[[7, 63]], want_logits=True)
+    np.testing.assert_array_equal(ids2[0], ids64[7]); np.testing.assert_array_equal(ids2[1], ids64[63])
+    np.testing.assert_array_equal(ids2, logits2.shape[2] - 1 - np.argmax(logits2[:, :, ::-1], axis=2))
+    assert np.isfinite(logits2).all() and len(np.unique(ids64)) > 10
