@@ -224,6 +224,11 @@ int lele_b200_sensevoice_transcribe_host(lele_b200_ctx* ctx, lele_b200_sensevoic
  * lele_b200_sensevoice_set_profiling(m, 1) was called before the forward (events are recorded
  * around every launch; not for timed runs). */
 int lele_b200_sensevoice_set_profiling(lele_b200_sensevoice* m, int enable);
+/* Borrow of a workspace buffer after a forward (the analogue of forward_with_workspace returning
+ * borrows of ws.buf_N, src/compiler/mod.rs:1269-1351).  name: "lfr","feats","x0","x","h","qkv",
+ * "fsmn","att","f1","keys".  *dptr is a device pointer valid until the next forward. */
+int lele_b200_sensevoice_workspace(lele_b200_sensevoice* m, const char* name, void** dptr,
+                                   size_t* nbytes);
 int lele_b200_sensevoice_last_profile(lele_b200_sensevoice* m, const char** names_host,
                                       float* ms_host, int* calls_host, int cap, int* n_out);
 

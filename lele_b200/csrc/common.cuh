@@ -89,6 +89,29 @@ __device__ __forceinline__ int lb_warp_sum_i(int v) {
     return v;
 }
 
+// Row reduction in the summation order of lele's AVX2 row kernels (avx/norm.rs:28-82 LayerNorm,
+// :169-205 softmax): four 8-lane accumulators over 32-element blocks (= one partial per warp
+// lane, element j -> lane j%32), merged (s0+s1)+(s2+s3), then the remaining 8-blocks into the
+// merged vector, the horizontal add ((v0+v4)+(v2+v6))+((v1+v5)+(v3+v7)), then the n%8 scalar
+// tail.  A warp reproduces that order exactly, so LayerNorm statistics / softmax sums -- and the
+// dynamic-quantisation min/max derived from them -- are bit-identical to the x86 reference order.
+// step_vec(acc, j) / step_tail(acc, j) fold element j into acc.  Result broadcast to all lanes.
+template <class SV, class ST>
+__device__ __forceinline__ float lb_avx_order_reduce(int n, int lane, SV step_vec, ST step_tail) {
+    float p = 0.0f;
+    const int n32 = n & ~31, n8 = n & ~7;
+    for (int j = lane; j < n32; j += 32) p = step_vec(p, j);
+    p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 8));
+    p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 16));
+    for (int j = n32 + (lane & 7); j < n8; j += 8) p = step_vec(p, j);
+    p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 4));
+    p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 2));
+    p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 1));
+    p = __shfl_sync(0xffffffffu, p, 0);
+    for (int j = n8; j < n; ++j) p = step_tail(p, j);
+    return p;
+}
+
 // order-preserving float <-> uint key, so per-clip min/max can use integer atomics
 __device__ __forceinline__ unsigned lb_fkey(float f) {
     unsigned b = __float_as_uint(f);

@@ -2,11 +2,13 @@
 // HBM-bound row kernels: one warp per row, 128-bit loads, warp-shuffle reductions.
 #include "common.cuh"
 
-// LayerNorm: mean = sum*(1/n); var = sumsq*(1/n) - mean^2 (not clamped); inv = 1/sqrt(var+eps);
-// y = fma((x-mean)*inv, gamma, beta) on the x86 SIMD body (first n/8*8 columns), plain
-// mul+add on the scalar tail (avx/norm.rs:84-133).  Optional fused per-slice min/max of the
-// output (keys, see common.cuh) feeds the dynamic quantiser of the next int8 linear.
-template <int kMaxVec>  // row cached in registers when n <= kMaxVec*128 and n % 4 == 0
+// LayerNorm (norm.rs:226 -> avx/norm.rs:10-133): mean = sum*(1/n); var = sumsq*(1/n) - mean^2 (not
+// clamped); inv = 1/sqrt(var+eps); y = fma((x-mean)*inv, gamma, beta) on the SIMD body (first
+// n/8*8 columns), plain mul+add on the scalar tail.  Sum / sum-of-squares follow the AVX2
+// accumulator order exactly (lb_avx_order_reduce), so the result is bit-identical to the x86
+// reference arithmetic.  One warp per row, coalesced 128-byte warp loads (element j -> lane j%32);
+// the second pass re-reads the row from L1/L2.  Optional fused per-slice min/max of the output
+// (order-preserving keys) feeds the dynamic quantiser of the next int8 linear.
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   long long outer, int n, float eps, float* __restrict__ out,
@@ -18,58 +20,20 @@ layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
     float* o = out + row * n;
     const float inv_n = __fdiv_rn(1.0f, (float)n);
     const int simd_end = (n / 8) * 8;
+    const float s = lb_avx_order_reduce(n, lane, [&](float acc, int j) { return __fadd_rn(acc, xr[j]); },
+                                        [&](float acc, int j) { return __fadd_rn(acc, xr[j]); });
+    const float sq = lb_avx_order_reduce(n, lane, [&](float acc, int j) { float t = xr[j]; return __fmaf_rn(t, t, acc); },
+                                         [&](float acc, int j) { float t = xr[j]; return __fadd_rn(acc, __fmul_rn(t, t)); });
+    const float mean = __fmul_rn(s, inv_n);
+    const float var = __fsub_rn(__fmul_rn(sq, inv_n), __fmul_rn(mean, mean));
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
     float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
-    const bool vec = kMaxVec > 0 && (n % 4 == 0) && n <= kMaxVec * 128 &&
-                     ((((uintptr_t)xr | (uintptr_t)o | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0);
-    if (vec) {
-        float4 v[kMaxVec > 0 ? kMaxVec : 1];
-        const int nv = n >> 2;
-        float s = 0.0f, sq = 0.0f;
-#pragma unroll
-        for (int i = 0; i < kMaxVec; ++i) {
-            int c = lane + 32 * i;
-            if (c < nv) {
-                v[i] = __ldg(reinterpret_cast<const float4*>(xr) + c);
-                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-                sq = fmaf(v[i].x, v[i].x, sq); sq = fmaf(v[i].y, v[i].y, sq);
-                sq = fmaf(v[i].z, v[i].z, sq); sq = fmaf(v[i].w, v[i].w, sq);
-            }
-        }
-        s = lb_warp_sum(s); sq = lb_warp_sum(sq);
-        const float mean = __fmul_rn(s, inv_n);
-        const float var = __fsub_rn(__fmul_rn(sq, inv_n), __fmul_rn(mean, mean));
-        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
-#pragma unroll
-        for (int i = 0; i < kMaxVec; ++i) {
-            int c = lane + 32 * i;
-            if (c < nv) {
-                float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-                float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
-                float in[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-                float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w}, r[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float sc = __fmul_rn(__fsub_rn(in[q], mean), inv);
-                    r[q] = (4 * c + q) < simd_end ? __fmaf_rn(sc, gg[q], bb[q]) : __fadd_rn(__fmul_rn(sc, gg[q]), bb[q]);
-                    vmin = fminf(vmin, r[q]); vmax = fmaxf(vmax, r[q]);
-                }
-                reinterpret_cast<float4*>(o)[c] = make_float4(r[0], r[1], r[2], r[3]);
-            }
-        }
-    } else {
-        float s = 0.0f, sq = 0.0f;
-        for (int j = lane; j < n; j += 32) { float t = xr[j]; s += t; sq = fmaf(t, t, sq); }
-        s = lb_warp_sum(s); sq = lb_warp_sum(sq);
-        const float mean = __fmul_rn(s, inv_n);
-        const float var = __fsub_rn(__fmul_rn(sq, inv_n), __fmul_rn(mean, mean));
-        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
-        for (int j = lane; j < n; j += 32) {
-            float g = gamma ? gamma[j] : 1.0f, b = beta ? beta[j] : 0.0f;
-            float sc = __fmul_rn(__fsub_rn(xr[j], mean), inv);
-            float r = j < simd_end ? __fmaf_rn(sc, g, b) : __fadd_rn(__fmul_rn(sc, g), b);
-            vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
-            o[j] = r;
-        }
+    for (int j = lane; j < n; j += 32) {
+        float g = gamma ? gamma[j] : 1.0f, b = beta ? beta[j] : 0.0f;
+        float sc = __fmul_rn(__fsub_rn(xr[j], mean), inv);
+        float r = j < simd_end ? __fmaf_rn(sc, g, b) : __fadd_rn(__fmul_rn(sc, g), b);
+        vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
+        o[j] = r;
     }
     if (minmax_keys) {
         vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
@@ -85,11 +49,7 @@ int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma,
                          int n, float eps, float* out, unsigned* minmax_keys, int rows_per_slice) {
     if (outer == 0) return LELE_B200_OK;
     const int warps = 8;
-    int grid = lb_ceil_div(outer, warps);
-    if (gamma && beta && n % 4 == 0 && n <= 8 * 128)
-        layer_norm_kernel<8><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
-    else
-        layer_norm_kernel<0><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
+    layer_norm_kernel<<<lb_ceil_div(outer, warps), warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }
@@ -114,14 +74,14 @@ softmax_kernel(const float* __restrict__ x, long long outer, int n, float* __res
     float mx = -3.402823466e+38f;
     for (int j = lane; j < n; j += 32) mx = fmaxf(mx, xr[j]);
     mx = lb_warp_max(mx);
-    float sum = 0.0f;
     for (int j = lane; j < n; j += 32) {
         float d = __fsub_rn(xr[j], mx);
-        float e = j < simd_end ? lb_cephes_expf(d) : expf(d);
-        o[j] = e;
-        sum += e;
+        o[j] = j < simd_end ? lb_cephes_expf(d) : expf(d);
     }
-    sum = lb_warp_sum(sum);
+    __syncwarp();
+    // sum in the AVX2 accumulator order (avx/norm.rs:169-205)
+    const float sum = lb_avx_order_reduce(n, lane, [&](float acc, int j) { return __fadd_rn(acc, o[j]); },
+                                          [&](float acc, int j) { return __fadd_rn(acc, o[j]); });
     const float inv = __fdiv_rn(1.0f, sum);
     for (int j = lane; j < n; j += 32) o[j] = __fmul_rn(o[j], inv);
 }

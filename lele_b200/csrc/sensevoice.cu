@@ -86,13 +86,13 @@ softmax_rows_kernel(float* __restrict__ s, long long rows, int n) {
     float mx = -3.402823466e+38f;
     for (int j = lane; j < n; j += 32) mx = fmaxf(mx, xr[j]);
     mx = lb_warp_max(mx);
-    float sum = 0.0f;
     for (int j = lane; j < n; j += 32) {
         float dlt = __fsub_rn(xr[j], mx);
-        float e = j < simd_end ? lb_cephes_expf(dlt) : expf(dlt);
-        xr[j] = e; sum += e;
+        xr[j] = j < simd_end ? lb_cephes_expf(dlt) : expf(dlt);
     }
-    sum = lb_warp_sum(sum);
+    __syncwarp();
+    const float sum = lb_avx_order_reduce(n, lane, [&](float acc, int j) { return __fadd_rn(acc, xr[j]); },
+                                          [&](float acc, int j) { return __fadd_rn(acc, xr[j]); });
     const float inv = __fdiv_rn(1.0f, sum);
     for (int j = lane; j < n; j += 32) xr[j] = __fmul_rn(xr[j], inv);
 }
@@ -391,6 +391,22 @@ extern "C" int lele_b200_sensevoice_transcribe_host(lele_b200_ctx* ctx, lele_b20
     LB_CHECK_CUDA(cudaMemcpyAsync(ids_host, m->ids_stage, sizeof(int32_t) * (size_t)n_clips * T, cudaMemcpyDeviceToHost, ctx->stream));
     LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_workspace(lele_b200_sensevoice* m, const char* name, void** dptr, size_t* nbytes) {
+    LB_REQUIRE(m && name && dptr && nbytes, "sensevoice_workspace: NULL argument");
+    const size_t B = m->max_clips, M = B * m->max_T;
+    const int wide = m->d_in > m->d ? m->d_in : m->d;
+    const int t = m->max_T - 4;
+    struct { const char* n; void* p; size_t b; } tab[] = {
+        {"lfr", m->lfr, sizeof(float) * B * t * m->d_in}, {"feats", m->feats, sizeof(float) * B * t * m->d_in},
+        {"x0", m->x0, sizeof(float) * M * m->d_in}, {"x", m->x, sizeof(float) * M * m->d}, {"h", m->h, sizeof(float) * M * wide},
+        {"qkv", m->qkv, sizeof(float) * M * 3 * m->d}, {"fsmn", m->fsmn, sizeof(float) * M * m->d}, {"att", m->att, sizeof(float) * M * m->d},
+        {"f1", m->f1, sizeof(float) * M * m->ffn}, {"keys", m->keys, sizeof(unsigned) * 2 * B * ((size_t)m->n_layers * 4 + 1)}};
+    for (auto& e : tab)
+        if (strcmp(e.n, name) == 0) { *dptr = e.p; *nbytes = e.b; return LELE_B200_OK; }
+    lb_set_error("sensevoice_workspace: unknown buffer '%s'", name);
+    return LELE_B200_ERR_ARG;
 }
 
 extern "C" int lele_b200_sensevoice_set_profiling(lele_b200_sensevoice* m, int enable) {

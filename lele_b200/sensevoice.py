@@ -99,6 +99,19 @@ class SenseVoice:
             q.free()
         return (idh[0], lgh[0]) if single else (idh, lgh)
 
+    def workspace(self, name: str, shape, dtype=np.float32) -> np.ndarray:
+        """Host copy of the leading `shape` elements of a workspace buffer after a forward
+        (forward_with_workspace-style borrow; used by tests to localise divergences)."""
+        p = vp(); nb = sz(0)
+        call("lele_b200_sensevoice_workspace", self.h, name.encode(), C.byref(p), C.byref(nb))
+        out = np.empty(shape, dtype=dtype)
+        if out.nbytes > nb.value:
+            raise LeleB200Error(f"workspace {name}: {out.nbytes} bytes requested, buffer holds {nb.value}")
+        self.ctx.sync()
+        call("lele_b200_d2h", self.ctx.h, out.ctypes.data_as(vp), p, sz(out.nbytes))
+        self.ctx.sync()
+        return out
+
     # ---- profiling (kernels/timing.rs analogue) ----
     def set_profiling(self, on: bool):
         call("lele_b200_sensevoice_set_profiling", self.h, i32(int(on)))

@@ -357,8 +357,9 @@ static void lo_sgemm_acc(const float *a, long rsa, long csa, const float *b, lon
             float av = alpha * a[i * rsa + kk * csa];
             const float *br = b + kk * rsb;
             float *cr = c + (size_t)i * n;
-            if (csb == 1) for (int j = 0; j < n; ++j) cr[j] += av * br[j];
-            else for (int j = 0; j < n; ++j) cr[j] += av * br[j * csb];
+            /* sequential-k FMA chain per output (x86 GEMM micro-kernels are FMA based) */
+            if (csb == 1) for (int j = 0; j < n; ++j) cr[j] = fmaf(av, br[j], cr[j]);
+            else for (int j = 0; j < n; ++j) cr[j] = fmaf(av, br[j * csb], cr[j]);
         }
 }
 
@@ -477,6 +478,24 @@ void lo_unary(int op, const float *x, size_t len, float *out) {
  * (not clamped), inv = 1/sqrt(var+eps), y = fma((x-mean)*inv, gamma, beta) in the SIMD
  * body (first n/8*8 of each row), plain mul+add in the scalar tail.  The SIMD lanes'
  * partial-sum order is not reproduced (sequential sum here). */
+/* Row reduction in the exact order of the AVX2 kernels (avx/norm.rs:28-82, :169-205): four
+ * 8-lane accumulators over 32-element blocks, merged (s0+s1)+(s2+s3); remaining 8-blocks added
+ * to the merged vector; horizontal ((v0+v4)+(v2+v6))+((v1+v5)+(v3+v7)); scalar tail.
+ * sq != 0: accumulate x*x (FMA in the vector part, mul+add in the tail). */
+static float lo_avx_row_sum(const float *x, int n, int sq) {
+    float p[32], v[8];
+    int j = 0;
+    for (int i = 0; i < 32; ++i) p[i] = 0.0f;
+    for (; j + 32 <= n; j += 32)
+        for (int i = 0; i < 32; ++i) p[i] = sq ? fmaf(x[j + i], x[j + i], p[i]) : p[i] + x[j + i];
+    for (int l = 0; l < 8; ++l) v[l] = (p[l] + p[8 + l]) + (p[16 + l] + p[24 + l]);
+    for (; j + 8 <= n; j += 8)
+        for (int l = 0; l < 8; ++l) v[l] = sq ? fmaf(x[j + l], x[j + l], v[l]) : v[l] + x[j + l];
+    float s = ((v[0] + v[4]) + (v[2] + v[6])) + ((v[1] + v[5]) + (v[3] + v[7]));
+    for (; j < n; ++j) s = sq ? s + x[j] * x[j] : s + x[j];
+    return s;
+}
+
 void lo_layer_norm(const float *x, const float *gamma, const float *beta, int outer, int n,
                    float eps, float *out) {
     float inv_n = 1.0f / (float)n;
@@ -484,8 +503,7 @@ void lo_layer_norm(const float *x, const float *gamma, const float *beta, int ou
     for (int r = 0; r < outer; ++r) {
         const float *xr = x + (size_t)r * n;
         float *o = out + (size_t)r * n;
-        float sum = 0.0f, sq = 0.0f;
-        for (int j = 0; j < n; ++j) { sum += xr[j]; sq = j < simd_end ? fmaf(xr[j], xr[j], sq) : sq + xr[j] * xr[j]; }
+        float sum = lo_avx_row_sum(xr, n, 0), sq = lo_avx_row_sum(xr, n, 1);
         float mean = sum * inv_n;
         float var = sq * inv_n - mean * mean;
         float inv = 1.0f / sqrtf(var + eps);
@@ -506,12 +524,8 @@ void lo_softmax(const float *x, int outer, int n, float *out) {
         float *o = out + (size_t)r * n;
         float mx = -3.402823466e+38f;
         for (int j = 0; j < n; ++j) if (xr[j] > mx) mx = xr[j];
-        float sum = 0.0f;
-        for (int j = 0; j < n; ++j) {
-            float e = j < simd_end ? lo_cephes_expf(xr[j] - mx) : expf(xr[j] - mx);
-            o[j] = e;
-            sum += e;
-        }
+        for (int j = 0; j < n; ++j) o[j] = j < simd_end ? lo_cephes_expf(xr[j] - mx) : expf(xr[j] - mx);
+        float sum = lo_avx_row_sum(o, n, 0); /* 4x8-lane accumulators, hsum_ps, scalar tail */
         float inv = 1.0f / sum;
         for (int j = 0; j < n; ++j) o[j] *= inv;
     }

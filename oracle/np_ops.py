@@ -168,7 +168,7 @@ def clip(x, lo, hi): return np.minimum(np.maximum(_a(x), f32(lo)), f32(hi))  # m
 
 
 def mod_f32(a, b):  # math.rs:1163-1192 : a - b*floor(a/b), 0 when b == 0
-    a, b = _a(a), np.broadcast_to(_a(b), np.shape(a))
+    a, b = np.broadcast_arrays(_a(a), _a(b))
     with np.errstate(divide="ignore", invalid="ignore"):
         r = a - b * np.floor(a / b)
     return np.where(b == 0, f32(0), r).astype(np.float32)
