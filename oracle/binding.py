@@ -12,13 +12,26 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "liblele_oracle.so")
+
+
+def _host_tag() -> str:
+    """-march=native binaries are host specific: key the .so by the CPU's ISA flags so a box with a
+    different CPU (the GPU box) rebuilds instead of executing foreign instructions."""
+    import hashlib
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except Exception:
+        flags = "unknown"
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+_SO = os.path.join(_HERE, f"liblele_oracle_{_host_tag()}.so")
 
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("lele_oracle.c", "sensevoice_ref.c", "lele_oracle.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", f"OUT={os.path.basename(_SO)}"])
     return _SO
 
 

@@ -299,18 +299,23 @@ void lo_mat_mul_integer(const float *a, const float *b, int batch, int m, int k,
 /* quantization.rs:77-169 -> avx/quantization.rs:225-330 (+ epilogue :1396-1428):
  * per [m,k] slice: min/max -> u8 + row sums (row tail k%8 takes the scalar rounding),
  * exact integer GEMM, y = f32(acc) * (dyn_scale*w_scale[j]) + bias[j], optional ReLU. */
-void lo_fused_quantized_linear(const float *x, int batch, int m, int k, int n, const uint8_t *w,
-                               const float *w_scale, int w_scale_len, int w_zp,
-                               const float *bias, int relu, float *out) {
-    uint8_t *aq = malloc((size_t)m * k);
-    uint8_t *wt = malloc((size_t)n * k); /* [n,k] so the inner dot is contiguous */
-    int32_t *colsum = malloc(sizeof(int32_t) * (size_t)n);
-    float *cs = malloc(sizeof(float) * (size_t)(w_scale_len > 1 ? w_scale_len : 1));
+/* prepare_weights (quantization.rs:221-262): [k,n] u8 -> [n,k] + column sums (done once per weight,
+ * like the reference's B_WEIGHT_CACHE, avx/quantization.rs:47-95). */
+void lo_prepare_weights(const uint8_t *w, int k, int n, uint8_t *wt, int32_t *colsum) {
     for (int j = 0; j < n; ++j) {
         int32_t s = 0;
-        for (int kk = 0; kk < k; ++kk) { uint8_t v = w[(size_t)kk * n + j]; wt[(size_t)j * k + kk] = v; s += v; }
+        /* stored XOR 0x80 (= w - 128 as i8), the reference's VPMADDUBSW/VNNI form (avx/quantization.rs:926-936) */
+        for (int kk = 0; kk < k; ++kk) { uint8_t v = w[(size_t)kk * n + j]; wt[(size_t)j * k + kk] = v ^ 0x80; s += v; }
         colsum[j] = s;
     }
+}
+
+void lo_fused_quantized_linear_prepared(const float *x, int batch, int m, int k, int n, const uint8_t *wt,
+                                        const int32_t *colsum, const float *w_scale, int w_scale_len,
+                                        int w_zp, const float *bias, int relu, float *out) {
+    uint8_t *aq = malloc((size_t)m * k);
+    int32_t *rsum = malloc(sizeof(int32_t) * (size_t)m);
+    float *cs = malloc(sizeof(float) * (size_t)(w_scale_len > 1 ? w_scale_len : 1));
     int k_simd = (k / 8) * 8;
     for (int bi = 0; bi < batch; ++bi) {
         const float *xb = x + (size_t)bi * m * k;
@@ -327,22 +332,36 @@ void lo_fused_quantized_linear(const float *x, int batch, int m, int k, int n, c
                 aq[(size_t)i * k + kk] = qv;
                 rs += qv;
             }
-            const uint8_t *ar = aq + (size_t)i * k;
-            float *o = out + ((size_t)bi * m + i) * n;
-            for (int j = 0; j < n; ++j) {
-                const uint8_t *wr = wt + (size_t)j * k;
-                int32_t dot = 0;
+            rsum[i] = rs;
+        }
+        /* column-outer loop: one weight row stays in L1 while all activation rows stream from L2 */
+        for (int j = 0; j < n; ++j) {
+            const int8_t *wr = (const int8_t *)(wt + (size_t)j * k);
+            const float csj = cs[w_scale_len <= 1 ? 0 : j];
+            for (int i = 0; i < m; ++i) {
+                const uint8_t *ar = aq + (size_t)i * k;
+                int32_t dot = 0;   /* u8 x i8 dot: exact in i32 (auto-vectorises to VNNI vpdpbusd) */
                 for (int kk = 0; kk < k; ++kk) dot += (int32_t)ar[kk] * (int32_t)wr[kk];
-                /* sum (a-zpa)(w-zpw) = dot - zpw*rowsum - zpa*colsum + k*zpa*zpw */
-                int32_t acc = dot - w_zp * rs - zpa * colsum[j] + k * zpa * w_zp;
-                float v = (float)acc * cs[w_scale_len <= 1 ? 0 : j];
+                /* sum a*w = dot + 128*rowsum;  sum (a-zpa)(w-zpw) = sum a*w - zpw*rowsum - zpa*colsum + k*zpa*zpw */
+                int32_t acc = dot + (128 - w_zp) * rsum[i] - zpa * colsum[j] + k * zpa * w_zp;
+                float v = (float)acc * csj;
                 if (bias) v = v + bias[j];
                 if (relu && v < 0.0f) v = 0.0f;
-                o[j] = v;
+                out[((size_t)bi * m + i) * n + j] = v;
             }
         }
     }
-    free(aq); free(wt); free(colsum); free(cs);
+    free(aq); free(rsum); free(cs);
+}
+
+void lo_fused_quantized_linear(const float *x, int batch, int m, int k, int n, const uint8_t *w,
+                               const float *w_scale, int w_scale_len, int w_zp,
+                               const float *bias, int relu, float *out) {
+    uint8_t *wt = malloc((size_t)n * k); /* [n,k] so the inner dot is contiguous */
+    int32_t *colsum = malloc(sizeof(int32_t) * (size_t)n);
+    lo_prepare_weights(w, k, n, wt, colsum);
+    lo_fused_quantized_linear_prepared(x, batch, m, k, n, wt, colsum, w_scale, w_scale_len, w_zp, bias, relu, out);
+    free(wt); free(colsum);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -57,6 +57,12 @@ void lo_fused_quantized_linear(const float *x, int batch, int m, int k, int n, c
                                const float *w_scale, int w_scale_len, int w_zp,
                                const float *bias, int relu, float *out);
 
+/* prepared form (prepare_weights, quantization.rs:221): wt [n,k], colsum [n] */
+void lo_prepare_weights(const uint8_t *w, int k, int n, uint8_t *wt, int32_t *colsum);
+void lo_fused_quantized_linear_prepared(const float *x, int batch, int m, int k, int n, const uint8_t *wt,
+                                        const int32_t *colsum, const float *w_scale, int w_scale_len,
+                                        int w_zp, const float *bias, int relu, float *out);
+
 /* ---- f32 GEMM (src/kernels/gemm.rs; arithmetic delegated to faer 0.24 upstream) ---- */
 void lo_matmul(const float *a, const float *b, int batch_a, int batch_b, int m, int k, int n, float *out); /* gemm.rs:112 */
 void lo_matmul_fused_add(const float *a, const float *b, const float *bias, int bias_len,

@@ -32,33 +32,39 @@ def test_forward_features_matches_oracle_per_layer(small_model):
     ref = R.SenseVoiceRef(blob)
     rng = np.random.default_rng(0)
     feats = (rng.standard_normal((3, 40, 560)) * np.array([1.0, 2.5, 0.3])[:, None, None]).astype(np.float32)
-    for nl, tol in [(0, 1e-6), (1, 1e-4), (2, 2e-4), (-1, 5e-4)]:
+    for nl, tol in [(0, 1e-6), (1, 1e-5), (2, 1e-5), (-1, 1e-5)]:
         got = m.forward(feats, 3, 0, n_layers=nl)
         for c in range(3):
             want = ref.forward(feats[c], 3, 0, n_layers=nl)
             assert got[c].shape == want.shape
             e = rel_err(got[c], want)
-            # f32 ops are within 1e-4; a quantiser rounding flip (|x*inv+zp - n.5| ~ 1e-6) moves one
-            # u8 by 1 LSB, so deeper prefixes get a proportionally looser, still normwise, bound
+            # identical features in => integer core exact and identical f32 op order (LayerNorm / softmax in
+            # the AVX2 accumulator order, sequential-k FMA GEMMs): the encoder is bit-exact up to ~1 ulp
             assert e < tol, (nl, c, e)
 
 
 def test_pcm_to_ids_matches_oracle(small_model):
+    """End to end from PCM.  Dynamic int8 quantisation turns 1e-6-level feature differences into
+    1-LSB rounding flips, so PCM-level logits are compared the way the reference's own e2e test
+    does (examples/sensevoice/tests/e2e_test.rs:69: MAE <= 1.0, argmax agreement), while the strict
+    bars are applied per stage: front-end 1e-4, encoder on identical features ~bit-exact."""
     blob, m = small_model
     ref = R.SenseVoiceRef(blob)
     pcm = synth_batch(0, 2, 89472)
     ids, logits = m.transcribe(pcm, want_logits=True)
+    feats_gpu = m.workspace("feats", (2, 93, 560))
     ids_host_path = m.transcribe(pcm)                          # host-buffer entry, fused-argmax epilogue (no logits written)
     np.testing.assert_array_equal(ids, ids_host_path)
     for c in range(2):
-        rids, rlog = ref.pcm_to_ids(pcm[c], want_logits=True)
-        assert rel_err(logits[c], rlog) < 1e-3
-        # greedy ids agree wherever the oracle's top-2 margin exceeds the logit tolerance
-        top2 = np.sort(rlog, axis=1)[:, -2:]
-        safe = (top2[:, 1] - top2[:, 0]) > 2e-3 * np.abs(rlog).max()
-        assert safe.mean() > 0.5
-        np.testing.assert_array_equal(ids[c][safe], rids[safe])
-        # and the GPU ids are the LAST-max argmax of the GPU logits (tokenizer.rs:55)
+        feats_ref = R.cmvn(R.frontend(pcm[c]))
+        assert rel_err(feats_gpu[c], feats_ref) < 1e-4                      # stage 1: front-end + CMVN
+        rlog = ref.forward(feats_gpu[c], 3, 0)                              # stage 2: encoder on identical features
+        assert rel_err(logits[c], rlog) < 1e-5
+        np.testing.assert_array_equal(ids[c], rlog.shape[1] - 1 - np.argmax(rlog[:, ::-1], axis=1))
+        rids, rlog_pcm = ref.pcm_to_ids(pcm[c], want_logits=True)          # whole path on the CPU
+        assert float(np.abs(logits[c] - rlog_pcm).mean()) < 0.05           # reference's own bar is MAE <= 1.0
+        assert (ids[c] == rids).mean() > 0.8
+        # the GPU ids are the LAST-max argmax of the GPU logits (tokenizer.rs:55)
         np.testing.assert_array_equal(ids[c], logits[c].shape[1] - 1 - np.argmax(logits[c][:, ::-1], axis=1))
 
 
@@ -92,7 +98,7 @@ def test_full_size_first_layers_vs_oracle(full_model):
     got = m.forward(feats[None], 3, 0, n_layers=2)[0]
     want = ref.forward(feats, 3, 0, n_layers=2)
     assert got.shape == (271, 512)
-    assert rel_err(got, want) < 2e-4
+    assert rel_err(got, want) < 1e-5
 
 
 def test_full_size_batch_properties(full_model):
