@@ -28,7 +28,8 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_THREADS = 384;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 33 * 4;   // per-warp 32x33 f32 transpose tile
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int UMMA_K = 32;                           // bytes per tcgen05.mma for 8-bit operands
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -126,7 +127,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    float* epi_stage = (float*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
     uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -208,18 +210,24 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int rs = 0, zpa = 0; float sa = 0.0f;
             if (row_ok) { rs = __ldg(ep.rowsum + row); zpa = __ldg(ep.row_zp + row); sa = __ldg(ep.row_scale + row); }
             const int row_corr = args.K * zpa * ep.w_zp - ep.w_zp * rs;
-            float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
             unsigned long long best = 0ull;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            // The warp's 32 rows span at most two slices (rows_per_slice >= 32 in every caller; checked on the host).
+            const int first_row = m_blk * BM + quad * 32;
+            const int slice_a = ep.minmax_keys ? first_row / ep.rows_per_slice : 0;
+            float mnA = 3.402823466e+38f, mxA = -3.402823466e+38f, mnB = 3.402823466e+38f, mxB = -3.402823466e+38f;
+            float* stg = epi_stage + (size_t)ew * (32 * 33);
 #pragma unroll 1
             for (int chunk = 0; chunk < 4; ++chunk) {
                 const int col0 = half * 128 + chunk * 32;             // column inside the tile
                 const int gcol0 = n_blk * BN + col0;                  // global column
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), r);
-                if (row_ok && gcol0 < args.N) {
-                    float v[32];
+                if (gcol0 >= args.N) continue;                        // warp-uniform
+                // ---- phase 1 (thread = row): exact integer corrections + scale + bias + ReLU, staged to smem ----
+                {
+                    const int ncols = min(32, args.N - gcol0);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int4 cs = __ldg(reinterpret_cast<const int4*>(ep.colsum + gcol0) + q);
@@ -234,42 +242,45 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             float t = __fmul_rn((float)acci, __fmul_rn(sa, wsv[e]));
                             if (ep.has_bias) t = __fadd_rn(t, biv[e]);
                             if (ep.relu) t = fmaxf(t, 0.0f);
-                            v[q * 4 + e] = t;
-                        }
-                    }
-                    const long long obase = (long long)row * args.N + gcol0;
-                    const int ncols = min(32, args.N - gcol0);
-                    if (ep.add1) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) if (e < ncols) v[e] = __fadd_rn(v[e], __ldg(ep.add1 + obase + e));
-                    }
-                    if (ep.add2) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) if (e < ncols) v[e] = __fadd_rn(__ldg(ep.add2 + obase + e), v[e]);
-                    }
-                    if (ep.minmax_keys) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) if (e < ncols) { vmin = fminf(vmin, v[e]); vmax = fmaxf(vmax, v[e]); }
-                    }
-                    if (ep.argmax_keys) {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) if (e < ncols) {
-                            unsigned long long key = ((unsigned long long)lb_fkey(v[e]) << 32) | (unsigned)(gcol0 + e);
-                            best = key > best ? key : best;
-                        }
-                    }
-                    if (ep.out) {
-                        float* o = ep.out + obase;
-                        if (ncols == 32 && ((args.N & 3) == 0)) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) if (e < ncols) o[e] = v[e];
+                            stg[lane * 33 + q * 4 + e] = t;
+                            if (ep.argmax_keys && row_ok && (q * 4 + e) < ncols) {   // CTC head: no residual adds follow
+                                unsigned long long key = ((unsigned long long)lb_fkey(t) << 32) | (unsigned)(gcol0 + q * 4 + e);
+                                best = key > best ? key : best;
+                            }
                         }
                     }
                 }
+                __syncwarp();
+                // ---- phase 2 (lane = column): coalesced residual loads / stores, 128 B per warp instruction ----
+                {
+                    const int col = gcol0 + lane;
+                    const bool col_ok = col < args.N;
+                    const int nrows = min(32, args.M - first_row);
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        if (rr >= nrows) break;                       // warp-uniform
+                        float v = stg[rr * 33 + lane];
+                        const long long o = (long long)(first_row + rr) * args.N + col;
+                        if (col_ok) {
+                            if (ep.add1) v = __fadd_rn(v, __ldg(ep.add1 + o));
+                            if (ep.add2) v = __fadd_rn(__ldg(ep.add2 + o), v);
+                            if (ep.out) ep.out[o] = v;
+                            if (ep.minmax_keys && ep.rows_per_slice >= 32) {
+                                if ((first_row + rr) / ep.rows_per_slice == slice_a) { mnA = fminf(mnA, v); mxA = fmaxf(mxA, v); }
+                                else { mnB = fminf(mnB, v); mxB = fmaxf(mxB, v); }
+                            }
+                        }
+                        if (ep.minmax_keys && ep.rows_per_slice < 32) {   // tiny slices: one reduction per row
+                            float lo = col_ok ? v : 3.402823466e+38f, hi = col_ok ? v : -3.402823466e+38f;
+                            lo = lb_warp_min(lo); hi = lb_warp_max(hi);
+                            if (lane == 0) {
+                                const int sl = (first_row + rr) / ep.rows_per_slice;
+                                atomicMin(ep.minmax_keys + 2 * sl, lb_fkey(lo)); atomicMax(ep.minmax_keys + 2 * sl + 1, lb_fkey(hi));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
             }
             // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
             tc_fence_before();
@@ -277,22 +288,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-            if (ep.minmax_keys) {
-                const int first_row = m_blk * BM + quad * 32;
-                const int last_row = min(first_row + 31, args.M - 1);
-                if (first_row < args.M) {
-                    if (first_row / ep.rows_per_slice == last_row / ep.rows_per_slice) {
-                        vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
-                        if (lane == 0) {
-                            int sl = first_row / ep.rows_per_slice;
-                            atomicMin(ep.minmax_keys + 2 * sl, lb_fkey(vmin));
-                            atomicMax(ep.minmax_keys + 2 * sl + 1, lb_fkey(vmax));
-                        }
-                    } else if (row_ok && vmin <= vmax) {
-                        int sl = row / ep.rows_per_slice;
-                        atomicMin(ep.minmax_keys + 2 * sl, lb_fkey(vmin));
-                        atomicMax(ep.minmax_keys + 2 * sl + 1, lb_fkey(vmax));
-                    }
+            if (ep.minmax_keys && first_row < args.M) {
+                mnA = lb_warp_min(mnA); mxA = lb_warp_max(mxA); mnB = lb_warp_min(mnB); mxB = lb_warp_max(mxB);
+                if (lane == 0) {
+                    if (mnA <= mxA) { atomicMin(ep.minmax_keys + 2 * slice_a, lb_fkey(mnA)); atomicMax(ep.minmax_keys + 2 * slice_a + 1, lb_fkey(mxA)); }
+                    if (mnB <= mxB) { atomicMin(ep.minmax_keys + 2 * (slice_a + 1), lb_fkey(mnB)); atomicMax(ep.minmax_keys + 2 * (slice_a + 1) + 1, lb_fkey(mxB)); }
                 }
             }
             if (ep.argmax_keys && row_ok && best != 0ull) atomicMax(ep.argmax_keys + row, best);
@@ -344,6 +344,8 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     LB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_i8_tc: empty problem");
     LB_REQUIRE(K % 16 == 0, "gemm_i8_tc: K=%d must be a multiple of 16 (TMA row pitch)", K);
     LB_REQUIRE((((uintptr_t)A | (uintptr_t)Wt) & 15) == 0, "gemm_i8_tc: operands must be 16-byte aligned");
+    LB_REQUIRE(!ep.minmax_keys || ep.rows_per_slice >= 1, "gemm_i8_tc: fused min/max needs rows_per_slice >= 1");
+    LB_REQUIRE(!ep.argmax_keys || (!ep.add1 && !ep.add2), "gemm_i8_tc: fused arg-max cannot be combined with residual adds");
     CUtensorMap ta, tb;
     int rc = make_tmap_u8(&ta, A, M, K, BM);
     if (rc) return rc;

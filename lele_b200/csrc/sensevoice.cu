@@ -67,6 +67,41 @@ fsmn_kernel(const float* __restrict__ qkv, const float* __restrict__ w /*[d,1,k]
     }
 }
 
+// Fast path: one thread per channel walks FS_TCH consecutive time steps with the K-tap window in
+// registers (one strided-but-coalesced load per output instead of K), no index divisions.
+// grid (d/128, ceil(T/FS_TCH), B).  Same tap order and unfused mul+add as fsmn_kernel.
+constexpr int FS_TCH = 16;
+template <int K>
+__global__ void __launch_bounds__(128)
+fsmn_window_kernel(const float* __restrict__ qkv, const float* __restrict__ w, int T, int d, float* __restrict__ out) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= d) return;
+    constexpr int PAD = (K - 1) / 2;
+    const int t0 = blockIdx.y * FS_TCH, b = blockIdx.z;
+    const float* vb = qkv + ((long long)b * T) * 3 * d + 2 * d + c;
+    float wk[K], win[FS_TCH + K - 1];
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) wk[kk] = __ldg(w + (long long)c * K + kk);
+#pragma unroll
+    for (int i = 0; i < FS_TCH + K - 1; ++i) {
+        int pos = t0 + i - PAD;
+        win[i] = (pos >= 0 && pos < T) ? vb[(long long)pos * 3 * d] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < FS_TCH; ++i) {
+        const int tt = t0 + i;
+        if (tt < T) {
+            float s = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                int pos = tt + kk - PAD;
+                if (pos >= 0 && pos < T) s = __fadd_rn(s, __fmul_rn(wk[kk], win[i + kk]));
+            }
+            out[((long long)b * T + tt) * d + c] = __fadd_rn(s, win[i + PAD]);
+        }
+    }
+}
+
 __global__ void scale_copy_q_kernel(const float* __restrict__ qkv, long long M, int d, float qscale, float* __restrict__ q) {
     const long long total = M * d;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -279,7 +314,11 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         }
         {
             ProfScope ps(m, ctx, P_FSMN);
-            fsmn_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), B, T, d, m->fsmn_k, m->fsmn);
+            if (m->fsmn_k == 11)
+                fsmn_window_kernel<11><<<dim3(lb_ceil_div(d, 128), lb_ceil_div(T, FS_TCH), B), 128, 0, ctx->stream>>>(
+                    m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), T, d, m->fsmn);
+            else
+                fsmn_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), B, T, d, m->fsmn_k, m->fsmn);
             LB_LAUNCH_CHECK(ctx);
             scale_copy_q_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, M, d, qscale, m->qs);
             LB_LAUNCH_CHECK(ctx);

@@ -52,12 +52,13 @@ def test_pcm_to_ids_matches_oracle(small_model):
     ref = R.SenseVoiceRef(blob)
     pcm = synth_batch(0, 2, 89472)
     ids, logits = m.transcribe(pcm, want_logits=True)
+    lfr_gpu = m.workspace("lfr", (2, 93, 560))
     feats_gpu = m.workspace("feats", (2, 93, 560))
     ids_host_path = m.transcribe(pcm)                          # host-buffer entry, fused-argmax epilogue (no logits written)
     np.testing.assert_array_equal(ids, ids_host_path)
     for c in range(2):
-        feats_ref = R.cmvn(R.frontend(pcm[c]))
-        assert rel_err(feats_gpu[c], feats_ref) < 1e-4                      # stage 1: front-end + CMVN
+        assert rel_err(lfr_gpu[c], R.frontend(pcm[c])) < 1e-4               # stage 1a: fbank + LFR
+        assert rel_err(feats_gpu[c], R.cmvn(lfr_gpu[c])) < 1e-4             # stage 1b: CMVN on identical input (1/std amplifies, so not chained)
         rlog = ref.forward(feats_gpu[c], 3, 0)                              # stage 2: encoder on identical features
         assert rel_err(logits[c], rlog) < 1e-5
         np.testing.assert_array_equal(ids[c], rlog.shape[1] - 1 - np.argmax(rlog[:, ::-1], axis=1))
