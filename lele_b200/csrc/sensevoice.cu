@@ -12,6 +12,7 @@
 // the CUDA kernels of this directory.
 #include "gemm_i8_tc.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 // ---- internal entry points from the other translation units ----
 int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n,
@@ -20,6 +21,10 @@ int lb_sgemm_strided_ldc(lele_b200_ctx* ctx, const float* A, long long rsa, long
                          long long rsb, long long csb, long long bsb, float* C, long long bsc, long long ldc, int batch, int m,
                          int k, int n, float alpha);
 int lb_argmax_keys_to_ids(lele_b200_ctx* ctx, const unsigned long long* keys, long long n, int32_t* out);
+bool lb_attention_tc_supported(int T, int d, int H);
+size_t lb_attention_tc_scratch_bytes(int B, int T, int d, int H);
+int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, int H, float qscale, void* scratch, float* att,
+                    unsigned* minmax_keys);
 
 namespace {
 enum { SV_G_EMBED = 0, SV_G_POS, SV_G_AFTER_G, SV_G_AFTER_B, SV_G_TP_G, SV_G_TP_B, SV_G_CTC_W, SV_G_CTC_SCALE, SV_G_CTC_BIAS,
@@ -29,9 +34,10 @@ enum { SV_L_LN1_G = 0, SV_L_LN1_B, SV_L_QKV_W, SV_L_QKV_SCALE, SV_L_QKV_BIAS, SV
        SV_L_FFN2_SCALE, SV_L_FFN2_BIAS, SV_L_FFN2_ZP, SV_NUM_LAYER };
 
 enum ProfClass { P_FRONTEND = 0, P_CMVN, P_PREP, P_LAYERNORM, P_QUANTIZE, P_GEMM_I8, P_FSMN, P_ATTN_QK, P_SOFTMAX, P_ATTN_PV,
-                 P_MINMAX, P_ARGMAX, P_MISC, P_NUM };
+                 P_MINMAX, P_ARGMAX, P_MISC, P_ATTN_TC, P_NUM };
 const char* kProfNames[P_NUM] = {"frontend_fbank_lfr", "cmvn", "prompt_scale_pos", "layer_norm", "quantize_rows", "gemm_i8_tcgen05",
-                                 "fsmn_dwconv", "attn_qk_sgemm", "softmax", "attn_pv_sgemm", "slice_minmax", "argmax", "misc"};
+                                 "fsmn_dwconv", "attn_qk_sgemm", "softmax", "attn_pv_sgemm", "slice_minmax", "argmax", "misc",
+                                 "attn_tcgen05_tf32x3"};
 
 // x0[b, r, :] = (r < 4 ? embed[id_r] : feats[b, r-4]) * sqrt(d) + pos[r]
 __global__ void prompt_scale_pos_kernel(const float* __restrict__ feats, const float* __restrict__ embed, const float* __restrict__ pos,
@@ -152,6 +158,8 @@ struct lele_b200_sensevoice {
     unsigned* keys = nullptr;
     unsigned long long* amax_keys = nullptr;
     void* qscratch = nullptr;
+    void* attn_scratch = nullptr;
+    int attn_simt = 0;   // LELE_B200_ATTN_SIMT=1: CUDA-core attention (cross-check of the tcgen05 path)
     // profiling
     int profiling = 0;
     std::vector<cudaEvent_t> ev_pool;
@@ -257,6 +265,8 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * B * ((size_t)m->n_layers * 4 + 1));
     if (!rc) rc = sv_alloc((void**)&m->amax_keys, sizeof(unsigned long long) * M);
     if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax));
+    if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
+    { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
     if (!rc) rc = sv_alloc((void**)&m->pcm_stage, sizeof(float) * B * (size_t)max_samples);
     if (!rc) rc = sv_alloc((void**)&m->ids_stage, sizeof(int32_t) * M);
     if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
@@ -269,7 +279,7 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (auto* q : m->lin) lele_b200_qweights_destroy(nullptr, q);
     void* bufs[] = {m->lfr, m->feats, m->x0, m->x, m->h, m->qkv, m->qs, m->fsmn, m->att, m->f1, m->scores, m->keys, m->amax_keys,
-                    m->qscratch, m->pcm_stage, m->ids_stage};
+                    m->qscratch, m->pcm_stage, m->ids_stage, m->attn_scratch};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : m->ev_pool) cudaEventDestroy(e);
     delete m;
@@ -320,25 +330,33 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             else
                 fsmn_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), B, T, d, m->fsmn_k, m->fsmn);
             LB_LAUNCH_CHECK(ctx);
-            scale_copy_q_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, M, d, qscale, m->qs);
-            LB_LAUNCH_CHECK(ctx);
         }
-        for (int hd = 0; hd < H; ++hd) {   // scores[b,hd] = (q*scale) k^T
-            SV_RUN(P_ATTN_QK, lb_sgemm_strided_ldc(ctx, m->qs + hd * dk, d, 1, (long long)T * d,
-                                                   m->qkv + d + hd * dk, 1, 3 * d, (long long)T * 3 * d,
-                                                   m->scores + (long long)hd * T * T, (long long)H * T * T, T, B, T, dk, T, 1.0f));
+        if (!m->attn_simt && lb_attention_tc_supported(T, d, H)) {
+            // fused tcgen05 attention (3xTF32), per-clip min/max of the output fused in its epilogue
+            SV_RUN(P_ATTN_TC, lb_attention_tc(ctx, m->qkv, B, T, d, H, qscale, m->attn_scratch, m->att, site(l * 4 + 1)));
+        } else {
+            {
+                ProfScope ps(m, ctx, P_FSMN);
+                scale_copy_q_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, M, d, qscale, m->qs);
+                LB_LAUNCH_CHECK(ctx);
+            }
+            for (int hd = 0; hd < H; ++hd) {   // scores[b,hd] = (q*scale) k^T
+                SV_RUN(P_ATTN_QK, lb_sgemm_strided_ldc(ctx, m->qs + hd * dk, d, 1, (long long)T * d,
+                                                       m->qkv + d + hd * dk, 1, 3 * d, (long long)T * 3 * d,
+                                                       m->scores + (long long)hd * T * T, (long long)H * T * T, T, B, T, dk, T, 1.0f));
+            }
+            {
+                ProfScope ps(m, ctx, P_SOFTMAX);
+                softmax_rows_kernel<<<lb_ceil_div((long long)B * H * T, 8), 256, 0, ctx->stream>>>(m->scores, (long long)B * H * T, T);
+                LB_LAUNCH_CHECK(ctx);
+            }
+            for (int hd = 0; hd < H; ++hd) {   // att[b, :, hd*dk:(hd+1)*dk] = P v
+                SV_RUN(P_ATTN_PV, lb_sgemm_strided_ldc(ctx, m->scores + (long long)hd * T * T, T, 1, (long long)H * T * T,
+                                                       m->qkv + 2 * d + hd * dk, 3 * d, 1, (long long)T * 3 * d,
+                                                       m->att + hd * dk, (long long)T * d, d, B, T, T, dk, 1.0f));
+            }
+            SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->att, B, (long long)T * d, site(l * 4 + 1)));
         }
-        {
-            ProfScope ps(m, ctx, P_SOFTMAX);
-            softmax_rows_kernel<<<lb_ceil_div((long long)B * H * T, 8), 256, 0, ctx->stream>>>(m->scores, (long long)B * H * T, T);
-            LB_LAUNCH_CHECK(ctx);
-        }
-        for (int hd = 0; hd < H; ++hd) {   // att[b, :, hd*dk:(hd+1)*dk] = P v
-            SV_RUN(P_ATTN_PV, lb_sgemm_strided_ldc(ctx, m->scores + (long long)hd * T * T, T, 1, (long long)H * T * T,
-                                                   m->qkv + 2 * d + hd * dk, 3 * d, 1, (long long)T * 3 * d,
-                                                   m->att + hd * dk, (long long)T * d, d, B, T, T, dk, 1.0f));
-        }
-        SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->att, B, (long long)T * d, site(l * 4 + 1)));
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->x; ep.rows_per_slice = T; ep.add1 = m->fsmn; ep.add2 = (cur == d) ? xin : nullptr;   // x = x + (lin + fsmn)
