@@ -21,15 +21,16 @@
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 128;          // BK in bytes == elements (u8)
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK;               // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK;               // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 384;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;   // 640
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 33 * 4;   // per-warp 32x33 f32 transpose tile
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_WARP_BYTES = 32 * 33 * 4 + 3 * 64 * 4;      // 32x33 f32 transpose tile + colsum/w_scale/bias of 64 columns
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int UMMA_K = 32;                           // bytes per tcgen05.mma for 8-bit operands
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -120,15 +121,27 @@ struct KernelArgs {
     LbI8Epilogue ep;
 };
 
+// Epilogue specialisations (compile-time, so the inner loops carry no uniform branches)
+enum EpiMode { EPI_PLAIN = 0, EPI_MINMAX, EPI_ARGMAX, EPI_R1, EPI_R2, EPI_R12 };
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ int4 lds_v4(uint32_t addr) {
+    int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts_s32(uint32_t addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const KernelArgs args) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024 B alignment
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;   // SWIZZLE_128B needs 1024 B alignment
+    uint8_t* smem = smem_raw + pad;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    float* epi_stage = (float*)(smem + STAGES * STAGE_BYTES);
-    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
+    uint8_t* epi_base = smem + STAGES * STAGE_BYTES;                       // per-warp staging tiles + column metadata
+    uint64_t* bars = (uint64_t*)(epi_base + EPI_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
     uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -197,86 +210,92 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue (8 warps) =====================
+        // ===================== epilogue: 16 warps, each owns 32 rows x 64 columns of every tile =====================
+        // phase 1 (thread = row): TMEM -> exact integer corrections, scale, bias, ReLU -> per-warp smem tile [32][33]
+        // phase 2 (lane = column): read the tile transposed -> residual adds / min-max -> 128-byte coalesced stores
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;           // which 128-column half of the tile
+        const int cgrp = ew >> 2;           // which 64-column group of the tile
         const LbI8Epilogue& ep = args.ep;
+        const uint32_t tile_s = smem_u32(epi_base) + (uint32_t)ew * EPI_WARP_BYTES;   // [32][33] f32
+        const uint32_t meta_s = tile_s + 32 * 33 * 4;                                   // colsum[64] | w_scale[64] | bias[64]
+        const float relu_lo = ep.relu ? 0.0f : -3.402823466e+38f;
+        const int N = args.N, M = args.M;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
-            const int row = m_blk * BM + quad * 32 + lane;
-            const bool row_ok = row < args.M;
+            const int first_row = m_blk * BM + quad * 32;
+            const int row = first_row + lane;
+            const bool row_ok = row < M;
+            const int gcol_w = n_blk * BN + cgrp * 64;                 // first global column of this warp
+            // column metadata of this warp's 64 columns (arrays are padded to a multiple of 256 columns)
+            __syncwarp();
+            sts_s32(meta_s + 4 * lane, __ldg(ep.colsum + gcol_w + lane));
+            sts_s32(meta_s + 4 * (32 + lane), __ldg(ep.colsum + gcol_w + 32 + lane));
+            sts_f32(meta_s + 256 + 4 * lane, __ldg(ep.w_scale + gcol_w + lane));
+            sts_f32(meta_s + 256 + 4 * (32 + lane), __ldg(ep.w_scale + gcol_w + 32 + lane));
+            sts_f32(meta_s + 512 + 4 * lane, __ldg(ep.bias + gcol_w + lane));
+            sts_f32(meta_s + 512 + 4 * (32 + lane), __ldg(ep.bias + gcol_w + 32 + lane));
             int rs = 0, zpa = 0; float sa = 0.0f;
             if (row_ok) { rs = __ldg(ep.rowsum + row); zpa = __ldg(ep.row_zp + row); sa = __ldg(ep.row_scale + row); }
             const int row_corr = args.K * zpa * ep.w_zp - ep.w_zp * rs;
             unsigned long long best = 0ull;
+            const int slice_a = (MODE == EPI_MINMAX) ? first_row / ep.rows_per_slice : 0;
+            float mnA = 3.402823466e+38f, mxA = -3.402823466e+38f, mnB = 3.402823466e+38f, mxB = -3.402823466e+38f;
+            const int nrows = min(32, M - first_row);
+            __syncwarp();
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            // The warp's 32 rows span at most two slices (rows_per_slice >= 32 in every caller; checked on the host).
-            const int first_row = m_blk * BM + quad * 32;
-            const int slice_a = ep.minmax_keys ? first_row / ep.rows_per_slice : 0;
-            float mnA = 3.402823466e+38f, mxA = -3.402823466e+38f, mnB = 3.402823466e+38f, mxB = -3.402823466e+38f;
-            float* stg = epi_stage + (size_t)ew * (32 * 33);
 #pragma unroll 1
-            for (int chunk = 0; chunk < 4; ++chunk) {
-                const int col0 = half * 128 + chunk * 32;             // column inside the tile
-                const int gcol0 = n_blk * BN + col0;                  // global column
+            for (int chunk = 0; chunk < 2; ++chunk) {
+                const int col0 = cgrp * 64 + chunk * 32;               // column inside the tile
+                const int gcol0 = n_blk * BN + col0;                   // global column
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), r);
-                if (gcol0 >= args.N) continue;                        // warp-uniform
-                // ---- phase 1 (thread = row): exact integer corrections + scale + bias + ReLU, staged to smem ----
-                {
-                    const int ncols = min(32, args.N - gcol0);
+                if (gcol0 >= N || nrows <= 0) continue;                // warp-uniform
+                // ---- phase 1 ----
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int4 cs = __ldg(reinterpret_cast<const int4*>(ep.colsum + gcol0) + q);
-                        const float4 ws = __ldg(reinterpret_cast<const float4*>(ep.w_scale + gcol0) + q);
-                        const float4 bi = __ldg(reinterpret_cast<const float4*>(ep.bias + gcol0) + q);
-                        const int csv[4] = {cs.x, cs.y, cs.z, cs.w};
-                        const float wsv[4] = {ws.x, ws.y, ws.z, ws.w};
-                        const float biv[4] = {bi.x, bi.y, bi.z, bi.w};
+                for (int q = 0; q < 8; ++q) {
+                    const int4 cs = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
+                    const int4 wsb = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
+                    const int4 bib = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
+                    const int csv[4] = {cs.x, cs.y, cs.z, cs.w};
+                    const float wsv[4] = {__int_as_float(wsb.x), __int_as_float(wsb.y), __int_as_float(wsb.z), __int_as_float(wsb.w)};
+                    const float biv[4] = {__int_as_float(bib.x), __int_as_float(bib.y), __int_as_float(bib.z), __int_as_float(bib.w)};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int acci = (int)r[q * 4 + e] + row_corr - zpa * csv[e];
-                            float t = __fmul_rn((float)acci, __fmul_rn(sa, wsv[e]));
-                            if (ep.has_bias) t = __fadd_rn(t, biv[e]);
-                            if (ep.relu) t = fmaxf(t, 0.0f);
-                            stg[lane * 33 + q * 4 + e] = t;
-                            if (ep.argmax_keys && row_ok && (q * 4 + e) < ncols) {   // CTC head: no residual adds follow
+                    for (int e = 0; e < 4; ++e) {
+                        const int acci = (int)r[q * 4 + e] + row_corr - zpa * csv[e];
+                        float t = __fmul_rn((float)acci, __fmul_rn(sa, wsv[e]));
+                        t = ep.has_bias ? __fadd_rn(t, biv[e]) : t;
+                        t = fmaxf(t, relu_lo);
+                        if (MODE == EPI_ARGMAX) {
+                            if (row_ok && gcol0 + q * 4 + e < N) {
                                 unsigned long long key = ((unsigned long long)lb_fkey(t) << 32) | (unsigned)(gcol0 + q * 4 + e);
                                 best = key > best ? key : best;
                             }
                         }
+                        sts_f32(tile_s + 4 * (lane * 33 + q * 4 + e), t);
                     }
                 }
+                if (MODE == EPI_ARGMAX && !ep.out) continue;           // ids only: nothing to write
                 __syncwarp();
-                // ---- phase 2 (lane = column): coalesced residual loads / stores, 128 B per warp instruction ----
-                {
-                    const int col = gcol0 + lane;
-                    const bool col_ok = col < args.N;
-                    const int nrows = min(32, args.M - first_row);
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        if (rr >= nrows) break;                       // warp-uniform
-                        float v = stg[rr * 33 + lane];
-                        const long long o = (long long)(first_row + rr) * args.N + col;
-                        if (col_ok) {
-                            if (ep.add1) v = __fadd_rn(v, __ldg(ep.add1 + o));
-                            if (ep.add2) v = __fadd_rn(__ldg(ep.add2 + o), v);
-                            if (ep.out) ep.out[o] = v;
-                            if (ep.minmax_keys && ep.rows_per_slice >= 32) {
-                                if ((first_row + rr) / ep.rows_per_slice == slice_a) { mnA = fminf(mnA, v); mxA = fmaxf(mxA, v); }
-                                else { mnB = fminf(mnB, v); mxB = fmaxf(mxB, v); }
-                            }
-                        }
-                        if (ep.minmax_keys && ep.rows_per_slice < 32) {   // tiny slices: one reduction per row
-                            float lo = col_ok ? v : 3.402823466e+38f, hi = col_ok ? v : -3.402823466e+38f;
-                            lo = lb_warp_min(lo); hi = lb_warp_max(hi);
-                            if (lane == 0) {
-                                const int sl = (first_row + rr) / ep.rows_per_slice;
-                                atomicMin(ep.minmax_keys + 2 * sl, lb_fkey(lo)); atomicMax(ep.minmax_keys + 2 * sl + 1, lb_fkey(hi));
-                            }
+                // ---- phase 2 ----
+                const int col = gcol0 + lane;
+                if (col < N) {
+                    const long long base = (long long)first_row * N + col;
+                    float* outp = ep.out + base;
+                    const float* a1 = (MODE == EPI_R1 || MODE == EPI_R12) ? ep.add1 + base : nullptr;
+                    const float* a2 = (MODE == EPI_R2 || MODE == EPI_R12) ? ep.add2 + base : nullptr;
+#pragma unroll 8
+                    for (int rr = 0; rr < nrows; ++rr) {
+                        float v = lds_f32(tile_s + 4 * (rr * 33 + lane));
+                        const long long o = (long long)rr * N;
+                        if (MODE == EPI_R1 || MODE == EPI_R12) v = __fadd_rn(v, __ldg(a1 + o));
+                        if (MODE == EPI_R2 || MODE == EPI_R12) v = __fadd_rn(__ldg(a2 + o), v);
+                        outp[o] = v;
+                        if (MODE == EPI_MINMAX) {
+                            if (rr < (slice_a + 1) * ep.rows_per_slice - first_row) { mnA = fminf(mnA, v); mxA = fmaxf(mxA, v); }
+                            else { mnB = fminf(mnB, v); mxB = fmaxf(mxB, v); }
                         }
                     }
                 }
@@ -288,14 +307,14 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
-            if (ep.minmax_keys && first_row < args.M) {
+            if (MODE == EPI_MINMAX && nrows > 0) {
                 mnA = lb_warp_min(mnA); mxA = lb_warp_max(mxA); mnB = lb_warp_min(mnB); mxB = lb_warp_max(mxB);
                 if (lane == 0) {
                     if (mnA <= mxA) { atomicMin(ep.minmax_keys + 2 * slice_a, lb_fkey(mnA)); atomicMax(ep.minmax_keys + 2 * slice_a + 1, lb_fkey(mxA)); }
                     if (mnB <= mxB) { atomicMin(ep.minmax_keys + 2 * (slice_a + 1), lb_fkey(mnB)); atomicMax(ep.minmax_keys + 2 * (slice_a + 1) + 1, lb_fkey(mxB)); }
                 }
             }
-            if (ep.argmax_keys && row_ok && best != 0ull) atomicMax(ep.argmax_keys + row, best);
+            if (MODE == EPI_ARGMAX && row_ok && best != 0ull) atomicMax(ep.argmax_keys + row, best);
         }
     }
 
@@ -344,7 +363,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     LB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_i8_tc: empty problem");
     LB_REQUIRE(K % 16 == 0, "gemm_i8_tc: K=%d must be a multiple of 16 (TMA row pitch)", K);
     LB_REQUIRE((((uintptr_t)A | (uintptr_t)Wt) & 15) == 0, "gemm_i8_tc: operands must be 16-byte aligned");
-    LB_REQUIRE(!ep.minmax_keys || ep.rows_per_slice >= 1, "gemm_i8_tc: fused min/max needs rows_per_slice >= 1");
+    LB_REQUIRE(!ep.minmax_keys || ep.rows_per_slice >= 32, "gemm_i8_tc: fused min/max needs rows_per_slice >= 32 (a warp's 32 rows may span at most two slices)");
     LB_REQUIRE(!ep.argmax_keys || (!ep.add1 && !ep.add2), "gemm_i8_tc: fused arg-max cannot be combined with residual adds");
     CUtensorMap ta, tb;
     int rc = make_tmap_u8(&ta, A, M, K, BM);
@@ -357,14 +376,26 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     args.num_n_blocks = lb_ceil_div(N, BN);
     args.num_k_blocks = lb_ceil_div(K, BK);
     args.ep = ep;
-    static bool attr_set = false;
-    if (!attr_set) {
-        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
     int tiles = args.num_m_blocks * args.num_n_blocks;
     int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-    gemm_i8_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, args);
+    int mode = EPI_PLAIN;
+    if (ep.argmax_keys) mode = EPI_ARGMAX;
+    else if (ep.minmax_keys) mode = EPI_MINMAX;
+    else if (ep.add1 && ep.add2) mode = EPI_R12;
+    else if (ep.add1) mode = EPI_R1;
+    else if (ep.add2) mode = EPI_R2;
+    LB_REQUIRE(!(ep.minmax_keys && (ep.add1 || ep.add2)), "gemm_i8_tc: fused min/max with residual adds is not instantiated");
+    LB_REQUIRE(ep.out || mode == EPI_ARGMAX, "gemm_i8_tc: no output requested");
+#define LB_LAUNCH_MODE(MD)                                                                                              \
+    case MD:                                                                                                            \
+        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+        gemm_i8_tc_kernel<MD><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, args);                            \
+        break;
+    switch (mode) {
+        LB_LAUNCH_MODE(EPI_PLAIN) LB_LAUNCH_MODE(EPI_MINMAX) LB_LAUNCH_MODE(EPI_ARGMAX) LB_LAUNCH_MODE(EPI_R1) LB_LAUNCH_MODE(EPI_R2)
+        LB_LAUNCH_MODE(EPI_R12)
+    }
+#undef LB_LAUNCH_MODE
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -368,8 +368,10 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
                                                  m->h, site(l * 4 + 2), T));
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
-            ep.out = m->f1; ep.rows_per_slice = T; ep.relu = 1; ep.minmax_keys = site(l * 4 + 3);
+            ep.out = m->f1; ep.rows_per_slice = T; ep.relu = 1;
+            ep.minmax_keys = T >= 32 ? site(l * 4 + 3) : nullptr;     // fused per-clip min/max of the ReLU output
             SV_LINEAR(ctx, m,m->h, site(l * 4 + 2), M, T, m->lin[l * 4 + 2], qs, ep);
+            if (T < 32) SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->f1, B, (long long)T * ffn, site(l * 4 + 3)));   // very short clips
         }
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
