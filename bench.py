@@ -205,8 +205,10 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    th0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
+    host_enqueue_ms = (time.perf_counter() - th0) * 1000.0 / args.steps   # CPU time to enqueue one step (no sync inside)
     e1.record(stream)
     barrier()
     launches = ctx.launch_count() - launches0
@@ -265,7 +267,7 @@ def run_ours(args):
                            "clips_per_gpu": B, "global_clips": n_total, "rows_per_clip": T, "parallelism": f"clip-sharded x{world}",
                            "l2": "inputs + weights per step (65.5 MB PCM + 240 MB blob) exceed the 126 MB L2 and every step streams >50 GB of activations"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(B * N_SAMPLES * 4), "d2h_bytes_per_step": int(B * T * 4)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "kernel_breakdown_ms": {k: round(v["ms"], 3) for k, v in prof.items()}, "hbm_peak_gbs": hbm}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -6,8 +6,8 @@
 //
 //   S = Q K^T          tcgen05.mma kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi: ~2^-21 relative,
 //                      i.e. f32-grade; plain TF32 would be 2^-11 and miss the 1e-4 bar)
-//   P = exp(S - max)   softmax warps read S from TMEM (one thread per query row), same polynomial
-//                      exp / libm tail and the same AVX2-order row sum as the CPU reference
+//   P = exp(S - max)   8 softmax warps read S from TMEM (two threads per query row, even / odd 32-key
+//                      chunks), same polynomial exp / libm tail split as the CPU reference
 //   O = P V            P is written to shared memory as the tf32 hi/lo A-operand, 32 keys at a time,
 //                      while the MMA warp consumes the previous chunk; O accumulates in TMEM
 //   out = O / sum      + fused per-clip min/max (feeds the next dynamic quantiser)
@@ -35,8 +35,8 @@ constexpr int TILE_V = DK * 128;      // 16 KB  [128 dims][32 keys]
 constexpr int STAGE_C = 2 * TILE_P + 2 * TILE_V;   // 64 KB
 constexpr int NSTAGE_C = 3;
 constexpr int SMEM_MAIN = NSTAGE_A * STAGE_A;      // 208 KB (>= NSTAGE_C * STAGE_C = 192 KB)
-constexpr int SMEM_BYTES = SMEM_MAIN + 1024 + 512;
-constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BYTES = SMEM_MAIN + 1024 + 256 + 2 * 128 * 4;   // + barriers + row-sum exchange
+constexpr int NUM_THREADS = 384;   // TMA, MMA, TMEM-alloc, spare + 8 softmax/epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int O_COL = 2 * NH;         // O accumulator starts at TMEM column 288
 
@@ -60,6 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(40);   // yield the issue slot: the single-thread TMA / MMA roles share SM sub-partitions with softmax warps
         if (clock64() - t0 > 4000000000ll) { printf("lele_b200 attn_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
@@ -175,6 +176,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     uint64_t* pv_empty = bars + 11;           // [3] MMA consumed the stage
     uint64_t* o_full = bars + 14;             // O complete
     uint32_t* tmem_base_smem = (uint32_t*)(bars + 16);
+    float* xsum = (float*)(smem + SMEM_MAIN + 256);   // [2][128] partial row sums of the two softmax groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x % args.n_qtiles;
@@ -276,12 +278,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ===================== softmax + epilogue: one thread per query row =====================
+        // ===================== softmax + epilogue: 8 warps, two threads per query row =====================
+        // group 0 (warps 4-7) takes the even 32-key chunks, group 1 (warps 8-11) the odd ones; both read the
+        // whole row for the max (cheap), each accumulates its share of the row sum, exchanged through smem.
         const int quad = warp & 3;
+        const int grp = (warp - 4) >> 2;
         const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
-        const int t = qt * AQ + r;                      // query index inside the clip
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const int n32 = T & ~31, n8 = T & ~7;
+        const int n8 = T & ~7;
         mbar_wait(s_full, 0);
         tc_fence_after();
         // ---- pass 1: row max over the T valid keys ----
@@ -292,12 +296,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 32; ++i) if (c * KC + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
-        // ---- pass 2: e = exp(s - max), AVX2-order sum, tf32 hi/lo split into the P stage ----
-        float p[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) p[i] = 0.0f;
-        float vsum[8], sum = 0.0f;
-        for (int c = 0; c < NKC; ++c) {
+        // ---- pass 2: e = exp(s - max) (polynomial exp on the x86 SIMD body j < T/8*8, libm on the tail, as the
+        //      reference softmax), tf32 hi/lo split into the swizzled K-major P tiles ----
+        float psum = 0.0f;
+        for (int c = grp; c < NKC; c += 2) {
             const int s = c % NSTAGE_C; const uint32_t ph = (c / NSTAGE_C) & 1;
             uint32_t v[32];
             tmem_ld32(trow + (uint32_t)(c * KC), v);
@@ -307,22 +309,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 const int j = c * KC + i;
                 const float dlt = __fsub_rn(__uint_as_float(v[i]), mx);
                 e[i] = j < n8 ? lb_cephes_expf(dlt) : (j < T ? expf(dlt) : 0.0f);
+                psum += e[i];
             }
-            if (c * KC < n32) {                          // a full 32-key block: one partial per element slot
-#pragma unroll
-                for (int i = 0; i < 32; ++i) p[i] = __fadd_rn(p[i], e[i]);
-            }
-            if (c * KC == n32) {                         // the block that holds the 8-blocks remainder and the scalar tail
-#pragma unroll
-                for (int l = 0; l < 8; ++l) vsum[l] = __fadd_rn(__fadd_rn(p[l], p[8 + l]), __fadd_rn(p[16 + l], p[24 + l]));
-#pragma unroll
-                for (int i = 0; i < 24; ++i) if (n32 + i < n8) vsum[i & 7] = __fadd_rn(vsum[i & 7], e[i]);
-                sum = __fadd_rn(__fadd_rn(__fadd_rn(vsum[0], vsum[4]), __fadd_rn(vsum[2], vsum[6])),
-                                __fadd_rn(__fadd_rn(vsum[1], vsum[5]), __fadd_rn(vsum[3], vsum[7])));
-#pragma unroll
-                for (int i = 0; i < 32; ++i) if (n32 + i >= n8 && n32 + i < T) sum = __fadd_rn(sum, e[i]);
-            }
-            // write this row's 32 probabilities (hi | lo) into the 128B-swizzled K-major P tiles
             mbar_wait(&pv_empty[s], ph ^ 1);
             uint8_t* st = smem + s * STAGE_C;
             float* ph_row = (float*)(st + r * 128);
@@ -342,22 +330,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[s]);
         }
-        if (n32 == NKC * KC) {                           // T is a multiple of 32: no remainder block was visited
-#pragma unroll
-            for (int l = 0; l < 8; ++l) vsum[l] = __fadd_rn(__fadd_rn(p[l], p[8 + l]), __fadd_rn(p[16 + l], p[24 + l]));
-            sum = __fadd_rn(__fadd_rn(__fadd_rn(vsum[0], vsum[4]), __fadd_rn(vsum[2], vsum[6])),
-                            __fadd_rn(__fadd_rn(vsum[1], vsum[5]), __fadd_rn(vsum[3], vsum[7])));
-        }
-        const float inv = __fdiv_rn(1.0f, sum);
+        // exchange the two partial row sums
+        xsum[grp * AQ + r] = psum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv = __fdiv_rn(1.0f, __fadd_rn(xsum[r], xsum[AQ + r]));
         // ---- epilogue: O / sum -> att, per-clip min/max; transposed through smem for coalesced stores ----
         mbar_wait(o_full, 0);
         tc_fence_after();
-        float* stg = (float*)smem + (size_t)quad * (32 * 33);   // phase-C buffers are idle now (all MMAs retired)
+        float* stg = (float*)smem + (size_t)(warp - 4) * (32 * 33);   // phase-C buffers are idle now (all MMAs retired)
         float mn = 3.402823466e+38f, mxo = -3.402823466e+38f;
         const int row0 = qt * AQ + quad * 32;
         const int nrows = min(32, T - row0);
 #pragma unroll 1
-        for (int ch = 0; ch < DK / 32; ++ch) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int ch = grp * 2 + cc;
             uint32_t v[32];
             tmem_ld32(trow + (uint32_t)(O_COL + ch * 32), v);
 #pragma unroll
@@ -374,7 +360,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             mn = lb_warp_min(mn); mxo = lb_warp_max(mxo);
             if (lane == 0) { atomicMin(args.minmax_keys + 2 * b, lb_fkey(mn)); atomicMax(args.minmax_keys + 2 * b + 1, lb_fkey(mxo)); }
         }
-        (void)t;
     }
 
     tc_fence_before();
@@ -399,7 +384,7 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 // f32 4-D tensor, innermost dim contiguous, 128B swizzle, zero OOB fill
-int make_map_f32_4d(CUtensorMap* map, const void* ptr, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+int make_map_f32_4d_uncached(CUtensorMap* map, const void* ptr, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
                     const unsigned box[4]) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
@@ -410,6 +395,22 @@ int make_map_f32_4d(CUtensorMap* map, const void* ptr, const unsigned long long 
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), d, s, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(f32 4d) failed (%d)", (int)r); return LELE_B200_ERR_CUDA; }
+    return LELE_B200_OK;
+}
+lele_b200_ctx* g_ctx_for_maps = nullptr;
+int make_map_f32_4d(CUtensorMap* map, const void* ptr, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+                    const unsigned box[4]) {
+    lele_b200_ctx* ctx = g_ctx_for_maps;
+    unsigned long long h = lb_hash_mix(0x66333234ull, (unsigned long long)(uintptr_t)ptr);
+    for (int i = 0; i < 4; ++i) h = lb_hash_mix(lb_hash_mix(h, dims[i]), box[i]);
+    for (int i = 0; i < 3; ++i) h = lb_hash_mix(h, strides_bytes[i]);
+    auto it = ctx->tmaps.find(h);
+    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    int rc = make_map_f32_4d_uncached(map, ptr, dims, strides_bytes, box);
+    if (rc) return rc;
+    std::vector<unsigned char> blob(sizeof(CUtensorMap));
+    memcpy(blob.data(), map, sizeof(CUtensorMap));
+    ctx->tmaps.emplace(h, std::move(blob));
     return LELE_B200_OK;
 }
 int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
@@ -451,6 +452,7 @@ int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, i
     const unsigned bv[4] = {KC, DK, 1, 1};
     CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
     int rc;
+    g_ctx_for_maps = ctx;
     if ((rc = make_map_f32_4d(&mqh, q_hi, dqk, sqk, bq))) return rc;
     if ((rc = make_map_f32_4d(&mql, q_lo, dqk, sqk, bq))) return rc;
     if ((rc = make_map_f32_4d(&mkh, k_hi, dqk, sqk, bk))) return rc;
@@ -460,7 +462,8 @@ int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, i
     AttnArgs a;
     a.B = B; a.T = T; a.H = H; a.n_qtiles = lb_ceil_div(T, AQ); a.n_kchunks = lb_ceil_div(T, KC); a.rows_per_slice = T;
     a.out = att; a.minmax_keys = minmax_keys;
-    LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    static thread_local bool attr_done = false;
+    if (!attr_done) { LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_done = true; }
     attn_tc_kernel<<<B * H * a.n_qtiles, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mqh, mql, mkh, mkl, mvh, mvl, a);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;

@@ -28,7 +28,14 @@ struct lele_b200_ctx {
     unsigned long long launches = 0;   // kernels launched through this ctx (bench "gpu_launches")
     // cached device constants (FFT twiddles per n, Hann window, sparse mel bank ...)
     std::unordered_map<std::string, void*> tables;
+    // encoded TMA descriptors keyed by (pointer, geometry): workspace / weight pointers are stable
+    // across forwards, so cuTensorMapEncodeTiled runs once per tensor instead of once per launch
+    std::unordered_map<unsigned long long, std::vector<unsigned char>> tmaps;
 };
+static inline unsigned long long lb_hash_mix(unsigned long long h, unsigned long long v) {
+    h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+}
 // returns the cached device copy of a host table, uploading it on first use
 int lb_table(lele_b200_ctx* ctx, const std::string& key, const void* host, size_t bytes, void** out);
 

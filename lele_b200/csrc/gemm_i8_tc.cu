@@ -59,6 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(40);   // yield the issue slot to the epilogue warps sharing this SM sub-partition
         if (clock64() - t0 > 4000000000ll) { printf("lele_b200 gemm_i8_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
@@ -357,6 +358,18 @@ int make_tmap_u8(CUtensorMap* map, const void* ptr, long long rows, long long co
     return LELE_B200_OK;
 }
 
+int cached_tmap_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_rows) {
+    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(lb_hash_mix(0x75386d61ull, (unsigned long long)(uintptr_t)ptr), (unsigned long long)rows),
+                                                   (unsigned long long)cols), (unsigned long long)box_rows);
+    auto it = ctx->tmaps.find(h);
+    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    int rc = make_tmap_u8(map, ptr, rows, cols, box_rows);
+    if (rc) return rc;
+    std::vector<unsigned char> blob(sizeof(CUtensorMap));
+    memcpy(blob.data(), map, sizeof(CUtensorMap));
+    ctx->tmaps.emplace(h, std::move(blob));
+    return LELE_B200_OK;
+}
 }  // namespace
 
 int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep) {
@@ -366,9 +379,9 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     LB_REQUIRE(!ep.minmax_keys || ep.rows_per_slice >= 32, "gemm_i8_tc: fused min/max needs rows_per_slice >= 32 (a warp's 32 rows may span at most two slices)");
     LB_REQUIRE(!ep.argmax_keys || (!ep.add1 && !ep.add2), "gemm_i8_tc: fused arg-max cannot be combined with residual adds");
     CUtensorMap ta, tb;
-    int rc = make_tmap_u8(&ta, A, M, K, BM);
+    int rc = cached_tmap_u8(ctx, &ta, A, M, K, BM);
     if (rc) return rc;
-    rc = make_tmap_u8(&tb, Wt, N, K, BN);
+    rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN);
     if (rc) return rc;
     KernelArgs args;
     args.M = M; args.N = N; args.K = K;
@@ -386,9 +399,13 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     else if (ep.add2) mode = EPI_R2;
     LB_REQUIRE(!(ep.minmax_keys && (ep.add1 || ep.add2)), "gemm_i8_tc: fused min/max with residual adds is not instantiated");
     LB_REQUIRE(ep.out || mode == EPI_ARGMAX, "gemm_i8_tc: no output requested");
+    static thread_local unsigned attr_done = 0;   // one process per GPU: the attribute is set once per instantiation
 #define LB_LAUNCH_MODE(MD)                                                                                              \
     case MD:                                                                                                            \
-        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+        if (!(attr_done & (1u << MD))) {                                                                                \
+            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+            attr_done |= (1u << MD);                                                                                    \
+        }                                                                                                               \
         gemm_i8_tc_kernel<MD><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, args);                            \
         break;
     switch (mode) {
