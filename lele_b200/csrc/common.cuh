@@ -103,11 +103,10 @@ __device__ __forceinline__ int lb_warp_sum_i(int v) {
 // tail.  A warp reproduces that order exactly, so LayerNorm statistics / softmax sums -- and the
 // dynamic-quantisation min/max derived from them -- are bit-identical to the x86 reference order.
 // step_vec(acc, j) / step_tail(acc, j) fold element j into acc.  Result broadcast to all lanes.
+// second half of the reduction: p holds this lane's partial over the full 32-element blocks
 template <class SV, class ST>
-__device__ __forceinline__ float lb_avx_order_reduce(int n, int lane, SV step_vec, ST step_tail) {
-    float p = 0.0f;
+__device__ __forceinline__ float lb_avx_order_finish(float p, int n, int lane, SV step_vec, ST step_tail) {
     const int n32 = n & ~31, n8 = n & ~7;
-    for (int j = lane; j < n32; j += 32) p = step_vec(p, j);
     p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 8));
     p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 16));
     for (int j = n32 + (lane & 7); j < n8; j += 8) p = step_vec(p, j);
@@ -117,6 +116,13 @@ __device__ __forceinline__ float lb_avx_order_reduce(int n, int lane, SV step_ve
     p = __shfl_sync(0xffffffffu, p, 0);
     for (int j = n8; j < n; ++j) p = step_tail(p, j);
     return p;
+}
+template <class SV, class ST>
+__device__ __forceinline__ float lb_avx_order_reduce(int n, int lane, SV step_vec, ST step_tail) {
+    float p = 0.0f;
+    const int n32 = n & ~31;
+    for (int j = lane; j < n32; j += 32) p = step_vec(p, j);
+    return lb_avx_order_finish(p, n, lane, step_vec, step_tail);
 }
 
 // order-preserving float <-> uint key, so per-clip min/max can use integer atomics

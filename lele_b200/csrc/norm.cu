@@ -9,6 +9,8 @@
 // reference arithmetic.  One warp per row, coalesced 128-byte warp loads (element j -> lane j%32);
 // the second pass re-reads the row from L1/L2.  Optional fused per-slice min/max of the output
 // (order-preserving keys) feeds the dynamic quantiser of the next int8 linear.
+// kRegs > 0: the row's full 32-element blocks live in registers (n <= 32*kRegs): one global read.
+template <int kRegs>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                   long long outer, int n, float eps, float* __restrict__ out,
@@ -19,21 +21,42 @@ layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
     const float* xr = x + row * n;
     float* o = out + row * n;
     const float inv_n = __fdiv_rn(1.0f, (float)n);
-    const int simd_end = (n / 8) * 8;
-    const float s = lb_avx_order_reduce(n, lane, [&](float acc, int j) { return __fadd_rn(acc, xr[j]); },
+    const int simd_end = (n / 8) * 8, n32 = n & ~31;
+    float v[kRegs > 0 ? kRegs : 1];
+    float ps = 0.0f, pq = 0.0f;
+    if (kRegs > 0) {
+#pragma unroll
+        for (int i = 0; i < kRegs; ++i) {
+            const int j = lane + 32 * i;
+            v[i] = j < n32 ? __ldg(xr + j) : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < kRegs; ++i)
+            if (lane + 32 * i < n32) { ps = __fadd_rn(ps, v[i]); pq = __fmaf_rn(v[i], v[i], pq); }
+    } else {
+        for (int j = lane; j < n32; j += 32) { float t = xr[j]; ps = __fadd_rn(ps, t); pq = __fmaf_rn(t, t, pq); }
+    }
+    const float s = lb_avx_order_finish(ps, n, lane, [&](float acc, int j) { return __fadd_rn(acc, xr[j]); },
                                         [&](float acc, int j) { return __fadd_rn(acc, xr[j]); });
-    const float sq = lb_avx_order_reduce(n, lane, [&](float acc, int j) { float t = xr[j]; return __fmaf_rn(t, t, acc); },
+    const float sq = lb_avx_order_finish(pq, n, lane, [&](float acc, int j) { float t = xr[j]; return __fmaf_rn(t, t, acc); },
                                          [&](float acc, int j) { float t = xr[j]; return __fadd_rn(acc, __fmul_rn(t, t)); });
     const float mean = __fmul_rn(s, inv_n);
     const float var = __fsub_rn(__fmul_rn(sq, inv_n), __fmul_rn(mean, mean));
     const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
     float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
-    for (int j = lane; j < n; j += 32) {
-        float g = gamma ? gamma[j] : 1.0f, b = beta ? beta[j] : 0.0f;
-        float sc = __fmul_rn(__fsub_rn(xr[j], mean), inv);
+    auto emit = [&](int j, float xv) {
+        float g = gamma ? __ldg(gamma + j) : 1.0f, b = beta ? __ldg(beta + j) : 0.0f;
+        float sc = __fmul_rn(__fsub_rn(xv, mean), inv);
         float r = j < simd_end ? __fmaf_rn(sc, g, b) : __fadd_rn(__fmul_rn(sc, g), b);
         vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
         o[j] = r;
+    };
+    if (kRegs > 0) {
+#pragma unroll
+        for (int i = 0; i < kRegs; ++i) { const int j = lane + 32 * i; if (j < n32) emit(j, v[i]); }
+        for (int j = n32 + lane; j < n; j += 32) emit(j, xr[j]);
+    } else {
+        for (int j = lane; j < n; j += 32) emit(j, xr[j]);
     }
     if (minmax_keys) {
         vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
@@ -49,7 +72,10 @@ int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma,
                          int n, float eps, float* out, unsigned* minmax_keys, int rows_per_slice) {
     if (outer == 0) return LELE_B200_OK;
     const int warps = 8;
-    layer_norm_kernel<<<lb_ceil_div(outer, warps), warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
+    const int grid = lb_ceil_div(outer, warps);
+    if (n <= 32 * 18) layer_norm_kernel<18><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
+    else if (n <= 32 * 64) layer_norm_kernel<64><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
+    else layer_norm_kernel<0><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -162,6 +162,13 @@ struct lele_b200_sensevoice {
     int attn_simt = 0;   // LELE_B200_ATTN_SIMT=1: CUDA-core attention (cross-check of the tcgen05 path)
     // profiling
     int profiling = 0;
+    // CUDA-graph replay of the whole forward (the ~1000 launches of one step are CPU-bound otherwise)
+    struct GraphKey { const float* pcm; int B, n_samples, lang, textnorm, n_layers; int32_t* ids; float* logits; };
+    int use_graph = 1;              // LELE_B200_GRAPH=0 disables
+    bool warmed = false;            // one eager forward has run (lazy tables / attributes / scratch are in place)
+    cudaGraphExec_t graph_exec = nullptr;
+    GraphKey graph_key = {};
+    unsigned long long graph_launches = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     struct Span { int cls; cudaEvent_t a, b; };
@@ -267,6 +274,7 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax));
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
+    { const char* e = getenv("LELE_B200_GRAPH"); m->use_graph = (e && e[0] == '0') ? 0 : 1; }
     if (!rc) rc = sv_alloc((void**)&m->pcm_stage, sizeof(float) * B * (size_t)max_samples);
     if (!rc) rc = sv_alloc((void**)&m->ids_stage, sizeof(int32_t) * M);
     if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
@@ -282,6 +290,7 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
                     m->qscratch, m->pcm_stage, m->ids_stage, m->attn_scratch};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : m->ev_pool) cudaEventDestroy(e);
+    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
     delete m;
     return LELE_B200_OK;
 }
@@ -424,6 +433,13 @@ extern "C" int lele_b200_sensevoice_forward_features(lele_b200_ctx* ctx, lele_b2
     return sv_finish_profile(ctx, m);
 }
 
+static int sv_forward_eager(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_dev, int n_clips, int n_samples, int t,
+                            int lang, int textnorm, int n_layers_limit, int32_t* ids_dev, float* logits_dev_opt) {
+    SV_RUN(P_FRONTEND, lele_b200_frontend_compute(ctx, pcm_dev, n_clips, n_samples, n_samples, nullptr, m->lfr));
+    SV_RUN(P_CMVN, lele_b200_cmvn(ctx, m->lfr, n_clips, t, m->d_in, 1e-5f, m->feats));
+    return sv_encoder(ctx, m, m->feats, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+}
+
 extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_dev, int n_clips, int n_samples,
                                             int lang, int textnorm, int n_layers_limit, int32_t* ids_dev, float* logits_dev_opt) {
     LB_REQUIRE(ctx && m && pcm_dev, "sensevoice_forward: NULL argument");
@@ -431,11 +447,37 @@ extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensev
     int frames = lele_b200_frontend_num_frames(n_samples);
     LB_REQUIRE(frames > 0, "sensevoice_forward: clip shorter than one frame (400 samples)");
     int t = (frames + 5) / 6;
-    SV_RUN(P_FRONTEND, lele_b200_frontend_compute(ctx, pcm_dev, n_clips, n_samples, n_samples, nullptr, m->lfr));
-    SV_RUN(P_CMVN, lele_b200_cmvn(ctx, m->lfr, n_clips, t, m->d_in, 1e-5f, m->feats));
-    int rc = sv_encoder(ctx, m, m->feats, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+    if (m->profiling || !m->use_graph) {
+        int rc = sv_forward_eager(ctx, m, pcm_dev, n_clips, n_samples, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+        if (rc) return rc;
+        m->warmed = true;
+        return sv_finish_profile(ctx, m);
+    }
+    const lele_b200_sensevoice::GraphKey key = {pcm_dev, n_clips, n_samples, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt};
+    if (m->graph_exec && memcmp(&key, &m->graph_key, sizeof(key)) == 0) {
+        LB_CHECK_CUDA(cudaGraphLaunch(m->graph_exec, ctx->stream));
+        ctx->launches += m->graph_launches;
+        return LELE_B200_OK;
+    }
+    // new shape / pointers: one eager pass (also the warm-up that performs every lazy allocation), then capture
+    int rc = sv_forward_eager(ctx, m, pcm_dev, n_clips, n_samples, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
     if (rc) return rc;
-    return sv_finish_profile(ctx, m);
+    m->warmed = true;
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    const unsigned long long l0 = ctx->launches;
+    LB_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    rc = sv_forward_eager(ctx, m, pcm_dev, n_clips, n_samples, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    m->graph_launches = ctx->launches - l0;
+    ctx->launches = l0;            // captured, not executed
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { lb_set_error("sensevoice_forward: graph capture failed: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
+    ce = cudaGraphInstantiate(&m->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { m->graph_exec = nullptr; lb_set_error("sensevoice_forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
+    m->graph_key = key;
+    return LELE_B200_OK;           // this call's result was produced by the eager pass above
 }
 
 extern "C" int lele_b200_sensevoice_transcribe_host(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_host, int n_clips,
