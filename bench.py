@@ -151,7 +151,11 @@ def run_ours(args):
     cfg = SenseVoiceConfig()
     B = CLIPS_PER_GPU
     n_total = B * world
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: the library launches on exactly this stream and every CUDA event
+    # below is recorded on it (a NULL handle would make the library create its own private stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = Context(local_rank, stream.cuda_stream)
 
     # ---- weights: built on rank 0, one NCCL broadcast to the other ranks ----

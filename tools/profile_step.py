@@ -10,7 +10,8 @@ from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob, synth_bat
 B = int(os.environ.get("PROF_CLIPS", "64"))
 cfg = SenseVoiceConfig()
 torch.cuda.set_device(0)
-ctx = Context(0, torch.cuda.current_stream().cuda_stream)
+st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+ctx = Context(0, st.cuda_stream)
 m = SenseVoice(build_blob(cfg, seed=1234), max_clips=B, max_samples=256000, ctx=ctx)
 pcm = torch.from_numpy(synth_batch(0, B)).cuda()
 ids = torch.empty((B, m.rows(256000)), dtype=torch.int32, device="cuda")
