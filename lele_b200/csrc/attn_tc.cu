@@ -358,7 +358,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         }
         if (args.minmax_keys && nrows > 0) {
             mn = lb_warp_min(mn); mxo = lb_warp_max(mxo);
-            if (lane == 0) { atomicMin(args.minmax_keys + 2 * b, lb_fkey(mn)); atomicMax(args.minmax_keys + 2 * b + 1, lb_fkey(mxo)); }
+            if (lane == 0) lb_mm_update(args.minmax_keys, b, mn, mxo);
         }
     }
 

@@ -136,6 +136,22 @@ __device__ __forceinline__ float lb_fkey_inv(unsigned k) {
 }
 #define LB_KEY_MIN_INIT 0xffffffffu /* identity for atomicMin over keys */
 #define LB_KEY_MAX_INIT 0x00000000u /* identity for atomicMax over keys */
+// Per-slice min/max keys are sharded over LB_MM_SLOTS address pairs (slot = blockIdx.x % slots) so the
+// ~10^4 atomics a launch issues do not serialise on 2 addresses per clip; consumers reduce the slots.
+// Layout: keys[slice][LB_MM_SLOTS][2] (min key, max key).
+#define LB_MM_SLOTS 8
+__device__ __forceinline__ void lb_mm_update(unsigned* keys, long long slice, float mn, float mx) {
+    unsigned* k = keys + ((size_t)slice * LB_MM_SLOTS + (blockIdx.x & (LB_MM_SLOTS - 1))) * 2;
+    atomicMin(k, lb_fkey(mn));
+    atomicMax(k + 1, lb_fkey(mx));
+}
+__device__ __forceinline__ void lb_mm_read(const unsigned* keys, long long slice, float& mn, float& mx) {
+    const unsigned* k = keys + (size_t)slice * LB_MM_SLOTS * 2;
+    unsigned a = LB_KEY_MIN_INIT, b = LB_KEY_MAX_INIT;
+#pragma unroll
+    for (int s = 0; s < LB_MM_SLOTS; ++s) { a = min(a, k[2 * s]); b = max(b, k[2 * s + 1]); }
+    mn = lb_fkey_inv(a); mx = lb_fkey_inv(b);
+}
 
 // Polynomial expf used by lele's x86 SIMD bodies (avx/math.rs:11-66): clamp, rint(x*log2e),
 // two-step ln2 reduction, degree-7 FMA Horner, 2^n through the exponent bits.

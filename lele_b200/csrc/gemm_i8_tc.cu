@@ -311,8 +311,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (MODE == EPI_MINMAX && nrows > 0) {
                 mnA = lb_warp_min(mnA); mxA = lb_warp_max(mxA); mnB = lb_warp_min(mnB); mxB = lb_warp_max(mxB);
                 if (lane == 0) {
-                    if (mnA <= mxA) { atomicMin(ep.minmax_keys + 2 * slice_a, lb_fkey(mnA)); atomicMax(ep.minmax_keys + 2 * slice_a + 1, lb_fkey(mxA)); }
-                    if (mnB <= mxB) { atomicMin(ep.minmax_keys + 2 * (slice_a + 1), lb_fkey(mnB)); atomicMax(ep.minmax_keys + 2 * (slice_a + 1) + 1, lb_fkey(mxB)); }
+                    if (mnA <= mxA) lb_mm_update(ep.minmax_keys, slice_a, mnA, mxA);
+                    if (mnB <= mxB) lb_mm_update(ep.minmax_keys, slice_a + 1, mnB, mxB);
                 }
             }
             if (MODE == EPI_ARGMAX && row_ok && best != 0ull) atomicMax(ep.argmax_keys + row, best);

@@ -61,9 +61,78 @@ layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
     if (minmax_keys) {
         vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
         if (lane == 0) {
-            long long slice = row / rows_per_slice;
-            atomicMin(minmax_keys + 2 * slice, lb_fkey(vmin));
-            atomicMax(minmax_keys + 2 * slice + 1, lb_fkey(vmax));
+            lb_mm_update(minmax_keys, row / rows_per_slice, vmin, vmax);
+        }
+    }
+}
+
+// Specialisation for the row widths of the SenseVoice encoder (N = 512, 560; N % 8 == 0): compile-time
+// trip counts, gamma/beta held in registers and reused over RPW consecutive rows per warp, no per-element
+// predication.  Same arithmetic and summation order as layer_norm_kernel.
+template <int N, int RPW>
+__global__ void __launch_bounds__(256)
+layer_norm_fixed_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        long long outer, float eps, float* __restrict__ out, unsigned* __restrict__ minmax_keys, int rows_per_slice) {
+    constexpr int NB = N / 32, REM = N % 32, REM8 = REM / 8;
+    static_assert(N % 8 == 0, "fixed LayerNorm kernel needs N % 8 == 0");
+    const int lane = threadIdx.x & 31;
+    const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+    if (row0 >= outer) return;
+    float g[NB], bt[NB], gr = 1.0f, br = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { g[i] = __ldg(gamma + 32 * i + lane); bt[i] = __ldg(beta + 32 * i + lane); }
+    if (REM > 0 && lane < REM) { gr = __ldg(gamma + NB * 32 + lane); br = __ldg(beta + NB * 32 + lane); }
+    const float inv_n = __fdiv_rn(1.0f, (float)N);
+    const long long slice_a = minmax_keys ? row0 / rows_per_slice : 0;
+    float mnA = 3.402823466e+38f, mxA = -3.402823466e+38f, mnB = 3.402823466e+38f, mxB = -3.402823466e+38f;
+#pragma unroll 1
+    for (int rr = 0; rr < RPW; ++rr) {
+        const long long row = row0 + rr;
+        if (row >= outer) break;
+        const float* xr = x + row * N;
+        float* o = out + row * N;
+        float v[NB], rem[REM8 > 0 ? REM8 : 1], xrem = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) v[i] = __ldg(xr + 32 * i + lane);
+#pragma unroll
+        for (int q = 0; q < REM8; ++q) rem[q] = __ldg(xr + NB * 32 + 8 * q + (lane & 7));
+        if (REM > 0 && lane < REM) xrem = __ldg(xr + NB * 32 + lane);
+        float ps = 0.0f, pq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { ps = __fadd_rn(ps, v[i]); pq = __fmaf_rn(v[i], v[i], pq); }
+        ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 8));  pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, 8));
+        ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 16)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, 16));
+#pragma unroll
+        for (int q = 0; q < REM8; ++q) { ps = __fadd_rn(ps, rem[q]); pq = __fmaf_rn(rem[q], rem[q], pq); }
+        ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 4)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, 4));
+        ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 2)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, 2));
+        ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, 1)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, 1));
+        ps = __shfl_sync(0xffffffffu, ps, 0); pq = __shfl_sync(0xffffffffu, pq, 0);
+        const float mean = __fmul_rn(ps, inv_n);
+        const float var = __fsub_rn(__fmul_rn(pq, inv_n), __fmul_rn(mean, mean));
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+        float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const float r = __fmaf_rn(__fmul_rn(__fsub_rn(v[i], mean), inv), g[i], bt[i]);
+            vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
+            o[32 * i + lane] = r;
+        }
+        if (REM > 0 && lane < REM) {
+            const float r = __fmaf_rn(__fmul_rn(__fsub_rn(xrem, mean), inv), gr, br);
+            vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
+            o[NB * 32 + lane] = r;
+        }
+        if (minmax_keys) {
+            if (row / rows_per_slice == slice_a) { mnA = fminf(mnA, vmin); mxA = fmaxf(mxA, vmax); }
+            else { mnB = fminf(mnB, vmin); mxB = fmaxf(mxB, vmax); }
+        }
+    }
+    if (minmax_keys) {
+        mnA = lb_warp_min(mnA); mxA = lb_warp_max(mxA); mnB = lb_warp_min(mnB); mxB = lb_warp_max(mxB);
+        if (lane == 0) {
+            if (mnA <= mxA) lb_mm_update(minmax_keys, slice_a, mnA, mxA);
+            if (mnB <= mxB) lb_mm_update(minmax_keys, slice_a + 1, mnB, mxB);
         }
     }
 }
@@ -72,6 +141,14 @@ int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma,
                          int n, float eps, float* out, unsigned* minmax_keys, int rows_per_slice) {
     if (outer == 0) return LELE_B200_OK;
     const int warps = 8;
+    constexpr int RPW = 4;
+    if (gamma && beta && (n == 512 || n == 560) && (!minmax_keys || rows_per_slice >= RPW)) {
+        const int grid = lb_ceil_div(outer, warps * RPW);
+        if (n == 512) layer_norm_fixed_kernel<512, RPW><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, eps, out, minmax_keys, rows_per_slice);
+        else layer_norm_fixed_kernel<560, RPW><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, eps, out, minmax_keys, rows_per_slice);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
+    }
     const int grid = lb_ceil_div(outer, warps);
     if (n <= 32 * 18) layer_norm_kernel<18><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
     else if (n <= 32 * 64) layer_norm_kernel<64><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);

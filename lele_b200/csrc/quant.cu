@@ -14,7 +14,7 @@
 // ---------------------------------------------------------------------------
 __global__ void minmax_init_kernel(unsigned* keys, int n_slices) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_slices) { keys[2 * i] = LB_KEY_MIN_INIT; keys[2 * i + 1] = LB_KEY_MAX_INIT; }
+    if (i < n_slices * LB_MM_SLOTS) { keys[2 * i] = LB_KEY_MIN_INIT; keys[2 * i + 1] = LB_KEY_MAX_INIT; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -44,13 +44,14 @@ slice_minmax_kernel(const float* __restrict__ x, long long slice_len, unsigned* 
         mn = lane < 8 ? smn[lane] : 3.402823466e+38f;
         mx = lane < 8 ? smx[lane] : -3.402823466e+38f;
         mn = lb_warp_min(mn); mx = lb_warp_max(mx);
-        if (lane == 0) { atomicMin(keys + 2 * slice, lb_fkey(mn)); atomicMax(keys + 2 * slice + 1, lb_fkey(mx)); }
+        if (lane == 0) lb_mm_update(keys, slice, mn, mx);
     }
 }
 
 // scale / zero point from the min/max keys (avx/quantization.rs:135-140)
 __device__ __forceinline__ void dq_params(const unsigned* keys, int slice, float& scale, float& zp, float& inv) {
-    float mn = lb_fkey_inv(keys[2 * slice]), mx = lb_fkey_inv(keys[2 * slice + 1]);
+    float mn, mx;
+    lb_mm_read(keys, slice, mn, mx);
     float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);
     float range = fmaxf(__fsub_rn(amax, amin), 1e-5f);
     scale = __fdiv_rn(range, 255.0f);
@@ -99,7 +100,7 @@ quantize_rows_kernel(const float* __restrict__ x, const unsigned* __restrict__ k
 }
 
 int lb_minmax_init(lele_b200_ctx* ctx, unsigned* keys, int n_slices) {
-    minmax_init_kernel<<<lb_ceil_div(n_slices, 128), 128, 0, ctx->stream>>>(keys, n_slices);
+    minmax_init_kernel<<<lb_ceil_div((long long)n_slices * LB_MM_SLOTS, 128), 128, 0, ctx->stream>>>(keys, n_slices);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }
@@ -151,7 +152,7 @@ extern "C" int lele_b200_dynamic_quantize_linear(lele_b200_ctx* ctx, const float
     }
     LB_REQUIRE(x && q, "dynamic_quantize_linear: NULL tensor");
     void* sc;
-    int rc = lb_scratch(ctx, sizeof(unsigned) * 2 * n_slices, &sc);
+    int rc = lb_scratch(ctx, sizeof(unsigned) * 2 * LB_MM_SLOTS * n_slices, &sc);
     if (rc) return rc;
     unsigned* keys = (unsigned*)sc;
     if ((rc = lb_minmax_init(ctx, keys, n_slices))) return rc;
@@ -297,9 +298,7 @@ gemm_i8_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ W
         if (ep.add1) v = __fadd_rn(v, ep.add1[o]);
         if (ep.add2) v = __fadd_rn(ep.add2[o], v);
         if (ep.minmax_keys) {
-            int sl = row / ep.rows_per_slice;
-            atomicMin(ep.minmax_keys + 2 * sl, lb_fkey(v));
-            atomicMax(ep.minmax_keys + 2 * sl + 1, lb_fkey(v));
+            lb_mm_update(ep.minmax_keys, row / ep.rows_per_slice, v, v);
         }
         if (ep.argmax_keys) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey(v) << 32) | (unsigned)col);
         if (ep.out) ep.out[o] = v;
@@ -353,7 +352,7 @@ extern "C" int lele_b200_fused_quantized_linear(lele_b200_ctx* ctx, const float*
     const long long M = (long long)n_slices * m;
     if (M == 0) return LELE_B200_OK;
     LB_REQUIRE(M < (1ll << 31), "fused_quantized_linear: too many rows");
-    size_t keys_bytes = align_up(sizeof(unsigned) * 2 * (size_t)n_slices, 256);
+    size_t keys_bytes = align_up(sizeof(unsigned) * 2 * LB_MM_SLOTS * (size_t)n_slices, 256);
     void* sc;
     int rc = lb_scratch(ctx, keys_bytes + lb_quant_scratch_bytes(M, w->k), &sc);
     if (rc) return rc;

@@ -269,7 +269,7 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc((void**)&m->att, sizeof(float) * M * m->d);
     if (!rc) rc = sv_alloc((void**)&m->f1, sizeof(float) * M * m->ffn);
     if (!rc) rc = sv_alloc((void**)&m->scores, sizeof(float) * B * m->heads * m->max_T * m->max_T);
-    if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * B * ((size_t)m->n_layers * 4 + 1));
+    if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1));
     if (!rc) rc = sv_alloc((void**)&m->amax_keys, sizeof(unsigned long long) * M);
     if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax));
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
@@ -310,7 +310,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     LB_REQUIRE(lang >= 0 && lang < m->n_embed && textnorm >= 0 && textnorm < m->n_embed, "sensevoice: prompt id out of range");
     const int n_sites = m->n_layers * 4 + 1;
     SV_RUN(P_MISC, lb_minmax_init(ctx, m->keys, n_sites * B));
-    auto site = [&](int s) { return m->keys + (size_t)2 * B * s; };
+    auto site = [&](int s) { return m->keys + (size_t)2 * LB_MM_SLOTS * B * s; };
     const LbQuantScratch qs = lb_quant_scratch_carve(m->qscratch, M, ffn > din ? ffn : din);
 
     {   // gather(embed, prompt ids) ++ concat ++ mul sqrt(d) ++ add pos
@@ -503,7 +503,7 @@ extern "C" int lele_b200_sensevoice_workspace(lele_b200_sensevoice* m, const cha
         {"lfr", m->lfr, sizeof(float) * B * t * m->d_in}, {"feats", m->feats, sizeof(float) * B * t * m->d_in},
         {"x0", m->x0, sizeof(float) * M * m->d_in}, {"x", m->x, sizeof(float) * M * m->d}, {"h", m->h, sizeof(float) * M * wide},
         {"qkv", m->qkv, sizeof(float) * M * 3 * m->d}, {"fsmn", m->fsmn, sizeof(float) * M * m->d}, {"att", m->att, sizeof(float) * M * m->d},
-        {"f1", m->f1, sizeof(float) * M * m->ffn}, {"keys", m->keys, sizeof(unsigned) * 2 * B * ((size_t)m->n_layers * 4 + 1)}};
+        {"f1", m->f1, sizeof(float) * M * m->ffn}, {"keys", m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1)}};
     for (auto& e : tab)
         if (strcmp(e.n, name) == 0) { *dptr = e.p; *nbytes = e.b; return LELE_B200_OK; }
     lb_set_error("sensevoice_workspace: unknown buffer '%s'", name);

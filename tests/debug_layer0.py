@@ -25,7 +25,8 @@ T = t + 4; d = 512; M = B * T
 def rel(a, b): return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 def keyinv(k):
     k = k.astype(np.uint32); b = np.where(k & 0x80000000, k & 0x7fffffff, ~k).astype(np.uint32); return b.view(np.float32)
-keys = m.workspace("keys", (3 * 4 + 1, B, 2), np.uint32)
+keys8 = m.workspace("keys", (3 * 4 + 1, B, 8, 2), np.uint32)   # sharded: [site][clip][slot][min,max]
+keys = np.stack([keys8[..., 0].min(-1), keys8[..., 1].max(-1)], -1)
 qkv_g = m.workspace("qkv", (M, 1536)); fsmn_g = m.workspace("fsmn", (M, 512)); att_g = m.workspace("att", (M, 512)); f1_g = m.workspace("f1", (M, 2048))
 x0_g = m.workspace("x0", (M, 560))
 for c in range(B):

@@ -64,11 +64,11 @@ def test_tcgen05_attention_stage(small_model_tc, t):
     m.forward(feats, 3, 0, n_layers=1)
     T = t + 4
     qkv = m.workspace("qkv", (B * T, 1536)); att = m.workspace("att", (B * T, 512))
-    keys = m.workspace("keys", (SMALL.n_layers * 4 + 1, B, 2), np.uint32)
+    keys = m.workspace("keys", (SMALL.n_layers * 4 + 1, B, 8, 2), np.uint32)    # [site][clip][slot][min,max], sharded atomics
     for c in range(B):
         want = _oracle_attention(qkv[c * T:(c + 1) * T], T)
         assert rel_err(att[c * T:(c + 1) * T], want) < 1e-5, (t, c)
-        k = keys[1, c].astype(np.uint32)                      # fused per-clip min/max of the attention output
+        k = np.array([keys[1, c, :, 0].min(), keys[1, c, :, 1].max()], np.uint32)   # fused per-clip min/max of the attention output
         dec = np.where(k & 0x80000000, k & 0x7fffffff, ~k).astype(np.uint32).view(np.float32)
         got = att[c * T:(c + 1) * T]
         assert dec[0] == got.min() and dec[1] == got.max()
