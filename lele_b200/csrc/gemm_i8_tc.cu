@@ -229,17 +229,25 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int row = first_row + lane;
             const bool row_ok = row < M;
             const int gcol_w = n_blk * BN + cgrp * 64;                 // first global column of this warp
-            // column metadata of this warp's 64 columns (arrays are padded to a multiple of 256 columns)
-            __syncwarp();
-            sts_s32(meta_s + 4 * lane, __ldg(ep.colsum + gcol_w + lane));
-            sts_s32(meta_s + 4 * (32 + lane), __ldg(ep.colsum + gcol_w + 32 + lane));
-            sts_f32(meta_s + 256 + 4 * lane, __ldg(ep.w_scale + gcol_w + lane));
-            sts_f32(meta_s + 256 + 4 * (32 + lane), __ldg(ep.w_scale + gcol_w + 32 + lane));
-            sts_f32(meta_s + 512 + 4 * lane, __ldg(ep.bias + gcol_w + lane));
-            sts_f32(meta_s + 512 + 4 * (32 + lane), __ldg(ep.bias + gcol_w + 32 + lane));
             int rs = 0, zpa = 0; float sa = 0.0f;
             if (row_ok) { rs = __ldg(ep.rowsum + row); zpa = __ldg(ep.row_zp + row); sa = __ldg(ep.row_scale + row); }
             const int row_corr = args.K * zpa * ep.w_zp - ep.w_zp * rs;
+            // Per-warp column metadata, pre-combined with the activation parameters of the clip that owns the warp's
+            // first row ("A"): zcA[c] = zp_A * colsum[c], csA[c] = scale_A * w_scale[c].  A warp's 32 rows touch a
+            // second clip only at clip boundaries (1 warp in ~8 for T' = 271); those rows take the uncombined path.
+            const int rps = ep.rows_per_slice > 0 ? ep.rows_per_slice : 0x7fffffff;
+            const int slice_first = first_row / rps;
+            const bool all_a = __all_sync(0xffffffffu, !row_ok || (row / rps) == slice_first);
+            const int zpa_a = __shfl_sync(0xffffffffu, zpa, 0);
+            const float sa_a = __shfl_sync(0xffffffffu, sa, 0);
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int c = hh * 32 + lane;
+                sts_s32(meta_s + 4 * c, zpa_a * __ldg(ep.colsum + gcol_w + c));
+                sts_f32(meta_s + 256 + 4 * c, __fmul_rn(sa_a, __ldg(ep.w_scale + gcol_w + c)));
+                sts_f32(meta_s + 512 + 4 * c, __ldg(ep.bias + gcol_w + c));
+            }
             unsigned long long best = 0ull;
             const int slice_a = (MODE == EPI_MINMAX) ? first_row / ep.rows_per_slice : 0;
             float mnA = 3.402823466e+38f, mxA = -3.402823466e+38f, mnB = 3.402823466e+38f, mxB = -3.402823466e+38f;
@@ -255,27 +263,33 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), r);
                 if (gcol0 >= N || nrows <= 0) continue;                // warp-uniform
                 // ---- phase 1 ----
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int4 cs = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
-                    const int4 wsb = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
-                    const int4 bib = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
-                    const int csv[4] = {cs.x, cs.y, cs.z, cs.w};
-                    const float wsv[4] = {__int_as_float(wsb.x), __int_as_float(wsb.y), __int_as_float(wsb.z), __int_as_float(wsb.w)};
-                    const float biv[4] = {__int_as_float(bib.x), __int_as_float(bib.y), __int_as_float(bib.z), __int_as_float(bib.w)};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int acci = (int)r[q * 4 + e] + row_corr - zpa * csv[e];
-                        float t = __fmul_rn((float)acci, __fmul_rn(sa, wsv[e]));
-                        t = ep.has_bias ? __fadd_rn(t, biv[e]) : t;
-                        t = fmaxf(t, relu_lo);
-                        if (MODE == EPI_ARGMAX) {
-                            if (row_ok && gcol0 + q * 4 + e < N) {
-                                unsigned long long key = ((unsigned long long)lb_fkey(t) << 32) | (unsigned)(gcol0 + q * 4 + e);
-                                best = key > best ? key : best;
-                            }
+                auto finish = [&](float t, float bias_v, int idx) {
+                    t = ep.has_bias ? __fadd_rn(t, bias_v) : t;
+                    t = fmaxf(t, relu_lo);
+                    if (MODE == EPI_ARGMAX) {
+                        if (row_ok && gcol0 + idx < N) {
+                            unsigned long long key = ((unsigned long long)lb_fkey(t) << 32) | (unsigned)(gcol0 + idx);
+                            best = key > best ? key : best;
                         }
-                        sts_f32(tile_s + 4 * (lane * 33 + q * 4 + e), t);
+                    }
+                    sts_f32(tile_s + 4 * (lane * 33 + idx), t);
+                };
+                if (all_a) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int4 zc = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
+                        const int4 csb = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
+                        const int4 bib = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
+                        finish(__fmul_rn((float)((int)r[q * 4 + 0] + row_corr - zc.x), __int_as_float(csb.x)), __int_as_float(bib.x), q * 4 + 0);
+                        finish(__fmul_rn((float)((int)r[q * 4 + 1] + row_corr - zc.y), __int_as_float(csb.y)), __int_as_float(bib.y), q * 4 + 1);
+                        finish(__fmul_rn((float)((int)r[q * 4 + 2] + row_corr - zc.z), __int_as_float(csb.z)), __int_as_float(bib.z), q * 4 + 2);
+                        finish(__fmul_rn((float)((int)r[q * 4 + 3] + row_corr - zc.w), __int_as_float(csb.w)), __int_as_float(bib.w), q * 4 + 3);
+                    }
+                } else {   // the warp straddles a clip boundary: uncombined metadata straight from global (L1-resident)
+#pragma unroll
+                    for (int idx = 0; idx < 32; ++idx) {
+                        const int acci = (int)r[idx] + row_corr - zpa * __ldg(ep.colsum + gcol0 + idx);
+                        finish(__fmul_rn((float)acci, __fmul_rn(sa, __ldg(ep.w_scale + gcol0 + idx))), __ldg(ep.bias + gcol0 + idx), idx);
                     }
                 }
                 if (MODE == EPI_ARGMAX && !ep.out) continue;           // ids only: nothing to write

@@ -64,7 +64,12 @@ __device__ __forceinline__ float dq_one(float v, float inv, float zp, bool simd)
 }
 
 // one warp per row: f32 [M,K] -> u8 [M,K] + row sums + per-row (scale, zp) for the GEMM epilogue
-// (dq_to_u8_rowsums_avx2, avx/quantization.rs:102-221)
+// (dq_to_u8_rowsums_avx2, avx/quantization.rs:102-221).  kAligned: K % 8 == 0 (every SenseVoice shape), i.e.
+// the whole row is "SIMD body" (fma + round-half-even) and no per-element tail predicate is needed.
+__device__ __forceinline__ unsigned dq_body(float v, float inv, float zp) {
+    return (unsigned)fminf(fmaxf(rintf(__fmaf_rn(v, inv, zp)), 0.0f), 255.0f);
+}
+template <bool kAligned>
 __global__ void __launch_bounds__(256)
 quantize_rows_kernel(const float* __restrict__ x, const unsigned* __restrict__ keys, long long M, int rows_per_slice, int K,
                      uint8_t* __restrict__ a_u8, int32_t* __restrict__ rowsum, float* __restrict__ row_scale,
@@ -77,18 +82,20 @@ quantize_rows_kernel(const float* __restrict__ x, const unsigned* __restrict__ k
     dq_params(keys, slice, scale, zp, inv);
     const float* xr = x + row * K;
     uint8_t* ar = a_u8 + row * K;
-    const int k_simd = (K / 8) * 8;
     int sum = 0;
-    if ((K & 3) == 0 && ((((uintptr_t)xr) & 15) == 0) && ((((uintptr_t)ar) & 3) == 0)) {
-        for (int c = lane; c < (K >> 2); c += 32) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(xr) + c);
-            int j = c << 2;
-            unsigned q0 = (unsigned)dq_one(v.x, inv, zp, j < k_simd), q1 = (unsigned)dq_one(v.y, inv, zp, j + 1 < k_simd),
-                     q2 = (unsigned)dq_one(v.z, inv, zp, j + 2 < k_simd), q3 = (unsigned)dq_one(v.w, inv, zp, j + 3 < k_simd);
+    if (kAligned) {
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        unsigned* a4 = reinterpret_cast<unsigned*>(ar);
+        const int nv = K >> 2;
+#pragma unroll 4
+        for (int c = lane; c < nv; c += 32) {
+            const float4 v = __ldg(x4 + c);
+            const unsigned q0 = dq_body(v.x, inv, zp), q1 = dq_body(v.y, inv, zp), q2 = dq_body(v.z, inv, zp), q3 = dq_body(v.w, inv, zp);
             sum += (int)(q0 + q1 + q2 + q3);
-            reinterpret_cast<unsigned*>(ar)[c] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            a4[c] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
         }
     } else {
+        const int k_simd = (K / 8) * 8;
         for (int j = lane; j < K; j += 32) {
             unsigned q = (unsigned)dq_one(xr[j], inv, zp, j < k_simd);
             sum += (int)q;
@@ -115,7 +122,10 @@ int lb_slice_minmax(lele_b200_ctx* ctx, const float* x, int n_slices, long long 
 }
 int lb_quantize_rows(lele_b200_ctx* ctx, const float* x, const unsigned* keys, long long M, int rows_per_slice, int K,
                      uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp) {
-    quantize_rows_kernel<<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, K, a_u8, rowsum, row_scale, row_zp);
+    if (K % 8 == 0 && ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)a_u8) & 3) == 0))
+        quantize_rows_kernel<true><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, K, a_u8, rowsum, row_scale, row_zp);
+    else
+        quantize_rows_kernel<false><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, K, a_u8, rowsum, row_scale, row_zp);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

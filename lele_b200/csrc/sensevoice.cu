@@ -169,6 +169,9 @@ struct lele_b200_sensevoice {
     cudaGraphExec_t graph_exec = nullptr;
     GraphKey graph_key = {};
     unsigned long long graph_launches = 0;
+    // side stream: the HBM-bound FSMN block runs concurrently with the latency-bound attention (both only read qkv)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     struct Span { int cls; cudaEvent_t a, b; };
@@ -275,6 +278,8 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("LELE_B200_GRAPH"); m->use_graph = (e && e[0] == '0') ? 0 : 1; }
+    if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); m->side = nullptr; }
     if (!rc) rc = sv_alloc((void**)&m->pcm_stage, sizeof(float) * B * (size_t)max_samples);
     if (!rc) rc = sv_alloc((void**)&m->ids_stage, sizeof(int32_t) * M);
     if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
@@ -291,6 +296,9 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : m->ev_pool) cudaEventDestroy(e);
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
     return LELE_B200_OK;
 }
@@ -331,15 +339,22 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             ep.out = m->qkv; ep.rows_per_slice = T;
             SV_LINEAR(ctx, m,m->h, site(l * 4 + 0), M, T, m->lin[l * 4 + 0], qs, ep);
         }
+        const bool fork = !m->profiling && m->side != nullptr;
+        cudaStream_t fs = fork ? m->side : ctx->stream;
+        if (fork) {
+            LB_CHECK_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
+            LB_CHECK_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+        }
         {
             ProfScope ps(m, ctx, P_FSMN);
             if (m->fsmn_k == 11)
-                fsmn_window_kernel<11><<<dim3(lb_ceil_div(d, 128), lb_ceil_div(T, FS_TCH), B), 128, 0, ctx->stream>>>(
+                fsmn_window_kernel<11><<<dim3(lb_ceil_div(d, 128), lb_ceil_div(T, FS_TCH), B), 128, 0, fs>>>(
                     m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), T, d, m->fsmn);
             else
-                fsmn_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), B, T, d, m->fsmn_k, m->fsmn);
+                fsmn_kernel<<<grid_for(M * d), 256, 0, fs>>>(m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), B, T, d, m->fsmn_k, m->fsmn);
             LB_LAUNCH_CHECK(ctx);
         }
+        if (fork) LB_CHECK_CUDA(cudaEventRecord(m->ev_join, m->side));
         if (!m->attn_simt && lb_attention_tc_supported(T, d, H)) {
             // fused tcgen05 attention (3xTF32), per-clip min/max of the output fused in its epilogue
             SV_RUN(P_ATTN_TC, lb_attention_tc(ctx, m->qkv, B, T, d, H, qscale, m->attn_scratch, m->att, site(l * 4 + 1)));
@@ -366,6 +381,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             }
             SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->att, B, (long long)T * d, site(l * 4 + 1)));
         }
+        if (fork) LB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_join, 0));   // out-proj epilogue adds the FSMN memory
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->x; ep.rows_per_slice = T; ep.add1 = m->fsmn; ep.add2 = (cur == d) ? xin : nullptr;   // x = x + (lin + fsmn)
