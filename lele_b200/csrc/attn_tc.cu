@@ -19,6 +19,7 @@
 // Geometry: dk = 128, T <= 288 keys (SenseVoice: 271).  Other shapes use the CUDA-core path.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -35,8 +36,11 @@ constexpr int TILE_V = DK * 128;      // 16 KB  [128 dims][32 keys]
 constexpr int STAGE_C = 2 * TILE_P + 2 * TILE_V;   // 64 KB
 constexpr int NSTAGE_C = 3;
 constexpr int SMEM_MAIN = NSTAGE_A * STAGE_A;      // 208 KB (>= NSTAGE_C * STAGE_C = 192 KB)
-constexpr int SMEM_BYTES = SMEM_MAIN + 1024 + 256 + 2 * 128 * 4;   // + barriers + row-sum exchange
-constexpr int NUM_THREADS = 384;   // TMA, MMA, TMEM-alloc, spare + 8 softmax/epilogue warps
+constexpr int MAX_KCHUNKS = 2 * NH / KC;           // 9
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_BYTES = SMEM_MAIN + 1024 + BAR_BYTES + 8 * 128 * 4;   // + barriers + row max / row sum exchange
+constexpr int NGRP = 4;            // softmax groups (4 warps each)
+constexpr int NUM_THREADS = 128 + NGRP * 128;   // TMA, MMA, TMEM-alloc, spare + 16 softmax/epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int O_COL = 2 * NH;         // O accumulator starts at TMEM column 288
 
@@ -111,6 +115,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void sts_v4f(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 struct AttnArgs {
@@ -118,22 +132,21 @@ struct AttnArgs {
     int rows_per_slice;           // = T (one clip per slice)
     float* out;                   // att [B*T, H*DK]
     unsigned* minmax_keys;        // [B][2] or NULL
+    float scale_l2e;              // d_k^-1/2 * log2(e): the query scale is folded into the exponent
+    int dbg;                      // LELE_B200_ATTN_DBG=1: CTA 300 prints its phase timeline (clock64)
 };
+#define ATT_DBG(idx) do { if (args.dbg && lane == 0) dbg_t[warp][idx] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------
 // pre-pass: tf32 hi/lo operand copies
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-attn_split_qk_kernel(const float* __restrict__ qkv, long long M, int d, float qscale, float* __restrict__ q_hi, float* __restrict__ q_lo,
-                     float* __restrict__ k_hi, float* __restrict__ k_lo) {
-    const long long total = M * d;
+attn_split_qk_kernel(const float* __restrict__ qkv, long long M, int d, float* __restrict__ qk_lo) {
+    const long long total = M * 2 * d;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long r = i / d; int c = (int)(i - r * d);
-        float q = __fmul_rn(qkv[r * 3 * d + c], qscale);          // mul(q, d_k^-1/2) exactly as the reference
-        float k = qkv[r * 3 * d + d + c];
-        float qh = tf32_hi(q), kh = tf32_hi(k);
-        q_hi[i] = qh; q_lo[i] = __fsub_rn(q, qh);
-        k_hi[i] = kh; k_lo[i] = __fsub_rn(k, kh);
+        long long r = i / (2 * d); int c = (int)(i - r * 2 * d);
+        const float x = qkv[r * 3 * d + c];                      // q (c < d) or k
+        qk_lo[i] = __fsub_rn(x, tf32_hi(x));
     }
 }
 // V [T, dk] per (b,h) -> V^T [dk, Tp] (keys contiguous, zero padded), hi/lo
@@ -164,21 +177,25 @@ attn_split_vt_kernel(const float* __restrict__ qkv, int T, int Tp, int d, int H,
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
                const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
-               const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl, const AttnArgs args) {
+               const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
+               const __grid_constant__ CUtensorMap map_out, const AttnArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + SMEM_MAIN);
     uint64_t* full_a = bars;                  // [2] TMA -> MMA (phase A)
     uint64_t* empty_a = bars + 2;             // [2] MMA -> TMA
     uint64_t* s_full = bars + 4;              // S complete (also: phase-A smem is free)
-    uint64_t* v_full = bars + 5;              // [3] V chunk landed
-    uint64_t* p_full = bars + 8;              // [3] P chunk written by the softmax warps
-    uint64_t* pv_empty = bars + 11;           // [3] MMA consumed the stage
-    uint64_t* o_full = bars + 14;             // O complete
-    uint32_t* tmem_base_smem = (uint32_t*)(bars + 16);
-    float* xsum = (float*)(smem + SMEM_MAIN + 256);   // [2][128] partial row sums of the two softmax groups
+    // phase-C barriers are per 32-key CHUNK (single use each, parity 0): the four softmax groups run up to two ring
+    // turns ahead of the tensor core, which a per-stage barrier's 1-bit phase parity could not tell apart
+    uint64_t* v_full = bars + 5;              // [MAX_KCHUNKS] V chunk landed
+    uint64_t* p_full = v_full + MAX_KCHUNKS;  // [MAX_KCHUNKS] P chunk written by the softmax warps
+    uint64_t* pv_done = p_full + MAX_KCHUNKS; // [MAX_KCHUNKS] MMA consumed the chunk (its ring stage is free again)
+    uint64_t* o_full = pv_done + MAX_KCHUNKS; // O complete
+    uint32_t* tmem_base_smem = (uint32_t*)(o_full + 1);
+    float* xch = (float*)(smem + SMEM_MAIN + BAR_BYTES);    // [2][NGRP][128] partial row max / row sums of the softmax groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ long long dbg_t[20][8];
     const int qt = blockIdx.x % args.n_qtiles;
     const int bh = blockIdx.x / args.n_qtiles;
     const int h = bh % args.H, b = bh / args.H;
@@ -190,7 +207,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
         mbar_init(s_full, 1); mbar_init(o_full, 1);
-        for (int s = 0; s < NSTAGE_C; ++s) { mbar_init(&v_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&pv_empty[s], 1); }
+        for (int c = 0; c < MAX_KCHUNKS; ++c) { mbar_init(&v_full[c], 1); mbar_init(&p_full[c], 4); mbar_init(&pv_done[c], 1); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -202,6 +219,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    if (warp == 0) ATT_DBG(0);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -222,12 +240,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             // phase C reuses the same shared memory: wait until every phase-A MMA has retired
             mbar_wait(s_full, 0);
             for (int c = 0; c < NKC; ++c) {
-                const int s = c % NSTAGE_C; const uint32_t ph = (c / NSTAGE_C) & 1;
-                mbar_wait(&pv_empty[s], ph ^ 1);
+                const int s = c % NSTAGE_C;
+                if (c >= NSTAGE_C) mbar_wait(&pv_done[c - NSTAGE_C], 0);
                 uint8_t* st = smem + s * STAGE_C;
-                mbar_expect_tx(&v_full[s], 2 * TILE_V);
-                tma_load_4d(st + 2 * TILE_P, &map_vh, &v_full[s], c * KC, 0, h, b);
-                tma_load_4d(st + 2 * TILE_P + TILE_V, &map_vl, &v_full[s], c * KC, 0, h, b);
+                mbar_expect_tx(&v_full[c], 2 * TILE_V);
+                tma_load_4d(st + 2 * TILE_P, &map_vh, &v_full[c], c * KC, 0, h, b);
+                tma_load_4d(st + 2 * TILE_P + TILE_V, &map_vl, &v_full[c], c * KC, 0, h, b);
             }
         }
     } else if (warp == 1) {
@@ -238,6 +256,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 const int s = kc & 1; const uint32_t ph = (kc >> 1) & 1;
                 mbar_wait(&full_a[s], ph);
                 tc_fence_after();
+                if (kc == 0) ATT_DBG(1);
+                if (kc == 3) ATT_DBG(2);
                 const uint32_t base = smem_u32(smem + s * STAGE_A);
                 const uint64_t qh = make_smem_desc(base), ql = make_smem_desc(base + TILE_Q);
                 const uint64_t kh = make_smem_desc(base + 2 * TILE_Q), kl = make_smem_desc(base + 2 * TILE_Q + TILE_K);
@@ -258,9 +278,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 if (kc == DK / KC - 1) umma_commit(s_full);
             }
             for (int c = 0; c < NKC; ++c) {
-                const int s = c % NSTAGE_C; const uint32_t ph = (c / NSTAGE_C) & 1;
-                mbar_wait(&v_full[s], ph);
-                mbar_wait(&p_full[s], ph);
+                const int s = c % NSTAGE_C;
+                mbar_wait(&v_full[c], 0);
+                mbar_wait(&p_full[c], 0);
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + s * STAGE_C);
                 const uint64_t phd = make_smem_desc(base), pld = make_smem_desc(base + TILE_P);
@@ -273,93 +293,117 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                     umma_tf32(dO, phd + ko, vld + ko, ID_O, 1u);
                     umma_tf32(dO, pld + ko, vhd + ko, ID_O, 1u);
                 }
-                umma_commit(&pv_empty[s]);
+                umma_commit(&pv_done[c]);
                 if (c == NKC - 1) umma_commit(o_full);
             }
         }
     } else if (warp >= 4) {
-        // ===================== softmax + epilogue: 8 warps, two threads per query row =====================
-        // group 0 (warps 4-7) takes the even 32-key chunks, group 1 (warps 8-11) the odd ones; both read the
-        // whole row for the max (cheap), each accumulates its share of the row sum, exchanged through smem.
+        // ===================== softmax + epilogue: 16 warps, four threads per query row =====================
+        // group g (warps 4+4g .. 7+4g) owns the 32-key chunks g, g+4, g+8: partial row max / row sum per group,
+        // exchanged through shared memory (named barrier over the 512 softmax threads).
         const int quad = warp & 3;
         const int grp = (warp - 4) >> 2;
         const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const int n8 = T & ~7;
         mbar_wait(s_full, 0);
         tc_fence_after();
+        ATT_DBG(3);
         // ---- pass 1: row max over the T valid keys ----
         float mx = -3.402823466e+38f;
-        for (int c = 0; c < NKC; ++c) {
+        for (int c = grp; c < NKC; c += NGRP) {
             uint32_t v[32];
             tmem_ld32(trow + (uint32_t)(c * KC), v);
+            if (c * KC + 32 <= T) {                       // warp-uniform: full chunk, no per-element masking
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (c * KC + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (c * KC + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
         }
-        // ---- pass 2: e = exp(s - max) (polynomial exp on the x86 SIMD body j < T/8*8, libm on the tail, as the
-        //      reference softmax), tf32 hi/lo split into the swizzled K-major P tiles ----
+        xch[grp * AQ + r] = mx;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        mx = fmaxf(fmaxf(xch[r], xch[AQ + r]), fmaxf(xch[2 * AQ + r], xch[3 * AQ + r]));
+        ATT_DBG(4);
+        // ---- pass 2: e = exp(s - max) = 2^((s - max) * log2 e): one FFMA + one MUFU.EX2 per element (ex2.approx is
+        //      accurate to ~2^-22 relative, the same class as the reference's degree-7 polynomial), then the tf32
+        //      hi/lo split into the swizzled K-major P tiles ----
+        const float L2E = args.scale_l2e;               // scores are unscaled: exp((s - max) * scale) = 2^((s - max) * scale * log2 e)
+        const float nmx = -__fmul_rn(mx, L2E);
         float psum = 0.0f;
-        for (int c = grp; c < NKC; c += 2) {
-            const int s = c % NSTAGE_C; const uint32_t ph = (c / NSTAGE_C) & 1;
+        for (int c = grp; c < NKC; c += NGRP) {
+            const int s = c % NSTAGE_C;
             uint32_t v[32];
             tmem_ld32(trow + (uint32_t)(c * KC), v);
             float e[32];
+            if (c * KC + 32 <= T) {                       // warp-uniform fast path: full chunk
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int j = c * KC + i;
-                const float dlt = __fsub_rn(__uint_as_float(v[i]), mx);
-                e[i] = j < n8 ? lb_cephes_expf(dlt) : (j < T ? expf(dlt) : 0.0f);
-                psum += e[i];
+                for (int i = 0; i < 32; ++i) e[i] = ex2_approx(__fmaf_rn(__uint_as_float(v[i]), L2E, nmx));
+            } else {                                      // last chunk: keys >= T contribute exactly 0
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float t = ex2_approx(__fmaf_rn(__uint_as_float(v[i]), L2E, nmx));
+                    e[i] = (c * KC + i < T) ? t : 0.0f;
+                }
             }
-            mbar_wait(&pv_empty[s], ph ^ 1);
-            uint8_t* st = smem + s * STAGE_C;
-            float* ph_row = (float*)(st + r * 128);
-            float* pl_row = (float*)(st + TILE_P + r * 128);
+            {   // pairwise tree keeps the dependent-add chain short
+                float t8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t8[i] = (e[i] + e[i + 8]) + (e[i + 16] + e[i + 24]);
+                psum += ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
+            }
+            if (c >= NSTAGE_C) mbar_wait(&pv_done[c - NSTAGE_C], 0);
+            const uint32_t ph_row = smem_u32(smem + s * STAGE_C) + (uint32_t)r * 128u;
+            const uint32_t pl_row = ph_row + TILE_P;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int phys = (q ^ (r & 7)) * 4;      // 16-byte chunk XOR (row % 8)
-                float4 hi, lo;
-                hi.x = tf32_hi(e[q * 4 + 0]); lo.x = __fsub_rn(e[q * 4 + 0], hi.x);
-                hi.y = tf32_hi(e[q * 4 + 1]); lo.y = __fsub_rn(e[q * 4 + 1], hi.y);
-                hi.z = tf32_hi(e[q * 4 + 2]); lo.z = __fsub_rn(e[q * 4 + 2], hi.z);
-                hi.w = tf32_hi(e[q * 4 + 3]); lo.w = __fsub_rn(e[q * 4 + 3], hi.w);
-                *reinterpret_cast<float4*>(ph_row + phys) = hi;
-                *reinterpret_cast<float4*>(pl_row + phys) = lo;
+                const uint32_t phys = (uint32_t)((q ^ (r & 7)) << 4);      // 16-byte chunk XOR (row % 8)
+                const float h0 = tf32_hi(e[q * 4 + 0]), h1 = tf32_hi(e[q * 4 + 1]), h2 = tf32_hi(e[q * 4 + 2]), h3 = tf32_hi(e[q * 4 + 3]);
+                sts_v4f(ph_row + phys, h0, h1, h2, h3);
+                sts_v4f(pl_row + phys, __fsub_rn(e[q * 4 + 0], h0), __fsub_rn(e[q * 4 + 1], h1), __fsub_rn(e[q * 4 + 2], h2), __fsub_rn(e[q * 4 + 3], h3));
             }
             fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[s]);
+            if (lane == 0) mbar_arrive(&p_full[c]);
         }
-        // exchange the two partial row sums
-        xsum[grp * AQ + r] = psum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float inv = __fdiv_rn(1.0f, __fadd_rn(xsum[r], xsum[AQ + r]));
-        // ---- epilogue: O / sum -> att, per-clip min/max; transposed through smem for coalesced stores ----
+        ATT_DBG(5);
+        // exchange the partial row sums (xch was last read before every thread passed the first named barrier +
+        // its own pass 2; a second barrier id keeps the max / sum exchanges apart)
+        xch[4 * AQ + grp * AQ + r] = psum;
+        asm volatile("bar.sync 2, 512;" ::: "memory");
+        const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(xch[4 * AQ + r], xch[5 * AQ + r]), __fadd_rn(xch[6 * AQ + r], xch[7 * AQ + r])));
+        // ---- epilogue: O / sum -> att (+ per-clip min/max): each warp owns 32 rows x 32 dims, staged in a swizzled
+        //      4 KB tile and written by one TMA tensor store (rows >= T are clipped by the 3-D map) ----
         mbar_wait(o_full, 0);
         tc_fence_after();
-        float* stg = (float*)smem + (size_t)(warp - 4) * (32 * 33);   // phase-C buffers are idle now (all MMAs retired)
-        float mn = 3.402823466e+38f, mxo = -3.402823466e+38f;
+        ATT_DBG(6);
+        const uint32_t stg = smem_u32(smem) + (uint32_t)(warp - 4) * 4096u;   // phase-C buffers are idle now (all MMAs retired)
         const int row0 = qt * AQ + quad * 32;
-        const int nrows = min(32, T - row0);
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            const int ch = grp * 2 + cc;
+        if (row0 < T) {                                   // warp-uniform
             uint32_t v[32];
-            tmem_ld32(trow + (uint32_t)(O_COL + ch * 32), v);
+            tmem_ld32(trow + (uint32_t)(O_COL + grp * 32), v);
+            float mn = 3.402823466e+38f, mxo = -3.402823466e+38f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __fmul_rn(__uint_as_float(v[i]), inv);
-            __syncwarp();
-            for (int rr = 0; rr < nrows; ++rr) {
-                const float val = stg[rr * 33 + lane];
-                args.out[((long long)b * T + row0 + rr) * (args.H * DK) + h * DK + ch * 32 + lane] = val;
-                mn = fminf(mn, val); mxo = fmaxf(mxo, val);
+            for (int q = 0; q < 8; ++q) {
+                const float o0 = __fmul_rn(__uint_as_float(v[q * 4 + 0]), inv), o1 = __fmul_rn(__uint_as_float(v[q * 4 + 1]), inv);
+                const float o2 = __fmul_rn(__uint_as_float(v[q * 4 + 2]), inv), o3 = __fmul_rn(__uint_as_float(v[q * 4 + 3]), inv);
+                mn = fminf(fminf(mn, o0), fminf(fminf(o1, o2), o3));
+                mxo = fmaxf(fmaxf(mxo, o0), fmaxf(fmaxf(o1, o2), o3));
+                sts_v4f(stg + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), o0, o1, o2, o3);
             }
+            fence_proxy_async();
             __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&map_out, stg, h * DK + grp * 32, row0, b);
+                tma_store_wait_all();
+            }
+            if (args.minmax_keys) {
+                const bool ok = row0 + lane < T;
+                mn = lb_warp_min(ok ? mn : 3.402823466e+38f); mxo = lb_warp_max(ok ? mxo : -3.402823466e+38f);
+                if (lane == 0) lb_mm_update(args.minmax_keys, b, mn, mxo);
+            }
         }
-        if (args.minmax_keys && nrows > 0) {
-            mn = lb_warp_min(mn); mxo = lb_warp_max(mxo);
-            if (lane == 0) lb_mm_update(args.minmax_keys, b, mn, mxo);
-        }
+        ATT_DBG(7);
     }
 
     tc_fence_before();
@@ -367,6 +411,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+    if (args.dbg && threadIdx.x == 0 && (blockIdx.x == 300 || blockIdx.x == 301 || blockIdx.x == 302)) {
+        const long long t0 = dbg_t[0][0];
+        printf("ATTDBG blk %d A0 %lld A3 %lld | S_done %lld p1 %lld p2 %lld/%lld O_done %lld epi %lld/%lld end %lld\n", blockIdx.x, dbg_t[1][1] - t0,
+               dbg_t[1][2] - t0, dbg_t[4][3] - t0, dbg_t[4][4] - t0, dbg_t[4][5] - t0, dbg_t[8][5] - t0, dbg_t[4][6] - t0, dbg_t[4][7] - t0,
+               dbg_t[8][7] - t0, clock64() - t0);
     }
 }
 
@@ -413,6 +463,25 @@ int make_map_f32_4d(CUtensorMap* map, const void* ptr, const unsigned long long 
     ctx->tmaps.emplace(h, std::move(blob));
     return LELE_B200_OK;
 }
+int make_map_f32_out3d(CUtensorMap* map, const void* ptr, unsigned long long cols, unsigned long long rows, unsigned long long clips) {
+    lele_b200_ctx* ctx = g_ctx_for_maps;
+    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(lb_hash_mix(0x6f337364ull, (unsigned long long)(uintptr_t)ptr), cols), rows), clips);
+    auto it = ctx->tmaps.find(h);
+    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
+    cuuint64_t d[3] = {cols, rows, clips};
+    cuuint64_t st[2] = {cols * 4, rows * cols * 4};
+    cuuint32_t bx[3] = {32, 32, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(att out) failed (%d)", (int)r); return LELE_B200_ERR_CUDA; }
+    std::vector<unsigned char> blob(sizeof(CUtensorMap));
+    memcpy(blob.data(), map, sizeof(CUtensorMap));
+    ctx->tmaps.emplace(h, std::move(blob));
+    return LELE_B200_OK;
+}
 int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
 }  // namespace
 
@@ -420,31 +489,41 @@ bool lb_attention_tc_supported(int T, int d, int H) { return H > 0 && d == H * D
 
 size_t lb_attention_tc_scratch_bytes(int B, int T, int d, int H) {
     const size_t Tp = (size_t)((T + 3) / 4 * 4);
-    return sizeof(float) * (4 * (size_t)B * T * d + 2 * (size_t)B * H * DK * Tp) + 6 * 256;
+    return sizeof(float) * (2 * (size_t)B * T * d + 2 * (size_t)B * H * DK * Tp) + 3 * 256;
 }
 
-// qkv [B*T, 3d] -> att [B*T, d]; optional fused per-clip min/max keys [B][2]
-int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, int H, float qscale, void* scratch, float* att,
-                    unsigned* minmax_keys) {
-    LB_REQUIRE(lb_attention_tc_supported(T, d, H), "attention_tc: unsupported geometry T=%d d=%d H=%d", T, d, H);
+void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float** qk_lo, float** vt_hi, float** vt_lo, int* tp) {
     const long long M = (long long)B * T;
     const int Tp = (T + 3) / 4 * 4;
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     uint8_t* p = (uint8_t*)scratch;
-    float* q_hi = (float*)p; p += al(sizeof(float) * M * d);
-    float* q_lo = (float*)p; p += al(sizeof(float) * M * d);
-    float* k_hi = (float*)p; p += al(sizeof(float) * M * d);
-    float* k_lo = (float*)p; p += al(sizeof(float) * M * d);
-    float* vt_hi = (float*)p; p += al(sizeof(float) * (size_t)B * H * DK * Tp);
-    float* vt_lo = (float*)p;
-    attn_split_qk_kernel<<<grid_for(M * d), 256, 0, ctx->stream>>>(qkv, M, d, qscale, q_hi, q_lo, k_hi, k_lo);
-    LB_LAUNCH_CHECK(ctx);
-    attn_split_vt_kernel<<<dim3(lb_ceil_div(Tp, 32), DK / 32, B * H), 256, 0, ctx->stream>>>(qkv, T, Tp, d, H, vt_hi, vt_lo);
-    LB_LAUNCH_CHECK(ctx);
+    *qk_lo = (float*)p; p += al(sizeof(float) * M * 2 * d);
+    *vt_hi = (float*)p; p += al(sizeof(float) * (size_t)B * H * DK * Tp);
+    *vt_lo = (float*)p;
+    *tp = Tp;
+}
 
-    // q/k: [B][T][H][DK] -> dims (DK, H, T, B)
+// qkv [B*T, 3d] -> att [B*T, d]; optional fused per-clip min/max keys [B][2].
+// operands_ready != 0: the QKV projection's epilogue already wrote lo(q), lo(k), V^T hi/lo into `scratch`
+// (gemm_i8_tc.cu EPI_QKV); otherwise the split pre-pass runs here.
+int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, int H, float qscale, void* scratch, float* att,
+                    unsigned* minmax_keys, int operands_ready) {
+    LB_REQUIRE(lb_attention_tc_supported(T, d, H), "attention_tc: unsupported geometry T=%d d=%d H=%d", T, d, H);
+    const long long M = (long long)B * T;
+    float *qk_lo, *vt_hi, *vt_lo; int Tp;
+    lb_attention_tc_operands(scratch, B, T, d, H, &qk_lo, &vt_hi, &vt_lo, &Tp);
+    if (!operands_ready) {
+        attn_split_qk_kernel<<<grid_for(M * 2 * d), 256, 0, ctx->stream>>>(qkv, M, d, qk_lo);
+        LB_LAUNCH_CHECK(ctx);
+        attn_split_vt_kernel<<<dim3(lb_ceil_div(Tp, 32), DK / 32, B * H), 256, 0, ctx->stream>>>(qkv, T, Tp, d, H, vt_hi, vt_lo);
+        LB_LAUNCH_CHECK(ctx);
+    }
+
+    // q/k hi = the raw f32 projections inside qkv (the tensor core reads the top 19 bits = tf32 truncation),
+    // lo from qk_lo: [B][T][H][DK] views -> dims (DK, H, T, B)
     const unsigned long long dqk[4] = {(unsigned long long)DK, (unsigned long long)H, (unsigned long long)T, (unsigned long long)B};
-    const unsigned long long sqk[3] = {(unsigned long long)DK * 4, (unsigned long long)d * 4, (unsigned long long)T * d * 4};
+    const unsigned long long sqh[3] = {(unsigned long long)DK * 4, (unsigned long long)3 * d * 4, (unsigned long long)T * 3 * d * 4};
+    const unsigned long long sql[3] = {(unsigned long long)DK * 4, (unsigned long long)2 * d * 4, (unsigned long long)T * 2 * d * 4};
     const unsigned bq[4] = {KC, 1, AQ, 1}, bk[4] = {KC, 1, NH, 1};
     // v^T: [B][H][DK][Tp] -> dims (Tp, DK, H, B)
     const unsigned long long dv[4] = {(unsigned long long)Tp, (unsigned long long)DK, (unsigned long long)H, (unsigned long long)B};
@@ -453,18 +532,23 @@ int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, i
     CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
     int rc;
     g_ctx_for_maps = ctx;
-    if ((rc = make_map_f32_4d(&mqh, q_hi, dqk, sqk, bq))) return rc;
-    if ((rc = make_map_f32_4d(&mql, q_lo, dqk, sqk, bq))) return rc;
-    if ((rc = make_map_f32_4d(&mkh, k_hi, dqk, sqk, bk))) return rc;
-    if ((rc = make_map_f32_4d(&mkl, k_lo, dqk, sqk, bk))) return rc;
+    if ((rc = make_map_f32_4d(&mqh, qkv, dqk, sqh, bq))) return rc;
+    if ((rc = make_map_f32_4d(&mql, qk_lo, dqk, sql, bq))) return rc;
+    if ((rc = make_map_f32_4d(&mkh, qkv + d, dqk, sqh, bk))) return rc;
+    if ((rc = make_map_f32_4d(&mkl, qk_lo + d, dqk, sql, bk))) return rc;
     if ((rc = make_map_f32_4d(&mvh, vt_hi, dv, sv, bv))) return rc;
     if ((rc = make_map_f32_4d(&mvl, vt_lo, dv, sv, bv))) return rc;
+    // att [B][T][H*DK] -> dims (H*DK, T, B), box 32 x 32 x 1 (one epilogue warp's sub-tile); rows >= T are clipped
+    CUtensorMap mout;
+    if ((rc = make_map_f32_out3d(&mout, att, (unsigned long long)H * DK, (unsigned long long)T, (unsigned long long)B))) return rc;
     AttnArgs a;
     a.B = B; a.T = T; a.H = H; a.n_qtiles = lb_ceil_div(T, AQ); a.n_kchunks = lb_ceil_div(T, KC); a.rows_per_slice = T;
     a.out = att; a.minmax_keys = minmax_keys;
+    a.scale_l2e = qscale * 1.4426950408889634f;
+    a.dbg = getenv("LELE_B200_ATTN_DBG") ? 1 : 0;
     static thread_local bool attr_done = false;
     if (!attr_done) { LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_done = true; }
-    attn_tc_kernel<<<B * H * a.n_qtiles, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mqh, mql, mkh, mkl, mvh, mvl, a);
+    attn_tc_kernel<<<B * H * a.n_qtiles, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mqh, mql, mkh, mkl, mvh, mvl, mout, a);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -17,6 +17,7 @@
 // Persistent: grid = #SMs, tiles walked n-fastest so concurrently running CTAs share A rows in L2.
 #include "gemm_i8_tc.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -28,8 +29,9 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;   // 640
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_WARP_BYTES = 32 * 33 * 4 + 3 * 64 * 4;      // 32x33 f32 transpose tile + colsum/w_scale/bias of 64 columns
-constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_WARP_BYTES;
+constexpr int EPI_TILE_BYTES = 32 * 128;                       // per-warp 32x32 f32 staging tile, 128B-swizzled (1024 B aligned)
+constexpr int EPI_META_BYTES = 3 * 64 * 4;                     // zp*colsum / scale / bias of the warp's 64 columns
+constexpr int EPI_BYTES = NUM_EPI_WARPS * (EPI_TILE_BYTES + EPI_META_BYTES);
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int UMMA_K = 32;                           // bytes per tcgen05.mma for 8-bit operands
 
@@ -123,7 +125,7 @@ struct KernelArgs {
 };
 
 // Epilogue specialisations (compile-time, so the inner loops carry no uniform branches)
-enum EpiMode { EPI_PLAIN = 0, EPI_MINMAX, EPI_ARGMAX, EPI_R1, EPI_R2, EPI_R12 };
+enum EpiMode { EPI_PLAIN = 0, EPI_MINMAX, EPI_ARGMAX, EPI_R1, EPI_R2, EPI_R12, EPI_QKV };
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
@@ -132,16 +134,29 @@ __device__ __forceinline__ int4 lds_v4(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_s32(uint32_t addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-template <int MODE>
+__device__ __forceinline__ void sts_v4f(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// TMA_OUT: the 32x32 f32 sub-tile a warp finished is written by one cp.async.bulk.tensor store from the
+// swizzled staging tile (no per-element store phase); used when the epilogue has no residual operand.
+template <int MODE, bool TMA_OUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const KernelArgs args) {
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_lo, const KernelArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;   // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem = smem_raw + pad;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* epi_base = smem + STAGES * STAGE_BYTES;                       // per-warp staging tiles + column metadata
+    uint8_t* epi_base = smem + STAGES * STAGE_BYTES;                       // per-warp staging tiles, then column metadata
     uint64_t* bars = (uint64_t*)(epi_base + EPI_BYTES);
     uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
@@ -152,7 +167,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = args.num_m_blocks * args.num_n_blocks;
 
-    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); if (MODE == EPI_QKV) prefetch_tmap(&tmap_lo); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
@@ -212,16 +227,22 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else if (warp >= 4) {
         // ===================== epilogue: 16 warps, each owns 32 rows x 64 columns of every tile =====================
-        // phase 1 (thread = row): TMEM -> exact integer corrections, scale, bias, ReLU -> per-warp smem tile [32][33]
-        // phase 2 (lane = column): read the tile transposed -> residual adds / min-max -> 128-byte coalesced stores
+        // phase 1 (thread = row): TMEM -> exact integer corrections, scale, bias, ReLU (+ min/max, arg-max) -> the warp's
+        //          staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) == the TMA SWIZZLE_128B
+        //          layout, so both the row-wise 16 B writes and the column-wise 4 B reads are bank-conflict free
+        // then     TMA_OUT: one elected lane issues a 32x32 tensor store (clipped at M / N by the hardware)
+        //          else   : phase 2 (lane = column) reads the tile transposed -> residual adds -> 128-byte coalesced stores
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
         const int cgrp = ew >> 2;           // which 64-column group of the tile
         const LbI8Epilogue& ep = args.ep;
-        const uint32_t tile_s = smem_u32(epi_base) + (uint32_t)ew * EPI_WARP_BYTES;   // [32][33] f32
-        const uint32_t meta_s = tile_s + 32 * 33 * 4;                                   // colsum[64] | w_scale[64] | bias[64]
+        const uint32_t tile_s = smem_u32(epi_base) + (uint32_t)ew * EPI_TILE_BYTES;
+        const uint32_t meta_s = smem_u32(epi_base) + NUM_EPI_WARPS * EPI_TILE_BYTES + (uint32_t)ew * EPI_META_BYTES;   // zp*colsum[64] | scale[64] | bias[64]
+        const uint32_t my_row_s = tile_s + (uint32_t)lane * 128u;
+        const uint32_t sw = (uint32_t)(lane & 7);
         const float relu_lo = ep.relu ? 0.0f : -3.402823466e+38f;
         const int N = args.N, M = args.M;
+        const float FMAX = 3.402823466e+38f;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
@@ -237,20 +258,23 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // second clip only at clip boundaries (1 warp in ~8 for T' = 271); those rows take the uncombined path.
             const int rps = ep.rows_per_slice > 0 ? ep.rows_per_slice : 0x7fffffff;
             const int slice_first = first_row / rps;
-            const bool all_a = __all_sync(0xffffffffu, !row_ok || (row / rps) == slice_first);
+            const bool in_a = row_ok && (row / rps) == slice_first;
+            const bool all_a = __all_sync(0xffffffffu, !row_ok || in_a);
             const int zpa_a = __shfl_sync(0xffffffffu, zpa, 0);
             const float sa_a = __shfl_sync(0xffffffffu, sa, 0);
             __syncwarp();
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int c = hh * 32 + lane;
-                sts_s32(meta_s + 4 * c, zpa_a * __ldg(ep.colsum + gcol_w + c));
-                sts_f32(meta_s + 256 + 4 * c, __fmul_rn(sa_a, __ldg(ep.w_scale + gcol_w + c)));
-                sts_f32(meta_s + 512 + 4 * c, __ldg(ep.bias + gcol_w + c));
+                const int cc = min(gcol_w + c, N - 1);
+                const int cs_raw = __ldg(ep.colsum + cc);
+                const float ws_raw = __ldg(ep.w_scale + cc);
+                sts_s32(meta_s + 4 * c, all_a ? zpa_a * cs_raw : cs_raw);               // straddling warps keep raw metadata
+                sts_f32(meta_s + 256 + 4 * c, all_a ? __fmul_rn(sa_a, ws_raw) : ws_raw);
+                sts_f32(meta_s + 512 + 4 * c, __ldg(ep.bias + cc));
             }
             unsigned long long best = 0ull;
-            const int slice_a = (MODE == EPI_MINMAX) ? first_row / ep.rows_per_slice : 0;
-            float mnA = 3.402823466e+38f, mxA = -3.402823466e+38f, mnB = 3.402823466e+38f, mxB = -3.402823466e+38f;
+            float vmin = FMAX, vmax = -FMAX;                           // this row's min / max over the warp's 64 columns
             const int nrows = min(32, M - first_row);
             __syncwarp();
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -262,8 +286,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), r);
                 if (gcol0 >= N || nrows <= 0) continue;                // warp-uniform
+                if (TMA_OUT) {                                         // the previous store must have read the staging tile
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
                 // ---- phase 1 ----
-                auto finish = [&](float t, float bias_v, int idx) {
+                const bool full_cols = gcol0 + 32 <= N;
+                auto finish = [&](float t, float bias_v, int idx) -> float {
                     t = ep.has_bias ? __fadd_rn(t, bias_v) : t;
                     t = fmaxf(t, relu_lo);
                     if (MODE == EPI_ARGMAX) {
@@ -272,7 +301,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                             best = key > best ? key : best;
                         }
                     }
-                    sts_f32(tile_s + 4 * (lane * 33 + idx), t);
+                    if (MODE == EPI_MINMAX) {
+                        if (full_cols || gcol0 + idx < N) { vmin = fminf(vmin, t); vmax = fmaxf(vmax, t); }
+                    }
+                    return t;
                 };
                 if (all_a) {
 #pragma unroll
@@ -280,41 +312,93 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         const int4 zc = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
                         const int4 csb = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
                         const int4 bib = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
-                        finish(__fmul_rn((float)((int)r[q * 4 + 0] + row_corr - zc.x), __int_as_float(csb.x)), __int_as_float(bib.x), q * 4 + 0);
-                        finish(__fmul_rn((float)((int)r[q * 4 + 1] + row_corr - zc.y), __int_as_float(csb.y)), __int_as_float(bib.y), q * 4 + 1);
-                        finish(__fmul_rn((float)((int)r[q * 4 + 2] + row_corr - zc.z), __int_as_float(csb.z)), __int_as_float(bib.z), q * 4 + 2);
-                        finish(__fmul_rn((float)((int)r[q * 4 + 3] + row_corr - zc.w), __int_as_float(csb.w)), __int_as_float(bib.w), q * 4 + 3);
+                        const float t0 = finish(__fmul_rn((float)((int)r[q * 4 + 0] + row_corr - zc.x), __int_as_float(csb.x)), __int_as_float(bib.x), q * 4 + 0);
+                        const float t1 = finish(__fmul_rn((float)((int)r[q * 4 + 1] + row_corr - zc.y), __int_as_float(csb.y)), __int_as_float(bib.y), q * 4 + 1);
+                        const float t2 = finish(__fmul_rn((float)((int)r[q * 4 + 2] + row_corr - zc.z), __int_as_float(csb.z)), __int_as_float(bib.z), q * 4 + 2);
+                        const float t3 = finish(__fmul_rn((float)((int)r[q * 4 + 3] + row_corr - zc.w), __int_as_float(csb.w)), __int_as_float(bib.w), q * 4 + 3);
+                        sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), t0, t1, t2, t3);
+                        if (MODE == EPI_QKV) { r[q * 4 + 0] = __float_as_uint(t0); r[q * 4 + 1] = __float_as_uint(t1); r[q * 4 + 2] = __float_as_uint(t2); r[q * 4 + 3] = __float_as_uint(t3); }
                     }
-                } else {   // the warp straddles a clip boundary: uncombined metadata straight from global (L1-resident)
+                } else {   // the warp straddles a clip boundary: raw column metadata, combined per row here
 #pragma unroll
-                    for (int idx = 0; idx < 32; ++idx) {
-                        const int acci = (int)r[idx] + row_corr - zpa * __ldg(ep.colsum + gcol0 + idx);
-                        finish(__fmul_rn((float)acci, __fmul_rn(sa, __ldg(ep.w_scale + gcol0 + idx))), __ldg(ep.bias + gcol0 + idx), idx);
+                    for (int q = 0; q < 8; ++q) {
+                        const int4 zc = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
+                        const int4 csb = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
+                        const int4 bib = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
+                        const float t0 = finish(__fmul_rn((float)((int)r[q * 4 + 0] + row_corr - zpa * zc.x), __fmul_rn(sa, __int_as_float(csb.x))), __int_as_float(bib.x), q * 4 + 0);
+                        const float t1 = finish(__fmul_rn((float)((int)r[q * 4 + 1] + row_corr - zpa * zc.y), __fmul_rn(sa, __int_as_float(csb.y))), __int_as_float(bib.y), q * 4 + 1);
+                        const float t2 = finish(__fmul_rn((float)((int)r[q * 4 + 2] + row_corr - zpa * zc.z), __fmul_rn(sa, __int_as_float(csb.z))), __int_as_float(bib.z), q * 4 + 2);
+                        const float t3 = finish(__fmul_rn((float)((int)r[q * 4 + 3] + row_corr - zpa * zc.w), __fmul_rn(sa, __int_as_float(csb.w))), __int_as_float(bib.w), q * 4 + 3);
+                        sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), t0, t1, t2, t3);
+                        if (MODE == EPI_QKV) { r[q * 4 + 0] = __float_as_uint(t0); r[q * 4 + 1] = __float_as_uint(t1); r[q * 4 + 2] = __float_as_uint(t2); r[q * 4 + 3] = __float_as_uint(t3); }
                     }
                 }
                 if (MODE == EPI_ARGMAX && !ep.out) continue;           // ids only: nothing to write
-                __syncwarp();
-                // ---- phase 2 ----
-                const int col = gcol0 + lane;
-                if (col < N) {
-                    const long long base = (long long)first_row * N + col;
-                    float* outp = ep.out + base;
-                    const float* a1 = (MODE == EPI_R1 || MODE == EPI_R12) ? ep.add1 + base : nullptr;
-                    const float* a2 = (MODE == EPI_R2 || MODE == EPI_R12) ? ep.add2 + base : nullptr;
-#pragma unroll 8
-                    for (int rr = 0; rr < nrows; ++rr) {
-                        float v = lds_f32(tile_s + 4 * (rr * 33 + lane));
-                        const long long o = (long long)rr * N;
-                        if (MODE == EPI_R1 || MODE == EPI_R12) v = __fadd_rn(v, __ldg(a1 + o));
-                        if (MODE == EPI_R2 || MODE == EPI_R12) v = __fadd_rn(__ldg(a2 + o), v);
-                        outp[o] = v;
-                        if (MODE == EPI_MINMAX) {
-                            if (rr < (slice_a + 1) * ep.rows_per_slice - first_row) { mnA = fminf(mnA, v); mxA = fmaxf(mxA, v); }
-                            else { mnB = fminf(mnB, v); mxB = fmaxf(mxB, v); }
+                if (TMA_OUT) {
+                    fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, first_row);
+                    if (MODE == EPI_QKV) {
+                        // tf32 operand preparation for the attention kernel; r[] holds the 32 finished f32 values of this row
+                        const int dmodel = N / 3;
+                        if (gcol0 < 2 * dmodel) {          // q / k columns: lo = x - trunc_tf32(x), second tensor store
+                            if (lane == 0) tma_store_wait_read();
+                            __syncwarp();
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float lo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float t = __uint_as_float(r[q * 4 + e]);
+                                    lo[e] = __fsub_rn(t, __uint_as_float(r[q * 4 + e] & 0xFFFFE000u));
+                                }
+                                sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+                            }
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) tma_store_2d(&tmap_lo, tile_s, gcol0, first_row);
+                        } else if (row_ok) {               // v columns: V^T, 32 consecutive keys (lanes) per store
+                            const int bb = row / rps, tt = row - bb * rps;
+                            const int cv = gcol0 - 2 * dmodel;
+                            const size_t base = ((size_t)bb * (dmodel >> 7) * 128 + cv) * (size_t)ep.vt_tp + tt;
+                            float* vh = ep.vt_hi + base;
+                            float* vl = ep.vt_lo + base;
+#pragma unroll
+                            for (int idx = 0; idx < 32; ++idx) {
+                                const float t = __uint_as_float(r[idx]);
+                                const float hi = __uint_as_float(r[idx] & 0xFFFFE000u);
+                                vh[(size_t)idx * ep.vt_tp] = hi;
+                                vl[(size_t)idx * ep.vt_tp] = __fsub_rn(t, hi);
+                            }
+                            if (tt == rps - 1) {           // last key of the clip: zero the [T, Tp) padding of its V^T rows
+                                for (int pd = 1; pd <= ep.vt_tp - rps; ++pd)
+#pragma unroll
+                                    for (int idx = 0; idx < 32; ++idx) { vh[(size_t)idx * ep.vt_tp + pd] = 0.0f; vl[(size_t)idx * ep.vt_tp + pd] = 0.0f; }
+                            }
                         }
                     }
+                } else {
+                    __syncwarp();
+                    // ---- phase 2 ----
+                    const int col = gcol0 + lane;
+                    if (col < N) {
+                        const long long base = (long long)first_row * N + col;
+                        float* outp = ep.out + base;
+                        const float* a1 = (MODE == EPI_R1 || MODE == EPI_R12) ? ep.add1 + base : nullptr;
+                        const float* a2 = (MODE == EPI_R2 || MODE == EPI_R12) ? ep.add2 + base : nullptr;
+                        const uint32_t rd_s = tile_s + (uint32_t)(lane & 3) * 4u;
+                        const uint32_t chunk_l = (uint32_t)(lane >> 2);
+#pragma unroll 8
+                        for (int rr = 0; rr < nrows; ++rr) {
+                            float v = lds_f32(rd_s + (uint32_t)rr * 128u + ((chunk_l ^ (uint32_t)(rr & 7)) << 4));
+                            const long long o = (long long)rr * N;
+                            if (MODE == EPI_R1 || MODE == EPI_R12) v = __fadd_rn(v, __ldg(a1 + o));
+                            if (MODE == EPI_R2 || MODE == EPI_R12) v = __fadd_rn(__ldg(a2 + o), v);
+                            outp[o] = v;
+                        }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
             tc_fence_before();
@@ -323,14 +407,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
             if (MODE == EPI_MINMAX && nrows > 0) {
-                mnA = lb_warp_min(mnA); mxA = lb_warp_max(mxA); mnB = lb_warp_min(mnB); mxB = lb_warp_max(mxB);
-                if (lane == 0) {
-                    if (mnA <= mxA) lb_mm_update(ep.minmax_keys, slice_a, mnA, mxA);
-                    if (mnB <= mxB) lb_mm_update(ep.minmax_keys, slice_a + 1, mnB, mxB);
+                // rows of clip A (the one owning the warp's first row) and of clip A+1 reduce separately
+                const float mnA = lb_warp_min(in_a ? vmin : FMAX), mxA = lb_warp_max(in_a ? vmax : -FMAX);
+                if (lane == 0 && mnA <= mxA) lb_mm_update(ep.minmax_keys, slice_first, mnA, mxA);
+                if (!all_a) {
+                    const bool in_b = row_ok && !in_a;
+                    const float mnB = lb_warp_min(in_b ? vmin : FMAX), mxB = lb_warp_max(in_b ? vmax : -FMAX);
+                    if (lane == 0 && mnB <= mxB) lb_mm_update(ep.minmax_keys, slice_first + 1, mnB, mxB);
                 }
             }
             if (MODE == EPI_ARGMAX && row_ok && best != 0ull) atomicMax(ep.argmax_keys + row, best);
         }
+        if (TMA_OUT && lane == 0) tma_store_wait_all();                // staging smem must outlive the bulk stores
     }
 
     tc_fence_before();
@@ -384,6 +472,28 @@ int cached_tmap_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long l
     ctx->tmaps.emplace(h, std::move(blob));
     return LELE_B200_OK;
 }
+
+// f32 [rows, cols] row-major output, box = 32 x 32 (one epilogue warp's sub-tile), 128B swizzle
+int cached_tmap_out_f32(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols) {
+    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(0x6f757466ull, (unsigned long long)(uintptr_t)ptr), (unsigned long long)rows),
+                                       (unsigned long long)cols);
+    auto it = ctx->tmaps.find(h);
+    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(out) failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return LELE_B200_ERR_CUDA; }
+    std::vector<unsigned char> blob(sizeof(CUtensorMap));
+    memcpy(blob.data(), map, sizeof(CUtensorMap));
+    ctx->tmaps.emplace(h, std::move(blob));
+    return LELE_B200_OK;
+}
 }  // namespace
 
 int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep) {
@@ -406,25 +516,50 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     int tiles = args.num_m_blocks * args.num_n_blocks;
     int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
     int mode = EPI_PLAIN;
-    if (ep.argmax_keys) mode = EPI_ARGMAX;
+    if (ep.qk_lo) mode = EPI_QKV;
+    else if (ep.argmax_keys) mode = EPI_ARGMAX;
     else if (ep.minmax_keys) mode = EPI_MINMAX;
     else if (ep.add1 && ep.add2) mode = EPI_R12;
     else if (ep.add1) mode = EPI_R1;
     else if (ep.add2) mode = EPI_R2;
     LB_REQUIRE(!(ep.minmax_keys && (ep.add1 || ep.add2)), "gemm_i8_tc: fused min/max with residual adds is not instantiated");
     LB_REQUIRE(ep.out || mode == EPI_ARGMAX, "gemm_i8_tc: no output requested");
+    // residual-free epilogues whose rows are 16-byte aligned store through TMA (no per-element store phase)
+    if (mode == EPI_QKV) {
+        LB_REQUIRE(N % 384 == 0 && ep.vt_hi && ep.vt_lo && ep.rows_per_slice > 0 && ep.vt_tp >= ep.rows_per_slice && !ep.add1 && !ep.add2 &&
+                   !ep.minmax_keys && !ep.argmax_keys && !getenv("LELE_B200_GEMM_NO_TMA_STORE"),
+                   "gemm_i8_tc: fused attention-operand epilogue needs N = 3 * heads * 128 and the V^T buffers");
+    }
+    const bool tma_out = (mode == EPI_PLAIN || mode == EPI_MINMAX || mode == EPI_QKV) && N % 4 == 0 && (((uintptr_t)ep.out) & 15) == 0 &&
+                         !getenv("LELE_B200_GEMM_NO_TMA_STORE");
+    CUtensorMap tout = ta, tlo = ta;
+    if (tma_out) {
+        rc = cached_tmap_out_f32(ctx, &tout, ep.out, M, N);
+        if (rc) return rc;
+    }
+    if (mode == EPI_QKV) {
+        LB_REQUIRE(tma_out, "gemm_i8_tc: fused attention-operand epilogue needs a 16-byte aligned output");
+        rc = cached_tmap_out_f32(ctx, &tlo, ep.qk_lo, M, N / 3 * 2);
+        if (rc) return rc;
+    }
     static thread_local unsigned attr_done = 0;   // one process per GPU: the attribute is set once per instantiation
-#define LB_LAUNCH_MODE(MD)                                                                                              \
-    case MD:                                                                                                            \
-        if (!(attr_done & (1u << MD))) {                                                                                \
-            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
-            attr_done |= (1u << MD);                                                                                    \
+#define LB_LAUNCH_MODE(MD, TM)                                                                                          \
+    {                                                                                                                   \
+        const unsigned bit = 1u << (MD * 2 + (TM ? 1 : 0));                                                             \
+        if (!(attr_done & bit)) {                                                                                       \
+            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+            attr_done |= bit;                                                                                           \
         }                                                                                                               \
-        gemm_i8_tc_kernel<MD><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, args);                            \
-        break;
+        gemm_i8_tc_kernel<MD, TM><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, tout, tlo, args);                  \
+    }
     switch (mode) {
-        LB_LAUNCH_MODE(EPI_PLAIN) LB_LAUNCH_MODE(EPI_MINMAX) LB_LAUNCH_MODE(EPI_ARGMAX) LB_LAUNCH_MODE(EPI_R1) LB_LAUNCH_MODE(EPI_R2)
-        LB_LAUNCH_MODE(EPI_R12)
+        case EPI_PLAIN: if (tma_out) LB_LAUNCH_MODE(EPI_PLAIN, true) else LB_LAUNCH_MODE(EPI_PLAIN, false) break;
+        case EPI_MINMAX: if (tma_out) LB_LAUNCH_MODE(EPI_MINMAX, true) else LB_LAUNCH_MODE(EPI_MINMAX, false) break;
+        case EPI_ARGMAX: LB_LAUNCH_MODE(EPI_ARGMAX, false) break;
+        case EPI_R1: LB_LAUNCH_MODE(EPI_R1, false) break;
+        case EPI_R2: LB_LAUNCH_MODE(EPI_R2, false) break;
+        case EPI_R12: LB_LAUNCH_MODE(EPI_R12, false) break;
+        case EPI_QKV: LB_LAUNCH_MODE(EPI_QKV, true) break;
     }
 #undef LB_LAUNCH_MODE
     LB_LAUNCH_CHECK(ctx);

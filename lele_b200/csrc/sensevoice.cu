@@ -24,7 +24,8 @@ int lb_argmax_keys_to_ids(lele_b200_ctx* ctx, const unsigned long long* keys, lo
 bool lb_attention_tc_supported(int T, int d, int H);
 size_t lb_attention_tc_scratch_bytes(int B, int T, int d, int H);
 int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, int H, float qscale, void* scratch, float* att,
-                    unsigned* minmax_keys);
+                    unsigned* minmax_keys, int operands_ready);
+void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float** qk_lo, float** vt_hi, float** vt_lo, int* tp);
 
 namespace {
 enum { SV_G_EMBED = 0, SV_G_POS, SV_G_AFTER_G, SV_G_AFTER_B, SV_G_TP_G, SV_G_TP_B, SV_G_CTC_W, SV_G_CTC_SCALE, SV_G_CTC_BIAS,
@@ -330,6 +331,8 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     const float qscale = 1.0f / sqrtf((float)dk);
     const float* xin = m->x0;
     int cur = din;
+    const bool attn_tc = !m->attn_simt && lb_attention_tc_supported(T, d, H);
+    int attn_ops_ready = 0;
     for (int l = 0; l < n_layers; ++l) {
         // ---- self-attention block ----
         SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, xin, (const float*)m->lt(l, SV_L_LN1_G), (const float*)m->lt(l, SV_L_LN1_B), M, cur,
@@ -337,6 +340,11 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->qkv; ep.rows_per_slice = T;
+            // the projection's epilogue also emits the tf32 lo / V^T operand copies of the fused attention kernel
+            if (attn_tc && m->lin[l * 4 + 0]->k % 16 == 0 && !getenv("LELE_B200_FORCE_SIMT") && !getenv("LELE_B200_GEMM_NO_TMA_STORE")) {
+                lb_attention_tc_operands(m->attn_scratch, B, T, d, H, &ep.qk_lo, &ep.vt_hi, &ep.vt_lo, &ep.vt_tp);
+                attn_ops_ready = 1;
+            } else attn_ops_ready = 0;
             SV_LINEAR(ctx, m,m->h, site(l * 4 + 0), M, T, m->lin[l * 4 + 0], qs, ep);
         }
         const bool fork = !m->profiling && m->side != nullptr;
@@ -355,9 +363,9 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             LB_LAUNCH_CHECK(ctx);
         }
         if (fork) LB_CHECK_CUDA(cudaEventRecord(m->ev_join, m->side));
-        if (!m->attn_simt && lb_attention_tc_supported(T, d, H)) {
+        if (attn_tc) {
             // fused tcgen05 attention (3xTF32), per-clip min/max of the output fused in its epilogue
-            SV_RUN(P_ATTN_TC, lb_attention_tc(ctx, m->qkv, B, T, d, H, qscale, m->attn_scratch, m->att, site(l * 4 + 1)));
+            SV_RUN(P_ATTN_TC, lb_attention_tc(ctx, m->qkv, B, T, d, H, qscale, m->attn_scratch, m->att, site(l * 4 + 1), attn_ops_ready));
         } else {
             {
                 ProfScope ps(m, ctx, P_FSMN);
