@@ -1,6 +1,7 @@
 // norm.cu -- LayerNorm / Softmax / BatchNorm / RMSNorm (src/kernels/norm.rs + avx/norm.rs).
 // HBM-bound row kernels: one warp per row, 128-bit loads, warp-shuffle reductions.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 // LayerNorm (norm.rs:226 -> avx/norm.rs:10-133): mean = sum*(1/n); var = sumsq*(1/n) - mean^2 (not
 // clamped); inv = 1/sqrt(var+eps); y = fma((x-mean)*inv, gamma, beta) on the SIMD body (first
@@ -69,10 +70,13 @@ layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
 // Specialisation for the row widths of the SenseVoice encoder (N = 512, 560; N % 8 == 0): compile-time
 // trip counts, gamma/beta held in registers and reused over RPW consecutive rows per warp, no per-element
 // predication.  Same arithmetic and summation order as layer_norm_kernel.
-template <int N, int RPW>
+// STORE = false: the normalised rows are not written; only (mean, 1/std) per row and the per-slice min/max of
+// the would-be output, for ln_quantize_kernel to re-derive and quantise the rows in one more read of x.
+template <int N, int RPW, bool STORE>
 __global__ void __launch_bounds__(256)
 layer_norm_fixed_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                        long long outer, float eps, float* __restrict__ out, unsigned* __restrict__ minmax_keys, int rows_per_slice) {
+                        long long outer, float eps, float* __restrict__ out, unsigned* __restrict__ minmax_keys, int rows_per_slice,
+                        float2* __restrict__ stats) {
     constexpr int NB = N / 32, REM = N % 32, REM8 = REM / 8;
     static_assert(N % 8 == 0, "fixed LayerNorm kernel needs N % 8 == 0");
     const int lane = threadIdx.x & 31;
@@ -90,7 +94,7 @@ layer_norm_fixed_kernel(const float* __restrict__ x, const float* __restrict__ g
         const long long row = row0 + rr;
         if (row >= outer) break;
         const float* xr = x + row * N;
-        float* o = out + row * N;
+        float* o = STORE ? out + row * N : nullptr;
         float v[NB], rem[REM8 > 0 ? REM8 : 1], xrem = 0.0f;
 #pragma unroll
         for (int i = 0; i < NB; ++i) v[i] = __ldg(xr + 32 * i + lane);
@@ -111,17 +115,18 @@ layer_norm_fixed_kernel(const float* __restrict__ x, const float* __restrict__ g
         const float mean = __fmul_rn(ps, inv_n);
         const float var = __fsub_rn(__fmul_rn(pq, inv_n), __fmul_rn(mean, mean));
         const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+        if (!STORE && lane == 0) stats[row] = make_float2(mean, inv);
         float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const float r = __fmaf_rn(__fmul_rn(__fsub_rn(v[i], mean), inv), g[i], bt[i]);
             vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
-            o[32 * i + lane] = r;
+            if (STORE) o[32 * i + lane] = r;
         }
         if (REM > 0 && lane < REM) {
             const float r = __fmaf_rn(__fmul_rn(__fsub_rn(xrem, mean), inv), gr, br);
             vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
-            o[NB * 32 + lane] = r;
+            if (STORE) o[NB * 32 + lane] = r;
         }
         if (minmax_keys) {
             if (row / rows_per_slice == slice_a) { mnA = fminf(mnA, vmin); mxA = fmaxf(mxA, vmax); }
@@ -144,8 +149,8 @@ int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma,
     constexpr int RPW = 4;
     if (gamma && beta && (n == 512 || n == 560) && (!minmax_keys || rows_per_slice >= RPW)) {
         const int grid = lb_ceil_div(outer, warps * RPW);
-        if (n == 512) layer_norm_fixed_kernel<512, RPW><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, eps, out, minmax_keys, rows_per_slice);
-        else layer_norm_fixed_kernel<560, RPW><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, eps, out, minmax_keys, rows_per_slice);
+        if (n == 512) layer_norm_fixed_kernel<512, RPW, true><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, eps, out, minmax_keys, rows_per_slice, nullptr);
+        else layer_norm_fixed_kernel<560, RPW, true><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, eps, out, minmax_keys, rows_per_slice, nullptr);
         LB_LAUNCH_CHECK(ctx);
         return LELE_B200_OK;
     }
@@ -153,6 +158,308 @@ int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma,
     if (n <= 32 * 18) layer_norm_kernel<18><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
     else if (n <= 32 * 64) layer_norm_kernel<64><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
     else layer_norm_kernel<0><<<grid, warps * 32, 0, ctx->stream>>>(x, gamma, beta, outer, n, eps, out, minmax_keys, rows_per_slice);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+// ---- LayerNorm fused with the dynamic quantiser that consumes it (SenseVoice encoder, N = 512) ----------------
+// The reference materialises LayerNorm's f32 output and re-reads it to quantise (norm.rs:227 ->
+// avx/quantization.rs:102).  Here pass 1 (layer_norm_fixed_kernel<.., STORE=false>) leaves only (mean, 1/std)
+// per row and the per-clip min/max of the normalised values; pass 2 re-derives each value with the identical
+// operation sequence (so it is bit-identical to what pass 1 measured) and emits u8 + row sums directly.
+// pass 1 for N = 512: RPW rows per warp, all row loads issued before anything depends on them
+template <int RPW>
+__global__ void __launch_bounds__(256)
+ln_stats512_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long outer, float eps,
+                   float2* __restrict__ stats, unsigned* __restrict__ minmax_keys, int rows_per_slice) {
+    constexpr int N = 512, NB = 16;
+    const int lane = threadIdx.x & 31;
+    const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+    if (row0 >= outer) return;
+    float v[RPW][NB];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const long long row = row0 + rr < outer ? row0 + rr : outer - 1;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) v[rr][i] = __ldg(x + row * N + 32 * i + lane);
+    }
+    float g[NB], bt[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { g[i] = __ldg(gamma + 32 * i + lane); bt[i] = __ldg(beta + 32 * i + lane); }
+    const float inv_n = __fdiv_rn(1.0f, (float)N);
+    const long long slice_a = row0 / rows_per_slice;
+    float mnA = 3.402823466e+38f, mxA = -3.402823466e+38f, mnB = 3.402823466e+38f, mxB = -3.402823466e+38f;
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const long long row = row0 + rr;
+        if (row < outer) {
+            float ps = 0.0f, pq = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) { ps = __fadd_rn(ps, v[rr][i]); pq = __fmaf_rn(v[rr][i], v[rr][i], pq); }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, o)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, o)); }
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, o)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, o)); }
+            ps = __shfl_sync(0xffffffffu, ps, 0); pq = __shfl_sync(0xffffffffu, pq, 0);
+            const float mean = __fmul_rn(ps, inv_n);
+            const float var = __fsub_rn(__fmul_rn(pq, inv_n), __fmul_rn(mean, mean));
+            const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+            if (lane == 0) stats[row] = make_float2(mean, inv);
+            float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const float r = __fmaf_rn(__fmul_rn(__fsub_rn(v[rr][i], mean), inv), g[i], bt[i]);
+                vmin = fminf(vmin, r); vmax = fmaxf(vmax, r);
+            }
+            if (row / rows_per_slice == slice_a) { mnA = fminf(mnA, vmin); mxA = fmaxf(mxA, vmax); }
+            else { mnB = fminf(mnB, vmin); mxB = fmaxf(mxB, vmax); }
+        }
+    }
+    mnA = lb_warp_min(mnA); mxA = lb_warp_max(mxA); mnB = lb_warp_min(mnB); mxB = lb_warp_max(mxB);
+    if (lane == 0) {
+        if (mnA <= mxA) lb_mm_update(minmax_keys, slice_a, mnA, mxA);
+        if (mnB <= mxB) lb_mm_update(minmax_keys, slice_a + 1, mnB, mxB);
+    }
+}
+
+__device__ __forceinline__ void lnq_params(const unsigned* keys, long long slice, float& scale, float& zp, float& inv) {
+    float mn, mx;
+    lb_mm_read(keys, slice, mn, mx);
+    const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);
+    const float range = fmaxf(__fsub_rn(amax, amin), 1e-5f);
+    scale = __fdiv_rn(range, 255.0f);
+    zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, scale)), 0.0f), 255.0f);
+    inv = __fdiv_rn(1.0f, scale);
+}
+__device__ __forceinline__ unsigned lnq_one(float x, float mean, float rstd, float g, float b, float inv, float zp) {
+    const float r = __fmaf_rn(__fmul_rn(__fsub_rn(x, mean), rstd), g, b);
+    return min(__float2uint_rn(__fmaf_rn(r, inv, zp)), 255u);   // == clamp(rint(.), 0, 255): the conversion saturates at 0
+}
+template <int N, int RPW>
+__global__ void __launch_bounds__(256)
+ln_quantize_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float2* __restrict__ stats, const unsigned* __restrict__ keys, long long M, int rows_per_slice,
+                   uint8_t* __restrict__ a_u8, int32_t* __restrict__ rowsum, float* __restrict__ row_scale, int32_t* __restrict__ row_zp) {
+    static_assert(N % 128 == 0, "one float4 per lane per 128 columns");
+    constexpr int NV = N / 128;
+    const int lane = threadIdx.x & 31;
+    const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+    if (row0 >= M) return;
+    // every global load is issued before the first dependent instruction
+    float4 v[RPW][NV];
+    float2 st[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const long long row = row0 + rr < M ? row0 + rr : M - 1;
+        const float4* x4 = reinterpret_cast<const float4*>(x + row * N);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[rr][j] = __ldg(x4 + lane + 32 * j);
+        st[rr] = __ldg(stats + row);
+    }
+    float4 g[NV], bt[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        g[j] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+        bt[j] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+    }
+    const long long slice_a = row0 / rows_per_slice;
+    float scA, zpA, inA, scB = 0.0f, zpB = 0.0f, inB = 0.0f;
+    lnq_params(keys, slice_a, scA, zpA, inA);
+    const long long last = (row0 + RPW - 1 < M ? row0 + RPW - 1 : M - 1);
+    if (last / rows_per_slice != slice_a) lnq_params(keys, slice_a + 1, scB, zpB, inB);
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        const long long row = row0 + rr;
+        if (row < M) {
+            const bool a = row / rows_per_slice == slice_a;
+            const float scale = a ? scA : scB, zp = a ? zpA : zpB, inv = a ? inA : inB;
+            unsigned* a4 = reinterpret_cast<unsigned*>(a_u8 + row * N);
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const unsigned q0 = lnq_one(v[rr][j].x, st[rr].x, st[rr].y, g[j].x, bt[j].x, inv, zp), q1 = lnq_one(v[rr][j].y, st[rr].x, st[rr].y, g[j].y, bt[j].y, inv, zp);
+                const unsigned q2 = lnq_one(v[rr][j].z, st[rr].x, st[rr].y, g[j].z, bt[j].z, inv, zp), q3 = lnq_one(v[rr][j].w, st[rr].x, st[rr].y, g[j].w, bt[j].w, inv, zp);
+                sum += (int)(q0 + q1 + q2 + q3);
+                a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            }
+            sum = lb_warp_sum_i(sum);
+            if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
+        }
+    }
+}
+
+// ---- single-pass variant: one thread-block cluster per clip keeps the clip's normalised rows in shared memory ----
+// CS CTAs (one SM each) split the clip's rows; each normalises its rows into shared memory (x is read exactly once),
+// the per-CTA min/max are exchanged through distributed shared memory, then every CTA quantises its resident rows.
+// No f32 intermediate, no statistics buffer, no global atomics.  Same arithmetic as the two-pass kernels.
+constexpr int LNQ_CS = 4;            // CTAs per clip
+constexpr int LNQ_WARPS = 16;
+constexpr int LNQ_CHUNK = 8;         // rows per bulk copy / mbarrier
+constexpr int LNQ_MAX_CHUNKS = 16;   // <= 128 rows per CTA
+__global__ void __launch_bounds__(LNQ_WARPS * 32, 1)
+ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int T, float eps,
+                        uint8_t* __restrict__ a_u8, int32_t* __restrict__ rowsum, float* __restrict__ row_scale, int32_t* __restrict__ row_zp,
+                        unsigned* __restrict__ keys_out) {
+    namespace cg = cooperative_groups;
+    constexpr int N = 512, NB = 16;
+    extern __shared__ __align__(16) float lnq_rows[];            // [R][512] normalised rows of this CTA
+    __shared__ float red[2][LNQ_WARPS];
+    __shared__ float cta_mm[2];                                   // read by the peer CTAs of the cluster
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int clip = blockIdx.y;
+    const int R = (T + LNQ_CS - 1) / LNQ_CS;
+    const int r_begin = rank * R, r_end = min(T, r_begin + R);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xc = x + (long long)clip * T * N;
+    // The CTA's rows are one contiguous block of x: fetch it with bulk async copies (LNQ_CHUNK rows per mbarrier) so
+    // every byte is in flight at once; warps normalise rows in place as their chunk lands.
+    __shared__ __align__(8) unsigned long long chunk_bar[LNQ_MAX_CHUNKS];
+    const int n_rows = r_end - r_begin;
+    const int n_chunks = (n_rows + LNQ_CHUNK - 1) / LNQ_CHUNK;
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < n_chunks; ++c)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&chunk_bar[c])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < n_chunks; ++c) {
+            const int rows = min(LNQ_CHUNK, n_rows - c * LNQ_CHUNK);
+            const uint32_t bytes = (uint32_t)rows * N * 4;
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&chunk_bar[c]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(lnq_rows + (size_t)c * LNQ_CHUNK * N)),
+                           "l"(xc + (long long)(r_begin + c * LNQ_CHUNK) * N), "r"(bytes), "r"(bar) : "memory");
+        }
+    }
+    float g[NB], bt[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { g[i] = __ldg(gamma + 32 * i + lane); bt[i] = __ldg(beta + 32 * i + lane); }
+    const float inv_n = __fdiv_rn(1.0f, (float)N);
+    float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+    for (int r = warp; r < n_rows; r += LNQ_WARPS) {
+        {   // wait for the chunk holding row r (single use: parity 0)
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&chunk_bar[r / LNQ_CHUNK]);
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar) : "memory");
+        }
+        float* o = lnq_rows + (size_t)r * N;
+        float v[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) v[i] = o[32 * i + lane];
+        float ps = 0.0f, pq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { ps = __fadd_rn(ps, v[i]); pq = __fmaf_rn(v[i], v[i], pq); }
+#pragma unroll
+        for (int of = 8; of <= 16; of <<= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, of)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, of)); }
+#pragma unroll
+        for (int of = 4; of >= 1; of >>= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, of)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, of)); }
+        ps = __shfl_sync(0xffffffffu, ps, 0); pq = __shfl_sync(0xffffffffu, pq, 0);
+        const float mean = __fmul_rn(ps, inv_n);
+        const float var = __fsub_rn(__fmul_rn(pq, inv_n), __fmul_rn(mean, mean));
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const float y = __fmaf_rn(__fmul_rn(__fsub_rn(v[i], mean), inv), g[i], bt[i]);
+            vmin = fminf(vmin, y); vmax = fmaxf(vmax, y);
+            o[32 * i + lane] = y;
+        }
+    }
+    vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
+    if (lane == 0) { red[0][warp] = vmin; red[1][warp] = vmax; }
+    __syncthreads();
+    if (warp == 0) {
+        float a = lane < LNQ_WARPS ? red[0][lane] : 3.402823466e+38f, b = lane < LNQ_WARPS ? red[1][lane] : -3.402823466e+38f;
+        a = lb_warp_min(a); b = lb_warp_max(b);
+        if (lane == 0) { cta_mm[0] = a; cta_mm[1] = b; }
+    }
+    cluster.sync();                                               // every CTA's (min, max) is published
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+#pragma unroll
+    for (int p = 0; p < LNQ_CS; ++p) {
+        const float* peer = cluster.map_shared_rank(cta_mm, p);
+        mn = fminf(mn, peer[0]); mx = fmaxf(mx, peer[1]);
+    }
+    if (keys_out && rank == 0 && threadIdx.x == 0) {              // diagnostics / tests: slot 0 of the clip's key set
+        keys_out[(size_t)clip * LB_MM_SLOTS * 2] = lb_fkey(mn); keys_out[(size_t)clip * LB_MM_SLOTS * 2 + 1] = lb_fkey(mx);
+    }
+    const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);
+    const float range = fmaxf(__fsub_rn(amax, amin), 1e-5f);
+    const float scale = __fdiv_rn(range, 255.0f);
+    const float zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, scale)), 0.0f), 255.0f);
+    const float inv = __fdiv_rn(1.0f, scale);
+    __syncwarp();
+    for (int r = warp; r < n_rows; r += LNQ_WARPS) {              // the same warp normalised this row
+        const float4* y4 = reinterpret_cast<const float4*>(lnq_rows + (size_t)r * N);
+        const long long row = (long long)clip * T + r_begin + r;
+        unsigned* a4 = reinterpret_cast<unsigned*>(a_u8 + row * N);
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < N / 128; ++j) {
+            const float4 y = y4[lane + 32 * j];
+            const unsigned q0 = min(__float2uint_rn(__fmaf_rn(y.x, inv, zp)), 255u), q1 = min(__float2uint_rn(__fmaf_rn(y.y, inv, zp)), 255u);
+            const unsigned q2 = min(__float2uint_rn(__fmaf_rn(y.z, inv, zp)), 255u), q3 = min(__float2uint_rn(__fmaf_rn(y.w, inv, zp)), 255u);
+            sum += (int)(q0 + q1 + q2 + q3);
+            a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+        }
+        sum = lb_warp_sum_i(sum);
+        if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
+    }
+    cluster.sync();                                               // peers may still be reading cta_mm
+}
+
+bool lb_layer_norm_quantize_cluster_supported(int n, int T) {
+    return n == 512 && T >= 1 && (T + LNQ_CS - 1) / LNQ_CS <= 100;   // 100 rows x 2 KB = 200 KB of shared memory, <= LNQ_MAX_CHUNKS chunks
+}
+// x [clips*T, 512] -> u8 rows + row sums + per-row (scale, zp); one launch, x read once
+int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, int clips, int T, float eps,
+                                   uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp, unsigned* keys_out) {
+    LB_REQUIRE(lb_layer_norm_quantize_cluster_supported(512, T) && gamma && beta, "layer_norm_quantize_cluster: unsupported shape");
+    if (clips == 0) return LELE_B200_OK;
+    const size_t smem = (size_t)((T + LNQ_CS - 1) / LNQ_CS) * 512 * 4;
+    static thread_local size_t smem_set = 0;
+    if (smem > smem_set) {
+        LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(LNQ_CS, clips, 1);
+    cfg.blockDim = dim3(LNQ_WARPS * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = LNQ_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_quant_cluster_kernel, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out));
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+bool lb_layer_norm_quantize_supported(int n, int rows_per_slice) { return n == 512 && rows_per_slice >= 4; }
+
+// pass 1: statistics + min/max keys (keys must be initialised by the caller)
+int lb_layer_norm_stats(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n, float eps,
+                        float* stats, unsigned* minmax_keys, int rows_per_slice) {
+    LB_REQUIRE(lb_layer_norm_quantize_supported(n, rows_per_slice) && gamma && beta && minmax_keys, "layer_norm_stats: unsupported shape");
+    if (outer == 0) return LELE_B200_OK;
+    ln_stats512_kernel<2><<<lb_ceil_div(outer, 8 * 2), 256, 0, ctx->stream>>>(x, gamma, beta, outer, eps, reinterpret_cast<float2*>(stats), minmax_keys,
+                                                                              rows_per_slice);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+// pass 2: u8 rows + row sums + per-row (scale, zero point)
+int lb_layer_norm_quantize(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n,
+                           const float* stats, const unsigned* keys, int rows_per_slice, uint8_t* a_u8, int32_t* rowsum,
+                           float* row_scale, int32_t* row_zp) {
+    LB_REQUIRE(lb_layer_norm_quantize_supported(n, rows_per_slice), "layer_norm_quantize: unsupported shape");
+    if (outer == 0) return LELE_B200_OK;
+    ln_quantize_kernel<512, 2><<<lb_ceil_div(outer, 8 * 2), 256, 0, ctx->stream>>>(x, gamma, beta, reinterpret_cast<const float2*>(stats), keys, outer,
+                                                                                    rows_per_slice, a_u8, rowsum, row_scale, row_zp);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -67,7 +67,9 @@ __device__ __forceinline__ float dq_one(float v, float inv, float zp, bool simd)
 // (dq_to_u8_rowsums_avx2, avx/quantization.rs:102-221).  kAligned: K % 8 == 0 (every SenseVoice shape), i.e.
 // the whole row is "SIMD body" (fma + round-half-even) and no per-element tail predicate is needed.
 __device__ __forceinline__ unsigned dq_body(float v, float inv, float zp) {
-    return (unsigned)fminf(fmaxf(rintf(__fmaf_rn(v, inv, zp)), 0.0f), 255.0f);
+    // round-half-even + clamp to [0, 255]: cvt.rni.u32.f32 saturates negatives (and NaN) to 0, so one conversion and
+    // one integer min give exactly clamp(rint(fma(v, inv, zp)), 0, 255)
+    return min(__float2uint_rn(__fmaf_rn(v, inv, zp)), 255u);
 }
 template <bool kAligned>
 __global__ void __launch_bounds__(256)
@@ -106,6 +108,35 @@ quantize_rows_kernel(const float* __restrict__ x, const unsigned* __restrict__ k
     if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
 }
 
+// Register-resident variant for the SenseVoice widths (K = 128 * KV): the whole row is loaded before the clip's
+// quantisation parameters are fetched, so the two L2 round trips overlap.
+template <int KV>
+__global__ void __launch_bounds__(256)
+quantize_rows_reg_kernel(const float* __restrict__ x, const unsigned* __restrict__ keys, long long M, int rows_per_slice,
+                         uint8_t* __restrict__ a_u8, int32_t* __restrict__ rowsum, float* __restrict__ row_scale,
+                         int32_t* __restrict__ row_zp) {
+    constexpr int K = KV * 128;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float4* x4 = reinterpret_cast<const float4*>(x + row * K);
+    float4 v[KV];
+#pragma unroll
+    for (int j = 0; j < KV; ++j) v[j] = __ldg(x4 + lane + 32 * j);
+    float scale, zp, inv;
+    dq_params(keys, (int)(row / rows_per_slice), scale, zp, inv);
+    unsigned* a4 = reinterpret_cast<unsigned*>(a_u8 + row * K);
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < KV; ++j) {
+        const unsigned q0 = dq_body(v[j].x, inv, zp), q1 = dq_body(v[j].y, inv, zp), q2 = dq_body(v[j].z, inv, zp), q3 = dq_body(v[j].w, inv, zp);
+        sum += (int)(q0 + q1 + q2 + q3);
+        a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+    }
+    sum = lb_warp_sum_i(sum);
+    if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
+}
+
 int lb_minmax_init(lele_b200_ctx* ctx, unsigned* keys, int n_slices) {
     minmax_init_kernel<<<lb_ceil_div((long long)n_slices * LB_MM_SLOTS, 128), 128, 0, ctx->stream>>>(keys, n_slices);
     LB_LAUNCH_CHECK(ctx);
@@ -122,7 +153,12 @@ int lb_slice_minmax(lele_b200_ctx* ctx, const float* x, int n_slices, long long 
 }
 int lb_quantize_rows(lele_b200_ctx* ctx, const float* x, const unsigned* keys, long long M, int rows_per_slice, int K,
                      uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp) {
-    if (K % 8 == 0 && ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)a_u8) & 3) == 0))
+    const bool al = ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)a_u8) & 3) == 0);
+    if (al && K == 512)
+        quantize_rows_reg_kernel<4><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, a_u8, rowsum, row_scale, row_zp);
+    else if (al && K == 2048)
+        quantize_rows_reg_kernel<16><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, a_u8, rowsum, row_scale, row_zp);
+    else if (K % 8 == 0 && al)
         quantize_rows_kernel<true><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, K, a_u8, rowsum, row_scale, row_zp);
     else
         quantize_rows_kernel<false><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, K, a_u8, rowsum, row_scale, row_zp);

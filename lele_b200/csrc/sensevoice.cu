@@ -15,6 +15,15 @@
 #include <stdlib.h>
 
 // ---- internal entry points from the other translation units ----
+bool lb_layer_norm_quantize_supported(int n, int rows_per_slice);
+bool lb_layer_norm_quantize_cluster_supported(int n, int T);
+int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, int clips, int T, float eps,
+                                   uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp, unsigned* keys_out);
+int lb_layer_norm_stats(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n, float eps,
+                        float* stats, unsigned* minmax_keys, int rows_per_slice);
+int lb_layer_norm_quantize(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n,
+                           const float* stats, const unsigned* keys, int rows_per_slice, uint8_t* a_u8, int32_t* rowsum,
+                           float* row_scale, int32_t* row_zp);
 int lb_layer_norm_minmax(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n,
                          float eps, float* out, unsigned* minmax_keys, int rows_per_slice);
 int lb_sgemm_strided_ldc(lele_b200_ctx* ctx, const float* A, long long rsa, long long csa, long long bsa, const float* B,
@@ -160,6 +169,7 @@ struct lele_b200_sensevoice {
     unsigned long long* amax_keys = nullptr;
     void* qscratch = nullptr;
     void* attn_scratch = nullptr;
+    int fuse_lnq = 1;                 // LayerNorm + quantiser fused for the encoder width (LELE_B200_FUSE_LNQ=0 disables)
     int attn_simt = 0;   // LELE_B200_ATTN_SIMT=1: CUDA-core attention (cross-check of the tcgen05 path)
     // profiling
     int profiling = 0;
@@ -207,6 +217,28 @@ int sv_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const
     lb_fill_weight_fields(ep, w, qs);
     SV_RUN(P_GEMM_I8, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
     return LELE_B200_OK;
+}
+
+// LayerNorm -> dynamic quantiser -> tcgen05 GEMM.  For the encoder width (512) the normalised f32 rows are never
+// materialised (norm.cu: statistics + min/max pass, then a re-deriving quantise pass); m->h holds the row statistics.
+int sv_ln_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const float* gamma, const float* beta, int n, unsigned* keys,
+                 long long M, int T, const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep) {
+    if (m->fuse_lnq == 1 && lb_layer_norm_quantize_cluster_supported(n, T) && M % T == 0) {
+        // one cluster per clip: x read once, normalised rows live in shared memory until the clip's min/max is known
+        SV_RUN(P_LAYERNORM, lb_layer_norm_quantize_cluster(ctx, x, gamma, beta, (int)(M / T), T, 1e-5f, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp, keys));
+        lb_fill_weight_fields(ep, w, qs);
+        SV_RUN(P_GEMM_I8, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+        return LELE_B200_OK;
+    }
+    if (m->fuse_lnq && lb_layer_norm_quantize_supported(n, T)) {
+        SV_RUN(P_LAYERNORM, lb_layer_norm_stats(ctx, x, gamma, beta, M, n, 1e-5f, m->h, keys, T));
+        SV_RUN(P_QUANTIZE, lb_layer_norm_quantize(ctx, x, gamma, beta, M, n, m->h, keys, T, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp));
+        lb_fill_weight_fields(ep, w, qs);
+        SV_RUN(P_GEMM_I8, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+        return LELE_B200_OK;
+    }
+    SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, x, gamma, beta, M, n, 1e-5f, m->h, keys, T));
+    return sv_linear(ctx, m, m->h, keys, M, T, w, qs, ep);
 }
 
 int sv_alloc(void** p, size_t bytes) {
@@ -279,6 +311,7 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("LELE_B200_GRAPH"); m->use_graph = (e && e[0] == '0') ? 0 : 1; }
+    { const char* e = getenv("LELE_B200_FUSE_LNQ"); m->fuse_lnq = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }   // 0 unfused, 1 cluster, 2 two-pass
     if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); m->side = nullptr; }
     if (!rc) rc = sv_alloc((void**)&m->pcm_stage, sizeof(float) * B * (size_t)max_samples);
@@ -335,8 +368,6 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     int attn_ops_ready = 0;
     for (int l = 0; l < n_layers; ++l) {
         // ---- self-attention block ----
-        SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, xin, (const float*)m->lt(l, SV_L_LN1_G), (const float*)m->lt(l, SV_L_LN1_B), M, cur,
-                                                 1e-5f, m->h, site(l * 4 + 0), T));
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->qkv; ep.rows_per_slice = T;
@@ -345,7 +376,9 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
                 lb_attention_tc_operands(m->attn_scratch, B, T, d, H, &ep.qk_lo, &ep.vt_hi, &ep.vt_lo, &ep.vt_tp);
                 attn_ops_ready = 1;
             } else attn_ops_ready = 0;
-            SV_LINEAR(ctx, m,m->h, site(l * 4 + 0), M, T, m->lin[l * 4 + 0], qs, ep);
+            int rc_ = sv_ln_linear(ctx, m, xin, (const float*)m->lt(l, SV_L_LN1_G), (const float*)m->lt(l, SV_L_LN1_B), cur, site(l * 4 + 0), M, T,
+                                   m->lin[l * 4 + 0], qs, ep);
+            if (rc_) return rc_;
         }
         const bool fork = !m->profiling && m->side != nullptr;
         cudaStream_t fs = fork ? m->side : ctx->stream;
@@ -397,13 +430,13 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         }
         xin = m->x; cur = d;
         // ---- feed-forward block ----
-        SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), M, d, 1e-5f,
-                                                 m->h, site(l * 4 + 2), T));
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->f1; ep.rows_per_slice = T; ep.relu = 1;
             ep.minmax_keys = T >= 32 ? site(l * 4 + 3) : nullptr;     // fused per-clip min/max of the ReLU output
-            SV_LINEAR(ctx, m,m->h, site(l * 4 + 2), M, T, m->lin[l * 4 + 2], qs, ep);
+            int rc_ = sv_ln_linear(ctx, m, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), d, site(l * 4 + 2), M, T,
+                                   m->lin[l * 4 + 2], qs, ep);
+            if (rc_) return rc_;
             if (T < 32) SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->f1, B, (long long)T * ffn, site(l * 4 + 3)));   // very short clips
         }
         {
@@ -412,9 +445,11 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             SV_LINEAR(ctx, m,m->f1, site(l * 4 + 3), M, T, m->lin[l * 4 + 3], qs, ep);
         }
         if (l == m->n_stage1 - 1) {   // after_norm (output replaces the residual stream)
+            // in place for the register-resident row kernels (a warp holds its whole row before writing it back)
+            float* ln_out = (d == 512 || d == 560) ? m->x : m->h;
             SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, m->x, (const float*)m->tensor(SV_G_AFTER_G), (const float*)m->tensor(SV_G_AFTER_B), M, d,
-                                                     1e-5f, m->h, nullptr, T));
-            LB_CHECK_CUDA(cudaMemcpyAsync(m->x, m->h, sizeof(float) * M * d, cudaMemcpyDeviceToDevice, ctx->stream));
+                                                     1e-5f, ln_out, nullptr, T));
+            if (ln_out != m->x) LB_CHECK_CUDA(cudaMemcpyAsync(m->x, m->h, sizeof(float) * M * d, cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
     if (n_layers < m->n_layers) {   // truncated run (tests): expose the hidden state
@@ -422,8 +457,6 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         return LELE_B200_OK;
     }
     const int ctc_site = m->n_layers * 4;
-    SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, xin, (const float*)m->tensor(SV_G_TP_G), (const float*)m->tensor(SV_G_TP_B), M, cur, 1e-5f, m->h,
-                                             site(ctc_site), T));
     if (ids_dev) {
         ProfScope ps(m, ctx, P_ARGMAX);
         init_u64_kernel<<<lb_ceil_div(M, 256), 256, 0, ctx->stream>>>(m->amax_keys, M);
@@ -432,7 +465,9 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     {
         LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
         ep.out = logits_opt; ep.rows_per_slice = T; ep.argmax_keys = ids_dev ? m->amax_keys : nullptr;
-        SV_LINEAR(ctx, m,m->h, site(ctc_site), M, T, m->lin[(size_t)m->n_layers * 4], qs, ep);
+        int rc_ = sv_ln_linear(ctx, m, xin, (const float*)m->tensor(SV_G_TP_G), (const float*)m->tensor(SV_G_TP_B), cur, site(ctc_site), M, T,
+                               m->lin[(size_t)m->n_layers * 4], qs, ep);
+        if (rc_) return rc_;
     }
     if (ids_dev) SV_RUN(P_ARGMAX, lb_argmax_keys_to_ids(ctx, m->amax_keys, M, ids_dev));
     return LELE_B200_OK;
