@@ -257,6 +257,13 @@ def run_ours(args):
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                     "launches_per_step": g["calls"], "avg_launch_ms": (g["ms"] / g["calls"]) if g["calls"] else None,
                     "algorithmic_flops_per_step": flops_step, "share_of_step": (g["ms"] / sum(v["ms"] for v in prof.values())) if prof else None}
+        try:   # DRAM bytes per launch of the same kernel from the committed ncu capture (tools/summarize_ncu.py traffic)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+            roofline["traffic"] = tr["dram_bytes_per_launch"]
+            roofline["traffic_unit"] = "bytes/launch (DRAM read + write)"
+            roofline["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -53,5 +53,23 @@ def report(path):
         print()
 
 
+def traffic(path, pattern="gemm_i8_tc_kernel"):
+    """Average DRAM bytes (read + write) per launch of the dominant kernel -> the JSON bench.py reports as roofline.traffic."""
+    import json
+    lines = open(path).read().splitlines()
+    start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
+    rd = csv.DictReader(io.StringIO("\n".join(lines[start:])))
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, ids = 0.0, set()
+    for r in rd:
+        if pattern not in r["Kernel Name"]:
+            continue
+        if r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r["Metric Value"].replace(",", "")) * mult[r["Metric Unit"]]
+            ids.add(r["ID"])
+    print(json.dumps({"kernel": pattern, "launches": len(ids), "dram_bytes_per_launch": tot / max(1, len(ids)),
+                      "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(ids)} launches of one forward ({path})"}))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2])
