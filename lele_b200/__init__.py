@@ -8,7 +8,7 @@ Package layout (only what the hot path needs):
   sensevoice_weights.py synthetic weights blob + synthetic PCM (numpy only, no CUDA)
 
 Importing the package loads liblele_b200.so and raises if it is missing: there is no CPU
-fallback.  (`lele_b200.sensevoice_weights` and `lele_b200.build` import without it.)
+fallback.  (`lele_b200/build.py` is run as a script / loaded by path, so it works before the .so exists.)
 """
 from ._lib import LeleB200Error, SO_PATH, lib  # noqa: F401  (fails loudly when the .so is absent)
 from . import features, kernels  # noqa: F401

@@ -18,7 +18,7 @@ class LeleB200Error(RuntimeError):
 def _load() -> C.CDLL:
     if not os.path.exists(SO_PATH):
         raise LeleB200Error(
-            f"{SO_PATH} is missing: build it with `python -m lele_b200.build` (nvcc, sm_100a). "
+            f"{SO_PATH} is missing: build it with `python lele_b200/build.py` (nvcc, sm_100a). "
             "lele_b200 has no CPU fallback.")
     lib = C.CDLL(SO_PATH)
     lib.lele_b200_last_error.restype = C.c_char_p

@@ -1,6 +1,6 @@
 """Builds liblele_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-Usage: python -m lele_b200.build [--force]
+Usage: python lele_b200/build.py [--force]   (run as a script: importing the package needs the built .so)
 nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box.
 """
 from __future__ import annotations

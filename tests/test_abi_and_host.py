@@ -15,8 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="session")
 def so_path():
-    from lele_b200.build import build
-    return build()
+    from lele_b200 import SO_PATH      # built by tests/conftest.py before the package is imported
+    return SO_PATH
 
 
 def declared_symbols():
