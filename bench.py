@@ -256,7 +256,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "kernel": "gemm_i8_tc_kernel (tcgen05 kind::i8, fused dequant epilogue)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                     "launches_per_step": g["calls"], "avg_launch_ms": (g["ms"] / g["calls"]) if g["calls"] else None,
-                    "algorithmic_flops_per_step": flops_step, "share_of_step": (g["ms"] / sum(v["ms"] for v in prof.values())) if prof else None}
+                    "algorithmic_flops_per_step": flops_step, "share_of_step": (g["ms"] / sum(v["ms"] for k, v in prof.items() if not k.startswith("gemm_i8:"))) if prof else None}
         try:   # DRAM bytes per launch of the same kernel from the committed ncu capture (tools/summarize_ncu.py traffic)
             tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
             roofline["traffic"] = tr["dram_bytes_per_launch"]

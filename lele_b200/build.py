@@ -16,7 +16,7 @@ OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "liblele_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("LELE_B200_NVCC_DEFS", "").split()
 
 
 def sources():

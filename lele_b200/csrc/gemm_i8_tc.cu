@@ -18,6 +18,7 @@
 #include "gemm_i8_tc.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -27,12 +28,18 @@ constexpr int A_STAGE_BYTES = BM * BK;               // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK;               // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;   // 640
+constexpr int FIRST_EPI_WARP = 2;                    // warp 0: TMA producer (+ TMEM alloc), warp 1: MMA issuer
+constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;   // 576 -> 112 registers per thread
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_TILE_BYTES = 32 * 128;                       // per-warp 32x32 f32 staging tile, 128B-swizzled (1024 B aligned)
 constexpr int EPI_META_BYTES = 3 * 64 * 4;                     // zp*colsum / scale / bias of the warp's 64 columns
 constexpr int EPI_BYTES = NUM_EPI_WARPS * (EPI_TILE_BYTES + EPI_META_BYTES);
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+#ifdef LELE_B200_GEMM_TIMELINE
+constexpr bool GEMM_DBG = true;    // role wait counters (clock64) printed by CTAs 0 / 77 when LELE_B200_GEMM_DBG=1; costs ~12 registers
+#else
+constexpr bool GEMM_DBG = false;
+#endif
 constexpr int UMMA_K = 32;                           // bytes per tcgen05.mma for 8-bit operands
 
 // ---- PTX wrappers ----------------------------------------------------------
@@ -120,12 +127,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 
 struct KernelArgs {
     int M, N, K;
+    int vec_io;
+    int dbg;            // LELE_B200_GEMM_DBG=1: CTAs 0 and 77 print where their producer / MMA / epilogue roles waited (clock64)
     int num_m_blocks, num_n_blocks, num_k_blocks;
     LbI8Epilogue ep;
 };
 
 // Epilogue specialisations (compile-time, so the inner loops carry no uniform branches)
-enum EpiMode { EPI_PLAIN = 0, EPI_MINMAX, EPI_ARGMAX, EPI_R1, EPI_R2, EPI_R12, EPI_QKV };
+enum EpiMode { EPI_PLAIN = 0, EPI_MINMAX, EPI_ARGMAX, EPI_R1, EPI_R2, EPI_R12, EPI_QKV, EPI_QUANT };
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
@@ -142,16 +151,23 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
                  ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// round-half-even + clamp to [0, 255] in one conversion (float -> integer cvt saturates to the destination range, NaN -> 0)
+__device__ __forceinline__ unsigned cvt_sat_u8(float v) { unsigned u; asm("cvt.rni.u8.f32 %0, %1;" : "=r"(u) : "f"(v)); return u; }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // TMA_OUT: the 32x32 f32 sub-tile a warp finished is written by one cp.async.bulk.tensor store from the
 // swizzled staging tile (no per-element store phase); used when the epilogue has no residual operand.
-template <int MODE, bool TMA_OUT>
+// RELU (compile-time; PLAIN / MINMAX / QUANT only): the per-element epilogue is bound by the half-rate ALU pipe (IADD3,
+// I2FP, FMNMX ...), so a ReLU that is not asked for -- or is implied (QUANT: unsigned saturation; MINMAX: max(relu(t)) =
+// max(max t, 0), min(relu(t)) >= 0) -- must not cost an FMNMX per element.
+template <int MODE, bool TMA_OUT, bool RELU>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_lo, const KernelArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    unsigned long long cta_t0 = 0;
+    if (GEMM_DBG && args.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;   // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem = smem_raw + pad;
     uint8_t* smem_a = smem;
@@ -174,7 +190,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 2) {   // whole warp: allocate all 512 TMEM columns (1 CTA/SM by construction)
+    if (warp == 0) {   // whole warp: allocate all 512 TMEM columns (1 CTA/SM by construction)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -187,28 +203,35 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            long long w_empty = 0; const long long t_begin = clock64();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
                 for (int kb = 0; kb < args.num_k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t0; }
+                    else mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
                     tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77))
+                printf("GEMMDBG blk %d TMA: total %lld wait_empty %lld\n", blockIdx.x, clock64() - t_begin, w_empty);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (single thread) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            long long w_tmem = 0, w_full = 0; const long long t_begin = clock64();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
+                if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t0; }
+                else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < args.num_k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);            // TMA bytes landed
+                    if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&full_bar[stage], phase); w_full += clock64() - t0; }
+                    else mbar_wait(&full_bar[stage], phase);            // TMA bytes landed
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
@@ -224,15 +247,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77))
+                printf("GEMMDBG blk %d MMA: total %lld wait_operands %lld wait_epilogue %lld (tiles %d, k-blocks %d)\n", blockIdx.x, clock64() - t_begin, w_full, w_tmem,
+                       (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, args.num_k_blocks);
         }
-    } else if (warp >= 4) {
+    } else if (warp >= FIRST_EPI_WARP) {
         // ===================== epilogue: 16 warps, each owns 32 rows x 64 columns of every tile =====================
         // phase 1 (thread = row): TMEM -> exact integer corrections, scale, bias, ReLU (+ min/max, arg-max) -> the warp's
         //          staging tile: 32 rows x 128 B, 16-byte chunks XOR-swizzled by (row & 7) == the TMA SWIZZLE_128B
         //          layout, so both the row-wise 16 B writes and the column-wise 4 B reads are bank-conflict free
         // then     TMA_OUT: one elected lane issues a 32x32 tensor store (clipped at M / N by the hardware)
         //          else   : phase 2 (lane = column) reads the tile transposed -> residual adds -> 128-byte coalesced stores
-        const int ew = warp - 4;
+        const int ew = warp - FIRST_EPI_WARP;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
         const int cgrp = ew >> 2;           // which 64-column group of the tile
         const LbI8Epilogue& ep = args.ep;
@@ -240,18 +266,40 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint32_t meta_s = smem_u32(epi_base) + NUM_EPI_WARPS * EPI_TILE_BYTES + (uint32_t)ew * EPI_META_BYTES;   // zp*colsum[64] | scale[64] | bias[64]
         const uint32_t my_row_s = tile_s + (uint32_t)lane * 128u;
         const uint32_t sw = (uint32_t)(lane & 7);
-        const float relu_lo = ep.relu ? 0.0f : -3.402823466e+38f;
         const int N = args.N, M = args.M;
         const float FMAX = 3.402823466e+38f;
+        const bool vec_io = !TMA_OUT && args.vec_io;       // rows 16-byte aligned: float4 residual loads / output stores
         int acc = 0; uint32_t acc_phase = 0;
+        long long w_acc = 0, t_busy0 = 0, busy = 0, d_ld = 0, d_math = 0; const long long t_begin = clock64();
+        int pf_rs = 0, pf_zpa = 0, pf_cs[2] = {0, 0}; float pf_sa = 0.0f, pf_ws[2] = {0.0f, 0.0f}, pf_bi[2] = {0.0f, 0.0f};
+        unsigned pf_qkey = 0;                                          // EPI_QUANT: one min/max key slot of the warp's clip A (lanes 0-15) / A+1 (16-31)
+        auto fetch_meta = [&](int t) {
+            if (t >= num_tiles) return;
+            const int mb = t / args.num_n_blocks, nb = t % args.num_n_blocks;
+            const int rw = mb * BM + quad * 32 + lane;
+            if (MODE == EPI_QUANT) {
+                const int rps_ = ep.rows_per_slice > 0 ? ep.rows_per_slice : 0x7fffffff;
+                const int sl = min((mb * BM + quad * 32) / rps_ + (lane >> 4), (M - 1) / rps_);
+                pf_qkey = __ldg(ep.q_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
+            }
+            pf_rs = 0; pf_zpa = 0; pf_sa = 0.0f;
+            if (rw < M) { pf_rs = __ldg(ep.rowsum + rw); pf_zpa = __ldg(ep.row_zp + rw); pf_sa = __ldg(ep.row_scale + rw); }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int cc = min(nb * BN + cgrp * 64 + hh * 32 + lane, N - 1);
+                pf_cs[hh] = __ldg(ep.colsum + cc); pf_ws[hh] = __ldg(ep.w_scale + cc); pf_bi[hh] = __ldg(ep.bias + cc);
+            }
+        };
+        fetch_meta(blockIdx.x);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
             const int first_row = m_blk * BM + quad * 32;
             const int row = first_row + lane;
             const bool row_ok = row < M;
             const int gcol_w = n_blk * BN + cgrp * 64;                 // first global column of this warp
-            int rs = 0, zpa = 0; float sa = 0.0f;
-            if (row_ok) { rs = __ldg(ep.rowsum + row); zpa = __ldg(ep.row_zp + row); sa = __ldg(ep.row_scale + row); }
+            // this tile's row / column metadata was fetched while the previous tile drained (pf_*), so no global-load
+            // latency sits between two accumulators
+            const int rs = pf_rs, zpa = pf_zpa; const float sa = pf_sa;
             const int row_corr = args.K * zpa * ep.w_zp - ep.w_zp * rs;
             // Per-warp column metadata, pre-combined with the activation parameters of the clip that owns the warp's
             // first row ("A"): zcA[c] = zp_A * colsum[c], csA[c] = scale_A * w_scale[c].  A warp's 32 rows touch a
@@ -266,74 +314,134 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int c = hh * 32 + lane;
-                const int cc = min(gcol_w + c, N - 1);
-                const int cs_raw = __ldg(ep.colsum + cc);
-                const float ws_raw = __ldg(ep.w_scale + cc);
-                sts_s32(meta_s + 4 * c, all_a ? zpa_a * cs_raw : cs_raw);               // straddling warps keep raw metadata
-                sts_f32(meta_s + 256 + 4 * c, all_a ? __fmul_rn(sa_a, ws_raw) : ws_raw);
-                sts_f32(meta_s + 512 + 4 * c, __ldg(ep.bias + cc));
+                sts_s32(meta_s + 4 * c, all_a ? zpa_a * pf_cs[hh] : pf_cs[hh]);               // straddling warps keep raw metadata
+                sts_f32(meta_s + 256 + 4 * c, all_a ? __fmul_rn(sa_a, pf_ws[hh]) : pf_ws[hh]);
+                sts_f32(meta_s + 512 + 4 * c, pf_bi[hh]);
             }
-            unsigned long long best = 0ull;
+            float q_inv = 0.0f, q_zp = 0.0f, q_scale = 0.0f; int q_sum = 0;
+            if (MODE == EPI_QUANT) {
+                // lanes 0-15 hold the 8 (min, max) key slots of clip A, lanes 16-31 those of clip A+1: reduce over the slots
+                unsigned k = pf_qkey;
+#pragma unroll
+                for (int of = 2; of <= 8; of <<= 1) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, k, of);
+                    k = (lane & 1) ? max(k, o) : min(k, o);
+                }
+                const int src = in_a ? 0 : 16;
+                const float mn = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src)), mx = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src + 1));
+                const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);          // dq_params (quant.cu)
+                q_scale = __fdiv_rn(fmaxf(__fsub_rn(amax, amin), 1e-5f), 255.0f);
+                q_zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, q_scale)), 0.0f), 255.0f);
+                q_inv = __fdiv_rn(1.0f, q_scale);
+            }
+            fetch_meta(tile + (int)gridDim.x);                         // next tile's metadata: consumed one iteration later
+            float best_t = -3.402823466e+38f; int best_c = -1;
             float vmin = FMAX, vmax = -FMAX;                           // this row's min / max over the warp's 64 columns
             const int nrows = min(32, M - first_row);
             __syncwarp();
-            mbar_wait(&tmem_full[acc], acc_phase);
+            if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&tmem_full[acc], acc_phase); t_busy0 = clock64(); w_acc += t_busy0 - t0; }
+            else mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll 1
             for (int chunk = 0; chunk < 2; ++chunk) {
                 const int col0 = cgrp * 64 + chunk * 32;               // column inside the tile
                 const int gcol0 = n_blk * BN + col0;                   // global column
                 uint32_t r[32];
+                long long t_c0 = 0;
+                if (GEMM_DBG && args.dbg) t_c0 = clock64();
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), r);
+                if (GEMM_DBG && args.dbg) { const long long t1 = clock64(); d_ld += t1 - t_c0; t_c0 = t1; }
                 if (gcol0 >= N || nrows <= 0) continue;                // warp-uniform
                 if (TMA_OUT) {                                         // the previous store must have read the staging tile
                     if (lane == 0) tma_store_wait_read();
                     __syncwarp();
                 }
-                // ---- phase 1 ----
-                const bool full_cols = gcol0 + 32 <= N;
-                auto finish = [&](float t, float bias_v, int idx) -> float {
-                    t = ep.has_bias ? __fadd_rn(t, bias_v) : t;
-                    t = fmaxf(t, relu_lo);
-                    if (MODE == EPI_ARGMAX) {
-                        if (row_ok && gcol0 + idx < N) {
-                            unsigned long long key = ((unsigned long long)lb_fkey(t) << 32) | (unsigned)(gcol0 + idx);
-                            best = key > best ? key : best;
-                        }
-                    }
-                    if (MODE == EPI_MINMAX) {
-                        if (full_cols || gcol0 + idx < N) { vmin = fminf(vmin, t); vmax = fmaxf(vmax, t); }
-                    }
-                    return t;
-                };
-                if (all_a) {
+                // Residual epilogues: 128-bit accesses, lane = (row % 4, 16-byte column chunk), 4 rows x 128 B per warp
+                // instruction, and every residual load of the sub-tile is issued before the accumulator math so that
+                // 4 KB (8 KB for two residuals) per warp is in flight while phase 1 runs.
+                constexpr bool HAS_R1 = (MODE == EPI_R1 || MODE == EPI_R12), HAS_R2 = (MODE == EPI_R2 || MODE == EPI_R12);
+                const int vq = lane & 7, vr = lane >> 3;
+                const bool vcol_ok = gcol0 + vq * 4 < N;               // N % 4 == 0 on this path: a float4 is all-in or all-out
+                const long long vbase = (long long)(first_row + vr) * N + gcol0 + vq * 4;
+                float4 res1[8], res2[8];
+                if ((HAS_R1 || HAS_R2) && vec_io) {
+                    if (MODE == EPI_R1) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int4 zc = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
-                        const int4 csb = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
-                        const int4 bib = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
-                        const float t0 = finish(__fmul_rn((float)((int)r[q * 4 + 0] + row_corr - zc.x), __int_as_float(csb.x)), __int_as_float(bib.x), q * 4 + 0);
-                        const float t1 = finish(__fmul_rn((float)((int)r[q * 4 + 1] + row_corr - zc.y), __int_as_float(csb.y)), __int_as_float(bib.y), q * 4 + 1);
-                        const float t2 = finish(__fmul_rn((float)((int)r[q * 4 + 2] + row_corr - zc.z), __int_as_float(csb.z)), __int_as_float(bib.z), q * 4 + 2);
-                        const float t3 = finish(__fmul_rn((float)((int)r[q * 4 + 3] + row_corr - zc.w), __int_as_float(csb.w)), __int_as_float(bib.w), q * 4 + 3);
-                        sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), t0, t1, t2, t3);
-                        if (MODE == EPI_QKV) { r[q * 4 + 0] = __float_as_uint(t0); r[q * 4 + 1] = __float_as_uint(t1); r[q * 4 + 2] = __float_as_uint(t2); r[q * 4 + 3] = __float_as_uint(t3); }
+                        for (int it = 0; it < 8; ++it)
+                            if (vcol_ok && it * 4 + vr < nrows) res1[it] = __ldg(reinterpret_cast<const float4*>(ep.add1 + vbase + (long long)it * 4 * N));
                     }
-                } else {   // the warp straddles a clip boundary: raw column metadata, combined per row here
+                    if (MODE == EPI_R2) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int4 zc = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
-                        const int4 csb = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
-                        const int4 bib = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
-                        const float t0 = finish(__fmul_rn((float)((int)r[q * 4 + 0] + row_corr - zpa * zc.x), __fmul_rn(sa, __int_as_float(csb.x))), __int_as_float(bib.x), q * 4 + 0);
-                        const float t1 = finish(__fmul_rn((float)((int)r[q * 4 + 1] + row_corr - zpa * zc.y), __fmul_rn(sa, __int_as_float(csb.y))), __int_as_float(bib.y), q * 4 + 1);
-                        const float t2 = finish(__fmul_rn((float)((int)r[q * 4 + 2] + row_corr - zpa * zc.z), __fmul_rn(sa, __int_as_float(csb.z))), __int_as_float(bib.z), q * 4 + 2);
-                        const float t3 = finish(__fmul_rn((float)((int)r[q * 4 + 3] + row_corr - zpa * zc.w), __fmul_rn(sa, __int_as_float(csb.w))), __int_as_float(bib.w), q * 4 + 3);
-                        sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), t0, t1, t2, t3);
-                        if (MODE == EPI_QKV) { r[q * 4 + 0] = __float_as_uint(t0); r[q * 4 + 1] = __float_as_uint(t1); r[q * 4 + 2] = __float_as_uint(t2); r[q * 4 + 3] = __float_as_uint(t3); }
+                        for (int it = 0; it < 8; ++it)
+                            if (vcol_ok && it * 4 + vr < nrows) res2[it] = __ldg(reinterpret_cast<const float4*>(ep.add2 + vbase + (long long)it * 4 * N));
                     }
                 }
-                if (MODE == EPI_ARGMAX && !ep.out) continue;           // ids only: nothing to write
+                // ---- phase 1 ----
+                const bool full_cols = gcol0 + 32 <= N;
+                // r[] <- the 32 finished f32 values of this row (accumulator registers are reused in place).  Four
+                // compile-time variants: FULL = all 32 columns exist (no per-element column predicate: VIADD + ISETP + FSEL
+                // per element would double the ALU-pipe work that bounds this loop), STRADDLE = the warp's rows span two
+                // clips (raw column metadata, combined per row here; 1 warp in ~8 for T' = 271).
+                auto phase1 = [&](auto full_tag, auto straddle_tag) {
+                    constexpr bool FULL = decltype(full_tag)::value, STRADDLE = decltype(straddle_tag)::value;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int4 zc4 = lds_v4(meta_s + 4 * (chunk * 32 + q * 4));
+                        const int4 cs4 = lds_v4(meta_s + 256 + 4 * (chunk * 32 + q * 4));
+                        const int4 bi4 = lds_v4(meta_s + 512 + 4 * (chunk * 32 + q * 4));
+                        const int zc[4] = {zc4.x, zc4.y, zc4.z, zc4.w};
+                        const float cs[4] = {__int_as_float(cs4.x), __int_as_float(cs4.y), __int_as_float(cs4.z), __int_as_float(cs4.w)};
+                        const float bi[4] = {__int_as_float(bi4.x), __int_as_float(bi4.y), __int_as_float(bi4.z), __int_as_float(bi4.w)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int idx = q * 4 + e;
+                            const int iv = (int)r[idx] + row_corr - (STRADDLE ? zpa * zc[e] : zc[e]);
+                            float t = __fmul_rn((float)iv, STRADDLE ? __fmul_rn(sa, cs[e]) : cs[e]);
+                            t = ep.has_bias ? __fadd_rn(t, bi[e]) : t;
+                            const bool col_ok = FULL || gcol0 + idx < N;
+                            if (MODE == EPI_ARGMAX) {                  // columns ascend, ">=" keeps the last maximum (tokenizer.rs:55)
+                                if (col_ok && t >= best_t) { best_t = t; best_c = gcol0 + idx; }
+                            }
+                            if (MODE == EPI_MINMAX) {
+                                if (col_ok) { if (!RELU) vmin = fminf(vmin, t); vmax = fmaxf(vmax, t); }
+                            }
+                            if (RELU && MODE != EPI_MINMAX && MODE != EPI_QUANT) t = fmaxf(t, 0.0f);
+                            r[idx] = __float_as_uint(t);
+                        }
+                    }
+                };
+                if (full_cols) { if (all_a) phase1(std::true_type{}, std::false_type{}); else phase1(std::true_type{}, std::true_type{}); }
+                else           { if (all_a) phase1(std::false_type{}, std::false_type{}); else phase1(std::false_type{}, std::true_type{}); }
+                if (GEMM_DBG && args.dbg) { const long long t1 = clock64(); d_math += t1 - t_c0; t_c0 = t1; }
+                if (MODE == EPI_QUANT) {
+                    // the consumer's dynamic quantiser fused here: u8 = clamp(rint(fma(y, 1/scale, zp)), 0, 255) with the clip's
+                    // (scale, zp) from the min/max a previous max-only pass of this same GEMM produced; ReLU is implied by the
+                    // unsigned saturation (a ReLU output has min >= 0, hence zp == 0).  32 B per row -> 1 KB staging -> TMA store.
+                    unsigned pk[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const unsigned u0 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[q * 4 + 0]), q_inv, q_zp));
+                        const unsigned u1 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[q * 4 + 1]), q_inv, q_zp));
+                        const unsigned u2 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[q * 4 + 2]), q_inv, q_zp));
+                        const unsigned u3 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[q * 4 + 3]), q_inv, q_zp));
+                        pk[q] = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
+                        q_sum = (int)__dp4a(pk[q], 0x01010101u, (unsigned)q_sum);
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, first_row);
+                    continue;
+                }
+                if (!ep.out) continue;                                 // arg-max ids only / max-only pass: nothing to write
+                if (RELU && MODE == EPI_MINMAX) {                      // (the min/max above ran on the unclamped values)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.0f));
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), __uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
                 if (TMA_OUT) {
                     fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
                     __syncwarp();
@@ -381,7 +489,43 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     __syncwarp();
                     // ---- phase 2 ----
                     const int col = gcol0 + lane;
-                    if (col < N) {
+                    if (vec_io) {
+                        if (MODE == EPI_R12) {      // two residuals do not fit beside the accumulator registers: loaded here
+                                                    // (r[] is dead), in two halves of 16 rows (4 KB per warp in flight)
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                                for (int it = hf * 4; it < hf * 4 + 4; ++it)
+                                    if (vcol_ok && it * 4 + vr < nrows) {
+                                        res1[it] = __ldg(reinterpret_cast<const float4*>(ep.add1 + vbase + (long long)it * 4 * N));
+                                        res2[it] = __ldg(reinterpret_cast<const float4*>(ep.add2 + vbase + (long long)it * 4 * N));
+                                    }
+#pragma unroll
+                                for (int it = hf * 4; it < hf * 4 + 4; ++it) {
+                                    const int rr = it * 4 + vr;
+                                    if (vcol_ok && rr < nrows) {
+                                        const int4 raw = lds_v4(tile_s + (uint32_t)rr * 128u + (((uint32_t)vq ^ (uint32_t)(rr & 7)) << 4));
+                                        float4 v = make_float4(__int_as_float(raw.x), __int_as_float(raw.y), __int_as_float(raw.z), __int_as_float(raw.w));
+                                        v.x = __fadd_rn(v.x, res1[it].x); v.y = __fadd_rn(v.y, res1[it].y); v.z = __fadd_rn(v.z, res1[it].z); v.w = __fadd_rn(v.w, res1[it].w);
+                                        v.x = __fadd_rn(res2[it].x, v.x); v.y = __fadd_rn(res2[it].y, v.y); v.z = __fadd_rn(res2[it].z, v.z); v.w = __fadd_rn(res2[it].w, v.w);
+                                        *reinterpret_cast<float4*>(ep.out + vbase + (long long)it * 4 * N) = v;
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int rr = it * 4 + vr;
+                                if (vcol_ok && rr < nrows) {
+                                    const int4 raw = lds_v4(tile_s + (uint32_t)rr * 128u + (((uint32_t)vq ^ (uint32_t)(rr & 7)) << 4));
+                                    float4 v = make_float4(__int_as_float(raw.x), __int_as_float(raw.y), __int_as_float(raw.z), __int_as_float(raw.w));
+                                    if (HAS_R1) { v.x = __fadd_rn(v.x, res1[it].x); v.y = __fadd_rn(v.y, res1[it].y); v.z = __fadd_rn(v.z, res1[it].z); v.w = __fadd_rn(v.w, res1[it].w); }
+                                    if (HAS_R2) { v.x = __fadd_rn(res2[it].x, v.x); v.y = __fadd_rn(res2[it].y, v.y); v.z = __fadd_rn(res2[it].z, v.z); v.w = __fadd_rn(res2[it].w, v.w); }
+                                    *reinterpret_cast<float4*>(ep.out + vbase + (long long)it * 4 * N) = v;
+                                }
+                            }
+                        }
+                    } else if (col < N) {
                         const long long base = (long long)first_row * N + col;
                         float* outp = ep.out + base;
                         const float* a1 = (MODE == EPI_R1 || MODE == EPI_R12) ? ep.add1 + base : nullptr;
@@ -405,7 +549,14 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (GEMM_DBG && args.dbg) busy += clock64() - t_busy0;
 
+            if (MODE == EPI_QUANT && row_ok) {
+                if (gcol_w < N) atomicAdd(ep.q_rowsum + row, q_sum);                       // 64 of the row's N columns
+                if (n_blk == 0 && cgrp == 0) { ep.q_row_scale[row] = q_scale; ep.q_row_zp[row] = (int)q_zp; }
+            }
+            if (MODE == EPI_MINMAX && ep.q_rowsum && row_ok && n_blk == 0 && cgrp == 0) ep.q_rowsum[row] = 0;   // max-only pass: arm the next pass's row sums
+            if (MODE == EPI_MINMAX && RELU && vmax > -FMAX) { vmin = 0.0f; vmax = fmaxf(vmax, 0.0f); }   // any value >= 0 gives amin = 0
             if (MODE == EPI_MINMAX && nrows > 0) {
                 // rows of clip A (the one owning the warp's first row) and of clip A+1 reduce separately
                 const float mnA = lb_warp_min(in_a ? vmin : FMAX), mxA = lb_warp_max(in_a ? vmax : -FMAX);
@@ -416,14 +567,23 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     if (lane == 0 && mnB <= mxB) lb_mm_update(ep.minmax_keys, slice_first + 1, mnB, mxB);
                 }
             }
-            if (MODE == EPI_ARGMAX && row_ok && best != 0ull) atomicMax(ep.argmax_keys + row, best);
+            if (MODE == EPI_ARGMAX && row_ok && best_c >= 0) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey(best_t) << 32) | (unsigned)best_c);
         }
         if (TMA_OUT && lane == 0) tma_store_wait_all();                // staging smem must outlive the bulk stores
+        if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (ew == 0 || ew == 15))
+            printf("GEMMDBG blk %d EPI warp %d: total %lld wait_accumulator %lld drain %lld (tmem ld %lld, math %lld)\n", blockIdx.x, ew, clock64() - t_begin, w_acc, busy, d_ld, d_math);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (GEMM_DBG && args.dbg && threadIdx.x == 0) {
+        unsigned long long t1; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("GEMMCTA mode %d blk %d sm %u t0 %llu t1 %llu\n", MODE, blockIdx.x, smid, cta_t0, t1);
+    }
+    if (warp == 0) {
+        __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
@@ -494,6 +654,27 @@ int cached_tmap_out_f32(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, l
     ctx->tmaps.emplace(h, std::move(blob));
     return LELE_B200_OK;
 }
+// u8 [rows, cols] row-major output, box = 32 x 32 (one epilogue warp's quantised sub-tile), no swizzle
+int cached_tmap_out_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols) {
+    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(0x6f757538ull, (unsigned long long)(uintptr_t)ptr), (unsigned long long)rows),
+                                       (unsigned long long)cols);
+    auto it = ctx->tmaps.find(h);
+    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(u8 out) failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return LELE_B200_ERR_CUDA; }
+    std::vector<unsigned char> blob(sizeof(CUtensorMap));
+    memcpy(blob.data(), map, sizeof(CUtensorMap));
+    ctx->tmaps.emplace(h, std::move(blob));
+    return LELE_B200_OK;
+}
 }  // namespace
 
 int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep) {
@@ -513,26 +694,39 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     args.num_n_blocks = lb_ceil_div(N, BN);
     args.num_k_blocks = lb_ceil_div(K, BK);
     args.ep = ep;
+    args.dbg = getenv("LELE_B200_GEMM_DBG") ? 1 : 0;
+    args.vec_io = (N % 4 == 0) && ((((uintptr_t)ep.out | (uintptr_t)ep.add1 | (uintptr_t)ep.add2) & 15) == 0) && !getenv("LELE_B200_GEMM_NO_VEC_IO");
     int tiles = args.num_m_blocks * args.num_n_blocks;
     int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
     int mode = EPI_PLAIN;
-    if (ep.qk_lo) mode = EPI_QKV;
+    if (ep.q_out) mode = EPI_QUANT;
+    else if (ep.qk_lo) mode = EPI_QKV;
     else if (ep.argmax_keys) mode = EPI_ARGMAX;
     else if (ep.minmax_keys) mode = EPI_MINMAX;
     else if (ep.add1 && ep.add2) mode = EPI_R12;
     else if (ep.add1) mode = EPI_R1;
     else if (ep.add2) mode = EPI_R2;
     LB_REQUIRE(!(ep.minmax_keys && (ep.add1 || ep.add2)), "gemm_i8_tc: fused min/max with residual adds is not instantiated");
-    LB_REQUIRE(ep.out || mode == EPI_ARGMAX, "gemm_i8_tc: no output requested");
+    LB_REQUIRE(ep.out || mode == EPI_ARGMAX || mode == EPI_MINMAX || mode == EPI_QUANT, "gemm_i8_tc: no output requested");
+    LB_REQUIRE(!ep.relu || mode == EPI_PLAIN || mode == EPI_MINMAX || mode == EPI_QUANT, "gemm_i8_tc: ReLU is only instantiated for the plain / min-max / quantising epilogues");
+    if (mode == EPI_QUANT) {
+        LB_REQUIRE(N % 32 == 0 && ep.q_rowsum && ep.q_row_scale && ep.q_row_zp && ep.q_keys && ep.rows_per_slice >= 32 && !ep.add1 && !ep.add2 &&
+                   !ep.minmax_keys && !ep.argmax_keys && !ep.out && (((uintptr_t)ep.q_out) & 15) == 0,
+                   "gemm_i8_tc: fused output quantiser needs N %% 32 == 0, rows_per_slice >= 32 and the q_* buffers, and excludes the other fusions");
+    }
     // residual-free epilogues whose rows are 16-byte aligned store through TMA (no per-element store phase)
     if (mode == EPI_QKV) {
         LB_REQUIRE(N % 384 == 0 && ep.vt_hi && ep.vt_lo && ep.rows_per_slice > 0 && ep.vt_tp >= ep.rows_per_slice && !ep.add1 && !ep.add2 &&
                    !ep.minmax_keys && !ep.argmax_keys && !getenv("LELE_B200_GEMM_NO_TMA_STORE"),
                    "gemm_i8_tc: fused attention-operand epilogue needs N = 3 * heads * 128 and the V^T buffers");
     }
-    const bool tma_out = (mode == EPI_PLAIN || mode == EPI_MINMAX || mode == EPI_QKV) && N % 4 == 0 && (((uintptr_t)ep.out) & 15) == 0 &&
+    const bool tma_out = (mode == EPI_PLAIN || mode == EPI_MINMAX || mode == EPI_QKV) && ep.out && N % 4 == 0 && (((uintptr_t)ep.out) & 15) == 0 &&
                          !getenv("LELE_B200_GEMM_NO_TMA_STORE");
     CUtensorMap tout = ta, tlo = ta;
+    if (mode == EPI_QUANT) {
+        rc = cached_tmap_out_u8(ctx, &tout, ep.q_out, M, N);
+        if (rc) return rc;
+    }
     if (tma_out) {
         rc = cached_tmap_out_f32(ctx, &tout, ep.out, M, N);
         if (rc) return rc;
@@ -542,26 +736,31 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
         rc = cached_tmap_out_f32(ctx, &tlo, ep.qk_lo, M, N / 3 * 2);
         if (rc) return rc;
     }
-    static thread_local unsigned attr_done = 0;   // one process per GPU: the attribute is set once per instantiation
-#define LB_LAUNCH_MODE(MD, TM)                                                                                          \
+    static thread_local unsigned long long attr_done = 0;   // one process per GPU: the attribute is set once per instantiation
+#define LB_LAUNCH_MODE3(MD, TM, RL)                                                                                     \
     {                                                                                                                   \
-        const unsigned bit = 1u << (MD * 2 + (TM ? 1 : 0));                                                             \
+        const unsigned long long bit = 1ull << (MD * 4 + (TM ? 2 : 0) + (RL ? 1 : 0));                                              \
         if (!(attr_done & bit)) {                                                                                       \
-            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD, TM, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
             attr_done |= bit;                                                                                           \
         }                                                                                                               \
-        gemm_i8_tc_kernel<MD, TM><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, tout, tlo, args);                  \
+        gemm_i8_tc_kernel<MD, TM, RL><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, tout, tlo, args);              \
     }
+#define LB_LAUNCH_MODE(MD, TM) LB_LAUNCH_MODE3(MD, TM, false)
+#define LB_LAUNCH_RELU(MD, TM) { if (ep.relu) LB_LAUNCH_MODE3(MD, TM, true) else LB_LAUNCH_MODE3(MD, TM, false) }
     switch (mode) {
-        case EPI_PLAIN: if (tma_out) LB_LAUNCH_MODE(EPI_PLAIN, true) else LB_LAUNCH_MODE(EPI_PLAIN, false) break;
-        case EPI_MINMAX: if (tma_out) LB_LAUNCH_MODE(EPI_MINMAX, true) else LB_LAUNCH_MODE(EPI_MINMAX, false) break;
+        case EPI_PLAIN: if (tma_out) LB_LAUNCH_RELU(EPI_PLAIN, true) else LB_LAUNCH_RELU(EPI_PLAIN, false) break;
+        case EPI_MINMAX: if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
         case EPI_ARGMAX: LB_LAUNCH_MODE(EPI_ARGMAX, false) break;
         case EPI_R1: LB_LAUNCH_MODE(EPI_R1, false) break;
         case EPI_R2: LB_LAUNCH_MODE(EPI_R2, false) break;
         case EPI_R12: LB_LAUNCH_MODE(EPI_R12, false) break;
         case EPI_QKV: LB_LAUNCH_MODE(EPI_QKV, true) break;
+        case EPI_QUANT: LB_LAUNCH_RELU(EPI_QUANT, true) break;
     }
 #undef LB_LAUNCH_MODE
+#undef LB_LAUNCH_MODE3
+#undef LB_LAUNCH_RELU
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

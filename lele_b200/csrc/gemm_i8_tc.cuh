@@ -29,6 +29,15 @@ struct LbI8Epilogue {
     float* vt_hi;
     float* vt_lo;
     int vt_tp;
+    // fused output quantiser (two-pass linear -> dynamic quantiser, no f32 round trip): pass 1 = this GEMM with out == NULL,
+    // minmax_keys set and q_rowsum set (max-only, zeroes q_rowsum); pass 2 = the same GEMM with q_out set: the epilogue
+    // quantises with the per-slice (scale, zp) derived from q_keys (the keys pass 1 reduced) and emits the next GEMM's
+    // operand directly: q_out u8 [M, N], q_rowsum [M] (atomic adds), q_row_scale / q_row_zp [M].  N % 32 == 0.
+    uint8_t* q_out;
+    int32_t* q_rowsum;
+    float* q_row_scale;
+    int32_t* q_row_zp;
+    const unsigned* q_keys;
 };
 
 // A: u8 [M, K] row-major (K-major); Wt: u8 [N, K] row-major (K-major).  K % 16 == 0.

@@ -292,19 +292,22 @@ ln_quantize_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 // CS CTAs (one SM each) split the clip's rows; each normalises its rows into shared memory (x is read exactly once),
 // the per-CTA min/max are exchanged through distributed shared memory, then every CTA quantises its resident rows.
 // No f32 intermediate, no statistics buffer, no global atomics.  Same arithmetic as the two-pass kernels.
-constexpr int LNQ_CS = 4;            // CTAs per clip
-constexpr int LNQ_WARPS = 16;
 constexpr int LNQ_CHUNK = 8;         // rows per bulk copy / mbarrier
 constexpr int LNQ_MAX_CHUNKS = 16;   // <= 128 rows per CTA
-__global__ void __launch_bounds__(LNQ_WARPS * 32, 1)
+// LNQ_CS CTAs per clip (the cluster), LNQ_WARPS warps per CTA, MINB co-resident CTAs per SM: 8 x 8 warps x 3 keeps ~105 rows
+// in flight per SM in three independent CTAs (their copy / normalise / exchange / quantise phases overlap) instead of one CTA
+// holding 69 rows and running its phases back to back.
+template <int LNQ_CS, int LNQ_WARPS, int MINB>
+__global__ void __launch_bounds__(LNQ_WARPS * 32, MINB)
 ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int T, float eps,
                         uint8_t* __restrict__ a_u8, int32_t* __restrict__ rowsum, float* __restrict__ row_scale, int32_t* __restrict__ row_zp,
-                        unsigned* __restrict__ keys_out) {
+                        unsigned* __restrict__ keys_out, int dbg) {
     namespace cg = cooperative_groups;
     constexpr int N = 512, NB = 16;
+    long long t_dbg[6]; t_dbg[0] = clock64();
     extern __shared__ __align__(16) float lnq_rows[];            // [R][512] normalised rows of this CTA
-    __shared__ float red[2][LNQ_WARPS];
-    __shared__ float cta_mm[2];                                   // read by the peer CTAs of the cluster
+    __shared__ float red[2][32];
+    __shared__ float peer_mm[LNQ_CS][2];                          // (min, max) of every CTA of the cluster, pushed by its owner
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int clip = blockIdx.y;
@@ -339,6 +342,7 @@ ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ g
     for (int i = 0; i < NB; ++i) { g[i] = __ldg(gamma + 32 * i + lane); bt[i] = __ldg(beta + 32 * i + lane); }
     const float inv_n = __fdiv_rn(1.0f, (float)N);
     float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+    t_dbg[1] = clock64();
     for (int r = warp; r < n_rows; r += LNQ_WARPS) {
         {   // wait for the chunk holding row r (single use: parity 0)
             const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&chunk_bar[r / LNQ_CHUNK]);
@@ -369,21 +373,23 @@ ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ g
             o[32 * i + lane] = y;
         }
     }
+    t_dbg[2] = clock64();
     vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
     if (lane == 0) { red[0][warp] = vmin; red[1][warp] = vmax; }
     __syncthreads();
     if (warp == 0) {
         float a = lane < LNQ_WARPS ? red[0][lane] : 3.402823466e+38f, b = lane < LNQ_WARPS ? red[1][lane] : -3.402823466e+38f;
         a = lb_warp_min(a); b = lb_warp_max(b);
-        if (lane == 0) { cta_mm[0] = a; cta_mm[1] = b; }
+        if (lane < LNQ_CS) {                                      // push into every CTA of the cluster (lane = destination rank):
+            float* dst = cluster.map_shared_rank(&peer_mm[rank][0], lane);   // after the barrier each CTA reads only its own
+            dst[0] = a; dst[1] = b;                               // shared memory, so no CTA has to outlive a peer's reads
+        }
     }
-    cluster.sync();                                               // every CTA's (min, max) is published
+    cluster.sync();                                               // every CTA's (min, max) has landed everywhere
+    t_dbg[3] = clock64();
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
 #pragma unroll
-    for (int p = 0; p < LNQ_CS; ++p) {
-        const float* peer = cluster.map_shared_rank(cta_mm, p);
-        mn = fminf(mn, peer[0]); mx = fmaxf(mx, peer[1]);
-    }
+    for (int p = 0; p < LNQ_CS; ++p) { mn = fminf(mn, peer_mm[p][0]); mx = fmaxf(mx, peer_mm[p][1]); }
     if (keys_out && rank == 0 && threadIdx.x == 0) {              // diagnostics / tests: slot 0 of the clip's key set
         keys_out[(size_t)clip * LB_MM_SLOTS * 2] = lb_fkey(mn); keys_out[(size_t)clip * LB_MM_SLOTS * 2 + 1] = lb_fkey(mx);
     }
@@ -409,33 +415,45 @@ ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ g
         sum = lb_warp_sum_i(sum);
         if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
     }
-    cluster.sync();                                               // peers may still be reading cta_mm
+    t_dbg[4] = clock64();
+    if (dbg && threadIdx.x == 0 && (blockIdx.y == 3 || blockIdx.y == 40) && blockIdx.x < 2)
+        printf("LNQDBG blk (%d,%d) start %lld | setup %lld rows %lld xchg %lld quant %lld end %lld\n", blockIdx.x, blockIdx.y, t_dbg[0] % 100000000ll, t_dbg[1] - t_dbg[0],
+               t_dbg[2] - t_dbg[0], t_dbg[3] - t_dbg[0], t_dbg[4] - t_dbg[0], clock64() - t_dbg[0]);
 }
 
+static int lnq_cluster_size() {
+    static int cs = 0;
+    if (!cs) { const char* e = getenv("LELE_B200_LNQ_CS"); cs = (e && e[0] == '4') ? 4 : 8; }
+    return cs;
+}
 bool lb_layer_norm_quantize_cluster_supported(int n, int T) {
-    return n == 512 && T >= 1 && (T + LNQ_CS - 1) / LNQ_CS <= 100;   // 100 rows x 2 KB = 200 KB of shared memory, <= LNQ_MAX_CHUNKS chunks
+    return n == 512 && T >= 1 && (T + lnq_cluster_size() - 1) / lnq_cluster_size() <= 100;   // 100 rows x 2 KB = 200 KB of shared memory, <= LNQ_MAX_CHUNKS chunks
 }
 // x [clips*T, 512] -> u8 rows + row sums + per-row (scale, zp); one launch, x read once
 int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, int clips, int T, float eps,
                                    uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp, unsigned* keys_out) {
     LB_REQUIRE(lb_layer_norm_quantize_cluster_supported(512, T) && gamma && beta, "layer_norm_quantize_cluster: unsupported shape");
     if (clips == 0) return LELE_B200_OK;
-    const size_t smem = (size_t)((T + LNQ_CS - 1) / LNQ_CS) * 512 * 4;
+    const int CS = lnq_cluster_size();
+    static const int dbg = getenv("LELE_B200_LNQ_DBG") ? 1 : 0;
+    const size_t smem = (size_t)((T + CS - 1) / CS) * 512 * 4;
     static thread_local size_t smem_set = 0;
     if (smem > smem_set) {
-        LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_kernel<4, 24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_kernel<8, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(LNQ_CS, clips, 1);
-    cfg.blockDim = dim3(LNQ_WARPS * 32, 1, 1);
+    cfg.gridDim = dim3(CS, clips, 1);
+    cfg.blockDim = dim3((CS == 4 ? 24 : 8) * 32, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = LNQ_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_quant_cluster_kernel, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out));
+    if (CS == 4) LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_quant_cluster_kernel<4, 24, 1>, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
+    else LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_quant_cluster_kernel<8, 8, 3>, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -44,10 +44,13 @@ enum { SV_L_LN1_G = 0, SV_L_LN1_B, SV_L_QKV_W, SV_L_QKV_SCALE, SV_L_QKV_BIAS, SV
        SV_L_FFN2_SCALE, SV_L_FFN2_BIAS, SV_L_FFN2_ZP, SV_NUM_LAYER };
 
 enum ProfClass { P_FRONTEND = 0, P_CMVN, P_PREP, P_LAYERNORM, P_QUANTIZE, P_GEMM_I8, P_FSMN, P_ATTN_QK, P_SOFTMAX, P_ATTN_PV,
-                 P_MINMAX, P_ARGMAX, P_MISC, P_ATTN_TC, P_NUM };
+                 P_MINMAX, P_ARGMAX, P_MISC, P_ATTN_TC,
+                 // per-site split of P_GEMM_I8 (also accumulated into it)
+                 P_G_QKV, P_G_OUT, P_G_FFN1_MAX, P_G_FFN1, P_G_FFN2, P_G_CTC, P_NUM };
 const char* kProfNames[P_NUM] = {"frontend_fbank_lfr", "cmvn", "prompt_scale_pos", "layer_norm", "quantize_rows", "gemm_i8_tcgen05",
                                  "fsmn_dwconv", "attn_qk_sgemm", "softmax", "attn_pv_sgemm", "slice_minmax", "argmax", "misc",
-                                 "attn_tcgen05_tf32x3"};
+                                 "attn_tcgen05_tf32x3",
+                                 "gemm_i8:qkv", "gemm_i8:out_proj", "gemm_i8:ffn1_max_pass", "gemm_i8:ffn1", "gemm_i8:ffn2", "gemm_i8:ctc"};
 
 // x0[b, r, :] = (r < 4 ? embed[id_r] : feats[b, r-4]) * sqrt(d) + pos[r]
 __global__ void prompt_scale_pos_kernel(const float* __restrict__ feats, const float* __restrict__ embed, const float* __restrict__ pos,
@@ -168,7 +171,9 @@ struct lele_b200_sensevoice {
     unsigned* keys = nullptr;
     unsigned long long* amax_keys = nullptr;
     void* qscratch = nullptr;
+    void* qscratch2 = nullptr;        // second quantised-operand set: FFN1's fused output quantiser writes it while reading the first
     void* attn_scratch = nullptr;
+    int ffn_twopass = 1;              // FFN1 as max-only pass + quantising pass (no f32 [M, ffn] round trip); LELE_B200_FFN_TWOPASS=0 disables
     int fuse_lnq = 1;                 // LayerNorm + quantiser fused for the encoder width (LELE_B200_FUSE_LNQ=0 disables)
     int attn_simt = 0;   // LELE_B200_ATTN_SIMT=1: CUDA-core attention (cross-check of the tcgen05 path)
     // profiling
@@ -212,33 +217,33 @@ struct ProfScope {
 // quantise the activation rows (per-clip keys already hold min/max) then the tcgen05 GEMM;
 // profiled as two classes so the GEMM's own duration feeds the roofline.
 int sv_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const unsigned* keys, long long M, int T,
-              const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep) {
+              const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep, int gcls) {
     SV_RUN(P_QUANTIZE, lb_quantize_rows(ctx, x, keys, M, T, w->k, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp));
     lb_fill_weight_fields(ep, w, qs);
-    SV_RUN(P_GEMM_I8, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+    SV_RUN(gcls, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
     return LELE_B200_OK;
 }
 
 // LayerNorm -> dynamic quantiser -> tcgen05 GEMM.  For the encoder width (512) the normalised f32 rows are never
 // materialised (norm.cu: statistics + min/max pass, then a re-deriving quantise pass); m->h holds the row statistics.
 int sv_ln_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const float* gamma, const float* beta, int n, unsigned* keys,
-                 long long M, int T, const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep) {
+                 long long M, int T, const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep, int gcls) {
     if (m->fuse_lnq == 1 && lb_layer_norm_quantize_cluster_supported(n, T) && M % T == 0) {
         // one cluster per clip: x read once, normalised rows live in shared memory until the clip's min/max is known
         SV_RUN(P_LAYERNORM, lb_layer_norm_quantize_cluster(ctx, x, gamma, beta, (int)(M / T), T, 1e-5f, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp, keys));
         lb_fill_weight_fields(ep, w, qs);
-        SV_RUN(P_GEMM_I8, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+        SV_RUN(gcls, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
         return LELE_B200_OK;
     }
     if (m->fuse_lnq && lb_layer_norm_quantize_supported(n, T)) {
         SV_RUN(P_LAYERNORM, lb_layer_norm_stats(ctx, x, gamma, beta, M, n, 1e-5f, m->h, keys, T));
         SV_RUN(P_QUANTIZE, lb_layer_norm_quantize(ctx, x, gamma, beta, M, n, m->h, keys, T, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp));
         lb_fill_weight_fields(ep, w, qs);
-        SV_RUN(P_GEMM_I8, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+        SV_RUN(gcls, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
         return LELE_B200_OK;
     }
     SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, x, gamma, beta, M, n, 1e-5f, m->h, keys, T));
-    return sv_linear(ctx, m, m->h, keys, M, T, w, qs, ep);
+    return sv_linear(ctx, m, m->h, keys, M, T, w, qs, ep, gcls);
 }
 
 int sv_alloc(void** p, size_t bytes) {
@@ -308,6 +313,8 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1));
     if (!rc) rc = sv_alloc((void**)&m->amax_keys, sizeof(unsigned long long) * M);
     if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax));
+    if (!rc) rc = sv_alloc(&m->qscratch2, lb_quant_scratch_bytes((long long)M, kmax));
+    { const char* e = getenv("LELE_B200_FFN_TWOPASS"); m->ffn_twopass = (e && e[0] == '0') ? 0 : 1; }
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("LELE_B200_GRAPH"); m->use_graph = (e && e[0] == '0') ? 0 : 1; }
@@ -326,7 +333,7 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (auto* q : m->lin) lele_b200_qweights_destroy(nullptr, q);
     void* bufs[] = {m->lfr, m->feats, m->x0, m->x, m->h, m->qkv, m->qs, m->fsmn, m->att, m->f1, m->scores, m->keys, m->amax_keys,
-                    m->qscratch, m->pcm_stage, m->ids_stage, m->attn_scratch};
+                    m->qscratch, m->qscratch2, m->pcm_stage, m->ids_stage, m->attn_scratch};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : m->ev_pool) cudaEventDestroy(e);
     if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
@@ -354,6 +361,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     SV_RUN(P_MISC, lb_minmax_init(ctx, m->keys, n_sites * B));
     auto site = [&](int s) { return m->keys + (size_t)2 * LB_MM_SLOTS * B * s; };
     const LbQuantScratch qs = lb_quant_scratch_carve(m->qscratch, M, ffn > din ? ffn : din);
+    const LbQuantScratch qs2 = lb_quant_scratch_carve(m->qscratch2, M, ffn > din ? ffn : din);
 
     {   // gather(embed, prompt ids) ++ concat ++ mul sqrt(d) ++ add pos
         ProfScope ps(m, ctx, P_PREP);
@@ -377,7 +385,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
                 attn_ops_ready = 1;
             } else attn_ops_ready = 0;
             int rc_ = sv_ln_linear(ctx, m, xin, (const float*)m->lt(l, SV_L_LN1_G), (const float*)m->lt(l, SV_L_LN1_B), cur, site(l * 4 + 0), M, T,
-                                   m->lin[l * 4 + 0], qs, ep);
+                                   m->lin[l * 4 + 0], qs, ep, P_G_QKV);
             if (rc_) return rc_;
         }
         const bool fork = !m->profiling && m->side != nullptr;
@@ -426,23 +434,45 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->x; ep.rows_per_slice = T; ep.add1 = m->fsmn; ep.add2 = (cur == d) ? xin : nullptr;   // x = x + (lin + fsmn)
-            SV_LINEAR(ctx, m,m->att, site(l * 4 + 1), M, T, m->lin[l * 4 + 1], qs, ep);
+            SV_LINEAR(ctx, m,m->att, site(l * 4 + 1), M, T, m->lin[l * 4 + 1], qs, ep, P_G_OUT);
         }
         xin = m->x; cur = d;
         // ---- feed-forward block ----
-        {
+        const lele_b200_qweights* w1 = m->lin[l * 4 + 2];
+        const bool twopass = m->ffn_twopass && T >= 32 && w1->n % 32 == 0 && w1->k % 16 == 0 && !getenv("LELE_B200_FORCE_SIMT");
+        if (twopass) {
+            // FFN1 twice over the same quantised LN output: pass 1 reduces only the per-clip max of the ReLU output (nothing is
+            // written), pass 2 recomputes the tile and quantises it in the epilogue -> the [M, ffn] f32 tensor of the reference
+            // (and its quantiser pass) never exists; FFN2 consumes the u8 operand directly.
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
-            ep.out = m->f1; ep.rows_per_slice = T; ep.relu = 1;
-            ep.minmax_keys = T >= 32 ? site(l * 4 + 3) : nullptr;     // fused per-clip min/max of the ReLU output
-            int rc_ = sv_ln_linear(ctx, m, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), d, site(l * 4 + 2), M, T,
-                                   m->lin[l * 4 + 2], qs, ep);
+            ep.rows_per_slice = T; ep.relu = 1; ep.minmax_keys = site(l * 4 + 3); ep.q_rowsum = qs2.rowsum;
+            int rc_ = sv_ln_linear(ctx, m, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), d, site(l * 4 + 2), M, T, w1, qs, ep, P_G_FFN1_MAX);
             if (rc_) return rc_;
-            if (T < 32) SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->f1, B, (long long)T * ffn, site(l * 4 + 3)));   // very short clips
-        }
-        {
-            LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
-            ep.out = m->x; ep.rows_per_slice = T; ep.add2 = m->x;                                          // x = x + ffn
-            SV_LINEAR(ctx, m,m->f1, site(l * 4 + 3), M, T, m->lin[l * 4 + 3], qs, ep);
+            LbI8Epilogue e2; memset(&e2, 0, sizeof(e2));
+            e2.rows_per_slice = T; e2.relu = 1; e2.q_out = qs2.a_u8; e2.q_rowsum = qs2.rowsum; e2.q_row_scale = qs2.row_scale; e2.q_row_zp = qs2.row_zp;
+            e2.q_keys = site(l * 4 + 3);
+            lb_fill_weight_fields(e2, w1, qs);
+            SV_RUN(P_G_FFN1, lb_gemm_i8(ctx, qs.a_u8, w1->wt, (int)M, w1->n, w1->k, e2));
+            LbI8Epilogue e3; memset(&e3, 0, sizeof(e3));
+            e3.out = m->x; e3.rows_per_slice = T; e3.add2 = m->x;                                          // x = x + ffn
+            const lele_b200_qweights* w2 = m->lin[l * 4 + 3];
+            lb_fill_weight_fields(e3, w2, qs2);
+            SV_RUN(P_G_FFN2, lb_gemm_i8(ctx, qs2.a_u8, w2->wt, (int)M, w2->n, w2->k, e3));
+        } else {
+            {
+                LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
+                ep.out = m->f1; ep.rows_per_slice = T; ep.relu = 1;
+                ep.minmax_keys = T >= 32 ? site(l * 4 + 3) : nullptr;     // fused per-clip min/max of the ReLU output
+                int rc_ = sv_ln_linear(ctx, m, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), d, site(l * 4 + 2), M, T,
+                                       m->lin[l * 4 + 2], qs, ep, P_G_FFN1);
+                if (rc_) return rc_;
+                if (T < 32) SV_RUN(P_MINMAX, lb_slice_minmax(ctx, m->f1, B, (long long)T * ffn, site(l * 4 + 3)));   // very short clips
+            }
+            {
+                LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
+                ep.out = m->x; ep.rows_per_slice = T; ep.add2 = m->x;                                          // x = x + ffn
+                SV_LINEAR(ctx, m,m->f1, site(l * 4 + 3), M, T, m->lin[l * 4 + 3], qs, ep, P_G_FFN2);
+            }
         }
         if (l == m->n_stage1 - 1) {   // after_norm (output replaces the residual stream)
             // in place for the register-resident row kernels (a warp holds its whole row before writing it back)
@@ -466,7 +496,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
         ep.out = logits_opt; ep.rows_per_slice = T; ep.argmax_keys = ids_dev ? m->amax_keys : nullptr;
         int rc_ = sv_ln_linear(ctx, m, xin, (const float*)m->tensor(SV_G_TP_G), (const float*)m->tensor(SV_G_TP_B), cur, site(ctc_site), M, T,
-                               m->lin[(size_t)m->n_layers * 4], qs, ep);
+                               m->lin[(size_t)m->n_layers * 4], qs, ep, P_G_CTC);
         if (rc_) return rc_;
     }
     if (ids_dev) SV_RUN(P_ARGMAX, lb_argmax_keys_to_ids(ctx, m->amax_keys, M, ids_dev));
@@ -477,7 +507,10 @@ static int sv_finish_profile(lele_b200_ctx* ctx, lele_b200_sensevoice* m) {
     if (!m->profiling) return LELE_B200_OK;
     LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < P_NUM; ++i) { m->prof_ms[i] = 0; m->prof_calls[i] = 0; }
-    for (auto& s : m->spans) { float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); m->prof_ms[s.cls] += ms; m->prof_calls[s.cls]++; }
+    for (auto& s : m->spans) {
+        float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); m->prof_ms[s.cls] += ms; m->prof_calls[s.cls]++;
+        if (s.cls >= P_G_QKV) { m->prof_ms[P_GEMM_I8] += ms; m->prof_calls[P_GEMM_I8]++; }
+    }
     m->spans.clear(); m->ev_used = 0;
     return LELE_B200_OK;
 }
