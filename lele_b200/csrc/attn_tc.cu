@@ -219,6 +219,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    lb_pdl_launch_dependents();
+    lb_pdl_wait();                 // PDL: the prologue above does not touch the projection's output
     if (warp == 0) ATT_DBG(0);
 
     if (warp == 0) {
@@ -548,7 +550,7 @@ int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, i
     a.dbg = getenv("LELE_B200_ATTN_DBG") ? 1 : 0;
     static thread_local bool attr_done = false;
     if (!attr_done) { LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_done = true; }
-    attn_tc_kernel<<<B * H * a.n_qtiles, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(mqh, mql, mkh, mkl, mvh, mvl, mout, a);
+    LB_CHECK_CUDA(lb_launch_pdl(attn_tc_kernel, dim3(B * H * a.n_qtiles), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, mqh, mql, mkh, mkl, mvh, mvl, mout, a));
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -71,6 +71,32 @@ int lb_scratch(lele_b200_ctx* ctx, size_t bytes, void** out);
 
 static inline int lb_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (PDL): the hot per-layer kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, call lb_pdl_launch_dependents() on entry and
+// lb_pdl_wait() after their data-independent prologue (barrier init, TMEM allocation, descriptor
+// prefetch, weight-side loads).  The next kernel's CTAs then become resident as this kernel's CTAs retire
+// and run their prologue under its tail instead of after a full drain + launch gap.  Every such kernel
+// executes the wait before touching activations, so completion order stays transitive along the stream.
+// LELE_B200_PDL=0 launches them plainly (the device-side instructions are no-ops then).
+bool lb_pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t lb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster_x > 1) { at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n; }
+    if (lb_pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    cfg.attrs = at; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void lb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void lb_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ----------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------

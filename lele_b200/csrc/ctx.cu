@@ -3,6 +3,7 @@
 // kernels/utils.rs:10 ensure_capacity, <Model>Workspace in src/compiler/mod.rs:1057-1092)
 // onto HBM: every workspace Vec / the weights blob gets a grow-only device mirror.
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 
 static thread_local char g_err[1024] = "";
@@ -125,6 +126,12 @@ extern "C" int lele_b200_arena_release(lele_b200_ctx* ctx, const void* host_base
         ctx->arena.erase(it);
     }
     return LELE_B200_OK;
+}
+
+bool lb_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LELE_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
 }
 
 int lb_scratch(lele_b200_ctx* ctx, size_t bytes, void** out) {

@@ -198,6 +198,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    // PDL: everything above is independent of the previous kernel's output; everything below reads it
+    lb_pdl_launch_dependents();
+    lb_pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -744,7 +747,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
             LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD, TM, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
             attr_done |= bit;                                                                                           \
         }                                                                                                               \
-        gemm_i8_tc_kernel<MD, TM, RL><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(ta, tb, tout, tlo, args);              \
+        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, ta, tb, tout, tlo, args)); \
     }
 #define LB_LAUNCH_MODE(MD, TM) LB_LAUNCH_MODE3(MD, TM, false)
 #define LB_LAUNCH_RELU(MD, TM) { if (ep.relu) LB_LAUNCH_MODE3(MD, TM, true) else LB_LAUNCH_MODE3(MD, TM, false) }

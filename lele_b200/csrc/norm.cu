@@ -326,6 +326,8 @@ ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ g
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    lb_pdl_launch_dependents();
+    lb_pdl_wait();                 // PDL: x is the previous kernel's output
     if (threadIdx.x == 0) {
         for (int c = 0; c < n_chunks; ++c) {
             const int rows = min(LNQ_CHUNK, n_rows - c * LNQ_CHUNK);
@@ -443,17 +445,8 @@ int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const flo
         LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_kernel<8, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(CS, clips, 1);
-    cfg.blockDim = dim3((CS == 4 ? 24 : 8) * 32, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (CS == 4) LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_quant_cluster_kernel<4, 24, 1>, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
-    else LB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ln_quant_cluster_kernel<8, 8, 3>, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
+    if (CS == 4) LB_CHECK_CUDA(lb_launch_pdl(ln_quant_cluster_kernel<4, 24, 1>, dim3(CS, clips, 1), dim3(24 * 32), smem, ctx->stream, CS, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
+    else LB_CHECK_CUDA(lb_launch_pdl(ln_quant_cluster_kernel<8, 8, 3>, dim3(CS, clips, 1), dim3(8 * 32), smem, ctx->stream, CS, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

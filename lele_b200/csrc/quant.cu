@@ -118,6 +118,8 @@ quantize_rows_reg_kernel(const float* __restrict__ x, const unsigned* __restrict
     constexpr int K = KV * 128;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    lb_pdl_launch_dependents();
+    lb_pdl_wait();
     if (row >= M) return;
     const float4* x4 = reinterpret_cast<const float4*>(x + row * K);
     float4 v[KV];
@@ -155,9 +157,9 @@ int lb_quantize_rows(lele_b200_ctx* ctx, const float* x, const unsigned* keys, l
                      uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp) {
     const bool al = ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)a_u8) & 3) == 0);
     if (al && K == 512)
-        quantize_rows_reg_kernel<4><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, a_u8, rowsum, row_scale, row_zp);
+        LB_CHECK_CUDA(lb_launch_pdl(quantize_rows_reg_kernel<4>, dim3(lb_ceil_div(M, 8)), dim3(256), 0, ctx->stream, 1, x, keys, M, rows_per_slice, a_u8, rowsum, row_scale, row_zp));
     else if (al && K == 2048)
-        quantize_rows_reg_kernel<16><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, a_u8, rowsum, row_scale, row_zp);
+        LB_CHECK_CUDA(lb_launch_pdl(quantize_rows_reg_kernel<16>, dim3(lb_ceil_div(M, 8)), dim3(256), 0, ctx->stream, 1, x, keys, M, rows_per_slice, a_u8, rowsum, row_scale, row_zp));
     else if (K % 8 == 0 && al)
         quantize_rows_kernel<true><<<lb_ceil_div(M, 8), 256, 0, ctx->stream>>>(x, keys, M, rows_per_slice, K, a_u8, rowsum, row_scale, row_zp);
     else
