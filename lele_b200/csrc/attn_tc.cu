@@ -13,8 +13,12 @@
 //   out = O / sum      + fused per-clip min/max (feeds the next dynamic quantiser)
 //
 // The [h,T,T] score / probability tensors never touch HBM (the reference materialises both).
-// A small pre-pass (attn_split_kernel) writes the tf32 hi/lo operand copies: q*scale, k ([M,d]) and
-// V^T ([B,H,dk,Tp], keys contiguous so it is a K-major B operand).
+// Operands: the tensor core reads the top 19 bits of a 32-bit operand (tf32 truncation), so the "hi" operand of
+// q, k and v is the raw f32 value; the "lo" residual x - trunc(x) is computed ON CHIP: TMA lands the raw tile in
+// shared memory and otherwise idle warps write the lo tile next to it (same swizzled layout, element-wise).  Only
+// one f32 copy of each operand crosses L2 -> SM (the kernel is bound by that fabric, not by the tensor pipe), and
+// no lo copy is ever written to HBM.  V is consumed as V^T ([B,H,dk,Tp], keys contiguous = K-major B operand),
+// written by the QKV projection's epilogue (gemm_i8_tc.cu EPI_QKV) or by attn_split_vt_kernel.
 //
 // Geometry: dk = 128, T <= 288 keys (SenseVoice: 271).  Other shapes use the CUDA-core path.
 #include "common.cuh"
@@ -123,9 +127,16 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sm
                  ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// lo = x - trunc_tf32(x) for one 16-byte chunk, shared -> shared
+__device__ __forceinline__ void lo_convert_16B(uint32_t src, uint32_t dst) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src));
+    sts_v4f(dst, __fsub_rn(v.x, tf32_hi(v.x)), __fsub_rn(v.y, tf32_hi(v.y)), __fsub_rn(v.z, tf32_hi(v.z)), __fsub_rn(v.w, tf32_hi(v.w)));
+}
 
 struct AttnArgs {
     int B, T, H, n_qtiles, n_kchunks;
@@ -138,20 +149,11 @@ struct AttnArgs {
 #define ATT_DBG(idx) do { if (args.dbg && lane == 0) dbg_t[warp][idx] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------
-// pre-pass: tf32 hi/lo operand copies
+// pre-pass (only when the QKV projection did not already emit it): V^T
 // ------------------------------------------------------------------------------------------
+// V [T, dk] per (b,h) -> V^T [dk, Tp] (keys contiguous, zero padded)
 __global__ void __launch_bounds__(256)
-attn_split_qk_kernel(const float* __restrict__ qkv, long long M, int d, float* __restrict__ qk_lo) {
-    const long long total = M * 2 * d;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long r = i / (2 * d); int c = (int)(i - r * 2 * d);
-        const float x = qkv[r * 3 * d + c];                      // q (c < d) or k
-        qk_lo[i] = __fsub_rn(x, tf32_hi(x));
-    }
-}
-// V [T, dk] per (b,h) -> V^T [dk, Tp] (keys contiguous, zero padded), hi/lo
-__global__ void __launch_bounds__(256)
-attn_split_vt_kernel(const float* __restrict__ qkv, int T, int Tp, int d, int H, float* __restrict__ vt_hi, float* __restrict__ vt_lo) {
+attn_split_vt_kernel(const float* __restrict__ qkv, int T, int Tp, int d, int H, float* __restrict__ vt) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z / H, h = blockIdx.z % H;
     const int t0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
@@ -164,9 +166,7 @@ attn_split_vt_kernel(const float* __restrict__ qkv, int T, int Tp, int d, int H,
     for (int j = ty; j < 32; j += 8) {
         int t = t0 + tx;
         if (t < Tp) {
-            float v = tile[tx][j], vh = tf32_hi(v);
-            long long o = (((long long)b * H + h) * DK + e0 + j) * Tp + t;
-            vt_hi[o] = vh; vt_lo[o] = __fsub_rn(v, vh);
+            vt[(((long long)b * H + h) * DK + e0 + j) * Tp + t] = tile[tx][j];
         }
     }
 }
@@ -175,10 +175,8 @@ attn_split_vt_kernel(const float* __restrict__ qkv, int T, int Tp, int d, int H,
 // fused attention
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
-               const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl,
-               const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
-               const __grid_constant__ CUtensorMap map_out, const AttnArgs args) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_kh,
+               const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_out, const AttnArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + SMEM_MAIN);
@@ -191,7 +189,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     uint64_t* p_full = v_full + MAX_KCHUNKS;  // [MAX_KCHUNKS] P chunk written by the softmax warps
     uint64_t* pv_done = p_full + MAX_KCHUNKS; // [MAX_KCHUNKS] MMA consumed the chunk (its ring stage is free again)
     uint64_t* o_full = pv_done + MAX_KCHUNKS; // O complete
-    uint32_t* tmem_base_smem = (uint32_t*)(o_full + 1);
+    uint64_t* conv_a = o_full + 1;            // [2] phase-A lo tiles written (16 converter warps) -> MMA
+    uint64_t* vl_full = conv_a + 2;           // [MAX_KCHUNKS] V lo chunk written (warps 2, 3) -> MMA
+    uint32_t* tmem_base_smem = (uint32_t*)(vl_full + MAX_KCHUNKS);
     float* xch = (float*)(smem + SMEM_MAIN + BAR_BYTES);    // [2][NGRP][128] partial row max / row sums of the softmax groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,12 +202,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     const int T = args.T, NKC = args.n_kchunks;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&map_qh); prefetch_tmap(&map_ql); prefetch_tmap(&map_kh); prefetch_tmap(&map_kl); prefetch_tmap(&map_vh); prefetch_tmap(&map_vl);
+        prefetch_tmap(&map_qh); prefetch_tmap(&map_kh); prefetch_tmap(&map_vh); prefetch_tmap(&map_out);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); mbar_init(&conv_a[s], NGRP * 4); }
         mbar_init(s_full, 1); mbar_init(o_full, 1);
-        for (int c = 0; c < MAX_KCHUNKS; ++c) { mbar_init(&v_full[c], 1); mbar_init(&p_full[c], 4); mbar_init(&pv_done[c], 1); }
+        for (int c = 0; c < MAX_KCHUNKS; ++c) { mbar_init(&v_full[c], 1); mbar_init(&p_full[c], 4); mbar_init(&pv_done[c], 1); mbar_init(&vl_full[c], 2); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -231,23 +231,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 const int s = kc & 1; const uint32_t ph = (kc >> 1) & 1;
                 mbar_wait(&empty_a[s], ph ^ 1);
                 uint8_t* st = smem + s * STAGE_A;
-                mbar_expect_tx(&full_a[s], STAGE_A);
+                mbar_expect_tx(&full_a[s], TILE_Q + TILE_K);     // raw (= hi) tiles only; the lo tiles are made on chip
                 tma_load_4d(st, &map_qh, &full_a[s], kc * KC, h, qt * AQ, b);
-                tma_load_4d(st + TILE_Q, &map_ql, &full_a[s], kc * KC, h, qt * AQ, b);
                 tma_load_4d(st + 2 * TILE_Q, &map_kh, &full_a[s], kc * KC, h, 0, b);
                 tma_load_4d(st + 2 * TILE_Q + NH * 128, &map_kh, &full_a[s], kc * KC, h, NH, b);
-                tma_load_4d(st + 2 * TILE_Q + TILE_K, &map_kl, &full_a[s], kc * KC, h, 0, b);
-                tma_load_4d(st + 2 * TILE_Q + TILE_K + NH * 128, &map_kl, &full_a[s], kc * KC, h, NH, b);
             }
-            // phase C reuses the same shared memory: wait until every phase-A MMA has retired
-            mbar_wait(s_full, 0);
+            // phase C reuses the same shared memory.  V chunk 0 lands in [32 KB, 64 KB) = the K tile of phase-A stage 0,
+            // which is free once the MMAs of k-chunk 2 retired (second completion of empty_a[0]): it is fetched (and its
+            // lo tile made) under the last k-chunk's MMAs; everything else waits until every phase-A MMA has retired.
             for (int c = 0; c < NKC; ++c) {
                 const int s = c % NSTAGE_C;
+                if (c == 0) mbar_wait(&empty_a[0], 1);
+                if (c == 1) mbar_wait(s_full, 0);
                 if (c >= NSTAGE_C) mbar_wait(&pv_done[c - NSTAGE_C], 0);
                 uint8_t* st = smem + s * STAGE_C;
-                mbar_expect_tx(&v_full[c], 2 * TILE_V);
+                mbar_expect_tx(&v_full[c], TILE_V);
                 tma_load_4d(st + 2 * TILE_P, &map_vh, &v_full[c], c * KC, 0, h, b);
-                tma_load_4d(st + 2 * TILE_P + TILE_V, &map_vl, &v_full[c], c * KC, 0, h, b);
             }
         }
     } else if (warp == 1) {
@@ -256,7 +255,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             constexpr uint32_t ID_S = idesc_tf32(NH), ID_O = idesc_tf32(DK);
             for (int kc = 0; kc < DK / KC; ++kc) {
                 const int s = kc & 1; const uint32_t ph = (kc >> 1) & 1;
-                mbar_wait(&full_a[s], ph);
+                mbar_wait(&full_a[s], ph);                       // raw tiles landed: the hi*hi products can start
                 tc_fence_after();
                 if (kc == 0) ATT_DBG(1);
                 if (kc == 3) ATT_DBG(2);
@@ -270,8 +269,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {       // 8 floats (32 B) per MMA: +2 in the >>4 address field
                         const uint64_t ko = (uint64_t)(k * 2);
-                        const uint32_t first = (kc == 0 && k == 0) ? 0u : 1u;
-                        umma_tf32(dS, qh + ko, kh + hoff + ko, ID_S, first);
+                        umma_tf32(dS, qh + ko, kh + hoff + ko, ID_S, (kc == 0 && k == 0) ? 0u : 1u);
+                    }
+                }
+                mbar_wait(&conv_a[s], ph);                       // ... the lo tiles are written (converter warps): cross terms
+                tc_fence_after();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t dS = tmem_base + (uint32_t)(half * NH);
+                    const uint64_t hoff = (uint64_t)((half * NH * 128) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
                         umma_tf32(dS, qh + ko, kl + hoff + ko, ID_S, 1u);
                         umma_tf32(dS, ql + ko, kh + hoff + ko, ID_S, 1u);
                     }
@@ -281,7 +290,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             }
             for (int c = 0; c < NKC; ++c) {
                 const int s = c % NSTAGE_C;
-                mbar_wait(&v_full[c], 0);
+                mbar_wait(&vl_full[c], 0);                       // V chunk landed and its lo tile is written
                 mbar_wait(&p_full[c], 0);
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + s * STAGE_C);
@@ -299,7 +308,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 if (c == NKC - 1) umma_commit(o_full);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
+        // ===================== warps 2, 3: lo(V^T) chunks, 64 threads x 16 float4 per 16 KB chunk =====================
+        const int t64 = (warp - 2) * 32 + lane;
+        for (int c = 0; c < NKC; ++c) {
+            const int s = c % NSTAGE_C;
+            mbar_wait(&v_full[c], 0);
+            const uint32_t vh = smem_u32(smem + s * STAGE_C + 2 * TILE_P);
+#pragma unroll 4
+            for (int i = t64; i < TILE_V / 16; i += 64) lo_convert_16B(vh + (uint32_t)i * 16u, vh + (uint32_t)TILE_V + (uint32_t)i * 16u);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&vl_full[c]);
+        }
+    } else {
         // ===================== softmax + epilogue: 16 warps, four threads per query row =====================
         // group g (warps 4+4g .. 7+4g) owns the 32-key chunks g, g+4, g+8: partial row max / row sum per group,
         // exchanged through shared memory (named barrier over the 512 softmax threads).
@@ -307,6 +329,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         const int grp = (warp - 4) >> 2;
         const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+        // ---- phase A: these warps are idle until S is complete, so they produce the lo(q), lo(k) tiles:
+        //      3328 float4 per 32-dim chunk over 512 threads; same offsets in the lo tile (the swizzle is positional) ----
+        {
+            const int t512 = threadIdx.x - 128;
+            for (int kc = 0; kc < DK / KC; ++kc) {
+                const int s = kc & 1; const uint32_t ph = (kc >> 1) & 1;
+                mbar_wait(&full_a[s], ph);
+                const uint32_t st = smem_u32(smem + s * STAGE_A);
+#pragma unroll
+                for (int i = t512; i < TILE_Q / 16; i += 512) lo_convert_16B(st + (uint32_t)i * 16u, st + (uint32_t)TILE_Q + (uint32_t)i * 16u);
+#pragma unroll
+                for (int i = t512; i < TILE_K / 16; i += 512)
+                    lo_convert_16B(st + 2u * TILE_Q + (uint32_t)i * 16u, st + 2u * TILE_Q + (uint32_t)TILE_K + (uint32_t)i * 16u);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv_a[s]);
+            }
+        }
         mbar_wait(s_full, 0);
         tc_fence_after();
         ATT_DBG(3);
@@ -395,15 +435,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                tma_store_3d(&map_out, stg, h * DK + grp * 32, row0, b);
-                tma_store_wait_all();
-            }
+            if (lane == 0) tma_store_3d(&map_out, stg, h * DK + grp * 32, row0, b);
             if (args.minmax_keys) {
                 const bool ok = row0 + lane < T;
                 mn = lb_warp_min(ok ? mn : 3.402823466e+38f); mxo = lb_warp_max(ok ? mxo : -3.402823466e+38f);
                 if (lane == 0) lb_mm_update(args.minmax_keys, b, mn, mxo);
             }
+            if (lane == 0) tma_store_wait_read();          // the staging tile must outlive the bulk store's READ only
         }
         ATT_DBG(7);
     }
@@ -484,62 +522,49 @@ int make_map_f32_out3d(CUtensorMap* map, const void* ptr, unsigned long long col
     ctx->tmaps.emplace(h, std::move(blob));
     return LELE_B200_OK;
 }
-int grid_for(long long total) { long long g = (total + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
 }  // namespace
 
 bool lb_attention_tc_supported(int T, int d, int H) { return H > 0 && d == H * DK && T >= 1 && T <= 2 * NH; }
 
 size_t lb_attention_tc_scratch_bytes(int B, int T, int d, int H) {
     const size_t Tp = (size_t)((T + 3) / 4 * 4);
-    return sizeof(float) * (2 * (size_t)B * T * d + 2 * (size_t)B * H * DK * Tp) + 3 * 256;
+    (void)d;
+    return sizeof(float) * (size_t)B * H * DK * Tp + 256;
 }
 
-void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float** qk_lo, float** vt_hi, float** vt_lo, int* tp) {
-    const long long M = (long long)B * T;
-    const int Tp = (T + 3) / 4 * 4;
-    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    uint8_t* p = (uint8_t*)scratch;
-    *qk_lo = (float*)p; p += al(sizeof(float) * M * 2 * d);
-    *vt_hi = (float*)p; p += al(sizeof(float) * (size_t)B * H * DK * Tp);
-    *vt_lo = (float*)p;
-    *tp = Tp;
+void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float** vt, int* tp) {
+    (void)B; (void)d; (void)H;
+    *vt = (float*)scratch;
+    *tp = (T + 3) / 4 * 4;
 }
 
 // qkv [B*T, 3d] -> att [B*T, d]; optional fused per-clip min/max keys [B][2].
-// operands_ready != 0: the QKV projection's epilogue already wrote lo(q), lo(k), V^T hi/lo into `scratch`
-// (gemm_i8_tc.cu EPI_QKV); otherwise the split pre-pass runs here.
+// operands_ready != 0: the QKV projection's epilogue already wrote V^T into `scratch`
+// (gemm_i8_tc.cu EPI_QKV); otherwise the transposing pre-pass runs here.
 int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, int H, float qscale, void* scratch, float* att,
                     unsigned* minmax_keys, int operands_ready) {
     LB_REQUIRE(lb_attention_tc_supported(T, d, H), "attention_tc: unsupported geometry T=%d d=%d H=%d", T, d, H);
-    const long long M = (long long)B * T;
-    float *qk_lo, *vt_hi, *vt_lo; int Tp;
-    lb_attention_tc_operands(scratch, B, T, d, H, &qk_lo, &vt_hi, &vt_lo, &Tp);
+    float* vt; int Tp;
+    lb_attention_tc_operands(scratch, B, T, d, H, &vt, &Tp);
     if (!operands_ready) {
-        attn_split_qk_kernel<<<grid_for(M * 2 * d), 256, 0, ctx->stream>>>(qkv, M, d, qk_lo);
-        LB_LAUNCH_CHECK(ctx);
-        attn_split_vt_kernel<<<dim3(lb_ceil_div(Tp, 32), DK / 32, B * H), 256, 0, ctx->stream>>>(qkv, T, Tp, d, H, vt_hi, vt_lo);
+        attn_split_vt_kernel<<<dim3(lb_ceil_div(Tp, 32), DK / 32, B * H), 256, 0, ctx->stream>>>(qkv, T, Tp, d, H, vt);
         LB_LAUNCH_CHECK(ctx);
     }
 
-    // q/k hi = the raw f32 projections inside qkv (the tensor core reads the top 19 bits = tf32 truncation),
-    // lo from qk_lo: [B][T][H][DK] views -> dims (DK, H, T, B)
+    // q/k = the raw f32 projections inside qkv: [B][T][H][DK] views -> dims (DK, H, T, B)
     const unsigned long long dqk[4] = {(unsigned long long)DK, (unsigned long long)H, (unsigned long long)T, (unsigned long long)B};
     const unsigned long long sqh[3] = {(unsigned long long)DK * 4, (unsigned long long)3 * d * 4, (unsigned long long)T * 3 * d * 4};
-    const unsigned long long sql[3] = {(unsigned long long)DK * 4, (unsigned long long)2 * d * 4, (unsigned long long)T * 2 * d * 4};
     const unsigned bq[4] = {KC, 1, AQ, 1}, bk[4] = {KC, 1, NH, 1};
     // v^T: [B][H][DK][Tp] -> dims (Tp, DK, H, B)
     const unsigned long long dv[4] = {(unsigned long long)Tp, (unsigned long long)DK, (unsigned long long)H, (unsigned long long)B};
     const unsigned long long sv[3] = {(unsigned long long)Tp * 4, (unsigned long long)DK * Tp * 4, (unsigned long long)H * DK * Tp * 4};
     const unsigned bv[4] = {KC, DK, 1, 1};
-    CUtensorMap mqh, mql, mkh, mkl, mvh, mvl;
+    CUtensorMap mqh, mkh, mvh;
     int rc;
     g_ctx_for_maps = ctx;
     if ((rc = make_map_f32_4d(&mqh, qkv, dqk, sqh, bq))) return rc;
-    if ((rc = make_map_f32_4d(&mql, qk_lo, dqk, sql, bq))) return rc;
     if ((rc = make_map_f32_4d(&mkh, qkv + d, dqk, sqh, bk))) return rc;
-    if ((rc = make_map_f32_4d(&mkl, qk_lo + d, dqk, sql, bk))) return rc;
-    if ((rc = make_map_f32_4d(&mvh, vt_hi, dv, sv, bv))) return rc;
-    if ((rc = make_map_f32_4d(&mvl, vt_lo, dv, sv, bv))) return rc;
+    if ((rc = make_map_f32_4d(&mvh, vt, dv, sv, bv))) return rc;
     // att [B][T][H*DK] -> dims (H*DK, T, B), box 32 x 32 x 1 (one epilogue warp's sub-tile); rows >= T are clipped
     CUtensorMap mout;
     if ((rc = make_map_f32_out3d(&mout, att, (unsigned long long)H * DK, (unsigned long long)T, (unsigned long long)B))) return rc;
@@ -550,7 +575,7 @@ int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, i
     a.dbg = getenv("LELE_B200_ATTN_DBG") ? 1 : 0;
     static thread_local bool attr_done = false;
     if (!attr_done) { LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_done = true; }
-    LB_CHECK_CUDA(lb_launch_pdl(attn_tc_kernel, dim3(B * H * a.n_qtiles), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, mqh, mql, mkh, mkl, mvh, mvl, mout, a));
+    LB_CHECK_CUDA(lb_launch_pdl(attn_tc_kernel, dim3(B * H * a.n_qtiles), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, mqh, mkh, mvh, mout, a));
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -79,6 +79,7 @@ static inline int lb_ceil_div(long long a, long long b) { return (int)((a + b - 
 // executes the wait before touching activations, so completion order stays transitive along the stream.
 // LELE_B200_PDL=0 launches them plainly (the device-side instructions are no-ops then).
 bool lb_pdl_enabled();
+bool lb_env_flag(const char* name, int dflt);   // "0" -> false, anything else -> true, unset -> dflt
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t lb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,

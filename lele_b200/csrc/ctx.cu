@@ -128,6 +128,12 @@ extern "C" int lele_b200_arena_release(lele_b200_ctx* ctx, const void* host_base
     return LELE_B200_OK;
 }
 
+bool lb_env_flag(const char* name, int dflt) {
+    const char* e = getenv(name);
+    if (!e || !e[0]) return dflt != 0;
+    return e[0] != '0';
+}
+
 bool lb_pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("LELE_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }

@@ -35,6 +35,19 @@ constexpr int EPI_TILE_BYTES = 32 * 128;                       // per-warp 32x32
 constexpr int EPI_META_BYTES = 3 * 64 * 4;                     // zp*colsum / scale / bias of the warp's 64 columns
 constexpr int EPI_BYTES = NUM_EPI_WARPS * (EPI_TILE_BYTES + EPI_META_BYTES);
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// RESB ("resident B") variant, K <= 4 k-blocks (K <= 512) and an epilogue that needs <= 1 KB of staging per warp (the
+// fused output quantiser, the max-only pass): a CTA keeps ONE n-block for its whole life, loads that 256 x K weight
+// tile once (128 KB stays in shared memory) and streams only A (16 KB per k-block, 4-stage ring = one full tile of
+// look-ahead): 64 KB instead of 192 KB of operand traffic per tile.  MEASURED (B200, FFN1 passes, M=17600): no gain
+// (37.3 vs 35.6 us) -- these GEMMs are bound by the epilogue (per-tile ~5.3 k cycles vs ~3.4 k for the MMAs), not by
+// the L2 -> SM operand fabric.  Kept as an opt-in (LELE_B200_GEMM_RESB=1) since it is bit-identical and tested.
+constexpr int RES_KB = 4;                                      // resident k-blocks of B
+constexpr int RES_A_STAGES = 4;
+constexpr int RES_EPI_TILE_BYTES = 1024;
+constexpr int RES_EPI_BYTES = NUM_EPI_WARPS * (RES_EPI_TILE_BYTES + EPI_META_BYTES);
+constexpr int RES_SMEM_BYTES = RES_KB * B_STAGE_BYTES + RES_A_STAGES * A_STAGE_BYTES + RES_EPI_BYTES + 1024 + 256;
+static_assert(SMEM_BYTES <= 232448 && RES_SMEM_BYTES <= 232448, "shared memory budget");
+constexpr int MAX_STAGES = STAGES > RES_A_STAGES ? STAGES : RES_A_STAGES;
 #ifdef LELE_B200_GEMM_TIMELINE
 constexpr bool GEMM_DBG = true;    // role wait counters (clock64) printed by CTAs 0 / 77 when LELE_B200_GEMM_DBG=1; costs ~12 registers
 #else
@@ -161,7 +174,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // RELU (compile-time; PLAIN / MINMAX / QUANT only): the per-element epilogue is bound by the half-rate ALU pipe (IADD3,
 // I2FP, FMNMX ...), so a ReLU that is not asked for -- or is implied (QUANT: unsigned saturation; MINMAX: max(relu(t)) =
 // max(max t, 0), min(relu(t)) >= 0) -- must not cost an FMNMX per element.
-template <int MODE, bool TMA_OUT, bool RELU>
+template <int MODE, bool TMA_OUT, bool RELU, bool RESB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_lo, const KernelArgs args) {
@@ -170,23 +183,30 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (GEMM_DBG && args.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;   // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem = smem_raw + pad;
+    constexpr int NST = RESB ? RES_A_STAGES : STAGES;                      // A (RESB) or A+B (ring) stages
+    constexpr int ETB = RESB ? RES_EPI_TILE_BYTES : EPI_TILE_BYTES;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* epi_base = smem + STAGES * STAGE_BYTES;                       // per-warp staging tiles, then column metadata
-    uint64_t* bars = (uint64_t*)(epi_base + EPI_BYTES);
-    uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
-    uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
-    uint64_t* tmem_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
-    uint64_t* tmem_empty = tmem_full + 2;      // [2]       epilogue -> MMA
-    uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+    uint8_t* smem_b = smem + NST * A_STAGE_BYTES;                          // RESB: the RES_KB resident k-block tiles of B
+    uint8_t* epi_base = smem_b + (RESB ? RES_KB : STAGES) * B_STAGE_BYTES; // per-warp staging tiles, then column metadata
+    uint64_t* bars = (uint64_t*)(epi_base + (RESB ? RES_EPI_BYTES : EPI_BYTES));
+    uint64_t* full_bar = bars;                     // [NST]  TMA -> MMA
+    uint64_t* empty_bar = bars + MAX_STAGES;       // [NST]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * MAX_STAGES;   // [2]    MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]    epilogue -> MMA
+    uint64_t* b_full = tmem_empty + 2;             // RESB: the resident weight tile landed
+    uint32_t* tmem_base_smem = (uint32_t*)(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = args.num_m_blocks * args.num_n_blocks;
+    // tile walk (both variants): tile = blockIdx.x + i * gridDim.x -> (m_blk, n_blk) = (tile / nnb, tile % nnb).
+    // RESB: the host launches gridDim.x as a multiple of nnb, so n_blk = blockIdx.x % nnb is the same for every tile of
+    // the CTA (its resident weight tile) and the CTA walks m-blocks blockIdx.x / nnb + i * gridDim.x / nnb.
 
-    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); if (MODE == EPI_QKV) prefetch_tmap(&tmap_lo); }
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
+        mbar_init(b_full, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -207,15 +227,21 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             long long w_empty = 0; const long long t_begin = clock64();
+            if (RESB && (int)blockIdx.x < num_tiles) {             // the CTA's weight tile: loaded once, resident
+                const int n_blk = (int)blockIdx.x % args.num_n_blocks;
+                mbar_expect_tx(b_full, (uint32_t)args.num_k_blocks * B_STAGE_BYTES);
+                for (int kb = 0; kb < args.num_k_blocks; ++kb)
+                    tma_load_2d(smem_b + kb * B_STAGE_BYTES, &tmap_b, b_full, kb * BK, n_blk * BN);
+            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
                 for (int kb = 0; kb < args.num_k_blocks; ++kb) {
                     if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t0; }
                     else mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[stage], RESB ? A_STAGE_BYTES : STAGE_BYTES);
                     tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (!RESB) tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
             if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77))
@@ -227,6 +253,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             long long w_tmem = 0, w_full = 0; const long long t_begin = clock64();
+            if (RESB && (int)blockIdx.x < num_tiles) { mbar_wait(b_full, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t0; }
                 else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
@@ -237,7 +264,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     else mbar_wait(&full_bar[stage], phase);            // TMA bytes landed
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (RESB ? kb : stage) * B_STAGE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance along K inside the 128B swizzle atom: +32 B == +2 in the (>>4) address field
@@ -246,7 +273,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     umma_commit(&empty_bar[stage]);                // frees the smem slot when the MMAs retire
                     if (kb == args.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -265,8 +292,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
         const int cgrp = ew >> 2;           // which 64-column group of the tile
         const LbI8Epilogue& ep = args.ep;
-        const uint32_t tile_s = smem_u32(epi_base) + (uint32_t)ew * EPI_TILE_BYTES;
-        const uint32_t meta_s = smem_u32(epi_base) + NUM_EPI_WARPS * EPI_TILE_BYTES + (uint32_t)ew * EPI_META_BYTES;   // zp*colsum[64] | scale[64] | bias[64]
+        const uint32_t tile_s = smem_u32(epi_base) + (uint32_t)ew * ETB;
+        const uint32_t meta_s = smem_u32(epi_base) + NUM_EPI_WARPS * ETB + (uint32_t)ew * EPI_META_BYTES;   // zp*colsum[64] | scale[64] | bias[64]
         const uint32_t my_row_s = tile_s + (uint32_t)lane * 128u;
         const uint32_t sw = (uint32_t)(lane & 7);
         const int N = args.N, M = args.M;
@@ -450,41 +477,20 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     __syncwarp();
                     if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, first_row);
                     if (MODE == EPI_QKV) {
-                        // tf32 operand preparation for the attention kernel; r[] holds the 32 finished f32 values of this row
+                        // operand preparation for the attention kernel: the v columns are also written transposed (V^T, keys
+                        // contiguous = the K-major B operand of P.V); r[] holds the 32 finished f32 values of this row.
+                        // (q / k are consumed straight out of `out`; every tf32 lo residual is computed on chip by attn_tc.cu.)
                         const int dmodel = N / 3;
-                        if (gcol0 < 2 * dmodel) {          // q / k columns: lo = x - trunc_tf32(x), second tensor store
-                            if (lane == 0) tma_store_wait_read();
-                            __syncwarp();
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                float lo[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float t = __uint_as_float(r[q * 4 + e]);
-                                    lo[e] = __fsub_rn(t, __uint_as_float(r[q * 4 + e] & 0xFFFFE000u));
-                                }
-                                sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
-                            }
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0) tma_store_2d(&tmap_lo, tile_s, gcol0, first_row);
-                        } else if (row_ok) {               // v columns: V^T, 32 consecutive keys (lanes) per store
+                        if (gcol0 >= 2 * dmodel && row_ok) {   // 32 consecutive keys (lanes) per store instruction
                             const int bb = row / rps, tt = row - bb * rps;
                             const int cv = gcol0 - 2 * dmodel;
-                            const size_t base = ((size_t)bb * (dmodel >> 7) * 128 + cv) * (size_t)ep.vt_tp + tt;
-                            float* vh = ep.vt_hi + base;
-                            float* vl = ep.vt_lo + base;
+                            float* vt = ep.vt + ((size_t)bb * (dmodel >> 7) * 128 + cv) * (size_t)ep.vt_tp + tt;
 #pragma unroll
-                            for (int idx = 0; idx < 32; ++idx) {
-                                const float t = __uint_as_float(r[idx]);
-                                const float hi = __uint_as_float(r[idx] & 0xFFFFE000u);
-                                vh[(size_t)idx * ep.vt_tp] = hi;
-                                vl[(size_t)idx * ep.vt_tp] = __fsub_rn(t, hi);
-                            }
+                            for (int idx = 0; idx < 32; ++idx) vt[(size_t)idx * ep.vt_tp] = __uint_as_float(r[idx]);
                             if (tt == rps - 1) {           // last key of the clip: zero the [T, Tp) padding of its V^T rows
                                 for (int pd = 1; pd <= ep.vt_tp - rps; ++pd)
 #pragma unroll
-                                    for (int idx = 0; idx < 32; ++idx) { vh[(size_t)idx * ep.vt_tp + pd] = 0.0f; vl[(size_t)idx * ep.vt_tp + pd] = 0.0f; }
+                                    for (int idx = 0; idx < 32; ++idx) vt[(size_t)idx * ep.vt_tp + pd] = 0.0f;
                             }
                         }
                     }
@@ -703,7 +709,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
     int mode = EPI_PLAIN;
     if (ep.q_out) mode = EPI_QUANT;
-    else if (ep.qk_lo) mode = EPI_QKV;
+    else if (ep.vt) mode = EPI_QKV;
     else if (ep.argmax_keys) mode = EPI_ARGMAX;
     else if (ep.minmax_keys) mode = EPI_MINMAX;
     else if (ep.add1 && ep.add2) mode = EPI_R12;
@@ -719,7 +725,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     }
     // residual-free epilogues whose rows are 16-byte aligned store through TMA (no per-element store phase)
     if (mode == EPI_QKV) {
-        LB_REQUIRE(N % 384 == 0 && ep.vt_hi && ep.vt_lo && ep.rows_per_slice > 0 && ep.vt_tp >= ep.rows_per_slice && !ep.add1 && !ep.add2 &&
+        LB_REQUIRE(N % 384 == 0 && ep.vt && ep.rows_per_slice > 0 && ep.vt_tp >= ep.rows_per_slice && !ep.add1 && !ep.add2 &&
                    !ep.minmax_keys && !ep.argmax_keys && !getenv("LELE_B200_GEMM_NO_TMA_STORE"),
                    "gemm_i8_tc: fused attention-operand epilogue needs N = 3 * heads * 128 and the V^T buffers");
     }
@@ -736,33 +742,44 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     }
     if (mode == EPI_QKV) {
         LB_REQUIRE(tma_out, "gemm_i8_tc: fused attention-operand epilogue needs a 16-byte aligned output");
-        rc = cached_tmap_out_f32(ctx, &tlo, ep.qk_lo, M, N / 3 * 2);
-        if (rc) return rc;
+    }
+    // resident-B variant (see RES_* above): small-K GEMMs whose epilogue needs no f32 staging tile
+    const bool resb = (mode == EPI_QUANT || (mode == EPI_MINMAX && !ep.out)) && args.num_k_blocks <= RES_KB &&
+                      args.num_n_blocks <= ctx->num_sms && lb_env_flag("LELE_B200_GEMM_RESB", 0);
+    if (resb) {   // grid = G * nnb: every CTA keeps one n-block (tile walk in the kernel)
+        int G = ctx->num_sms / args.num_n_blocks;
+        if (G > args.num_m_blocks) G = args.num_m_blocks;
+        grid = G * args.num_n_blocks;
     }
     static thread_local unsigned long long attr_done = 0;   // one process per GPU: the attribute is set once per instantiation
-#define LB_LAUNCH_MODE3(MD, TM, RL)                                                                                     \
+#define LB_LAUNCH_MODE4(MD, TM, RL, RB)                                                                                 \
     {                                                                                                                   \
-        const unsigned long long bit = 1ull << (MD * 4 + (TM ? 2 : 0) + (RL ? 1 : 0));                                              \
+        const unsigned long long bit = 1ull << (MD * 8 + (RB ? 4 : 0) + (TM ? 2 : 0) + (RL ? 1 : 0));                   \
+        const int smem_bytes = RB ? RES_SMEM_BYTES : SMEM_BYTES;                                                        \
         if (!(attr_done & bit)) {                                                                                       \
-            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD, TM, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD, TM, RL, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
             attr_done |= bit;                                                                                           \
         }                                                                                                               \
-        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, ta, tb, tout, tlo, args)); \
+        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, ctx->stream, 1, ta, tb, tout, tlo, args)); \
     }
+#define LB_LAUNCH_MODE3(MD, TM, RL) LB_LAUNCH_MODE4(MD, TM, RL, false)
+#define LB_LAUNCH_RESB(MD, TM) { if (ep.relu) LB_LAUNCH_MODE4(MD, TM, true, true) else LB_LAUNCH_MODE4(MD, TM, false, true) }
 #define LB_LAUNCH_MODE(MD, TM) LB_LAUNCH_MODE3(MD, TM, false)
 #define LB_LAUNCH_RELU(MD, TM) { if (ep.relu) LB_LAUNCH_MODE3(MD, TM, true) else LB_LAUNCH_MODE3(MD, TM, false) }
     switch (mode) {
         case EPI_PLAIN: if (tma_out) LB_LAUNCH_RELU(EPI_PLAIN, true) else LB_LAUNCH_RELU(EPI_PLAIN, false) break;
-        case EPI_MINMAX: if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
+        case EPI_MINMAX: if (resb) LB_LAUNCH_RESB(EPI_MINMAX, false) else if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
         case EPI_ARGMAX: LB_LAUNCH_MODE(EPI_ARGMAX, false) break;
         case EPI_R1: LB_LAUNCH_MODE(EPI_R1, false) break;
         case EPI_R2: LB_LAUNCH_MODE(EPI_R2, false) break;
         case EPI_R12: LB_LAUNCH_MODE(EPI_R12, false) break;
         case EPI_QKV: LB_LAUNCH_MODE(EPI_QKV, true) break;
-        case EPI_QUANT: LB_LAUNCH_RELU(EPI_QUANT, true) break;
+        case EPI_QUANT: if (resb) LB_LAUNCH_RESB(EPI_QUANT, true) else LB_LAUNCH_RELU(EPI_QUANT, true) break;
     }
 #undef LB_LAUNCH_MODE
 #undef LB_LAUNCH_MODE3
+#undef LB_LAUNCH_MODE4
+#undef LB_LAUNCH_RESB
 #undef LB_LAUNCH_RELU
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;

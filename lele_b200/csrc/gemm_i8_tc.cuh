@@ -22,12 +22,10 @@ struct LbI8Epilogue {
     int rows_per_slice;
     unsigned long long* argmax_keys;  // [M] max over columns of (fkey(out) << 32 | col)
     float* out;                // [M, N]; may be NULL when only argmax_keys is wanted
-    // fused tf32 operand preparation for attn_tc.cu (QKV projection only, N = 3 * heads * 128, rows_per_slice = T):
-    // besides out = [q | k | v] the epilogue writes lo(q), lo(k) (x - tf32_trunc(x)) to qk_lo [M, 2N/3] and
-    // V^T hi / lo to vt_hi / vt_lo [clips][heads][128][vt_tp] (keys contiguous, the K-major B operand of P.V)
-    float* qk_lo;
-    float* vt_hi;
-    float* vt_lo;
+    // fused operand preparation for attn_tc.cu (QKV projection only, N = 3 * heads * 128, rows_per_slice = T):
+    // besides out = [q | k | v] the epilogue writes V^T to vt [clips][heads][128][vt_tp] (keys contiguous, the K-major
+    // B operand of P.V).  q / k are read straight from `out`; the tf32 lo residuals are computed on chip by attn_tc.cu.
+    float* vt;
     int vt_tp;
     // fused output quantiser (two-pass linear -> dynamic quantiser, no f32 round trip): pass 1 = this GEMM with out == NULL,
     // minmax_keys set and q_rowsum set (max-only, zeroes q_rowsum); pass 2 = the same GEMM with q_out set: the epilogue

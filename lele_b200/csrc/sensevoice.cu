@@ -34,7 +34,7 @@ bool lb_attention_tc_supported(int T, int d, int H);
 size_t lb_attention_tc_scratch_bytes(int B, int T, int d, int H);
 int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, int H, float qscale, void* scratch, float* att,
                     unsigned* minmax_keys, int operands_ready);
-void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float** qk_lo, float** vt_hi, float** vt_lo, int* tp);
+void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float** vt, int* tp);
 
 namespace {
 enum { SV_G_EMBED = 0, SV_G_POS, SV_G_AFTER_G, SV_G_AFTER_B, SV_G_TP_G, SV_G_TP_B, SV_G_CTC_W, SV_G_CTC_SCALE, SV_G_CTC_BIAS,
@@ -188,6 +188,17 @@ struct lele_b200_sensevoice {
     // side stream: the HBM-bound FSMN block runs concurrently with the latency-bound attention (both only read qkv)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // clip lanes: the batch is split into n_lanes groups of clips that run the encoder on their own streams (own
+    // workspace slices, own min/max keys).  Every kernel of the layer body is a short (20-120 us) launch separated
+    // from its successor by a drain / launch / pipeline-ramp gap; with two independent chains in flight one lane's
+    // CTAs fill the SMs while the other lane's kernel drains.  Clips are independent end to end, so this is the same
+    // computation (bit-identical per clip).  LELE_B200_LANES=1 disables.
+    static constexpr int MAX_LANES = 4;
+    int n_lanes = 2;
+    lele_b200_sensevoice* lane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};   // shallow views (pointers offset per call)
+    lele_b200_ctx* lane_ctx[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};      // [0] unused (lane 0 runs on the caller's ctx)
+    cudaEvent_t ev_lane_fork = nullptr, ev_lane_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    bool is_view = false;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     struct Span { int cls; cudaEvent_t a, b; };
@@ -312,8 +323,8 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc((void**)&m->scores, sizeof(float) * B * m->heads * m->max_T * m->max_T);
     if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1));
     if (!rc) rc = sv_alloc((void**)&m->amax_keys, sizeof(unsigned long long) * M);
-    if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax));
-    if (!rc) rc = sv_alloc(&m->qscratch2, lb_quant_scratch_bytes((long long)M, kmax));
+    if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax) + 4096 * lele_b200_sensevoice::MAX_LANES);   // + per-lane carve alignment
+    if (!rc) rc = sv_alloc(&m->qscratch2, lb_quant_scratch_bytes((long long)M, kmax) + 4096 * lele_b200_sensevoice::MAX_LANES);
     { const char* e = getenv("LELE_B200_FFN_TWOPASS"); m->ffn_twopass = (e && e[0] == '0') ? 0 : 1; }
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
@@ -324,6 +335,29 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc((void**)&m->pcm_stage, sizeof(float) * B * (size_t)max_samples);
     if (!rc) rc = sv_alloc((void**)&m->ids_stage, sizeof(int32_t) * M);
     if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
+    {   // clip lanes (see the struct): views are shallow copies whose workspace pointers are re-based per call
+        const char* e = getenv("LELE_B200_LANES");
+        m->n_lanes = e ? atoi(e) : 2;
+        if (m->n_lanes < 1) m->n_lanes = 1;
+        if (m->n_lanes > lele_b200_sensevoice::MAX_LANES) m->n_lanes = lele_b200_sensevoice::MAX_LANES;
+        if (m->n_lanes > 1) {
+            bool ok = cudaEventCreateWithFlags(&m->ev_lane_fork, cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; i < m->n_lanes && ok; ++i) {
+                lele_b200_sensevoice* v = new lele_b200_sensevoice(*m);
+                v->is_view = true; v->graph_exec = nullptr; v->n_lanes = 1;
+                for (int j = 0; j < lele_b200_sensevoice::MAX_LANES; ++j) { v->lane[j] = nullptr; v->lane_ctx[j] = nullptr; v->ev_lane_join[j] = nullptr; }
+                m->lane[i] = v;
+                if (i == 0) continue;
+                v->side = nullptr; v->ev_fork = nullptr; v->ev_join = nullptr;
+                ok = lele_b200_ctx_create(ctx->device, nullptr, &m->lane_ctx[i]) == LELE_B200_OK &&
+                     cudaEventCreateWithFlags(&m->ev_lane_join[i], cudaEventDisableTiming) == cudaSuccess;
+                if (ok && (cudaStreamCreateWithFlags(&v->side, cudaStreamNonBlocking) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&v->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&v->ev_join, cudaEventDisableTiming) != cudaSuccess)) { cudaGetLastError(); v->side = nullptr; }
+            }
+            if (!ok) { cudaGetLastError(); m->n_lanes = 1; }
+        }
+    }
     *out = m;
     return LELE_B200_OK;
 }
@@ -340,6 +374,18 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
     if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    for (int i = 0; i < lele_b200_sensevoice::MAX_LANES; ++i) {
+        lele_b200_sensevoice* v = m->lane[i];
+        if (v && i > 0) {
+            if (v->side) { cudaStreamSynchronize(v->side); cudaStreamDestroy(v->side); }
+            if (v->ev_fork) cudaEventDestroy(v->ev_fork);
+            if (v->ev_join) cudaEventDestroy(v->ev_join);
+        }
+        delete v;                                        // shallow view: owns nothing else
+        if (m->lane_ctx[i]) lele_b200_ctx_destroy(m->lane_ctx[i]);
+        if (m->ev_lane_join[i]) cudaEventDestroy(m->ev_lane_join[i]);
+    }
+    if (m->ev_lane_fork) cudaEventDestroy(m->ev_lane_fork);
     delete m;
     return LELE_B200_OK;
 }
@@ -379,9 +425,9 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->qkv; ep.rows_per_slice = T;
-            // the projection's epilogue also emits the tf32 lo / V^T operand copies of the fused attention kernel
+            // the projection's epilogue also emits the V^T operand copy of the fused attention kernel
             if (attn_tc && m->lin[l * 4 + 0]->k % 16 == 0 && !getenv("LELE_B200_FORCE_SIMT") && !getenv("LELE_B200_GEMM_NO_TMA_STORE")) {
-                lb_attention_tc_operands(m->attn_scratch, B, T, d, H, &ep.qk_lo, &ep.vt_hi, &ep.vt_lo, &ep.vt_tp);
+                lb_attention_tc_operands(m->attn_scratch, B, T, d, H, &ep.vt, &ep.vt_tp);
                 attn_ops_ready = 1;
             } else attn_ops_ready = 0;
             int rc_ = sv_ln_linear(ctx, m, xin, (const float*)m->lt(l, SV_L_LN1_G), (const float*)m->lt(l, SV_L_LN1_B), cur, site(l * 4 + 0), M, T,
@@ -503,6 +549,49 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     return LELE_B200_OK;
 }
 
+// The batch split into clip lanes (lele_b200_sensevoice::n_lanes): lane i runs clips [c_i, c_i + n_i) through
+// sv_encoder on its own stream with re-based workspace pointers; lane 0 stays on the caller's stream, which forks the
+// others with an event and joins them at the end (works eagerly and under stream capture alike).
+static int sv_encoder_lanes(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* feats, int B, int t, int lang, int textnorm,
+                            int n_layers_limit, int32_t* ids_dev, float* logits_opt) {
+    const int nl = (m->profiling || m->n_lanes < 2 || B < 2 * m->n_lanes) ? 1 : m->n_lanes;
+    if (nl == 1) return sv_encoder(ctx, m, feats, B, t, lang, textnorm, n_layers_limit, ids_dev, logits_opt);
+    const int T = t + 4, d = m->d, din = m->d_in, H = m->heads, ffn = m->ffn, dk = d / H;
+    const int wide = din > d ? din : d, kmax = ffn > din ? ffn : din;
+    const size_t n_sites = (size_t)m->n_layers * 4 + 1;
+    const int n_layers = (n_layers_limit >= 0 && n_layers_limit < m->n_layers) ? n_layers_limit : m->n_layers;
+    const long long out_w = n_layers < m->n_layers ? (n_layers == 0 ? din : d) : m->vocab;
+    const size_t Tp = (size_t)((T + 3) / 4 * 4);
+    LB_CHECK_CUDA(cudaEventRecord(m->ev_lane_fork, ctx->stream));
+    int c0 = 0, rc = 0;
+    size_t q_off = 0;
+    for (int i = 0; i < nl; ++i) {
+        const int nb = B / nl + (i < B % nl ? 1 : 0);
+        lele_b200_sensevoice* v = m->lane[i];
+        lele_b200_ctx* lctx = i == 0 ? ctx : m->lane_ctx[i];
+        const long long r0 = (long long)c0 * T;
+        v->x0 = m->x0 + r0 * din; v->x = m->x + r0 * d; v->h = m->h + r0 * wide; v->qkv = m->qkv + r0 * 3 * d; v->qs = m->qs + r0 * d;
+        v->fsmn = m->fsmn + r0 * d; v->att = m->att + r0 * d; v->f1 = m->f1 + r0 * ffn;
+        v->scores = m->scores + (long long)c0 * H * T * T;
+        v->keys = m->keys + 2 * LB_MM_SLOTS * n_sites * (size_t)c0;
+        v->amax_keys = m->amax_keys + r0;
+        v->qscratch = (uint8_t*)m->qscratch + q_off; v->qscratch2 = (uint8_t*)m->qscratch2 + q_off;
+        v->attn_scratch = (float*)m->attn_scratch + (size_t)c0 * H * dk * Tp;
+        v->profiling = 0;
+        if (i > 0) LB_CHECK_CUDA(cudaStreamWaitEvent(lctx->stream, m->ev_lane_fork, 0));
+        if (!rc) rc = sv_encoder(lctx, v, feats + (long long)c0 * t * din, nb, t, lang, textnorm, n_layers_limit, ids_dev ? ids_dev + r0 : nullptr,
+                                 logits_opt ? logits_opt + r0 * out_w : nullptr);
+        if (i > 0) {   // join even after an error so that an enclosing stream capture stays well formed
+            LB_CHECK_CUDA(cudaEventRecord(m->ev_lane_join[i], lctx->stream));
+            LB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_lane_join[i], 0));
+            ctx->launches += lctx->launches; lctx->launches = 0;
+        }
+        c0 += nb;
+        q_off += (lb_quant_scratch_bytes((long long)nb * T, kmax) + 4095) / 4096 * 4096;
+    }
+    return rc;
+}
+
 static int sv_finish_profile(lele_b200_ctx* ctx, lele_b200_sensevoice* m) {
     if (!m->profiling) return LELE_B200_OK;
     LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -520,7 +609,7 @@ extern "C" int lele_b200_sensevoice_forward_features(lele_b200_ctx* ctx, lele_b2
                                                      float* logits_dev_opt) {
     LB_REQUIRE(ctx && m && feats_dev, "sensevoice_forward_features: NULL argument");
     LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && t >= 1 && t + 4 <= m->max_T, "sensevoice_forward_features: batch/length exceeds workspace");
-    int rc = sv_encoder(ctx, m, feats_dev, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+    int rc = sv_encoder_lanes(ctx, m, feats_dev, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
     if (rc) return rc;
     return sv_finish_profile(ctx, m);
 }
@@ -529,7 +618,7 @@ static int sv_forward_eager(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const f
                             int lang, int textnorm, int n_layers_limit, int32_t* ids_dev, float* logits_dev_opt) {
     SV_RUN(P_FRONTEND, lele_b200_frontend_compute(ctx, pcm_dev, n_clips, n_samples, n_samples, nullptr, m->lfr));
     SV_RUN(P_CMVN, lele_b200_cmvn(ctx, m->lfr, n_clips, t, m->d_in, 1e-5f, m->feats));
-    return sv_encoder(ctx, m, m->feats, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+    return sv_encoder_lanes(ctx, m, m->feats, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
 }
 
 extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_dev, int n_clips, int n_samples,

@@ -74,6 +74,26 @@ def test_tcgen05_attention_stage(small_model_tc, t):
         assert dec[0] == got.min() and dec[1] == got.max()
 
 
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_clip_lanes_bit_identical(lanes, monkeypatch):
+    """The runner splits a batch into clip lanes that execute on concurrent streams (own workspace slices, own
+    min/max keys).  Clips are independent, so any lane count must give bit-identical logits and ids
+    (7 clips -> uneven lanes; product configuration: tcgen05 attention, two-pass FFN1, CUDA-graph replay)."""
+    blob = build_blob(SMALL, seed=11)
+    pcm = synth_batch(3, 7, 16000 * 3)
+    outs = []
+    for n in (1, lanes):
+        monkeypatch.setenv("LELE_B200_LANES", str(n))
+        m = SenseVoice(blob, max_clips=7, max_samples=pcm.shape[1])
+        ids, logits = m.transcribe(pcm, want_logits=True)
+        for _ in range(2):                                # eager + capture, then a replay of the captured graph
+            np.testing.assert_array_equal(ids, m.transcribe(pcm))
+        outs.append((ids, logits))
+        m.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
 def test_tc_network_close_to_oracle(small_model_tc):
     """Whole small network with the tensor-core attention: f32-grade attention differences can flip
     individual u8 roundings of the next dynamic quantiser (1 LSB), so the bar is normwise."""
