@@ -172,6 +172,11 @@ __device__ __forceinline__ void lb_mm_update(unsigned* keys, long long slice, fl
     atomicMin(k, lb_fkey(mn));
     atomicMax(k + 1, lb_fkey(mx));
 }
+__device__ __forceinline__ void lb_mm_update_keys(unsigned* keys, long long slice, unsigned kmin, unsigned kmax) {
+    unsigned* k = keys + ((size_t)slice * LB_MM_SLOTS + (blockIdx.x & (LB_MM_SLOTS - 1))) * 2;
+    atomicMin(k, kmin);
+    atomicMax(k + 1, kmax);
+}
 __device__ __forceinline__ void lb_mm_read(const unsigned* keys, long long slice, float& mn, float& mx) {
     const unsigned* k = keys + (size_t)slice * LB_MM_SLOTS * 2;
     unsigned a = LB_KEY_MIN_INIT, b = LB_KEY_MAX_INIT;

@@ -29,7 +29,10 @@ constexpr int B_STAGE_BYTES = BN * BK;               // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int FIRST_EPI_WARP = 2;                    // warp 0: TMA producer (+ TMEM alloc), warp 1: MMA issuer
-constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;   // 576 -> 112 registers per thread
+// 18 warps -> 5 on two of the four SM sub-partitions (16 K registers each) -> ptxas caps every thread at 96 registers.
+// setmaxnreg re-balancing (control warpgroup down, epilogue warps up to 104-112) was tried: ptxas then spills far more
+// (600-1600 B per thread), so the cap stays and the residual epilogues live with ~100-300 B of spills.
+constexpr int NUM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;   // 576
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_TILE_BYTES = 32 * 128;                       // per-warp 32x32 f32 staging tile, 128B-swizzled (1024 B aligned)
 constexpr int EPI_META_BYTES = 3 * 64 * 4;                     // zp*colsum / scale / bias of the warp's 64 columns
@@ -143,12 +146,23 @@ struct KernelArgs {
     int vec_io;
     int dbg;            // LELE_B200_GEMM_DBG=1: CTAs 0 and 77 print where their producer / MMA / epilogue roles waited (clock64)
     int num_m_blocks, num_n_blocks, num_k_blocks;
+    int rps;            // rows per slice (0x7fffffff when the epilogue has no slices)
+    float inv_rps;      // 1.0f / rps: slice index by float multiply + one exact correction step (no integer division)
     LbI8Epilogue ep;
 };
 
 // Epilogue specialisations (compile-time, so the inner loops carry no uniform branches)
 enum EpiMode { EPI_PLAIN = 0, EPI_MINMAX, EPI_ARGMAX, EPI_R1, EPI_R2, EPI_R12, EPI_QKV, EPI_QUANT };
 
+// n / d for 0 <= n < 2^22 with inv = 1.0f / d: float estimate + one exact correction (an integer division costs ~35
+// instructions and the epilogue needs several per tile per warp)
+__device__ __forceinline__ int div_by_rps(int n, int d, float inv) {
+    int q = __float2int_rz(__fmul_rn(__int2float_rn(n), inv));
+    const int r = n - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ int4 lds_v4(uint32_t addr) {
@@ -303,13 +317,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         long long w_acc = 0, t_busy0 = 0, busy = 0, d_ld = 0, d_math = 0; const long long t_begin = clock64();
         int pf_rs = 0, pf_zpa = 0, pf_cs[2] = {0, 0}; float pf_sa = 0.0f, pf_ws[2] = {0.0f, 0.0f}, pf_bi[2] = {0.0f, 0.0f};
         unsigned pf_qkey = 0;                                          // EPI_QUANT: one min/max key slot of the warp's clip A (lanes 0-15) / A+1 (16-31)
-        auto fetch_meta = [&](int t) {
+        const int nnb = args.num_n_blocks;
+        const int rps = args.rps; const float inv_rps = args.inv_rps;
+        const int last_slice = div_by_rps(M - 1, rps, inv_rps);
+        // tile coordinates advance incrementally (tile += gridDim.x): no per-tile integer divisions
+        const int step_m = (int)gridDim.x / nnb, step_n = (int)gridDim.x % nnb;
+        int m_blk = (int)blockIdx.x / nnb, n_blk = (int)blockIdx.x % nnb;
+        auto fetch_meta = [&](int t, int mb, int nb) {
             if (t >= num_tiles) return;
-            const int mb = t / args.num_n_blocks, nb = t % args.num_n_blocks;
             const int rw = mb * BM + quad * 32 + lane;
             if (MODE == EPI_QUANT) {
-                const int rps_ = ep.rows_per_slice > 0 ? ep.rows_per_slice : 0x7fffffff;
-                const int sl = min((mb * BM + quad * 32) / rps_ + (lane >> 4), (M - 1) / rps_);
+                const int sl = min(div_by_rps(mb * BM + quad * 32, rps, inv_rps) + (lane >> 4), last_slice);
                 pf_qkey = __ldg(ep.q_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
             }
             pf_rs = 0; pf_zpa = 0; pf_sa = 0.0f;
@@ -320,9 +338,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 pf_cs[hh] = __ldg(ep.colsum + cc); pf_ws[hh] = __ldg(ep.w_scale + cc); pf_bi[hh] = __ldg(ep.bias + cc);
             }
         };
-        fetch_meta(blockIdx.x);
+        fetch_meta(blockIdx.x, m_blk, n_blk);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
             const int first_row = m_blk * BM + quad * 32;
             const int row = first_row + lane;
             const bool row_ok = row < M;
@@ -334,9 +351,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // Per-warp column metadata, pre-combined with the activation parameters of the clip that owns the warp's
             // first row ("A"): zcA[c] = zp_A * colsum[c], csA[c] = scale_A * w_scale[c].  A warp's 32 rows touch a
             // second clip only at clip boundaries (1 warp in ~8 for T' = 271); those rows take the uncombined path.
-            const int rps = ep.rows_per_slice > 0 ? ep.rows_per_slice : 0x7fffffff;
-            const int slice_first = first_row / rps;
-            const bool in_a = row_ok && (row / rps) == slice_first;
+            const int slice_first = div_by_rps(first_row, rps, inv_rps);
+            const bool in_a = row_ok && row < (slice_first + 1) * rps;     // rows ascend: the warp's rows are in slice A or A+1
             const bool all_a = __all_sync(0xffffffffu, !row_ok || in_a);
             const int zpa_a = __shfl_sync(0xffffffffu, zpa, 0);
             const float sa_a = __shfl_sync(0xffffffffu, sa, 0);
@@ -364,7 +380,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 q_zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, q_scale)), 0.0f), 255.0f);
                 q_inv = __fdiv_rn(1.0f, q_scale);
             }
-            fetch_meta(tile + (int)gridDim.x);                         // next tile's metadata: consumed one iteration later
+            {   // next tile's coordinates and metadata (consumed one iteration later)
+                int mb_n = m_blk + step_m, nb_n = n_blk + step_n;
+                if (nb_n >= nnb) { nb_n -= nnb; ++mb_n; }
+                fetch_meta(tile + (int)gridDim.x, mb_n, nb_n);
+            }
             float best_t = -3.402823466e+38f; int best_c = -1;
             float vmin = FMAX, vmax = -FMAX;                           // this row's min / max over the warp's 64 columns
             const int nrows = min(32, M - first_row);
@@ -482,7 +502,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         // (q / k are consumed straight out of `out`; every tf32 lo residual is computed on chip by attn_tc.cu.)
                         const int dmodel = N / 3;
                         if (gcol0 >= 2 * dmodel && row_ok) {   // 32 consecutive keys (lanes) per store instruction
-                            const int bb = row / rps, tt = row - bb * rps;
+                            const int bb = div_by_rps(row, rps, inv_rps), tt = row - bb * rps;
                             const int cv = gcol0 - 2 * dmodel;
                             float* vt = ep.vt + ((size_t)bb * (dmodel >> 7) * 128 + cv) * (size_t)ep.vt_tp + tt;
 #pragma unroll
@@ -567,16 +587,20 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (MODE == EPI_MINMAX && ep.q_rowsum && row_ok && n_blk == 0 && cgrp == 0) ep.q_rowsum[row] = 0;   // max-only pass: arm the next pass's row sums
             if (MODE == EPI_MINMAX && RELU && vmax > -FMAX) { vmin = 0.0f; vmax = fmaxf(vmax, 0.0f); }   // any value >= 0 gives amin = 0
             if (MODE == EPI_MINMAX && nrows > 0) {
-                // rows of clip A (the one owning the warp's first row) and of clip A+1 reduce separately
-                const float mnA = lb_warp_min(in_a ? vmin : FMAX), mxA = lb_warp_max(in_a ? vmax : -FMAX);
-                if (lane == 0 && mnA <= mxA) lb_mm_update(ep.minmax_keys, slice_first, mnA, mxA);
+                // rows of clip A (the one owning the warp's first row) and of clip A+1 reduce separately; the reduction runs
+                // on the order-preserving integer keys the atomics use anyway (one REDUX per value instead of a 5-step shuffle tree)
+                const unsigned kmin = lb_fkey(vmin), kmax = lb_fkey(vmax);
+                const unsigned mnA = __reduce_min_sync(0xffffffffu, in_a ? kmin : LB_KEY_MIN_INIT), mxA = __reduce_max_sync(0xffffffffu, in_a ? kmax : LB_KEY_MAX_INIT);
+                if (lane == 0 && mnA <= mxA) lb_mm_update_keys(ep.minmax_keys, slice_first, mnA, mxA);
                 if (!all_a) {
                     const bool in_b = row_ok && !in_a;
-                    const float mnB = lb_warp_min(in_b ? vmin : FMAX), mxB = lb_warp_max(in_b ? vmax : -FMAX);
-                    if (lane == 0 && mnB <= mxB) lb_mm_update(ep.minmax_keys, slice_first + 1, mnB, mxB);
+                    const unsigned mnB = __reduce_min_sync(0xffffffffu, in_b ? kmin : LB_KEY_MIN_INIT), mxB = __reduce_max_sync(0xffffffffu, in_b ? kmax : LB_KEY_MAX_INIT);
+                    if (lane == 0 && mnB <= mxB) lb_mm_update_keys(ep.minmax_keys, slice_first + 1, mnB, mxB);
                 }
             }
             if (MODE == EPI_ARGMAX && row_ok && best_c >= 0) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey(best_t) << 32) | (unsigned)best_c);
+            m_blk += step_m; n_blk += step_n;
+            if (n_blk >= nnb) { n_blk -= nnb; ++m_blk; }
         }
         if (TMA_OUT && lane == 0) tma_store_wait_all();                // staging smem must outlive the bulk stores
         if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (ew == 0 || ew == 15))
@@ -703,6 +727,9 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     args.num_n_blocks = lb_ceil_div(N, BN);
     args.num_k_blocks = lb_ceil_div(K, BK);
     args.ep = ep;
+    args.rps = ep.rows_per_slice > 0 ? ep.rows_per_slice : 0x7fffffff;
+    args.inv_rps = 1.0f / (float)args.rps;
+    LB_REQUIRE(M < (1 << 22), "gemm_i8_tc: M=%d exceeds the 2^22 rows the epilogue's slice arithmetic is exact for", M);
     args.dbg = getenv("LELE_B200_GEMM_DBG") ? 1 : 0;
     args.vec_io = (N % 4 == 0) && ((((uintptr_t)ep.out | (uintptr_t)ep.add1 | (uintptr_t)ep.add2) & 15) == 0) && !getenv("LELE_B200_GEMM_NO_VEC_IO");
     int tiles = args.num_m_blocks * args.num_n_blocks;
