@@ -35,13 +35,13 @@ def linear_flops_per_clip(cfg, T):
     return tot
 
 
-def cpu_baseline_run(blob, n_threads, first_clip):
-    """Times the CPU restatement of lele's path (oracle port): one 16 s clip per thread, each
-    thread single-threaded like lele itself (Par::Seq, src/kernels/gemm.rs:196)."""
+def cpu_baseline_run(blob, n_threads, first_clip, n_samples=N_SAMPLES):
+    """Times the CPU restatement of lele's path (oracle port): one clip (16 s unless bounded) per thread,
+    each thread single-threaded like lele itself (Par::Seq, src/kernels/gemm.rs:196)."""
     from lele_b200.sensevoice_weights import synth_pcm
     from oracle.binding import SenseVoiceRef
     ref = SenseVoiceRef(blob)
-    clips = [synth_pcm(first_clip + i, N_SAMPLES) for i in range(n_threads)]
+    clips = [synth_pcm(first_clip + i, n_samples) for i in range(n_threads)]
     ref.pcm_to_ids(clips[0][:16000])  # touch code / page in the blob
     out = [None] * n_threads
 
@@ -53,7 +53,7 @@ def cpu_baseline_run(blob, n_threads, first_clip):
     [t.start() for t in ths]
     [t.join() for t in ths]
     dt = time.perf_counter() - t0
-    return n_threads * AUDIO_S_PER_CLIP / dt, dt
+    return n_threads * (n_samples / 16000.0) / dt, dt
 
 
 class ClockSampler:
@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -114,18 +114,27 @@ def run_reference(args):
     cfg = SenseVoiceConfig()
     blob = build_blob(cfg, seed=1234)
     cores = os.cpu_count() or 1
+    # bounded sample: a step is one clip per host thread; the clip is the workload's 16 s unless the whole
+    # (warmup + steps) run would exceed the time budget, in which case every step uses a shorter clip (stated in `sample`)
+    budget_s = float(os.environ.get("LELE_B200_REF_BUDGET_S", "300"))
+    _, cal_dt = cpu_baseline_run(blob, cores, 0, 2 * 16000)        # calibration: 2 s clips
+    per_audio_s = cal_dt / 2.0
+    n_steps_total = max(args.steps + args.warmup, 1)
+    clip_s = int(min(16.0, max(2.0, np.floor(budget_s / (n_steps_total * per_audio_s)))))
+    n_samples = clip_s * 16000
     for _ in range(args.warmup):
-        cpu_baseline_run(blob, cores, 0)
+        cpu_baseline_run(blob, cores, 0, n_samples)
     vals, total = [], 0.0
     for s in range(args.steps):
-        v, dt = cpu_baseline_run(blob, cores, s * cores)
+        v, dt = cpu_baseline_run(blob, cores, s * cores, n_samples)
         vals.append(v); total += dt
-    value = args.steps * cores * AUDIO_S_PER_CLIP / total
-    sample = f"{cores} clips x 16 s per step (one clip per host thread, full 70-layer network + front-end)"
+    value = args.steps * cores * clip_s / total
+    sample = (f"{cores} clips x {clip_s} s per step (one clip per host thread, full 70-layer network + front-end)"
+              + ("" if clip_s == 16 else f"; clip shortened from 16 s to keep {n_steps_total} steps within {budget_s:.0f} s"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 x u8 -> i32 (f32 epilogue / attention)", "data": "synthetic",
-            "config": {"workload": "SenseVoiceSmall-shaped ASR, synthetic 16 kHz x 16 s clips, random-init int8 weights", "clips_per_step": cores},
+            "config": {"workload": "SenseVoiceSmall-shaped ASR (70 SANM layers d512 h4 ffn2048, CTC 25055), synthetic 16 kHz x 16 s clips, random-init int8 weights", "clips_per_step": cores, "clip_seconds": clip_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -285,6 +294,170 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# ---------------------------------------------------------------------------------------------
+# --ops: per-operator measurement of SURVEY.md section 8(a) rows (one JSON line per operator):
+# device time of the C-ABI entry (CUDA events, inputs resident in HBM, L2 flushed between
+# repetitions) -> roofline fraction, next to the CPU oracle (one host thread, as lele runs).
+# ---------------------------------------------------------------------------------------------
+def run_ops(args):
+    import torch
+    from lele_b200 import features as F
+    from lele_b200 import kernels as K
+    from lele_b200 import _lib
+    from oracle import reference_api as R            # cpu_baseline leg only (the checker, never the product path)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --ops: no CUDA device")
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    ctx = K.Context(0, stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    bf16 = float(peaks.get("bf16_tflops", 1600.0))
+    PEAK = {"hbm": (hbm, "GB/s", "MEASURED_PEAKS.hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"),
+            "tensor_i8": (2 * bf16, "TFLOP/s", "2 x MEASURED_PEAKS.bf16_tflops (burst; int8 nominally 2x bf16)"),
+            "tensor_f32": (bf16 / 6, "TFLOP/s", "MEASURED_PEAKS.bf16_tflops / 2 (tf32) / 3 (3xTF32 = f32-grade accuracy)")}
+    NOT_TIMED = {"lele_b200_h2d", "lele_b200_d2h", "lele_b200_malloc", "lele_b200_free", "lele_b200_sync", "lele_b200_ctx_create",
+                 "lele_b200_prepare_weights", "lele_b200_hann_window", "lele_b200_mel_filterbank"}
+    state = {"on": False, "ms": 0.0, "launches": 0, "calls": []}
+    orig_call = _lib.call
+    REPS = 5
+
+    def timed_call(name, *a):
+        if not state["on"] or name in NOT_TIMED:
+            return orig_call(name, *a)
+        orig_call(name, *a); orig_call(name, *a)                 # warm-up (lazy tables, attributes)
+        torch.cuda.synchronize()
+        ms = []
+        l0 = ctx.launch_count()
+        for _ in range(REPS):
+            flush.zero_()                                          # > L2: every repetition starts cold
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); orig_call(name, *a); e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        state["ms"] += float(np.median(ms)); state["launches"] += (ctx.launch_count() - l0) // REPS; state["calls"].append(name)
+
+    K.call = timed_call; F.call = timed_call
+    rng = np.random.default_rng(7)
+    f = lambda *sh: rng.standard_normal(sh).astype(np.float32)
+    rows = []
+
+    def op(row, name, gpu_fn, cpu_fn, bound, alg_bytes, alg_flops, cpu_scale=1.0, note=""):
+        """gpu_fn(): runs the host mirror on the full-size inputs (timed inside timed_call);
+        cpu_fn(): the oracle on 1/cpu_scale of the work (one host thread)."""
+        state.update(on=True, ms=0.0, launches=0, calls=[])
+        try:
+            got = gpu_fn()
+            state["on"] = False
+            t0 = time.perf_counter(); want = cpu_fn(); cpu_s = (time.perf_counter() - t0) * cpu_scale
+        except Exception as e:                                   # keep the table going; the failure is reported in place
+            state["on"] = False
+            print(json.dumps({"op": name, "row": row, "error": f"{type(e).__name__}: {e}"}), flush=True)
+            return
+        ms = state["ms"]
+        peak, unit, src = PEAK[bound]
+        achieved = (alg_bytes / 1e9 if bound == "hbm" else alg_flops / 1e12) / (ms / 1e3)
+        ok = None
+        if cpu_scale == 1.0 and want is not None and got is not None:
+            g = got[0] if isinstance(got, tuple) else got; w = want[0] if isinstance(want, tuple) else want
+            ok = bool(np.allclose(np.asarray(g, np.float64), np.asarray(w, np.float64), rtol=1e-4, atol=1e-4 * float(np.abs(w).max() + 1e-30)))
+        line = {"op": name, "row": row, "ms": ms, "gpu_launches": state["launches"], "entry": state["calls"],
+                "roofline": {"bound": "hbm" if bound == "hbm" else "tensor", "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                             "peak_source": src, "algorithmic_bytes": alg_bytes, "algorithmic_flops": alg_flops, "traffic": None},
+                "cpu_baseline": {"seconds": cpu_s, "cores": 1, "kind": "port", "sample": f"1/{int(cpu_scale)} of the GPU work, scaled" if cpu_scale != 1.0 else "same inputs"},
+                "speedup_vs_1_core": cpu_s / (ms / 1e3), "matches_oracle": ok, "note": note}
+        rows.append(line)
+        print(json.dumps(line), flush=True)
+
+    B, T, d, ffn = 64, 275, 512, 2048
+    M = B * T
+    # ---- a1-a7 front-end ----
+    from lele_b200.sensevoice_weights import synth_batch
+    pcm = synth_batch(0, B, N_SAMPLES)
+    fe = F.SenseVoiceFrontend()
+    op("a1-a6", "SenseVoiceFrontend.compute [64 x 16 s]", lambda: fe.compute(pcm, ctx=ctx), lambda: R.frontend(pcm[0]), "hbm",
+       B * (N_SAMPLES * 4 + 267 * 560 * 4), B * 43e6, cpu_scale=B)
+    lfr1 = f(267, 560)
+    op("a7", "Cmvn.compute [267,560]", lambda: F.Cmvn().compute(lfr1, ctx=ctx), lambda: R.cmvn(lfr1), "hbm", 2 * lfr1.nbytes, 0, note="per clip (the batched form runs inside the runner)")
+    # ---- a8/a9 int8 ----
+    x = f(M, d)
+    w_u8 = rng.integers(0, 256, (d, ffn)).astype(np.uint8); ws = (rng.random(ffn).astype(np.float32) + 0.5) / 255 / np.sqrt(d); bi = f(ffn) * 0.02
+    pw = K.PreparedWeights(w_u8, ws, 128, bi, ctx)
+    op("a8", "fused_quantized_linear [17600,512]x[512,2048] +ReLU", lambda: K.fused_quantized_linear(x, pw, ws, 128, bi, True, ctx=ctx),
+       lambda: R.fused_quantized_linear(x[:T], w_u8.astype(np.float32), ws, 128.0, bi, True), "tensor_i8",
+       M * d * 4 * 2 + M * d + d * ffn + M * ffn * 4, 2.0 * M * d * ffn, cpu_scale=B, note="min/max + quantise + tcgen05 GEMM + f32 epilogue, one slice")
+    op("a9", "dynamic_quantize_linear [17600,512]", lambda: K.dynamic_quantize_linear(x, ctx=ctx), lambda: R.dynamic_quantize_linear(x), "hbm", x.nbytes * 3, 0,
+       note="output is f32-coded u8 (reference semantics): read x twice + write 4 B/elt")
+    # ---- a10 f32 GEMM ----
+    qa, kb = f(256, 271, 128), f(256, 128, 271)
+    op("a10", "matmul [256,271,128]x[256,128,271]", lambda: K.matmul(qa, kb, ctx=ctx), lambda: R.matmul(qa[:4], kb[:4]), "tensor_f32",
+       qa.nbytes + kb.nbytes + 256 * 271 * 271 * 4, 2.0 * 256 * 271 * 271 * 128, cpu_scale=64, note="generic matmul = CUDA-core sgemm (the fused attention kernel is the tensor-core path for this shape)")
+    ga, gb, gc = f(1024, 1024), f(1024, 1024), f(1024)
+    op("a10", "gemm 1024^3 (+C)", lambda: K.gemm(ga, gb, gc, 1.0, 1.0, False, False, ctx=ctx), lambda: R.gemm(ga[:64], gb, gc, 1.0, 1.0, False, False), "tensor_f32",
+       3 * ga.nbytes, 2.0 * 1024 ** 3, cpu_scale=16, note="CUDA-core sgemm")
+    # ---- a11-a13 conv ----
+    xc = f(B, d, 271); wd = f(d, 1, 11) * 0.1
+    op("a11", "conv1d depthwise k=11 [64,512,271]", lambda: K.conv1d(xc, wd, None, (1,), d, (5, 5), (1,), ctx=ctx), lambda: R.conv1d(xc[:1], wd, None, (1,), d, (5, 5), (1,)), "hbm",
+       2 * xc.nbytes, 2.0 * xc.size * 11, cpu_scale=B)
+    x2 = f(8, 64, 160, 160); w2 = f(64, 64, 3, 3) * 0.05; b2 = f(64)
+    op("a12", "conv2d_silu 3x3 64->64 @160x160 x8", lambda: K.conv2d_silu(x2, w2, b2, (1, 1), 1, (1, 1, 1, 1), (1, 1), ctx=ctx),
+       lambda: R.conv2d(x2[:1, :, :40], w2, b2, (1, 1), 1, (1, 1, 1, 1), (1, 1), 2), "tensor_f32", 2 * x2.nbytes + w2.nbytes, 2.0 * 8 * 64 * 64 * 9 * 160 * 160, cpu_scale=32,
+       note="im2col + CUDA-core sgemm (Yolo26n-seg's largest layer)")
+    w11 = f(128, 64, 1, 1) * 0.1
+    op("a12", "conv2d 1x1 64->128 @160x160 x8", lambda: K.conv2d(x2, w11, None, (1, 1), 1, (0, 0, 0, 0), (1, 1), 0, ctx=ctx),
+       lambda: R.conv2d(x2[:1, :, :40], w11, None, (1, 1), 1, (0, 0, 0, 0), (1, 1), 0), "tensor_f32", x2.nbytes * 3 + w11.nbytes, 2.0 * 8 * 128 * 64 * 160 * 160, cpu_scale=32)
+    xt = f(8, 64, 80, 80); wt = f(64, 64, 2, 2) * 0.1
+    op("a13", "conv_transpose k2 s2 [8,64,80,80]", lambda: K.conv_transpose(xt, wt, None, (1, 1), (0, 0, 0, 0), (2, 2), ctx=ctx),
+       lambda: R.conv_transpose(xt[:1], wt, None, (1, 1), (0, 0, 0, 0), (2, 2)), "tensor_f32", xt.nbytes * 5 + wt.nbytes, 2.0 * 8 * 64 * 64 * 4 * 80 * 80, cpu_scale=8)
+    # ---- a14/a15 recurrent ----
+    S, I, H = 175, 128, 128
+    xs = f(S, 1, I); wl, rl, bl = f(1, 4 * H, I) * 0.1, f(1, 4 * H, H) * 0.1, f(1, 8 * H) * 0.1
+    op("a14", "lstm S=175 I=H=128", lambda: K.lstm(xs, wl, rl, bl, ctx=ctx), lambda: R.lstm(xs, wl, rl, bl), "hbm", (wl.nbytes + rl.nbytes) * S, 2.0 * S * 4 * H * (I + H),
+       note="batch=1 recurrence: latency-bound; bytes = W,R re-read per step (SURVEY 8d)")
+    wg, rg, bg = f(1, 3 * H, I) * 0.1, f(1, 3 * H, H) * 0.1, f(1, 6 * H) * 0.1
+    op("a15", "gru S=175 I=H=128", lambda: K.gru(xs, wg, rg, bg, ctx=ctx), lambda: R.gru(xs, wg, rg, bg), "hbm", (wg.nbytes + rg.nbytes) * S, 2.0 * S * 3 * H * (I + H), note="batch=1 recurrence: latency-bound")
+    # ---- a16/a17 norms ----
+    g1, b1 = f(d), f(d)
+    op("a16", "layer_norm [17600,512]", lambda: K.layer_norm(x, g1, b1, -1, 1e-5, ctx=ctx), lambda: R.layer_norm(x, g1, b1, -1, 1e-5), "hbm", 2 * x.nbytes, 0)
+    sc = f(B * 4 * 271, 271)
+    op("a17", "softmax [69376,271]", lambda: K.softmax(sc, -1, ctx=ctx), lambda: R.softmax(sc), "hbm", 2 * sc.nbytes, 0)
+    # ---- a18 stft ----
+    sig = f(1, 16000 * 60)
+    op("a18", "stft_power_spectrum 60 s n_fft=512 hop=160", lambda: K.stft_power_spectrum(sig, 512, 160, 400, None, ctx=ctx), lambda: R.stft(sig, 512, 160, 400, None, True), "hbm",
+       sig.nbytes + (sig.size // 160) * 257 * 4, 0)
+    # ---- a19 element-wise ----
+    y = f(M, ffn); y2 = f(M, ffn)
+    op("a19", "add [17600,2048]", lambda: K.add(y, y2, ctx=ctx), lambda: R.add(y, y2), "hbm", 3 * y.nbytes, 0)
+    brow = f(ffn)
+    op("a19", "mul broadcast [17600,2048]*[2048]", lambda: K.mul(y, brow, ctx=ctx), lambda: R.mul(y, brow), "hbm", 2 * y.nbytes, 0)
+    op("a19", "sigmoid [17600,2048]", lambda: K.sigmoid(y, ctx=ctx), lambda: R.sigmoid(y), "hbm", 2 * y.nbytes, 0)
+    op("a19", "silu [17600,2048]", lambda: K.silu(y, ctx=ctx), lambda: R.silu(y), "hbm", 2 * y.nbytes, 0)
+    # ---- a20 indexing ----
+    q4 = f(B, 271, 4, 128)
+    op("a20", "transpose [64,271,4,128] perm 0213", lambda: K.transpose(q4, (0, 2, 1, 3), ctx=ctx), lambda: R.transpose(q4, (0, 2, 1, 3)), "hbm", 2 * q4.nbytes, 0)
+    op("a20", "concat axis=1 2x[17600,2048]", lambda: K.concat([y, y2], 1, ctx=ctx), lambda: R.concat([y, y2], 1), "hbm", 4 * y.nbytes, 0)
+    idx = rng.integers(0, M, 20000).astype(np.int64)
+    op("a20", "gather rows 20000 of [17600,2048]", lambda: K.gather(y, idx, 0, ctx=ctx), lambda: R.gather(y, idx, 0), "hbm", 2 * 20000 * ffn * 4, 0)
+    op("a20", "max_pool2d 5x5 s1 p2 [8,64,160,160]", lambda: K.max_pool2d(x2, (5, 5), (2, 2, 2, 2), (1, 1), (1, 1), False, ctx=ctx), lambda: R.max_pool2d(x2[:1], (5, 5), (2, 2, 2, 2), (1, 1), (1, 1), False), "hbm",
+       2 * x2.nbytes, 0, cpu_scale=8)
+    K.call = orig_call; F.call = orig_call
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ops_roofline.md"), "w") as fh:
+        fh.write("# per-operator roofline (bench.py --ops): device time of the C-ABI entry, inputs in HBM, L2 flushed between repetitions\n\n")
+        fh.write(f"peaks: HBM {hbm:.0f} GB/s; int8 tensor {PEAK['tensor_i8'][0]:.0f} TFLOP/s; f32-grade (3xTF32) tensor {PEAK['tensor_f32'][0]:.0f} TFLOP/s\n\n")
+        fh.write("| row | operator | ms | launches | bound | achieved | peak | frac | CPU oracle (1 core) s | x vs 1 core | == oracle |\n|---|---|---:|---:|---|---:|---:|---:|---:|---:|---|\n")
+        for r in rows:
+            ro = r["roofline"]
+            fh.write(f"| {r['row']} | {r['op']} | {r['ms']:.3f} | {r['gpu_launches']} | {ro['bound']} | {ro['achieved']:.1f} {ro['unit']} | {ro['peak']:.0f} | {ro['frac']:.3f} | "
+                     f"{r['cpu_baseline']['seconds']:.3f} | {r['speedup_vs_1_core']:.0f} | {r['matches_oracle']} |\n")
+
+
 def _init_model_from_device(model, ctx, header_np, nbytes, dev_ptr, max_clips, max_samples):
     """SenseVoice over a blob that is already resident in HBM (it arrived by NCCL broadcast)."""
     import ctypes as C
@@ -307,8 +480,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops", action="store_true", help="per-operator roofline table of the SURVEY 8(a) rows (not the headline line)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.ops:
+        run_ops(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
