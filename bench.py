@@ -397,10 +397,13 @@ def run_ops(args):
     # ---- a10 f32 GEMM ----
     qa, kb = f(256, 271, 128), f(256, 128, 271)
     op("a10", "matmul [256,271,128]x[256,128,271]", lambda: K.matmul(qa, kb, ctx=ctx), lambda: R.matmul(qa[:4], kb[:4]), "tensor_f32",
-       qa.nbytes + kb.nbytes + 256 * 271 * 271 * 4, 2.0 * 256 * 271 * 271 * 128, cpu_scale=64, note="generic matmul = CUDA-core sgemm (the fused attention kernel is the tensor-core path for this shape)")
+       qa.nbytes + kb.nbytes + 256 * 271 * 271 * 4, 2.0 * 256 * 271 * 271 * 128, cpu_scale=64, note="tcgen05 3xTF32, [K,N] operand gathered in-kernel")
     ga, gb, gc = f(1024, 1024), f(1024, 1024), f(1024)
     op("a10", "gemm 1024^3 (+C)", lambda: K.gemm(ga, gb, gc, 1.0, 1.0, False, False, ctx=ctx), lambda: R.gemm(ga[:64], gb, gc, 1.0, 1.0, False, False), "tensor_f32",
-       3 * ga.nbytes, 2.0 * 1024 ** 3, cpu_scale=16, note="CUDA-core sgemm")
+       3 * ga.nbytes, 2.0 * 1024 ** 3, cpu_scale=16, note="tcgen05 3xTF32")
+    gA, gB = f(4096, 4096), f(4096, 4096)
+    op("a10", "gemm 4096^3 transB", lambda: K.gemm(gA, gB, None, 1.0, 0.0, False, True, ctx=ctx), lambda: R.gemm(gA[:8], gB, None, 1.0, 0.0, False, True), "tensor_f32",
+       3 * gA.nbytes, 2.0 * 4096 ** 3, cpu_scale=512, note="tcgen05 3xTF32, both operands K-major (TMA)")
     # ---- a11-a13 conv ----
     xc = f(B, d, 271); wd = f(d, 1, 11) * 0.1
     op("a11", "conv1d depthwise k=11 [64,512,271]", lambda: K.conv1d(xc, wd, None, (1,), d, (5, 5), (1,), ctx=ctx), lambda: R.conv1d(xc[:1], wd, None, (1,), d, (5, 5), (1,)), "hbm",
@@ -408,7 +411,7 @@ def run_ops(args):
     x2 = f(8, 64, 160, 160); w2 = f(64, 64, 3, 3) * 0.05; b2 = f(64)
     op("a12", "conv2d_silu 3x3 64->64 @160x160 x8", lambda: K.conv2d_silu(x2, w2, b2, (1, 1), 1, (1, 1, 1, 1), (1, 1), ctx=ctx),
        lambda: R.conv2d(x2[:1, :, :40], w2, b2, (1, 1), 1, (1, 1, 1, 1), (1, 1), 2), "tensor_f32", 2 * x2.nbytes + w2.nbytes, 2.0 * 8 * 64 * 64 * 9 * 160 * 160, cpu_scale=32,
-       note="im2col + CUDA-core sgemm (Yolo26n-seg's largest layer)")
+       note="implicit GEMM on tcgen05 3xTF32, bias + SiLU fused (Yolo26n-seg's largest layer)")
     w11 = f(128, 64, 1, 1) * 0.1
     op("a12", "conv2d 1x1 64->128 @160x160 x8", lambda: K.conv2d(x2, w11, None, (1, 1), 1, (0, 0, 0, 0), (1, 1), 0, ctx=ctx),
        lambda: R.conv2d(x2[:1, :, :40], w11, None, (1, 1), 1, (0, 0, 0, 0), (1, 1), 0), "tensor_f32", x2.nbytes * 3 + w11.nbytes, 2.0 * 8 * 128 * 64 * 160 * 160, cpu_scale=32)

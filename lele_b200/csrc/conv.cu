@@ -6,7 +6,7 @@
 //  * depthwise / grouped / conv1d: direct CUDA-core kernels (HBM-bound).
 //  * conv_transpose: gather form (each output pixel sums its contributing taps) - no
 //    zero-fill + scatter-add round trip.
-#include "common.cuh"
+#include "gemm_tf32_tc.cuh"
 
 int lb_sgemm_strided(lele_b200_ctx* ctx, const float* A, long long rsa, long long csa, long long bsa, const float* B,
                      long long rsb, long long csb, long long bsb, float* C, int batch, int m, int k, int n, float alpha,
@@ -72,6 +72,32 @@ __global__ void im2col_kernel(const float* __restrict__ x, Conv2dGeom g, float* 
         int oy = p / g.ow, ox = p % g.ow;
         int iy = oy * g.sh + ky * g.dh - g.pt, ix = ox * g.sw + kx * g.dw - g.pl;
         col[i] = (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) ? x[((long long)c * g.h + iy) * g.w + ix] : 0.0f;
+    }
+}
+// conv_transpose, step 2: out[n,o,oy,ox] = sum over the taps (ky, kx ascending, as the reference's scatter order) of
+// colm[n][(o*kh+ky)*kw+kx][iy*wd+ix] + bias[o]; colm = W^T X came from the tensor-core GEMM
+__global__ void col2im_gather_kernel(const float* __restrict__ colm, const float* __restrict__ bias, int nb, int h, int wd, int oc, int kh, int kw,
+                                     int pt, int pl, int sh, int sw, int dh, int dw, int oh, int ow, float* __restrict__ out) {
+    const long long total = (long long)nb * oc * oh * ow, hw = (long long)h * wd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
+        const int o = (int)((i / ((long long)ow * oh)) % oc), n = (int)(i / ((long long)ow * oh * oc));
+        float s = 0.0f;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int ty = oy + pt - ky * dh;
+            if (ty < 0 || ty % sh) continue;
+            const int iy = ty / sh;
+            if (iy >= h) continue;
+            for (int kx = 0; kx < kw; ++kx) {
+                const int tx = ox + pl - kx * dw;
+                if (tx < 0 || tx % sw) continue;
+                const int ix = tx / sw;
+                if (ix >= wd) continue;
+                s = __fadd_rn(s, colm[(((long long)n * oc + o) * kh * kw + (long long)ky * kw + kx) * hw + (long long)iy * wd + ix]);
+            }
+        }
+        if (bias) s = __fadd_rn(s, bias[o]);
+        out[i] = s;
     }
 }
 // bias + activation over [planes, hw]; SIMD body = first hw/8*8 of each plane (avx/math.rs:344-470)
@@ -145,12 +171,31 @@ extern "C" int lele_b200_conv2d(lele_b200_ctx* ctx, const float* x, const float*
     const long long hw = (long long)g.oh * g.ow;
     if (nb == 0) return LELE_B200_OK;
     int rc;
+    bool fused_epilogue = false;
+    LbGemmTcEpilogue tep; tep.bias_row = bias; tep.act = act; tep.simd_end = (int)((hw / 8) * 8);
+    const long long kdim = (long long)ic * kh * kw;
+    const bool tc_ok = group == 1 && kdim % 4 == 0 && oc >= 16 && hw >= 64 && kdim >= 16 && hw * kdim * oc >= (1ll << 22) &&
+                       lb_gemm_tc_supported(w, kdim, 0, w, kdim, 0, oc, (int)hw, (int)kdim);
     if (group == 1 && kh == 1 && kw == 1 && g.sh == 1 && g.sw == 1 && pads[0] == 0 && pads[1] == 0 && pads[2] == 0 && pads[3] == 0) {
         // 1x1: out[b] = W[OC,IC] x X[b][IC,HW]
-        rc = lb_sgemm_strided(ctx, w, ic, 1, 0, x, hw, 1, (long long)ic * hw, out, nb, oc, ic, (int)hw, 1.0f, 0);
-        if (rc) return rc;
-    } else if (group == 1 && (long long)ic * kh * kw >= 32) {
-        const long long kdim = (long long)ic * kh * kw;
+        if (tc_ok) {   // tensor cores: the kernel gathers X[b] [IC, HW] as its N-major B operand; bias + activation fused in the epilogue
+            LbGatherB gb; memset(&gb, 0, sizeof(gb));
+            gb.mode = 1; gb.ptr = x; gb.ldk = hw; gb.bs = (long long)ic * hw;
+            if ((rc = lb_gemm_tf32x3_gather(ctx, w, ic, 0, gb, out, hw, (long long)oc * hw, nb, oc, (int)hw, ic, tep))) return rc;
+            fused_epilogue = true;
+        } else {
+            rc = lb_sgemm_strided(ctx, w, ic, 1, 0, x, hw, 1, (long long)ic * hw, out, nb, oc, ic, (int)hw, 1.0f, 0);
+            if (rc) return rc;
+        }
+    } else if (tc_ok) {
+        // implicit GEMM on the tensor cores: out[b] = W[OC,K] . im2col(x[b])[HW,K]^T with the im2col element computed on the
+        // fly by the kernel's operand producers (no col buffer), the whole batch in one launch, bias + activation fused
+        LbGatherB gb; memset(&gb, 0, sizeof(gb));
+        gb.mode = 2; gb.ptr = x; gb.bs = (long long)ic * h * wd; gb.h = h; gb.w = wd; gb.kh = kh; gb.kw = kw; gb.pt = g.pt; gb.pl = g.pl;
+        gb.sh = g.sh; gb.sw = g.sw; gb.dh = g.dh; gb.dw = g.dw; gb.ow = g.ow;
+        if ((rc = lb_gemm_tf32x3_gather(ctx, w, kdim, 0, gb, out, hw, (long long)oc * hw, nb, oc, (int)hw, (int)kdim, tep))) return rc;
+        fused_epilogue = true;
+    } else if (group == 1 && kdim >= 32) {
         void* col;
         if ((rc = lb_scratch(ctx, sizeof(float) * (size_t)kdim * hw, &col))) return rc;
         for (int b = 0; b < nb; ++b) {
@@ -163,6 +208,7 @@ extern "C" int lele_b200_conv2d(lele_b200_ctx* ctx, const float* x, const float*
         conv2d_direct_kernel<<<grid_for((long long)nb * oc * hw), 256, 0, ctx->stream>>>(x, w, nb, g, out);
         LB_LAUNCH_CHECK(ctx);
     }
+    if (fused_epilogue) return LELE_B200_OK;
     if (bias || act) {
         bias_act_kernel<<<grid_for((long long)nb * oc * hw), 256, 0, ctx->stream>>>(out, (long long)nb * oc, oc, hw, bias, act);
         LB_LAUNCH_CHECK(ctx);
@@ -179,6 +225,23 @@ extern "C" int lele_b200_conv_transpose(lele_b200_ctx* ctx, const float* x, cons
     LB_REQUIRE(oh > 0 && ow > 0, "conv_transpose: output dimensions must be positive, got out_h=%d out_w=%d (conv2d.rs:3025)", oh, ow);
     long long total = (long long)nb * oc * oh * ow;
     if (total == 0) return LELE_B200_OK;
+    const long long hw = (long long)h * wd; const int mk = oc * kh * kw;
+    if (ic % 4 == 0 && ic >= 16 && mk >= 16 && hw >= 64 && hw * ic * mk >= (1ll << 22) && lb_gemm_tc_supported(x, ic, 0, x, ic, 0, mk, (int)hw, ic)) {
+        // the reference's own structure (conv2d.rs:3069-3128): col = W^T X as a GEMM -- here on the tensor cores -- then the
+        // scatter-add, done as a gather per output element in the same tap order
+        void* sc; int rc;
+        const size_t n_wt = (size_t)mk * ic, n_col = (size_t)nb * mk * hw;
+        if ((rc = lb_scratch(ctx, sizeof(float) * (n_wt + n_col) + 512, &sc))) return rc;
+        float* wt = (float*)sc; float* colm = wt + (n_wt + 63) / 64 * 64;
+        if ((rc = lb_transpose_f32(ctx, w, mk, 0, wt, ic, 0, 1, ic, mk))) return rc;       // W [ic, oc*kh*kw] -> [oc*kh*kw, ic] (K-major A operand)
+        LbGatherB gb; memset(&gb, 0, sizeof(gb));
+        gb.mode = 1; gb.ptr = x; gb.ldk = hw; gb.bs = (long long)ic * hw;                    // X[b] [ic, hw] gathered as the N-major B operand
+        LbGemmTcEpilogue tep;
+        if ((rc = lb_gemm_tf32x3_gather(ctx, wt, ic, 0, gb, colm, hw, (long long)mk * hw, nb, mk, (int)hw, ic, tep))) return rc;
+        col2im_gather_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(colm, bias, nb, h, wd, oc, kh, kw, pads[0], pads[1], strides[0], strides[1], dils[0], dils[1], oh, ow, out);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
+    }
     conv_transpose_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(x, w, bias, nb, ic, h, wd, oc, kh, kw, pads[0], pads[1], strides[0],
                                                                    strides[1], dils[0], dils[1], oh, ow, out);
     LB_LAUNCH_CHECK(ctx);

@@ -2,7 +2,7 @@
 // Upstream arithmetic is faer 0.24 (un-vendored); the reference's own tests pin this boundary
 // to 1e-5..1e-3 abs, i.e. any correctly-rounded-ish f32 GEMM.  CUDA cores, fp32 FMA,
 // 64x64x16 shared-memory tiles, 4x4 register blocking; strides make transposes free.
-#include "common.cuh"
+#include "gemm_tf32_tc.cuh"
 
 namespace {
 constexpr int TM = 64, TN = 64, TK = 16;
@@ -117,14 +117,46 @@ int lb_sgemm_strided_ldc(lele_b200_ctx* ctx, const float* A, long long rsa, long
     return launch_sgemm(ctx, A, rsa, csa, bsa, B, rsb, csb, bsb, C, batch, m, k, n, alpha, 0, bsc, ldc);
 }
 
+
+// Tensor-core dispatch (gemm_tf32_tc.cu): op(A) [m,k] and op(B)^T [n,k] must be K-major; operands stored the other way
+// round are transposed into the context scratch first (one extra pass over that operand).  Small problems and
+// operands TMA cannot address (k % 4 != 0, unaligned) stay on the CUDA-core kernel.
+//   a_kmajor: A stored [m,k] (else [k,m]);  b_nmajor: B stored [k,n] (else [n,k])
+static bool tc_worthwhile(int batch, int m, int k, int n) {
+    return (long long)batch * m * n * k >= (1ll << 22) && k >= 16 && n >= 16 && m >= 16;
+}
+static int gemm_tc_or_simt(lele_b200_ctx* ctx, const float* a, bool a_kmajor, long long bsa, const float* b, bool b_nmajor, long long bsb,
+                           float* c, int batch, int m, int k, int n, float alpha, int pre_mode) {
+    const bool tc = tc_worthwhile(batch, m, k, n) && k % 4 == 0 && ((long long)m * k) % 4 == 0 && lb_gemm_tc_supported(a, k, 0, a, k, 0, m, n, k) &&
+                    (b_nmajor || (((long long)n * k) % 4 == 0 && (((uintptr_t)b) & 15) == 0));
+    if (tc) {
+        const float* A = a;
+        long long bsA = bsa;
+        if (!a_kmajor) {   // stored [k, m] -> [m, k] (one transposing pass into the context scratch; rare: gemm with transA)
+            const int nba = bsa ? batch : 1;
+            void* sc; int rc = lb_scratch(ctx, sizeof(float) * (size_t)nba * m * k, &sc);
+            if (rc) return rc;
+            if ((rc = lb_transpose_f32(ctx, a, m, bsa, (float*)sc, k, (long long)m * k, nba, k, m))) return rc;
+            A = (const float*)sc; bsA = bsa ? (long long)m * k : 0;
+        }
+        LbGemmTcEpilogue ep; ep.alpha = alpha; ep.pre_mode = pre_mode;
+        if (b_nmajor) {    // [k, n]: gathered by the kernel itself (no transpose pass)
+            LbGatherB gb; memset(&gb, 0, sizeof(gb));
+            gb.mode = 1; gb.ptr = b; gb.ldk = n; gb.bs = bsb;
+            return lb_gemm_tf32x3_gather(ctx, A, k, bsA, gb, c, n, (long long)m * n, batch, m, n, k, ep);
+        }
+        return lb_gemm_tf32x3_nt(ctx, A, k, bsA, b, k, bsb, c, n, (long long)m * n, batch, m, n, k, ep);
+    }
+    return launch_sgemm(ctx, a, a_kmajor ? k : 1, a_kmajor ? 1 : m, bsa, b, b_nmajor ? n : 1, b_nmajor ? 1 : k, bsb, c, batch, m, k, n, alpha, pre_mode);
+}
+
 extern "C" int lele_b200_matmul(lele_b200_ctx* ctx, const float* a, const float* b, int batch_a, int batch_b, int m, int k,
                                 int n, float* out) {
     LB_REQUIRE(ctx && a && b && out, "matmul: NULL argument");
     LB_REQUIRE(batch_a >= 1 && batch_b >= 1 && (batch_a == batch_b || batch_a == 1 || batch_b == 1),
                "matmul: batch mismatch %d vs %d (gemm.rs:134)", batch_a, batch_b);
     int fb = batch_a > batch_b ? batch_a : batch_b;
-    return launch_sgemm(ctx, a, k, 1, batch_a == 1 ? 0 : (long long)m * k, b, n, 1, batch_b == 1 ? 0 : (long long)k * n, out,
-                        fb, m, k, n, 1.0f, 0);
+    return gemm_tc_or_simt(ctx, a, true, batch_a == 1 ? 0 : (long long)m * k, b, true, batch_b == 1 ? 0 : (long long)k * n, out, fb, m, k, n, 1.0f, 0);
 }
 
 extern "C" int lele_b200_matmul_fused_add(lele_b200_ctx* ctx, const float* a, const float* b, const float* bias, int bias_len,
@@ -136,11 +168,9 @@ extern "C" int lele_b200_matmul_fused_add(lele_b200_ctx* ctx, const float* a, co
     if (bias_len == n) {  // pre-fill rows with bias, then accumulate (gemm.rs:247-330)
         fill_rows_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(out, (long long)fb * m, n, bias);
         LB_LAUNCH_CHECK(ctx);
-        return launch_sgemm(ctx, a, k, 1, batch_a == 1 ? 0 : (long long)m * k, b, n, 1, batch_b == 1 ? 0 : (long long)k * n,
-                            out, fb, m, k, n, 1.0f, 1);
+        return gemm_tc_or_simt(ctx, a, true, batch_a == 1 ? 0 : (long long)m * k, b, true, batch_b == 1 ? 0 : (long long)k * n, out, fb, m, k, n, 1.0f, 1);
     }
-    int rc = launch_sgemm(ctx, a, k, 1, batch_a == 1 ? 0 : (long long)m * k, b, n, 1, batch_b == 1 ? 0 : (long long)k * n, out,
-                          fb, m, k, n, 1.0f, 0);
+    int rc = gemm_tc_or_simt(ctx, a, true, batch_a == 1 ? 0 : (long long)m * k, b, true, batch_b == 1 ? 0 : (long long)k * n, out, fb, m, k, n, 1.0f, 0);
     if (rc) return rc;
     add_mod_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(out, total, bias, bias_len);
     LB_LAUNCH_CHECK(ctx);
@@ -153,6 +183,5 @@ extern "C" int lele_b200_gemm(lele_b200_ctx* ctx, const float* a, const float* b
     if ((long long)m * n == 0) return LELE_B200_OK;
     gemm_prefill_kernel<<<grid_for((long long)m * n), 256, 0, ctx->stream>>>(out, m, n, c, c_len, beta);
     LB_LAUNCH_CHECK(ctx);
-    return launch_sgemm(ctx, a, trans_a ? 1 : k, trans_a ? m : 1, 0, b, trans_b ? 1 : n, trans_b ? k : 1, 0, out, 1, m, k, n,
-                        alpha, 1);
+    return gemm_tc_or_simt(ctx, a, !trans_a, 0, b, !trans_b, 0, out, 1, m, k, n, alpha, 1);
 }

@@ -175,6 +175,42 @@ def test_matmul_family():
                 close(G.gemm(A, B, cc, 0.5, 2.0, ta, tb), R.gemm(A, B, cc, 0.5, 2.0, ta, tb), atol_frac=1e-5)
 
 
+def test_tensor_core_f32_gemm_paths():
+    """Shapes large enough for the tcgen05 3xTF32 path (csrc/gemm_tf32_tc.cu): M/N/K tails (TMA zero fill), K not a
+    multiple of the 32-float chunk, batch + broadcast operands, transposed operands (pre-transposing pass), alpha /
+    beta*C / bias pre-fill, im2col / 1x1 / conv_transpose lowering with the fused bias + activation epilogue.
+    Bar: 2e-5 of the output magnitude vs the oracle (3xTF32 is ~2^-21 per product; required: 1e-4), and the same vs float64."""
+    rng = np.random.default_rng(50)
+    for (ba, bb, m, k, n) in [(1, 1, 300, 260, 200), (6, 6, 271, 128, 271), (5, 1, 130, 36, 129), (1, 4, 64, 512, 96), (2, 2, 257, 2048, 64)]:
+        a = rng.standard_normal((ba, m, k) if ba > 1 else (m, k)).astype(np.float32)
+        b = rng.standard_normal((bb, k, n) if bb > 1 else (k, n)).astype(np.float32)
+        got = G.matmul(a, b)
+        close(got, R.matmul(a, b), rtol=2e-5, atol_frac=2e-5)
+        close(got, (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32), rtol=2e-5, atol_frac=2e-5)
+    a = rng.standard_normal((200, 320)).astype(np.float32); b = rng.standard_normal((320, 144)).astype(np.float32)
+    bias = rng.standard_normal(144).astype(np.float32)
+    close(G.matmul_fused_add(a, b, bias), R.matmul_fused_add(a, b, bias), rtol=2e-5, atol_frac=2e-5)
+    for ta in (False, True):
+        for tb in (False, True):
+            A = a.T.copy() if ta else a; B = b.T.copy() if tb else b
+            for c in (None, rng.standard_normal(144).astype(np.float32), rng.standard_normal(200 * 144).astype(np.float32)):
+                close(G.gemm(A, B, c, 0.5, 2.0, ta, tb), R.gemm(A, B, c, 0.5, 2.0, ta, tb), rtol=2e-5, atol_frac=2e-5)
+    # conv2d: im2col lowering (3x3, strides, dilation), 1x1 lowering, OC below / above one 128-row tile, all activations
+    for (ic, oc, k, s, p, d, hh, ww) in [(16, 32, 3, 1, 1, 1, 40, 44), (64, 64, 3, 1, 1, 1, 24, 24), (32, 160, 3, 2, 1, 1, 33, 31), (16, 24, 3, 1, 2, 2, 30, 30),
+                                          (64, 128, 1, 1, 0, 1, 40, 40), (48, 200, 1, 1, 0, 1, 19, 23)]:
+        x = rng.standard_normal((2, ic, hh, ww)).astype(np.float32)
+        w = (rng.standard_normal((oc, ic, k, k)) / np.sqrt(ic * k * k)).astype(np.float32)
+        b = rng.standard_normal(oc).astype(np.float32)
+        for act in (0, 1, 2):
+            close(G.conv2d(x, w, b, (d, d), 1, (p, p, p, p), (s, s), act), R.conv2d(x, w, b, (d, d), 1, (p, p, p, p), (s, s), act), rtol=2e-5, atol_frac=2e-5)
+        close(G.conv2d(x, w, None, (d, d), 1, (p, p, p, p), (s, s), 0), R.conv2d(x, w, None, (d, d), 1, (p, p, p, p), (s, s), 0), rtol=2e-5, atol_frac=2e-5)
+    # conv_transpose: k = stride (Yolo), overlapping taps with padding
+    for (ic, oc, k, s, p, hh, ww) in [(64, 64, 2, 2, 0, 40, 40), (32, 16, 3, 2, 1, 21, 26), (16, 8, 4, 1, 1, 30, 31)]:
+        x = rng.standard_normal((2, ic, hh, ww)).astype(np.float32); w = (rng.standard_normal((ic, oc, k, k)) / np.sqrt(ic)).astype(np.float32)
+        b = rng.standard_normal(oc).astype(np.float32)
+        close(G.conv_transpose(x, w, b, (1, 1), (p, p, p, p), (s, s)), R.conv_transpose(x, w, b, (1, 1), (p, p, p, p), (s, s)), rtol=2e-5, atol_frac=2e-5)
+
+
 def test_convs():
     rng = np.random.default_rng(6)
     for (ic, oc, k, s, p, g, d) in [(3, 8, 3, 1, 1, 1, 1), (4, 8, 3, 2, 1, 1, 1), (4, 4, 3, 1, 1, 4, 1), (64, 64, 3, 1, 1, 64, 1), (8, 16, 1, 1, 0, 1, 1), (16, 32, 3, 1, 2, 1, 2), (6, 4, 3, 1, 1, 2, 1)]:
