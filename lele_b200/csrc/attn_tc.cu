@@ -37,9 +37,15 @@ constexpr int STAGE_A = 2 * TILE_Q + 2 * TILE_K;   // 104 KB
 constexpr int NSTAGE_A = 2;
 constexpr int TILE_P = AQ * 128;      // 16 KB
 constexpr int TILE_V = DK * 128;      // 16 KB  [128 dims][32 keys]
-constexpr int STAGE_C = 2 * TILE_P + 2 * TILE_V;   // 64 KB
-constexpr int NSTAGE_C = 3;
-constexpr int SMEM_MAIN = NSTAGE_A * STAGE_A;      // 208 KB (>= NSTAGE_C * STAGE_C = 192 KB)
+// phase C (reuses the phase-A memory): a 4-slot V ring (raw + lo, 32 KB per slot) at [0, 128 KB) and a 2-slot P ring
+// (hi + lo, 32 KB per slot) at [128 KB, 192 KB).  V slots 0-2 lie inside phase-A stage 0, which is free once the MMAs of
+// k-chunk 2 retired, so the first three V chunks are fetched (and split) under the last k-chunk's MMAs; the V chain
+// (TMA latency -> lo split -> 12 MMAs -> slot free) is the steady-state limiter of this phase, hence 4 slots for V and 2 for P.
+constexpr int NSLOT_V = 4, NSLOT_P = 2, V_EARLY = 3;
+constexpr int SLOT_V = 2 * TILE_V, SLOT_P = 2 * TILE_P;
+constexpr int P_BASE = NSLOT_V * SLOT_V;           // 128 KB
+constexpr int SMEM_MAIN = NSTAGE_A * STAGE_A;      // 208 KB (>= P_BASE + NSLOT_P * SLOT_P = 192 KB)
+static_assert(V_EARLY * SLOT_V <= STAGE_A && P_BASE + NSLOT_P * SLOT_P <= SMEM_MAIN, "phase-C layout");
 constexpr int MAX_KCHUNKS = 2 * NH / KC;           // 9
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = SMEM_MAIN + 1024 + BAR_BYTES + 8 * 128 * 4;   // + barriers + row max / row sum exchange
@@ -236,17 +242,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 tma_load_4d(st + 2 * TILE_Q, &map_kh, &full_a[s], kc * KC, h, 0, b);
                 tma_load_4d(st + 2 * TILE_Q + NH * 128, &map_kh, &full_a[s], kc * KC, h, NH, b);
             }
-            // phase C reuses the same shared memory.  V chunk 0 lands in [32 KB, 64 KB) = the K tile of phase-A stage 0,
-            // which is free once the MMAs of k-chunk 2 retired (second completion of empty_a[0]): it is fetched (and its
-            // lo tile made) under the last k-chunk's MMAs; everything else waits until every phase-A MMA has retired.
+            // phase C reuses the same shared memory (layout above): V chunks 0..2 as soon as phase-A stage 0 is free
+            // (second completion of empty_a[0]), chunk 3 once every phase-A MMA has retired, later chunks as slots free up
             for (int c = 0; c < NKC; ++c) {
-                const int s = c % NSTAGE_C;
                 if (c == 0) mbar_wait(&empty_a[0], 1);
-                if (c == 1) mbar_wait(s_full, 0);
-                if (c >= NSTAGE_C) mbar_wait(&pv_done[c - NSTAGE_C], 0);
-                uint8_t* st = smem + s * STAGE_C;
+                if (c == V_EARLY) mbar_wait(s_full, 0);
+                if (c >= NSLOT_V) mbar_wait(&pv_done[c - NSLOT_V], 0);
+                uint8_t* vs = smem + (c % NSLOT_V) * SLOT_V;
                 mbar_expect_tx(&v_full[c], TILE_V);
-                tma_load_4d(st + 2 * TILE_P, &map_vh, &v_full[c], c * KC, 0, h, b);
+                tma_load_4d(vs, &map_vh, &v_full[c], c * KC, 0, h, b);
             }
         }
     } else if (warp == 1) {
@@ -289,13 +293,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 if (kc == DK / KC - 1) umma_commit(s_full);
             }
             for (int c = 0; c < NKC; ++c) {
-                const int s = c % NSTAGE_C;
                 mbar_wait(&vl_full[c], 0);                       // V chunk landed and its lo tile is written
                 mbar_wait(&p_full[c], 0);
                 tc_fence_after();
-                const uint32_t base = smem_u32(smem + s * STAGE_C);
-                const uint64_t phd = make_smem_desc(base), pld = make_smem_desc(base + TILE_P);
-                const uint64_t vhd = make_smem_desc(base + 2 * TILE_P), vld = make_smem_desc(base + 2 * TILE_P + TILE_V);
+                const uint32_t pb = smem_u32(smem + P_BASE + (c % NSLOT_P) * SLOT_P), vb = smem_u32(smem + (c % NSLOT_V) * SLOT_V);
+                const uint64_t phd = make_smem_desc(pb), pld = make_smem_desc(pb + TILE_P);
+                const uint64_t vhd = make_smem_desc(vb), vld = make_smem_desc(vb + TILE_V);
                 const uint32_t dO = tmem_base + (uint32_t)O_COL;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -312,9 +315,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         // ===================== warps 2, 3: lo(V^T) chunks, 64 threads x 16 float4 per 16 KB chunk =====================
         const int t64 = (warp - 2) * 32 + lane;
         for (int c = 0; c < NKC; ++c) {
-            const int s = c % NSTAGE_C;
             mbar_wait(&v_full[c], 0);
-            const uint32_t vh = smem_u32(smem + s * STAGE_C + 2 * TILE_P);
+            const uint32_t vh = smem_u32(smem + (c % NSLOT_V) * SLOT_V);
 #pragma unroll 4
             for (int i = t64; i < TILE_V / 16; i += 64) lo_convert_16B(vh + (uint32_t)i * 16u, vh + (uint32_t)TILE_V + (uint32_t)i * 16u);
             fence_proxy_async();
@@ -374,7 +376,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         const float nmx = -__fmul_rn(mx, L2E);
         float psum = 0.0f;
         for (int c = grp; c < NKC; c += NGRP) {
-            const int s = c % NSTAGE_C;
             uint32_t v[32];
             tmem_ld32(trow + (uint32_t)(c * KC), v);
             float e[32];
@@ -394,8 +395,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 for (int i = 0; i < 8; ++i) t8[i] = (e[i] + e[i + 8]) + (e[i + 16] + e[i + 24]);
                 psum += ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
             }
-            if (c >= NSTAGE_C) mbar_wait(&pv_done[c - NSTAGE_C], 0);
-            const uint32_t ph_row = smem_u32(smem + s * STAGE_C) + (uint32_t)r * 128u;
+            if (c >= NSLOT_P) mbar_wait(&pv_done[c - NSLOT_P], 0);
+            const uint32_t ph_row = smem_u32(smem + P_BASE + (c % NSLOT_P) * SLOT_P) + (uint32_t)r * 128u;
             const uint32_t pl_row = ph_row + TILE_P;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
