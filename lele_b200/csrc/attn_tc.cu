@@ -8,8 +8,9 @@
 //                      i.e. f32-grade; plain TF32 would be 2^-11 and miss the 1e-4 bar)
 //   P = exp(S - max)   8 softmax warps read S from TMEM (two threads per query row, even / odd 32-key
 //                      chunks), same polynomial exp / libm tail split as the CPU reference
-//   O = P V            P is written to shared memory as the tf32 hi/lo A-operand, 32 keys at a time,
-//                      while the MMA warp consumes the previous chunk; O accumulates in TMEM
+//   O = P V            P goes back into TENSOR MEMORY as the tf32 hi/lo A operand (hi in place of its S chunk,
+//                      lo in a 3-slot ring), 32 keys at a time, while the MMA warp consumes the previous chunks
+//                      (tcgen05.mma with A in TMEM); O accumulates in TMEM
 //   out = O / sum      + fused per-clip min/max (feeds the next dynamic quantiser)
 //
 // The [h,T,T] score / probability tensors never touch HBM (the reference materialises both).
@@ -37,15 +38,17 @@ constexpr int STAGE_A = 2 * TILE_Q + 2 * TILE_K;   // 104 KB
 constexpr int NSTAGE_A = 2;
 constexpr int TILE_P = AQ * 128;      // 16 KB
 constexpr int TILE_V = DK * 128;      // 16 KB  [128 dims][32 keys]
-// phase C (reuses the phase-A memory): a 4-slot V ring (raw + lo, 32 KB per slot) at [0, 128 KB) and a 2-slot P ring
-// (hi + lo, 32 KB per slot) at [128 KB, 192 KB).  V slots 0-2 lie inside phase-A stage 0, which is free once the MMAs of
-// k-chunk 2 retired, so the first three V chunks are fetched (and split) under the last k-chunk's MMAs; the V chain
-// (TMA latency -> lo split -> 12 MMAs -> slot free) is the steady-state limiter of this phase, hence 4 slots for V and 2 for P.
-constexpr int NSLOT_V = 4, NSLOT_P = 2, V_EARLY = 3;
-constexpr int SLOT_V = 2 * TILE_V, SLOT_P = 2 * TILE_P;
-constexpr int P_BASE = NSLOT_V * SLOT_V;           // 128 KB
-constexpr int SMEM_MAIN = NSTAGE_A * STAGE_A;      // 208 KB (>= P_BASE + NSLOT_P * SLOT_P = 192 KB)
-static_assert(V_EARLY * SLOT_V <= STAGE_A && P_BASE + NSLOT_P * SLOT_P <= SMEM_MAIN, "phase-C layout");
+// phase C (reuses the phase-A memory): a 6-slot V ring (raw + lo, 32 KB per slot).  P never touches shared memory: the
+// softmax warps write it back into TENSOR MEMORY -- hi(P) in place of the S chunk it was computed from, lo(P) into a 3-slot
+// ring in the 96 spare columns -- and the P.V products read their A operand from TMEM (tcgen05.mma, A in TMEM).  Both
+// phases of this kernel are bound by shared-memory bandwidth (128 B/clk/SM: operand reads of the MMAs + TMA writes +
+// the lo splits); this removes 80 of the 176 KB per 32-key chunk that phase C moved through shared memory.
+// V slots 0-2 lie inside phase-A stage 0, which is free once the MMAs of k-chunk 2 retired, so the first three V chunks
+// are fetched (and split) under the last k-chunk's MMAs.
+constexpr int NSLOT_V = 6, V_EARLY = 3, NSLOT_PL = 3;
+constexpr int SLOT_V = 2 * TILE_V;
+constexpr int SMEM_MAIN = NSTAGE_A * STAGE_A;      // 208 KB (>= NSLOT_V * SLOT_V = 192 KB)
+static_assert(V_EARLY * SLOT_V <= STAGE_A && NSLOT_V * SLOT_V <= SMEM_MAIN, "phase-C layout");
 constexpr int MAX_KCHUNKS = 2 * NH / KC;           // 9
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = SMEM_MAIN + 1024 + BAR_BYTES + 8 * 128 * 4;   // + barriers + row max / row sum exchange
@@ -53,6 +56,8 @@ constexpr int NGRP = 4;            // softmax groups (4 warps each)
 constexpr int NUM_THREADS = 128 + NGRP * 128;   // TMA, MMA, TMEM-alloc, spare + 16 softmax/epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int O_COL = 2 * NH;         // O accumulator starts at TMEM column 288
+constexpr int PL_COL = O_COL + DK;    // lo(P) ring: columns 416..511
+static_assert(PL_COL + NSLOT_PL * KC <= TMEM_COLS, "TMEM layout");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -109,6 +114,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -202,6 +226,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ long long dbg_t[20][8];
+    __shared__ long long dbg_c[4][5];          // group-0 warp: per p2 chunk {start, after tmem ld, after exp, after slot wait, after store}
     const int qt = blockIdx.x % args.n_qtiles;
     const int bh = blockIdx.x / args.n_qtiles;
     const int h = bh % args.H, b = bh / args.H;
@@ -294,18 +319,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
             }
             for (int c = 0; c < NKC; ++c) {
                 mbar_wait(&vl_full[c], 0);                       // V chunk landed and its lo tile is written
-                mbar_wait(&p_full[c], 0);
+                mbar_wait(&p_full[c], 0);                        // hi(P) / lo(P) of the chunk are in tensor memory
                 tc_fence_after();
-                const uint32_t pb = smem_u32(smem + P_BASE + (c % NSLOT_P) * SLOT_P), vb = smem_u32(smem + (c % NSLOT_V) * SLOT_V);
-                const uint64_t phd = make_smem_desc(pb), pld = make_smem_desc(pb + TILE_P);
+                const uint32_t vb = smem_u32(smem + (c % NSLOT_V) * SLOT_V);
                 const uint64_t vhd = make_smem_desc(vb), vld = make_smem_desc(vb + TILE_V);
+                const uint32_t a_hi = tmem_base + (uint32_t)(c * KC);                       // in place of S chunk c
+                const uint32_t a_lo = tmem_base + (uint32_t)(PL_COL + (c % NSLOT_PL) * KC);
                 const uint32_t dO = tmem_base + (uint32_t)O_COL;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t ko = (uint64_t)(k * 2);
-                    umma_tf32(dO, phd + ko, vhd + ko, ID_O, (c == 0 && k == 0) ? 0u : 1u);
-                    umma_tf32(dO, phd + ko, vld + ko, ID_O, 1u);
-                    umma_tf32(dO, pld + ko, vhd + ko, ID_O, 1u);
+                    umma_tf32_ts(dO, a_hi + (uint32_t)(k * 8), vhd + ko, ID_O, (c == 0 && k == 0) ? 0u : 1u);
+                    umma_tf32_ts(dO, a_hi + (uint32_t)(k * 8), vld + ko, ID_O, 1u);
+                    umma_tf32_ts(dO, a_lo + (uint32_t)(k * 8), vhd + ko, ID_O, 1u);
                 }
                 umma_commit(&pv_done[c]);
                 if (c == NKC - 1) umma_commit(o_full);
@@ -371,13 +397,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         ATT_DBG(4);
         // ---- pass 2: e = exp(s - max) = 2^((s - max) * log2 e): one FFMA + one MUFU.EX2 per element (ex2.approx is
         //      accurate to ~2^-22 relative, the same class as the reference's degree-7 polynomial), then the tf32
-        //      hi/lo split into the swizzled K-major P tiles ----
+        //      hi/lo split, stored to tensor memory (tcgen05.st) as the A operand of P.V ----
         const float L2E = args.scale_l2e;               // scores are unscaled: exp((s - max) * scale) = 2^((s - max) * scale * log2 e)
         const float nmx = -__fmul_rn(mx, L2E);
         float psum = 0.0f;
         for (int c = grp; c < NKC; c += NGRP) {
+            const bool dbgw = args.dbg && warp == 4 && lane == 0;
+            if (dbgw) dbg_c[c / NGRP][0] = clock64();
             uint32_t v[32];
             tmem_ld32(trow + (uint32_t)(c * KC), v);
+            if (dbgw) dbg_c[c / NGRP][1] = clock64();
             float e[32];
             if (c * KC + 32 <= T) {                       // warp-uniform fast path: full chunk
 #pragma unroll
@@ -395,19 +424,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 for (int i = 0; i < 8; ++i) t8[i] = (e[i] + e[i + 8]) + (e[i + 16] + e[i + 24]);
                 psum += ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
             }
-            if (c >= NSLOT_P) mbar_wait(&pv_done[c - NSLOT_P], 0);
-            const uint32_t ph_row = smem_u32(smem + P_BASE + (c % NSLOT_P) * SLOT_P) + (uint32_t)r * 128u;
-            const uint32_t pl_row = ph_row + TILE_P;
+            if (dbgw) dbg_c[c / NGRP][2] = clock64();
+            uint32_t lo[32];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint32_t phys = (uint32_t)((q ^ (r & 7)) << 4);      // 16-byte chunk XOR (row % 8)
-                const float h0 = tf32_hi(e[q * 4 + 0]), h1 = tf32_hi(e[q * 4 + 1]), h2 = tf32_hi(e[q * 4 + 2]), h3 = tf32_hi(e[q * 4 + 3]);
-                sts_v4f(ph_row + phys, h0, h1, h2, h3);
-                sts_v4f(pl_row + phys, __fsub_rn(e[q * 4 + 0], h0), __fsub_rn(e[q * 4 + 1], h1), __fsub_rn(e[q * 4 + 2], h2), __fsub_rn(e[q * 4 + 3], h3));
+            for (int i = 0; i < 32; ++i) {
+                const float hi = tf32_hi(e[i]);
+                lo[i] = __float_as_uint(__fsub_rn(e[i], hi));
+                v[i] = __float_as_uint(hi);
             }
-            fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core (async proxy)
+            tmem_st32(trow + (uint32_t)(c * KC), v);              // hi(P) over the S chunk this warp just consumed
+            if (c >= NSLOT_PL) mbar_wait(&pv_done[c - NSLOT_PL], 0);   // the lo slot's previous user has been multiplied
+            if (dbgw) dbg_c[c / NGRP][3] = clock64();
+            tmem_st32(trow + (uint32_t)(PL_COL + (c % NSLOT_PL) * KC), lo);
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[c]);
+            if (dbgw) dbg_c[c / NGRP][4] = clock64();
         }
         ATT_DBG(5);
         // exchange the partial row sums (xch was last read before every thread passed the first named barrier +
@@ -458,8 +491,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         printf("ATTDBG blk %d A0 %lld A3 %lld | S_done %lld p1 %lld p2 %lld/%lld O_done %lld epi %lld/%lld end %lld\n", blockIdx.x, dbg_t[1][1] - t0,
                dbg_t[1][2] - t0, dbg_t[4][3] - t0, dbg_t[4][4] - t0, dbg_t[4][5] - t0, dbg_t[8][5] - t0, dbg_t[4][6] - t0, dbg_t[4][7] - t0,
                dbg_t[8][7] - t0, clock64() - t0);
+        for (int i = 0; i < 3; ++i)
+            printf("ATTDBG blk %d p2 chunk %d: start %lld ld %lld exp %lld slot %lld stored %lld\n", blockIdx.x, i * NGRP, dbg_c[i][0] - t0, dbg_c[i][1] - t0, dbg_c[i][2] - t0,
+                   dbg_c[i][3] - t0, dbg_c[i][4] - t0);
     }
 }
+
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -542,6 +579,11 @@ void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float**
 // qkv [B*T, 3d] -> att [B*T, d]; optional fused per-clip min/max keys [B][2].
 // operands_ready != 0: the QKV projection's epilogue already wrote V^T into `scratch`
 // (gemm_i8_tc.cu EPI_QKV); otherwise the transposing pre-pass runs here.
+// Note on the last q-tile: T' = 275 = 2 x 128 + 19, so a third of the CTAs work on 7 % of the rows.  Moving those rows to a
+// CUDA-core kernel on the side stream (reference-order f32, bit-identical to the oracle) was built and measured: the
+// tensor-core kernel drops from 6 to 4 CTA rounds, but the SIMT kernel (latency-bound at 1-2 CTAs per SM, and its CTAs
+// block whole SMs the 219 KB tensor-core CTAs need) cost more than it saved (3.36 -> 3.84 ms on the 8-layer stack), so
+// every tile stays on the tensor cores.
 int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, int H, float qscale, void* scratch, float* att,
                     unsigned* minmax_keys, int operands_ready) {
     LB_REQUIRE(lb_attention_tc_supported(T, d, H), "attention_tc: unsupported geometry T=%d d=%d H=%d", T, d, H);
