@@ -192,6 +192,11 @@ int lele_b200_topk(lele_b200_ctx* ctx, const float* x, long long outer, int n, i
                    float* indices);
 /* argmax over the last axis; ties -> LAST index (Iterator::max_by, sensevoice tokenizer.rs:55) */
 int lele_b200_argmax_last(lele_b200_ctx* ctx, const float* x, long long outer, int n, int32_t* out);
+/* greedy decode filter (examples/sensevoice/src/tokenizer.rs:37-75): per clip keep, in frame order,
+ * the ids that are neither blank (0) nor flagged in skip_mask[vocab] (the "<|...|>" special tokens; NULL = none);
+ * out_ids [n_clips, t] is padded with -1, out_len [n_clips] holds the kept counts.  All pointers are device pointers. */
+int lele_b200_greedy_filter(lele_b200_ctx* ctx, const int32_t* ids, int n_clips, int t, const uint8_t* skip_mask,
+                            int vocab, int32_t* out_ids, int32_t* out_len);
 
 /* ---- SenseVoice-shaped graph runner: the batched replay of the model.rs call sequence
  *      (examples/sensevoice/src/main.rs:73-140) with the weights blob resident in HBM ---- */

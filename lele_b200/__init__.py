@@ -14,3 +14,4 @@ from ._lib import LeleB200Error, SO_PATH, lib  # noqa: F401  (fails loudly when 
 from . import features, kernels  # noqa: F401
 from .sensevoice import SenseVoice  # noqa: F401
 from .kernels import Context, default_context  # noqa: F401
+from .tokenizer import Tokenizer  # noqa: F401

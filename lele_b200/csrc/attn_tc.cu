@@ -580,7 +580,7 @@ void lb_attention_tc_operands(void* scratch, int B, int T, int d, int H, float**
 // operands_ready != 0: the QKV projection's epilogue already wrote V^T into `scratch`
 // (gemm_i8_tc.cu EPI_QKV); otherwise the transposing pre-pass runs here.
 // Note on the last q-tile: T' = 275 = 2 x 128 + 19, so a third of the CTAs work on 7 % of the rows.  Moving those rows to a
-// CUDA-core kernel on the side stream (reference-order f32, bit-identical to the oracle) was built and measured: the
+// CUDA-core kernel on the side stream (reference-order f32) was built and measured: the
 // tensor-core kernel drops from 6 to 4 CTA rounds, but the SIMT kernel (latency-bound at 1-2 CTAs per SM, and its CTAs
 // block whole SMs the 219 KB tensor-core CTAs need) cost more than it saved (3.36 -> 3.84 ms on the 8-layer stack), so
 // every tile stays on the tensor cores.

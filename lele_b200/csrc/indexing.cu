@@ -285,6 +285,36 @@ extern "C" int lele_b200_topk(lele_b200_ctx* ctx, const float* x, long long oute
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }
+// Greedy decode filter (examples/sensevoice/src/tokenizer.rs:37-75): per clip, keep the frame ids that are neither blank
+// (id 0) nor flagged in skip_mask (the "<|...|>" special tokens), in frame order.  One warp per clip, ballot compaction.
+__global__ void __launch_bounds__(32)
+greedy_filter_kernel(const int32_t* __restrict__ ids, int t, const uint8_t* __restrict__ skip_mask, int vocab, int32_t* __restrict__ out_ids,
+                     int32_t* __restrict__ out_len) {
+    const int clip = blockIdx.x, lane = threadIdx.x;
+    const int32_t* in = ids + (long long)clip * t;
+    int32_t* out = out_ids + (long long)clip * t;
+    int n = 0;
+    for (int t0 = 0; t0 < t; t0 += 32) {
+        const int i = t0 + lane;
+        const int id = i < t ? in[i] : 0;
+        const bool keep = i < t && id != 0 && id > 0 && id < vocab && !(skip_mask && skip_mask[id]);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[n + __popc(m & ((1u << lane) - 1u))] = id;
+        n += __popc(m);
+    }
+    for (int i = n + lane; i < t; i += 32) out[i] = -1;      // padding
+    if (lane == 0) out_len[clip] = n;
+}
+
+extern "C" int lele_b200_greedy_filter(lele_b200_ctx* ctx, const int32_t* ids, int n_clips, int t, const uint8_t* skip_mask, int vocab,
+                                       int32_t* out_ids, int32_t* out_len) {
+    LB_REQUIRE(ctx && ids && out_ids && out_len && n_clips >= 0 && t >= 0 && vocab > 0, "greedy_filter: bad arguments");
+    if (n_clips == 0) return LELE_B200_OK;
+    greedy_filter_kernel<<<n_clips, 32, 0, ctx->stream>>>(ids, t, skip_mask, vocab, out_ids, out_len);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
 extern "C" int lele_b200_argmax_last(lele_b200_ctx* ctx, const float* x, long long outer, int n, int32_t* out) {
     LB_REQUIRE(ctx && x && out && n > 0, "argmax_last: bad arguments");
     if (outer == 0) return LELE_B200_OK;

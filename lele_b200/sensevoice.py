@@ -99,6 +99,22 @@ class SenseVoice:
             q.free()
         return (idh[0], lgh[0]) if single else (idh, lgh)
 
+    def transcribe_text(self, pcm, tokenizer, language: int = 3, text_norm: int = 0):
+        """pcm [B, n] -> one string per clip: the whole example pipeline (main.rs:73-150) with only the kept token ids
+        of each clip leaving the GPU (device arg-max in the CTC epilogue + device greedy filter, tokenizer.rs:37)."""
+        p = np.ascontiguousarray(pcm, dtype=np.float32)
+        if p.ndim == 1:
+            p = p[None]
+        b, n = p.shape
+        T = self.rows(n)
+        if T == 0:
+            raise LeleB200Error("transcribe_text: clip shorter than one frame (400 samples)")
+        bp = self.ctx.upload(p); ids = self.ctx.empty(b * T)
+        self.forward_pcm_dev(bp.ptr, b, n, ids.ptr, None, language, text_norm)
+        kept = tokenizer.filter_ids_device(ids.ptr, b, T, self.ctx)
+        bp.free(); ids.free()
+        return [tokenizer.text(k) for k in kept]
+
     def workspace(self, name: str, shape, dtype=np.float32) -> np.ndarray:
         """Host copy of the leading `shape` elements of a workspace buffer after a forward
         (forward_with_workspace-style borrow; used by tests to localise divergences)."""

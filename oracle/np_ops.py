@@ -192,3 +192,31 @@ def reduce(x, axes, keepdims, kind):  # math.rs:1527-1921
     if kind == "l2":
         return np.sqrt(np.add.reduce(x * x, axis=axes, keepdims=keepdims, dtype=np.float32)).astype(np.float32)
     raise ValueError(kind)
+
+
+# ---- greedy decode (examples/sensevoice/src/tokenizer.rs:37-82): test infrastructure only ----
+def greedy_filter(ids, skip_mask):
+    """Per clip: frame ids that are not blank (0) and not flagged in skip_mask, in frame order (tokenizer.rs:62-68)."""
+    out = []
+    for row in np.asarray(ids):
+        out.append(np.array([int(i) for i in row if i != 0 and 0 < i < len(skip_mask) and not skip_mask[i]], np.int32))
+    return out
+
+
+def decode_greedy(logits, id_to_token):
+    """logits [B, T, V] -> texts: arg-max with the LAST maximum winning (Iterator::max_by, tokenizer.rs:55), skip id 0 and
+    "<|...|>" tokens, join, replace the sentencepiece underscore with a space, trim (tokenizer.rs:71-79)."""
+    lg = np.asarray(logits, np.float32)
+    texts = []
+    for b in range(lg.shape[0]):
+        toks = []
+        for t in range(lg.shape[1]):
+            row = lg[b, t]
+            tid = int(row.shape[0] - 1 - np.argmax(row[::-1]))
+            if tid < len(id_to_token):
+                tok = id_to_token[tid]
+                if tid == 0 or (tok.startswith("<|") and tok.endswith("|>")):
+                    continue
+                toks.append(tok)
+        texts.append("".join(toks).replace("\u2581", " ").strip())
+    return texts

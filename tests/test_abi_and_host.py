@@ -138,3 +138,23 @@ def test_bench_reference_arm_cli_contract():
     """bench.py --impl reference must parse and (without running the 10 s/clip workload here) expose the flags."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "--impl" in r.stdout and "--gpus" in r.stdout and "--steps" in r.stdout and "--warmup" in r.stdout
+
+
+def test_tokenizer_host_logic(tmp_path):
+    """Tokenizer.from_file / skip_mask / text follow examples/sensevoice/src/tokenizer.rs:10-82 (split at the LAST space,
+    blank + "<|...|>" tokens skipped, sentencepiece underscore -> space, trim); checked against the oracle restatement."""
+    from lele_b200.tokenizer import Tokenizer
+    from oracle import np_ops as N
+    toks = ["<blank>", "<|zh|>", "\u2581he", "llo", "\u2581wor ld", "<|NEUTRAL|>", "!", "<|", "|>"]
+    f = tmp_path / "tokens.txt"
+    f.write_text("".join(f"{t} {i}\n" for i, t in enumerate(toks)) + "malformed_line_without_id\n", encoding="utf-8")
+    tk = Tokenizer.from_file(str(f))
+    assert tk.id_to_token == toks and tk.vocab_size() == len(toks)
+    assert tk.skip_mask().tolist() == [1, 1, 0, 0, 0, 1, 0, 0, 0]
+    rng = np.random.default_rng(3)
+    logits = rng.standard_normal((3, 17, len(toks))).astype(np.float32)
+    logits[0, 5, 2] = logits[0, 5, 6] = 9.0                      # tie: the LAST maximum wins (tokenizer.rs:55)
+    ids = logits.shape[2] - 1 - np.argmax(logits[:, :, ::-1], axis=2)
+    kept = N.greedy_filter(ids, tk.skip_mask())
+    assert [tk.text(k) for k in kept] == N.decode_greedy(logits, toks)
+    assert tk.text([2, 3, 4, 6]) == "hello wor ld!"

@@ -294,6 +294,35 @@ def test_indexing_exact():
     np.testing.assert_array_equal(am, t.shape[1] - 1 - np.argmax(t[:, ::-1], axis=1))   # LAST max wins (Iterator::max_by)
 
 
+def test_greedy_decode_filter_on_device():
+    """Device arg-max + greedy filter (tokenizer.rs:37-82) against the oracle restatement: bit-exact ids and texts,
+    including rows that keep nothing, rows that keep everything, and t not a multiple of the warp width."""
+    from lele_b200.tokenizer import Tokenizer
+    from oracle import np_ops as N
+    rng = np.random.default_rng(9)
+    vocab = 300
+    toks = ["<blank>"] + [("<|sp%d|>" % i) if i % 7 == 0 else ("\u2581w%d" % i if i % 3 == 0 else "t%d" % i) for i in range(1, vocab)]
+    tk = Tokenizer(toks)
+    for (b, t) in [(1, 1), (3, 31), (5, 64), (4, 275), (2, 97)]:
+        logits = rng.standard_normal((b, t, vocab)).astype(np.float32)
+        logits[0, :, 0] += 50.0 if b > 1 else 0.0                  # clip 0: all blank -> empty string
+        if b > 2:
+            logits[2, :, 5] += 50.0                                # clip 2: every frame kept
+        if t > 3:
+            logits[-1, 3, 10] = logits[-1, 3, 200] = 60.0          # tie -> last index
+        assert tk.decode_greedy(logits, b, t, vocab) == N.decode_greedy(logits, toks)
+        ids = (vocab - 1 - np.argmax(logits[:, :, ::-1], axis=2)).astype(np.int32)
+        from lele_b200.kernels import default_context
+        ctx = default_context()
+        buf = ctx.upload(ids, np.int32)
+        kept = tk.filter_ids_device(buf.ptr, b, t, ctx)
+        buf.free()
+        want = N.greedy_filter(ids, tk.skip_mask())
+        assert len(kept) == len(want)
+        for k, w in zip(kept, want):
+            np.testing.assert_array_equal(k, w)
+
+
 def test_error_behaviour_matches_reference_panics():
     from lele_b200 import LeleB200Error
     from lele_b200 import kernels as K
