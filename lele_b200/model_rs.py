@@ -1,0 +1,329 @@
+"""Runs a `lele_gen`-generated `model.rs` on the B200 back-end without a Rust toolchain.
+
+The AOT compiler emits every model as a straight-line list of `lele::kernels::<op>(...)` calls whose weights are
+`(offset, len, shape)` views into one `weights.bin` blob (src/compiler/mod.rs:1053-1092, :1381-1505; a committed
+sample is examples/yolo26n-seg/src/yolo26seg.rs).  `parse_model_rs` turns such a file into a small JSON-able
+"program" (statement list + weight literals); `run_program` replays it against an operator namespace -- by default
+the CUDA product (`lele_b200.kernels` over the C ABI), in tests also the CPU oracle -- so a compiled model is a
+drop-in: same operator names, argument order and `weights.bin` layout.
+
+Only the statement forms the code generator emits are understood (src/compiler/generate.rs:802-997,
+src/compiler/ops/*.rs); anything else raises.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+
+__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view"]
+
+_DTYPES = {"weight_f32": ("<f4", None), "weight_i64": ("<i8", None), "weight_i64_f32": ("<i8", np.float32), "weight_i32": ("<i4", None),
+           "weight_i32_i64": ("<i4", np.int64), "weight_i32_f32": ("<i4", np.float32), "weight_u8": ("u1", np.float32), "weight_i8": ("i1", np.float32),
+           "weight_f16": ("<f2", np.float32)}
+
+
+def weight_view(blob, kind: str, offset: int, length: int, shape):
+    """TensorView::from_bytes_* (src/tensor.rs:131-257): typed view of blob[offset : offset+len] with the literal shape."""
+    src, cast = _DTYPES[kind]
+    a = np.frombuffer(blob, dtype=src, count=length // np.dtype(src).itemsize, offset=offset)
+    if cast is not None:
+        a = a.astype(cast)
+    return a.reshape(tuple(shape)) if len(shape) else a.reshape(())
+
+
+# ------------------------------------------------------------------------------------------------ parsing
+def _split_top(s: str):
+    """Split on top-level commas (parentheses / brackets / string literals respected)."""
+    out, depth, cur, in_str = [], 0, [], False
+    for ch in s:
+        if in_str:
+            cur.append(ch)
+            if ch == '"':
+                in_str = False
+            continue
+        if ch == '"':
+            in_str = True; cur.append(ch); continue
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append("".join(cur).strip()); cur = []
+        else:
+            cur.append(ch)
+    if "".join(cur).strip():
+        out.append("".join(cur).strip())
+    return out
+
+
+_W = re.compile(r"^&?self\.(weight_[a-z0-9_]+)\((\d+),\s*(\d+),\s*&\[([^\]]*)\]\)(.*)$")
+
+
+def _parse_arg(a: str):
+    a = a.strip()
+    if a == "None":
+        return None
+    if a.startswith("Some(") and a.endswith(")"):
+        return _parse_arg(a[5:-1])
+    if a in ("true", "false"):
+        return a == "true"
+    if a.startswith('"') and a.endswith('"'):
+        return {"str": a[1:-1]}
+    m = _W.match(a)
+    if m:
+        kind, off, ln, shp, tail = m.group(1), int(m.group(2)), int(m.group(3)), m.group(4), m.group(5).strip()
+        shape = [int(x) for x in shp.split(",") if x.strip()]
+        w = {"weight": [kind, off, ln, shape]}
+        if tail in ("", ".data"):
+            return w
+        if tail == ".data[0] as usize":
+            return {"weight_scalar": w["weight"]}
+        if tail == ".as_i64_vec()":
+            return {"weight_list": w["weight"]}
+        raise ValueError(f"model.rs: unsupported weight expression tail {tail!r}")
+    if a.startswith("&[") and a.endswith("]"):
+        items = _split_top(a[2:-1])
+        if items and items[0].startswith("&"):
+            return {"vars": [i.lstrip("&").strip() for i in items]}
+        return {"list": [_num(i) for i in items]}
+    if a.startswith("&mut "):
+        return {"out": a[5:].strip()}
+    if a.startswith("&"):
+        return {"var": a[1:].strip()}
+    if re.fullmatch(r"-?\d+(\.\d+)?([eE][-+]?\d+)?(f32|i64|usize)?", a):
+        return _num(a)
+    if re.fullmatch(r"[A-Za-z_][A-Za-z0-9_]*", a):
+        return {"var": a}
+    raise ValueError(f"model.rs: unsupported argument {a!r}")
+
+
+def _num(t: str):
+    t = re.sub(r"(f32|i64|usize|i32)$", "", t.strip())
+    return float(t) if any(c in t for c in ".eE") and not t.lstrip("-").isdigit() else int(t)
+
+
+def parse_model_rs(text: str) -> dict:
+    """-> {"class", "workspace_buffers", "inputs": [names], "statements": [{"outs", "op", "args"}], "outputs": [names]}"""
+    text = text.replace(".data.iter().map(|&v| v as i64).collect::<Vec<_>>()", ".as_i64_vec()")
+    cls = re.search(r"pub struct (\w+)<'a>", text)
+    n_bufs = len(re.findall(r"pub buf_\d+: Vec<f32>", text))
+    stmts, inputs, outputs = [], None, None
+    in_chunk, splits, split_src = False, None, None
+    for raw in text.splitlines():
+        line = raw.strip()
+        m = re.match(r"fn run_chunk_\d+<'w>\(&self, ws: [^,]+, (.*)\) -> ", line)
+        if m:
+            in_chunk = True
+            names = re.findall(r"(\w+): TensorView", m.group(1))
+            inputs = names if inputs is None else inputs
+            continue
+        if not in_chunk:
+            continue
+        if line == "}":
+            in_chunk = False
+            continue
+        if line.startswith("//") or not line:
+            continue
+        m = re.match(r"^\((.*)\)$", line)                      # tail expression: (a.to_owned(), b.to_owned())
+        if m:
+            outputs = [p.strip().replace(".to_owned()", "") for p in _split_top(m.group(1))]
+            continue
+        m = re.match(r"^let splits_slice = &\[(.*)\];$", line)
+        if m:
+            splits = [int(x) for x in m.group(1).split(",") if x.strip()]
+            continue
+        m = re.match(r"^let mut split_results = lele::kernels::split_owned\(&(\w+), (-?\d+), splits_slice\);$", line)
+        if m:
+            split_src = (m.group(1), int(m.group(2)), splits)
+            continue
+        m = re.match(r"^let (\w+) = split_results\.swap_remove\((\d+)\);$", line)
+        if m:
+            stmts.append({"outs": [m.group(1)], "op": "split_take", "args": [{"var": split_src[0]}, split_src[1], {"list": split_src[2]}, int(m.group(2))]})
+            continue
+        if re.match(r"^let mut buf_\w+ = Vec::<f32>::new\(\);$", line):
+            continue
+        m = re.match(r"^let (\w+) = (\w+)\.clone\(\);", line)
+        if m:
+            stmts.append({"outs": [m.group(1)], "op": "identity", "args": [{"var": m.group(2)}]})
+            continue
+        m = re.match(r"^let \((\w+), (\w+)\) = lele::kernels::(\w+)\((.*)\);$", line) or re.match(r"^let (\w+)() = lele::kernels::(\w+)\((.*)\);$", line)
+        if m:
+            outs = [m.group(1)] + ([m.group(2)] if m.group(2) else [])
+            args = [_parse_arg(a) for a in _split_top(m.group(4))]
+            args = [a for a in args if not (isinstance(a, dict) and "out" in a)]      # workspace buffers: the arena is the back-end's business
+            stmts.append({"outs": outs, "op": m.group(3), "args": args})
+            continue
+        raise ValueError(f"model.rs: unsupported statement: {line[:160]}")
+    if inputs is None or outputs is None:
+        raise ValueError("model.rs: no run_chunk body found")
+    return {"class": cls.group(1) if cls else "Model", "workspace_buffers": n_bufs, "inputs": inputs, "statements": stmts, "outputs": outputs}
+
+
+# ------------------------------------------------------------------------------------------------ execution
+class CudaOps:
+    """The operator namespace `run_program` drives, over `lele_b200.kernels` (every call is a C-ABI launch)."""
+
+    def __init__(self, ctx=None):
+        from . import kernels as K
+        self.K, self.ctx = K, ctx
+
+    def conv2d(self, x, w, bias, dilations, group, pads, strides, act): return self.K.conv2d(x, w, bias, dilations, group, pads, strides, act, ctx=self.ctx)
+    def conv_transpose(self, x, w, bias, dilations, pads, strides): return self.K.conv_transpose(x, w, bias, dilations, pads, strides, ctx=self.ctx)
+    def matmul(self, a, b): return self.K.matmul(a, b, ctx=self.ctx)
+    def softmax(self, x, axis): return self.K.softmax(x, axis, ctx=self.ctx)
+    def max_pool2d(self, x, kernel, pads, strides, dilations, ceil_mode): return self.K.max_pool2d(x, kernel, pads, strides, dilations, ceil_mode, ctx=self.ctx)
+    def concat(self, xs, axis): return self.K.concat(xs, axis, ctx=self.ctx)
+    def slice(self, x, starts, ends, axes, steps): return self.K.slice(x, starts, ends, axes, steps, ctx=self.ctx)
+    def gather(self, x, idx, axis): return self.K.gather(x, idx, axis, ctx=self.ctx)
+    def gather_elements(self, x, idx, axis): return self.K.gather_elements(x, idx, axis, ctx=self.ctx)
+    def transpose(self, x, perm): return self.K.transpose(x, perm, ctx=self.ctx)
+    def split(self, x, axis, splits): return self.K.split(x, axis, splits, ctx=self.ctx)
+    def tile(self, x, repeats): return self.K.tile(x, repeats, ctx=self.ctx)
+    def topk(self, x, k): return self.K.topk(x, k, ctx=self.ctx)
+    def resize_nearest(self, x, scales, sizes, mode): return self.K.resize_nearest(x, scales, sizes, mode, ctx=self.ctx)
+    def reduce(self, x, axes, keepdims, kind):
+        return {"sum": self.K.reduce_sum, "mean": self.K.reduce_mean, "max": self.K.reduce_max, "l2": self.K.reduce_l2}[kind](x, axes, keepdims, ctx=self.ctx)
+    def binary(self, op, a, b): return getattr(self.K, op)(a, b, ctx=self.ctx)
+    def unary(self, op, x): return getattr(self.K, op)(x, ctx=self.ctx)
+    def layer_norm(self, x, g, b, axis, eps): return self.K.layer_norm(x, g, b, axis, eps, ctx=self.ctx)
+
+
+class _NamespaceOps:
+    """Adapter for a module exposing the shared operator vocabulary of the test suite (same names as CudaOps)."""
+
+    def __init__(self, ns):
+        self.ns = ns
+
+    def __getattr__(self, name):
+        return getattr(self.ns, name)
+
+    def binary(self, op, a, b): return getattr(self.ns, op)(a, b)
+    def unary(self, op, x): return getattr(self.ns, op)(x)
+    def resize_nearest(self, x, scales, sizes, mode): return self.ns.resize_nearest(x, scales=scales, sizes=sizes, mode=mode)
+
+
+def _reshape(x, shape):  # shape.rs:2-93: 0 copies the input dim, -1 is inferred
+    shp = [x.shape[i] if s == 0 else s for i, s in enumerate(shape)]
+    return np.ascontiguousarray(x).reshape(shp)
+
+
+def run_program(program: dict, blob, inputs, ops=None, trace=None):
+    """Replays the statement list.  `blob` = the model's weights.bin bytes, `inputs` = arrays in `program["inputs"]` order.
+    `ops`: CudaOps (default) or any module with the shared operator vocabulary.  Returns the outputs as numpy arrays."""
+    if ops is None:
+        ops = CudaOps()
+    elif not hasattr(ops, "binary"):
+        ops = _NamespaceOps(ops)
+    env = {n: np.ascontiguousarray(a, dtype=np.float32) for n, a in zip(program["inputs"], inputs)}
+    split_cache = {}
+
+    def val(a):
+        if isinstance(a, dict):
+            if "var" in a: return env[a["var"]]
+            if "vars" in a: return [env[v] for v in a["vars"]]
+            if "weight" in a: return weight_view(blob, *a["weight"])
+            if "weight_scalar" in a: return int(weight_view(blob, *a["weight_scalar"]).reshape(-1)[0])
+            if "weight_list" in a: return [int(v) for v in weight_view(blob, *a["weight_list"]).reshape(-1)]
+            if "list" in a: return list(a["list"])
+            if "str" in a: return a["str"]
+        return a
+
+    for st in program["statements"]:
+        op, a = st["op"], [val(x) for x in st["args"]]
+        if op in ("conv2d", "conv2d_silu", "conv2d_fused"):
+            act = 2 if op == "conv2d_silu" else (1 if (op == "conv2d_fused" and a[7]) else 0)
+            r = ops.conv2d(a[0], a[1], a[2], a[3], a[4], a[5], a[6], act)
+        elif op == "conv_transpose":
+            if a[4] != 1:
+                raise ValueError("ConvTranspose: group > 1 not supported yet (conv2d.rs:3042)")
+            r = ops.conv_transpose(a[0], a[1], a[2], a[3], a[5], a[6])
+        elif op in ("add", "sub", "mul", "div", "mod_f32"):
+            r = ops.binary(op, a[0], a[1])
+        elif op in ("sigmoid", "silu", "relu"):
+            r = ops.unary(op, a[0])
+        elif op == "concat":
+            r = ops.concat(a[0], a[1])
+        elif op == "split_take":
+            key = (st["args"][0]["var"], a[1], tuple(a[2]))
+            if key not in split_cache:
+                split_cache[key] = ops.split(a[0], a[1], a[2])
+            r = split_cache[key][a[3]]
+        elif op == "identity":
+            r = a[0]
+        elif op == "reshape":
+            r = _reshape(a[0], a[1])
+        elif op == "flatten":
+            x = np.ascontiguousarray(a[0]); ax = a[1] % (x.ndim + 1) if a[1] < 0 else a[1]
+            r = x.reshape(int(np.prod(x.shape[:ax], dtype=np.int64)), -1)
+        elif op == "unsqueeze":
+            r = np.ascontiguousarray(a[0])
+            for ax in sorted(x % (r.ndim + 1) if x < 0 else x for x in a[1]):
+                r = np.expand_dims(r, ax)
+        elif op == "transpose":
+            r = ops.transpose(a[0], a[1])
+        elif op == "resize_nearest":
+            scales = None if a[1] is None else [float(v) for v in np.asarray(a[1]).reshape(-1)]
+            r = ops.resize_nearest(a[0], scales, a[2], a[3])
+        elif op == "matmul":
+            r = ops.matmul(a[0], a[1])
+        elif op == "softmax":
+            r = ops.softmax(a[0], a[1])
+        elif op == "max_pool2d":                     # (x, kernel, strides, pads, dilations, ceil_mode)
+            r = ops.max_pool2d(a[0], a[1], a[3], a[2], a[4], a[5])
+        elif op == "slice":
+            r = ops.slice(a[0], a[1], a[2], a[3], a[4])
+        elif op == "reduce_max":
+            r = ops.reduce(a[0], a[1], a[2], "max")
+        elif op == "topk":                            # (x, k, axis, largest, sorted): last axis, descending, stable (conv2d.rs:1385)
+            r = ops.topk(a[0], a[1])
+        elif op == "tile":
+            r = ops.tile(a[0], a[1])
+        elif op == "gather_elements":
+            r = ops.gather_elements(a[0], a[1], a[2])
+        elif op == "gather":
+            r = ops.gather(a[0], a[1], a[2])
+        else:
+            raise ValueError(f"model.rs: operator {op} is not wired into run_program")
+        if len(st["outs"]) == 1:
+            env[st["outs"][0]] = r
+        else:
+            for n, v in zip(st["outs"], r):
+                env[n] = v
+        if trace is not None:
+            trace.append((st["outs"][0], op, env[st["outs"][0]]))
+    return [env[n] for n in program["outputs"]]
+
+
+def synth_blob(program: dict, seed: int = 7, constants=None) -> bytes:
+    """A weights.bin stand-in for a parsed program when the real blob is not available:
+    convolution / matmul weights ~ N(0, 1/sqrt(fan_in)), biases ~ N(0, 0.1), every other f32 view ~ N(0, 1);
+    `constants` = {offset: array} overrides (shape constants, anchors, k ...), written with the view's own dtype."""
+    size, views = 0, {}
+    for st in program["statements"]:
+        for i, a in enumerate(st["args"]):
+            if isinstance(a, dict):
+                for key in ("weight", "weight_scalar", "weight_list"):
+                    if key in a:
+                        kind, off, ln, shape = a[key]
+                        size = max(size, off + ln)
+                        role = "w" if (st["op"] in ("conv2d", "conv2d_silu", "conv_transpose") and i == 1) else ("b" if st["op"].startswith("conv") and i == 2 else "x")
+                        views[off] = (kind, ln, shape, role)
+    blob = np.zeros(size, np.uint8)
+    rng = np.random.default_rng(seed)
+    for off in sorted(views):
+        kind, ln, shape, role = views[off]
+        src = np.dtype(_DTYPES[kind][0])
+        n = ln // src.itemsize
+        if constants is not None and off in constants:
+            v = np.asarray(constants[off]).astype(src).reshape(-1)
+        elif src.kind == "f":
+            fan_in = int(np.prod(shape[1:])) if (role == "w" and len(shape) > 1) else 1
+            sd = 1.0 / np.sqrt(fan_in) if role == "w" else (0.1 if role == "b" else 1.0)
+            v = (rng.standard_normal(n) * sd).astype(src)
+        else:
+            v = np.ones(n, src)
+        if v.size != n:
+            raise ValueError(f"synth_blob: constant at offset {off} has {v.size} elements, the view holds {n}")
+        blob[off:off + ln] = v.view(np.uint8)
+    return blob.tobytes()

@@ -158,3 +158,61 @@ def test_tokenizer_host_logic(tmp_path):
     kept = N.greedy_filter(ids, tk.skip_mask())
     assert [tk.text(k) for k in kept] == N.decode_greedy(logits, toks)
     assert tk.text([2, 3, 4, 6]) == "hello wor ld!"
+
+
+def test_model_rs_parser_and_replay_on_oracle():
+    """lele_b200/model_rs.py: the statement forms lele_gen emits (src/compiler/generate.rs:802-997) parse into a program and
+    replay against the shared operator vocabulary; here on the CPU oracle with a tiny generated-style body."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("model_rs", os.path.join(ROOT, "lele_b200", "model_rs.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    from oracle import reference_api as R
+    text = """
+pub struct TinyWorkspace { pub buf_0: Vec<f32>, pub buf_1: Vec<f32>, }
+pub struct Tiny<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut TinyWorkspace, images: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>) {
+        let a = lele::kernels::conv2d_silu(&images, &self.weight_f32(0, 432, &[4, 3, 3, 3]), Some(&self.weight_f32(432, 16, &[4])), &[1, 1], 1, &[1, 1, 1, 1], &[2, 2], &mut ws.buf_0);
+        let splits_slice = &[2, 2];
+        let mut split_results = lele::kernels::split_owned(&a, 1, splits_slice);
+        let a1 = split_results.swap_remove(1);
+        let a0 = split_results.swap_remove(0);
+        let b = lele::kernels::add(&a0, &a1, &mut ws.buf_1);
+        let c = lele::kernels::concat(&[&a0, &b], 1, &mut ws.buf_0);
+        let d = lele::kernels::resize_nearest(&c, Some(&self.weight_f32(448, 16, &[4]).data), None, "asymmetric", &mut ws.buf_1);
+        let e = lele::kernels::reshape(&d, &[1, 4, -1]);
+        let mut buf_v = Vec::<f32>::new();
+        let mut buf_i = Vec::<f32>::new();
+        let (tv, ti) = lele::kernels::topk(&e, self.weight_i64(464, 8, &[1]).data[0] as usize, -1, true, true, &mut buf_v, &mut buf_i);
+        let f = tv.clone(); // Cast f32->f32 is no-op
+        (f.to_owned(), ti.to_owned())
+    }
+"""
+    prog = m.parse_model_rs(text)
+    assert prog["class"] == "Tiny" and prog["inputs"] == ["images"] and prog["outputs"] == ["f", "ti"] and prog["workspace_buffers"] == 2
+    assert [st["op"] for st in prog["statements"]] == ["conv2d_silu", "split_take", "split_take", "add", "concat", "resize_nearest", "reshape", "topk", "identity"]
+    blob = m.synth_blob(prog, 1, {448: [1, 1, 2, 2], 464: [5]})
+    assert len(blob) == 472
+    x = np.random.default_rng(0).random((1, 3, 8, 8), dtype=np.float32)
+    f, ti = m.run_program(prog, blob, [x], R)
+    w = m.weight_view(blob, "weight_f32", 0, 432, [4, 3, 3, 3]); b = m.weight_view(blob, "weight_f32", 432, 16, [4])
+    a = R.conv2d(x, w, b, (1, 1), 1, (1, 1, 1, 1), (2, 2), 2)
+    c = np.concatenate([a[:, :2], a[:, :2] + a[:, 2:]], 1)
+    e = np.repeat(np.repeat(c, 2, 2), 2, 3).reshape(1, 4, -1)
+    want_v, want_i = R.topk(e, 5)
+    np.testing.assert_array_equal(f, want_v); np.testing.assert_array_equal(ti, want_i)
+    with pytest.raises(ValueError):
+        m.parse_model_rs(text.replace("let b = lele::kernels::add(&a0, &a1, &mut ws.buf_1);", "let b = unsafe { transmute(a0) };"))
+
+
+def test_generated_model_fixture_is_consistent():
+    """tests/golden/yolo26seg_program.json (from the reference's committed lele_gen output, see make_model_program.py):
+    337 statements, 21 workspace buffers, a 10 993 208-byte weights.bin."""
+    import importlib.util, json
+    spec = importlib.util.spec_from_file_location("model_rs", os.path.join(ROOT, "lele_b200", "model_rs.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    prog = json.load(open(os.path.join(ROOT, "tests", "golden", "yolo26seg_program.json")))
+    assert prog["class"] == "Yolo26Seg" and prog["workspace_buffers"] == 21 and len(prog["statements"]) == 337
+    ops = [st["op"] for st in prog["statements"]]
+    assert ops.count("conv2d") + ops.count("conv2d_silu") == 117 and ops.count("conv_transpose") == 1
+    blob = m.synth_blob(prog, 7, {int(k): v for k, v in prog["constants"].items()})
+    assert len(blob) == 10993208

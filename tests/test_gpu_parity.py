@@ -323,6 +323,44 @@ def test_greedy_decode_filter_on_device():
             np.testing.assert_array_equal(k, w)
 
 
+def test_generated_yolo26seg_model_replay():
+    """BASELINE config 5 / SURVEY 8f rank 2: the reference's committed lele_gen output (Yolo26n-seg, 337 statements, 117
+    convolutions + ConvTranspose + attention + top-k head) replayed statement by statement over the C ABI -- implicit-GEMM
+    convolutions on tcgen05 -- against the same replay on the CPU oracle, 640x640 input, synthetic weights.bin.
+    Every intermediate tensor up to the first TopK is held to 1e-4 of its magnitude; the detections (order decided by
+    near-equal scores under random weights) are compared as a set."""
+    import json, os
+    from lele_b200 import model_rs as MR
+    prog = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "yolo26seg_program.json")))
+    pts, strd = [], []
+    for s_, g in ((8, 80), (16, 40), (32, 20)):
+        ys, xs = np.meshgrid(np.arange(g) + 0.5, np.arange(g) + 0.5, indexing="ij")
+        pts.append(np.stack([xs.reshape(-1), ys.reshape(-1)], 0)); strd.append(np.full(g * g, s_, np.float32))
+    consts = {int(k): v for k, v in prog["constants"].items()}
+    consts[prog["anchor_points_offset"]] = np.concatenate(pts, 1)[None]; consts[prog["anchor_strides_offset"]] = np.concatenate(strd)[None]
+    blob = MR.synth_blob(prog, 7, consts)
+    x = np.random.default_rng(7).random((1, 3, 640, 640), dtype=np.float32)
+    tg, tr = [], []
+    og = MR.run_program(prog, blob, [x], MR.CudaOps(), trace=tg)
+    orf = MR.run_program(prog, blob, [x], R, trace=tr)
+    assert og[0].shape == (1, 300, 38) and og[1].shape == (1, 32, 160, 160)
+    worst = 0.0
+    for (n1, op1, a), (n2, op2, b) in zip(tg, tr):
+        assert n1 == n2 and op1 == op2
+        if op1 == "topk":
+            break
+        a = np.asarray(a, np.float32); b = np.asarray(b, np.float32)
+        assert a.shape == b.shape, (n1, a.shape, b.shape)
+        err = float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+        worst = max(worst, err)
+        assert err < 1e-4, (n1, op1, err)
+    close(og[1], orf[1], rtol=1e-4, atol_frac=1e-4)                       # prototype masks
+    # detections: rows = (box 4, score, class, 32 mask coefficients); match rows by (class, rounded box)
+    key = lambda r: (int(r[5]), tuple(np.round(r[:4], 1)))
+    kg = {key(r) for r in og[0][0]}; kr = {key(r) for r in orf[0][0]}
+    assert len(kg & kr) >= 0.9 * len(kr), (len(kg & kr), len(kr), worst)
+
+
 def test_error_behaviour_matches_reference_panics():
     from lele_b200 import LeleB200Error
     from lele_b200 import kernels as K
