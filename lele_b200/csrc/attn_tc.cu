@@ -43,12 +43,12 @@ constexpr int TILE_V = DK * 128;      // 16 KB  [128 dims][32 keys]
 // ring in the 96 spare columns -- and the P.V products read their A operand from TMEM (tcgen05.mma, A in TMEM).  Both
 // phases of this kernel are bound by shared-memory bandwidth (128 B/clk/SM: operand reads of the MMAs + TMA writes +
 // the lo splits); this removes 80 of the 176 KB per 32-key chunk that phase C moved through shared memory.
-// V slots 0-2 lie inside phase-A stage 0, which is free once the MMAs of k-chunk 2 retired, so the first three V chunks
-// are fetched (and split) under the last k-chunk's MMAs.
+// V slots 0-2 lie inside the phase-A stage whose last use is k-chunk 2, so the first three V chunks are fetched (and
+// split) under the last k-chunk's MMAs (slot addresses: see the kernel's shared-memory map).
 constexpr int NSLOT_V = 6, V_EARLY = 3, NSLOT_PL = 3;
 constexpr int SLOT_V = 2 * TILE_V;
 constexpr int SMEM_MAIN = NSTAGE_A * STAGE_A;      // 208 KB (>= NSLOT_V * SLOT_V = 192 KB)
-static_assert(V_EARLY * SLOT_V <= STAGE_A && NSLOT_V * SLOT_V <= SMEM_MAIN, "phase-C layout");
+static_assert(V_EARLY * SLOT_V <= STAGE_A && (NSLOT_V - V_EARLY) * SLOT_V <= STAGE_A, "phase-C layout");
 constexpr int MAX_KCHUNKS = 2 * NH / KC;           // 9
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = SMEM_MAIN + 1024 + BAR_BYTES + 8 * 128 * 4;   // + barriers + row max / row sum exchange
@@ -204,40 +204,49 @@ attn_split_vt_kernel(const float* __restrict__ qkv, int T, int Tp, int d, int H,
 // ------------------------------------------------------------------------------------------
 // fused attention
 // ------------------------------------------------------------------------------------------
+// Persistent: grid = min(#SMs, items), CTA walks items blockIdx.x, +gridDim.x, ... (item = (clip, head, q-tile), the
+// q-tiles of one (clip, head) are consecutive items = concurrently running CTAs share K / V in L2).  TMEM, barriers and
+// tensor-map prefetch are set up once; the next item's first Q/K chunks are fetched and its hi.hi products issued while
+// the softmax warps are still writing the previous item's output (the epilogue is bound by global-write bandwidth).
+// Shared-memory map (208 KB):  phase A: stage 0 = [0, 104 KB), stage 1 = [104, 208 KB); an item's k-chunks use stages
+// 1, 0, 1, 0, so its first chunk only needs the previous item's P.V MMAs to have retired (o_full) and its second the
+// previous epilogue's staging tiles to have been read (epi_done).  phase C: V slots 0-2 at [104, 200 KB) (stage 1, free
+// once k-chunk 2's MMAs retired), V slots 3-5 at [0, 96 KB) (stage 0, free at s_full); epilogue staging [0, 64 KB).
+// Every barrier completes a fixed number of times per item, so wait parities follow from the CTA's item counter.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_kh,
                const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_out, const AttnArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + SMEM_MAIN);
-    uint64_t* full_a = bars;                  // [2] TMA -> MMA (phase A)
-    uint64_t* empty_a = bars + 2;             // [2] MMA -> TMA
-    uint64_t* s_full = bars + 4;              // S complete (also: phase-A smem is free)
-    // phase-C barriers are per 32-key CHUNK (single use each, parity 0): the four softmax groups run up to two ring
-    // turns ahead of the tensor core, which a per-stage barrier's 1-bit phase parity could not tell apart
+    uint64_t* full_a = bars;                  // [2] TMA -> converters / MMA (phase A); 2 completions per item
+    uint64_t* empty_a = bars + 2;             // [2] MMA -> TMA; 2 completions per item
+    uint64_t* s_full = bars + 4;              // S complete (also: phase-A smem is free); 1 per item
+    // phase-C barriers are per 32-key CHUNK (one completion per item each): the four softmax groups run up to two ring
+    // turns ahead of the tensor core, which a per-slot barrier's 1-bit phase parity could not tell apart
     uint64_t* v_full = bars + 5;              // [MAX_KCHUNKS] V chunk landed
     uint64_t* p_full = v_full + MAX_KCHUNKS;  // [MAX_KCHUNKS] P chunk written by the softmax warps
-    uint64_t* pv_done = p_full + MAX_KCHUNKS; // [MAX_KCHUNKS] MMA consumed the chunk (its ring stage is free again)
+    uint64_t* pv_done = p_full + MAX_KCHUNKS; // [MAX_KCHUNKS] MMA consumed the chunk (its ring slot is free again)
     uint64_t* o_full = pv_done + MAX_KCHUNKS; // O complete
     uint64_t* conv_a = o_full + 1;            // [2] phase-A lo tiles written (16 converter warps) -> MMA
     uint64_t* vl_full = conv_a + 2;           // [MAX_KCHUNKS] V lo chunk written (warps 2, 3) -> MMA
-    uint32_t* tmem_base_smem = (uint32_t*)(vl_full + MAX_KCHUNKS);
+    uint64_t* epi_done = vl_full + MAX_KCHUNKS; // the 16 epilogue warps' staging tiles have been read by their TMA stores
+    uint32_t* tmem_base_smem = (uint32_t*)(epi_done + 1);
     float* xch = (float*)(smem + SMEM_MAIN + BAR_BYTES);    // [2][NGRP][128] partial row max / row sums of the softmax groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ long long dbg_t[20][8];
     __shared__ long long dbg_c[4][5];          // group-0 warp: per p2 chunk {start, after tmem ld, after exp, after slot wait, after store}
-    const int qt = blockIdx.x % args.n_qtiles;
-    const int bh = blockIdx.x / args.n_qtiles;
-    const int h = bh % args.H, b = bh / args.H;
     const int T = args.T, NKC = args.n_kchunks;
+    const int n_items = args.B * args.H * args.n_qtiles;
+    const int dbg_it = 1;                      // the item of this CTA whose timeline is recorded
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_qh); prefetch_tmap(&map_kh); prefetch_tmap(&map_vh); prefetch_tmap(&map_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); mbar_init(&conv_a[s], NGRP * 4); }
-        mbar_init(s_full, 1); mbar_init(o_full, 1);
+        mbar_init(s_full, 1); mbar_init(o_full, 1); mbar_init(epi_done, NGRP * 4);
         for (int c = 0; c < MAX_KCHUNKS; ++c) { mbar_init(&v_full[c], 1); mbar_init(&p_full[c], 4); mbar_init(&pv_done[c], 1); mbar_init(&vl_full[c], 2); }
         fence_barrier_init();
         fence_proxy_async();
@@ -252,102 +261,122 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     const uint32_t tmem_base = *tmem_base_smem;
     lb_pdl_launch_dependents();
     lb_pdl_wait();                 // PDL: the prologue above does not touch the projection's output
-    if (warp == 0) ATT_DBG(0);
+#define ATT_DBG_IT(idx) do { if (args.dbg && lane == 0 && it == dbg_it) dbg_t[warp][idx] = clock64(); } while (0)
+    // phase-A stage of k-chunk kc, and the index u of this use among the stage's uses (2 per item) -> barrier parity u & 1
+#define STAGE_OF(kc) (((kc) + 1) & 1)
+#define USE_OF(it, kc) ((it) * 2 + ((kc) >> 1))
+    auto v_slot = [&](int c) -> uint8_t* { const int v = c % NSLOT_V; return smem + (v < V_EARLY ? STAGE_A + v * SLOT_V : (v - V_EARLY) * SLOT_V); };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            // phase A: 4 k-chunks of 32 dims through a 2-stage ring
-            for (int kc = 0; kc < DK / KC; ++kc) {
-                const int s = kc & 1; const uint32_t ph = (kc >> 1) & 1;
-                mbar_wait(&empty_a[s], ph ^ 1);
-                uint8_t* st = smem + s * STAGE_A;
-                mbar_expect_tx(&full_a[s], TILE_Q + TILE_K);     // raw (= hi) tiles only; the lo tiles are made on chip
-                tma_load_4d(st, &map_qh, &full_a[s], kc * KC, h, qt * AQ, b);
-                tma_load_4d(st + 2 * TILE_Q, &map_kh, &full_a[s], kc * KC, h, 0, b);
-                tma_load_4d(st + 2 * TILE_Q + NH * 128, &map_kh, &full_a[s], kc * KC, h, NH, b);
-            }
-            // phase C reuses the same shared memory (layout above): V chunks 0..2 as soon as phase-A stage 0 is free
-            // (second completion of empty_a[0]), chunk 3 once every phase-A MMA has retired, later chunks as slots free up
-            for (int c = 0; c < NKC; ++c) {
-                if (c == 0) mbar_wait(&empty_a[0], 1);
-                if (c == V_EARLY) mbar_wait(s_full, 0);
-                if (c >= NSLOT_V) mbar_wait(&pv_done[c - NSLOT_V], 0);
-                uint8_t* vs = smem + (c % NSLOT_V) * SLOT_V;
-                mbar_expect_tx(&v_full[c], TILE_V);
-                tma_load_4d(vs, &map_vh, &v_full[c], c * KC, 0, h, b);
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int qt = item % args.n_qtiles, bh = item / args.n_qtiles, h = bh % args.H, b = bh / args.H;
+                const uint32_t ip = (uint32_t)it & 1u, pp = ip ^ 1u;      // this / the previous item's completion parity
+                if (it == dbg_it) ATT_DBG(0);
+                // phase A: 4 k-chunks of 32 dims through the 2-stage ring (stages 1, 0, 1, 0)
+                for (int kc = 0; kc < DK / KC; ++kc) {
+                    const int s = STAGE_OF(kc); const uint32_t ph = (uint32_t)USE_OF(it, kc) & 1u;
+                    if (it > 0 && kc == 0) mbar_wait(o_full, pp);         // stage 1 held the previous item's V slots 0-2
+                    if (it > 0 && kc == 1) mbar_wait(epi_done, pp);       // stage 0 held its V slots 3-5 and the epilogue staging
+                    mbar_wait(&empty_a[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_A;
+                    mbar_expect_tx(&full_a[s], TILE_Q + TILE_K);     // raw (= hi) tiles only; the lo tiles are made on chip
+                    tma_load_4d(st, &map_qh, &full_a[s], kc * KC, h, qt * AQ, b);
+                    tma_load_4d(st + 2 * TILE_Q, &map_kh, &full_a[s], kc * KC, h, 0, b);
+                    tma_load_4d(st + 2 * TILE_Q + NH * 128, &map_kh, &full_a[s], kc * KC, h, NH, b);
+                }
+                // phase C: V chunks 0..2 as soon as stage 1 is free (the MMAs of k-chunk 2 retired: its second completion of
+                // this item), chunk 3.. once every phase-A MMA has retired, chunks >= 6 as slots free up
+                for (int c = 0; c < NKC; ++c) {
+                    if (c == 0) mbar_wait(&empty_a[1], (uint32_t)(it * 2 + 1) & 1u);
+                    if (c == V_EARLY) mbar_wait(s_full, ip);
+                    if (c >= NSLOT_V) mbar_wait(&pv_done[c - NSLOT_V], ip);
+                    mbar_expect_tx(&v_full[c], TILE_V);
+                    tma_load_4d(v_slot(c), &map_vh, &v_full[c], c * KC, 0, h, b);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t ID_S = idesc_tf32(NH), ID_O = idesc_tf32(DK);
-            for (int kc = 0; kc < DK / KC; ++kc) {
-                const int s = kc & 1; const uint32_t ph = (kc >> 1) & 1;
-                mbar_wait(&full_a[s], ph);                       // raw tiles landed: the hi*hi products can start
-                tc_fence_after();
-                if (kc == 0) ATT_DBG(1);
-                if (kc == 3) ATT_DBG(2);
-                const uint32_t base = smem_u32(smem + s * STAGE_A);
-                const uint64_t qh = make_smem_desc(base), ql = make_smem_desc(base + TILE_Q);
-                const uint64_t kh = make_smem_desc(base + 2 * TILE_Q), kl = make_smem_desc(base + 2 * TILE_Q + TILE_K);
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t ip = (uint32_t)it & 1u;
+                if (it > 0) { mbar_wait(o_full, ip ^ 1u); tc_fence_after(); }   // the previous P.V MMAs (they read hi(P) from the S columns) retired
+                for (int kc = 0; kc < DK / KC; ++kc) {
+                    const int s = STAGE_OF(kc); const uint32_t ph = (uint32_t)USE_OF(it, kc) & 1u;
+                    mbar_wait(&full_a[s], ph);                       // raw tiles landed: the hi*hi products can start
+                    tc_fence_after();
+                    if (kc == 0) ATT_DBG_IT(1);
+                    if (kc == 3) ATT_DBG_IT(2);
+                    const uint32_t base = smem_u32(smem + s * STAGE_A);
+                    const uint64_t qh = make_smem_desc(base), ql = make_smem_desc(base + TILE_Q);
+                    const uint64_t kh = make_smem_desc(base + 2 * TILE_Q), kl = make_smem_desc(base + 2 * TILE_Q + TILE_K);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t dS = tmem_base + (uint32_t)(half * NH);
-                    const uint64_t hoff = (uint64_t)((half * NH * 128) >> 4);
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t dS = tmem_base + (uint32_t)(half * NH);
+                        const uint64_t hoff = (uint64_t)((half * NH * 128) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {       // 8 floats (32 B) per MMA: +2 in the >>4 address field
-                        const uint64_t ko = (uint64_t)(k * 2);
-                        umma_tf32(dS, qh + ko, kh + hoff + ko, ID_S, (kc == 0 && k == 0) ? 0u : 1u);
+                        for (int k = 0; k < 4; ++k) {       // 8 floats (32 B) per MMA: +2 in the >>4 address field
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            umma_tf32(dS, qh + ko, kh + hoff + ko, ID_S, (kc == 0 && k == 0) ? 0u : 1u);
+                        }
                     }
-                }
-                mbar_wait(&conv_a[s], ph);                       // ... the lo tiles are written (converter warps): cross terms
-                tc_fence_after();
+                    mbar_wait(&conv_a[s], ph);                       // ... the lo tiles are written (converter warps): cross terms
+                    tc_fence_after();
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t dS = tmem_base + (uint32_t)(half * NH);
-                    const uint64_t hoff = (uint64_t)((half * NH * 128) >> 4);
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t dS = tmem_base + (uint32_t)(half * NH);
+                        const uint64_t hoff = (uint64_t)((half * NH * 128) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);
+                            umma_tf32(dS, qh + ko, kl + hoff + ko, ID_S, 1u);
+                            umma_tf32(dS, ql + ko, kh + hoff + ko, ID_S, 1u);
+                        }
+                    }
+                    umma_commit(&empty_a[s]);
+                    if (kc == DK / KC - 1) umma_commit(s_full);
+                }
+                for (int c = 0; c < NKC; ++c) {
+                    mbar_wait(&vl_full[c], ip);                      // V chunk landed and its lo tile is written
+                    mbar_wait(&p_full[c], ip);                       // hi(P) / lo(P) of the chunk are in tensor memory
+                    tc_fence_after();
+                    const uint32_t vb = smem_u32(v_slot(c));
+                    const uint64_t vhd = make_smem_desc(vb), vld = make_smem_desc(vb + TILE_V);
+                    const uint32_t a_hi = tmem_base + (uint32_t)(c * KC);                       // in place of S chunk c
+                    const uint32_t a_lo = tmem_base + (uint32_t)(PL_COL + (c % NSLOT_PL) * KC);
+                    const uint32_t dO = tmem_base + (uint32_t)O_COL;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);
-                        umma_tf32(dS, qh + ko, kl + hoff + ko, ID_S, 1u);
-                        umma_tf32(dS, ql + ko, kh + hoff + ko, ID_S, 1u);
+                        umma_tf32_ts(dO, a_hi + (uint32_t)(k * 8), vhd + ko, ID_O, (c == 0 && k == 0) ? 0u : 1u);
+                        umma_tf32_ts(dO, a_hi + (uint32_t)(k * 8), vld + ko, ID_O, 1u);
+                        umma_tf32_ts(dO, a_lo + (uint32_t)(k * 8), vhd + ko, ID_O, 1u);
                     }
+                    umma_commit(&pv_done[c]);
+                    if (c == NKC - 1) umma_commit(o_full);
                 }
-                umma_commit(&empty_a[s]);
-                if (kc == DK / KC - 1) umma_commit(s_full);
-            }
-            for (int c = 0; c < NKC; ++c) {
-                mbar_wait(&vl_full[c], 0);                       // V chunk landed and its lo tile is written
-                mbar_wait(&p_full[c], 0);                        // hi(P) / lo(P) of the chunk are in tensor memory
-                tc_fence_after();
-                const uint32_t vb = smem_u32(smem + (c % NSLOT_V) * SLOT_V);
-                const uint64_t vhd = make_smem_desc(vb), vld = make_smem_desc(vb + TILE_V);
-                const uint32_t a_hi = tmem_base + (uint32_t)(c * KC);                       // in place of S chunk c
-                const uint32_t a_lo = tmem_base + (uint32_t)(PL_COL + (c % NSLOT_PL) * KC);
-                const uint32_t dO = tmem_base + (uint32_t)O_COL;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t ko = (uint64_t)(k * 2);
-                    umma_tf32_ts(dO, a_hi + (uint32_t)(k * 8), vhd + ko, ID_O, (c == 0 && k == 0) ? 0u : 1u);
-                    umma_tf32_ts(dO, a_hi + (uint32_t)(k * 8), vld + ko, ID_O, 1u);
-                    umma_tf32_ts(dO, a_lo + (uint32_t)(k * 8), vhd + ko, ID_O, 1u);
-                }
-                umma_commit(&pv_done[c]);
-                if (c == NKC - 1) umma_commit(o_full);
             }
         }
     } else if (warp < 4) {
         // ===================== warps 2, 3: lo(V^T) chunks, 64 threads x 16 float4 per 16 KB chunk =====================
         const int t64 = (warp - 2) * 32 + lane;
-        for (int c = 0; c < NKC; ++c) {
-            mbar_wait(&v_full[c], 0);
-            const uint32_t vh = smem_u32(smem + (c % NSLOT_V) * SLOT_V);
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t ip = (uint32_t)it & 1u;
+            for (int c = 0; c < NKC; ++c) {
+                mbar_wait(&v_full[c], ip);
+                const uint32_t vh = smem_u32(v_slot(c));
 #pragma unroll 4
-            for (int i = t64; i < TILE_V / 16; i += 64) lo_convert_16B(vh + (uint32_t)i * 16u, vh + (uint32_t)TILE_V + (uint32_t)i * 16u);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&vl_full[c]);
+                for (int i = t64; i < TILE_V / 16; i += 64) lo_convert_16B(vh + (uint32_t)i * 16u, vh + (uint32_t)TILE_V + (uint32_t)i * 16u);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&vl_full[c]);
+            }
         }
     } else {
         // ===================== softmax + epilogue: 16 warps, four threads per query row =====================
@@ -357,12 +386,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         const int grp = (warp - 4) >> 2;
         const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-        // ---- phase A: these warps are idle until S is complete, so they produce the lo(q), lo(k) tiles:
-        //      3328 float4 per 32-dim chunk over 512 threads; same offsets in the lo tile (the swizzle is positional) ----
-        {
-            const int t512 = threadIdx.x - 128;
+        const int t512 = threadIdx.x - 128;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int qt = item % args.n_qtiles, bh = item / args.n_qtiles, h = bh % args.H, b = bh / args.H;
+            const uint32_t ip = (uint32_t)it & 1u;
+            // ---- phase A: these warps are idle until S is complete, so they produce the lo(q), lo(k) tiles:
+            //      3328 float4 per 32-dim chunk over 512 threads; same offsets in the lo tile (the swizzle is positional) ----
             for (int kc = 0; kc < DK / KC; ++kc) {
-                const int s = kc & 1; const uint32_t ph = (kc >> 1) & 1;
+                const int s = STAGE_OF(kc); const uint32_t ph = (uint32_t)USE_OF(it, kc) & 1u;
                 mbar_wait(&full_a[s], ph);
                 const uint32_t st = smem_u32(smem + s * STAGE_A);
 #pragma unroll
@@ -374,111 +406,117 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&conv_a[s]);
             }
-        }
-        mbar_wait(s_full, 0);
-        tc_fence_after();
-        ATT_DBG(3);
-        // ---- pass 1: row max over the T valid keys ----
-        float mx = -3.402823466e+38f;
-        for (int c = grp; c < NKC; c += NGRP) {
-            uint32_t v[32];
-            tmem_ld32(trow + (uint32_t)(c * KC), v);
-            if (c * KC + 32 <= T) {                       // warp-uniform: full chunk, no per-element masking
+            mbar_wait(s_full, ip);
+            tc_fence_after();
+            ATT_DBG_IT(3);
+            // ---- pass 1: row max over the T valid keys ----
+            float mx = -3.402823466e+38f;
+            for (int c = grp; c < NKC; c += NGRP) {
+                uint32_t v[32];
+                tmem_ld32(trow + (uint32_t)(c * KC), v);
+                if (c * KC + 32 <= T) {                       // warp-uniform: full chunk, no per-element masking
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-            } else {
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) if (c * KC + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
-            }
-        }
-        xch[grp * AQ + r] = mx;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        mx = fmaxf(fmaxf(xch[r], xch[AQ + r]), fmaxf(xch[2 * AQ + r], xch[3 * AQ + r]));
-        ATT_DBG(4);
-        // ---- pass 2: e = exp(s - max) = 2^((s - max) * log2 e): one FFMA + one MUFU.EX2 per element (ex2.approx is
-        //      accurate to ~2^-22 relative, the same class as the reference's degree-7 polynomial), then the tf32
-        //      hi/lo split, stored to tensor memory (tcgen05.st) as the A operand of P.V ----
-        const float L2E = args.scale_l2e;               // scores are unscaled: exp((s - max) * scale) = 2^((s - max) * scale * log2 e)
-        const float nmx = -__fmul_rn(mx, L2E);
-        float psum = 0.0f;
-        for (int c = grp; c < NKC; c += NGRP) {
-            const bool dbgw = args.dbg && warp == 4 && lane == 0;
-            if (dbgw) dbg_c[c / NGRP][0] = clock64();
-            uint32_t v[32];
-            tmem_ld32(trow + (uint32_t)(c * KC), v);
-            if (dbgw) dbg_c[c / NGRP][1] = clock64();
-            float e[32];
-            if (c * KC + 32 <= T) {                       // warp-uniform fast path: full chunk
-#pragma unroll
-                for (int i = 0; i < 32; ++i) e[i] = ex2_approx(__fmaf_rn(__uint_as_float(v[i]), L2E, nmx));
-            } else {                                      // last chunk: keys >= T contribute exactly 0
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float t = ex2_approx(__fmaf_rn(__uint_as_float(v[i]), L2E, nmx));
-                    e[i] = (c * KC + i < T) ? t : 0.0f;
+                    for (int i = 0; i < 32; ++i) if (c * KC + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
             }
-            {   // pairwise tree keeps the dependent-add chain short
-                float t8[8];
+            xch[grp * AQ + r] = mx;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            mx = fmaxf(fmaxf(xch[r], xch[AQ + r]), fmaxf(xch[2 * AQ + r], xch[3 * AQ + r]));
+            ATT_DBG_IT(4);
+            // ---- pass 2: e = exp(s - max) = 2^((s - max) * log2 e): one FFMA + one MUFU.EX2 per element (ex2.approx is
+            //      accurate to ~2^-22 relative, the same class as the reference's degree-7 polynomial), then the tf32
+            //      hi/lo split, stored to tensor memory (tcgen05.st) as the A operand of P.V ----
+            const float L2E = args.scale_l2e;               // scores are unscaled: exp((s - max) * scale) = 2^((s - max) * scale * log2 e)
+            const float nmx = -__fmul_rn(mx, L2E);
+            float psum = 0.0f;
+            for (int c = grp; c < NKC; c += NGRP) {
+                const bool dbgw = args.dbg && warp == 4 && lane == 0 && it == dbg_it;
+                if (dbgw) dbg_c[c / NGRP][0] = clock64();
+                uint32_t v[32];
+                tmem_ld32(trow + (uint32_t)(c * KC), v);
+                if (dbgw) dbg_c[c / NGRP][1] = clock64();
+                float e[32];
+                if (c * KC + 32 <= T) {                       // warp-uniform fast path: full chunk
 #pragma unroll
-                for (int i = 0; i < 8; ++i) t8[i] = (e[i] + e[i + 8]) + (e[i + 16] + e[i + 24]);
-                psum += ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
-            }
-            if (dbgw) dbg_c[c / NGRP][2] = clock64();
-            uint32_t lo[32];
+                    for (int i = 0; i < 32; ++i) e[i] = ex2_approx(__fmaf_rn(__uint_as_float(v[i]), L2E, nmx));
+                } else {                                      // last chunk: keys >= T contribute exactly 0
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float hi = tf32_hi(e[i]);
-                lo[i] = __float_as_uint(__fsub_rn(e[i], hi));
-                v[i] = __float_as_uint(hi);
+                    for (int i = 0; i < 32; ++i) {
+                        const float t = ex2_approx(__fmaf_rn(__uint_as_float(v[i]), L2E, nmx));
+                        e[i] = (c * KC + i < T) ? t : 0.0f;
+                    }
+                }
+                {   // pairwise tree keeps the dependent-add chain short
+                    float t8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t8[i] = (e[i] + e[i + 8]) + (e[i + 16] + e[i + 24]);
+                    psum += ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
+                }
+                if (dbgw) dbg_c[c / NGRP][2] = clock64();
+                uint32_t lo[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float hi = tf32_hi(e[i]);
+                    lo[i] = __float_as_uint(__fsub_rn(e[i], hi));
+                    v[i] = __float_as_uint(hi);
+                }
+                tmem_st32(trow + (uint32_t)(c * KC), v);              // hi(P) over the S chunk this warp just consumed
+                if (c >= NSLOT_PL) mbar_wait(&pv_done[c - NSLOT_PL], ip);   // the lo slot's previous user has been multiplied
+                if (dbgw) dbg_c[c / NGRP][3] = clock64();
+                tmem_st32(trow + (uint32_t)(PL_COL + (c % NSLOT_PL) * KC), lo);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[c]);
+                if (dbgw) dbg_c[c / NGRP][4] = clock64();
             }
-            tmem_st32(trow + (uint32_t)(c * KC), v);              // hi(P) over the S chunk this warp just consumed
-            if (c >= NSLOT_PL) mbar_wait(&pv_done[c - NSLOT_PL], 0);   // the lo slot's previous user has been multiplied
-            if (dbgw) dbg_c[c / NGRP][3] = clock64();
-            tmem_st32(trow + (uint32_t)(PL_COL + (c % NSLOT_PL) * KC), lo);
-            tmem_st_wait();
-            tc_fence_before();
+            ATT_DBG_IT(5);
+            // exchange the partial row sums (a second barrier id keeps the max / sum exchanges apart; the max exchange of
+            // the NEXT item cannot start before every thread has passed this barrier, and vice versa)
+            xch[4 * AQ + grp * AQ + r] = psum;
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(xch[4 * AQ + r], xch[5 * AQ + r]), __fadd_rn(xch[6 * AQ + r], xch[7 * AQ + r])));
+            // ---- epilogue: O / sum -> att (+ per-clip min/max): each warp owns 32 rows x 32 dims, staged in a swizzled
+            //      4 KB tile and written by one TMA tensor store (rows >= T are clipped by the 3-D map) ----
+            mbar_wait(o_full, ip);
+            tc_fence_after();
+            ATT_DBG_IT(6);
+            const uint32_t stg = smem_u32(smem) + (uint32_t)(warp - 4) * 4096u;   // V slots 3, 4 are idle now (all MMAs retired)
+            const int row0 = qt * AQ + quad * 32;
+            if (row0 < T) {                                   // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(trow + (uint32_t)(O_COL + grp * 32), v);
+                float mn = 3.402823466e+38f, mxo = -3.402823466e+38f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float o0 = __fmul_rn(__uint_as_float(v[q * 4 + 0]), inv), o1 = __fmul_rn(__uint_as_float(v[q * 4 + 1]), inv);
+                    const float o2 = __fmul_rn(__uint_as_float(v[q * 4 + 2]), inv), o3 = __fmul_rn(__uint_as_float(v[q * 4 + 3]), inv);
+                    mn = fminf(fminf(mn, o0), fminf(fminf(o1, o2), o3));
+                    mxo = fmaxf(fmaxf(mxo, o0), fmaxf(fmaxf(o1, o2), o3));
+                    sts_v4f(stg + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), o0, o1, o2, o3);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tma_store_3d(&map_out, stg, h * DK + grp * 32, row0, b);
+                if (args.minmax_keys) {
+                    const bool ok = row0 + lane < T;
+                    mn = lb_warp_min(ok ? mn : 3.402823466e+38f); mxo = lb_warp_max(ok ? mxo : -3.402823466e+38f);
+                    if (lane == 0) lb_mm_update(args.minmax_keys, b, mn, mxo);
+                }
+                if (lane == 0) tma_store_wait_read();          // the staging tile must outlive the bulk store's READ only
+            }
+            tc_fence_before();                                 // this warp's TMEM reads of O are done (the next item's P.V overwrites O)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[c]);
-            if (dbgw) dbg_c[c / NGRP][4] = clock64();
+            if (lane == 0) mbar_arrive(epi_done);
+            ATT_DBG_IT(7);
         }
-        ATT_DBG(5);
-        // exchange the partial row sums (xch was last read before every thread passed the first named barrier +
-        // its own pass 2; a second barrier id keeps the max / sum exchanges apart)
-        xch[4 * AQ + grp * AQ + r] = psum;
-        asm volatile("bar.sync 2, 512;" ::: "memory");
-        const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(xch[4 * AQ + r], xch[5 * AQ + r]), __fadd_rn(xch[6 * AQ + r], xch[7 * AQ + r])));
-        // ---- epilogue: O / sum -> att (+ per-clip min/max): each warp owns 32 rows x 32 dims, staged in a swizzled
-        //      4 KB tile and written by one TMA tensor store (rows >= T are clipped by the 3-D map) ----
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        ATT_DBG(6);
-        const uint32_t stg = smem_u32(smem) + (uint32_t)(warp - 4) * 4096u;   // phase-C buffers are idle now (all MMAs retired)
-        const int row0 = qt * AQ + quad * 32;
-        if (row0 < T) {                                   // warp-uniform
-            uint32_t v[32];
-            tmem_ld32(trow + (uint32_t)(O_COL + grp * 32), v);
-            float mn = 3.402823466e+38f, mxo = -3.402823466e+38f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float o0 = __fmul_rn(__uint_as_float(v[q * 4 + 0]), inv), o1 = __fmul_rn(__uint_as_float(v[q * 4 + 1]), inv);
-                const float o2 = __fmul_rn(__uint_as_float(v[q * 4 + 2]), inv), o3 = __fmul_rn(__uint_as_float(v[q * 4 + 3]), inv);
-                mn = fminf(fminf(mn, o0), fminf(fminf(o1, o2), o3));
-                mxo = fmaxf(fmaxf(mxo, o0), fmaxf(fmaxf(o1, o2), o3));
-                sts_v4f(stg + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), o0, o1, o2, o3);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) tma_store_3d(&map_out, stg, h * DK + grp * 32, row0, b);
-            if (args.minmax_keys) {
-                const bool ok = row0 + lane < T;
-                mn = lb_warp_min(ok ? mn : 3.402823466e+38f); mxo = lb_warp_max(ok ? mxo : -3.402823466e+38f);
-                if (lane == 0) lb_mm_update(args.minmax_keys, b, mn, mxo);
-            }
-            if (lane == 0) tma_store_wait_read();          // the staging tile must outlive the bulk store's READ only
-        }
-        ATT_DBG(7);
     }
+#undef STAGE_OF
+#undef USE_OF
+#undef ATT_DBG_IT
 
     tc_fence_before();
     __syncthreads();
@@ -486,7 +524,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
-    if (args.dbg && threadIdx.x == 0 && (blockIdx.x == 300 || blockIdx.x == 301 || blockIdx.x == 302)) {
+    if (args.dbg && threadIdx.x == 0 && (blockIdx.x == 60 || blockIdx.x == 61 || blockIdx.x == 62) && (int)blockIdx.x + dbg_it * (int)gridDim.x < n_items) {
         const long long t0 = dbg_t[0][0];
         printf("ATTDBG blk %d A0 %lld A3 %lld | S_done %lld p1 %lld p2 %lld/%lld O_done %lld epi %lld/%lld end %lld\n", blockIdx.x, dbg_t[1][1] - t0,
                dbg_t[1][2] - t0, dbg_t[4][3] - t0, dbg_t[4][4] - t0, dbg_t[4][5] - t0, dbg_t[8][5] - t0, dbg_t[4][6] - t0, dbg_t[4][7] - t0,
@@ -496,7 +534,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
                    dbg_c[i][3] - t0, dbg_c[i][4] - t0);
     }
 }
-
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -618,7 +655,9 @@ int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, i
     a.dbg = getenv("LELE_B200_ATTN_DBG") ? 1 : 0;
     static thread_local bool attr_done = false;
     if (!attr_done) { LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_done = true; }
-    LB_CHECK_CUDA(lb_launch_pdl(attn_tc_kernel, dim3(B * H * a.n_qtiles), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, mqh, mkh, mvh, mout, a));
+    const int n_items = B * H * a.n_qtiles;
+    const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;     // persistent: one CTA per SM walks the items
+    LB_CHECK_CUDA(lb_launch_pdl(attn_tc_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, mqh, mkh, mvh, mout, a));
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }
