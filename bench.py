@@ -59,6 +59,9 @@ def cpu_baseline_run(blob, n_threads, first_clip, n_samples=N_SAMPLES):
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvidia-smi needs ~100 ms to start and the timed region is ~120 ms, so the sampler is started before the warm-up and
+    # every sample is stamped with the host clock: the report uses the samples inside [mark_begin, mark_end] (the timed
+    # region) and falls back to everything taken under load (warm-up + timed region) when fewer than 3 fall inside.
 
     def __init__(self, gpu_index):
         self.proc = None
@@ -76,7 +79,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -86,8 +95,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        inside = [ln for (ts, ln) in self.lines if t0 is not None and t1 is not None and t0 <= ts <= t1 + 0.02]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
         sm, smax, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -100,7 +115,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(pw)), "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def run_reference(args):
@@ -209,12 +225,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    if sampler:
+        sampler.mark_begin()
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -224,6 +242,8 @@ def run_ours(args):
     host_enqueue_ms = (time.perf_counter() - th0) * 1000.0 / args.steps   # CPU time to enqueue one step (no sync inside)
     e1.record(stream)
     barrier()
+    if sampler:
+        sampler.mark_end()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)

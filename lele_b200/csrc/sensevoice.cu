@@ -192,9 +192,10 @@ struct lele_b200_sensevoice {
     // workspace slices, own min/max keys).  Every kernel of the layer body is a short (20-120 us) launch separated
     // from its successor by a drain / launch / pipeline-ramp gap; with two independent chains in flight one lane's
     // CTAs fill the SMs while the other lane's kernel drains.  Clips are independent end to end, so this is the same
-    // computation (bit-identical per clip).  LELE_B200_LANES=1 disables.
+    // computation (bit-identical per clip).  Measured: +1.5 % with 2 lanes before the attention kernel became persistent, -0.6 % after
+    // (both kernels of a pair now hold every SM for their whole life), so the default is 1; LELE_B200_LANES=2..4 enables.
     static constexpr int MAX_LANES = 4;
-    int n_lanes = 2;
+    int n_lanes = 1;
     lele_b200_sensevoice* lane[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};   // shallow views (pointers offset per call)
     lele_b200_ctx* lane_ctx[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};      // [0] unused (lane 0 runs on the caller's ctx)
     cudaEvent_t ev_lane_fork = nullptr, ev_lane_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
@@ -337,7 +338,7 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
     {   // clip lanes (see the struct): views are shallow copies whose workspace pointers are re-based per call
         const char* e = getenv("LELE_B200_LANES");
-        m->n_lanes = e ? atoi(e) : 2;
+        m->n_lanes = e ? atoi(e) : 1;
         if (m->n_lanes < 1) m->n_lanes = 1;
         if (m->n_lanes > lele_b200_sensevoice::MAX_LANES) m->n_lanes = lele_b200_sensevoice::MAX_LANES;
         if (m->n_lanes > 1) {
