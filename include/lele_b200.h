@@ -223,6 +223,14 @@ int lele_b200_sensevoice_forward_features(lele_b200_ctx* ctx, lele_b200_sensevoi
 int lele_b200_sensevoice_transcribe_host(lele_b200_ctx* ctx, lele_b200_sensevoice* m,
                                          const float* pcm_host, int n_clips, int n_samples,
                                          int lang, int textnorm, int32_t* ids_host);
+/* Pipelined form of the above (serving loop): submit batch i into slot i % 2, collect it with transcribe_wait(slot).
+ * The H2D copy of the next batch and the D2H of the previous ids run on their own streams, so copies overlap the
+ * forward; pcm_host / ids_host (pinned) must stay valid until the matching wait.  A slot cannot be re-submitted
+ * before it was waited for. */
+int lele_b200_sensevoice_transcribe_host_async(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_host,
+                                               int n_clips, int n_samples, int lang, int textnorm,
+                                               int32_t* ids_host, int slot);
+int lele_b200_sensevoice_transcribe_wait(lele_b200_ctx* ctx, lele_b200_sensevoice* m, int slot);
 /* per-kernel-class device time of the last forward, ms (the analogue of kernels/timing.rs
  * print()): names_host receives up to `cap` const char*, ms_host the summed device time of
  * the class and calls_host its launch-group count; *n_out = classes written.  Only filled when

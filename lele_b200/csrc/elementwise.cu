@@ -80,6 +80,28 @@ __global__ void binary_bcast_kernel(int op, const float* __restrict__ a, const f
         out[i] = bin_op(op, a[oa], b[ob]);
     }
 }
+// Periodic broadcast: one operand has the output's shape, the other is broadcast with index (i / inner) % period
+// (trailing-dims operand such as a bias row: inner = 1; per-channel NC[HW] operand: inner = H*W).  float4 over the big
+// operand; the small operand is read per element (L1-resident) or as float4 when inner == 1.
+__global__ void binary_periodic_kernel(int op, const float* __restrict__ big, const float* __restrict__ small, long long total, long long inner,
+                                       long long period, int small_is_a, float* __restrict__ out) {
+    const long long nv = total >> 2, stride = (long long)gridDim.x * blockDim.x;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += stride) {
+        const long long i = q << 2;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(big) + q);
+        float s0, s1, s2, s3;
+        if (inner == 1) {                                   // period % 4 == 0 (checked by the caller): 4 consecutive small elements
+            const float4 y = __ldg(reinterpret_cast<const float4*>(small + (i % period)));
+            s0 = y.x; s1 = y.y; s2 = y.z; s3 = y.w;
+        } else {                                            // inner % 4 == 0: the 4 elements share one small element
+            s0 = s1 = s2 = s3 = __ldg(small + (i / inner) % period);
+        }
+        float4 r;
+        if (small_is_a) r = make_float4(bin_op(op, s0, x.x), bin_op(op, s1, x.y), bin_op(op, s2, x.z), bin_op(op, s3, x.w));
+        else r = make_float4(bin_op(op, x.x, s0), bin_op(op, x.y, s1), bin_op(op, x.z, s2), bin_op(op, x.w, s3));
+        reinterpret_cast<float4*>(out)[q] = r;
+    }
+}
 __global__ void where_kernel(const float* __restrict__ c, const float* __restrict__ x, const float* __restrict__ y, Bcast bc,
                              float* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < bc.total; i += (long long)gridDim.x * blockDim.x) {
@@ -121,9 +143,19 @@ __device__ __forceinline__ float un_op(int op, float v, bool simd) {
     return v;
 }
 __global__ void unary_kernel(int op, const float* __restrict__ x, long long len, float* __restrict__ out) {
-    const long long simd_end = (len / 8) * 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
-        out[i] = un_op(op, x[i], i < simd_end);
+    const long long simd_end = (len / 8) * 8, stride = (long long)gridDim.x * blockDim.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0) {      // float4 body (a float4 never straddles the 8-element SIMD boundary)
+        const long long nv = len >> 2;
+        for (long long q = t; q < nv; q += stride) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + q);
+            const bool simd = (q << 2) < simd_end;
+            reinterpret_cast<float4*>(out)[q] = make_float4(un_op(op, v.x, simd), un_op(op, v.y, simd), un_op(op, v.z, simd), un_op(op, v.w, simd));
+        }
+        for (long long i = (nv << 2) + t; i < len; i += stride) out[i] = un_op(op, x[i], i < simd_end);
+        return;
+    }
+    for (long long i = t; i < len; i += stride) out[i] = un_op(op, x[i], i < simd_end);
 }
 __global__ void clip_kernel(const float* __restrict__ x, long long len, float lo, float hi, float* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
@@ -166,7 +198,25 @@ extern "C" int lele_b200_binary(lele_b200_ctx* ctx, int op, const float* a, cons
     if ((na == bc.total || na == 1) && (nb == bc.total || nb == 1)) {   // same-shape / scalar fast paths (math.rs:414-470)
         binary_flat_kernel<<<grid_for(bc.total, 4), 256, 0, ctx->stream>>>(op, a, b, bc.total, na == 1 && bc.total != 1, nb == 1 && bc.total != 1, out);
     } else {
-        binary_bcast_kernel<<<grid_for(bc.total), 256, 0, ctx->stream>>>(op, a, b, bc, out);
+        // periodic fast path: one operand full-size, the other's non-broadcast dims form one contiguous run of output dims
+        bool done = false;
+        if ((na == bc.total) != (nb == bc.total) && bc.total % 4 == 0 && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15) == 0) {
+            const bool small_is_a = nb == bc.total;
+            const long long* ss = small_is_a ? bc.sa : bc.sb;
+            int lo = -1, hi = -1; bool ok = true;
+            for (int d = 0; d < bc.rank; ++d) if (bc.out_shape[d] != 1 && ss[d] != 0) { if (lo < 0) lo = d; hi = d; }
+            long long period = 1, inner = 1, expect = 1;
+            if (lo < 0) ok = false;
+            for (int d = bc.rank - 1; d >= 0 && ok; --d) {
+                if (d > hi) inner *= bc.out_shape[d];
+                else if (d >= lo) { if (bc.out_shape[d] != 1 && ss[d] != expect) ok = false; expect *= bc.out_shape[d]; period *= bc.out_shape[d]; }
+            }
+            if (ok && ((inner == 1 && period % 4 == 0) || (inner > 1 && inner % 4 == 0))) {
+                binary_periodic_kernel<<<grid_for(bc.total, 4), 256, 0, ctx->stream>>>(op, small_is_a ? b : a, small_is_a ? a : b, bc.total, inner, period, small_is_a ? 1 : 0, out);
+                done = true;
+            }
+        }
+        if (!done) binary_bcast_kernel<<<grid_for(bc.total), 256, 0, ctx->stream>>>(op, a, b, bc, out);
     }
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;

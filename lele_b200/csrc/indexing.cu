@@ -16,6 +16,39 @@ __global__ void strided_copy_kernel(const float* __restrict__ in, StridedArgs a,
         out[i] = in[off];
     }
 }
+// Row copy: the innermost output dim is contiguous in the input (stride 1) and a multiple of 4 floats, both sides 16-byte
+// aligned (transpose [0,2,1,3], slice / split along an outer axis, expand of outer dims): the row index is decomposed once
+// per row and the row moves as float4 -- HBM-rate instead of one div/mod chain per element.
+__global__ void __launch_bounds__(256)
+strided_rows_kernel(const float* __restrict__ in, StridedArgs a, long long n_rows, int row_v4, float* __restrict__ out) {
+    const int lanes_per_row = row_v4 >= 32 ? 32 : (row_v4 >= 16 ? 16 : (row_v4 >= 8 ? 8 : 4));
+    const int rows_per_block = 256 / lanes_per_row;
+    const int sub = threadIdx.x % lanes_per_row;
+    for (long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / lanes_per_row; row < n_rows; row += (long long)gridDim.x * rows_per_block) {
+        long long rem = row, off = a.offset;
+        for (int d = a.rank - 2; d >= 0; --d) { const long long c = rem % a.shape[d]; rem /= a.shape[d]; off += c * a.stride[d]; }
+        const float4* src = reinterpret_cast<const float4*>(in + off);
+        float4* dst = reinterpret_cast<float4*>(out + row * (long long)row_v4 * 4);
+        for (int q = sub; q < row_v4; q += lanes_per_row) dst[q] = __ldg(src + q);
+    }
+}
+// gather along axis 0-like layouts with a long contiguous inner run: one sub-warp per gathered row, float4 copies
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ data, long long outer, int axis_dim, int inner_v4, const float* __restrict__ indices, long long n_idx,
+                   float* __restrict__ out) {
+    const int lanes_per_row = inner_v4 >= 32 ? 32 : (inner_v4 >= 16 ? 16 : (inner_v4 >= 8 ? 8 : 4));
+    const int rows_per_block = 256 / lanes_per_row;
+    const int sub = threadIdx.x % lanes_per_row;
+    const long long n_rows = outer * n_idx;
+    for (long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / lanes_per_row; row < n_rows; row += (long long)gridDim.x * rows_per_block) {
+        const long long o = row / n_idx, k = row - o * n_idx;
+        long long idx = (long long)indices[k];
+        if (idx < 0) idx += axis_dim;                             // negative index wrap (manipulation.rs:610)
+        const float4* src = reinterpret_cast<const float4*>(data + (o * axis_dim + idx) * (long long)inner_v4 * 4);
+        float4* dst = reinterpret_cast<float4*>(out + row * (long long)inner_v4 * 4);
+        for (int q = sub; q < inner_v4; q += lanes_per_row) dst[q] = __ldg(src + q);
+    }
+}
 // 32x32 tiled transpose of the two innermost output dims when the innermost INPUT stride is not 1
 // but some other output dim has input stride 1: covers [0,2,1,3]/[0,2,3,1]/2-D transposes
 // (manipulation.rs:644-1080 fast paths) with coalesced reads and writes.
@@ -42,6 +75,20 @@ transpose_tiled_kernel(const float* __restrict__ in, long long in_off, long long
 }
 
 struct ConcatArgs { const float* in[16]; long long axis_len[16]; long long axis_off[16]; int n; };
+// row variant: every input is an [outer, axis_len_s * inner] block of the [outer, total_axis * inner] output; when every
+// block width and offset is a multiple of 4 floats the blocks move as float4 rows, one warp per (outer index, input) row
+__global__ void __launch_bounds__(256)
+concat_rows_kernel(ConcatArgs a, long long outer, long long inner, long long total_axis, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long n_rows = outer * a.n;
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (long long)gridDim.x * 8) {
+        const long long o = row / a.n; const int s = (int)(row - o * a.n);
+        const long long w4 = a.axis_len[s] * inner / 4;
+        const float4* src = reinterpret_cast<const float4*>(a.in[s] + o * a.axis_len[s] * inner);
+        float4* dst = reinterpret_cast<float4*>(out + (o * total_axis + a.axis_off[s]) * inner);
+        for (long long q = lane; q < w4; q += 32) dst[q] = __ldg(src + q);
+    }
+}
 __global__ void concat_kernel(ConcatArgs a, long long outer, long long inner, long long total_axis, float* __restrict__ out) {
     const long long total = outer * total_axis * inner;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -168,6 +215,26 @@ __global__ void resize_nearest_kernel(const float* __restrict__ x, long long nc,
     }
 }
 struct PoolArgs { int h, w, oh, ow, kh, kw, pt, pl, sh, sw, dh, dw; };
+// plane-tiled variant: blockIdx.z = (n, c) plane, 32 x 8 outputs per block, 32-bit index math, window rows walked with
+// the bounds hoisted (the flat kernel pays three 64-bit divisions per output); max is order-independent -> bit-exact
+__global__ void __launch_bounds__(256)
+max_pool2d_plane_kernel(const float* __restrict__ x, PoolArgs a, float* __restrict__ out) {
+    const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ox >= a.ow || oy >= a.oh) return;
+    const float* xp = x + (long long)blockIdx.z * a.h * a.w;
+    float m = -INFINITY;
+    const int ix0 = ox * a.sw - a.pl, iy0 = oy * a.sh - a.pt;
+    for (int ky = 0; ky < a.kh; ++ky) {
+        const int iy = iy0 + ky * a.dh;
+        if (iy < 0 || iy >= a.h) continue;
+        const float* row = xp + iy * a.w;
+        for (int kx = 0; kx < a.kw; ++kx) {
+            const int ix = ix0 + kx * a.dw;
+            if (ix >= 0 && ix < a.w) m = fmaxf(m, __ldg(row + ix));
+        }
+    }
+    out[((long long)blockIdx.z * a.oh + oy) * a.ow + ox] = m;
+}
 __global__ void max_pool2d_kernel(const float* __restrict__ x, long long nc, PoolArgs a, float* __restrict__ out) {
     const long long total = nc * a.oh * a.ow;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -217,6 +284,20 @@ extern "C" int lele_b200_strided_copy(lele_b200_ctx* ctx, const float* in, long 
             return LELE_B200_OK;
         }
     }
+    // row-copy path: contiguous innermost run of >= 16 bytes, everything 16-byte aligned
+    if (rank >= 1 && in_strides[rank - 1] == 1 && out_shape[rank - 1] % 4 == 0 && out_shape[rank - 1] >= 4 && out_shape[rank - 1] <= (1ll << 30) &&
+        ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0 && in_offset % 4 == 0) {
+        bool aligned = true;
+        for (int i = 0; i < rank - 1; ++i) if (out_shape[i] != 1 && in_strides[i] % 4 != 0) aligned = false;
+        if (aligned) {
+            const long long n_rows = a.total / out_shape[rank - 1];
+            const int row_v4 = (int)(out_shape[rank - 1] / 4);
+            const int lanes = row_v4 >= 32 ? 32 : (row_v4 >= 16 ? 16 : (row_v4 >= 8 ? 8 : 4));
+            strided_rows_kernel<<<grid_for(n_rows * lanes), 256, 0, ctx->stream>>>(in, a, n_rows, row_v4, out);
+            LB_LAUNCH_CHECK(ctx);
+            return LELE_B200_OK;
+        }
+    }
     strided_copy_kernel<<<grid_for(a.total), 256, 0, ctx->stream>>>(in, a, out);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
@@ -232,6 +313,13 @@ extern "C" int lele_b200_concat(lele_b200_ctx* ctx, const float* const* inputs, 
         a.in[a.n] = inputs[i]; a.axis_len[a.n] = axis_lens[i]; a.axis_off[a.n] = off; off += axis_lens[i]; ++a.n;
     }
     if (a.n == 0 || outer * off * inner == 0) return LELE_B200_OK;
+    bool rows_ok = ((((uintptr_t)out) & 15) == 0) && (off * inner) % 4 == 0;
+    for (int i = 0; i < a.n; ++i) rows_ok = rows_ok && (a.axis_len[i] * inner) % 4 == 0 && (a.axis_off[i] * inner) % 4 == 0 && ((((uintptr_t)a.in[i]) & 15) == 0) && a.axis_len[i] * inner >= 32;
+    if (rows_ok) {
+        concat_rows_kernel<<<grid_for(outer * a.n * 32), 256, 0, ctx->stream>>>(a, outer, inner, off, out);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
+    }
     concat_kernel<<<grid_for(outer * off * inner), 256, 0, ctx->stream>>>(a, outer, inner, off, out);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
@@ -255,6 +343,13 @@ extern "C" int lele_b200_gather(lele_b200_ctx* ctx, const float* data, long long
                                 const float* indices, long long n_indices, float* out) {
     LB_REQUIRE(ctx && data && indices && out, "gather: NULL argument");
     if (outer * n_indices * inner == 0) return LELE_B200_OK;
+    if (inner % 4 == 0 && inner >= 16 && inner <= (1ll << 30) && ((((uintptr_t)data) | ((uintptr_t)out)) & 15) == 0) {
+        const int inner_v4 = (int)(inner / 4);
+        const int lanes = inner_v4 >= 32 ? 32 : (inner_v4 >= 16 ? 16 : (inner_v4 >= 8 ? 8 : 4));
+        gather_rows_kernel<<<grid_for(outer * n_indices * lanes), 256, 0, ctx->stream>>>(data, outer, axis_dim, inner_v4, indices, n_indices, out);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
+    }
     gather_kernel<<<grid_for(outer * n_indices * inner), 256, 0, ctx->stream>>>(data, outer, axis_dim, inner, indices, n_indices, out);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
@@ -342,6 +437,11 @@ extern "C" int lele_b200_max_pool2d(lele_b200_ctx* ctx, const float* x, int nb, 
     a.ow = (ceil_mode ? (nw + a.sw - 1) / a.sw : nw / a.sw) + 1;
     long long total = (long long)nb * c * a.oh * a.ow;
     if (total <= 0) return LELE_B200_OK;
+    if ((long long)nb * c <= 65535 && lb_ceil_div(a.oh, 8) <= 65535) {
+        max_pool2d_plane_kernel<<<dim3(lb_ceil_div(a.ow, 32), lb_ceil_div(a.oh, 8), nb * c), 256, 0, ctx->stream>>>(x, a, out);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
+    }
     max_pool2d_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(x, (long long)nb * c, a, out);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;

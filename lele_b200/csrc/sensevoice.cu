@@ -182,9 +182,20 @@ struct lele_b200_sensevoice {
     struct GraphKey { const float* pcm; int B, n_samples, lang, textnorm, n_layers; int32_t* ids; float* logits; };
     int use_graph = 1;              // LELE_B200_GRAPH=0 disables
     bool warmed = false;            // one eager forward has run (lazy tables / attributes / scratch are in place)
-    cudaGraphExec_t graph_exec = nullptr;
-    GraphKey graph_key = {};
-    unsigned long long graph_launches = 0;
+    // small cache of captured forwards (the pipelined host entry alternates between two staging buffers)
+    static constexpr int N_GRAPHS = 4;
+    cudaGraphExec_t graph_exec[N_GRAPHS] = {nullptr, nullptr, nullptr, nullptr};
+    GraphKey graph_key[N_GRAPHS] = {};
+    unsigned long long graph_launches[N_GRAPHS] = {0, 0, 0, 0};
+    int graph_next = 0;             // round-robin replacement
+    // pipelined host entry (transcribe_host_async): 2 slots of staging, H2D / D2H on their own streams so the copy of
+    // batch i+1 overlaps the forward of batch i
+    static constexpr int N_SLOTS = 2;
+    float* pcm_slot[N_SLOTS] = {nullptr, nullptr};
+    int32_t* ids_slot[N_SLOTS] = {nullptr, nullptr};
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[N_SLOTS] = {nullptr, nullptr}, ev_fwd[N_SLOTS] = {nullptr, nullptr}, ev_d2h[N_SLOTS] = {nullptr, nullptr};
+    bool slot_busy[N_SLOTS] = {false, false};
     // side stream: the HBM-bound FSMN block runs concurrently with the latency-bound attention (both only read qkv)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -345,7 +356,7 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
             bool ok = cudaEventCreateWithFlags(&m->ev_lane_fork, cudaEventDisableTiming) == cudaSuccess;
             for (int i = 0; i < m->n_lanes && ok; ++i) {
                 lele_b200_sensevoice* v = new lele_b200_sensevoice(*m);
-                v->is_view = true; v->graph_exec = nullptr; v->n_lanes = 1;
+                v->is_view = true; for (int g = 0; g < lele_b200_sensevoice::N_GRAPHS; ++g) v->graph_exec[g] = nullptr; v->n_lanes = 1;
                 for (int j = 0; j < lele_b200_sensevoice::MAX_LANES; ++j) { v->lane[j] = nullptr; v->lane_ctx[j] = nullptr; v->ev_lane_join[j] = nullptr; }
                 m->lane[i] = v;
                 if (i == 0) continue;
@@ -371,7 +382,16 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
                     m->qscratch, m->qscratch2, m->pcm_stage, m->ids_stage, m->attn_scratch};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : m->ev_pool) cudaEventDestroy(e);
-    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    for (int g = 0; g < lele_b200_sensevoice::N_GRAPHS; ++g) if (m->graph_exec[g]) cudaGraphExecDestroy(m->graph_exec[g]);
+    for (int sl = 0; sl < lele_b200_sensevoice::N_SLOTS; ++sl) {
+        if (m->pcm_slot[sl]) cudaFree(m->pcm_slot[sl]);
+        if (m->ids_slot[sl]) cudaFree(m->ids_slot[sl]);
+        if (m->ev_h2d[sl]) cudaEventDestroy(m->ev_h2d[sl]);
+        if (m->ev_fwd[sl]) cudaEventDestroy(m->ev_fwd[sl]);
+        if (m->ev_d2h[sl]) cudaEventDestroy(m->ev_d2h[sl]);
+    }
+    if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
+    if (m->d2h_stream) cudaStreamDestroy(m->d2h_stream);
     if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
@@ -636,29 +656,31 @@ extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensev
         return sv_finish_profile(ctx, m);
     }
     const lele_b200_sensevoice::GraphKey key = {pcm_dev, n_clips, n_samples, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt};
-    if (m->graph_exec && memcmp(&key, &m->graph_key, sizeof(key)) == 0) {
-        LB_CHECK_CUDA(cudaGraphLaunch(m->graph_exec, ctx->stream));
-        ctx->launches += m->graph_launches;
-        return LELE_B200_OK;
-    }
+    for (int g = 0; g < lele_b200_sensevoice::N_GRAPHS; ++g)
+        if (m->graph_exec[g] && memcmp(&key, &m->graph_key[g], sizeof(key)) == 0) {
+            LB_CHECK_CUDA(cudaGraphLaunch(m->graph_exec[g], ctx->stream));
+            ctx->launches += m->graph_launches[g];
+            return LELE_B200_OK;
+        }
     // new shape / pointers: one eager pass (also the warm-up that performs every lazy allocation), then capture
     int rc = sv_forward_eager(ctx, m, pcm_dev, n_clips, n_samples, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
     if (rc) return rc;
     m->warmed = true;
-    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    const int gi = m->graph_next; m->graph_next = (m->graph_next + 1) % lele_b200_sensevoice::N_GRAPHS;
+    if (m->graph_exec[gi]) { cudaGraphExecDestroy(m->graph_exec[gi]); m->graph_exec[gi] = nullptr; }
     const unsigned long long l0 = ctx->launches;
     LB_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     rc = sv_forward_eager(ctx, m, pcm_dev, n_clips, n_samples, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-    m->graph_launches = ctx->launches - l0;
+    m->graph_launches[gi] = ctx->launches - l0;
     ctx->launches = l0;            // captured, not executed
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) { lb_set_error("sensevoice_forward: graph capture failed: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
-    ce = cudaGraphInstantiate(&m->graph_exec, graph, 0);
+    ce = cudaGraphInstantiate(&m->graph_exec[gi], graph, 0);
     cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { m->graph_exec = nullptr; lb_set_error("sensevoice_forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
-    m->graph_key = key;
+    if (ce != cudaSuccess) { m->graph_exec[gi] = nullptr; lb_set_error("sensevoice_forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
+    m->graph_key[gi] = key;
     return LELE_B200_OK;           // this call's result was produced by the eager pass above
 }
 
@@ -673,6 +695,58 @@ extern "C" int lele_b200_sensevoice_transcribe_host(lele_b200_ctx* ctx, lele_b20
     if (rc) return rc;
     LB_CHECK_CUDA(cudaMemcpyAsync(ids_host, m->ids_stage, sizeof(int32_t) * (size_t)n_clips * T, cudaMemcpyDeviceToHost, ctx->stream));
     LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LELE_B200_OK;
+}
+
+// Pipelined host entry: submit batch i into slot i % 2 and collect it later; the H2D copy of the next batch (its own
+// stream) overlaps the forward of the current one, the D2H of the ids (a third stream) overlaps the next forward.
+// pcm_host / ids_host should be pinned; both must stay valid until the matching wait.
+static int sv_pipeline_init(lele_b200_sensevoice* m) {
+    if (m->h2d_stream) return LELE_B200_OK;
+    LB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->h2d_stream, cudaStreamNonBlocking));
+    LB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
+    const size_t B = m->max_clips, M = B * m->max_T;
+    for (int sl = 0; sl < lele_b200_sensevoice::N_SLOTS; ++sl) {
+        int rc = sv_alloc((void**)&m->pcm_slot[sl], sizeof(float) * B * (size_t)m->max_samples);
+        if (!rc) rc = sv_alloc((void**)&m->ids_slot[sl], sizeof(int32_t) * M);
+        if (rc) return rc;
+        LB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_h2d[sl], cudaEventDisableTiming));
+        LB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_fwd[sl], cudaEventDisableTiming));
+        LB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_d2h[sl], cudaEventDisableTiming));
+    }
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_transcribe_host_async(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_host, int n_clips,
+                                                          int n_samples, int lang, int textnorm, int32_t* ids_host, int slot) {
+    LB_REQUIRE(ctx && m && pcm_host && ids_host, "sensevoice_transcribe_host_async: NULL argument");
+    LB_REQUIRE(slot >= 0 && slot < lele_b200_sensevoice::N_SLOTS, "sensevoice_transcribe_host_async: slot %d out of range", slot);
+    LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && n_samples <= m->max_samples, "sensevoice_transcribe_host_async: batch/length exceeds workspace");
+    LB_REQUIRE(!m->slot_busy[slot], "sensevoice_transcribe_host_async: slot %d still in flight (call transcribe_wait first)", slot);
+    int T = lele_b200_sensevoice_rows(m, n_samples);
+    LB_REQUIRE(T > 0, "sensevoice_transcribe_host_async: clip shorter than one frame");
+    int rc = sv_pipeline_init(m);
+    if (rc) return rc;
+    // the slot's staging buffers were last read by the forward / D2H of its previous batch, which transcribe_wait(slot) joined
+    LB_CHECK_CUDA(cudaMemcpyAsync(m->pcm_slot[slot], pcm_host, sizeof(float) * (size_t)n_clips * n_samples, cudaMemcpyHostToDevice, m->h2d_stream));
+    LB_CHECK_CUDA(cudaEventRecord(m->ev_h2d[slot], m->h2d_stream));
+    LB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_h2d[slot], 0));
+    rc = lele_b200_sensevoice_forward(ctx, m, m->pcm_slot[slot], n_clips, n_samples, lang, textnorm, -1, m->ids_slot[slot], nullptr);
+    if (rc) return rc;
+    LB_CHECK_CUDA(cudaEventRecord(m->ev_fwd[slot], ctx->stream));
+    LB_CHECK_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_fwd[slot], 0));
+    LB_CHECK_CUDA(cudaMemcpyAsync(ids_host, m->ids_slot[slot], sizeof(int32_t) * (size_t)n_clips * T, cudaMemcpyDeviceToHost, m->d2h_stream));
+    LB_CHECK_CUDA(cudaEventRecord(m->ev_d2h[slot], m->d2h_stream));
+    m->slot_busy[slot] = true;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_transcribe_wait(lele_b200_ctx* ctx, lele_b200_sensevoice* m, int slot) {
+    LB_REQUIRE(ctx && m, "sensevoice_transcribe_wait: NULL argument");
+    LB_REQUIRE(slot >= 0 && slot < lele_b200_sensevoice::N_SLOTS, "sensevoice_transcribe_wait: slot %d out of range", slot);
+    if (!m->slot_busy[slot]) return LELE_B200_OK;
+    LB_CHECK_CUDA(cudaEventSynchronize(m->ev_d2h[slot]));
+    m->slot_busy[slot] = false;
     return LELE_B200_OK;
 }
 

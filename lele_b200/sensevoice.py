@@ -52,6 +52,14 @@ class SenseVoice:
         call("lele_b200_sensevoice_transcribe_host", self.ctx.h, self.h, vp(pcm_host_ptr), i32(n_clips), i32(n_samples), i32(lang),
              i32(textnorm), vp(ids_host_ptr))
 
+    def transcribe_host_async(self, pcm_host_ptr: int, n_clips: int, n_samples: int, ids_host_ptr: int, slot: int, lang: int = 3, textnorm: int = 0):
+        """Pipelined serving form: submit into slot 0/1, collect with transcribe_wait(slot); copies overlap the forward."""
+        call("lele_b200_sensevoice_transcribe_host_async", self.ctx.h, self.h, vp(pcm_host_ptr), i32(n_clips), i32(n_samples), i32(lang),
+             i32(textnorm), vp(ids_host_ptr), i32(slot))
+
+    def transcribe_wait(self, slot: int):
+        call("lele_b200_sensevoice_transcribe_wait", self.ctx.h, self.h, i32(slot))
+
     # ---- numpy forms ----
     def forward(self, speech, language: int = 3, text_norm: int = 0, n_layers: int = -1, want_ids: bool = False):
         """model.forward(speech [B,T,560] or [T,560], speech_lengths, language, text_norm) -> logits [B,T+4,vocab]

@@ -94,6 +94,28 @@ def test_clip_lanes_bit_identical(lanes, monkeypatch):
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
 
 
+def test_pipelined_host_entry_matches_blocking(small_model_tc):
+    """transcribe_host_async / transcribe_wait (two batches in flight, copies on their own streams) returns exactly the ids
+    of the blocking entry for every batch, in submission order; a busy slot is refused."""
+    import torch
+    from lele_b200 import LeleB200Error
+    blob, m = small_model_tc
+    batches = [synth_batch(10 * i, 3, 16000 * 2) for i in range(5)]
+    want = [m.transcribe(b) for b in batches]
+    T = want[0].shape[1]
+    pins = [torch.from_numpy(b).pin_memory() for b in batches]
+    outs = [torch.zeros((3, T), dtype=torch.int32).pin_memory() for _ in batches]
+    for i, p in enumerate(pins):
+        if i >= 2:
+            m.transcribe_wait(i % 2)
+        m.transcribe_host_async(p.data_ptr(), 3, p.shape[1], outs[i].data_ptr(), i % 2)
+    with pytest.raises(LeleB200Error):
+        m.transcribe_host_async(pins[0].data_ptr(), 3, pins[0].shape[1], outs[0].data_ptr(), (len(pins) - 1) % 2)   # still in flight
+    m.transcribe_wait(0); m.transcribe_wait(1)
+    for w, o in zip(want, outs):
+        np.testing.assert_array_equal(w, o.numpy())
+
+
 def test_tc_network_close_to_oracle(small_model_tc):
     """Whole small network with the tensor-core attention: f32-grade attention differences can flip
     individual u8 roundings of the next dynamic quantiser (1 LSB), so the bar is normwise."""
