@@ -57,11 +57,12 @@ def cpu_baseline_run(blob, n_threads, first_clip, n_samples=N_SAMPLES):
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING the run through NVML (in-process; the nvidia-smi CLI in a 20 ms loop
-    was measured to slow the timed region by ~10 %).  The timed region is ~120 ms, so sampling starts before the warm-up and
-    every sample carries a host time stamp: the report uses the samples inside [mark_begin, mark_end] and falls back to
-    everything taken under load (warm-up + timed region) when fewer than 3 fall inside."""
-    PERIOD_S = 0.04
+    """SM clock / power / throttle reasons sampled DURING the run through NVML (the same counters as the recipe's nvidia-smi
+    line, in-process), started before the warm-up and stopped after the timed region.  Queries go through the GPU's
+    management firmware and were measured to slow the ~120 ms timed region by 5-10 % at 20-40 ms periods, so the recipe's
+    200 ms period is kept; every sample carries a host time stamp: the report uses the samples inside
+    [mark_begin, mark_end] and falls back to everything taken under load (warm-up + timed region) when fewer than 3 fall inside."""
+    PERIOD_S = 0.2      # the profiling recipe's rate (nvidia-smi -lms 200); 25-40 ms periods slowed the timed region by 5-10 %
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
