@@ -423,6 +423,165 @@ ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ g
                t_dbg[2] - t_dbg[0], t_dbg[3] - t_dbg[0], t_dbg[4] - t_dbg[0], clock64() - t_dbg[0]);
 }
 
+
+// ---- register-row variant: the clip's rows do not fit the chip's shared memory in one wave (64 clips x 275 rows x 2 KB =
+// 36 MB vs 33.6 MB), so with shared memory alone 512 CTAs run as 444 + 68 -- two waves, the second almost empty.  Here every
+// warp keeps RR of its rows in REGISTERS (loaded with plain coalesced loads) and only the rest goes through the bulk-copy /
+// shared-memory path: 27 instead of 35 rows of shared memory per CTA -> 4 CTAs per SM -> all 512 CTAs resident at once.
+// Same arithmetic as ln_quant_cluster_kernel (bit-identical outputs).
+template <int LNQ_CS, int LNQ_WARPS, int MINB, int RR>
+__global__ void __launch_bounds__(LNQ_WARPS * 32, MINB)
+ln_quant_cluster_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int T, float eps,
+                            uint8_t* __restrict__ a_u8, int32_t* __restrict__ rowsum, float* __restrict__ row_scale, int32_t* __restrict__ row_zp,
+                            unsigned* __restrict__ keys_out) {
+    namespace cg = cooperative_groups;
+    constexpr int N = 512, NB = 16;
+    extern __shared__ __align__(16) float lnq_rows[];            // [n_smem][512] normalised rows (the CTA's rows after the register rows)
+    __shared__ float red[2][32];
+    __shared__ float peer_mm[LNQ_CS][2];
+    __shared__ __align__(8) unsigned long long chunk_bar[LNQ_MAX_CHUNKS];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int clip = blockIdx.y;
+    const int R = (T + LNQ_CS - 1) / LNQ_CS;
+    const int r_begin = rank * R, r_end = min(T, r_begin + R);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xc = x + (long long)clip * T * N;
+    const int n_rows = max(r_end - r_begin, 0);
+    const int n_reg = min(LNQ_WARPS * RR, n_rows);              // rows [0, n_reg) of the CTA live in registers (row r -> warp r % NW)
+    const int n_smem = n_rows - n_reg;
+    const int n_chunks = (n_smem + LNQ_CHUNK - 1) / LNQ_CHUNK;
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < n_chunks; ++c)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&chunk_bar[c])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    lb_pdl_launch_dependents();
+    lb_pdl_wait();                 // PDL: x is the previous kernel's output
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < n_chunks; ++c) {
+            const int rows = min(LNQ_CHUNK, n_smem - c * LNQ_CHUNK);
+            const uint32_t bytes = (uint32_t)rows * N * 4;
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&chunk_bar[c]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(lnq_rows + (size_t)c * LNQ_CHUNK * N)),
+                           "l"(xc + (long long)(r_begin + n_reg + c * LNQ_CHUNK) * N), "r"(bytes), "r"(bar) : "memory");
+        }
+    }
+    float yr[RR][NB];
+#pragma unroll
+    for (int i = 0; i < RR; ++i) {                               // register rows: plain coalesced loads, all in flight
+        const int r = warp + i * LNQ_WARPS;
+        if (r < n_reg) {
+            const float* src = xc + (long long)(r_begin + r) * N;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) yr[i][j] = __ldg(src + 32 * j + lane);
+        }
+    }
+    float g[NB], bt[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { g[i] = __ldg(gamma + 32 * i + lane); bt[i] = __ldg(beta + 32 * i + lane); }
+    const float inv_n = __fdiv_rn(1.0f, (float)N);
+    float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+    auto normalise = [&](float (&v)[NB]) {                       // v <- LayerNorm(v) (same operation order as ln_quant_cluster_kernel)
+        float ps = 0.0f, pq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { ps = __fadd_rn(ps, v[i]); pq = __fmaf_rn(v[i], v[i], pq); }
+#pragma unroll
+        for (int of = 8; of <= 16; of <<= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, of)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, of)); }
+#pragma unroll
+        for (int of = 4; of >= 1; of >>= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, of)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, of)); }
+        ps = __shfl_sync(0xffffffffu, ps, 0); pq = __shfl_sync(0xffffffffu, pq, 0);
+        const float mean = __fmul_rn(ps, inv_n);
+        const float var = __fsub_rn(__fmul_rn(pq, inv_n), __fmul_rn(mean, mean));
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const float y = __fmaf_rn(__fmul_rn(__fsub_rn(v[i], mean), inv), g[i], bt[i]);
+            vmin = fminf(vmin, y); vmax = fmaxf(vmax, y);
+            v[i] = y;
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < RR; ++i)
+        if (warp + i * LNQ_WARPS < n_reg) normalise(yr[i]);
+    for (int r = warp; r < n_smem; r += LNQ_WARPS) {
+        {   // wait for the chunk holding shared-memory row r (single use: parity 0)
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&chunk_bar[r / LNQ_CHUNK]);
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar) : "memory");
+        }
+        float* o = lnq_rows + (size_t)r * N;
+        float v[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) v[i] = o[32 * i + lane];
+        normalise(v);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) o[32 * i + lane] = v[i];
+    }
+    vmin = lb_warp_min(vmin); vmax = lb_warp_max(vmax);
+    if (lane == 0) { red[0][warp] = vmin; red[1][warp] = vmax; }
+    __syncthreads();
+    if (warp == 0) {
+        float a = lane < LNQ_WARPS ? red[0][lane] : 3.402823466e+38f, b = lane < LNQ_WARPS ? red[1][lane] : -3.402823466e+38f;
+        a = lb_warp_min(a); b = lb_warp_max(b);
+        if (lane < LNQ_CS) {
+            float* dst = cluster.map_shared_rank(&peer_mm[rank][0], lane);
+            dst[0] = a; dst[1] = b;
+        }
+    }
+    cluster.sync();
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+#pragma unroll
+    for (int p = 0; p < LNQ_CS; ++p) { mn = fminf(mn, peer_mm[p][0]); mx = fmaxf(mx, peer_mm[p][1]); }
+    if (keys_out && rank == 0 && threadIdx.x == 0) {
+        keys_out[(size_t)clip * LB_MM_SLOTS * 2] = lb_fkey(mn); keys_out[(size_t)clip * LB_MM_SLOTS * 2 + 1] = lb_fkey(mx);
+    }
+    const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);
+    const float range = fmaxf(__fsub_rn(amax, amin), 1e-5f);
+    const float scale = __fdiv_rn(range, 255.0f);
+    const float zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, scale)), 0.0f), 255.0f);
+    const float inv = __fdiv_rn(1.0f, scale);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < RR; ++i) {                               // register rows: lane holds elements 32 j + lane -> byte stores, 32 B per warp store
+        const int r = warp + i * LNQ_WARPS;
+        if (r < n_reg) {
+            const long long row = (long long)clip * T + r_begin + r;
+            uint8_t* dst = a_u8 + row * N + lane;
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const unsigned q = min(__float2uint_rn(__fmaf_rn(yr[i][j], inv, zp)), 255u);
+                sum += (int)q;
+                dst[32 * j] = (uint8_t)q;
+            }
+            sum = lb_warp_sum_i(sum);
+            if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
+        }
+    }
+    for (int r = warp; r < n_smem; r += LNQ_WARPS) {
+        const float4* y4 = reinterpret_cast<const float4*>(lnq_rows + (size_t)r * N);
+        const long long row = (long long)clip * T + r_begin + n_reg + r;
+        unsigned* a4 = reinterpret_cast<unsigned*>(a_u8 + row * N);
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < N / 128; ++j) {
+            const float4 y = y4[lane + 32 * j];
+            const unsigned q0 = min(__float2uint_rn(__fmaf_rn(y.x, inv, zp)), 255u), q1 = min(__float2uint_rn(__fmaf_rn(y.y, inv, zp)), 255u);
+            const unsigned q2 = min(__float2uint_rn(__fmaf_rn(y.z, inv, zp)), 255u), q3 = min(__float2uint_rn(__fmaf_rn(y.w, inv, zp)), 255u);
+            sum += (int)(q0 + q1 + q2 + q3);
+            a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+        }
+        sum = lb_warp_sum_i(sum);
+        if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
+    }
+}
+
 static int lnq_cluster_size() {
     static int cs = 0;
     if (!cs) { const char* e = getenv("LELE_B200_LNQ_CS"); cs = (e && e[0] == '4') ? 4 : 8; }
@@ -438,6 +597,21 @@ int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const flo
     if (clips == 0) return LELE_B200_OK;
     const int CS = lnq_cluster_size();
     static const int dbg = getenv("LELE_B200_LNQ_DBG") ? 1 : 0;
+    // register-row variant (CS = 8): 4 warps x 2 register rows, the other rows in shared memory -> 4 CTAs per SM, one wave
+    if (CS == 8 && lb_env_flag("LELE_B200_LNQ_REG", 0)) {   // opt-in: the kernel itself is faster (18.6 vs 22 us) but the replayed step is not (PDL overlap), so the default stays
+        const int R = (T + CS - 1) / CS;
+        const size_t smem_r = (size_t)(R > 8 ? R - 8 : 0) * 512 * 4;
+        if (smem_r <= 56 * 1024 && (R > 8 ? R - 8 : 0) <= LNQ_CHUNK * LNQ_MAX_CHUNKS) {
+            static thread_local size_t smem_r_set = 0;
+            if (smem_r > smem_r_set || smem_r_set == 0) {
+                LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_reg_kernel<8, 4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_r ? smem_r : 16)));
+                smem_r_set = smem_r ? smem_r : 16;
+            }
+            LB_CHECK_CUDA(lb_launch_pdl(ln_quant_cluster_reg_kernel<8, 4, 4, 2>, dim3(CS, clips, 1), dim3(4 * 32), smem_r, ctx->stream, CS, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out));
+            LB_LAUNCH_CHECK(ctx);
+            return LELE_B200_OK;
+        }
+    }
     const size_t smem = (size_t)((T + CS - 1) / CS) * 512 * 4;
     static thread_local size_t smem_set = 0;
     if (smem > smem_set) {

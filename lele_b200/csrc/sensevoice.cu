@@ -681,6 +681,8 @@ extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensev
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { m->graph_exec[gi] = nullptr; lb_set_error("sensevoice_forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
     m->graph_key[gi] = key;
+    cudaGraphUpload(m->graph_exec[gi], ctx->stream);   // pre-stage the executable graph on the device: the first replay then costs what every replay costs
+    cudaGetLastError();
     return LELE_B200_OK;           // this call's result was produced by the eager pass above
 }
 
