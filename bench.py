@@ -57,46 +57,31 @@ def cpu_baseline_run(blob, n_threads, first_clip, n_samples=N_SAMPLES):
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING the run through NVML (the same counters as the recipe's nvidia-smi
-    line, in-process), started before the warm-up and stopped after the timed region.  Queries go through the GPU's
-    management firmware and were measured to slow the ~120 ms timed region by 5-10 % at 20-40 ms periods, so the recipe's
-    200 ms period is kept; every sample carries a host time stamp: the report uses the samples inside
+    """The profiling recipe's clocks line: `nvidia-smi --query-gpu=... -lms 200` started before the warm-up and killed after the
+    timed region (B200_PROFILING.md).  Denser sampling, and in-process NVML queries at any rate, were measured to slow the
+    ~120 ms timed region by 4-10 % (the queries go through the GPU's management firmware), so the recipe's separate process
+    and period are kept.  Every line is stamped with the host clock on arrival: the report uses the samples inside
     [mark_begin, mark_end] and falls back to everything taken under load (warm-up + timed region) when fewer than 3 fall inside."""
-    PERIOD_S = 0.2      # the profiling recipe's rate (nvidia-smi -lms 200); 25-40 ms periods slowed the timed region by 5-10 %
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
+        self.proc = None
         self.gpu = gpu_index
-        self.samples = []          # (t, sm_mhz, sm_max_mhz, power_w, reasons bitmask)
-        self.stop_flag = False
-        self.thread = None
-        self.err = None
+        self.lines = []
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
-            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-        except Exception as e:    # noqa: BLE001
-            self.err = f"NVML unavailable: {e}"
-            return
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
 
-    def _loop(self):
-        nv = self.nv
-        while not self.stop_flag:
-            try:
-                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else \
-                    int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((time.perf_counter(), sm, self.smax, pw, rs))
-            except Exception as e:    # noqa: BLE001
-                self.err = str(e)
-                return
-            time.sleep(self.PERIOD_S)
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
 
     def mark_begin(self):
         self.t0 = time.perf_counter()
@@ -105,21 +90,35 @@ class ClockSampler:
         self.t1 = time.perf_counter()
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=1.0)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
         t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
-        inside = [x for x in self.samples if t0 is not None and t1 is not None and t0 <= x[0] <= t1 + 0.01]
+        inside = [ln for (ts, ln) in self.lines if t0 is not None and t1 is not None and t0 <= ts <= t1 + 0.05]
         window = "timed region"
         if len(inside) < 3:
-            inside, window = list(self.samples), "warm-up + timed region (timed region shorter than 3 sampling periods)"
-        # NVML clocks-event-reason bits: 0x8 hw_slowdown, 0x40 hw_thermal_slowdown, 0x20 sw_thermal_slowdown, 0x4 sw_power_cap
-        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
-        reasons = sorted({n for x in inside for bit, n in names.items() if x[4] & bit})
-        return {"sm_mhz": float(np.median([x[1] for x in inside])), "sm_max_mhz": float(max(x[2] for x in inside)), "power_w_max": float(max(x[3] for x in inside)),
-                "samples": len(inside), "window": window, "source": "NVML", "reasons": reasons}
+            inside = [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
+        sm, smax, reasons, pw = [], [], set(), []
+        for ln in inside:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(pw)), "samples": len(sm), "window": window,
+                "source": "nvidia-smi -lms 200", "reasons": sorted(reasons)}
 
 
 def run_reference(args):
@@ -244,7 +243,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("LELE_B200_BENCH_NO_CLOCKS")) else None   # (diagnostic switch)
     if sampler:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
