@@ -259,6 +259,23 @@ def test_lstm_gru_larger():
             close(got, ref, atol_frac=1e-4)
 
 
+def test_rnn_resident_kernel_bit_identical(monkeypatch):
+    """The resident-R recurrent kernel (R^T rows in registers + shared memory for the whole sequence) keeps the summation
+    order of the streaming kernel: identical bits for LSTM and GRU at H = 128 (Silero / config-1 class), seq = 175."""
+    rng = np.random.default_rng(17)
+    hid, isz, seq = 128, 128, 175
+    x = rng.standard_normal((seq, 1, isz)).astype(np.float32)
+    w = (rng.standard_normal((1, 4 * hid, isz)) / np.sqrt(isz)).astype(np.float32); r = (rng.standard_normal((1, 4 * hid, hid)) / np.sqrt(hid)).astype(np.float32)
+    b = (0.1 * rng.standard_normal((1, 8 * hid))).astype(np.float32)
+    fast_l = G.lstm(x, w, r, b); fast_g = G.gru(x, w[:, :3 * hid], r[:, :3 * hid], b[:, :6 * hid])
+    monkeypatch.setenv("LELE_B200_RNN_STREAM_R", "1")
+    slow_l = G.lstm(x, w, r, b); slow_g = G.gru(x, w[:, :3 * hid], r[:, :3 * hid], b[:, :6 * hid])
+    for a, bb in zip(fast_l + fast_g, slow_l + slow_g):
+        np.testing.assert_array_equal(a, bb)
+    for got, ref in zip(fast_l, R.lstm(x, w, r, b)):
+        close(got, ref, atol_frac=1e-4)
+
+
 # ---------------------------------------------------------------- indexing (bit-exact)
 def test_indexing_exact():
     rng = np.random.default_rng(8)
