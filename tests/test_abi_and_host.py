@@ -216,3 +216,24 @@ def test_generated_model_fixture_is_consistent():
     assert ops.count("conv2d") + ops.count("conv2d_silu") == 117 and ops.count("conv_transpose") == 1
     blob = m.synth_blob(prog, 7, {int(k): v for k, v in prog["constants"].items()})
     assert len(blob) == 10993208
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract keys, the
+    oracle port on the host cores, bounded by its time budget (here squeezed so the clip shortens to 2 s)."""
+    import json
+    env = dict(os.environ, LELE_B200_REF_BUDGET_S="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "audio-s/s" and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["value"] > 0 and line["steps"] == 1 and line["vs_baseline"] is None and line["scaling"] == "weak"
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == line["value"] and "2 s per step" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["clip_seconds"] == 2 and "SenseVoiceSmall" in line["config"]["workload"]
+    # under torchrun only rank 0 runs the CPU arm; the other ranks exit 0 without work or output
+    out1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=120)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
