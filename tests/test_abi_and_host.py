@@ -222,7 +222,7 @@ def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract keys, the
     oracle port on the host cores, bounded by its time budget (here squeezed so the clip shortens to 2 s)."""
     import json
-    env = dict(os.environ, LELE_B200_REF_BUDGET_S="1")
+    env = dict(os.environ, LELE_B200_REF_BUDGET_S="0.1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
