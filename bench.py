@@ -326,7 +326,7 @@ def run_ours(args):
                 blob_host = build_blob(cfg, seed=1234)
             v, dt = cpu_baseline_run(blob_host, cores, 0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cores} clips x 16 s, one per host thread, full network ({dt:.1f} s wall); scalar C restatement of lele's x86 path, not lele's AVX2 kernels (lele publishes 39.1 audio-s/s on one Apple-Silicon core, README.md:19)"}
+                   "sample": f"{cores} clips x 16 s, one per host thread, full network ({dt:.1f} s wall); C restatement of lele's x86 path (register-blocked AVX-512 VNNI int8 / FMA f32 GEMM micro-kernels where the host has them), not lele's own AVX2 kernels (lele publishes 39.1 audio-s/s on one Apple-Silicon core, README.md:19)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> i32 (f32 epilogue / attention)", "data": "synthetic",
                 "config": {"workload": "SenseVoiceSmall-shaped ASR (70 SANM layers d512 h4 ffn2048, CTC 25055), synthetic 16 kHz x 16 s clips, random-init int8 weights",

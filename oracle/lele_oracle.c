@@ -7,6 +7,14 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__AVX512F__) && defined(__AVX512BW__) && defined(__AVX512VNNI__)
+#include <immintrin.h>
+#define LO_HAVE_VNNI512 1
+#endif
+#if defined(__AVX512F__)
+#include <immintrin.h>
+#define LO_HAVE_AVX512F 1
+#endif
 
 #define LO_PI 3.14159265358979323846f /* std::f32::consts::PI rounds to the same f32 */
 
@@ -310,13 +318,43 @@ void lo_prepare_weights(const uint8_t *w, int k, int n, uint8_t *wt, int32_t *co
     }
 }
 
-void lo_fused_quantized_linear_prepared(const float *x, int batch, int m, int k, int n, const uint8_t *wt,
-                                        const int32_t *colsum, const float *w_scale, int w_scale_len,
-                                        int w_zp, const float *bias, int relu, float *out) {
+/* VNNI layout of a prepared weight: [ceil(k/4)][n16][4] i8 (n16 = n rounded up to 16, zero padded), built once per weight
+ * like the reference's B_WEIGHT_CACHE.  Returns NULL on hosts without AVX-512 VNNI (the scalar loop is used then). */
+int8_t *lo_pack_weights_vnni(const uint8_t *wt, int k, int n) {
+#ifdef LO_HAVE_VNNI512
+    const int k4 = (k + 3) / 4, n16 = (n + 15) / 16 * 16;
+    int8_t *wp = aligned_alloc(64, (size_t)k4 * n16 * 4);
+    if (!wp) return NULL;
+    memset(wp, 0, (size_t)k4 * n16 * 4);
+    const int kq = k / 4;   /* whole quads: a [n][kq] -> [kq][n16] transpose of 4-byte units, 16 x 16 tiles */
+    for (int j0 = 0; j0 < n; j0 += 16)
+        for (int q0 = 0; q0 < kq; q0 += 16)
+            for (int j = j0; j < j0 + 16 && j < n; ++j)
+                for (int q = q0; q < q0 + 16 && q < kq; ++q)
+                    memcpy(wp + ((size_t)q * n16 + j) * 4, wt + (size_t)j * k + 4 * q, 4);
+    for (int j = 0; j < n; ++j)
+        for (int kk = kq * 4; kk < k; ++kk) wp[((size_t)(kk >> 2) * n16 + j) * 4 + (kk & 3)] = (int8_t)wt[(size_t)j * k + kk];
+    return wp;
+#else
+    (void)wt; (void)k; (void)n;
+    return NULL;
+#endif
+}
+void lo_free_packed(int8_t *wp) { free(wp); }
+
+void lo_fused_quantized_linear_packed(const float *x, int batch, int m, int k, int n, const uint8_t *wt, const int8_t *wp_in,
+                                      const int32_t *colsum, const float *w_scale, int w_scale_len,
+                                      int w_zp, const float *bias, int relu, float *out) {
     uint8_t *aq = malloc((size_t)m * k);
     int32_t *rsum = malloc(sizeof(int32_t) * (size_t)m);
     float *cs = malloc(sizeof(float) * (size_t)(w_scale_len > 1 ? w_scale_len : 1));
     int k_simd = (k / 8) * 8;
+#ifdef LO_HAVE_VNNI512
+    int8_t *wp_own = wp_in ? NULL : lo_pack_weights_vnni(wt, k, n);
+    const int8_t *wp = wp_in ? wp_in : wp_own;
+#else
+    (void)wp_in;
+#endif
     for (int bi = 0; bi < batch; ++bi) {
         const float *xb = x + (size_t)bi * m * k;
         float scale, zpf;
@@ -334,8 +372,94 @@ void lo_fused_quantized_linear_prepared(const float *x, int batch, int m, int k,
             }
             rsum[i] = rs;
         }
-        /* column-outer loop: one weight row stays in L1 while all activation rows stream from L2 */
-        for (int j = 0; j < n; ++j) {
+        /* The integer core is exact, so any evaluation order gives the same bits.  On AVX-512 VNNI hosts it runs as a
+         * register-blocked u8 x i8 GEMM (vpdpbusd = the reference's x86 instruction class, avx/quantization.rs:926-936,
+         * 1203-1603): weights repacked to the VNNI layout [k/4][n][4], 4 rows x 64 columns of i32 accumulators per block,
+         * activation quads broadcast -- so that the timed CPU baseline is a SIMD micro-kernel like lele's, not a scalar loop.
+         * The f32 epilogue is the scalar one lane by lane (separate mul and add, :1417-1423). */
+        int j0 = 0;
+#ifdef LO_HAVE_VNNI512
+        if (wp) {
+            const int k4 = (k + 3) / 4, n16 = (n + 15) / 16 * 16, kp = k4 * 4;
+            uint8_t *ap = aligned_alloc(64, ((size_t)m * kp + 63) / 64 * 64);
+            int32_t *colz = malloc(sizeof(int32_t) * (size_t)n16);
+            float *csv = malloc(sizeof(float) * (size_t)n16), *bv = malloc(sizeof(float) * (size_t)n16);
+            for (int i = 0; i < m; ++i) {
+                memcpy(ap + (size_t)i * kp, aq + (size_t)i * k, (size_t)k);
+                memset(ap + (size_t)i * kp + k, 0, (size_t)(kp - k));
+            }
+            for (int j = 0; j < n16; ++j) {
+                colz[j] = j < n ? zpa * colsum[j] : 0;
+                csv[j] = j < n ? cs[w_scale_len <= 1 ? 0 : j] : 0.0f;
+                bv[j] = (j < n && bias) ? bias[j] : 0.0f;
+            }
+            const int32_t kzz = k * zpa * w_zp;
+            /* k is walked in blocks of KQ quads so that the 64-column weight panel of a block (KQ x 256 B = 32 KB) stays in L1
+             * while all row blocks stream past it; partial i32 sums of a column panel wait in `part` between k-blocks */
+            enum { KQ = 128 };
+            int32_t *part = (k4 > KQ) ? aligned_alloc(64, (((size_t)m + 3) / 4 * 4) * 64 * sizeof(int32_t)) : NULL;
+            for (int jb = 0; jb < n16; jb += 64) {
+                const int nv = (n16 - jb) >= 64 ? 4 : (n16 - jb) / 16;
+                for (int q0 = 0; q0 < k4; q0 += KQ) {
+                    const int q1 = (q0 + KQ < k4) ? q0 + KQ : k4;
+                    const int first = q0 == 0, last = q1 == k4;
+                    for (int i0 = 0; i0 < m; i0 += 4) {
+                        const int nr = (m - i0) >= 4 ? 4 : (m - i0);
+                        __m512i acc[4][4];
+                        if (first) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) acc[r][c] = _mm512_setzero_si512(); }
+                        else { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) acc[r][c] = _mm512_load_si512((const void *)(part + ((size_t)(i0 + r) * 4 + c) * 16)); }
+                        if (nr == 4 && nv == 4) {       /* full block: constant trip counts keep the 16 accumulators in registers */
+                            const uint8_t *a0 = ap + (size_t)i0 * kp;
+                            for (int q = q0; q < q1; ++q) {
+                                const int8_t *wq = wp + ((size_t)q * n16 + jb) * 4;
+                                const __m512i w0 = _mm512_load_si512((const void *)wq), w1 = _mm512_load_si512((const void *)(wq + 64));
+                                const __m512i w2 = _mm512_load_si512((const void *)(wq + 128)), w3 = _mm512_load_si512((const void *)(wq + 192));
+#define LO_ROW(r)                                                                                              \
+                                {                                                                              \
+                                    int32_t a4; memcpy(&a4, a0 + (size_t)(r) * kp + 4 * q, 4);                 \
+                                    const __m512i av = _mm512_set1_epi32(a4);                                  \
+                                    acc[r][0] = _mm512_dpbusd_epi32(acc[r][0], av, w0); acc[r][1] = _mm512_dpbusd_epi32(acc[r][1], av, w1); \
+                                    acc[r][2] = _mm512_dpbusd_epi32(acc[r][2], av, w2); acc[r][3] = _mm512_dpbusd_epi32(acc[r][3], av, w3); \
+                                }
+                                LO_ROW(0) LO_ROW(1) LO_ROW(2) LO_ROW(3)
+#undef LO_ROW
+                            }
+                        } else {
+                            for (int q = q0; q < q1; ++q) {
+                                __m512i wv[4], av[4];
+                                const int8_t *wq = wp + ((size_t)q * n16 + jb) * 4;
+                                for (int c = 0; c < nv; ++c) wv[c] = _mm512_load_si512((const void *)(wq + c * 64));
+                                for (int r = 0; r < nr; ++r) { int32_t a4; memcpy(&a4, ap + (size_t)(i0 + r) * kp + 4 * q, 4); av[r] = _mm512_set1_epi32(a4); }
+                                for (int r = 0; r < nr; ++r) for (int c = 0; c < nv; ++c) acc[r][c] = _mm512_dpbusd_epi32(acc[r][c], av[r], wv[c]);
+                            }
+                        }
+                        if (!last) {
+                            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) _mm512_store_si512((void *)(part + ((size_t)(i0 + r) * 4 + c) * 16), acc[r][c]);
+                            continue;
+                        }
+                        for (int r = 0; r < nr; ++r) {
+                            const int i = i0 + r;
+                            const __m512i rowc = _mm512_set1_epi32((128 - w_zp) * rsum[i] + kzz);
+                            for (int c = 0; c < nv; ++c) {
+                                const int j = jb + c * 16;
+                                const __mmask16 mk = (j + 16 <= n) ? (__mmask16)0xFFFF : (__mmask16)((1u << (n - j)) - 1u);
+                                /* dot + (128 - w_zp) * rowsum - zpa * colsum + k * zpa * w_zp  (two's-complement adds: order-free) */
+                                __m512i a32 = _mm512_sub_epi32(_mm512_add_epi32(acc[r][c], rowc), _mm512_loadu_si512((const void *)(colz + j)));
+                                __m512 v = _mm512_mul_ps(_mm512_cvtepi32_ps(a32), _mm512_loadu_ps(csv + j));
+                                if (bias) v = _mm512_add_ps(v, _mm512_loadu_ps(bv + j));
+                                if (relu) v = _mm512_mask_blend_ps(_mm512_cmp_ps_mask(v, _mm512_setzero_ps(), _CMP_LT_OQ), v, _mm512_setzero_ps());
+                                _mm512_mask_storeu_ps(out + ((size_t)bi * m + i) * n + j, mk, v);
+                            }
+                        }
+                    }
+                }
+            }
+            free(part);
+            free(ap); free(colz); free(csv); free(bv);
+            j0 = n;
+        }
+#endif
+        for (int j = j0; j < n; ++j) {
             const int8_t *wr = (const int8_t *)(wt + (size_t)j * k);
             const float csj = cs[w_scale_len <= 1 ? 0 : j];
             for (int i = 0; i < m; ++i) {
@@ -351,7 +475,16 @@ void lo_fused_quantized_linear_prepared(const float *x, int batch, int m, int k,
             }
         }
     }
+#ifdef LO_HAVE_VNNI512
+    free(wp_own);
+#endif
     free(aq); free(rsum); free(cs);
+}
+
+void lo_fused_quantized_linear_prepared(const float *x, int batch, int m, int k, int n, const uint8_t *wt,
+                                        const int32_t *colsum, const float *w_scale, int w_scale_len,
+                                        int w_zp, const float *bias, int relu, float *out) {
+    lo_fused_quantized_linear_packed(x, batch, m, k, n, wt, NULL, colsum, w_scale, w_scale_len, w_zp, bias, relu, out);
 }
 
 void lo_fused_quantized_linear(const float *x, int batch, int m, int k, int n, const uint8_t *w,
@@ -371,6 +504,51 @@ void lo_fused_quantized_linear(const float *x, int batch, int m, int k, int n, c
 /* ------------------------------------------------------------------------- */
 static void lo_sgemm_acc(const float *a, long rsa, long csa, const float *b, long rsb, long csb,
                          int m, int k, int n, float alpha, float *c /* [m,n] += */) {
+#ifdef LO_HAVE_AVX512F
+    if (csb == 1) {
+        /* register-blocked form of the loop below (4 rows x 64 columns of accumulators, k outermost inside a block): every
+         * output is still  c = fmaf(alpha * a[i,kk], b[kk,j], c)  for kk ascending, i.e. the same bits, at SIMD GEMM speed
+         * (the reference's f32 GEMM is faer's AVX micro-kernel) */
+        for (int j0 = 0; j0 < n; j0 += 64) {
+            const int nv = (n - j0) >= 64 ? 4 : (n - j0 + 15) / 16;
+            __mmask16 mk[4];
+            for (int cc = 0; cc < 4; ++cc) { const int rem = n - (j0 + 16 * cc); mk[cc] = rem >= 16 ? (__mmask16)0xFFFF : (rem > 0 ? (__mmask16)((1u << rem) - 1u) : 0); }
+            for (int i0 = 0; i0 < m; i0 += 4) {
+                const int nr = (m - i0) >= 4 ? 4 : (m - i0);
+                __m512 acc[4][4];
+                for (int r = 0; r < 4; ++r) for (int cc = 0; cc < 4; ++cc)
+                    acc[r][cc] = (r < nr && cc < nv) ? _mm512_maskz_loadu_ps(mk[cc], c + (size_t)(i0 + r) * n + j0 + 16 * cc) : _mm512_setzero_ps();
+                if (nr == 4 && nv == 4 && mk[3] == (__mmask16)0xFFFF) {
+                    for (int kk = 0; kk < k; ++kk) {
+                        const float *br = b + kk * rsb + j0;
+                        const __m512 b0 = _mm512_loadu_ps(br), b1 = _mm512_loadu_ps(br + 16), b2 = _mm512_loadu_ps(br + 32), b3 = _mm512_loadu_ps(br + 48);
+#define LO_ROW(r)                                                                                            \
+                        {                                                                                    \
+                            const __m512 av = _mm512_set1_ps(alpha * a[(i0 + (r)) * rsa + kk * csa]);        \
+                            acc[r][0] = _mm512_fmadd_ps(av, b0, acc[r][0]); acc[r][1] = _mm512_fmadd_ps(av, b1, acc[r][1]); \
+                            acc[r][2] = _mm512_fmadd_ps(av, b2, acc[r][2]); acc[r][3] = _mm512_fmadd_ps(av, b3, acc[r][3]); \
+                        }
+                        LO_ROW(0) LO_ROW(1) LO_ROW(2) LO_ROW(3)
+#undef LO_ROW
+                    }
+                } else {
+                    for (int kk = 0; kk < k; ++kk) {
+                        const float *br = b + kk * rsb + j0;
+                        __m512 bv[4];
+                        for (int cc = 0; cc < nv; ++cc) bv[cc] = _mm512_maskz_loadu_ps(mk[cc], br + 16 * cc);
+                        for (int r = 0; r < nr; ++r) {
+                            const __m512 av = _mm512_set1_ps(alpha * a[(i0 + r) * rsa + kk * csa]);
+                            for (int cc = 0; cc < nv; ++cc) acc[r][cc] = _mm512_fmadd_ps(av, bv[cc], acc[r][cc]);
+                        }
+                    }
+                }
+                for (int r = 0; r < nr; ++r) for (int cc = 0; cc < nv; ++cc)
+                    _mm512_mask_storeu_ps(c + (size_t)(i0 + r) * n + j0 + 16 * cc, mk[cc], acc[r][cc]);
+            }
+        }
+        return;
+    }
+#endif
     for (int i = 0; i < m; ++i)
         for (int kk = 0; kk < k; ++kk) {
             float av = alpha * a[i * rsa + kk * csa];

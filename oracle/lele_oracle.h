@@ -59,6 +59,12 @@ void lo_fused_quantized_linear(const float *x, int batch, int m, int k, int n, c
 
 /* prepared form (prepare_weights, quantization.rs:221): wt [n,k], colsum [n] */
 void lo_prepare_weights(const uint8_t *w, int k, int n, uint8_t *wt, int32_t *colsum);
+/* optional VNNI repack of a prepared weight (NULL on hosts without AVX-512 VNNI) + the entry that takes it */
+int8_t *lo_pack_weights_vnni(const uint8_t *wt, int k, int n);
+void lo_free_packed(int8_t *wp);
+void lo_fused_quantized_linear_packed(const float *x, int batch, int m, int k, int n, const uint8_t *wt, const int8_t *wp,
+                                      const int32_t *colsum, const float *w_scale, int w_scale_len,
+                                      int w_zp, const float *bias, int relu, float *out);
 void lo_fused_quantized_linear_prepared(const float *x, int batch, int m, int k, int n, const uint8_t *wt,
                                         const int32_t *colsum, const float *w_scale, int w_scale_len,
                                         int w_zp, const float *bias, int relu, float *out);

@@ -32,6 +32,7 @@ struct lo_sv_model {
     /* prepared weights (one-time transpose + column sums, the reference's B_WEIGHT_CACHE) */
     uint8_t **wt;      /* [n_layers*4 + 1] */
     int32_t **colsum;
+    int8_t **wp;       /* VNNI repack of wt (NULL entries on hosts without AVX-512 VNNI) */
 };
 
 static const void *sv_t(const lo_sv_model *m, int idx) { return m->blob + m->table[2 * idx]; }
@@ -52,6 +53,7 @@ lo_sv_model *lo_sv_create(const uint8_t *blob, size_t nbytes) {
     int nl = m->n_layers * 4 + 1;
     m->wt = calloc(nl, sizeof(uint8_t *));
     m->colsum = calloc(nl, sizeof(int32_t *));
+    m->wp = calloc(nl, sizeof(int8_t *));
     for (int l = 0; l < m->n_layers; ++l) {
         int cur = l == 0 ? m->d_in : m->d;
         int ks[4] = { cur, m->d, m->d, m->ffn }, ns[4] = { 3 * m->d, m->d, m->ffn, m->d };
@@ -60,18 +62,20 @@ lo_sv_model *lo_sv_create(const uint8_t *blob, size_t nbytes) {
             m->wt[l * 4 + q] = malloc((size_t)ks[q] * ns[q]);
             m->colsum[l * 4 + q] = malloc(sizeof(int32_t) * ns[q]);
             lo_prepare_weights(sv_l(m, l, which[q]), ks[q], ns[q], m->wt[l * 4 + q], m->colsum[l * 4 + q]);
+            m->wp[l * 4 + q] = lo_pack_weights_vnni(m->wt[l * 4 + q], ks[q], ns[q]);
         }
     }
     m->wt[nl - 1] = malloc((size_t)m->d * m->vocab);
     m->colsum[nl - 1] = malloc(sizeof(int32_t) * m->vocab);
     lo_prepare_weights(sv_t(m, SV_G_CTC_W), m->d, m->vocab, m->wt[nl - 1], m->colsum[nl - 1]);
+    m->wp[nl - 1] = lo_pack_weights_vnni(m->wt[nl - 1], m->d, m->vocab);
     return m;
 }
 void lo_sv_destroy(lo_sv_model *m) {
     if (!m) return;
     int nl = m->n_layers * 4 + 1;
-    for (int i = 0; i < nl; ++i) { free(m->wt[i]); free(m->colsum[i]); }
-    free(m->wt); free(m->colsum); free(m);
+    for (int i = 0; i < nl; ++i) { free(m->wt[i]); free(m->colsum[i]); lo_free_packed(m->wp[i]); }
+    free(m->wt); free(m->colsum); free(m->wp); free(m);
 }
 int lo_sv_vocab(const lo_sv_model *m) { return m->vocab; }
 
@@ -106,7 +110,7 @@ int lo_sv_forward(const lo_sv_model *m, const float *feats, int t, int lang, int
     int cur = din;
     for (int l = 0; l < n_layers; ++l) {
         lo_layer_norm(x, sv_l(m, l, SV_L_LN1_G), sv_l(m, l, SV_L_LN1_B), T, cur, 1e-5f, h);
-        lo_fused_quantized_linear_prepared(h, 1, T, cur, 3 * d, m->wt[l * 4 + 0], m->colsum[l * 4 + 0], sv_l(m, l, SV_L_QKV_SCALE),
+        lo_fused_quantized_linear_packed(h, 1, T, cur, 3 * d, m->wt[l * 4 + 0], m->wp[l * 4 + 0], m->colsum[l * 4 + 0], sv_l(m, l, SV_L_QKV_SCALE),
                                   3 * d, *(const uint8_t *)sv_l(m, l, SV_L_QKV_ZP),
                                   sv_l(m, l, SV_L_QKV_BIAS), 0, qkv);
         /* split + head transposes: q [H,T,dk] (scaled), k^T [H,dk,T], v [H,T,dk]; v^T [d,T] */
@@ -133,16 +137,16 @@ int lo_sv_forward(const lo_sv_model *m, const float *feats, int t, int lang, int
         for (int hd = 0; hd < H; ++hd)
             for (int i = 0; i < T; ++i)
                 memcpy(om + (size_t)i * d + (size_t)hd * dk, oh + ((size_t)hd * T + i) * dk, sizeof(float) * dk);
-        lo_fused_quantized_linear_prepared(om, 1, T, d, d, m->wt[l * 4 + 1], m->colsum[l * 4 + 1], sv_l(m, l, SV_L_OUT_SCALE), d,
+        lo_fused_quantized_linear_packed(om, 1, T, d, d, m->wt[l * 4 + 1], m->wp[l * 4 + 1], m->colsum[l * 4 + 1], sv_l(m, l, SV_L_OUT_SCALE), d,
                                   *(const uint8_t *)sv_l(m, l, SV_L_OUT_ZP), sv_l(m, l, SV_L_OUT_BIAS), 0, att);
         sv_add(att, fsmn, (size_t)T * d, att);
         if (cur == d) sv_add(x, att, (size_t)T * d, x);
         else memcpy(x, att, sizeof(float) * (size_t)T * d);
         cur = d;
         lo_layer_norm(x, sv_l(m, l, SV_L_LN2_G), sv_l(m, l, SV_L_LN2_B), T, d, 1e-5f, h);
-        lo_fused_quantized_linear_prepared(h, 1, T, d, ffn, m->wt[l * 4 + 2], m->colsum[l * 4 + 2], sv_l(m, l, SV_L_FFN1_SCALE), ffn,
+        lo_fused_quantized_linear_packed(h, 1, T, d, ffn, m->wt[l * 4 + 2], m->wp[l * 4 + 2], m->colsum[l * 4 + 2], sv_l(m, l, SV_L_FFN1_SCALE), ffn,
                                   *(const uint8_t *)sv_l(m, l, SV_L_FFN1_ZP), sv_l(m, l, SV_L_FFN1_BIAS), 1, f1);
-        lo_fused_quantized_linear_prepared(f1, 1, T, ffn, d, m->wt[l * 4 + 3], m->colsum[l * 4 + 3], sv_l(m, l, SV_L_FFN2_SCALE), d,
+        lo_fused_quantized_linear_packed(f1, 1, T, ffn, d, m->wt[l * 4 + 3], m->wp[l * 4 + 3], m->colsum[l * 4 + 3], sv_l(m, l, SV_L_FFN2_SCALE), d,
                                   *(const uint8_t *)sv_l(m, l, SV_L_FFN2_ZP), sv_l(m, l, SV_L_FFN2_BIAS), 0, f2);
         sv_add(x, f2, (size_t)T * d, x);
         if (l == m->n_stage1 - 1) {
@@ -152,7 +156,7 @@ int lo_sv_forward(const lo_sv_model *m, const float *feats, int t, int lang, int
     }
     if (n_layers == m->n_layers) {
         lo_layer_norm(x, sv_t(m, SV_G_TP_G), sv_t(m, SV_G_TP_B), T, cur, 1e-5f, h);
-        lo_fused_quantized_linear_prepared(h, 1, T, cur, m->vocab, m->wt[m->n_layers * 4], m->colsum[m->n_layers * 4], sv_t(m, SV_G_CTC_SCALE), m->vocab,
+        lo_fused_quantized_linear_packed(h, 1, T, cur, m->vocab, m->wt[m->n_layers * 4], m->wp[m->n_layers * 4], m->colsum[m->n_layers * 4], sv_t(m, SV_G_CTC_SCALE), m->vocab,
                                   *(const uint8_t *)sv_t(m, SV_G_CTC_ZP), sv_t(m, SV_G_CTC_BIAS), 0, logits);
     } else {
         /* truncated run (tests): expose the hidden state instead of logits */
