@@ -62,7 +62,7 @@ _W = re.compile(r"^&?self\.(weight_[a-z0-9_]+)\((\d+),\s*(\d+),\s*&\[([^\]]*)\]\
 
 def _parse_arg(a: str):
     a = a.strip()
-    if a == "None":
+    if a in ("None", "&lele::tensor::TensorView::empty()"):
         return None
     if a.startswith("Some(") and a.endswith(")"):
         return _parse_arg(a[5:-1])
@@ -147,12 +147,15 @@ def parse_model_rs(text: str) -> dict:
         if m:
             stmts.append({"outs": [m.group(1)], "op": "identity", "args": [{"var": m.group(2)}]})
             continue
-        m = re.match(r"^let \((\w+), (\w+)\) = lele::kernels::(\w+)\((.*)\);$", line) or re.match(r"^let (\w+)() = lele::kernels::(\w+)\((.*)\);$", line)
+        m = re.match(r"^let \((\w+), ([\w, ]+)\) = \(lele::kernels::(layer_norm)\((.*)\), lele::tensor::TensorView::empty\(\)[^;]*\);$", line)
+        if m:                                                    # LayerNormalization with unused Mean / InvStdDev outputs (ops/nn.rs:261)
+            line = f"let {m.group(1)} = lele::kernels::layer_norm({m.group(4)});"
+        m = re.match(r"^let \(([\w, ]+)\) = lele::kernels::(\w+)\((.*)\);$", line) or re.match(r"^let (\w+) = lele::kernels::(\w+)\((.*)\);$", line)
         if m:
-            outs = [m.group(1)] + ([m.group(2)] if m.group(2) else [])
-            args = [_parse_arg(a) for a in _split_top(m.group(4))]
+            outs = [o.strip() for o in m.group(1).split(",")]   # "_" = an output the graph never reads
+            args = [_parse_arg(a) for a in _split_top(m.group(3))]
             args = [a for a in args if not (isinstance(a, dict) and "out" in a)]      # workspace buffers: the arena is the back-end's business
-            stmts.append({"outs": outs, "op": m.group(3), "args": args})
+            stmts.append({"outs": outs, "op": m.group(2), "args": args})
             continue
         raise ValueError(f"model.rs: unsupported statement: {line[:160]}")
     if inputs is None or outputs is None:
@@ -187,6 +190,14 @@ class CudaOps:
     def binary(self, op, a, b): return getattr(self.K, op)(a, b, ctx=self.ctx)
     def unary(self, op, x): return getattr(self.K, op)(x, ctx=self.ctx)
     def layer_norm(self, x, g, b, axis, eps): return self.K.layer_norm(x, g, b, axis, eps, ctx=self.ctx)
+    def gemm(self, a, b, c, alpha, beta, ta, tb): return self.K.gemm(a, b, c, alpha, beta, ta, tb, ctx=self.ctx)
+    def matmul_fused_add(self, a, b, bias): return self.K.matmul_fused_add(a, b, bias, ctx=self.ctx)
+    def conv1d(self, x, w, bias, dilations, group, pads, strides, relu): return self.K.conv1d_fused(x, w, bias, dilations, group, pads, strides, relu, ctx=self.ctx)
+    def pad(self, x, pads, value, mode): return self.K.pad(x, pads, value, mode, ctx=self.ctx)
+    def expand(self, x, shape): return self.K.expand(x, shape, ctx=self.ctx)
+    def where(self, c, x, y): return self.K.where_op(c, x, y, ctx=self.ctx)
+    def lstm(self, x, w, r, bias, h0, c0): return self.K.lstm(x, w, r, bias, None, h0, c0, ctx=self.ctx)
+    def gru(self, x, w, r, bias, h0): return self.K.gru(x, w, r, bias, h0, ctx=self.ctx)
 
 
 class _NamespaceOps:
@@ -198,8 +209,10 @@ class _NamespaceOps:
     def __getattr__(self, name):
         return getattr(self.ns, name)
 
-    def binary(self, op, a, b): return getattr(self.ns, op)(a, b)
-    def unary(self, op, x): return getattr(self.ns, op)(x)
+    _ALIAS = {"tanh_kernel": "tanh", "max": "maximum"}
+
+    def binary(self, op, a, b): return getattr(self.ns, self._ALIAS.get(op, op))(a, b)
+    def unary(self, op, x): return getattr(self.ns, self._ALIAS.get(op, op))(x)
     def resize_nearest(self, x, scales, sizes, mode): return self.ns.resize_nearest(x, scales=scales, sizes=sizes, mode=mode)
 
 
@@ -238,10 +251,35 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
             if a[4] != 1:
                 raise ValueError("ConvTranspose: group > 1 not supported yet (conv2d.rs:3042)")
             r = ops.conv_transpose(a[0], a[1], a[2], a[3], a[5], a[6])
-        elif op in ("add", "sub", "mul", "div", "mod_f32"):
+        elif op in ("add", "sub", "mul", "div", "mod_f32", "max", "prelu"):
             r = ops.binary(op, a[0], a[1])
-        elif op in ("sigmoid", "silu", "relu"):
+        elif op in ("sigmoid", "silu", "relu", "tanh_kernel", "erf", "exp", "sqrt", "neg", "reciprocal", "softplus"):
             r = ops.unary(op, a[0])
+        elif op == "layer_norm":                      # (x, scale, bias, axis, epsilon)  ops/nn.rs:282
+            if a[1] is None or a[2] is None:          # the x86 kernel reads scale and bias unconditionally (norm.rs:244)
+                raise ValueError("layer_norm: scale and bias are required (norm.rs:244)")
+            r = ops.layer_norm(a[0], a[1], a[2], a[3], a[4])
+        elif op == "gemm":                            # (a, b, c, alpha, beta, trans_a, trans_b)  ops/nn.rs:109
+            r = ops.gemm(a[0], a[1], a[2], a[3], a[4], a[5], a[6])
+        elif op == "lstm":                            # (x, w, r, bias, sequence_lens, initial_h, initial_c) -> (Y, H, C)  ops/nn.rs:146
+            r = ops.lstm(a[0], a[1], a[2], a[3], a[5], a[6])
+        elif op == "gru":                             # (x, w, r, bias, initial_h, linear_before_reset) -> (Y, H)  ops/nn.rs:195
+            r = ops.gru(a[0], a[1], a[2], a[3], a[4])
+        elif op == "matmul_fused_add":
+            r = ops.matmul_fused_add(a[0], a[1], a[2])
+        elif op in ("conv1d", "conv1d_fused"):        # same argument form as conv2d (ops/nn.rs:57); _fused appends the ReLU flag
+            r = ops.conv1d(a[0], a[1], a[2], a[3], a[4], a[5], a[6], bool(a[7]) if (op == "conv1d_fused" and len(a) > 7) else False)
+        elif op in ("reduce_sum", "reduce_mean", "reduce_l2"):
+            r = ops.reduce(a[0], a[1], a[2], op[len("reduce_"):])
+        elif op == "pad":                             # (x, pads, constant_value, mode)  ops/tensor.rs:403
+            r = ops.pad(a[0], a[1], float(a[2]) if a[2] is not None else 0.0, a[3])
+        elif op == "expand":
+            r = ops.expand(a[0], a[1])
+        elif op == "squeeze":
+            x = np.ascontiguousarray(a[0]); axes = a[1]
+            r = np.squeeze(x, axis=tuple(ax % x.ndim for ax in axes)) if axes else np.squeeze(x)
+        elif op == "where_op":
+            r = ops.where(a[0], a[1], a[2])
         elif op == "concat":
             r = ops.concat(a[0], a[1])
         elif op == "split_take":
@@ -289,7 +327,8 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
             env[st["outs"][0]] = r
         else:
             for n, v in zip(st["outs"], r):
-                env[n] = v
+                if n != "_":
+                    env[n] = v
         if trace is not None:
             trace.append((st["outs"][0], op, env[st["outs"][0]]))
     return [env[n] for n in program["outputs"]]

@@ -1,0 +1,79 @@
+"""Generated-style model.rs snippets shared by the CPU and GPU replay tests: statement forms of src/compiler/ops/{nn,math,tensor}.rs
+beyond the Yolo fixture (layer_norm, gemm, conv1d, math, reductions, pad, expand, squeeze, where_op, LSTM / GRU tuples)."""
+import numpy as np
+
+from oracle import reference_api as R  # noqa: F401  (tests only)
+
+H, I = 8, 6
+
+MATH_TEXT = """
+pub struct T2Workspace { pub buf_0: Vec<f32>, }
+pub struct T2<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut T2Workspace, x: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>) {
+        let a = lele::kernels::layer_norm(&x, &self.weight_f32(0, 32, &[8]), &self.weight_f32(32, 32, &[8]), -1, 0.00001, &mut ws.buf_0);
+        let b = lele::kernels::gemm(&a, &self.weight_f32(64, 192, &[6, 8]), Some(&self.weight_f32(256, 24, &[6])), 1.0, 1.0, false, true, &mut ws.buf_0);
+        let c = lele::kernels::tanh_kernel(&b, &mut ws.buf_0);
+        let d = lele::kernels::max(&c, &self.weight_f32(280, 4, &[1]), &mut ws.buf_0);
+        let e = lele::kernels::reduce_mean(&d, &[1], true, &mut ws.buf_0);
+        let f = lele::kernels::exp(&e, &mut ws.buf_0);
+        let g = lele::kernels::expand(&f, &[5, 6], &mut ws.buf_0);
+        let h = lele::kernels::where_op(&d, &g, &b, &mut ws.buf_0);
+        let p = lele::kernels::pad(&h, &[0, 1, 0, 2], 0.5, "constant", &mut ws.buf_0);
+        let q = lele::kernels::unsqueeze(&p, &[0]);
+        let r = lele::kernels::conv1d(&q, &self.weight_f32(284, 60, &[3, 5, 1]), None, &[1], 1, &[0, 0], &[1], &mut ws.buf_0);
+        let s = lele::kernels::squeeze(&r, &[0]);
+        (s.to_owned(), e.to_owned())
+    }
+"""
+
+
+def math_forms(m):
+    prog = m.parse_model_rs(MATH_TEXT)
+    blob = m.synth_blob(prog, 3, {280: [0.0]})
+    x = np.random.default_rng(1).standard_normal((5, 8)).astype(np.float32)
+    return prog, blob, x
+
+
+def math_forms_direct(m, blob, x):
+    W = lambda off, ln, shp: m.weight_view(blob, "weight_f32", off, ln, shp)
+    a = R.layer_norm(x, W(0, 32, [8]), W(32, 32, [8]), -1, 1e-5)
+    b = R.gemm(a, W(64, 192, [6, 8]), W(256, 24, [6]).reshape(-1), 1.0, 1.0, False, True)
+    d = R.maximum(R.tanh(b), W(280, 4, [1]))
+    e = R.reduce(d, [1], True, "mean")
+    h = R.where(d, R.expand(R.exp(e), [5, 6]), b)
+    p = R.pad(h, [0, 1, 0, 2], 0.5, "constant")
+    r = R.conv1d(p[None], W(284, 60, [3, 5, 1]), None, (1,), 1, (0, 0), (1,), False)
+    return r[0], e
+
+
+def recurrent_text():
+    return f"""
+pub struct T3Workspace {{ pub buf_0: Vec<f32>, }}
+pub struct T3<'a> {{ data: &'a [u8] }}
+    fn run_chunk_0<'w>(&self, ws: &'w mut T3Workspace, x: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>, TensorView<'static, f32>) {{
+        let mut buf_y_h = Vec::<f32>::new();
+        let mut buf_y_c = Vec::<f32>::new();
+        let (y, yh, yc) = lele::kernels::lstm(&x, &self.weight_f32(0, {4*H*I*4}, &[1, {4*H}, {I}]), &self.weight_f32({4*H*I*4}, {4*H*H*4}, &[1, {4*H}, {H}]), Some(&self.weight_f32({4*H*(I+H)*4}, {8*H*4}, &[1, {8*H}])), None, None, None, &mut ws.buf_0, &mut buf_y_h, &mut buf_y_c);
+        let y2 = lele::kernels::reshape(&y, &[0, 1, {H}]);
+        let mut buf_g_h = Vec::<f32>::new();
+        let mut buf_g = Vec::<f32>::new();
+        let (g, _) = lele::kernels::gru(&y2, &self.weight_f32(2000, {3*H*H*4}, &[1, {3*H}, {H}]), &self.weight_f32(3000, {3*H*H*4}, &[1, {3*H}, {H}]), None, Some(&yh), false, &mut buf_g, &mut buf_g_h);
+        let (n, _, _) = (lele::kernels::layer_norm(&g, &self.weight_f32(4000, {H*4}, &[{H}]), &self.weight_f32(4100, {H*4}, &[{H}]), -1, 0.00001, &mut ws.buf_0), lele::tensor::TensorView::empty(), lele::tensor::TensorView::empty());
+        (n.to_owned(), yh.to_owned(), yc.to_owned())
+    }}
+"""
+
+
+def recurrent_forms(m):
+    prog = m.parse_model_rs(recurrent_text())
+    blob = m.synth_blob(prog, 5)
+    x = np.random.default_rng(2).standard_normal((7, 1, I)).astype(np.float32)
+    return prog, blob, x
+
+
+def recurrent_forms_direct(m, blob, x):
+    W = lambda off, ln, shp: m.weight_view(blob, "weight_f32", off, ln, shp)
+    y, yh, yc = R.lstm(x, W(0, 4*H*I*4, [1, 4*H, I]), W(4*H*I*4, 4*H*H*4, [1, 4*H, H]), W(4*H*(I+H)*4, 8*H*4, [1, 8*H]))
+    g, _ = R.gru(y.reshape(7, 1, H), W(2000, 3*H*H*4, [1, 3*H, H]), W(3000, 3*H*H*4, [1, 3*H, H]), None, yh)
+    n = R.layer_norm(g, W(4000, H*4, [H]), W(4100, H*4, [H]), -1, 1e-5)
+    return n, yh, yc

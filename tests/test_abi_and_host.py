@@ -204,6 +204,85 @@ pub struct Tiny<'a> { data: &'a [u8] }
         m.parse_model_rs(text.replace("let b = lele::kernels::add(&a0, &a1, &mut ws.buf_1);", "let b = unsafe { transmute(a0) };"))
 
 
+def _model_rs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("model_rs", os.path.join(ROOT, "lele_b200", "model_rs.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_model_rs_more_statement_forms_on_oracle():
+    """More of the forms src/compiler/ops/*.rs emits (layer_norm, gemm, conv1d, unary / binary math, reductions, pad, expand,
+    squeeze, where_op): parsed and replayed on the oracle, checked against direct oracle calls."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    prog, blob, x = MF.math_forms(m)
+    s_out, e_out = m.run_program(prog, blob, [x], MF.R)
+    s_ref, e_ref = MF.math_forms_direct(m, blob, x)
+    np.testing.assert_array_equal(e_out, e_ref)
+    np.testing.assert_array_equal(s_out, s_ref)
+    assert s_out.shape == (3, 9)
+
+
+def test_model_rs_recurrent_and_tuple_forms_on_oracle():
+    """Multi-output statements of ops/nn.rs: LSTM (Y, H, C), GRU with and without the `_` placeholder, LayerNormalization
+    with unused extra outputs, and the empty-TensorView scale that the x86 kernel cannot take."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    prog, blob, x = MF.recurrent_forms(m)
+    assert [s["outs"] for s in prog["statements"]] == [["y", "yh", "yc"], ["y2"], ["g", "_"], ["n"]]
+    got = m.run_program(prog, blob, [x], MF.R)
+    for a, b in zip(got, MF.recurrent_forms_direct(m, blob, x)):
+        np.testing.assert_array_equal(a, b)
+    bad = MF.recurrent_text().replace(f"&self.weight_f32(4000, {MF.H*4}, &[{MF.H}])", "&lele::tensor::TensorView::empty()")
+    with pytest.raises(ValueError, match="scale and bias are required"):
+        m.run_program(m.parse_model_rs(bad), blob, [x], MF.R)
+
+
+def test_cuda_ops_glue_binds_to_kernel_signatures(so_path):
+    """CudaOps is the only untested-on-CPU piece of the replay: here every call it makes is bound against the real
+    lele_b200.kernels signature (inspect.signature(...).bind) and then answered by the oracle, so an argument-order or
+    keyword mistake in the glue fails on the CPU box, not on the GPU one."""
+    import inspect
+    from lele_b200 import kernels as K, model_rs as MR
+    from tests import model_forms as MF
+    R = MF.R
+    seen = []
+
+    class BoundK:
+        def __getattr__(self, name):
+            real = getattr(K, name)
+            sig = inspect.signature(real)
+
+            def f(*args, **kw):
+                b = sig.bind(*args, **kw); b.apply_defaults()
+                assert "ctx" in b.arguments
+                seen.append(name)
+                v = {k: b.arguments[k] for k in b.arguments if k != "ctx"}
+                vals = list(v.values())
+                if name == "layer_norm": return R.layer_norm(v["x"], v["scale"], v["bias"], v["axis"], v["epsilon"])
+                if name == "gemm": return R.gemm(v["a"], v["b"], None if v["c"] is None else np.asarray(v["c"]).reshape(-1), v["alpha"], v["beta"], v["trans_a"], v["trans_b"])
+                if name == "conv1d_fused": return R.conv1d(vals[0], vals[1], vals[2], tuple(vals[3]), vals[4], tuple(vals[5]), tuple(vals[6]), vals[7])
+                if name == "lstm":
+                    assert v["sequence_lens"] is None
+                    return R.lstm(v["input"], v["w"], v["r"], v["bias"], v["initial_h"], v["initial_c"])
+                if name == "gru":
+                    assert v["linear_before_reset"] is False
+                    return R.gru(v["input"], v["w"], v["r"], v["bias"], v["initial_h"])
+                if name.startswith("reduce_"): return R.reduce(vals[0], list(vals[1]), vals[2], name[len("reduce_"):])
+                return getattr(R, {"tanh_kernel": "tanh", "max": "maximum", "where_op": "where"}.get(name, name))(*vals)
+            return f
+
+    ops = MR.CudaOps.__new__(MR.CudaOps); ops.K, ops.ctx = BoundK(), None
+    prog, blob, x = MF.math_forms(MR)
+    for a, b in zip(MR.run_program(prog, blob, [x], ops), MF.math_forms_direct(MR, blob, x)):
+        np.testing.assert_array_equal(a, b)
+    prog, blob, x = MF.recurrent_forms(MR)
+    for a, b in zip(MR.run_program(prog, blob, [x], ops), MF.recurrent_forms_direct(MR, blob, x)):
+        np.testing.assert_array_equal(a, b)
+    assert {"layer_norm", "gemm", "tanh_kernel", "max", "reduce_mean", "exp", "expand", "where_op", "pad", "conv1d_fused", "lstm", "gru"} <= set(seen)
+
+
 def test_generated_model_fixture_is_consistent():
     """tests/golden/yolo26seg_program.json (from the reference's committed lele_gen output, see make_model_program.py):
     337 statements, 21 workspace buffers, a 10 993 208-byte weights.bin."""
