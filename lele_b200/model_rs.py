@@ -109,7 +109,7 @@ def parse_model_rs(text: str) -> dict:
     cls = re.search(r"pub struct (\w+)<'a>", text)
     n_bufs = len(re.findall(r"pub buf_\d+: Vec<f32>", text))
     stmts, inputs, outputs = [], None, None
-    in_chunk, splits, split_src = False, None, None
+    in_chunk, splits, split_src, skip_next = False, None, None, False
     for raw in text.splitlines():
         line = raw.strip()
         m = re.match(r"fn run_chunk_\d+<'w>\(&self, ws: [^,]+, (.*)\) -> ", line)
@@ -124,6 +124,14 @@ def parse_model_rs(text: str) -> dict:
             in_chunk = False
             continue
         if line.startswith("//") or not line:
+            continue
+        if line == '#[cfg(target_arch = "aarch64")]':          # the pre-packed NEON arm of a statement pair (patterns.rs:383, ops/math.rs:60):
+            skip_next = True                                     # this back-end takes the portable arm that follows
+            continue
+        if line.startswith("#[cfg(not(target_arch"):
+            continue
+        if skip_next:
+            skip_next = False
             continue
         m = re.match(r"^\((.*)\)$", line)                      # tail expression: (a.to_owned(), b.to_owned())
         if m:
@@ -141,9 +149,15 @@ def parse_model_rs(text: str) -> dict:
         if m:
             stmts.append({"outs": [m.group(1)], "op": "split_take", "args": [{"var": split_src[0]}, split_src[1], {"list": split_src[2]}, int(m.group(2))]})
             continue
-        if re.match(r"^let mut buf_\w+ = Vec::<f32>::new\(\);$", line):
+        if re.match(r"^let mut buf_\w+ = Vec::<(f32|i64)>::new\(\);$", line):
             continue
-        m = re.match(r"^let (\w+) = (\w+)\.clone\(\);", line)
+        m = re.match(r"^let (\w+) = self\.(\w+)\((.*)\);$", line)   # helper methods of src/compiler/snippets/default_methods.rs
+        if m:
+            args = [_parse_arg(a) for a in _split_top(m.group(3))]
+            args = [a for a in args if not (isinstance(a, dict) and "out" in a)]
+            stmts.append({"outs": [m.group(1)], "op": "self." + m.group(2), "args": args})
+            continue
+        m = re.match(r"^let (\w+) = (\w+)\.(?:clone|to_owned)\(\);", line)
         if m:
             stmts.append({"outs": [m.group(1)], "op": "identity", "args": [{"var": m.group(2)}]})
             continue
@@ -196,6 +210,11 @@ class CudaOps:
     def pad(self, x, pads, value, mode): return self.K.pad(x, pads, value, mode, ctx=self.ctx)
     def expand(self, x, shape): return self.K.expand(x, shape, ctx=self.ctx)
     def where(self, c, x, y): return self.K.where_op(c, x, y, ctx=self.ctx)
+    def fused_quantized_linear(self, x, w, ws, wz, bias, relu): return self.K.fused_quantized_linear(x, w, ws, wz, bias, relu, ctx=self.ctx)
+    def dynamic_quantize_linear(self, x): return self.K.dynamic_quantize_linear(x, ctx=self.ctx)
+    def mat_mul_integer(self, a, b, zp_a, zp_b): return self.K.mat_mul_integer(a, b, zp_a, zp_b, ctx=self.ctx)
+    def clip(self, x, lo, hi): return self.K.clip(x, lo, hi, ctx=self.ctx)
+    def batch_norm(self, x, scale, bias, mean, var, eps): return self.K.batch_norm(x, scale, bias, mean, var, eps, ctx=self.ctx)
     def lstm(self, x, w, r, bias, h0, c0): return self.K.lstm(x, w, r, bias, None, h0, c0, ctx=self.ctx)
     def gru(self, x, w, r, bias, h0): return self.K.gru(x, w, r, bias, h0, ctx=self.ctx)
 
@@ -265,6 +284,26 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
             r = ops.lstm(a[0], a[1], a[2], a[3], a[5], a[6])
         elif op == "gru":                             # (x, w, r, bias, initial_h, linear_before_reset) -> (Y, H)  ops/nn.rs:195
             r = ops.gru(a[0], a[1], a[2], a[3], a[4])
+        elif op in ("self.linear_quantized", "self.linear_quantized_relu"):   # (x, weight_u8 [K,N], weight_scale, weight_zero, bias)  default_methods.rs:36-62
+            zero = int(np.asarray(a[3]).reshape(-1)[0]) if np.size(a[3]) else 0
+            r = ops.fused_quantized_linear(a[0], a[1], a[2], zero, a[4], op.endswith("_relu"))
+        elif op == "self.layer_norm":                 # (x, scale, bias, epsilon tensor, two)  default_methods.rs:24: axis -1, eps = epsilon[0] or 1e-5
+            eps = np.asarray(a[3]).reshape(-1)
+            r = ops.layer_norm(a[0], a[1], a[2], -1, float(eps[0]) if eps.size else 1e-5)
+        elif op == "self.linear":
+            r = ops.matmul_fused_add(a[0], a[1], a[2])
+        elif op == "self.conv1d_relu":                # (x, w, bias, stride, dilation, groups, padding)  default_methods.rs:1
+            r = ops.conv1d(a[0], a[1], a[2], [a[4]], a[5], [a[6], a[6]], [a[3]], True)
+        elif op == "dynamic_quantize_linear":         # -> (q as f32, scale, zero_point)  ops/tensor.rs:407
+            r = ops.dynamic_quantize_linear(a[0])
+        elif op == "mat_mul_integer":                 # (a, b, a_zero_point, b_zero_point)  ops/math.rs:43; zero points are scalar tensors
+            zp = [0.0 if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z in (a[2], a[3])]
+            r = ops.mat_mul_integer(a[0], a[1], zp[0], zp[1])
+        elif op == "clip":                            # (x, min, max): scalar tensors, None = the f32 range (math.rs:1984)
+            lim = [d if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z, d in ((a[1], float(np.finfo(np.float32).min)), (a[2], float(np.finfo(np.float32).max)))]
+            r = ops.clip(a[0], lim[0], lim[1])
+        elif op == "batch_norm":                      # (x, scale, bias, mean, var, epsilon)  ops/nn.rs:352
+            r = ops.batch_norm(a[0], a[1], a[2], a[3], a[4], a[5])
         elif op == "matmul_fused_add":
             r = ops.matmul_fused_add(a[0], a[1], a[2])
         elif op in ("conv1d", "conv1d_fused"):        # same argument form as conv2d (ops/nn.rs:57); _fused appends the ReLU flag

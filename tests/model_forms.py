@@ -77,3 +77,56 @@ def recurrent_forms_direct(m, blob, x):
     g, _ = R.gru(y.reshape(7, 1, H), W(2000, 3*H*H*4, [1, 3*H, H]), W(3000, 3*H*H*4, [1, 3*H, H]), None, yh)
     n = R.layer_norm(g, W(4000, H*4, [H]), W(4100, H*4, [H]), -1, 1e-5)
     return n, yh, yc
+
+
+QUANT_TEXT = """
+pub struct T4Workspace { pub buf_0: Vec<f32>, pub buf_1: Vec<f32>, }
+pub struct T4<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut T4Workspace, x: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>) {
+        let a = self.layer_norm(&x, self.weight_f32(0, 64, &[16]), self.weight_f32(64, 64, &[16]), self.weight_f32(128, 4, &[]), self.weight_f32(132, 4, &[]), &mut ws.buf_0);
+        #[cfg(target_arch = "aarch64")]
+        let b = self.linear_quantized_relu_arm(&a, 200, 384, 16, 24, self.weight_f32(600, 4, &[]), self.weight_u8(604, 1, &[]), self.weight_f32(608, 96, &[24]), &mut ws.buf_1);
+        #[cfg(not(target_arch = "aarch64"))]
+        let b = self.linear_quantized_relu(&a, self.weight_u8(200, 384, &[16, 24]), self.weight_f32(600, 4, &[]), self.weight_u8(604, 1, &[]), self.weight_f32(608, 96, &[24]), &mut ws.buf_1);
+        let c = self.linear_quantized(&b, self.weight_u8(704, 384, &[24, 16]), self.weight_f32(1088, 64, &[16]), self.weight_u8(1152, 1, &[]), self.weight_f32(1156, 64, &[16]), &mut ws.buf_0);
+        let mut buf_q = Vec::<f32>::new();
+        let mut buf_qs = Vec::<f32>::new();
+        let mut buf_qz = Vec::<f32>::new();
+        let (q_ref, qs_ref, qz_ref) = lele::kernels::dynamic_quantize_linear(&c, &mut buf_q, &mut buf_qs, &mut buf_qz);
+        let q = q_ref.to_owned();
+        let qs = qs_ref.to_owned();
+        let qz = qz_ref.to_owned();
+        #[cfg(target_arch = "aarch64")]
+        let d = self.mat_mul_integer_arm(&q, 1220, 384, 16, 24, Some(&qz), Some(&self.weight_u8(1604, 1, &[])), &mut ws.buf_1);
+        #[cfg(not(target_arch = "aarch64"))]
+        let d = lele::kernels::mat_mul_integer(&q, &self.weight_u8(1220, 384, &[16, 24]), Some(&qz), Some(&self.weight_u8(1604, 1, &[])), &mut ws.buf_1);
+        let e = lele::kernels::mul(&d, &qs, &mut ws.buf_0);
+        let f = lele::kernels::clip(&e, Some(&self.weight_f32(1608, 4, &[])), None, &mut ws.buf_1);
+        let g = self.linear(&f, &self.weight_f32(1612, 768, &[24, 8]), &self.weight_f32(2380, 32, &[8]), &mut ws.buf_0);
+        (g.to_owned(), d.to_owned())
+    }
+"""
+
+
+def quant_forms(m):
+    """The int8 statement pairs of patterns.rs:383-430 / ops/math.rs:43-95 (aarch64 arm skipped, portable arm taken) and the helper
+    methods of snippets/default_methods.rs."""
+    prog = m.parse_model_rs(QUANT_TEXT)
+    rng = np.random.default_rng(11)
+    consts = {128: [1e-5], 132: [2.0], 200: rng.integers(0, 256, 384), 600: [0.02], 604: [128], 704: rng.integers(0, 256, 384),
+              1088: 0.01 + 0.02 * rng.random(16), 1152: [121], 1220: rng.integers(0, 256, 384), 1604: [130], 1608: [-1.5]}
+    blob = m.synth_blob(prog, 9, consts)
+    x = rng.standard_normal((2, 5, 16)).astype(np.float32)
+    return prog, blob, x
+
+
+def quant_forms_direct(m, blob, x):
+    W = lambda kind, off, ln, shp: m.weight_view(blob, "weight_" + kind, off, ln, shp)
+    a = R.layer_norm(x, W("f32", 0, 64, [16]), W("f32", 64, 64, [16]), -1, 1e-5)
+    b = R.fused_quantized_linear(a, W("u8", 200, 384, [16, 24]), W("f32", 600, 4, []), 128, W("f32", 608, 96, [24]), True)
+    c = R.fused_quantized_linear(b, W("u8", 704, 384, [24, 16]), W("f32", 1088, 64, [16]), 121, W("f32", 1156, 64, [16]), False)
+    q, qs, qz = R.dynamic_quantize_linear(c)
+    d = R.mat_mul_integer(q, W("u8", 1220, 384, [16, 24]), float(qz), 130.0)
+    f = R.clip(R.mul(d, qs), -1.5, float(np.finfo(np.float32).max))
+    g = R.matmul_fused_add(f, W("f32", 1612, 768, [24, 8]), W("f32", 2380, 32, [8]))
+    return g, d

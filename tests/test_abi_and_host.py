@@ -239,6 +239,22 @@ def test_model_rs_recurrent_and_tuple_forms_on_oracle():
         m.run_program(m.parse_model_rs(bad), blob, [x], MF.R)
 
 
+def test_model_rs_quantised_forms_on_oracle():
+    """The int8 path of a generated model: cfg(aarch64) / cfg(not(aarch64)) statement pairs, self.linear_quantized[_relu],
+    self.layer_norm, DynamicQuantizeLinear tuple + to_owned, MatMulInteger with scalar zero-point tensors, clip, self.linear."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    prog, blob, x = MF.quant_forms(m)
+    ops_seen = [s["op"] for s in prog["statements"]]
+    assert "self.linear_quantized_relu_arm" not in ops_seen and "self.mat_mul_integer_arm" not in ops_seen
+    assert ops_seen.count("identity") == 3 and prog["workspace_buffers"] == 2
+    got = m.run_program(prog, blob, [x], MF.R)
+    ref = MF.quant_forms_direct(m, blob, x)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
+    assert got[0].shape == (2, 5, 8) and np.abs(got[1]).max() > 0
+
+
 def test_cuda_ops_glue_binds_to_kernel_signatures(so_path):
     """CudaOps is the only untested-on-CPU piece of the replay: here every call it makes is bound against the real
     lele_b200.kernels signature (inspect.signature(...).bind) and then answered by the oracle, so an argument-order or
@@ -270,6 +286,10 @@ def test_cuda_ops_glue_binds_to_kernel_signatures(so_path):
                     assert v["linear_before_reset"] is False
                     return R.gru(v["input"], v["w"], v["r"], v["bias"], v["initial_h"])
                 if name.startswith("reduce_"): return R.reduce(vals[0], list(vals[1]), vals[2], name[len("reduce_"):])
+                if name == "fused_quantized_linear": return R.fused_quantized_linear(v["input"], v["weight_int8"], v["weight_scale"], v["weight_zero"], v["bias"], v["apply_relu"])
+                if name == "mat_mul_integer":
+                    assert v["scale"] is None and v["bias"] is None and v["relu"] is False
+                    return R.mat_mul_integer(v["a"], v["b"], v["a_zero_point"], v["b_zero_point"])
                 return getattr(R, {"tanh_kernel": "tanh", "max": "maximum", "where_op": "where"}.get(name, name))(*vals)
             return f
 
@@ -280,6 +300,10 @@ def test_cuda_ops_glue_binds_to_kernel_signatures(so_path):
     prog, blob, x = MF.recurrent_forms(MR)
     for a, b in zip(MR.run_program(prog, blob, [x], ops), MF.recurrent_forms_direct(MR, blob, x)):
         np.testing.assert_array_equal(a, b)
+    prog, blob, x = MF.quant_forms(MR)
+    for a, b in zip(MR.run_program(prog, blob, [x], ops), MF.quant_forms_direct(MR, blob, x)):
+        np.testing.assert_array_equal(a, b)
+    assert {"fused_quantized_linear", "dynamic_quantize_linear", "mat_mul_integer", "clip", "matmul_fused_add", "mul"} <= set(seen)
     assert {"layer_norm", "gemm", "tanh_kernel", "max", "reduce_mean", "exp", "expand", "where_op", "pad", "conv1d_fused", "lstm", "gru"} <= set(seen)
 
 

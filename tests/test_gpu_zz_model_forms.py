@@ -1,5 +1,7 @@
-"""GPU replay of the generated-style statement forms in tests/model_forms.py over the C ABI (CudaOps), against the same replay on
-the CPU oracle.  f32 bar: 1e-4 relative with a 1e-4 * max|ref| floor, as in tests/test_gpu_parity.py."""
+"""GPU replay of the generated-style statement forms in tests/model_forms.py over the C ABI (CudaOps) in lock-step with the CPU
+oracle: every statement runs on both back-ends with the same inputs (the oracle's result is carried forward, so one rounding
+difference cannot flip a quantiser code or a `where` condition further down).  Bars: exact for the integer stages (u8 codes, int32
+sums, fused quantised linear), 1e-4 relative with a 1e-4 * max|ref| floor for f32, as in tests/test_gpu_parity.py."""
 import numpy as np
 import pytest
 
@@ -8,24 +10,35 @@ pytestmark = pytest.mark.gpu
 from tests import model_forms as MF            # noqa: E402
 from tests.test_gpu_parity import close        # noqa: E402
 
+EXACT = {"dynamic_quantize_linear", "mat_mul_integer", "fused_quantized_linear", "pad", "expand", "where", "concat", "transpose"}
 
-def test_math_statement_forms_replay():
+
+class Lockstep:
+    def __init__(self, MR):
+        self.gpu, self.cpu, self.calls = MR.CudaOps(), MR._NamespaceOps(MF.R), []
+
+    def __getattr__(self, name):
+        def f(*args):
+            g, c = getattr(self.gpu, name)(*args), getattr(self.cpu, name)(*args)
+            op = args[0] if name in ("binary", "unary") else name
+            for a, b in zip(g if isinstance(g, tuple) else (g,), c if isinstance(c, tuple) else (c,)):
+                if op in EXACT:
+                    np.testing.assert_array_equal(np.asarray(a, np.float32), np.asarray(b, np.float32), err_msg=op)
+                else:
+                    close(np.asarray(a), np.asarray(b))
+            self.calls.append(op)
+            return c
+        return f
+
+
+@pytest.mark.parametrize("case", ["math", "recurrent", "quant"])
+def test_statement_forms_lockstep(case):
     from lele_b200 import model_rs as MR
-    prog, blob, x = MF.math_forms(MR)
-    tg, tr = [], []
-    got = MR.run_program(prog, blob, [x], MR.CudaOps(), trace=tg)
-    ref = MR.run_program(prog, blob, [x], MF.R, trace=tr)
-    for (n1, op1, a), (n2, op2, b) in zip(tg, tr):
-        assert (n1, op1) == (n2, op2)
-        close(a, b)
-    for a, b in zip(got, ref):
-        close(a, b)
-
-
-def test_recurrent_statement_forms_replay():
-    from lele_b200 import model_rs as MR
-    prog, blob, x = MF.recurrent_forms(MR)
-    got = MR.run_program(prog, blob, [x], MR.CudaOps())
-    ref = MR.run_program(prog, blob, [x], MF.R)
-    for a, b in zip(got, ref):
-        close(a, b)
+    make, direct = {"math": (MF.math_forms, MF.math_forms_direct), "recurrent": (MF.recurrent_forms, MF.recurrent_forms_direct),
+                    "quant": (MF.quant_forms, MF.quant_forms_direct)}[case]
+    prog, blob, x = make(MR)
+    ops = Lockstep(MR)
+    got = MR.run_program(prog, blob, [x], ops)
+    for a, b in zip(got, direct(MR, blob, x)):
+        np.testing.assert_array_equal(a, b)           # the carried values are the oracle's
+    assert len(ops.calls) >= {"math": 10, "recurrent": 3, "quant": 8}[case]
