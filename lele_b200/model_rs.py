@@ -82,14 +82,24 @@ def _parse_arg(a: str):
         if tail == ".as_i64_vec()":
             return {"weight_list": w["weight"]}
         raise ValueError(f"model.rs: unsupported weight expression tail {tail!r}")
+    m = re.fullmatch(r"&(\w+)\.data\[\.\.\]", a)                       # an i64 shape tensor used as a slice (ops/tensor.rs:27)
+    if m:
+        return {"i64vec": m.group(1)}
+    m = re.fullmatch(r"&lele::kernels::to_i64_vec\((.+)\)", a)           # inline conversion of a tensor or a weight literal (ops/math.rs:232)
+    if m:
+        return {"i64vec_of": _parse_arg(m.group(1))}
     if a.startswith("&[") and a.endswith("]"):
         items = _split_top(a[2:-1])
         if items and items[0].startswith("&"):
-            return {"vars": [i.lstrip("&").strip() for i in items]}
+            if all(re.fullmatch(r"&\w+", i) for i in items):
+                return {"vars": [i.lstrip("&").strip() for i in items]}
+            return {"items": [_parse_arg(i) for i in items]}            # tensors and weight literals mixed (Concat of a shape with constants)
         return {"list": [_num(i) for i in items]}
+    if re.fullmatch(r"-?\d+i64", a):
+        return {"i64": int(a[:-3])}
     if a.startswith("&mut "):
         return {"out": a[5:].strip()}
-    if a.startswith("&"):
+    if re.fullmatch(r"&\s*[A-Za-z_][A-Za-z0-9_]*", a):
         return {"var": a[1:].strip()}
     if re.fullmatch(r"-?\d+(\.\d+)?([eE][-+]?\d+)?(f32|i64|usize)?", a):
         return _num(a)
@@ -149,7 +159,7 @@ def parse_model_rs(text: str) -> dict:
         if m:
             stmts.append({"outs": [m.group(1)], "op": "split_take", "args": [{"var": split_src[0]}, split_src[1], {"list": split_src[2]}, int(m.group(2))]})
             continue
-        if re.match(r"^let mut buf_\w+ = Vec::<(f32|i64)>::new\(\);$", line):
+        if re.match(r"^let mut (buf|temp_cast_buf)_\w+ = Vec::<(f32|i64)>::new\(\);$", line):
             continue
         m = re.match(r"^let (\w+) = self\.(\w+)\((.*)\);$", line)   # helper methods of src/compiler/snippets/default_methods.rs
         if m:
@@ -157,14 +167,14 @@ def parse_model_rs(text: str) -> dict:
             args = [a for a in args if not (isinstance(a, dict) and "out" in a)]
             stmts.append({"outs": [m.group(1)], "op": "self." + m.group(2), "args": args})
             continue
-        m = re.match(r"^let (\w+) = (\w+)\.(?:clone|to_owned)\(\);", line)
+        m = re.match(r"^let (\w+) = (\w+)\.(?:clone|to_owned)\(\);", line)                 # incl. "// Cast f32->f32 is no-op" (ops/tensor.rs:236)
         if m:
             stmts.append({"outs": [m.group(1)], "op": "identity", "args": [{"var": m.group(2)}]})
             continue
         m = re.match(r"^let \((\w+), ([\w, ]+)\) = \(lele::kernels::(layer_norm)\((.*)\), lele::tensor::TensorView::empty\(\)[^;]*\);$", line)
         if m:                                                    # LayerNormalization with unused Mean / InvStdDev outputs (ops/nn.rs:261)
             line = f"let {m.group(1)} = lele::kernels::layer_norm({m.group(4)});"
-        m = re.match(r"^let \(([\w, ]+)\) = lele::kernels::(\w+)\((.*)\);$", line) or re.match(r"^let (\w+) = lele::kernels::(\w+)\((.*)\);$", line)
+        m = re.match(r"^let \(([\w, ]+)\) = lele::kernels::(\w+)\((.*)\);$", line) or re.match(r"^let (\w+) = lele::kernels::(?:utils::)?(\w+)\((.*)\);$", line)
         if m:
             outs = [o.strip() for o in m.group(1).split(",")]   # "_" = an output the graph never reads
             args = [_parse_arg(a) for a in _split_top(m.group(3))]
@@ -235,9 +245,89 @@ class _NamespaceOps:
     def resize_nearest(self, x, scales, sizes, mode): return self.ns.resize_nearest(x, scales=scales, sizes=sizes, mode=mode)
 
 
+def _c(x, dtype=None):  # C-contiguous without np.ascontiguousarray's promotion of rank-0 values to rank 1
+    return np.asarray(x, dtype=dtype, order="C")
+
+
 def _reshape(x, shape):  # shape.rs:2-93: 0 copies the input dim, -1 is inferred
     shp = [x.shape[i] if s == 0 else s for i, s in enumerate(shape)]
-    return np.ascontiguousarray(x).reshape(shp)
+    return _c(x).reshape(shp)
+
+
+def _to_i64_list(x):  # to_i64_vec (manipulation.rs:1082): `as i64` truncation of every element
+    if isinstance(x, (list, tuple)):
+        return [int(v) for v in x]
+    return [int(v) for v in np.asarray(x).reshape(-1)]
+
+
+def _is_i64(x):
+    return isinstance(x, (np.ndarray, np.generic)) and np.asarray(x).dtype == np.int64
+
+
+def _scalar0(x, dflt):
+    x = np.asarray(x).reshape(-1)
+    return x[0] if x.size else dflt
+
+
+def _host_i64_op(op, a):
+    """Shape arithmetic.  The code generator types shape-carrying values as i64 tensors (generate.rs var_types) and the reference
+    computes them with the same generic kernels on the host; they are a few elements each and decide tensor SHAPES, so they stay
+    host values here as well (numpy int64) and never reach the device.  Returns None when the statement is not of this class."""
+    if op == "shape":                                 # shape.rs:100
+        return np.array(np.asarray(a[0]).shape, np.int64)
+    if op == "size":                                  # shape.rs:95: rank-0 tensor holding the element count
+        return np.array(np.asarray(a[0]).size, np.int64)
+    if op == "to_i64_vec":
+        return _to_i64_list(a[0])
+    if op == "cast_to_i64":                           # utils.rs:85
+        return np.trunc(np.asarray(a[0])).astype(np.int64) if np.asarray(a[0]).dtype.kind == "f" else np.asarray(a[0]).astype(np.int64)
+    if op == "cast_to_f32":                           # utils.rs:71
+        return np.asarray(a[0]).astype(np.float32)
+    if op == "constant_of_shape":                     # shape.rs:122: the value literal decides the element type
+        shp = tuple(_to_i64_list(a[0]))
+        return np.full(shp, a[1], np.int64 if isinstance(a[1], np.int64) else np.float32)
+    if op == "range_i64":                             # math.rs:2057
+        s0, lim, d = int(_scalar0(a[0], 0)), int(_scalar0(a[1], 0)), int(_scalar0(a[2], 1))
+        n = max(int(np.ceil((lim - s0) / d)), 0) if d != 0 else 0
+        return s0 + np.arange(n, dtype=np.int64) * d
+    if op == "range":                                 # math.rs:2033: start + i * delta in f32
+        s0, lim, d = np.float32(_scalar0(a[0], 0.0)), np.float32(_scalar0(a[1], 0.0)), np.float32(_scalar0(a[2], 1.0))
+        n = int(max(np.ceil(np.float32(lim - s0) / d), 0.0)) if d != 0 else 0
+        return (s0 + np.arange(n, dtype=np.float32) * d).astype(np.float32)
+    if op in ("equal_i64", "equal_i64_f32_r", "equal_i64_f32_r_i64", "equal_i64_f32_lhs"):   # math.rs:1201-1236: operands compared as i64
+        x, y = (np.trunc(np.asarray(v)).astype(np.int64) if np.asarray(v).dtype.kind == "f" else np.asarray(v, np.int64) for v in a[:2])
+        return (x == y).astype(np.int64)
+    if op == "less_i64":                              # math.rs:2161
+        return (np.asarray(a[0]) < np.asarray(a[1])).astype(np.int64)
+    tens = [v for v in a if isinstance(v, (np.ndarray, np.generic))]
+    if op == "concat":
+        tens = list(a[0])
+    if not tens or not all(_is_i64(v) for v in tens):
+        return None
+    if op in ("add", "sub", "mul"):
+        return {"add": np.add, "sub": np.subtract, "mul": np.multiply}[op](a[0], a[1]).astype(np.int64)
+    if op == "div":                                   # Rust i64 division truncates toward zero
+        x, y = np.broadcast_arrays(np.asarray(a[0]), np.asarray(a[1]))
+        return (np.sign(x) * np.sign(y) * (np.abs(x) // np.abs(y))).astype(np.int64)
+    if op == "not":                                   # math.rs:1508
+        return (np.asarray(a[0]) == 0).astype(np.int64)
+    if op == "gather":                                # manipulation.rs:589 on an i64 tensor (picking dims out of a shape)
+        x, idx = np.asarray(a[0]), np.asarray(a[1])
+        return np.take(x, np.where(idx < 0, idx + x.shape[a[2]], idx), axis=a[2]).astype(np.int64)
+    if op == "concat":
+        return np.concatenate([np.atleast_1d(v) for v in a[0]], axis=a[1])
+    if op == "slice":
+        x = np.asarray(a[0]); sl = [np.s_[:]] * x.ndim
+        starts, ends, axes, steps = a[1], a[2], (a[3] or list(range(len(a[1])))), (a[4] or [1] * len(a[1]))
+        for st_, en, ax, sp in zip(starts, ends, axes, steps):
+            sl[ax] = np.s_[int(np.clip(st_, -2**62, 2**62)):int(np.clip(en, -2**62, 2**62)):int(sp)]
+        return _c(x[tuple(sl)])
+    if op == "where_op":
+        return np.where(np.asarray(a[0]) != 0, a[1], a[2]).astype(np.int64)
+    if op == "expand":
+        x = np.asarray(a[0]); shp = np.broadcast_shapes(x.shape, tuple(a[1]))
+        return _c(np.broadcast_to(x, shp))
+    return None                                       # reshape / unsqueeze / squeeze / flatten / identity keep the dtype below
 
 
 def run_program(program: dict, blob, inputs, ops=None, trace=None):
@@ -247,13 +337,18 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
         ops = CudaOps()
     elif not hasattr(ops, "binary"):
         ops = _NamespaceOps(ops)
-    env = {n: np.ascontiguousarray(a, dtype=np.float32) for n, a in zip(program["inputs"], inputs)}
+    env = {n: _c(a, np.int64 if np.asarray(a).dtype.kind in "iu" else np.float32)
+           for n, a in zip(program["inputs"], inputs)}
     split_cache = {}
 
     def val(a):
         if isinstance(a, dict):
             if "var" in a: return env[a["var"]]
             if "vars" in a: return [env[v] for v in a["vars"]]
+            if "items" in a: return [val(i) for i in a["items"]]
+            if "i64vec" in a: return _to_i64_list(env[a["i64vec"]])
+            if "i64vec_of" in a: return _to_i64_list(val(a["i64vec_of"]))
+            if "i64" in a: return np.int64(a["i64"])
             if "weight" in a: return weight_view(blob, *a["weight"])
             if "weight_scalar" in a: return int(weight_view(blob, *a["weight_scalar"]).reshape(-1)[0])
             if "weight_list" in a: return [int(v) for v in weight_view(blob, *a["weight_list"]).reshape(-1)]
@@ -263,7 +358,10 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
 
     for st in program["statements"]:
         op, a = st["op"], [val(x) for x in st["args"]]
-        if op in ("conv2d", "conv2d_silu", "conv2d_fused"):
+        r = _host_i64_op(op, a)
+        if r is not None:
+            pass
+        elif op in ("conv2d", "conv2d_silu", "conv2d_fused"):
             act = 2 if op == "conv2d_silu" else (1 if (op == "conv2d_fused" and a[7]) else 0)
             r = ops.conv2d(a[0], a[1], a[2], a[3], a[4], a[5], a[6], act)
         elif op == "conv_transpose":
@@ -315,7 +413,7 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
         elif op == "expand":
             r = ops.expand(a[0], a[1])
         elif op == "squeeze":
-            x = np.ascontiguousarray(a[0]); axes = a[1]
+            x = _c(a[0]); axes = a[1]
             r = np.squeeze(x, axis=tuple(ax % x.ndim for ax in axes)) if axes else np.squeeze(x)
         elif op == "where_op":
             r = ops.where(a[0], a[1], a[2])
@@ -331,10 +429,10 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
         elif op == "reshape":
             r = _reshape(a[0], a[1])
         elif op == "flatten":
-            x = np.ascontiguousarray(a[0]); ax = a[1] % (x.ndim + 1) if a[1] < 0 else a[1]
+            x = _c(a[0]); ax = a[1] % (x.ndim + 1) if a[1] < 0 else a[1]
             r = x.reshape(int(np.prod(x.shape[:ax], dtype=np.int64)), -1)
         elif op == "unsqueeze":
-            r = np.ascontiguousarray(a[0])
+            r = _c(a[0])
             for ax in sorted(x % (r.ndim + 1) if x < 0 else x for x in a[1]):
                 r = np.expand_dims(r, ax)
         elif op == "transpose":
@@ -379,7 +477,8 @@ def synth_blob(program: dict, seed: int = 7, constants=None) -> bytes:
     `constants` = {offset: array} overrides (shape constants, anchors, k ...), written with the view's own dtype."""
     size, views = 0, {}
     for st in program["statements"]:
-        for i, a in enumerate(st["args"]):
+        flat = [(i, a) for i, a in enumerate(st["args"])] + [(i, b) for i, a in enumerate(st["args"]) if isinstance(a, dict) for b in (a.get("items", []) + ([a["i64vec_of"]] if "i64vec_of" in a else []))]
+        for i, a in flat:
             if isinstance(a, dict):
                 for key in ("weight", "weight_scalar", "weight_list"):
                     if key in a:

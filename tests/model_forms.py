@@ -130,3 +130,56 @@ def quant_forms_direct(m, blob, x):
     f = R.clip(R.mul(d, qs), -1.5, float(np.finfo(np.float32).max))
     g = R.matmul_fused_add(f, W("f32", 1612, 768, [24, 8]), W("f32", 2380, 32, [8]))
     return g, d
+
+
+SHAPE_TEXT = """
+pub struct T5Workspace { pub buf_0: Vec<f32>, pub buf_1: Vec<f32>, }
+pub struct T5<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut T5Workspace, x: TensorView<'w, f32>, len: TensorView<'w, i64>) -> (TensorView<'static, f32>, TensorView<'static, i64>, TensorView<'static, i64>) {
+        let s = lele::kernels::shape(&x);
+        let b = lele::kernels::gather(&s, &self.weight_i64(0, 8, &[]), 0, &mut ws.buf_0);
+        let t = lele::kernels::gather(&s, &self.weight_i64(8, 8, &[]), 0, &mut ws.buf_0);
+        let bu = lele::kernels::unsqueeze(&b, &[0]);
+        let tu = lele::kernels::unsqueeze(&t, &[0]);
+        let c = lele::kernels::concat(&[&bu, &tu, &self.weight_i64(16, 16, &[2])], 0, &mut ws.buf_0);
+        let temp_i64_1 = lele::kernels::to_i64_vec(&c);
+        let r = lele::kernels::reshape(&x, &temp_i64_1);
+        let p = lele::kernels::transpose(&r, &[0, 2, 1, 3], &mut ws.buf_1);
+        let mut temp_cast_buf_tf = Vec::<f32>::new();
+        let tf = lele::kernels::utils::cast_to_f32(&t, &mut temp_cast_buf_tf);
+        let sq = lele::kernels::sqrt(&tf, &mut ws.buf_0);
+        let y = lele::kernels::div(&p, &sq, &mut ws.buf_0);
+        let mut buf_rg = Vec::<i64>::new();
+        let rg = lele::kernels::range_i64(&self.weight_i64(32, 8, &[]), &t, &self.weight_i64(40, 8, &[]), &mut buf_rg);
+        let ru = lele::kernels::unsqueeze(&rg, &[0]);
+        let lu = lele::kernels::unsqueeze(&len, &[1]);
+        let mk = lele::kernels::less_i64(&ru, &lu, &mut ws.buf_1);
+        let mut temp_cast_buf_mf = Vec::<f32>::new();
+        let mf = lele::kernels::utils::cast_to_f32(&mk, &mut temp_cast_buf_mf);
+        let m4 = lele::kernels::unsqueeze(&mf, &[1, 3]);
+        let z = lele::kernels::mul(&y, &m4, &mut ws.buf_1);
+        let h = lele::kernels::mul(&t, &self.weight_i64(48, 8, &[]), &mut ws.buf_0);
+        let zs = lele::kernels::slice(&z, &[1], &t.data[..], &[3], &[1], &mut ws.buf_0);
+        let k = lele::kernels::constant_of_shape(&c, 0.0, &mut ws.buf_1);
+        let sz = lele::kernels::size(&k);
+        let e = lele::kernels::reduce_sum(&zs, &lele::kernels::to_i64_vec(&self.weight_i64(56, 8, &[1])), false, &mut ws.buf_1);
+        (e.to_owned(), h.to_owned(), sz.to_owned())
+    }
+"""
+
+
+def shape_forms(m):
+    """Dynamic-shape plumbing of an exported transformer block: Shape -> Gather -> Unsqueeze -> Concat -> Reshape on i64 host tensors,
+    a length mask from Range / Less, Cast back to f32 for the device multiply (ops/tensor.rs:10-70, :191-291; ops/math.rs:360-405)."""
+    prog = m.parse_model_rs(SHAPE_TEXT)
+    blob = m.synth_blob(prog, 4, {0: [0], 8: [1], 16: [4, 4], 32: [0], 40: [1], 48: [2], 56: [-1]})
+    x = np.random.default_rng(5).standard_normal((2, 5, 16)).astype(np.float32)
+    return prog, blob, [x, np.array([3, 5], np.int64)]
+
+
+def shape_forms_direct(x, lens):
+    bsz, t, _ = x.shape
+    y = R.div(R.transpose(x.reshape(bsz, t, 4, 4), [0, 2, 1, 3]), R.sqrt(np.float32(t)))
+    mask = (np.arange(t)[None, :] < lens[:, None]).astype(np.float32)[:, None, :, None]
+    z = R.mul(y, mask)
+    return R.reduce(z[..., 1:], [-1], False, "sum"), np.array(2 * t, np.int64), np.array(bsz * t * 16, np.int64)

@@ -255,6 +255,45 @@ def test_model_rs_quantised_forms_on_oracle():
     assert got[0].shape == (2, 5, 8) and np.abs(got[1]).max() > 0
 
 
+def test_model_rs_shape_arithmetic_stays_on_the_host():
+    """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
+    inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    prog, blob, inputs = MF.shape_forms(m)
+
+    class Spy(m._NamespaceOps):
+        calls = []
+
+        def __getattr__(self, name):
+            f = getattr(self.ns, name)
+
+            def g(*a, **k):
+                Spy.calls.append(name)
+                for v in a:
+                    assert not (isinstance(v, np.ndarray) and v.dtype == np.int64 and name != "transpose"), (name, "i64 tensor reached the device namespace")
+                return f(*a, **k)
+            return g
+
+        def binary(self, op, a, b):
+            Spy.calls.append(op); assert np.asarray(a).dtype == np.float32 and np.asarray(b).dtype == np.float32
+            return super().binary(op, a, b)
+
+        def unary(self, op, x):
+            Spy.calls.append(op); assert np.asarray(x).dtype == np.float32
+            return super().unary(op, x)
+
+    got = m.run_program(prog, blob, inputs, Spy(MF.R))
+    ref = MF.shape_forms_direct(*inputs)
+    for a, b in zip(got, ref):
+        assert np.asarray(a).dtype == np.asarray(b).dtype and np.asarray(a).shape == np.asarray(b).shape
+        np.testing.assert_array_equal(a, b)
+    assert Spy.calls == ["transpose", "sqrt", "div", "mul", "slice", "reduce"]
+    # integer division truncates toward zero, like Rust's i64 `/`
+    assert m._host_i64_op("div", [np.array([-7, 7, -7], np.int64), np.array([2, -2, -2], np.int64)]).tolist() == [-3, -3, 3]
+    assert m._host_i64_op("div", [np.ones(2, np.float32), np.ones(2, np.float32)]) is None
+
+
 def test_cuda_ops_glue_binds_to_kernel_signatures(so_path):
     """CudaOps is the only untested-on-CPU piece of the replay: here every call it makes is bound against the real
     lele_b200.kernels signature (inspect.signature(...).bind) and then answered by the oracle, so an argument-order or
