@@ -404,6 +404,7 @@ def neg(x, ctx=None): return _unary("neg", x, ctx)
 def reciprocal(x, ctx=None): return _unary("reciprocal", x, ctx)
 def sin(x, ctx=None): return _unary("sin", x, ctx)
 def cos(x, ctx=None): return _unary("cos", x, ctx)
+def not_(x, ctx=None): return _unary("not", x, ctx)  # lele::kernels::not (math.rs:1508); `not` is a Python keyword
 
 
 def clip(x, lo, hi, ctx=None):

@@ -161,6 +161,19 @@ def parse_model_rs(text: str) -> dict:
             continue
         if re.match(r"^let mut (buf|temp_cast_buf)_\w+ = Vec::<(f32|i64)>::new\(\);$", line):
             continue
+        m = re.match(r"^let (\w+) = (self\.weight_\w+\(.*\));$", line)     # Identity / Constant of a stored tensor (ops/tensor.rs:443)
+        if m:
+            stmts.append({"outs": [m.group(1)], "op": "constant", "args": [_parse_arg(m.group(2))]})
+            continue
+        m = re.match(r"^let (\w+) = lele::tensor::TensorView::from_owned\(vec!\[(.*)\], vec!\[(.*)\]\);$", line)   # small inline constant (:459, :489)
+        if m:
+            vals = [float(v) for v in m.group(2).split(",") if v.strip()]
+            stmts.append({"outs": [m.group(1)], "op": "literal", "args": [{"list": vals}, {"list": [int(v) for v in m.group(3).split(",") if v.strip()]}]})
+            continue
+        m = re.match(r"^let (\w+) = lele::tensor::TensorView::empty\(\);", line)           # absent / oversized constant (:483, :514)
+        if m:
+            stmts.append({"outs": [m.group(1)], "op": "literal", "args": [{"list": []}, {"list": [0]}]})
+            continue
         m = re.match(r"^let (\w+) = self\.(\w+)\((.*)\);$", line)   # helper methods of src/compiler/snippets/default_methods.rs
         if m:
             args = [_parse_arg(a) for a in _split_top(m.group(3))]
@@ -212,7 +225,7 @@ class CudaOps:
     def reduce(self, x, axes, keepdims, kind):
         return {"sum": self.K.reduce_sum, "mean": self.K.reduce_mean, "max": self.K.reduce_max, "l2": self.K.reduce_l2}[kind](x, axes, keepdims, ctx=self.ctx)
     def binary(self, op, a, b): return getattr(self.K, op)(a, b, ctx=self.ctx)
-    def unary(self, op, x): return getattr(self.K, op)(x, ctx=self.ctx)
+    def unary(self, op, x): return getattr(self.K, "not_" if op == "not" else op)(x, ctx=self.ctx)
     def layer_norm(self, x, g, b, axis, eps): return self.K.layer_norm(x, g, b, axis, eps, ctx=self.ctx)
     def gemm(self, a, b, c, alpha, beta, ta, tb): return self.K.gemm(a, b, c, alpha, beta, ta, tb, ctx=self.ctx)
     def matmul_fused_add(self, a, b, bias): return self.K.matmul_fused_add(a, b, bias, ctx=self.ctx)
@@ -224,6 +237,7 @@ class CudaOps:
     def dynamic_quantize_linear(self, x): return self.K.dynamic_quantize_linear(x, ctx=self.ctx)
     def mat_mul_integer(self, a, b, zp_a, zp_b): return self.K.mat_mul_integer(a, b, zp_a, zp_b, ctx=self.ctx)
     def clip(self, x, lo, hi): return self.K.clip(x, lo, hi, ctx=self.ctx)
+    def stft(self, x, n_fft, hop, win, window): return self.K.stft(x, n_fft, hop, win, window, ctx=self.ctx)
     def batch_norm(self, x, scale, bias, mean, var, eps): return self.K.batch_norm(x, scale, bias, mean, var, eps, ctx=self.ctx)
     def lstm(self, x, w, r, bias, h0, c0): return self.K.lstm(x, w, r, bias, None, h0, c0, ctx=self.ctx)
     def gru(self, x, w, r, bias, h0): return self.K.gru(x, w, r, bias, h0, ctx=self.ctx)
@@ -238,7 +252,7 @@ class _NamespaceOps:
     def __getattr__(self, name):
         return getattr(self.ns, name)
 
-    _ALIAS = {"tanh_kernel": "tanh", "max": "maximum"}
+    _ALIAS = {"tanh_kernel": "tanh", "max": "maximum", "not": "not_"}
 
     def binary(self, op, a, b): return getattr(self.ns, self._ALIAS.get(op, op))(a, b)
     def unary(self, op, x): return getattr(self.ns, self._ALIAS.get(op, op))(x)
@@ -361,6 +375,16 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
         r = _host_i64_op(op, a)
         if r is not None:
             pass
+        elif op == "constant":
+            r = a[0]
+        elif op == "literal":
+            r = np.asarray(a[0], np.float32).reshape(tuple(a[1]))
+        elif op == "stft":                            # (signal, n_fft, frame_step, n_fft, window)  ops/math.rs:480
+            r = ops.stft(a[0], a[1], a[2], a[3], a[4])
+        elif op in ("pow", "equal", "less"):
+            r = ops.binary(op, a[0], a[1])
+        elif op in ("log", "sin", "cos", "not"):
+            r = ops.unary(op, a[0])
         elif op in ("conv2d", "conv2d_silu", "conv2d_fused"):
             act = 2 if op == "conv2d_silu" else (1 if (op == "conv2d_fused" and a[7]) else 0)
             r = ops.conv2d(a[0], a[1], a[2], a[3], a[4], a[5], a[6], act)

@@ -165,6 +165,17 @@ def neg(x): return -_a(x)                                          # math.rs:214
 def sqrt(x): return np.sqrt(_a(x))                                 # math.rs:1460
 def reciprocal(x): return (f32(1.0) / _a(x)).astype(np.float32)    # math.rs:893
 def clip(x, lo, hi): return np.minimum(np.maximum(_a(x), f32(lo)), f32(hi))  # math.rs:1984
+# libm-backed f32 functions (Rust's f32::powf / ln / sin / cos call the platform libm; numpy's float32 loops do the same):
+# parity bar 1e-5 relative with an absolute floor, not bit-exact
+def pow(a, b): return np.power(_a(a), _a(b)).astype(np.float32)    # noqa: A001  math.rs:1481
+def log(x):                                                          # math.rs:2130
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.log(_a(x)).astype(np.float32)
+def sin(x): return np.sin(_a(x)).astype(np.float32)                # math.rs:2084
+def cos(x): return np.cos(_a(x)).astype(np.float32)                # math.rs:2096
+def equal(a, b): return (_a(a) == _a(b)).astype(np.float32)        # math.rs:1193: 1.0 / 0.0
+def less(a, b): return (_a(a) < _a(b)).astype(np.float32)          # math.rs:2154
+def not_(x): return (_a(x) == 0).astype(np.float32)                # math.rs:1508
 
 
 def mod_f32(a, b):  # math.rs:1163-1192 : a - b*floor(a/b), 0 when b == 0

@@ -59,5 +59,6 @@ gather_elements = N.gather_elements
 resize_nearest = N.resize_nearest
 add, sub, mul, div = N.add, N.sub, N.mul, N.div
 maximum, neg, sqrt, reciprocal, clip, mod_f32, prelu = N.maximum, N.neg, N.sqrt, N.reciprocal, N.clip, N.mod_f32, N.prelu
+pow, log, sin, cos, equal, less, not_ = N.pow, N.log, N.sin, N.cos, N.equal, N.less, N.not_  # noqa: A001
 reduce = N.reduce
 SenseVoiceRef = B.SenseVoiceRef

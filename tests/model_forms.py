@@ -183,3 +183,41 @@ def shape_forms_direct(x, lens):
     mask = (np.arange(t)[None, :] < lens[:, None]).astype(np.float32)[:, None, :, None]
     z = R.mul(y, mask)
     return R.reduce(z[..., 1:], [-1], False, "sum"), np.array(2 * t, np.int64), np.array(bsz * t * 16, np.int64)
+
+
+CONST_TEXT = """
+pub struct T6Workspace { pub buf_0: Vec<f32>, }
+pub struct T6<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut T6Workspace, x: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>) {
+        let win = self.weight_f32(0, 256, &[64]);
+        let two = lele::tensor::TensorView::from_owned(vec![2.0], vec![1]);
+        let big = lele::tensor::TensorView::empty(); // Large
+        let sp = lele::kernels::stft(&x, 64, 16, 64, Some(&win), &mut ws.buf_0);
+        let p = lele::kernels::pow(&sp, &two, &mut ws.buf_0);
+        let e = lele::kernels::reduce_sum(&p, &[-1], false, &mut ws.buf_0);
+        let l = lele::kernels::log(&e, &mut ws.buf_0);
+        let s = lele::kernels::sin(&l, &mut ws.buf_0);
+        let c = lele::kernels::cos(&l, &mut ws.buf_0);
+        let lt = lele::kernels::less(&s, &c, &mut ws.buf_0);
+        let nt = lele::kernels::not(&lt, &mut ws.buf_0);
+        let eq = lele::kernels::equal(&nt, &lt, &mut ws.buf_0);
+        let y = lele::kernels::where_op(&lt, &s, &c, &mut ws.buf_0);
+        (y.to_owned(), eq.to_owned())
+    }
+"""
+
+
+def const_forms(m):
+    """Constant / Identity statements (stored tensor, inline literal, empty), STFT with a stored window, and the libm-backed math."""
+    prog = m.parse_model_rs(CONST_TEXT)
+    blob = m.synth_blob(prog, 6, {0: np.hanning(64)})
+    x = np.random.default_rng(8).standard_normal(400).astype(np.float32)
+    return prog, blob, x
+
+
+def const_forms_direct(m, blob, x):
+    win = m.weight_view(blob, "weight_f32", 0, 256, [64])
+    l = R.log(R.reduce(R.pow(R.stft(x, 64, 16, 64, win), np.float32(2.0)), [-1], False, "sum"))
+    s, c = R.sin(l), R.cos(l)
+    lt = R.less(s, c)
+    return R.where(lt, s, c), R.equal(R.not_(lt), lt)

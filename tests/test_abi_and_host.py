@@ -255,6 +255,17 @@ def test_model_rs_quantised_forms_on_oracle():
     assert got[0].shape == (2, 5, 8) and np.abs(got[1]).max() > 0
 
 
+def test_model_rs_constants_stft_and_libm_math_on_oracle():
+    from tests import model_forms as MF
+    m = _model_rs()
+    prog, blob, x = MF.const_forms(m)
+    assert [s["op"] for s in prog["statements"]][:3] == ["constant", "literal", "literal"]
+    got = m.run_program(prog, blob, [x], MF.R)
+    for a, b in zip(got, MF.const_forms_direct(m, blob, x)):
+        np.testing.assert_array_equal(a, b)
+    assert got[0].shape == (22, 33) and not got[1].any()          # (400 - 64) / 16 + 1 frames x 33 bins; not(x) never equals x
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
@@ -329,6 +340,9 @@ def test_cuda_ops_glue_binds_to_kernel_signatures(so_path):
                 if name == "mat_mul_integer":
                     assert v["scale"] is None and v["bias"] is None and v["relu"] is False
                     return R.mat_mul_integer(v["a"], v["b"], v["a_zero_point"], v["b_zero_point"])
+                if name == "stft":
+                    assert v["power"] is False
+                    return R.stft(v["input"], v["n_fft"], v["hop_length"], v["win_length"], v["window"])
                 return getattr(R, {"tanh_kernel": "tanh", "max": "maximum", "where_op": "where"}.get(name, name))(*vals)
             return f
 
@@ -342,6 +356,10 @@ def test_cuda_ops_glue_binds_to_kernel_signatures(so_path):
     prog, blob, x = MF.quant_forms(MR)
     for a, b in zip(MR.run_program(prog, blob, [x], ops), MF.quant_forms_direct(MR, blob, x)):
         np.testing.assert_array_equal(a, b)
+    prog, blob, x = MF.const_forms(MR)
+    for a, b in zip(MR.run_program(prog, blob, [x], ops), MF.const_forms_direct(MR, blob, x)):
+        np.testing.assert_array_equal(a, b)
+    assert {"stft", "pow", "log", "sin", "cos", "less", "not_", "equal"} <= set(seen)
     assert {"fused_quantized_linear", "dynamic_quantize_linear", "mat_mul_integer", "clip", "matmul_fused_add", "mul"} <= set(seen)
     assert {"layer_norm", "gemm", "tanh_kernel", "max", "reduce_mean", "exp", "expand", "where_op", "pad", "conv1d_fused", "lstm", "gru"} <= set(seen)
 
