@@ -143,7 +143,7 @@ def parse_model_rs(text: str) -> dict:
         if skip_next:
             skip_next = False
             continue
-        m = re.match(r"^\((.*)\)$", line)                      # tail expression: (a.to_owned(), b.to_owned())
+        m = re.match(r"^\((.*)\)$", line) or re.match(r"^(\w+\.to_owned\(\))$", line)   # tail expression: (a.to_owned(), b.to_owned()) or a.to_owned()
         if m:
             outputs = [p.strip().replace(".to_owned()", "") for p in _split_top(m.group(1))]
             continue
@@ -197,6 +197,15 @@ def parse_model_rs(text: str) -> dict:
         raise ValueError(f"model.rs: unsupported statement: {line[:160]}")
     if inputs is None or outputs is None:
         raise ValueError("model.rs: no run_chunk body found")
+    # A model split into several run_chunk_N functions shares one set of tensor names (generate.rs:704-790), so the statement list
+    # is simply the chunks in order; the graph's own inputs and outputs are those of forward_with_workspace (mod.rs:1306-1350).
+    fw = re.search(r"pub fn forward_with_workspace<'w>\(&self, ws: [^,]+, (.*?)\) -> [^{]*\{\n(.*?)\n    \}", text, re.S)
+    if fw:
+        inputs = re.findall(r"(\w+): TensorView", fw.group(1))
+        tail = fw.group(2).strip().splitlines()[-1].strip()
+        outputs = [p.strip() for p in _split_top(tail[1:-1] if tail.startswith("(") else tail)]
+        if not all(re.fullmatch(r"\w+", o) for o in outputs):
+            raise ValueError(f"model.rs: graph output that is a stored tensor is not supported: {tail[:120]}")
     return {"class": cls.group(1) if cls else "Model", "workspace_buffers": n_bufs, "inputs": inputs, "statements": stmts, "outputs": outputs}
 
 

@@ -266,6 +266,44 @@ def test_model_rs_constants_stft_and_libm_math_on_oracle():
     assert got[0].shape == (22, 33) and not got[1].any()          # (400 - 64) / 16 + 1 frames x 33 bins; not(x) never equals x
 
 
+def test_model_rs_multi_chunk_model():
+    """A graph split into run_chunk_0 / run_chunk_1 (generate.rs:704): statements are the chunks in order, graph inputs and outputs
+    come from forward_with_workspace -- here the second chunk consumes a graph input the first never sees, and a chunk with a
+    single live output returns it without a tuple."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    text = """
+pub struct T7Workspace { pub buf_0: Vec<f32>, }
+pub struct T7<'a> { data: &'a [u8] }
+    #[inline(never)]
+    fn run_chunk_0<'w>(&self, ws: &'w mut T7Workspace, x: TensorView<'w, f32>) -> TensorView<'static, f32> {
+        let a = lele::kernels::relu(&x, &mut ws.buf_0);
+        a.to_owned()
+    }
+
+    #[inline(never)]
+    fn run_chunk_1<'w>(&self, ws: &'w mut T7Workspace, a: TensorView<'w, f32>, y: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>) {
+        let b = lele::kernels::add(&a, &y, &mut ws.buf_0);
+        let c = lele::kernels::mul(&b, &self.weight_f32(0, 12, &[3]), &mut ws.buf_0);
+        (b.to_owned(), c.to_owned())
+    }
+
+    pub fn forward_with_workspace<'w>(&self, ws: &'w mut T7Workspace, x: TensorView<'w>, y: TensorView<'w>) -> (TensorView<'w>, TensorView<'w>) {
+        let (a) = self.run_chunk_0(ws, x);
+        let (b, c) = self.run_chunk_1(ws, a, y);
+        (c, b)
+    }
+}
+"""
+    prog = m.parse_model_rs(text)
+    assert prog["inputs"] == ["x", "y"] and prog["outputs"] == ["c", "b"] and [s["op"] for s in prog["statements"]] == ["relu", "add", "mul"]
+    blob = m.synth_blob(prog, 1)
+    x = np.array([[-1.0, 2.0, 3.0]], np.float32); y = np.array([[10.0, 20.0, 30.0]], np.float32)
+    c, b = m.run_program(prog, blob, [x, y], MF.R)
+    np.testing.assert_array_equal(b, np.maximum(x, 0) + y)
+    np.testing.assert_array_equal(c, b * m.weight_view(blob, "weight_f32", 0, 12, [3]))
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
