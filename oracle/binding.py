@@ -111,12 +111,18 @@ def cmvn(x, eps=1e-5):
 
 
 def stft(sig, n_fft, hop, win, window=None, power=False):
+    sig_in = sig
     sig = _f(sig).reshape(-1); L = sig.size
     frames = 1 if L < win else (L - win) // hop + 1
     nfr = n_fft // 2 + 1
     out = np.empty((frames, nfr) if power else (frames, nfr, 2), np.float32)
     w = None if window is None else _f(window)
     lib().lo_stft(_p(sig), C.c_int(L), C.c_int(n_fft), C.c_int(hop), C.c_int(win), _p(w), C.c_int(int(power)), _p(out))
+    lead = np.shape(sig_in)[:-1]
+    if len(lead) >= 1:   # math.rs:2362-2367: an input of rank >= 2 gets a leading batch dim; the data is still one flat signal
+        if int(np.prod(lead)) != 1:
+            raise ValueError("stft: batch > 1 gives a shape that does not match the data upstream (math.rs:2364)")
+        out = out.reshape((1,) + out.shape)
     return out
 
 

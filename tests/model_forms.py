@@ -221,3 +221,63 @@ def const_forms_direct(m, blob, x):
     s, c = R.sin(l), R.cos(l)
     lt = R.less(s, c)
     return R.where(lt, s, c), R.equal(R.not_(lt), lt)
+
+
+VH = 16   # hidden size of the synthetic streaming model (Silero: 128)
+
+
+def vad_text(chunk=512):
+    """A recurrent streaming model with Silero's calling convention (examples/silero/src/main.rs:121): (input [1, chunk], state [2,1,H],
+    sr [1] i64) -> (probability [1,1], new state [2,1,H]).  STFT power frames -> Conv1d+ReLU -> LSTM over the frames with the carried
+    (h, c) -> Gemm + Sigmoid on the last hidden state."""
+    H, nfr = VH, 33
+    o_cw = 0; o_cb = o_cw + 8 * nfr * 4; o_w = o_cb + 8 * 4; o_r = o_w + 4 * H * 8 * 4; o_b = o_r + 4 * H * H * 4; o_g = o_b + 8 * H * 4; o_gb = o_g + H * 4
+    return f"""
+pub struct SynthVadWorkspace {{ pub buf_0: Vec<f32>, pub buf_1: Vec<f32>, }}
+pub struct SynthVad<'a> {{ data: &'a [u8] }}
+    fn run_chunk_0<'w>(&self, ws: &'w mut SynthVadWorkspace, input: TensorView<'w, f32>, sr: TensorView<'w, i64>, state: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>) {{
+        let k = lele::tensor::TensorView::from_owned(vec![0.000030517578], vec![1]);
+        let sc = lele::kernels::mul(&input, &k, &mut ws.buf_0);
+        let sp = lele::kernels::stft(&sc, 64, 64, 64, None, &mut ws.buf_1);
+        let pw = lele::kernels::mul(&sp, &sp, &mut ws.buf_0);
+        let en = lele::kernels::reduce_sum(&pw, &[-1], false, &mut ws.buf_1);
+        let et = lele::kernels::transpose(&en, &[0, 2, 1], &mut ws.buf_0);
+        let cv = self.conv1d_relu(et, self.weight_f32({o_cw}, {8 * nfr * 4}, &[8, {nfr}, 1]), Some(&self.weight_f32({o_cb}, 32, &[8])), 1, 1, 1, 0, &mut ws.buf_1);
+        let ct = lele::kernels::transpose(&cv, &[2, 0, 1], &mut ws.buf_0);
+        let h0 = lele::kernels::slice(&state, &[0], &[1], &[0], &[1], &mut ws.buf_1);
+        let c0 = lele::kernels::slice(&state, &[1], &[2], &[0], &[1], &mut ws.buf_1);
+        let mut buf_y_h = Vec::<f32>::new();
+        let mut buf_y_c = Vec::<f32>::new();
+        let (y, yh, yc) = lele::kernels::lstm(&ct, &self.weight_f32({o_w}, {4 * H * 8 * 4}, &[1, {4 * H}, 8]), &self.weight_f32({o_r}, {4 * H * H * 4}, &[1, {4 * H}, {H}]), Some(&self.weight_f32({o_b}, {8 * H * 4}, &[1, {8 * H}])), None, Some(&h0), Some(&c0), &mut ws.buf_0, &mut buf_y_h, &mut buf_y_c);
+        let stateN = lele::kernels::concat(&[&yh, &yc], 0, &mut ws.buf_1);
+        let hf = lele::kernels::reshape(&yh, &[1, {H}]);
+        let lg = lele::kernels::gemm(&hf, &self.weight_f32({o_g}, {H * 4}, &[1, {H}]), Some(&self.weight_f32({o_gb}, 4, &[1])), 1.0, 1.0, false, true, &mut ws.buf_0);
+        let output = lele::kernels::sigmoid(&lg, &mut ws.buf_1);
+        (output.to_owned(), stateN.to_owned())
+    }}
+
+    pub fn forward_with_workspace<'w>(&self, ws: &'w mut SynthVadWorkspace, input: TensorView<'w>, state: TensorView<'w>, sr: TensorView<'w, i64>) -> (TensorView<'w>, TensorView<'w>) {{
+        let (output, stateN) = self.run_chunk_0(ws, input, sr, state);
+        (output, stateN)
+    }}
+}}
+"""
+
+
+def vad_model(m):
+    prog = m.parse_model_rs(vad_text())
+    return prog, m.synth_blob(prog, 21)
+
+
+def vad_chunk_direct(m, blob, chunk, state):
+    """The same chunk step written as direct oracle calls."""
+    H, nfr = VH, 33
+    o_cw = 0; o_cb = o_cw + 8 * nfr * 4; o_w = o_cb + 32; o_r = o_w + 4 * H * 8 * 4; o_b = o_r + 4 * H * H * 4; o_g = o_b + 8 * H * 4; o_gb = o_g + H * 4
+    W = lambda off, ln, shp: m.weight_view(blob, "weight_f32", off, ln, shp)
+    x = R.mul((chunk * np.float32(32768.0)).reshape(1, -1), np.array([0.000030517578], np.float32))
+    sp = R.stft(x, 64, 64, 64, None)
+    en = R.reduce(R.mul(sp, sp), [-1], False, "sum")
+    cv = R.conv1d(R.transpose(en, [0, 2, 1]), W(o_cw, 8 * nfr * 4, [8, nfr, 1]), W(o_cb, 32, [8]), [1], 1, [0, 0], [1], True)
+    y, yh, yc = R.lstm(R.transpose(cv, [2, 0, 1]), W(o_w, 4 * H * 8 * 4, [1, 4 * H, 8]), W(o_r, 4 * H * H * 4, [1, 4 * H, H]), W(o_b, 8 * H * 4, [1, 8 * H]), state[0:1], state[1:2])
+    prob = R.sigmoid(R.gemm(yh.reshape(1, H), W(o_g, H * 4, [1, H]), W(o_gb, 4, [1]).reshape(-1), 1.0, 1.0, False, True))
+    return float(prob.reshape(-1)[0]), np.concatenate([yh, yc], 0)

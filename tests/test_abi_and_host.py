@@ -304,6 +304,66 @@ pub struct T7<'a> { data: &'a [u8] }
     np.testing.assert_array_equal(c, b * m.weight_view(blob, "weight_f32", 0, 12, [3]))
 
 
+def test_vad_segment_logic_known_answers():
+    """Segment state machine and merge pass of examples/silero/src/main.rs:155-229, against hand-computed answers
+    (16 kHz, 512-sample chunks: min silence 3200, min speech 6400, pad 1920, merge gap 3200 samples)."""
+    from lele_b200.vad import VadConfig, collect_segments, merge_segments, ms_to_samples
+    assert [ms_to_samples(ms, 16000) for ms in (200.0, 400.0, 120.0)] == [3200, 6400, 1920]
+    assert ms_to_samples(0.03125, 16000) == 1 and ms_to_samples(0.03, 16000) == 0          # 0.5 rounds away from zero
+    assert ms_to_samples(120.0, 8000) == 960
+    hi, lo = 0.9, 0.1
+    # speech in chunks 10..29, then silence: released once 7 silent chunks (3584 >= 3200) have passed, at frame_end = 37 * 512
+    probs = [lo] * 10 + [hi] * 20 + [lo] * 20
+    n = 50 * 512 - 100
+    assert collect_segments(probs, n) == [(10 * 512 - 1920, 37 * 512 + 1920)]
+    # a burst shorter than min_speech is dropped: 3 chunks + 7 release chunks + pads = 1920 + 10*512 + 1920 = 8960 >= 6400 -> kept;
+    # with pad 0 it is 10 * 512 = 5120 < 6400 -> dropped
+    probs = [lo] * 5 + [hi] * 3 + [lo] * 30
+    assert collect_segments(probs, 38 * 512) == [(5 * 512 - 1920, 15 * 512 + 1920)]
+    assert collect_segments(probs, 38 * 512, config=VadConfig(speech_pad_ms=0.0)) == []
+    # the threshold is inclusive, a short dip (6 chunks < min silence) does not release, start saturates at 0
+    probs = [0.3] * 4 + [lo] * 6 + [0.3] * 10 + [lo] * 20
+    assert collect_segments(probs, 40 * 512) == [(0, 27 * 512 + 1920)]
+    # still triggered at the end of the clip: the segment ends at the unpadded length; the release pad is clamped to it too
+    probs = [lo] * 5 + [hi] * 20
+    assert collect_segments(probs, 25 * 512 - 7) == [(5 * 512 - 1920, 25 * 512 - 7)]
+    probs = [lo] * 3 + [hi] * 20 + [lo] * 7
+    assert collect_segments(probs, 30 * 512 - 300) == [(0, 30 * 512 - 300)]            # 3 * 512 - 1920 saturates at 0
+    # merge: overlap, gap <= 3200 joined, larger gap kept apart, input order irrelevant
+    assert merge_segments([(20000, 30000), (0, 10000), (9000, 12000), (15200, 16000), (40000, 41000)]) == [(0, 16000), (20000, 30000), (40000, 41000)]
+    assert merge_segments([(0, 10), (3211, 3300)]) == [(0, 10), (3211, 3300)] and merge_segments([(0, 10), (3210, 3300)]) == [(0, 3300)]
+    assert merge_segments([]) == []
+
+
+def test_streaming_vad_carries_state_across_chunks():
+    """StreamingVad over a replayed recurrent model (synthetic weights, Silero's calling convention): chunk loop, x32768 scaling, zero
+    padding of the last chunk and the (h, c) hand-over, against the same steps written as direct oracle calls."""
+    from lele_b200 import model_rs as MR
+    from lele_b200.vad import StreamingVad
+    from tests import model_forms as MF
+    prog, blob = MF.vad_model(MR)
+    assert prog["inputs"] == ["input", "state", "sr"] and prog["outputs"] == ["output", "stateN"]
+    rng = np.random.default_rng(33)
+    audio = (0.1 * rng.standard_normal(512 * 3 + 200)).astype(np.float32)
+    vad = StreamingVad(prog, blob, ops=MF.R, state_shape=(2, 1, MF.VH))
+    probs = vad.process(audio)
+    assert probs.shape == (4,) and np.all((probs > 0) & (probs < 1))
+    padded = np.zeros(4 * 512, np.float32); padded[:audio.size] = audio
+    state = np.zeros((2, 1, MF.VH), np.float32); want = []
+    for i in range(4):
+        p, state = MF.vad_chunk_direct(MR, blob, padded[i * 512:(i + 1) * 512], state)
+        want.append(p)
+    np.testing.assert_array_equal(probs, np.asarray(want, np.float32))
+    np.testing.assert_array_equal(vad.state, state)
+    assert len(set(np.round(probs, 6))) > 1                        # the state matters: chunks are not scored independently
+    fresh = StreamingVad(prog, blob, ops=MF.R, state_shape=(2, 1, MF.VH))
+    assert fresh.push(padded[512:1024]) != probs[1]
+    with pytest.raises(ValueError, match="expected 512"):
+        vad.push(np.zeros(100, np.float32))
+    segs = vad.segments(audio)
+    assert isinstance(segs, list) and len(vad.probs) == 4          # segments() restarts the stream
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""

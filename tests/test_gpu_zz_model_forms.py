@@ -42,3 +42,21 @@ def test_statement_forms_lockstep(case):
     for a, b in zip(got, direct(MR, blob, x)):
         np.testing.assert_array_equal(a, b)           # the carried values are the oracle's
     assert len(ops.calls) >= {"math": 10, "recurrent": 3, "quant": 8, "shape": 6, "const": 10}[case]
+
+
+def test_streaming_vad_on_device():
+    """the Silero-style chunk loop (x32768, carried (h, c) state) over a replayed recurrent model -- first in
+    lock-step with the oracle per statement, then free-running on the C ABI against the oracle's own stream."""
+    from lele_b200 import model_rs as MR
+    from lele_b200.vad import StreamingVad
+    prog, blob = MF.vad_model(MR)
+    audio = (0.1 * np.random.default_rng(33).standard_normal(512 * 3 + 200)).astype(np.float32)
+    ops = Lockstep(MR)
+    locked = StreamingVad(prog, blob, ops=ops, state_shape=(2, 1, MF.VH)).process(audio)
+    assert locked.shape == (4,) and len(ops.calls) == 4 * 13
+    ref = StreamingVad(prog, blob, ops=MF.R, state_shape=(2, 1, MF.VH)).process(audio)
+    np.testing.assert_array_equal(locked, ref)
+    free = StreamingVad(prog, blob, state_shape=(2, 1, MF.VH))            # default operator namespace: CudaOps
+    np.testing.assert_allclose(free.process(audio), ref, rtol=1e-3, atol=1e-4)
+    cpu = StreamingVad(prog, blob, ops=MF.R, state_shape=(2, 1, MF.VH)); cpu.process(audio)
+    np.testing.assert_allclose(free.state, cpu.state, rtol=1e-3, atol=1e-4)
