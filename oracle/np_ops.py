@@ -109,6 +109,11 @@ def tile(x, repeats):  # math.rs:2249-2300
     return np.tile(_a(x), tuple(int(r) for r in repeats))
 
 
+def flatten(x, axis=1):  # shape.rs:105-120
+    x = _a(x); axis = axis + x.ndim if axis < 0 else axis
+    return x.reshape(int(np.prod(x.shape[:axis], dtype=np.int64)), int(np.prod(x.shape[axis:], dtype=np.int64)))
+
+
 def reshape(x, shape):  # shape.rs:2-93 (0 = copy dim, -1 = infer)
     x = _a(x)
     shp = [x.shape[i] if (s == 0 and i < x.ndim) else int(s) for i, s in enumerate(shape)]

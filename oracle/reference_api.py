@@ -54,6 +54,7 @@ where = N.where_op
 expand = N.expand
 tile = N.tile
 reshape = N.reshape
+flatten = N.flatten
 topk = N.topk
 gather_elements = N.gather_elements
 resize_nearest = N.resize_nearest

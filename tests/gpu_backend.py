@@ -78,6 +78,7 @@ topk = lambda x, k: K.topk(x, k)
 gather_elements = K.gather_elements
 add, sub, mul, div = K.add, K.sub, K.mul, K.div
 maximum, neg, sqrt, reciprocal, clip, mod_f32, prelu = K.max, K.neg, K.sqrt, K.reciprocal, K.clip, K.mod_f32, K.prelu
+pow, log, sin, cos, equal, less, not_, flatten = K.pow, K.log, K.sin, K.cos, K.equal, K.less, K.not_, K.flatten  # noqa: A001
 
 
 def resize_nearest(x, scales=None, sizes=None, mode="asymmetric"):
