@@ -113,26 +113,31 @@ def _num(t: str):
     return float(t) if any(c in t for c in ".eE") and not t.lstrip("-").isdigit() else int(t)
 
 
-def parse_model_rs(text: str) -> dict:
-    """-> {"class", "workspace_buffers", "inputs": [names], "statements": [{"outs", "op", "args"}], "outputs": [names]}"""
-    text = text.replace(".data.iter().map(|&v| v as i64).collect::<Vec<_>>()", ".as_i64_vec()")
-    cls = re.search(r"pub struct (\w+)<'a>", text)
-    n_bufs = len(re.findall(r"pub buf_\d+: Vec<f32>", text))
-    stmts, inputs, outputs = [], None, None
-    in_chunk, splits, split_src, skip_next = False, None, None, False
-    for raw in text.splitlines():
-        line = raw.strip()
-        m = re.match(r"fn run_chunk_\d+<'w>\(&self, ws: [^,]+, (.*)\) -> ", line)
-        if m:
-            in_chunk = True
-            names = re.findall(r"(\w+): TensorView", m.group(1))
-            inputs = names if inputs is None else inputs
-            continue
-        if not in_chunk:
-            continue
-        if line == "}":
-            in_chunk = False
-            continue
+_IF = re.compile(r"^let \(([\w, ]*)\) = if (\w+)\.data\.get\(0\)\.map\(\|v\| \*v != 0(?:\.0)?\)\.unwrap_or\(false\) \{$")
+
+
+def _parse_tail(expr: str):
+    """`(a.to_owned(), self.weight(0, 4, &[1]).to_owned())` or `a.to_owned()` -> [arg]: tensor names or stored tensors."""
+    expr = expr.strip()
+    items = _split_top(expr[1:-1]) if expr.startswith("(") else [expr]
+    out = []
+    for it in items:
+        it = re.sub(r"\.to_owned\(\)$", "", it.strip())
+        it = re.sub(r"^self\.weight\(", "self.weight_f32(", it)            # control_flow.rs:84 names the f32 loader `weight`
+        out.append(_parse_arg(it))
+    return out
+
+
+def _parse_block(lines, i):
+    """Statements from lines[i] up to the line that closes the block (`}`, `} else {` or `};`).  Returns (statements, tail, index of
+    the closing line); `tail` = the block's value expression as a list of args, or None."""
+    stmts, tail = [], None
+    splits, split_src, skip_next = None, None, False
+    while i < len(lines):
+        line = lines[i]
+        if line in ("}", "} else {", "};"):
+            return stmts, tail, i
+        i += 1
         if line.startswith("//") or not line:
             continue
         if line == '#[cfg(target_arch = "aarch64")]':          # the pre-packed NEON arm of a statement pair (patterns.rs:383, ops/math.rs:60):
@@ -143,9 +148,23 @@ def parse_model_rs(text: str) -> dict:
         if skip_next:
             skip_next = False
             continue
-        m = re.match(r"^\((.*)\)$", line) or re.match(r"^(\w+\.to_owned\(\))$", line)   # tail expression: (a.to_owned(), b.to_owned()) or a.to_owned()
+        m = _IF.match(line)                                      # ONNX If (ops/control_flow.rs:17-152): both branches are blocks with a tail
         if m:
-            outputs = [p.strip().replace(".to_owned()", "") for p in _split_top(m.group(1))]
+            then_s, then_t, i = _parse_block(lines, i)
+            if lines[i] != "} else {":
+                raise ValueError("model.rs: malformed if / else block")
+            else_s, else_t, i = _parse_block(lines, i + 1)
+            if lines[i] != "};":
+                raise ValueError("model.rs: malformed if / else block")
+            i += 1
+            outs = [o.strip() for o in m.group(1).split(",") if o.strip()]
+            if then_t is None or else_t is None or len(then_t) != len(outs) or len(else_t) != len(outs):
+                raise ValueError("model.rs: if / else branches must yield one value per output")
+            stmts.append({"outs": outs, "op": "if", "args": [{"var": m.group(2)}],
+                          "then": {"statements": then_s, "outputs": then_t}, "else": {"statements": else_s, "outputs": else_t}})
+            continue
+        if re.match(r"^\(.*\)$", line) or re.match(r"^\w+\.to_owned\(\)$", line):   # tail expression: (a.to_owned(), b.to_owned()) or a.to_owned()
+            tail = _parse_tail(line)
             continue
         m = re.match(r"^let splits_slice = &\[(.*)\];$", line)
         if m:
@@ -195,6 +214,32 @@ def parse_model_rs(text: str) -> dict:
             stmts.append({"outs": outs, "op": m.group(2), "args": args})
             continue
         raise ValueError(f"model.rs: unsupported statement: {line[:160]}")
+    raise ValueError("model.rs: unterminated block")
+
+
+def parse_model_rs(text: str) -> dict:
+    """-> {"class", "workspace_buffers", "inputs": [names], "statements": [{"outs", "op", "args"}], "outputs": [names]}
+    (an `if` statement carries its two branches as nested {"statements", "outputs"} blocks)."""
+    text = text.replace(".data.iter().map(|&v| v as i64).collect::<Vec<_>>()", ".as_i64_vec()")
+    cls = re.search(r"pub struct (\w+)<'a>", text)
+    n_bufs = len(re.findall(r"pub buf_\d+: Vec<f32>", text))
+    lines = [raw.strip() for raw in text.splitlines()]
+    stmts, inputs, outputs, i = [], None, None, 0
+    while i < len(lines):
+        m = re.match(r"fn run_chunk_\d+<'w>\(&self, ws: [^,]+, (.*)\) -> ", lines[i])
+        i += 1
+        if not m:
+            continue
+        if inputs is None:
+            inputs = re.findall(r"(\w+): TensorView", m.group(1))
+        body, tail, i = _parse_block(lines, i)
+        if lines[i] != "}":
+            raise ValueError("model.rs: malformed run_chunk body")
+        stmts += body
+        if tail is not None:
+            if not all(isinstance(t, dict) and "var" in t for t in tail):
+                raise ValueError("model.rs: a chunk returns tensors by name (generate.rs:772)")
+            outputs = [t["var"] for t in tail]
     if inputs is None or outputs is None:
         raise ValueError("model.rs: no run_chunk body found")
     # A model split into several run_chunk_N functions shares one set of tensor names (generate.rs:704-790), so the statement list
@@ -379,7 +424,20 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
             if "str" in a: return a["str"]
         return a
 
-    for st in program["statements"]:
+    def exec_block(statements):
+        for st in statements:
+            exec_statement(st)
+
+    def exec_statement(st):
+        if st["op"] == "if":                          # ops/control_flow.rs:41: the first element of the condition decides; names are
+            cond = np.asarray(env[st["args"][0]["var"]]).reshape(-1)   # graph-wide, so the taken branch runs in the same environment
+            branch = st["then"] if (cond.size and cond[0] != 0) else st["else"]
+            exec_block(branch["statements"])
+            for n, o in zip(st["outs"], branch["outputs"]):
+                env[n] = val(o)
+            if trace is not None:
+                trace.append((st["outs"][0] if st["outs"] else "", "if", env[st["outs"][0]] if st["outs"] else None))
+            return
         op, a = st["op"], [val(x) for x in st["args"]]
         r = _host_i64_op(op, a)
         if r is not None:
@@ -435,6 +493,12 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
             r = ops.clip(a[0], lim[0], lim[1])
         elif op == "batch_norm":                      # (x, scale, bias, mean, var, epsilon)  ops/nn.rs:352
             r = ops.batch_norm(a[0], a[1], a[2], a[3], a[4], a[5])
+        elif op in ("self.embedding_concat", "self.embedding_concat_i64"):   # (shape, value, weight)  default_methods.rs:182-232: ConstantOfShape + Concat
+            shp = _to_i64_list(a[0]); w = np.asarray(a[2])          # on axis 0 as one flat append: a table with a constant tail, built on the host
+            if op.endswith("_i64"):
+                w = w.astype(np.int64)
+            tail = np.full(int(np.prod(shp, dtype=np.int64)) if shp else 1, a[1], w.dtype)
+            r = np.concatenate([w.reshape(-1), tail]).reshape((w.shape[0] + (shp[0] if shp else 1),) + tuple(w.shape[1:]))
         elif op == "matmul_fused_add":
             r = ops.matmul_fused_add(a[0], a[1], a[2])
         elif op in ("conv1d", "conv1d_fused"):        # same argument form as conv2d (ops/nn.rs:57); _fused appends the ReLU flag
@@ -501,6 +565,8 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
                     env[n] = v
         if trace is not None:
             trace.append((st["outs"][0], op, env[st["outs"][0]]))
+
+    exec_block(program["statements"])
     return [env[n] for n in program["outputs"]]
 
 
@@ -509,7 +575,16 @@ def synth_blob(program: dict, seed: int = 7, constants=None) -> bytes:
     convolution / matmul weights ~ N(0, 1/sqrt(fan_in)), biases ~ N(0, 0.1), every other f32 view ~ N(0, 1);
     `constants` = {offset: array} overrides (shape constants, anchors, k ...), written with the view's own dtype."""
     size, views = 0, {}
-    for st in program["statements"]:
+
+    def walk(statements):
+        for st in statements:
+            yield st
+            for br in ("then", "else"):
+                if br in st:
+                    yield from walk(st[br]["statements"])
+                    yield {"op": "tail", "args": list(st[br]["outputs"])}
+
+    for st in walk(program["statements"]):
         flat = [(i, a) for i, a in enumerate(st["args"])] + [(i, b) for i, a in enumerate(st["args"]) if isinstance(a, dict) for b in (a.get("items", []) + ([a["i64vec_of"]] if "i64vec_of" in a else []))]
         for i, a in flat:
             if isinstance(a, dict):

@@ -364,6 +364,57 @@ def test_streaming_vad_carries_state_across_chunks():
     assert isinstance(segs, list) and len(vad.probs) == 4          # segments() restarts the stream
 
 
+def test_model_rs_if_blocks_and_embedding_concat():
+    """ONNX If as emitted by ops/control_flow.rs (Silero's sample-rate switch is one): the first element of the condition picks the
+    branch, branches may nest and may yield stored tensors (`self.weight(...)`); plus the ConstantOfShape + Concat helper."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    text = """
+pub struct T8Workspace { pub buf_0: Vec<f32>, pub buf_1: Vec<f32>, }
+pub struct T8<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut T8Workspace, sr: TensorView<'w, i64>, x: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>, TensorView<'static, f32>) {
+        let mut buf_is16 = Vec::<i64>::new();
+        let is16 = lele::kernels::equal_i64(&sr, &self.weight_i64(0, 8, &[]), &mut buf_is16);
+        let (y, z) = if is16.data.get(0).map(|v| *v != 0).unwrap_or(false) {
+            let a = lele::kernels::mul(&x, &self.weight_f32(8, 4, &[1]), &mut ws.buf_0);
+            let (p) = if a.data.get(0).map(|v| *v != 0.0).unwrap_or(false) {
+                let q = lele::kernels::relu(&a, &mut ws.buf_1);
+                (q.to_owned())
+            } else {
+                (a.to_owned())
+            };
+            (p.to_owned(), self.weight(12, 12, &[3]).to_owned())
+        } else {
+            let b = lele::kernels::neg(&x, &mut ws.buf_0);
+            (b.to_owned(), x.to_owned())
+        };
+        let e = self.embedding_concat(&self.weight_i64(24, 16, &[2]), 0.5, self.weight_f32(40, 24, &[2, 3]), &mut ws.buf_1);
+        (y.to_owned(), z.to_owned(), e.to_owned())
+    }
+
+    pub fn forward_with_workspace<'w>(&self, ws: &'w mut T8Workspace, x: TensorView<'w>, sr: TensorView<'w, i64>) -> (TensorView<'w>, TensorView<'w>, TensorView<'w>) {
+        let (y, z, e) = self.run_chunk_0(ws, sr, x);
+        (y, z, e)
+    }
+}
+"""
+    prog = m.parse_model_rs(text)
+    st_if = prog["statements"][1]
+    assert st_if["op"] == "if" and st_if["outs"] == ["y", "z"] and st_if["then"]["statements"][1]["op"] == "if"
+    assert st_if["then"]["outputs"][1] == {"weight": ["weight_f32", 12, 12, [3]]}
+    blob = m.synth_blob(prog, 2, {0: [16000], 8: [2.0], 12: [7.0, 8.0, 9.0], 24: [1, 3], 40: [1, 2, 3, 4, 5, 6]})
+    x = np.array([-1.0, 2.0, -3.0], np.float32)
+    y, z, e = m.run_program(prog, blob, [x, np.array([16000], np.int64)], MF.R)
+    np.testing.assert_array_equal(y, [0.0, 4.0, 0.0]); np.testing.assert_array_equal(z, [7.0, 8.0, 9.0])       # then / then
+    np.testing.assert_array_equal(e, [[1, 2, 3], [4, 5, 6], [0.5, 0.5, 0.5]])
+    y, z, _ = m.run_program(prog, blob, [np.array([0.0, 2.0, -3.0], np.float32), np.array([16000], np.int64)], MF.R)
+    np.testing.assert_array_equal(y, [0.0, 4.0, -6.0])                                                           # then / else (a[0] == 0)
+    y, z, _ = m.run_program(prog, blob, [x, np.array([8000], np.int64)], MF.R)
+    np.testing.assert_array_equal(y, [1.0, -2.0, 3.0]); np.testing.assert_array_equal(z, x)                      # else
+    with pytest.raises(ValueError, match="one value per output"):
+        m.parse_model_rs(text.replace("(b.to_owned(), x.to_owned())", "(b.to_owned())"))
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
