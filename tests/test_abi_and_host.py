@@ -35,6 +35,32 @@ def test_header_symbols_exported(so_path):
     assert exported == set(names), (sorted(exported - set(names)), sorted(set(names) - exported))   # nothing undeclared leaks either
 
 
+def test_rust_ffi_matches_header():
+    """bindings/rust/cuda_ffi.rs (the reference-side binding) is generated from include/lele_b200.h:
+    the committed file must be what the generator produces now, with one declaration per symbol, the same argument count, and
+    `*const` exactly where the C prototype says `const`."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    header = open(os.path.join(ROOT, "include", "lele_b200.h")).read()
+    committed = open(os.path.join(ROOT, "bindings", "rust", "cuda_ffi.rs")).read()
+    assert committed == g.generate(header), "run python tools/gen_rust_ffi.py"
+    decls = {name: (ret, args) for ret, name, args in g.c_declarations(header)}
+    assert sorted(decls) == declared_symbols()
+    rust = dict(re.findall(r"pub fn (lele_b200_\w+)\((.*)\) -> ", committed))
+    assert sorted(rust) == sorted(decls)
+    for name, (ret, args) in decls.items():
+        rargs = [a for a in rust[name].split(", ") if a]
+        assert len(rargs) == len(args), name
+        for (ctype, _), ra in zip(args, rargs):
+            assert ctype.count("*") == ra.count("*"), (name, ctype, ra)
+            if "*" in ctype:                                   # the pointee's constness is the innermost Rust pointer's
+                innermost = ra.split(": ")[1].split(" ")[-2]
+                assert innermost == ("*const" if ctype.startswith("const ") else "*mut"), (name, ctype, ra)
+    assert g.rust_type("const float* const*") == "*const *const f32" and g.rust_type("lele_b200_ctx**") == "*mut *mut Ctx"
+    assert g.rust_type("const int32_t*") == "*const i32" and g.rust_type("size_t") == "usize" and g.rust_type("unsigned long long") == "c_ulonglong"
+
+
 def test_host_only_entry_points(so_path):
     """hann_window / mel_filterbank / frame counting are host functions of the ABI: callable without a GPU
     and identical to the oracle (same f32 libm arithmetic as the reference)."""
