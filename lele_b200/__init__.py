@@ -8,6 +8,7 @@ Package layout (only what the hot path needs):
   sensevoice_weights.py synthetic weights blob + synthetic PCM (numpy only, no CUDA)
   tokenizer.py          examples/sensevoice tokenizer + on-device greedy-decode filter
   model_rs.py           parses a lele_gen-generated model.rs and replays it over the C ABI
+  e2e.py                the reference's e2e golden checks (examples/*/tests/e2e_test.rs) over the replay; SKIP while files are missing
   vad.py                streaming VAD caller (examples/silero): chunk loop with carried state, segment logic
 
 Importing the package loads liblele_b200.so and raises if it is missing: there is no CPU

@@ -1,6 +1,7 @@
 """Runs a `lele_gen`-generated `model.rs` on the B200 back-end without a Rust toolchain.
 
-The AOT compiler emits every model as a straight-line list of `lele::kernels::<op>(...)` calls whose weights are
+The AOT compiler emits every model as a list of `lele::kernels::<op>(...)` calls (straight-line except for ONNX `If` blocks,
+spread over one or more `run_chunk_N` functions) whose weights are
 `(offset, len, shape)` views into one `weights.bin` blob (src/compiler/mod.rs:1053-1092, :1381-1505; a committed
 sample is examples/yolo26n-seg/src/yolo26seg.rs).  `parse_model_rs` turns such a file into a small JSON-able
 "program" (statement list + weight literals); `run_program` replays it against an operator namespace -- by default
@@ -8,7 +9,9 @@ the CUDA product (`lele_b200.kernels` over the C ABI), in tests also the CPU ora
 drop-in: same operator names, argument order and `weights.bin` layout.
 
 Only the statement forms the code generator emits are understood (src/compiler/generate.rs:802-997,
-src/compiler/ops/*.rs); anything else raises.
+src/compiler/ops/*.rs, patterns.rs, snippets/default_methods.rs; table in INTEGRATION.md); anything else raises.  Tensor work
+goes to the operator namespace; i64 shape arithmetic (Shape / Gather / Concat / Range ... on a handful of elements) is
+evaluated on the host, as upstream.
 """
 from __future__ import annotations
 

@@ -441,6 +441,60 @@ pub struct T8<'a> { data: &'a [u8] }
         m.parse_model_rs(text.replace("(b.to_owned(), x.to_owned())", "(b.to_owned())"))
 
 
+def test_e2e_golden_checks_skip_and_compare(tmp_path):
+    """lele_b200.e2e mirrors examples/*/tests/e2e_test.rs: SKIP (None) while a weights / .npy file is missing, the reference's
+    tolerances once they exist.  The goldens here are synthetic (written by the oracle replay, then perturbed)."""
+    from lele_b200 import e2e, model_rs as MR
+    from tests import model_forms as MF
+    d = str(tmp_path)
+    # --- silero-shaped
+    prog, blob = MF.vad_model(MR)
+    open(os.path.join(d, "silerovad.rs"), "w").write(MF.vad_text()); open(os.path.join(d, "silerovad_weights.bin"), "wb").write(blob)
+    args = (os.path.join(d, "silerovad.rs"), os.path.join(d, "silerovad_weights.bin"), [os.path.join(d, "missing"), d])
+    assert e2e.check_silero(*args, ops=MF.R) is None                                       # fixtures absent -> SKIP
+    x = (1000 * np.random.default_rng(4).standard_normal((1, 512))).astype(np.float32); st = np.zeros((2, 1, MF.VH), np.float32)
+    out, st_out = MR.run_program(prog, blob, [x, st, np.array([16000], np.int64)], MF.R)
+    for n, v in (("silero_input", x), ("silero_state_in", st), ("silero_sr", np.array([16000], np.int64)), ("silero_output", out + 5e-5), ("silero_state_out", st_out)):
+        np.save(os.path.join(d, n + ".npy"), v)
+    rep = e2e.check_silero(*args, ops=MF.R)
+    assert rep["output_diff"] < 1e-4 and rep["state_max_diff"] == 0.0
+    np.save(os.path.join(d, "silero_output.npy"), out + 1e-3)
+    with pytest.raises(AssertionError, match="silero output diff"):
+        e2e.check_silero(*args, ops=MF.R)
+    # --- sensevoice-shaped: logits MAE <= 1.0 and at least one arg-max frame in common
+    text = """
+pub struct SvWorkspace { pub buf_0: Vec<f32>, }
+pub struct Sv<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut SvWorkspace, x: TensorView<'w, f32>) -> TensorView<'static, f32> {
+        let logits = lele::kernels::matmul(&x, &self.weight_f32(0, 15680, &[560, 7]), &mut ws.buf_0);
+        logits.to_owned()
+    }
+
+    pub fn forward_with_workspace<'w>(&self, ws: &'w mut SvWorkspace, x: TensorView<'w>, x_length: TensorView<'w, i64>, language: TensorView<'w, i64>, text_norm: TensorView<'w, i64>) -> TensorView<'w> {
+        let (logits) = self.run_chunk_0(ws, x);
+        logits
+    }
+}
+"""
+    prog = MR.parse_model_rs(text); blob = MR.synth_blob(prog, 3)
+    assert prog["inputs"] == ["x", "x_length", "language", "text_norm"] and prog["outputs"] == ["logits"]
+    open(os.path.join(d, "sensevoice.rs"), "w").write(text); open(os.path.join(d, "sensevoice_weights.bin"), "wb").write(blob)
+    x = np.random.default_rng(5).standard_normal((1, 10, 560)).astype(np.float32)
+    logits = MR.run_program(prog, blob, [x, np.array([10]), np.array([0]), np.array([15])], MF.R)[0]
+    np.save(os.path.join(d, "sensevoice_input_x.npy"), x)
+    for n, v in (("x_length", 10), ("language", 0), ("text_norm", 15)):
+        np.save(os.path.join(d, f"sensevoice_input_{n}.npy"), np.array([v], np.int32))
+    args = (os.path.join(d, "sensevoice.rs"), os.path.join(d, "sensevoice_weights.bin"), [d])
+    assert e2e.check_sensevoice(*args, ops=MF.R, vocab=7) is None                          # logits golden still missing
+    np.save(os.path.join(d, "sensevoice_logits.npy"), logits + 0.25)
+    rep = e2e.check_sensevoice(*args, ops=MF.R, vocab=7)
+    assert abs(rep["mae"] - 0.25) < 1e-4 and rep["argmax_match"] == rep["frames"] == 10
+    np.save(os.path.join(d, "sensevoice_logits.npy"), logits + 1.5)
+    with pytest.raises(AssertionError, match="mae"):
+        e2e.check_sensevoice(*args, ops=MF.R, vocab=7)
+    assert e2e.check_yolo26(os.path.join(d, "yolo26.rs"), os.path.join(d, "yolo26_weights.bin"), [d]) is None
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
