@@ -10,6 +10,16 @@ pytestmark = pytest.mark.gpu
 from tests import model_forms as MF            # noqa: E402
 from tests.test_gpu_parity import close        # noqa: E402
 
+from tests import gpu_backend as G                       # noqa: E402
+from tests.kat_runner import KATS, kat_id, run_kat      # noqa: E402
+
+
+@pytest.mark.parametrize("k", [k for k in KATS if "checks" in k], ids=kat_id)
+def test_reference_kat_on_gpu_second_batch(k):
+    """The KATs transcribed after the round's last GPU run (tests/golden/make_reference_kats.py, `kat2` entries)."""
+    run_kat(G, k)
+
+
 EXACT = {"dynamic_quantize_linear", "mat_mul_integer", "fused_quantized_linear", "pad", "expand", "where", "concat", "transpose", "slice", "less", "equal", "not"}
 
 
