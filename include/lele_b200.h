@@ -55,7 +55,7 @@ int lele_b200_d2d(lele_b200_ctx* ctx, void* dst_dev, const void* src_dev, size_t
 int lele_b200_arena_bind(lele_b200_ctx* ctx, const void* host_base, size_t nbytes, void** dptr);
 int lele_b200_arena_release(lele_b200_ctx* ctx, const void* host_base);
 
-/* ---- lele::features (src/features/*.rs) ---- */
+/* ---- lele::features (src/features/ *.rs) ---- */
 int lele_b200_hann_window(int size, float* out_host);                          /* window.rs:2 */
 int lele_b200_mel_filterbank(float sample_rate, int n_fft, int n_mels, float f_min, float f_max,
                              float* out_host /*[n_mels, n_fft/2+1]*/);           /* mel.rs:7 */

@@ -35,6 +35,21 @@ def test_header_symbols_exported(so_path):
     assert exported == set(names), (sorted(exported - set(names)), sorted(set(names) - exported))   # nothing undeclared leaks either
 
 
+def test_header_is_strict_c99_and_c_example_runs(so_path, tmp_path):
+    """The boundary is a C ABI: include/lele_b200.h must compile as pedantic C99 (no C++-isms), and examples/c/abi_tour.c -- a plain
+    C caller -- must build against it, link the library, run its host-only part, and stop cleanly at the device check on a CPU box."""
+    exe = str(tmp_path / "abi_tour")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c", "abi_tour.c"), "-L", os.path.dirname(so_path), "-llele_b200", "-lm",
+           "-Wl,-rpath," + os.path.dirname(so_path), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.stdout, run.stderr)
+    assert "hann(4) = 0.00 0.75 0.75 0.00" in run.stdout and "1598 frames -> 267 LFR rows" in run.stdout
+    assert ("no CUDA device" in run.stdout) or ("layer_norm([1,2,3]) = -1.2247" in run.stdout)
+
+
 def test_rust_ffi_matches_header():
     """bindings/rust/cuda_ffi.rs (the reference-side binding) is generated from include/lele_b200.h:
     the committed file must be what the generator produces now, with one declaration per symbol, the same argument count, and

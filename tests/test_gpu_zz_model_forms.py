@@ -70,3 +70,20 @@ def test_streaming_vad_on_device():
     np.testing.assert_allclose(free.process(audio), ref, rtol=1e-3, atol=1e-4)
     cpu = StreamingVad(prog, blob, ops=MF.R, state_shape=(2, 1, MF.VH)); cpu.process(audio)
     np.testing.assert_allclose(free.state, cpu.state, rtol=1e-3, atol=1e-4)
+
+
+def test_c_caller_runs_an_operator(tmp_path):
+    """examples/c/abi_tour.c: a plain C99 program drives layer_norm through the explicit-copy entry points and checks the reference's
+    known answer (tests/verify_operators.rs:34)."""
+    import os
+    import subprocess
+    from lele_b200 import SO_PATH
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_tour")
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c", "abi_tour.c"),
+                    "-L", os.path.dirname(SO_PATH), "-llele_b200", "-lm", "-Wl,-rpath," + os.path.dirname(SO_PATH), "-o", exe], check=True)
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, (run.stdout, run.stderr)
+    import re
+    assert "layer_norm([1,2,3]) = -1.2247" in run.stdout
+    assert int(re.search(r"kernel launches issued by this context: (\d+)", run.stdout).group(1)) >= 1
