@@ -50,6 +50,29 @@ def test_header_is_strict_c99_and_c_example_runs(so_path, tmp_path):
     assert ("no CUDA device" in run.stdout) or ("layer_norm([1,2,3]) = -1.2247" in run.stdout)
 
 
+def test_library_sass_is_blackwell_native(so_path):
+    """What B200_PROFILING.md calls the proof of a Blackwell-native kernel, checked on the built library: tcgen05.mma (UTCIMMA for the
+    int8 GEMM, UTCHMMA for the 3xTF32 attention / f32 GEMM), tensor-memory loads, TMA loads and stores -- and no legacy mma.sync."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", so_path], capture_output=True, text=True, timeout=600).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1); per_kernel[cur] = set()
+        elif cur:
+            m = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+            if m:
+                per_kernel[cur].add(m.group(1))
+    find = lambda part: [ops for k, ops in per_kernel.items() if part in k]
+    assert find("gemm_i8_tc_kernel") and all({"UTCIMMA", "LDTM", "UTMALDG", "UTCBAR"} <= ops for ops in find("gemm_i8_tc_kernel"))
+    assert all({"UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG"} <= ops for ops in find("attn_tc_kernel")) and find("attn_tc_kernel")
+    assert all({"UTCHMMA", "LDTM"} <= ops for ops in find("gemm_tf32x3_nt_kernel")) and len(find("gemm_tf32x3_nt_kernel")) == 3
+    assert not any({"HMMA", "IMMA", "HGMMA", "IGMMA"} & ops for ops in per_kernel.values())
+
+
 def test_rust_ffi_matches_header():
     """bindings/rust/cuda_ffi.rs (the reference-side binding) is generated from include/lele_b200.h:
     the committed file must be what the generator produces now, with one declaration per symbol, the same argument count, and
