@@ -458,6 +458,16 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
         elif op in ("conv2d", "conv2d_silu", "conv2d_fused"):
             act = 2 if op == "conv2d_silu" else (1 if (op == "conv2d_fused" and a[7]) else 0)
             r = ops.conv2d(a[0], a[1], a[2], a[3], a[4], a[5], a[6], act)
+        elif op == "conv_integer":                    # (x, w, x_zero_point, w_zero_point, dilations, group, pads, strides)  ops/nn.rs:328
+            # conv2d.rs:1507-2000: an f32 convolution of (x - x_zp) with (w - w_zp); the im2col pads with RAW zeros, so a padded
+            # position contributes (0 - x_zp) (conv2d.rs:2025) -- hence pad first, shift second, convolve without padding
+            xz, wz = (0.0 if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z in (a[2], a[3]))
+            p4 = list(a[6]) if len(a[6]) >= 4 else (list(a[6]) * 2 if len(a[6]) == 2 else [0, 0, 0, 0])
+            x = ops.pad(a[0], [0, 0, p4[0], p4[1], 0, 0, p4[2], p4[3]], 0.0, "constant") if any(p4) else a[0]
+            if xz != 0.0:
+                x = ops.binary("sub", x, np.array([xz], np.float32))
+            w = np.asarray(a[1], np.float32) - np.float32(wz)
+            r = ops.conv2d(x, w, None, a[4], a[5], [0, 0, 0, 0], a[7], 0)
         elif op == "conv_transpose":
             if a[4] != 1:
                 raise ValueError("ConvTranspose: group > 1 not supported yet (conv2d.rs:3042)")

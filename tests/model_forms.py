@@ -281,3 +281,36 @@ def vad_chunk_direct(m, blob, chunk, state):
     y, yh, yc = R.lstm(R.transpose(cv, [2, 0, 1]), W(o_w, 4 * H * 8 * 4, [1, 4 * H, 8]), W(o_r, 4 * H * H * 4, [1, 4 * H, H]), W(o_b, 8 * H * 4, [1, 8 * H]), state[0:1], state[1:2])
     prob = R.sigmoid(R.gemm(yh.reshape(1, H), W(o_g, H * 4, [1, H]), W(o_gb, 4, [1]).reshape(-1), 1.0, 1.0, False, True))
     return float(prob.reshape(-1)[0]), np.concatenate([yh, yc], 0)
+
+
+CONVINT_TEXT = """
+pub struct T9Workspace { pub buf_0: Vec<f32>, }
+pub struct T9<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut T9Workspace, q: TensorView<'w, f32>, qz: TensorView<'w, f32>) -> TensorView<'static, f32> {
+        let y = lele::kernels::conv_integer(&q, &self.weight_u8(0, 54, &[3, 2, 3, 3]), Some(&qz), Some(&self.weight_u8(54, 1, &[])), &[1, 1], 1, &[1, 1, 1, 1], &[2, 2], &mut ws.buf_0);
+        y.to_owned()
+    }
+"""
+
+
+def convint_forms(m):
+    prog = m.parse_model_rs(CONVINT_TEXT)
+    rng = np.random.default_rng(12)
+    wq = rng.integers(0, 256, 54)
+    blob = m.synth_blob(prog, 1, {0: wq, 54: [120]})
+    q = rng.integers(0, 256, (1, 2, 5, 6)).astype(np.float32)
+    return prog, blob, [q, np.array([7.0], np.float32)]
+
+
+def convint_forms_direct(m, blob, xs):
+    """Direct evaluation in float64: pad the raw tensor with zeros, shift by the zero points, 3x3 stride-2 windows (conv2d.rs:2025)."""
+    q = xs[0]
+    wq = m.weight_view(blob, "weight_u8", 0, 54, [3, 2, 3, 3]).astype(np.float64)
+    xp = np.zeros((1, 2, 7, 8), np.float64); xp[:, :, 1:6, 1:7] = q; xp -= float(xs[1][0])
+    w = wq - 120.0
+    want = np.zeros((1, 3, 3, 3))
+    for oc in range(3):
+        for i in range(3):
+            for j in range(3):
+                want[0, oc, i, j] = (xp[0, :, 2 * i:2 * i + 3, 2 * j:2 * j + 3] * w[oc]).sum()
+    return [want.astype(np.float32)]

@@ -533,6 +533,17 @@ pub struct Sv<'a> { data: &'a [u8] }
     assert e2e.check_yolo26(os.path.join(d, "yolo26.rs"), os.path.join(d, "yolo26_weights.bin"), [d]) is None
 
 
+def test_model_rs_conv_integer_pads_with_raw_zeros():
+    """ConvInteger as the reference computes it (conv2d.rs:1507-2025): f32 convolution of (x - x_zp) and (w - w_zp) where the padding
+    is applied to the raw tensor, i.e. a padded position contributes (0 - x_zp).  Checked against a direct float64 evaluation."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    prog, blob, xs = MF.convint_forms(m)
+    y = m.run_program(prog, blob, xs, MF.R)[0]
+    assert y.shape == (1, 3, 3, 3)
+    np.testing.assert_array_equal(y, MF.convint_forms_direct(m, blob, xs)[0])          # integer-valued and far below 2^24: exact in f32
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""

@@ -41,17 +41,17 @@ class Lockstep:
         return f
 
 
-@pytest.mark.parametrize("case", ["math", "recurrent", "quant", "shape", "const"])
+@pytest.mark.parametrize("case", ["math", "recurrent", "quant", "shape", "const", "convint"])
 def test_statement_forms_lockstep(case):
     from lele_b200 import model_rs as MR
     make, direct = {"math": (MF.math_forms, MF.math_forms_direct), "recurrent": (MF.recurrent_forms, MF.recurrent_forms_direct),
-                    "quant": (MF.quant_forms, MF.quant_forms_direct), "shape": (MF.shape_forms, lambda m, blob, xs: MF.shape_forms_direct(*xs)), "const": (MF.const_forms, MF.const_forms_direct)}[case]
+                    "quant": (MF.quant_forms, MF.quant_forms_direct), "shape": (MF.shape_forms, lambda m, blob, xs: MF.shape_forms_direct(*xs)), "const": (MF.const_forms, MF.const_forms_direct), "convint": (MF.convint_forms, MF.convint_forms_direct)}[case]
     prog, blob, x = make(MR)
     ops = Lockstep(MR)
     got = MR.run_program(prog, blob, x if isinstance(x, list) else [x], ops)
     for a, b in zip(got, direct(MR, blob, x)):
         np.testing.assert_array_equal(a, b)           # the carried values are the oracle's
-    assert len(ops.calls) >= {"math": 10, "recurrent": 3, "quant": 8, "shape": 6, "const": 10}[case]
+    assert len(ops.calls) >= {"math": 10, "recurrent": 3, "quant": 8, "shape": 6, "const": 10, "convint": 3}[case]
 
 
 def test_streaming_vad_on_device():
