@@ -19,7 +19,7 @@ import re
 
 import numpy as np
 
-__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view"]
+__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view", "GeneratedModel"]
 
 _DTYPES = {"weight_f32": ("<f4", None), "weight_i64": ("<i8", None), "weight_i64_f32": ("<i8", np.float32), "weight_i32": ("<i4", None),
            "weight_i32_i64": ("<i4", np.int64), "weight_i32_f32": ("<i4", np.float32), "weight_u8": ("u1", np.float32), "weight_i8": ("i1", np.float32),
@@ -625,3 +625,71 @@ def synth_blob(program: dict, seed: int = 7, constants=None) -> bytes:
             raise ValueError(f"synth_blob: constant at offset {off} has {v.size} elements, the view holds {n}")
         blob[off:off + ln] = v.view(np.uint8)
     return blob.tobytes()
+
+
+class GeneratedModel:
+    """The Python stand-in for the struct `lele_gen` emits (`pub struct <Class><'a> { data: &'a [u8] }`, mod.rs:1100-1135):
+    `GeneratedModel(open("yolo26seg.rs").read(), weights_bytes)` is `Yolo26Seg::new(&bin)`, `forward(*inputs)` is `forward`
+    (inputs in the order of `forward_with_workspace`; one array back for a single-output graph, a tuple otherwise)."""
+
+    def __init__(self, model_rs_text: str, weights: bytes, ops=None):
+        self.program = parse_model_rs(model_rs_text)
+        self.class_name = self.program["class"]
+        need = _blob_extent(self.program)
+        if len(weights) < need:
+            raise ValueError(f"{self.class_name}: weights blob has {len(weights)} bytes, the generated code reads up to byte {need}")
+        self.weights = weights
+        self.ops = ops
+
+    @classmethod
+    def from_files(cls, rs_path: str, weights_path: str | None = None, ops=None):
+        """`weights_path` defaults to `<stem>_weights.bin` next to the source, the name the compiler writes (mod.rs:1372)."""
+        import os
+        if weights_path is None:
+            weights_path = os.path.splitext(rs_path)[0] + "_weights.bin"
+        return cls(open(rs_path).read(), open(weights_path, "rb").read(), ops)
+
+    @property
+    def input_names(self):
+        return list(self.program["inputs"])
+
+    @property
+    def output_names(self):
+        return list(self.program["outputs"])
+
+    def forward(self, *inputs):
+        if len(inputs) != len(self.program["inputs"]):
+            raise ValueError(f"{self.class_name}.forward takes {len(self.program['inputs'])} tensors ({', '.join(self.program['inputs'])})")
+        out = run_program(self.program, self.weights, list(inputs), self.ops)
+        return out[0] if len(out) == 1 else tuple(out)
+
+    __call__ = forward
+
+
+def _blob_extent(program: dict) -> int:
+    """Highest byte any weight literal of the program touches."""
+    end = 0
+
+    def visit(a):
+        nonlocal end
+        if isinstance(a, dict):
+            for key in ("weight", "weight_scalar", "weight_list"):
+                if key in a:
+                    end = max(end, a[key][1] + a[key][2])
+            for b in a.get("items", []):
+                visit(b)
+            if "i64vec_of" in a:
+                visit(a["i64vec_of"])
+
+    def walk(statements):
+        for st in statements:
+            for a in st["args"]:
+                visit(a)
+            for br in ("then", "else"):
+                if br in st:
+                    walk(st[br]["statements"])
+                    for o in st[br]["outputs"]:
+                        visit(o)
+
+    walk(program["statements"])
+    return end

@@ -544,6 +544,25 @@ def test_model_rs_conv_integer_pads_with_raw_zeros():
     np.testing.assert_array_equal(y, MF.convint_forms_direct(m, blob, xs)[0])          # integer-valued and far below 2^24: exact in f32
 
 
+def test_generated_model_object(tmp_path):
+    """GeneratedModel = the generated struct's `new(&bin)` + `forward`: file naming of the compiler, input arity, blob size check."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    prog, blob = MF.vad_model(m)
+    rs = tmp_path / "synthvad.rs"; rs.write_text(MF.vad_text()); (tmp_path / "synthvad_weights.bin").write_bytes(blob)
+    model = m.GeneratedModel.from_files(str(rs), ops=MF.R)
+    assert model.class_name == "SynthVad" and model.input_names == ["input", "state", "sr"] and model.output_names == ["output", "stateN"]
+    x = (500 * np.random.default_rng(1).standard_normal((1, 512))).astype(np.float32); st = np.zeros((2, 1, MF.VH), np.float32)
+    out, st2 = model(x, st, np.array([16000], np.int64))
+    want = m.run_program(prog, blob, [x, st, np.array([16000], np.int64)], MF.R)
+    np.testing.assert_array_equal(out, want[0]); np.testing.assert_array_equal(st2, want[1])
+    with pytest.raises(ValueError, match="takes 3 tensors"):
+        model.forward(x)
+    with pytest.raises(ValueError, match="reads up to byte"):
+        m.GeneratedModel(MF.vad_text(), blob[:-4], MF.R)
+    assert m._blob_extent(prog) == len(blob)
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
