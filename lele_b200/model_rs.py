@@ -291,6 +291,8 @@ class CudaOps:
     def expand(self, x, shape): return self.K.expand(x, shape, ctx=self.ctx)
     def where(self, c, x, y): return self.K.where_op(c, x, y, ctx=self.ctx)
     def fused_quantized_linear(self, x, w, ws, wz, bias, relu): return self.K.fused_quantized_linear(x, w, ws, wz, bias, relu, ctx=self.ctx)
+    def prepare_weights(self, w, ws, wz, bias):     # prepare_weights (quantization.rs:221): packed once, resident in HBM
+        return self.K.PreparedWeights(np.clip(np.asarray(w), 0, 255).astype(np.uint8), ws, wz, None if bias is None or np.size(bias) == 0 else bias, self.ctx)
     def dynamic_quantize_linear(self, x): return self.K.dynamic_quantize_linear(x, ctx=self.ctx)
     def mat_mul_integer(self, a, b, zp_a, zp_b): return self.K.mat_mul_integer(a, b, zp_a, zp_b, ctx=self.ctx)
     def clip(self, x, lo, hi): return self.K.clip(x, lo, hi, ctx=self.ctx)
@@ -401,9 +403,12 @@ def _host_i64_op(op, a):
     return None                                       # reshape / unsqueeze / squeeze / flatten / identity keep the dtype below
 
 
-def run_program(program: dict, blob, inputs, ops=None, trace=None):
+def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
     """Replays the statement list.  `blob` = the model's weights.bin bytes, `inputs` = arrays in `program["inputs"]` order.
-    `ops`: CudaOps (default) or any module with the shared operator vocabulary.  Returns the outputs as numpy arrays."""
+    `ops`: CudaOps (default) or any module with the shared operator vocabulary.  Returns the outputs as numpy arrays.
+    `cache`: a dict the caller keeps across calls of one model -- decoded weight views and, where the namespace offers
+    `prepare_weights`, the device-resident packed int8 weights of each quantised linear are made once (the role of
+    B_WEIGHT_CACHE upstream, avx/quantization.rs:47-95: keyed by the weight's place in the blob)."""
     if ops is None:
         ops = CudaOps()
     elif not hasattr(ops, "binary"):
@@ -420,7 +425,13 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
             if "i64vec" in a: return _to_i64_list(env[a["i64vec"]])
             if "i64vec_of" in a: return _to_i64_list(val(a["i64vec_of"]))
             if "i64" in a: return np.int64(a["i64"])
-            if "weight" in a: return weight_view(blob, *a["weight"])
+            if "weight" in a:
+                if cache is None:
+                    return weight_view(blob, *a["weight"])
+                key = ("w", a["weight"][0], a["weight"][1], a["weight"][2], tuple(a["weight"][3]))
+                if key not in cache:
+                    cache[key] = weight_view(blob, *a["weight"])
+                return cache[key]
             if "weight_scalar" in a: return int(weight_view(blob, *a["weight_scalar"]).reshape(-1)[0])
             if "weight_list" in a: return [int(v) for v in weight_view(blob, *a["weight_list"]).reshape(-1)]
             if "list" in a: return list(a["list"])
@@ -488,7 +499,13 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None):
             r = ops.gru(a[0], a[1], a[2], a[3], a[4])
         elif op in ("self.linear_quantized", "self.linear_quantized_relu"):   # (x, weight_u8 [K,N], weight_scale, weight_zero, bias)  default_methods.rs:36-62
             zero = int(np.asarray(a[3]).reshape(-1)[0]) if np.size(a[3]) else 0
-            r = ops.fused_quantized_linear(a[0], a[1], a[2], zero, a[4], op.endswith("_relu"))
+            w = a[1]
+            if cache is not None and hasattr(ops, "prepare_weights") and all(isinstance(x, dict) and "weight" in x for x in st["args"][1:5]):
+                key = ("pw",) + tuple(x["weight"][1] for x in st["args"][1:5])
+                if key not in cache:
+                    cache[key] = ops.prepare_weights(a[1], a[2], zero, a[4])
+                w = cache[key]
+            r = ops.fused_quantized_linear(a[0], w, a[2], zero, a[4], op.endswith("_relu"))
         elif op == "self.layer_norm":                 # (x, scale, bias, epsilon tensor, two)  default_methods.rs:24: axis -1, eps = epsilon[0] or 1e-5
             eps = np.asarray(a[3]).reshape(-1)
             r = ops.layer_norm(a[0], a[1], a[2], -1, float(eps[0]) if eps.size else 1e-5)
@@ -640,6 +657,7 @@ class GeneratedModel:
             raise ValueError(f"{self.class_name}: weights blob has {len(weights)} bytes, the generated code reads up to byte {need}")
         self.weights = weights
         self.ops = ops
+        self._cache = {}
 
     @classmethod
     def from_files(cls, rs_path: str, weights_path: str | None = None, ops=None):
@@ -660,7 +678,9 @@ class GeneratedModel:
     def forward(self, *inputs):
         if len(inputs) != len(self.program["inputs"]):
             raise ValueError(f"{self.class_name}.forward takes {len(self.program['inputs'])} tensors ({', '.join(self.program['inputs'])})")
-        out = run_program(self.program, self.weights, list(inputs), self.ops)
+        if self.ops is None:
+            self.ops = CudaOps()
+        out = run_program(self.program, self.weights, list(inputs), self.ops, cache=self._cache)
         return out[0] if len(out) == 1 else tuple(out)
 
     __call__ = forward

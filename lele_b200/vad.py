@@ -91,6 +91,7 @@ class StreamingVad:
         self.program, self.blob = program, blob
         self.ops = ops if ops is not None else model_rs.CudaOps()
         self.sample_rate, self.chunk_size, self.state_shape = int(sample_rate), int(chunk_size), tuple(state_shape)
+        self._cache = {}                                           # decoded weights / prepared int8 weights: once per stream object
         self.reset()
 
     def reset(self):
@@ -103,7 +104,8 @@ class StreamingVad:
         if chunk.size != self.chunk_size:
             raise ValueError(f"StreamingVad: chunk of {chunk.size} samples, expected {self.chunk_size}")
         x = (chunk * np.float32(32768.0)).reshape(1, self.chunk_size)                                   # main.rs:115
-        out, new_state = model_rs.run_program(self.program, self.blob, [x, self.state, np.array([self.sample_rate], np.int64)], self.ops)
+        out, new_state = model_rs.run_program(self.program, self.blob, [x, self.state, np.array([self.sample_rate], np.int64)], self.ops,
+                                                  cache=self._cache)
         self.state = np.asarray(new_state, np.float32).reshape(self.state_shape)                       # main.rs:129
         out = np.asarray(out).reshape(-1)
         if out.size:                                                                                    # main.rs:124

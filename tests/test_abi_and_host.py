@@ -563,6 +563,41 @@ def test_generated_model_object(tmp_path):
     assert m._blob_extent(prog) == len(blob)
 
 
+def test_generated_model_prepares_int8_weights_once():
+    """The per-model cache: weight views are decoded once, and a namespace that offers prepare_weights (CudaOps does) is asked to
+    pack each quantised linear's weight exactly once across forwards -- the B_WEIGHT_CACHE behaviour (avx/quantization.rs:47-95)."""
+    import inspect
+    from lele_b200 import kernels as K, model_rs as MR
+    from tests import model_forms as MF
+    prog, blob, x = MF.quant_forms(MR)
+    made = []
+
+    class PackingOps(MR._NamespaceOps):
+        def prepare_weights(self, w, ws, wz, bias):
+            made.append((np.asarray(w).shape, int(wz)))
+            return ("packed", np.asarray(w), ws, wz, bias)
+
+        def fused_quantized_linear(self, x_, w, ws, wz, bias, relu):
+            if isinstance(w, tuple):
+                _, w, ws, wz, bias = w
+            return self.ns.fused_quantized_linear(x_, w, ws, wz, bias, relu)
+
+    model = MR.GeneratedModel(MF.QUANT_TEXT, blob, PackingOps(MF.R))
+    first = model(x)
+    for _ in range(2):
+        again = model(x)
+        for a, b in zip(first, again):
+            np.testing.assert_array_equal(a, b)
+    for a, b in zip(first, MF.quant_forms_direct(MR, blob, x)):
+        np.testing.assert_array_equal(a, b)
+    assert made == [((16, 24), 128), ((24, 16), 121)]                     # two linears, three forwards, two packings
+    assert sum(1 for k in model._cache if k[0] == "w") >= 8
+    # the real namespace builds lele_b200.kernels.PreparedWeights with arguments its constructor accepts
+    sig = inspect.signature(K.PreparedWeights.__init__)
+    sig.bind(None, np.zeros((4, 4), np.uint8), np.ones(1, np.float32), 3, None, None)
+    assert "prepare_weights" in MR.CudaOps.__dict__
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""

@@ -87,3 +87,17 @@ def test_c_caller_runs_an_operator(tmp_path):
     import re
     assert "layer_norm([1,2,3]) = -1.2247" in run.stdout
     assert int(re.search(r"kernel launches issued by this context: (\d+)", run.stdout).group(1)) >= 1
+
+
+def test_generated_model_prepares_int8_weights_once_on_device():
+    """GeneratedModel keeps each quantised linear's packed weight resident (lele_b200_prepare_weights once per model, the role of
+    B_WEIGHT_CACHE upstream): repeated forwards are bit-identical to each other and to the per-call path."""
+    from lele_b200 import model_rs as MR
+    prog, blob, x = MF.quant_forms(MR)
+    model = MR.GeneratedModel(MF.QUANT_TEXT, blob)
+    first, second = model(x), model(x)
+    per_call = MR.run_program(prog, blob, [x], MR.CudaOps())
+    for a, b, c in zip(first, second, per_call):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
+    assert sum(1 for k in model._cache if k[0] == "pw") == 2
