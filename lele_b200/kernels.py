@@ -359,6 +359,43 @@ def gru(input, w, r, bias=None, initial_h=None, linear_before_reset=False, ctx=N
     return out
 
 
+def _rnn_streams(gates, input, w, r, bias, initial_h, initial_c, ctx):
+    """n_seq independent batch-1 sequences that share one set of weights, in ONE launch (the `n_seq` argument of
+    lele_b200_lstm / lele_b200_gru; one CTA per stream).  Every stream gets exactly what the single-sequence call returns for it:
+    the hoisted W.x GEMM and the recurrence sum in the same order whatever n_seq is."""
+    ctx = ctx or default_context()
+    x, w, r = _f(input), _f(w), _f(r)
+    if x.ndim != 3: raise LeleB200Error("rnn streams: input must be [n_seq, seq, input_size]")
+    n_seq, seq, isz = x.shape
+    if w.shape[0] != 1: raise LeleB200Error("RNN: Only num_directions=1 supported (rnn.rs:85)")
+    hid = w.shape[1] // gates
+    if w.shape[2] != isz or r.shape[1:] != (gates * hid, hid): raise LeleB200Error("rnn streams: W / R shape mismatch")
+    states = [None if a is None else _f(a).reshape(n_seq, hid) for a in ((initial_h, initial_c) if gates == 4 else (initial_h,))]
+    bufs = [ctx.upload(x), ctx.upload(w), ctx.upload(r), None if bias is None else ctx.upload(_f(bias))] + [None if a is None else ctx.upload(a) for a in states]
+    y = ctx.empty(_b.max(n_seq * seq * hid, 1)); outs = [ctx.empty(_b.max(n_seq * hid, 1)) for _ in states]
+    p = [vp(None if b is None else b.ptr) for b in bufs]
+    dims = (i32(n_seq), i32(seq), i32(isz), i32(hid))
+    if gates == 4:
+        call("lele_b200_lstm", ctx.h, p[0], p[1], p[2], p[3], p[4], p[5], *dims, vp(y.ptr), vp(outs[0].ptr), vp(outs[1].ptr))
+    else:
+        call("lele_b200_gru", ctx.h, p[0], p[1], p[2], p[3], p[4], *dims, vp(y.ptr), vp(outs[0].ptr))
+    res = (ctx.download(y, (n_seq, seq, hid)),) + tuple(ctx.download(o, (n_seq, hid)) for o in outs)
+    for b in bufs + [y] + outs:
+        if b is not None: b.free()
+    return res
+
+
+def lstm_streams(input, w, r, bias=None, initial_h=None, initial_c=None, ctx=None):
+    """Many streams per launch (SURVEY 8f rank 4): input [n_seq, S, I], states [n_seq, H] -> (Y [n_seq, S, H], H [n_seq, H], C [n_seq, H]);
+    stream s equals `lstm(input[s][:, None, :], ..., initial_h[s], initial_c[s])` (rnn.rs:67 is batch-1 only)."""
+    return _rnn_streams(4, input, w, r, bias, initial_h, initial_c, ctx)
+
+
+def gru_streams(input, w, r, bias=None, initial_h=None, ctx=None):
+    """input [n_seq, S, I], initial_h [n_seq, H] -> (Y [n_seq, S, H], H [n_seq, H]); stream s equals `gru` on that stream alone (rnn.rs:246)."""
+    return _rnn_streams(3, input, w, r, bias, initial_h, None, ctx)
+
+
 # ---------------------------------------------------------------- math.rs
 _BIN = {"add": 0, "sub": 1, "mul": 2, "div": 3, "max": 4, "pow": 5, "mod_f32": 6, "prelu": 7, "equal": 8, "less": 9}
 _UN = {"relu": 0, "sigmoid": 1, "tanh_kernel": 2, "silu": 3, "erf": 4, "gelu": 5, "exp": 6, "softplus": 7, "log": 8, "sqrt": 9,

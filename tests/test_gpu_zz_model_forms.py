@@ -101,3 +101,33 @@ def test_generated_model_prepares_int8_weights_once_on_device():
         np.testing.assert_array_equal(a, b)
         np.testing.assert_array_equal(a, c)
     assert sum(1 for k in model._cache if k[0] == "pw") == 2
+
+
+@pytest.mark.parametrize("hid,isz,seq,n_seq", [(128, 128, 40, 24), (16, 8, 9, 5)])
+def test_recurrent_streams_match_single_sequence_calls(hid, isz, seq, n_seq):
+    """SURVEY 8f rank 4, the device half: many VAD streams advance in one launch (one CTA per stream, shared weights, per-stream
+    carried state).  Each stream must be bit-identical to the batch-1 call the reference's `lstm` / `gru` correspond to, and
+    within the f32 bar of the oracle."""
+    from lele_b200 import kernels as K
+    rng = np.random.default_rng(hid + n_seq)
+    x = rng.standard_normal((n_seq, seq, isz)).astype(np.float32)
+    w = (rng.standard_normal((1, 4 * hid, isz)) / np.sqrt(isz)).astype(np.float32); r = (rng.standard_normal((1, 4 * hid, hid)) / np.sqrt(hid)).astype(np.float32)
+    b = (0.1 * rng.standard_normal((1, 8 * hid))).astype(np.float32)
+    h0 = rng.standard_normal((n_seq, hid)).astype(np.float32); c0 = rng.standard_normal((n_seq, hid)).astype(np.float32)
+    y, h, c = K.lstm_streams(x, w, r, b, h0, c0)
+    assert y.shape == (n_seq, seq, hid) and h.shape == c.shape == (n_seq, hid)
+    for s in (0, 1, n_seq - 1):
+        y1, h1, c1 = K.lstm(x[s][:, None, :], w, r, b, None, h0[s].reshape(1, 1, hid), c0[s].reshape(1, 1, hid))
+        np.testing.assert_array_equal(y[s], y1.reshape(seq, hid)); np.testing.assert_array_equal(h[s], h1.reshape(hid)); np.testing.assert_array_equal(c[s], c1.reshape(hid))
+        yr, hr, cr = MF.R.lstm(x[s][:, None, :], w, r, b, h0[s].reshape(1, 1, hid), c0[s].reshape(1, 1, hid))
+        close(y[s], yr.reshape(seq, hid)); close(c[s], cr.reshape(hid))
+    w3, r3, b3 = w[:, :3 * hid], r[:, :3 * hid], b[:, :6 * hid]
+    yg, hg = K.gru_streams(x, w3, r3, b3, h0)
+    for s in (0, n_seq - 1):
+        y1, h1 = K.gru(x[s][:, None, :], w3, r3, b3, h0[s].reshape(1, 1, hid))
+        np.testing.assert_array_equal(yg[s], y1.reshape(seq, hid)); np.testing.assert_array_equal(hg[s], h1.reshape(hid))
+        yr, hr = MF.R.gru(x[s][:, None, :], w3, r3, b3, h0[s].reshape(1, 1, hid))
+        close(yg[s], yr.reshape(seq, hid))
+    y0, h0z, _ = K.lstm_streams(x, w, r, None)                      # no bias, zero initial state
+    y1, _, _ = K.lstm(x[2][:, None, :], w, r, None)
+    np.testing.assert_array_equal(y0[2], y1.reshape(seq, hid))
