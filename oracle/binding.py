@@ -113,6 +113,8 @@ def cmvn(x, eps=1e-5):
 def stft(sig, n_fft, hop, win, window=None, power=False):
     sig_in = sig
     sig = _f(sig).reshape(-1); L = sig.size
+    if L == 0:   # math.rs:2313-2316 / :2381-2384: an empty signal gives an empty tensor, not one zero frame
+        return np.zeros((0, 0, n_fft // 2 + 1) if power else (0, 0, n_fft // 2 + 1, 2), np.float32)
     frames = 1 if L < win else (L - win) // hop + 1
     nfr = n_fft // 2 + 1
     out = np.empty((frames, nfr) if power else (frames, nfr, 2), np.float32)

@@ -131,3 +131,14 @@ def test_recurrent_streams_match_single_sequence_calls(hid, isz, seq, n_seq):
     y0, h0z, _ = K.lstm_streams(x, w, r, None)                      # no bias, zero initial state
     y1, _, _ = K.lstm(x[2][:, None, :], w, r, None)
     np.testing.assert_array_equal(y0[2], y1.reshape(seq, hid))
+
+
+def test_stft_shape_rules_on_device():
+    """math.rs:2313-2316, :2362-2367, :2381-2384: empty signal -> empty tensor, rank >= 2 input -> leading batch dim."""
+    from lele_b200 import kernels as K
+    sig = np.sin(np.arange(800, dtype=np.float32) * np.float32(0.01))
+    for power in (False, True):
+        assert K.stft(np.zeros(0, np.float32), 256, 64, 256, None, power).shape == MF.R.stft(np.zeros(0, np.float32), 256, 64, 256, None, power).shape
+        g, r = K.stft(sig[None, :], 256, 128, 256, None, power), MF.R.stft(sig[None, :], 256, 128, 256, None, power)
+        assert g.shape == r.shape == ((1, 5, 129) if power else (1, 5, 129, 2))
+        close(g, r, atol_frac=1e-5)

@@ -83,6 +83,13 @@ def test_stft_reference_properties():  # tests/regression_kernels.rs:426-517
     mid = p[p.shape[0] // 2]
     other = np.concatenate([mid[:5], mid[-4:]])
     assert mid[16] > 5 * other.max()
+    # shape rules of math.rs:2313-2316, :2362-2367, :2381-2384: empty signal -> empty tensor; shorter than a window -> one frame;
+    # rank >= 2 input -> leading batch dim
+    assert R.stft(np.zeros(0, np.float32), 256, 64, 256).shape == (0, 0, 129, 2)
+    assert R.stft(np.zeros(0, np.float32), 256, 64, 256, power=True).shape == (0, 0, 129)
+    assert R.stft(sig[:100], 256, 64, 256).shape == (1, 129, 2)
+    assert R.stft(sig[None, :], 256, 128, 256).shape == (1, 5, 129, 2) and R.stft(sig[None, :], 256, 128, 256, power=True).shape == (1, 5, 129)
+    np.testing.assert_array_equal(R.stft(sig[None, :], 256, 128, 256)[0], c)
 
 
 def _ref_gru(x, w, r, bw, br, hs):  # tests/regression_kernels.rs:602-633 (f64 restatement)
