@@ -452,7 +452,7 @@ def clip(x, lo, hi, ctx=None):
 def _reduce(kind, x, axes, keepdims, ctx=None):
     """math.rs:1527-1921.  Arbitrary axes: transposed to a single middle axis first."""
     x = _f(x)
-    axes = sorted(a % x.ndim for a in axes) if len(axes) else list(range(x.ndim))
+    axes = sorted({a % x.ndim for a in axes})   # deduplicated (math.rs:1629); an empty list reduces nothing upstream (reduce_mask stays false, :1631)
     keep = [i for i in range(x.ndim) if i not in axes]
     xt = np.ascontiguousarray(np.transpose(x, keep + axes)) if axes != list(range(x.ndim - len(axes), x.ndim)) else x
     outer = _prod([x.shape[i] for i in keep]); alen = _prod([x.shape[i] for i in axes])

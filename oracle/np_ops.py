@@ -197,7 +197,7 @@ def prelu(x, slope):  # math.rs:2012
 
 def reduce(x, axes, keepdims, kind):  # math.rs:1527-1921
     x = _a(x)
-    axes = tuple(a + x.ndim if a < 0 else a for a in axes) if len(axes) else tuple(range(x.ndim))
+    axes = tuple(sorted({a + x.ndim if a < 0 else a for a in axes}))   # sorted + dedup (math.rs:1628); an EMPTY list reduces nothing (reduce_mask stays false, math.rs:1631): sum -> 0 + x, l2 -> |x|
     if kind == "sum":
         return np.add.reduce(x, axis=axes, keepdims=keepdims, dtype=np.float32)
     if kind == "mean":

@@ -142,3 +142,13 @@ def test_stft_shape_rules_on_device():
         g, r = K.stft(sig[None, :], 256, 128, 256, None, power), MF.R.stft(sig[None, :], 256, 128, 256, None, power)
         assert g.shape == r.shape == ((1, 5, 129) if power else (1, 5, 129, 2))
         close(g, r, atol_frac=1e-5)
+
+
+def test_reduce_axes_edge_semantics_on_device():
+    """math.rs:1611-1650: axes de-duplicated; an empty list reduces nothing (sum / mean -> 0 + x, max -> x, l2 -> |x|)."""
+    x = np.array([[1.0, -2.0, 0.5], [3.0, -0.0, -7.0]], np.float32)
+    for kind in ("sum", "mean", "max", "l2"):
+        for keep in (True, False):
+            np.testing.assert_array_equal(G.reduce(x, [], keep, kind), MF.R.reduce(x, [], keep, kind))
+        np.testing.assert_array_equal(G.reduce(x, [1, 1, -1], False, kind).shape, (2,))
+        close(G.reduce(x, [1, 1, -1], False, kind), MF.R.reduce(x, [1, 1, -1], False, kind), atol_frac=1e-6)

@@ -224,3 +224,16 @@ def test_frontend_shapes_and_edges():
     ref = np.log(np.maximum(wts @ pw, 1e-5))
     mel = R.frontend(synth_pcm(1, 4000), want_mel=True)[0]
     np.testing.assert_allclose(mel[1], ref, rtol=2e-4, atol=2e-4)
+
+
+def test_reduce_axes_edge_semantics():  # math.rs:1611-1650 (same prologue in reduce_mean / reduce_max / reduce_l2)
+    """Axes are resolved, sorted and de-duplicated; an empty list reduces NOTHING (the mask stays all-false): sum and mean return
+    0 + x, max returns x, l2 returns |x| -- unlike ONNX, where empty axes mean "all"."""
+    x = np.array([[1.0, -2.0], [3.0, -0.0]], np.float32)
+    for kind, want in (("sum", x + 0.0), ("mean", x + 0.0), ("max", x), ("l2", np.abs(x))):
+        for keep in (True, False):
+            got = R.reduce(x, [], keep, kind)
+            assert got.shape == (2, 2)
+            np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(R.reduce(x, [1, 1, -1], False, "sum"), [-1.0, 3.0])
+    np.testing.assert_array_equal(R.reduce(x, [1, 0], False, "max"), 3.0)
