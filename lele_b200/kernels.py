@@ -642,20 +642,33 @@ def argmax_last(x, ctx=None):
 
 
 # zero-copy shape ops stay on the host (shape.rs:2-223)
+def _fh(a):   # like _f, but a rank-0 value keeps its rank (np.ascontiguousarray would make it rank 1)
+    return np.asarray(a, dtype=np.float32, order="C")
+
+
 def reshape(x, shape):
-    x = _f(x)
-    return x.reshape([x.shape[i] if (s == 0 and i < x.ndim) else int(s) for i, s in enumerate(shape)])
+    """shape.rs:2 (three-pass target resolution)"""
+    from .model_rs import resolve_reshape
+    x = _fh(x)
+    try:
+        return x.reshape(resolve_reshape(x.shape, shape))
+    except ValueError as e:
+        raise LeleB200Error(str(e))
 
 
 def flatten(x, axis=1):
-    x = _f(x); return x.reshape(_prod(x.shape[:axis]), -1)
+    """shape.rs:105: [prod(shape[:axis]), prod(shape[axis:])], negative axis counted from the end"""
+    x = _fh(x); axis = axis + x.ndim if axis < 0 else axis
+    return x.reshape(_prod(x.shape[:axis]), _prod(x.shape[axis:]))
 
 
 def unsqueeze(x, axes):
-    x = _f(x)
-    for a in sorted(int(a) % (x.ndim + 1) for a in axes): x = np.expand_dims(x, a)
-    return x
+    """shape.rs:133 (raw axes sorted, resolved against the output rank, inserted in turn)"""
+    from .model_rs import unsqueeze_shape
+    x = _fh(x); return x.reshape(unsqueeze_shape(x.shape, axes))
 
 
-def squeeze(x, axes=()):
-    x = _f(x); return np.squeeze(x, tuple(int(a) for a in axes) if len(axes) else None)
+def squeeze(x, axes=None):
+    """shape.rs:157: axes None = every dim of 1; with axes only listed dims that ARE 1 go (an empty list removes nothing)"""
+    from .model_rs import squeeze_shape
+    x = _fh(x); return x.reshape(squeeze_shape(x.shape, axes))

@@ -19,7 +19,7 @@ import re
 
 import numpy as np
 
-__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view", "GeneratedModel"]
+__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view", "GeneratedModel", "resolve_reshape", "squeeze_shape", "unsqueeze_shape"]
 
 _DTYPES = {"weight_f32": ("<f4", None), "weight_i64": ("<i8", None), "weight_i64_f32": ("<i8", np.float32), "weight_i32": ("<i4", None),
            "weight_i32_i64": ("<i4", np.int64), "weight_i32_f32": ("<i4", np.float32), "weight_u8": ("u1", np.float32), "weight_i8": ("i1", np.float32),
@@ -322,9 +322,74 @@ def _c(x, dtype=None):  # C-contiguous without np.ascontiguousarray's promotion 
     return np.asarray(x, dtype=dtype, order="C")
 
 
-def _reshape(x, shape):  # shape.rs:2-93: 0 copies the input dim, -1 is inferred
-    shp = [x.shape[i] if s == 0 else s for i, s in enumerate(shape)]
-    return _c(x).reshape(shp)
+def resolve_reshape(in_shape, target):
+    """The three passes of `reshape` (shape.rs:2-52): (1) ONNX rules -- 0 copies the input dim at that position, one -1 is inferred;
+    (2) every 0 re-read as -1; (3) a target of higher rank than the input collapsed to [first, -1, last rank-1 dims].  The first
+    pass whose element count matches wins; otherwise the reference panics."""
+    in_shape = [int(d) for d in in_shape]; target = [int(d) for d in target]
+    total = 1
+    for d in in_shape:
+        total *= d
+
+    def attempt(tgt):                                  # try_reshape_with_zeros, shape.rs:54-93
+        new, known, infer = [], 1, None
+        for i, d in enumerate(tgt):
+            if d == -1:
+                if infer is not None:
+                    return None
+                infer = i
+            elif d == 0:
+                if i >= len(in_shape):
+                    return None
+                new.append(in_shape[i]); known *= in_shape[i]
+            else:
+                new.append(d); known *= d
+        if infer is not None:
+            if known == 0 or total % known != 0:
+                return None
+            new.insert(infer, total // known)
+        prod = 1
+        for d in new:
+            prod *= d
+        return new if prod == total else None
+
+    for tgt in (target, [-1 if d == 0 else d for d in target]):
+        got = attempt(tgt)
+        if got is not None:
+            return got
+    if len(target) > len(in_shape) > 0:
+        tail = target[len(target) - (len(in_shape) - 1):] if len(in_shape) > 1 else []
+        got = attempt([target[0] if target[0] > 0 else -1, -1] + [d if d > 0 else -1 for d in tail])
+        if got is not None:
+            return got
+    raise ValueError(f"Reshape: element count mismatch (input={in_shape} target={target})")
+
+
+def squeeze_shape(in_shape, axes):
+    """`squeeze` (shape.rs:157-183): with axes, a dim goes only if it is listed AND equals 1 (anything else listed is silently kept;
+    an empty list removes nothing); without axes (None), every dim equal to 1 goes."""
+    if axes is None:
+        return [int(d) for d in in_shape if d != 1]
+    pick = {int(a) + len(in_shape) if a < 0 else int(a) for a in axes}
+    return [int(d) for i, d in enumerate(in_shape) if not (d == 1 and i in pick)]
+
+
+def unsqueeze_shape(in_shape, axes):
+    """`unsqueeze` (shape.rs:133-156): the output rank is fixed first, the RAW axes are sorted (negative ones come first), each is
+    resolved against the output rank and inserted in turn; a position past the current end appends."""
+    new, rank = [int(d) for d in in_shape], len(in_shape) + len(axes)
+    for a in sorted(int(a) for a in axes):
+        idx = rank + a if a < 0 else a
+        if idx <= len(new):
+            new.insert(idx, 1)
+        else:
+            new.append(1)
+    return new
+
+
+def _reshape(x, shape):
+    x = _c(x)
+    return x.reshape(resolve_reshape(x.shape, shape))
 
 
 def _to_i64_list(x):  # to_i64_vec (manipulation.rs:1082): `as i64` truncation of every element
@@ -540,8 +605,8 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
         elif op == "expand":
             r = ops.expand(a[0], a[1])
         elif op == "squeeze":
-            x = _c(a[0]); axes = a[1]
-            r = np.squeeze(x, axis=tuple(ax % x.ndim for ax in axes)) if axes else np.squeeze(x)
+            x = _c(a[0])
+            r = x.reshape(squeeze_shape(x.shape, a[1]))
         elif op == "where_op":
             r = ops.where(a[0], a[1], a[2])
         elif op == "concat":
@@ -556,12 +621,11 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
         elif op == "reshape":
             r = _reshape(a[0], a[1])
         elif op == "flatten":
-            x = _c(a[0]); ax = a[1] % (x.ndim + 1) if a[1] < 0 else a[1]
-            r = x.reshape(int(np.prod(x.shape[:ax], dtype=np.int64)), -1)
+            x = _c(a[0]); ax = a[1] + x.ndim if a[1] < 0 else a[1]                 # shape.rs:109: negative axis counted from the end
+            r = x.reshape(int(np.prod(x.shape[:ax], dtype=np.int64)), int(np.prod(x.shape[ax:], dtype=np.int64)))
         elif op == "unsqueeze":
             r = _c(a[0])
-            for ax in sorted(x % (r.ndim + 1) if x < 0 else x for x in a[1]):
-                r = np.expand_dims(r, ax)
+            r = r.reshape(unsqueeze_shape(r.shape, a[1]))
         elif op == "transpose":
             r = ops.transpose(a[0], a[1])
         elif op == "resize_nearest":

@@ -114,10 +114,52 @@ def flatten(x, axis=1):  # shape.rs:105-120
     return x.reshape(int(np.prod(x.shape[:axis], dtype=np.int64)), int(np.prod(x.shape[axis:], dtype=np.int64)))
 
 
-def reshape(x, shape):  # shape.rs:2-93 (0 = copy dim, -1 = infer)
-    x = _a(x)
-    shp = [x.shape[i] if (s == 0 and i < x.ndim) else int(s) for i, s in enumerate(shape)]
-    return x.reshape(shp)
+def _try_reshape(in_shape, tgt, total):  # try_reshape_with_zeros, shape.rs:54-93
+    new, known, infer = [], 1, None
+    for i, d in enumerate(tgt):
+        if d == -1:
+            if infer is not None:
+                return None
+            infer = i
+        elif d == 0:
+            if i >= len(in_shape):
+                return None
+            new.append(in_shape[i]); known *= in_shape[i]
+        else:
+            new.append(int(d)); known *= int(d)
+    if infer is not None:
+        if known == 0 or total % known:
+            return None
+        new.insert(infer, total // known)
+    return new if int(np.prod(new, dtype=np.int64)) == total else None
+
+
+def reshape(x, shape):  # shape.rs:2-52: ONNX 0 / -1 rules, then 0 read as -1, then rank collapse [first, -1, last rank-1 dims]
+    x = _a(x); tgt = [int(s) for s in shape]; ish = list(x.shape)
+    tries = [tgt, [-1 if d == 0 else d for d in tgt]]
+    if len(tgt) > x.ndim > 0:
+        tries.append([tgt[0] if tgt[0] > 0 else -1, -1] + [d if d > 0 else -1 for d in (tgt[len(tgt) - (x.ndim - 1):] if x.ndim > 1 else [])])
+    for t in tries:
+        shp = _try_reshape(ish, t, x.size)
+        if shp is not None:
+            return x.reshape(shp)
+    raise ValueError(f"Reshape: element count mismatch (input={ish} target={tgt})")
+
+
+def unsqueeze(x, axes):  # shape.rs:133-156: raw axes sorted, resolved against the OUTPUT rank, inserted one after the other
+    x = np.asarray(x, np.float32); new = list(x.shape); rank = x.ndim + len(axes)
+    for a in sorted(int(a) for a in axes):
+        idx = rank + a if a < 0 else a
+        new.insert(idx, 1) if idx <= len(new) else new.append(1)
+    return x.reshape(new)
+
+
+def squeeze(x, axes=None):  # shape.rs:157-183
+    x = np.asarray(x, np.float32)
+    if axes is None:
+        return x.reshape([d for d in x.shape if d != 1])
+    pick = {a + x.ndim if a < 0 else a for a in axes}
+    return x.reshape([d for i, d in enumerate(x.shape) if not (d == 1 and i in pick)])
 
 
 def topk(x, k):  # conv2d.rs:1385-1437: last axis, stable, indices as f32

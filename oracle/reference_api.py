@@ -55,6 +55,8 @@ expand = N.expand
 tile = N.tile
 reshape = N.reshape
 flatten = N.flatten
+squeeze = N.squeeze
+unsqueeze = N.unsqueeze
 topk = N.topk
 gather_elements = N.gather_elements
 resize_nearest = N.resize_nearest

@@ -598,6 +598,55 @@ def test_generated_model_prepares_int8_weights_once():
     assert "prepare_weights" in MR.CudaOps.__dict__
 
 
+RESHAPE_CASES = [  # (input shape, target, expected) -- shape.rs:2-93; None = the reference panics
+    ([2, 2], [4], [4]), ([2, 2], [1, -1], [1, 4]),                      # src/kernels/shape.rs:194-203
+    ([2, 3], [-1, 2], [3, 2]), ([2, 2, 3], [2, -1, 2], [2, 3, 2]),      # tests/regression_kernels.rs:934-945
+    ([2, 3, 4], [0, 12], [2, 12]), ([2, 3, 4], [0, 0, -1], [2, 3, 4]),  # pass 1: 0 copies the input dim
+    ([4, 6], [0, 3], [8, 3]),                                           # pass 2: [4, 3] has the wrong count, so 0 is re-read as -1
+    ([1, 64, 601], [1, 96000, 64, 601], [1, 1, 64, 601]),               # pass 3: the example in the reference's comment (shape.rs:26)
+    ([6], [2, 5, 3], [2, 1, 3]),                                        # pass 3 on a rank-1 input: [first, -1] + last 0 dims ... = [2, -1] fails, then panic?
+    ([6], [4], None), ([2, 3], [-1, -1], None), ([2, 3], [0, 0, 0], None),
+]
+
+
+def test_reshape_and_squeeze_follow_the_reference_rules(so_path):
+    """Host shape logic in three places (oracle, lele_b200.kernels, model_rs replay) against the rules of shape.rs."""
+    from lele_b200 import LeleB200Error, kernels as K, model_rs as MR
+    from oracle import reference_api as R
+    for ish, tgt, want in RESHAPE_CASES:
+        x = np.arange(int(np.prod(ish)), dtype=np.float32).reshape(ish)
+        if ish == [6] and tgt == [2, 5, 3]:
+            want = None                                              # rank-1 input: the collapsed target is [2, -1] -> [2, 3], see below
+            assert MR.resolve_reshape(ish, tgt) == [2, 3]
+            assert list(R.reshape(x, tgt).shape) == [2, 3] and list(K.reshape(x, tgt).shape) == [2, 3]
+            continue
+        if want is None:
+            with pytest.raises(ValueError, match="element count mismatch"):
+                MR.resolve_reshape(ish, tgt)
+            with pytest.raises(ValueError, match="element count mismatch"):
+                R.reshape(x, tgt)
+            with pytest.raises(LeleB200Error, match="element count mismatch"):
+                K.reshape(x, tgt)
+            continue
+        assert MR.resolve_reshape(ish, tgt) == want, (ish, tgt)
+        for got in (R.reshape(x, tgt), K.reshape(x, tgt), MR._reshape(x, tgt)):
+            assert list(got.shape) == want
+            np.testing.assert_array_equal(got.reshape(-1), x.reshape(-1))
+    x = np.zeros((1, 3, 1, 2), np.float32)
+    for axes, want in ((None, [3, 2]), ([], [1, 3, 1, 2]), ([0], [3, 1, 2]), ([0, 1], [3, 1, 2]), ([-2, 0], [3, 2]), ([1, 3], [1, 3, 1, 2])):
+        assert MR.squeeze_shape(x.shape, axes) == want, axes
+        assert list(R.squeeze(x, axes).shape) == want and list(K.squeeze(x, axes).shape) == want
+    v = np.zeros(3, np.float32)
+    for axes, want in (([0], [1, 3]), ([-1], [3, 1]), ([-1, -2], [3, 1, 1]), ([0, -1], [1, 3, 1]), ([1, 2], [3, 1, 1]), ([0, 1], [1, 1, 3]), ([5], [3, 1])):
+        assert MR.unsqueeze_shape(v.shape, axes) == want, axes
+        assert list(R.unsqueeze(v, axes).shape) == want and list(K.unsqueeze(v, axes).shape) == want
+        if max(axes) < 3:
+            assert np.expand_dims(v, tuple(axes)).shape == tuple(want)     # agrees with numpy wherever numpy accepts the axes
+    assert list(K.flatten(np.zeros((2, 3, 4)), -1).shape) == [6, 4] and list(R.flatten(np.zeros((2, 3, 4)), -1).shape) == [6, 4]
+    one = np.ones((1, 1), np.float32)                                   # src/kernels/shape.rs:214-223
+    assert R.squeeze(one, None).shape == () and K.squeeze(one).shape == () and K.unsqueeze(K.squeeze(one), [0]).shape == (1,)
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
