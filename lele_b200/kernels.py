@@ -607,7 +607,7 @@ def gather(data, indices, axis=0, ctx=None):
     """manipulation.rs:589"""
     x = _f(data); idx = _f(indices); ax = axis % x.ndim
     outer = _prod(x.shape[:ax]); inner = _prod(x.shape[ax + 1:])
-    shp = tuple(x.shape[:ax]) + tuple(idx.shape) + tuple(x.shape[ax + 1:])
+    shp = tuple(x.shape[:ax]) + tuple(np.shape(indices)) + tuple(x.shape[ax + 1:])   # a rank-0 index removes the axis (manipulation.rs:609)
     return _run(shp, lambda c, o, px, pi: call("lele_b200_gather", c.h, px, i64(outer), i32(x.shape[ax]), i64(inner), pi, i64(idx.size), o), x, idx, ctx=ctx)
 
 

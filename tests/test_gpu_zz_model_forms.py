@@ -152,3 +152,13 @@ def test_reduce_axes_edge_semantics_on_device():
             np.testing.assert_array_equal(G.reduce(x, [], keep, kind), MF.R.reduce(x, [], keep, kind))
         np.testing.assert_array_equal(G.reduce(x, [1, 1, -1], False, kind).shape, (2,))
         close(G.reduce(x, [1, 1, -1], False, kind), MF.R.reduce(x, [1, 1, -1], False, kind), atol_frac=1e-6)
+
+
+def test_gather_with_scalar_index_drops_the_axis():
+    """manipulation.rs:604-611: the output shape splices in the INDEX shape, so a rank-0 index removes the gathered axis."""
+    x = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    for axis in (0, 1, -1):
+        g, r = G.gather(x, np.array(1, np.int64), axis), MF.R.gather(x, np.array(1, np.int64), axis)
+        assert g.shape == r.shape and g.ndim == 2
+        np.testing.assert_array_equal(g, r)
+    np.testing.assert_array_equal(G.gather(x, np.array([[2, -1]], np.int64), 1), MF.R.gather(x, np.array([[2, -1]], np.int64), 1))
