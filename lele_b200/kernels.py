@@ -551,7 +551,10 @@ def expand(x, shape, ctx=None):
 
 def split(x, axis, splits, ctx=None):
     """manipulation.rs:1091 / split_owned :1153"""
-    x = _f(x); ax = axis % x.ndim; st = _estrides(x.shape); outs, o = [], 0
+    x = _f(x)
+    if not -x.ndim <= axis < x.ndim: raise LeleB200Error("Split: axis out of bounds (manipulation.rs:1169)")
+    ax = axis % x.ndim; st = _estrides(x.shape); outs, o = [], 0
+    if sum(int(s) for s in splits) != x.shape[ax]: raise LeleB200Error("Split: splits sum mismatch (manipulation.rs:1173)")
     for s in splits:
         shp = list(x.shape); shp[ax] = int(s)
         outs.append(_strided(x, shp, st, o * st[ax], ctx)); o += int(s)

@@ -86,6 +86,10 @@ def transpose(x, perm=()):  # manipulation.rs:644-1080 (empty perm = reverse)
 def split(x, axis, splits):  # manipulation.rs:1091-1213
     x = _a(x)
     ax = axis + x.ndim if axis < 0 else axis
+    if not 0 <= ax < x.ndim:
+        raise ValueError("Split: axis out of bounds")          # manipulation.rs:1169
+    if sum(int(s) for s in splits) != x.shape[ax]:
+        raise ValueError("Split: splits sum mismatch")         # manipulation.rs:1173
     outs, o = [], 0
     for s in splits:
         sl = [slice(None)] * x.ndim

@@ -647,6 +647,33 @@ def test_reshape_and_squeeze_follow_the_reference_rules(so_path):
     assert R.squeeze(one, None).shape == () and K.squeeze(one).shape == () and K.unsqueeze(K.squeeze(one), [0]).shape == (1,)
 
 
+def test_precondition_failures_raise_before_any_device_work(so_path):
+    """Where the reference panics on a violated precondition, the mirror raises LeleB200Error with the same message -- from host code,
+    before a context or a device buffer is touched (so this runs on the CPU box; `ctx=object()` proves no context is used)."""
+    from lele_b200 import LeleB200Error, kernels as K
+    from oracle import reference_api as R
+    z = lambda *s: np.zeros(s, np.float32)
+    nothing = object()
+    cases = [
+        ("splits sum mismatch", lambda: K.split(z(2, 6), 1, [2, 2], ctx=nothing)),                        # manipulation.rs:1173
+        ("axis out of bounds", lambda: K.split(z(2, 6), 2, [6], ctx=nothing)),                             # manipulation.rs:1169
+        ("element count mismatch", lambda: K.reshape(z(2, 3), [4])),                                       # shape.rs:48
+        ("K mismatch", lambda: K.matmul(z(2, 3), z(4, 5), ctx=nothing)),                                   # gemm.rs:129
+        ("Gemm K dim mismatch", lambda: K.gemm(z(2, 3), z(4, 5), ctx=nothing)),                            # gemm.rs:465
+        ("only the last axis", lambda: K.softmax(z(2, 3), 0, ctx=nothing)),                                # norm.rs:218
+        ("Only batch_size=1", lambda: K.lstm(z(2, 2, 4), z(1, 8, 4), z(1, 8, 2), ctx=nothing)),            # rnn.rs:88
+        ("Only num_directions=1", lambda: K.gru(z(2, 1, 4), z(2, 6, 4), z(2, 6, 2), ctx=nothing)),         # rnn.rs:262
+        ("expected rank-4", lambda: K.conv_transpose(z(1, 2, 3), z(2, 2, 1, 1), ctx=nothing)),             # conv2d.rs:2989
+        ("group > 1 not supported", lambda: K.conv_transpose(z(1, 2, 3, 3), z(2, 2, 1, 1), group=2, ctx=nothing)),   # conv2d.rs:3042
+    ]
+    for msg, fn in cases:
+        with pytest.raises(LeleB200Error, match=msg):
+            fn()
+    for msg, fn in (("splits sum mismatch", lambda: R.split(z(2, 6), 1, [2, 2])), ("element count mismatch", lambda: R.reshape(z(2, 3), [4]))):
+        with pytest.raises(ValueError, match=msg):
+            fn()
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
