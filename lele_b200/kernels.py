@@ -544,7 +544,12 @@ def slice(x, starts, ends, axes=(), steps=(), ctx=None):  # noqa: A001
 
 def expand(x, shape, ctx=None):
     """math.rs:2168"""
-    x = _f(x); tgt = np.broadcast_shapes(x.shape, tuple(int(s) for s in shape))
+    from .model_rs import expand_shape
+    x = _f(x)
+    try:
+        tgt = tuple(expand_shape(x.shape, shape))       # 0 = the input's size, two-way broadcasting (math.rs:2189-2204)
+    except ValueError as e:
+        raise LeleB200Error(str(e))
     xs = [1] * (len(tgt) - x.ndim) + list(x.shape); st = _estrides(xs)
     return _strided(x, list(tgt), [0 if xs[i] == 1 else st[i] for i in range(len(tgt))], 0, ctx)
 

@@ -19,7 +19,7 @@ import re
 
 import numpy as np
 
-__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view", "GeneratedModel", "resolve_reshape", "squeeze_shape", "unsqueeze_shape"]
+__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view", "GeneratedModel", "resolve_reshape", "squeeze_shape", "unsqueeze_shape", "expand_shape"]
 
 _DTYPES = {"weight_f32": ("<f4", None), "weight_i64": ("<i8", None), "weight_i64_f32": ("<i8", np.float32), "weight_i32": ("<i4", None),
            "weight_i32_i64": ("<i4", np.int64), "weight_i32_f32": ("<i4", np.float32), "weight_u8": ("u1", np.float32), "weight_i8": ("i1", np.float32),
@@ -387,6 +387,23 @@ def unsqueeze_shape(in_shape, axes):
     return new
 
 
+def expand_shape(in_shape, target):
+    """`expand` (math.rs:2175-2210): shapes right-aligned, a target entry of 0 means "the input's size here", then two-way
+    broadcasting (equal, or either side 1); anything else is the reference's panic."""
+    n = max(len(in_shape), len(target)); out = []
+    for i in range(n):
+        d_in = int(in_shape[i - (n - len(in_shape))]) if i >= n - len(in_shape) else 1
+        d_t = int(target[i - (n - len(target))]) if i >= n - len(target) else 1
+        d_t = d_in if d_t == 0 else d_t
+        if d_in == d_t or d_in == 1:
+            out.append(d_t)
+        elif d_t == 1:
+            out.append(d_in)
+        else:
+            raise ValueError(f"Expand: incompatible dimensions at dim index {i} (from left): in={d_in} target={d_t}. Full shapes: in={list(in_shape)} target={list(target)}")
+    return out
+
+
 def _reshape(x, shape):
     x = _c(x)
     return x.reshape(resolve_reshape(x.shape, shape))
@@ -463,8 +480,8 @@ def _host_i64_op(op, a):
     if op == "where_op":
         return np.where(np.asarray(a[0]) != 0, a[1], a[2]).astype(np.int64)
     if op == "expand":
-        x = np.asarray(a[0]); shp = np.broadcast_shapes(x.shape, tuple(a[1]))
-        return _c(np.broadcast_to(x, shp))
+        x = np.asarray(a[0])
+        return _c(np.broadcast_to(x, tuple(expand_shape(x.shape, a[1]))))
     return None                                       # reshape / unsqueeze / squeeze / flatten / identity keep the dtype below
 
 

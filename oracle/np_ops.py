@@ -104,8 +104,14 @@ def where_op(cond, x, y):  # manipulation.rs:1215-1399 (non-zero = true)
 
 
 def expand(x, shape):  # math.rs:2168-2248
-    x = _a(x)
-    tgt = np.broadcast_shapes(x.shape, tuple(int(s) for s in shape))
+    x = _a(x); shape = [int(s) for s in shape]; n = max(x.ndim, len(shape)); tgt = []
+    for i in range(n):                                   # right-aligned; 0 = "the input's size here" (math.rs:2189); two-way broadcast
+        d_in = x.shape[i - (n - x.ndim)] if i >= n - x.ndim else 1
+        d_t = shape[i - (n - len(shape))] if i >= n - len(shape) else 1
+        d_t = d_in if d_t == 0 else d_t
+        if d_in != d_t and d_in != 1 and d_t != 1:
+            raise ValueError(f"Expand: incompatible dimensions at dim index {i} (from left): in={d_in} target={d_t}")
+        tgt.append(d_in if d_t == 1 else d_t)
     return np.ascontiguousarray(np.broadcast_to(x, tgt))
 
 

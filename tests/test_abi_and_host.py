@@ -643,6 +643,16 @@ def test_reshape_and_squeeze_follow_the_reference_rules(so_path):
         if max(axes) < 3:
             assert np.expand_dims(v, tuple(axes)).shape == tuple(want)     # agrees with numpy wherever numpy accepts the axes
     assert list(K.flatten(np.zeros((2, 3, 4)), -1).shape) == [6, 4] and list(R.flatten(np.zeros((2, 3, 4)), -1).shape) == [6, 4]
+    for ish, tgt, want in (([3, 1], [3, 4], [3, 4]), ([1, 1, 3], [1, 2, 3], [1, 2, 3]), ([3], [2, 1], [2, 3]), ([2, 3], [0, 0], [2, 3]), ([2, 1], [0, 5], [2, 5]),
+                           ([4], [1], [4]), ([2, 3], [3, 1, 1], [3, 2, 3])):                                           # math.rs:2175-2204
+        assert MR.expand_shape(ish, tgt) == want, (ish, tgt)
+        assert list(R.expand(np.zeros(ish, np.float32), tgt).shape) == want
+    with pytest.raises(ValueError, match="Expand: incompatible dimensions at dim index 1"):
+        MR.expand_shape([2, 3], [2, 4])
+    with pytest.raises(ValueError, match="Expand: incompatible dimensions"):
+        R.expand(np.zeros((2, 3), np.float32), [2, 4])
+    with pytest.raises(LeleB200Error, match="Expand: incompatible dimensions"):
+        K.expand(np.zeros((2, 3), np.float32), [2, 4], ctx=object())
     one = np.ones((1, 1), np.float32)                                   # src/kernels/shape.rs:214-223
     assert R.squeeze(one, None).shape == () and K.squeeze(one).shape == () and K.unsqueeze(K.squeeze(one), [0]).shape == (1,)
 

@@ -162,3 +162,10 @@ def test_gather_with_scalar_index_drops_the_axis():
         assert g.shape == r.shape and g.ndim == 2
         np.testing.assert_array_equal(g, r)
     np.testing.assert_array_equal(G.gather(x, np.array([[2, -1]], np.int64), 1), MF.R.gather(x, np.array([[2, -1]], np.int64), 1))
+
+
+def test_expand_zero_means_input_dim_on_device():
+    """math.rs:2189: a 0 in the Expand target keeps the input's size at that position."""
+    x = np.arange(6, dtype=np.float32).reshape(2, 1, 3)
+    for tgt in ([0, 4, 0], [2, 4, 3], [5, 1, 1, 1], [0, 0, 0]):
+        np.testing.assert_array_equal(G.expand(x, tgt), MF.R.expand(x, tgt))
