@@ -600,6 +600,7 @@ def concat(inputs, axis, ctx=None):
 def pad(x, pads, constant_value=0.0, mode="constant", ctx=None):
     """manipulation.rs:382"""
     x = _f(x); r = x.ndim
+    if r > 4: raise LeleB200Error(f"Pad: Rank {r} not fully implemented (manipulation.rs:485)")
     p = [_b.max(int(v), 0) for v in pads]
     if len(p) < 2 * r:
         half = len(p) // 2; miss = r - half; full = [0] * (2 * r)
@@ -607,7 +608,7 @@ def pad(x, pads, constant_value=0.0, mode="constant", ctx=None):
             full[miss + i] = p[i]; full[r + miss + i] = p[half + i]
         p = full
     shp = [x.shape[i] + p[i] + p[i + r] for i in range(r)]
-    m = {"constant": 0, "edge": 1, "reflect": 2}[mode]
+    m = {"edge": 1, "reflect": 2}.get(mode, 0)     # any other mode string leaves the constant fill in place (manipulation.rs:487-491)
     return _run(tuple(shp), lambda c, o, px: call("lele_b200_pad", c.h, px, _ll(x.shape), i32(r), _ll(p), i32(m), f32(constant_value), o), x, ctx=ctx)
 
 
@@ -629,6 +630,7 @@ def gather_elements(data, indices, axis, ctx=None):
 def tile(x, repeats, ctx=None):
     """math.rs:2249"""
     x = _f(x); rep = [int(r) for r in repeats]
+    if len(rep) != x.ndim: raise LeleB200Error("Tile: repeats length must match input rank (math.rs:2256)")
     shp = [x.shape[i] * rep[i] for i in range(x.ndim)]
     return _run(tuple(shp), lambda c, o, px: call("lele_b200_tile", c.h, px, _ll(x.shape), _ll(rep), i32(x.ndim), o), x, ctx=ctx)
 

@@ -55,6 +55,8 @@ def slice_(x, starts, ends, axes=(), steps=()):  # manipulation.rs:209-381
 def pad(x, pads, value=0.0, mode="constant"):  # manipulation.rs:382-588
     x = _a(x)
     r = x.ndim
+    if r > 4:
+        raise ValueError(f"Pad: Rank {r} not fully implemented")   # manipulation.rs:485
     p = [max(int(v), 0) for v in pads]
     if len(p) < 2 * r:
         half = len(p) // 2
@@ -65,7 +67,7 @@ def pad(x, pads, value=0.0, mode="constant"):  # manipulation.rs:382-588
             full[r + miss + i] = p[half + i]
         p = full
     widths = [(p[i], p[i + r]) for i in range(r)]
-    if mode == "constant":
+    if mode not in ("edge", "reflect"):                             # only these two are special-cased (manipulation.rs:487-491)
         return np.pad(x, widths, mode="constant", constant_values=f32(value))
     return np.pad(x, widths, mode=mode)  # "edge" / "reflect" match numpy's definitions
 
@@ -116,7 +118,10 @@ def expand(x, shape):  # math.rs:2168-2248
 
 
 def tile(x, repeats):  # math.rs:2249-2300
-    return np.tile(_a(x), tuple(int(r) for r in repeats))
+    x = _a(x)
+    if len(repeats) != x.ndim:
+        raise ValueError("Tile: repeats length must match input rank")   # math.rs:2256
+    return np.tile(x, tuple(int(r) for r in repeats))
 
 
 def flatten(x, axis=1):  # shape.rs:105-120

@@ -668,6 +668,8 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
         ("splits sum mismatch", lambda: K.split(z(2, 6), 1, [2, 2], ctx=nothing)),                        # manipulation.rs:1173
         ("axis out of bounds", lambda: K.split(z(2, 6), 2, [6], ctx=nothing)),                             # manipulation.rs:1169
         ("element count mismatch", lambda: K.reshape(z(2, 3), [4])),                                       # shape.rs:48
+        ("repeats length must match input rank", lambda: K.tile(z(2, 3), [2], ctx=nothing)),              # math.rs:2256
+        ("Pad: Rank 5 not fully implemented", lambda: K.pad(z(1, 1, 1, 1, 2), [0] * 10, ctx=nothing)),    # manipulation.rs:485
         ("K mismatch", lambda: K.matmul(z(2, 3), z(4, 5), ctx=nothing)),                                   # gemm.rs:129
         ("Gemm K dim mismatch", lambda: K.gemm(z(2, 3), z(4, 5), ctx=nothing)),                            # gemm.rs:465
         ("only the last axis", lambda: K.softmax(z(2, 3), 0, ctx=nothing)),                                # norm.rs:218
@@ -679,7 +681,9 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
     for msg, fn in cases:
         with pytest.raises(LeleB200Error, match=msg):
             fn()
-    for msg, fn in (("splits sum mismatch", lambda: R.split(z(2, 6), 1, [2, 2])), ("element count mismatch", lambda: R.reshape(z(2, 3), [4]))):
+    np.testing.assert_array_equal(R.pad(z(2), [1, 1], 3.0, "wrap"), [3.0, 0.0, 0.0, 3.0])                      # unknown mode = constant fill
+    for msg, fn in (("splits sum mismatch", lambda: R.split(z(2, 6), 1, [2, 2])), ("element count mismatch", lambda: R.reshape(z(2, 3), [4])),
+                    ("repeats length must match", lambda: R.tile(z(2, 3), [2])), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
         with pytest.raises(ValueError, match=msg):
             fn()
 
