@@ -578,8 +578,8 @@ def concat(inputs, axis, ctx=None):
         return np.zeros((0,), np.float32)
     ax = axis % ne[0].ndim
     for a in ne:
-        if a.ndim != ne[0].ndim or any(a.shape[i] != ne[0].shape[i] for i in range(a.ndim) if i != ax):
-            raise LeleB200Error("concat: rank / non-axis dims must match (manipulation.rs:130)")
+        if a.ndim != ne[0].ndim: raise LeleB200Error("Concat: ranks mismatch (manipulation.rs:159)")
+        if any(a.shape[i] != ne[0].shape[i] for i in range(a.ndim) if i != ax): raise LeleB200Error("Concat: inner dim mismatch (manipulation.rs:162)")
     outer = _prod(ne[0].shape[:ax]); inner = _prod(ne[0].shape[ax + 1:])
     total_ax = sum(a.shape[ax] for a in ne)
     shp = list(ne[0].shape); shp[ax] = total_ax

@@ -18,7 +18,15 @@ def _a(x):
 # ---- manipulation.rs ----
 def concat(xs, axis):  # manipulation.rs:108-207 (empty inputs skipped)
     xs = [_a(x) for x in xs if np.asarray(x).size > 0]
-    return np.concatenate(xs, axis=axis)
+    if not xs:
+        return np.zeros((0,), np.float32)                       # TensorView::empty(), manipulation.rs:131-144
+    ax = axis + xs[0].ndim if axis < 0 else axis
+    for x in xs:
+        if x.ndim != xs[0].ndim:
+            raise ValueError("Concat: ranks mismatch")          # manipulation.rs:159
+        if any(x.shape[d] != xs[0].shape[d] for d in range(x.ndim) if d != ax):
+            raise ValueError("Concat: inner dim mismatch")      # manipulation.rs:162
+    return np.concatenate(xs, axis=ax)
 
 
 def _slice_bounds(dim, start, end, step):  # manipulation.rs:268-330

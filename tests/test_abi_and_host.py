@@ -669,6 +669,8 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
         ("axis out of bounds", lambda: K.split(z(2, 6), 2, [6], ctx=nothing)),                             # manipulation.rs:1169
         ("element count mismatch", lambda: K.reshape(z(2, 3), [4])),                                       # shape.rs:48
         ("repeats length must match input rank", lambda: K.tile(z(2, 3), [2], ctx=nothing)),              # math.rs:2256
+        ("Concat: ranks mismatch", lambda: K.concat([z(2, 3), z(3)], 0, ctx=nothing)),                     # manipulation.rs:159
+        ("Concat: inner dim mismatch", lambda: K.concat([z(2, 3), z(2, 4), z(0)], 0, ctx=nothing)),        # manipulation.rs:162
         ("Pad: Rank 5 not fully implemented", lambda: K.pad(z(1, 1, 1, 1, 2), [0] * 10, ctx=nothing)),    # manipulation.rs:485
         ("K mismatch", lambda: K.matmul(z(2, 3), z(4, 5), ctx=nothing)),                                   # gemm.rs:129
         ("Gemm K dim mismatch", lambda: K.gemm(z(2, 3), z(4, 5), ctx=nothing)),                            # gemm.rs:465
@@ -682,8 +684,11 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
         with pytest.raises(LeleB200Error, match=msg):
             fn()
     np.testing.assert_array_equal(R.pad(z(2), [1, 1], 3.0, "wrap"), [3.0, 0.0, 0.0, 3.0])                      # unknown mode = constant fill
+    assert R.concat([z(0), z(0)], 0).shape == (0,) and K.concat([z(0), z(0)], 0, ctx=nothing).shape == (0,)       # manipulation.rs:131-144
+    assert R.concat([z(0), z(2, 3), z(1, 3)], -2).shape == (3, 3)
     for msg, fn in (("splits sum mismatch", lambda: R.split(z(2, 6), 1, [2, 2])), ("element count mismatch", lambda: R.reshape(z(2, 3), [4])),
-                    ("repeats length must match", lambda: R.tile(z(2, 3), [2])), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
+                    ("repeats length must match", lambda: R.tile(z(2, 3), [2])), ("Concat: ranks mismatch", lambda: R.concat([z(2, 3), z(3)], 0)),
+                    ("Concat: inner dim mismatch", lambda: R.concat([z(2, 3), z(2, 4)], 0)), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
         with pytest.raises(ValueError, match=msg):
             fn()
 
