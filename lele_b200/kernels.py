@@ -312,12 +312,16 @@ def resize_nearest(input, scales=None, sizes=None, coordinate_transform_mode="as
     """conv2d.rs:1261"""
     x = _f(input); nb, c, h, w = x.shape
     if sizes is not None:
+        if len(sizes) < 4: raise LeleB200Error("Resize: sizes must have at least 4 elements (conv2d.rs:1301)")
+        if not (sizes[2] > 0 and sizes[3] > 0): raise LeleB200Error("Resize: sizes H and W must be positive (conv2d.rs:1305)")
         oh, ow = int(sizes[2]), int(sizes[3])
     elif scales is not None:
         sh = np.float32(scales[2]) if len(scales) >= 3 else np.float32(1); sw = np.float32(scales[3]) if len(scales) >= 4 else np.float32(1)
+        if not (sh > 0 and sw > 0): raise LeleB200Error("Resize: scales must be positive (conv2d.rs:1312)")
         oh, ow = int(np.float64(h) * np.float64(sh)), int(np.float64(w) * np.float64(sw))
     else:
         raise LeleB200Error("Resize: either scales or sizes must be provided (conv2d.rs:1318)")
+    if not (oh > 0 and ow > 0): raise LeleB200Error(f"Resize: output dimensions must be positive, got out_h={oh} out_w={ow} (conv2d.rs:1323)")
     mode = 0 if coordinate_transform_mode == "asymmetric" else 1
     return _run((nb, c, oh, ow), lambda cx, o, px: call("lele_b200_resize_nearest", cx.h, px, i32(nb), i32(c), i32(h), i32(w), i32(oh), i32(ow), i32(mode), o), x, ctx=ctx)
 

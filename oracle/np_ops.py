@@ -204,11 +204,21 @@ def resize_nearest(x, scales=None, sizes=None, mode="asymmetric"):  # conv2d.rs:
     x = _a(x)
     n, c, h, w = x.shape
     if sizes is not None:
+        if len(sizes) < 4:
+            raise ValueError("Resize: sizes must have at least 4 elements")        # conv2d.rs:1301
+        if not (sizes[2] > 0 and sizes[3] > 0):
+            raise ValueError("Resize: sizes H and W must be positive")             # conv2d.rs:1305 (test at :3619)
         oh, ow = int(sizes[2]), int(sizes[3])
-    else:
+    elif scales is not None:
         sh = scales[2] if len(scales) >= 3 else 1.0
         sw = scales[3] if len(scales) >= 4 else 1.0
+        if not (sh > 0 and sw > 0):
+            raise ValueError("Resize: scales must be positive")                    # conv2d.rs:1312
         oh, ow = int(np.float64(h) * np.float64(f32(sh))), int(np.float64(w) * np.float64(f32(sw)))
+    else:
+        raise ValueError("Resize: either scales or sizes must be provided")        # conv2d.rs:1318
+    if not (oh > 0 and ow > 0):
+        raise ValueError(f"Resize: output dimensions must be positive, got out_h={oh} out_w={ow}")   # conv2d.rs:1323
     hs, ws = f32(h) / f32(oh), f32(w) / f32(ow)
 
     def src(o, scale, lim):

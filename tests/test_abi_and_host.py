@@ -669,6 +669,10 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
         ("axis out of bounds", lambda: K.split(z(2, 6), 2, [6], ctx=nothing)),                             # manipulation.rs:1169
         ("element count mismatch", lambda: K.reshape(z(2, 3), [4])),                                       # shape.rs:48
         ("repeats length must match input rank", lambda: K.tile(z(2, 3), [2], ctx=nothing)),              # math.rs:2256
+        ("sizes H and W must be positive", lambda: K.resize_nearest(z(1, 1, 1, 1), None, [1, 1, -1, 10], ctx=nothing)),   # conv2d.rs:3619 (should_panic test)
+        ("scales must be positive", lambda: K.resize_nearest(z(1, 1, 2, 2), [1, 1, 0.0, 2.0], ctx=nothing)),             # conv2d.rs:1312
+        ("either scales or sizes", lambda: K.resize_nearest(z(1, 1, 2, 2), ctx=nothing)),                                 # conv2d.rs:1318
+        ("output dimensions must be positive", lambda: K.resize_nearest(z(1, 1, 2, 2), [1, 1, 0.25, 1.0], ctx=nothing)),  # conv2d.rs:1323
         ("Concat: ranks mismatch", lambda: K.concat([z(2, 3), z(3)], 0, ctx=nothing)),                     # manipulation.rs:159
         ("Concat: inner dim mismatch", lambda: K.concat([z(2, 3), z(2, 4), z(0)], 0, ctx=nothing)),        # manipulation.rs:162
         ("Pad: Rank 5 not fully implemented", lambda: K.pad(z(1, 1, 1, 1, 2), [0] * 10, ctx=nothing)),    # manipulation.rs:485
@@ -688,7 +692,8 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
     assert R.concat([z(0), z(2, 3), z(1, 3)], -2).shape == (3, 3)
     for msg, fn in (("splits sum mismatch", lambda: R.split(z(2, 6), 1, [2, 2])), ("element count mismatch", lambda: R.reshape(z(2, 3), [4])),
                     ("repeats length must match", lambda: R.tile(z(2, 3), [2])), ("Concat: ranks mismatch", lambda: R.concat([z(2, 3), z(3)], 0)),
-                    ("Concat: inner dim mismatch", lambda: R.concat([z(2, 3), z(2, 4)], 0)), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
+                    ("Concat: inner dim mismatch", lambda: R.concat([z(2, 3), z(2, 4)], 0)),
+                    ("sizes H and W must be positive", lambda: R.resize_nearest(z(1, 1, 1, 1), None, [1, 1, -1, 10])), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
         with pytest.raises(ValueError, match=msg):
             fn()
 
