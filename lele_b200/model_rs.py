@@ -659,7 +659,11 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
         elif op == "reduce_max":
             r = ops.reduce(a[0], a[1], a[2], "max")
         elif op == "topk":                            # (x, k, axis, largest, sorted): last axis, descending, stable (conv2d.rs:1385)
-            r = ops.topk(a[0], a[1])
+            if len(a) > 3 and a[3] is False:          # largest = false: ascending stable order = the descending stable order of -x
+                v, i = ops.topk(ops.unary("neg", a[0]), a[1])
+                r = (ops.unary("neg", v), i)
+            else:
+                r = ops.topk(a[0], a[1])
         elif op == "tile":
             r = ops.tile(a[0], a[1])
         elif op == "gather_elements":

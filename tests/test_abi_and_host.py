@@ -698,6 +698,28 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
             fn()
 
 
+def test_model_rs_topk_smallest():
+    """TopK with largest = false (conv2d.rs:1421): ascending, ties in original order; k clamps to the axis length."""
+    from tests import model_forms as MF
+    m = _model_rs()
+    text = """
+pub struct TkWorkspace { pub buf_0: Vec<f32>, pub buf_1: Vec<f32>, }
+pub struct Tk<'a> { data: &'a [u8] }
+    fn run_chunk_0<'w>(&self, ws: &'w mut TkWorkspace, x: TensorView<'w, f32>) -> (TensorView<'static, f32>, TensorView<'static, f32>, TensorView<'static, f32>) {
+        let (lo, lo_i) = lele::kernels::topk(&x, self.weight_i64(0, 8, &[1]).data[0] as usize, -1, false, true, &mut ws.buf_0, &mut ws.buf_1);
+        let (hi, hi_i) = lele::kernels::topk(&x, self.weight_i64(8, 8, &[1]).data[0] as usize, -1, true, true, &mut ws.buf_0, &mut ws.buf_1);
+        (lo.to_owned(), lo_i.to_owned(), hi.to_owned())
+    }
+"""
+    prog = m.parse_model_rs(text)
+    blob = m.synth_blob(prog, 1, {0: [3], 8: [9]})
+    x = np.array([[2.0, -1.0, 2.0, 0.5, -1.0], [0.0, -0.0, 5.0, -3.0, 5.0]], np.float32)
+    lo, lo_i, hi = m.run_program(prog, blob, [x], MF.R)
+    np.testing.assert_array_equal(lo, [[-1.0, -1.0, 0.5], [-3.0, 0.0, 0.0]])
+    np.testing.assert_array_equal(lo_i, [[1, 4, 3], [3, 0, 1]])
+    np.testing.assert_array_equal(hi, [[2.0, 2.0, 0.5, -1.0, -1.0], [5.0, 5.0, 0.0, 0.0, -3.0]])       # k = 9 clamps to 5
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
