@@ -127,10 +127,14 @@ def _lead(a, b):
 def matmul(a, b, ctx=None):
     """gemm.rs:112"""
     a, b = _f(a), _f(b)
+    if a.ndim < 2 or b.ndim < 2:
+        raise LeleB200Error("MatMul: both operands need rank >= 2 (gemm.rs:122-123)")
     if a.shape[-1] != b.shape[-2]:
-        raise LeleB200Error(f"matmul: K mismatch {a.shape} x {b.shape} (gemm.rs:129)")
+        raise LeleB200Error(f"MatMul K dim mismatch: {a.shape[-1]} vs {b.shape[-2]} (gemm.rs:129)")
     m, k = a.shape[-2:]; n = b.shape[-1]
     ba, bb, lead = _lead(a, b)
+    if not (bb == 1 or bb == ba):
+        raise LeleB200Error("MatMul broadcast not fully supported yet (gemm.rs:134)")
     return _run(tuple(lead) + (m, n), lambda c, o, pa, pb: call("lele_b200_matmul", c.h, pa, pb, i32(ba), i32(bb), i32(m), i32(k), i32(n), o), a, b, ctx=ctx)
 
 

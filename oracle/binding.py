@@ -158,9 +158,15 @@ def fused_quantized_linear(x, w_u8, w_scale, w_zp, bias, relu=False):
 # ---- gemm ----
 def matmul(a, b):
     a = _f(a); b = _f(b)
+    if a.ndim < 2 or b.ndim < 2:
+        raise ValueError("MatMul: both operands need rank >= 2")                               # gemm.rs:122-123
     m, k = a.shape[-2:]; n = b.shape[-1]
+    if k != b.shape[-2]:
+        raise ValueError(f"MatMul K dim mismatch: {k} vs {b.shape[-2]}")                        # gemm.rs:129
     ba = int(np.prod(a.shape[:-2])) if a.ndim > 2 else 1
     bb = int(np.prod(b.shape[:-2])) if b.ndim > 2 else 1
+    if not (bb == 1 or bb == ba):
+        raise ValueError("MatMul broadcast not fully supported yet")                           # gemm.rs:134
     lead = a.shape[:-2] if ba >= bb else b.shape[:-2]
     out = np.empty(tuple(lead) + (m, n), np.float32)
     lib().lo_matmul(_p(a), _p(b), C.c_int(ba), C.c_int(bb), C.c_int(m), C.c_int(k), C.c_int(n), _p(out))

@@ -676,7 +676,9 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
         ("Concat: ranks mismatch", lambda: K.concat([z(2, 3), z(3)], 0, ctx=nothing)),                     # manipulation.rs:159
         ("Concat: inner dim mismatch", lambda: K.concat([z(2, 3), z(2, 4), z(0)], 0, ctx=nothing)),        # manipulation.rs:162
         ("Pad: Rank 5 not fully implemented", lambda: K.pad(z(1, 1, 1, 1, 2), [0] * 10, ctx=nothing)),    # manipulation.rs:485
-        ("K mismatch", lambda: K.matmul(z(2, 3), z(4, 5), ctx=nothing)),                                   # gemm.rs:129
+        ("MatMul K dim mismatch: 3 vs 4", lambda: K.matmul(z(2, 3), z(4, 5), ctx=nothing)),                # gemm.rs:129
+        ("MatMul broadcast not fully supported yet", lambda: K.matmul(z(2, 3), z(4, 3, 5), ctx=nothing)),  # gemm.rs:134
+        ("rank >= 2", lambda: K.matmul(z(3), z(3, 5), ctx=nothing)),                                       # gemm.rs:122
         ("Gemm K dim mismatch", lambda: K.gemm(z(2, 3), z(4, 5), ctx=nothing)),                            # gemm.rs:465
         ("only the last axis", lambda: K.softmax(z(2, 3), 0, ctx=nothing)),                                # norm.rs:218
         ("Only batch_size=1", lambda: K.lstm(z(2, 2, 4), z(1, 8, 4), z(1, 8, 2), ctx=nothing)),            # rnn.rs:88
@@ -693,7 +695,8 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
     for msg, fn in (("splits sum mismatch", lambda: R.split(z(2, 6), 1, [2, 2])), ("element count mismatch", lambda: R.reshape(z(2, 3), [4])),
                     ("repeats length must match", lambda: R.tile(z(2, 3), [2])), ("Concat: ranks mismatch", lambda: R.concat([z(2, 3), z(3)], 0)),
                     ("Concat: inner dim mismatch", lambda: R.concat([z(2, 3), z(2, 4)], 0)),
-                    ("sizes H and W must be positive", lambda: R.resize_nearest(z(1, 1, 1, 1), None, [1, 1, -1, 10])), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
+                    ("sizes H and W must be positive", lambda: R.resize_nearest(z(1, 1, 1, 1), None, [1, 1, -1, 10])),
+                    ("MatMul K dim mismatch: 3 vs 4", lambda: R.matmul(z(2, 3), z(4, 5))), ("broadcast not fully supported", lambda: R.matmul(z(2, 3), z(4, 3, 5))), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
         with pytest.raises(ValueError, match=msg):
             fn()
 
