@@ -600,8 +600,8 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
         elif op == "mat_mul_integer":                 # (a, b, a_zero_point, b_zero_point)  ops/math.rs:43; zero points are scalar tensors
             zp = [0.0 if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z in (a[2], a[3])]
             r = ops.mat_mul_integer(a[0], a[1], zp[0], zp[1])
-        elif op == "clip":                            # (x, min, max): scalar tensors, None = the f32 range (math.rs:1984)
-            lim = [d if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z, d in ((a[1], float(np.finfo(np.float32).min)), (a[2], float(np.finfo(np.float32).max)))]
+        elif op == "clip":                            # (x, min, max): scalar tensors; a missing bound is -inf / +inf (math.rs:15-20, :1990-1997)
+            lim = [d if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z, d in ((a[1], float("-inf")), (a[2], float("inf")))]
             r = ops.clip(a[0], lim[0], lim[1])
         elif op == "batch_norm":                      # (x, scale, bias, mean, var, epsilon)  ops/nn.rs:352
             r = ops.batch_norm(a[0], a[1], a[2], a[3], a[4], a[5])

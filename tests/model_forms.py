@@ -127,7 +127,7 @@ def quant_forms_direct(m, blob, x):
     c = R.fused_quantized_linear(b, W("u8", 704, 384, [24, 16]), W("f32", 1088, 64, [16]), 121, W("f32", 1156, 64, [16]), False)
     q, qs, qz = R.dynamic_quantize_linear(c)
     d = R.mat_mul_integer(q, W("u8", 1220, 384, [16, 24]), float(qz), 130.0)
-    f = R.clip(R.mul(d, qs), -1.5, float(np.finfo(np.float32).max))
+    f = R.clip(R.mul(d, qs), -1.5, float("inf"))
     g = R.matmul_fused_add(f, W("f32", 1612, 768, [24, 8]), W("f32", 2380, 32, [8]))
     return g, d
 
