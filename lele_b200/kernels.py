@@ -431,7 +431,10 @@ def div(a, b, ctx=None): return _binary("div", a, b, ctx)
 def max(a, b, ctx=None): return _binary("max", a, b, ctx)  # noqa: A001 (lele::kernels::max)
 def pow(a, b, ctx=None): return _binary("pow", a, b, ctx)  # noqa: A001
 def mod_f32(a, b, ctx=None): return _binary("mod_f32", a, b, ctx)
-def prelu(a, slope, ctx=None): return _binary("prelu", a, slope, ctx)
+def prelu(a, slope, ctx=None):
+    """math.rs:2012: a one-element slope keeps the input's shape whatever the slope's rank; otherwise NumPy broadcasting"""
+    s = _f(slope)
+    return _binary("prelu", a, s.reshape(1) if s.size == 1 else s, ctx)
 def equal(a, b, ctx=None): return _binary("equal", a, b, ctx)
 def less(a, b, ctx=None): return _binary("less", a, b, ctx)
 def relu(x, ctx=None): return _unary("relu", x, ctx)

@@ -265,9 +265,11 @@ def mod_f32(a, b):  # math.rs:1163-1192 : a - b*floor(a/b), 0 when b == 0
     return np.where(b == 0, f32(0), r).astype(np.float32)
 
 
-def prelu(x, slope):  # math.rs:2012
-    x = _a(x)
-    return np.where(x < 0, x * _a(slope), x).astype(np.float32)
+def prelu(x, slope):  # math.rs:2012: a one-element slope keeps the input's shape (:2017-2028), otherwise broadcasting
+    x = _a(x); s = _a(slope)
+    if s.size == 1:
+        s = s.reshape(1)
+    return np.where(x < 0, x * s, x).astype(np.float32)
 
 
 def reduce(x, axes, keepdims, kind):  # math.rs:1527-1921
