@@ -274,7 +274,10 @@ def conv1d(input, weights, bias=None, dilations=(1,), group=1, pads=(0, 0), stri
 def _conv2d(x, w, bias, dilations, group, pads, strides, act, ctx):
     x, w = _f(x), _f(w); nb, ic, h, wd = x.shape; oc, _, kh, kw = w.shape
     p = _pads4(pads); s = list(strides) or [1, 1]; d = list(dilations) or [1, 1]
-    oh = (h + p[0] + p[2] - d[0] * (kh - 1) - 1) // s[0] + 1; ow = (wd + p[1] + p[3] - d[1] * (kw - 1) - 1) // s[1] + 1
+    eh = h + p[0] + p[2] - d[0] * (kh - 1) - 1; ew = wd + p[1] + p[3] - d[1] * (kw - 1) - 1
+    oh = eh // s[0] + 1; ow = ew // s[1] + 1
+    if eh < 0 or ew < 0 or oh <= 0 or ow <= 0:   # upstream the unsigned subtraction overflows or the assertion fires (conv2d.rs:274-291)
+        raise LeleB200Error(f"conv2d: output dimensions must be positive, got out_h={oh} out_w={ow} (conv2d.rs:288)")
     bi = None if bias is None else _f(bias)
     return _run((nb, oc, oh, ow), lambda c, o, px, pw, pb: call("lele_b200_conv2d", c.h, px, pw, pb, i32(nb), i32(ic), i32(h), i32(wd), i32(oc), i32(kh), i32(kw), i32(group), _ints(p), _ints(s), _ints(d), i32(act), o), x, w, bi, ctx=ctx)
 

@@ -257,6 +257,8 @@ def conv2d(x, w, bias=None, dilations=(1, 1), group=1, pads=(0, 0, 0, 0), stride
     oh = C.c_int(); ow = C.c_int()
     lib().lo_conv2d(_p(x), _p(w), None, C.c_int(nb), C.c_int(ic), C.c_int(h), C.c_int(wd), C.c_int(oc), C.c_int(kh), C.c_int(kw),
                     C.c_int(group), p, s, d, C.c_int(act), None, C.byref(oh), C.byref(ow))
+    if oh.value <= 0 or ow.value <= 0 or h + p[0] + p[2] - d[0] * (kh - 1) - 1 < 0 or wd + p[1] + p[3] - d[1] * (kw - 1) - 1 < 0:
+        raise ValueError(f"conv2d: output dimensions must be positive, got out_h={oh.value} out_w={ow.value}")   # conv2d.rs:274-291
     out = np.empty((nb, oc, oh.value, ow.value), np.float32)
     bi = None if bias is None else _f(bias)
     lib().lo_conv2d(_p(x), _p(w), _p(bi), C.c_int(nb), C.c_int(ic), C.c_int(h), C.c_int(wd), C.c_int(oc), C.c_int(kh), C.c_int(kw),
@@ -270,6 +272,8 @@ def conv_transpose(x, w, bias=None, dilations=(1, 1), pads=(0, 0, 0, 0), strides
     oh = C.c_int(); ow = C.c_int()
     lib().lo_conv_transpose(_p(x), _p(w), None, C.c_int(nb), C.c_int(ic), C.c_int(h), C.c_int(wd), C.c_int(oc), C.c_int(kh), C.c_int(kw),
                             p, s, d, None, C.byref(oh), C.byref(ow))
+    if oh.value <= 0 or ow.value <= 0 or h + p[0] + p[2] - d[0] * (kh - 1) - 1 < 0 or wd + p[1] + p[3] - d[1] * (kw - 1) - 1 < 0:
+        raise ValueError(f"conv2d: output dimensions must be positive, got out_h={oh.value} out_w={ow.value}")   # conv2d.rs:274-291
     out = np.empty((nb, oc, oh.value, ow.value), np.float32)
     bi = None if bias is None else _f(bias)
     lib().lo_conv_transpose(_p(x), _p(w), _p(bi), C.c_int(nb), C.c_int(ic), C.c_int(h), C.c_int(wd), C.c_int(oc), C.c_int(kh), C.c_int(kw),

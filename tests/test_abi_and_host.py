@@ -673,6 +673,7 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
         ("scales must be positive", lambda: K.resize_nearest(z(1, 1, 2, 2), [1, 1, 0.0, 2.0], ctx=nothing)),             # conv2d.rs:1312
         ("either scales or sizes", lambda: K.resize_nearest(z(1, 1, 2, 2), ctx=nothing)),                                 # conv2d.rs:1318
         ("output dimensions must be positive", lambda: K.resize_nearest(z(1, 1, 2, 2), [1, 1, 0.25, 1.0], ctx=nothing)),  # conv2d.rs:1323
+        ("conv2d: output dimensions must be positive", lambda: K.conv2d(z(1, 1, 2, 2), z(1, 1, 3, 3), ctx=nothing)),       # conv2d.rs:288
         ("Concat: ranks mismatch", lambda: K.concat([z(2, 3), z(3)], 0, ctx=nothing)),                     # manipulation.rs:159
         ("Concat: inner dim mismatch", lambda: K.concat([z(2, 3), z(2, 4), z(0)], 0, ctx=nothing)),        # manipulation.rs:162
         ("Pad: Rank 5 not fully implemented", lambda: K.pad(z(1, 1, 1, 1, 2), [0] * 10, ctx=nothing)),    # manipulation.rs:485
@@ -696,6 +697,7 @@ def test_precondition_failures_raise_before_any_device_work(so_path):
                     ("repeats length must match", lambda: R.tile(z(2, 3), [2])), ("Concat: ranks mismatch", lambda: R.concat([z(2, 3), z(3)], 0)),
                     ("Concat: inner dim mismatch", lambda: R.concat([z(2, 3), z(2, 4)], 0)),
                     ("sizes H and W must be positive", lambda: R.resize_nearest(z(1, 1, 1, 1), None, [1, 1, -1, 10])),
+                    ("conv2d: output dimensions must be positive", lambda: R.conv2d(z(1, 1, 2, 2), z(1, 1, 3, 3))),
                     ("MatMul K dim mismatch: 3 vs 4", lambda: R.matmul(z(2, 3), z(4, 5))), ("broadcast not fully supported", lambda: R.matmul(z(2, 3), z(4, 3, 5))), ("Rank 5 not fully implemented", lambda: R.pad(z(1, 1, 1, 1, 2), [0] * 10))):
         with pytest.raises(ValueError, match=msg):
             fn()
