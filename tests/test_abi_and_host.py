@@ -725,6 +725,87 @@ pub struct Tk<'a> { data: &'a [u8] }
     np.testing.assert_array_equal(hi, [[2.0, 2.0, 0.5, -1.0, -1.0], [5.0, 5.0, 0.0, 0.0, -3.0]])       # k = 9 clamps to 5
 
 
+def test_host_wrappers_marshal_and_shape_like_the_oracle(so_path, monkeypatch):
+    """Every lele_b200.kernels wrapper is run with a stand-in context and a recording `call` (no device): the Python side must get
+    through its shape logic, hand the C entry point exactly as many arguments as its prototype declares, size its output buffer for
+    what it downloads, and return the shape the oracle returns for the same inputs."""
+    import importlib.util
+    from lele_b200 import kernels as K
+    from oracle import reference_api as R
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "tools", "gen_rust_ffi.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    nargs = {name: len(args) for _, name, args in g.c_declarations(open(os.path.join(ROOT, "include", "lele_b200.h")).read())}
+    seen = []
+
+    def fake_call(name, *args):
+        assert len(args) == nargs[name], (name, len(args), nargs[name])
+        seen.append(name)
+
+    class Buf:
+        def __init__(self, n): self.ptr, self.n = 4096, n
+        def free(self): pass
+
+    class Ctx:
+        h = None
+        def upload(self, a, dtype=np.float32): return Buf(np.asarray(a).size)
+        def empty(self, n, itemsize=4): return Buf(int(n))
+        def download(self, b, shape, dtype=np.float32):
+            assert int(np.prod(shape, dtype=np.int64)) <= max(b.n, 1), (shape, b.n)
+            return np.zeros(shape, dtype)
+        def sync(self): pass
+
+    monkeypatch.setattr(K, "call", fake_call)
+    ctx = Ctx()
+    z = lambda *s: np.zeros(s, np.float32)
+    o = lambda *s: np.ones(s, np.float32)
+    cases = [   # (device-wrapper call, oracle call)
+        (lambda: K.matmul(z(3, 4, 5), z(5, 6), ctx=ctx), lambda: R.matmul(z(3, 4, 5), z(5, 6))),
+        (lambda: K.matmul_fused_add(z(4, 5), z(5, 6), z(6), ctx=ctx), lambda: R.matmul_fused_add(z(4, 5), z(5, 6), z(6))),
+        (lambda: K.gemm(z(5, 4), z(6, 5), z(6), 1.0, 1.0, True, True, ctx=ctx), lambda: R.gemm(z(5, 4), z(6, 5), z(6), 1.0, 1.0, True, True)),
+        (lambda: K.layer_norm(z(2, 3, 8), o(8), z(8), -1, 1e-5, ctx=ctx), lambda: R.layer_norm(z(2, 3, 8), o(8), z(8), -1, 1e-5)),
+        (lambda: K.softmax(z(2, 7), -1, ctx=ctx), lambda: R.softmax(z(2, 7), -1)),
+        (lambda: K.batch_norm(z(2, 3, 4), o(3), z(3), z(3), o(3), ctx=ctx), lambda: R.batch_norm(z(2, 3, 4), o(3), z(3), z(3), o(3))),
+        (lambda: K.dynamic_quantize_linear(o(2, 5), ctx=ctx)[0], lambda: R.dynamic_quantize_linear(o(2, 5))[0]),
+        (lambda: K.mat_mul_integer(z(2, 3, 4), z(4, 5), 1.0, 2.0, ctx=ctx), lambda: R.mat_mul_integer(z(2, 3, 4), z(4, 5), 1.0, 2.0)),
+        (lambda: K.fused_quantized_linear(z(2, 5, 16), z(16, 24), o(24), np.array([128.0], np.float32), z(24), True, ctx=ctx),
+         lambda: R.fused_quantized_linear(z(2, 5, 16), z(16, 24), o(24), 128, z(24), True)),
+        (lambda: K.conv1d_fused(z(1, 2, 9), z(4, 2, 3), z(4), [1], 1, [1, 1], [2], True, ctx=ctx), lambda: R.conv1d(z(1, 2, 9), z(4, 2, 3), z(4), [1], 1, [1, 1], [2], True)),
+        (lambda: K.conv2d(z(1, 2, 7, 8), z(3, 2, 3, 3), None, (1, 1), 1, (1, 1, 1, 1), (2, 2), ctx=ctx), lambda: R.conv2d(z(1, 2, 7, 8), z(3, 2, 3, 3), None, (1, 1), 1, (1, 1, 1, 1), (2, 2))),
+        (lambda: K.conv_transpose(z(1, 2, 4, 4), z(2, 3, 3, 3), None, (1, 1), (1, 1, 1, 1), (2, 2), ctx=ctx), lambda: R.conv_transpose(z(1, 2, 4, 4), z(2, 3, 3, 3), None, (1, 1), (1, 1, 1, 1), (2, 2))),
+        (lambda: K.max_pool2d(z(1, 2, 7, 8), (3, 2), (1, 0, 1, 0), (2, 2), (1, 1), True, ctx=ctx), lambda: R.max_pool2d(z(1, 2, 7, 8), (3, 2), (1, 0, 1, 0), (2, 2), (1, 1), True)),
+        (lambda: K.resize_nearest(z(1, 2, 3, 4), [1, 1, 2.0, 1.5], None, "asymmetric", ctx=ctx), lambda: R.resize_nearest(z(1, 2, 3, 4), [1, 1, 2.0, 1.5], None, "asymmetric")),
+        (lambda: K.lstm(z(5, 1, 3), z(1, 16, 3), z(1, 16, 4), z(1, 32), None, z(1, 1, 4), z(1, 1, 4), ctx=ctx)[0], lambda: R.lstm(z(5, 1, 3), z(1, 16, 3), z(1, 16, 4), z(1, 32), z(1, 1, 4), z(1, 1, 4))[0]),
+        (lambda: K.gru(z(5, 1, 3), z(1, 12, 3), z(1, 12, 4), None, None, ctx=ctx)[1], lambda: R.gru(z(5, 1, 3), z(1, 12, 3), z(1, 12, 4), None, None)[1]),
+        (lambda: K.add(z(3, 1, 5), z(4, 5), ctx=ctx), lambda: R.add(z(3, 1, 5), z(4, 5))),
+        (lambda: K.prelu(z(2, 3), o(1, 1, 1), ctx=ctx), lambda: R.prelu(z(2, 3), o(1, 1, 1))),
+        (lambda: K.tanh_kernel(z(7), ctx=ctx), lambda: R.tanh(z(7))),
+        (lambda: K.not_(z(2, 2), ctx=ctx), lambda: R.not_(z(2, 2))),
+        (lambda: K.clip(z(4), -1.0, float("inf"), ctx=ctx), lambda: R.clip(z(4), -1.0, float("inf"))),
+        (lambda: K.reduce_sum(z(2, 3, 4), [0, 2], False, ctx=ctx), lambda: R.reduce(z(2, 3, 4), [0, 2], False, "sum")),
+        (lambda: K.reduce_l2(z(2, 3), [], True, ctx=ctx), lambda: R.reduce(z(2, 3), [], True, "l2")),
+        (lambda: K.reduce_max(z(2, 3), [1, -1], True, ctx=ctx), lambda: R.reduce(z(2, 3), [1, -1], True, "max")),
+        (lambda: K.where_op(o(3, 1), z(1, 4), z(3, 4), ctx=ctx), lambda: R.where(o(3, 1), z(1, 4), z(3, 4))),
+        (lambda: K.stft(z(1, 300), 64, 32, 64, None, False, ctx=ctx), lambda: R.stft(z(1, 300), 64, 32, 64, None, False)),
+        (lambda: K.stft(z(300), 64, 32, 64, o(64), True, ctx=ctx), lambda: R.stft(z(300), 64, 32, 64, o(64), True)),
+        (lambda: K.transpose(z(2, 3, 4), (2, 0, 1), ctx=ctx), lambda: R.transpose(z(2, 3, 4), (2, 0, 1))),
+        (lambda: K.slice(z(4, 6), [1], [2**63 - 1], [1], [2], ctx=ctx), lambda: R.slice(z(4, 6), [1], [2**63 - 1], [1], [2])),
+        (lambda: K.expand(z(2, 1, 3), [0, 4, 0], ctx=ctx), lambda: R.expand(z(2, 1, 3), [0, 4, 0])),
+        (lambda: K.split(z(2, 6), 1, [1, 5], ctx=ctx)[1], lambda: R.split(z(2, 6), 1, [1, 5])[1]),
+        (lambda: K.concat([z(2, 3), z(0), z(2, 1)], -1, ctx=ctx), lambda: R.concat([z(2, 3), z(0), z(2, 1)], -1)),
+        (lambda: K.pad(z(2, 3), [1, 2], 0.0, "edge", ctx=ctx), lambda: R.pad(z(2, 3), [1, 2], 0.0, "edge")),
+        (lambda: K.gather(z(2, 3, 4), np.array(1), 1, ctx=ctx), lambda: R.gather(z(2, 3, 4), np.array(1), 1)),
+        (lambda: K.gather_elements(z(2, 3), z(2, 2), 1, ctx=ctx), lambda: R.gather_elements(z(2, 3), z(2, 2), 1)),
+        (lambda: K.tile(z(2, 3), [2, 1], ctx=ctx), lambda: R.tile(z(2, 3), [2, 1])),
+        (lambda: K.topk(z(2, 9), 4, ctx=ctx)[1], lambda: R.topk(z(2, 9), 4)[1]),
+        (lambda: K.lstm_streams(z(3, 5, 2), z(1, 16, 2), z(1, 16, 4), None, z(3, 4), z(3, 4), ctx=ctx)[0], lambda: z(3, 5, 4)),
+        (lambda: K.gru_streams(z(3, 5, 2), z(1, 12, 2), z(1, 12, 4), z(1, 24), None, ctx=ctx)[1], lambda: z(3, 4)),
+    ]
+    for dev, ref in cases:
+        got, want = dev(), ref()
+        assert np.asarray(got).shape == np.asarray(want).shape, (seen[-1:], np.asarray(got).shape, np.asarray(want).shape)
+    assert len(set(seen)) >= 29, sorted(set(seen))
+
+
 def test_model_rs_shape_arithmetic_stays_on_the_host():
     """i64 shape tensors (Shape / Gather / Concat / Range / Less / Cast / ConstantOfShape / Size, `&t.data[..]`, temp_i64 vectors,
     inline to_i64_vec) are evaluated as host int64 values; only f32 tensor work reaches the operator namespace."""
