@@ -237,3 +237,49 @@ def test_reduce_axes_edge_semantics():  # math.rs:1611-1650 (same prologue in re
             np.testing.assert_array_equal(got, want)
     np.testing.assert_array_equal(R.reduce(x, [1, 1, -1], False, "sum"), [-1.0, 3.0])
     np.testing.assert_array_equal(R.reduce(x, [1, 0], False, "max"), 3.0)
+
+
+def _ref_lstm(x, w, r, b, h0, c0):
+    """ONNX LSTM, forward, no peepholes, gate order i, o, f, c (rnn.rs:67-230) in float64."""
+    x, w, r = x.astype(np.float64), w[0].astype(np.float64), r[0].astype(np.float64)
+    hs = r.shape[1]
+    wb, rb = (b[0, :4 * hs].astype(np.float64), b[0, 4 * hs:].astype(np.float64)) if b is not None else (np.zeros(4 * hs), np.zeros(4 * hs))
+    h = np.zeros(hs) if h0 is None else h0.reshape(-1).astype(np.float64)
+    c = np.zeros(hs) if c0 is None else c0.reshape(-1).astype(np.float64)
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    ys = []
+    for t in range(x.shape[0]):
+        g = w @ x[t, 0] + r @ h + wb + rb
+        i, o, f, cc = sig(g[:hs]), sig(g[hs:2 * hs]), sig(g[2 * hs:3 * hs]), np.tanh(g[3 * hs:])
+        c = f * c + i * cc
+        h = o * np.tanh(c)
+        ys.append(h.copy())
+    return np.array(ys), h, c
+
+
+@pytest.mark.parametrize("hs,isz,seq,with_state", [(4, 3, 1, False), (4, 3, 6, True), (20, 7, 9, True), (128, 64, 5, False)])
+def test_lstm_vs_float64_restatement(hs, isz, seq, with_state):
+    """An independent check of the LSTM semantics (gate order, bias split Wb | Rb, state hand-over): the oracle against the ONNX
+    formulas in float64, 1e-5 absolute (the first case is the reference's own test input, tests/regression_kernels.rs:977-984)."""
+    if (hs, isz, seq) == (4, 3, 1):
+        x = np.array([0.1, -0.2, 0.3], np.float32).reshape(1, 1, 3)
+        w = (np.arange(4 * hs * isz) * 0.01).astype(np.float32).reshape(1, 4 * hs, isz)
+        r = (np.arange(4 * hs * hs) * 0.02 - 0.1).astype(np.float32).reshape(1, 4 * hs, hs)
+        b = (np.arange(8 * hs) * 0.005).astype(np.float32).reshape(1, 8 * hs)
+    else:
+        rng = np.random.default_rng(hs + seq)
+        x = rng.standard_normal((seq, 1, isz)).astype(np.float32)
+        w = (rng.standard_normal((1, 4 * hs, isz)) / np.sqrt(isz)).astype(np.float32); r = (rng.standard_normal((1, 4 * hs, hs)) / np.sqrt(hs)).astype(np.float32)
+        b = (0.1 * rng.standard_normal((1, 8 * hs))).astype(np.float32)
+    h0 = c0 = None
+    if with_state:
+        rng = np.random.default_rng(99)
+        h0 = rng.standard_normal((1, 1, hs)).astype(np.float32); c0 = rng.standard_normal((1, 1, hs)).astype(np.float32)
+    y, h, c = R.lstm(x, w, r, b, h0, c0)
+    yr, hr, cr = _ref_lstm(x, w, r, b, h0, c0)
+    assert y.shape == (seq, 1, 1, hs) and h.shape == (1, 1, hs) and c.shape == (1, 1, hs)
+    np.testing.assert_allclose(y.reshape(seq, hs), yr, atol=1e-5, rtol=0)
+    np.testing.assert_allclose(h.reshape(hs), hr, atol=1e-5, rtol=0); np.testing.assert_allclose(c.reshape(hs), cr, atol=2e-5, rtol=0)
+    if b is not None:
+        y2, _, _ = R.lstm(x, w, r, None, h0, c0)
+        np.testing.assert_allclose(y2.reshape(seq, hs), _ref_lstm(x, w, r, None, h0, c0)[0], atol=1e-5, rtol=0)
