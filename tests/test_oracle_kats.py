@@ -283,3 +283,36 @@ def test_lstm_vs_float64_restatement(hs, isz, seq, with_state):
     if b is not None:
         y2, _, _ = R.lstm(x, w, r, None, h0, c0)
         np.testing.assert_allclose(y2.reshape(seq, hs), _ref_lstm(x, w, r, None, h0, c0)[0], atol=1e-5, rtol=0)
+
+
+def test_stft_vs_numpy_rfft():  # math.rs:2304-2370: default window = periodic Hann over win_length, zero beyond win / signal end
+    rng = np.random.default_rng(6)
+    sig = rng.standard_normal(700).astype(np.float32)
+    n_fft, hop, win = 128, 48, 96
+    got = R.stft(sig, n_fft, hop, win)
+    frames = (700 - win) // hop + 1
+    hann = 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(win) / win))
+    want = np.zeros((frames, n_fft // 2 + 1, 2))
+    for f in range(frames):
+        fr = np.zeros(n_fft); seg = sig[f * hop:f * hop + win].astype(np.float64); fr[:seg.size] = seg * hann[:seg.size]
+        sp = np.fft.rfft(fr); want[f, :, 0], want[f, :, 1] = sp.real, sp.imag
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, atol=2e-4)
+    w = rng.standard_normal(win).astype(np.float32)                         # explicit window
+    got = R.stft(sig, n_fft, hop, win, w, power=True)
+    for f in (0, frames - 1):
+        fr = np.zeros(n_fft); fr[:win] = sig[f * hop:f * hop + win].astype(np.float64) * w
+        np.testing.assert_allclose(got[f], np.abs(np.fft.rfft(fr)) ** 2, rtol=1e-3, atol=1e-3)
+
+
+def test_norms_vs_float64_formulas():  # norm.rs: batch_norm (per channel, inference form), rms_norm, softmax
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((2, 3, 5, 4)).astype(np.float32)
+    sc, bi, mu = (rng.standard_normal(3).astype(np.float32) for _ in range(3)); var = rng.uniform(0.5, 2.0, 3).astype(np.float32)
+    want = (x.astype(np.float64) - mu[None, :, None, None]) / np.sqrt(var[None, :, None, None].astype(np.float64) + 1e-5) * sc[None, :, None, None] + bi[None, :, None, None]
+    np.testing.assert_allclose(R.batch_norm(x, sc, bi, mu, var, 1e-5), want, atol=1e-5)
+    y = rng.standard_normal((7, 33)).astype(np.float32); g = rng.standard_normal(33).astype(np.float32)
+    want = y.astype(np.float64) / np.sqrt((y.astype(np.float64) ** 2).mean(-1, keepdims=True) + 1e-6) * g
+    np.testing.assert_allclose(R.rms_norm(y, g, 1e-6), want, atol=1e-5)
+    e = np.exp(y.astype(np.float64) - y.max(-1, keepdims=True))
+    np.testing.assert_allclose(R.softmax(y, -1), e / e.sum(-1, keepdims=True), atol=1e-6)
