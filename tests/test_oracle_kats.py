@@ -316,3 +316,37 @@ def test_norms_vs_float64_formulas():  # norm.rs: batch_norm (per channel, infer
     np.testing.assert_allclose(R.rms_norm(y, g, 1e-6), want, atol=1e-5)
     e = np.exp(y.astype(np.float64) - y.max(-1, keepdims=True))
     np.testing.assert_allclose(R.softmax(y, -1), e / e.sum(-1, keepdims=True), atol=1e-6)
+
+
+def test_frontend_vs_float64_restatement():
+    """The whole front-end of src/features/pipeline.rs:67-196 written independently in float64 numpy (x32768, per-frame mean removal,
+    in-frame pre-emphasis 0.97 with the first sample untouched, symmetric Hann, zero-pad 400 -> 512, |rfft|^2, HTK triangular mel
+    bank from 20 Hz to Nyquist, ln(max(., 1e-5)), LFR m=7 n=6 with edge clamping) against the oracle: log-mel within 5e-4
+    absolute (f32 FFT + f32 sums of ~1e9-sized powers), LFR exact on the oracle's own mel."""
+    from lele_b200.sensevoice_weights import synth_batch
+    pcm = synth_batch(3, 1, 16000 + 123)[0]
+    mel, out = R.frontend(pcm, want_mel=True)
+    x = pcm.astype(np.float64) * 32768.0
+    n_frames = (x.size - 400) // 160 + 1
+    hann = 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(400) / 399.0))
+    hz2mel = lambda hz: 2595.0 * np.log10(1.0 + hz / 700.0)
+    mel2hz = lambda m: 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    pts = mel2hz(hz2mel(20.0) + np.arange(82) * (hz2mel(8000.0) - hz2mel(20.0)) / 81.0)
+    freqs = np.arange(257) * 16000.0 / 512.0
+    bank = np.zeros((80, 257))
+    for i in range(80):
+        lo, ce, hi = pts[i], pts[i + 1], pts[i + 2]
+        up = (freqs > lo) & (freqs < ce); dn = (freqs >= ce) & (freqs < hi)
+        bank[i, up] = (freqs[up] - lo) / (ce - lo); bank[i, dn] = (hi - freqs[dn]) / (hi - ce)
+    want = np.zeros((n_frames, 80))
+    for f in range(n_frames):
+        fr = x[f * 160:f * 160 + 400].copy()
+        fr -= fr.mean()
+        fr[1:] -= 0.97 * fr[:-1]
+        buf = np.zeros(512); buf[:400] = fr * hann
+        want[f] = np.log(np.maximum(bank @ (np.abs(np.fft.rfft(buf)) ** 2), 1e-5))
+    assert mel.shape == want.shape == (n_frames, 80)
+    np.testing.assert_allclose(mel, want, atol=5e-4)          # measured 1e-4 (f32 FFT and mel sums of ~1e9-sized powers)
+    t_lfr = -(-n_frames // 6)
+    idx = np.clip(np.arange(t_lfr)[:, None] * 6 + np.arange(7)[None, :] - 3, 0, n_frames - 1)
+    np.testing.assert_array_equal(out, mel[idx].reshape(t_lfr, 560))
