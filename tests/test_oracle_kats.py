@@ -350,3 +350,43 @@ def test_frontend_vs_float64_restatement():
     t_lfr = -(-n_frames // 6)
     idx = np.clip(np.arange(t_lfr)[:, None] * 6 + np.arange(7)[None, :] - 3, 0, n_frames - 1)
     np.testing.assert_array_equal(out, mel[idx].reshape(t_lfr, 560))
+
+
+def test_network_oracle_equals_composition_of_pinned_operators():
+    """oracle/sensevoice_ref.c (the whole-network CPU restatement the GPU runner is compared with) against the same first encoder
+    layer composed from the operator-level oracle functions, which are the ones pinned to the reference's KATs: prompt embedding +
+    sqrt(d) scaling + positions, LayerNorm, fused int8 QKV, FSMN memory (depthwise conv k=11 on V + V), 4-head softmax attention,
+    int8 out-projection + FSMN residual, LayerNorm, int8 FFN (ReLU) + residual.  Synthetic weights (no model file exists)."""
+    from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob
+    cfg = SenseVoiceConfig(n_layers=3, vocab=1000, n_stage1=2, max_t=128)
+    blob = build_blob(cfg, seed=7)
+    hdr = blob[:256].view(np.int32); nt = int(hdr[12])
+    table = blob[256:256 + 16 * nt].view(np.uint64).reshape(-1, 2)
+
+    def T_(i, dt=np.float32):
+        o, n = int(table[i, 0]), int(table[i, 1])
+        return blob[o:o + n].view(dt)
+
+    L = lambda w, dt=np.float32: T_(10 + w, dt)                      # layer 0 tensors
+    rng = np.random.default_rng(0)
+    t = 40; T = t + 4
+    for scale in (1.0, 2.5):
+        feats = (rng.standard_normal((t, 560)) * scale).astype(np.float32)
+        embed = T_(0).reshape(16, 560); pos = T_(1).reshape(-1, 560)
+        x0 = np.concatenate([embed[[3, 1, 2, 0]], feats], 0) * np.float32(np.sqrt(np.float32(512))) + pos[:T]
+        h = R.layer_norm(x0, L(0), L(1), -1, 1e-5)
+        qkv = R.fused_quantized_linear(h[None], L(2, np.uint8).reshape(560, 1536), L(3), int(L(5, np.uint8)[0]), L(4))[0]
+        q, k, v = qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]
+        fs = R.conv1d(v.T[None], L(6).reshape(512, 1, 11), None, (1,), 512, (5, 5), (1,))[0].T + v
+        qh = (q.reshape(T, 4, 128).transpose(1, 0, 2) * np.float32(1.0 / np.sqrt(np.float32(128)))).astype(np.float32)
+        kh = k.reshape(T, 4, 128).transpose(1, 2, 0); vh = v.reshape(T, 4, 128).transpose(1, 0, 2)
+        o = R.matmul(R.softmax(R.matmul(qh, kh)), vh).transpose(1, 0, 2).reshape(T, 512)
+        a = R.fused_quantized_linear(o[None], L(7, np.uint8).reshape(512, 512), L(8), int(L(10, np.uint8)[0]), L(9))[0] + fs
+        h2 = R.layer_norm(a, L(11), L(12), -1, 1e-5)
+        f1 = R.fused_quantized_linear(h2[None], L(13, np.uint8).reshape(512, 2048), L(14), int(L(16, np.uint8)[0]), L(15), True)[0]
+        f2 = R.fused_quantized_linear(f1[None], L(17, np.uint8).reshape(2048, 512), L(18), int(L(20, np.uint8)[0]), L(19))[0]
+        want = a + f2
+        got = R.SenseVoiceRef(blob).forward(feats, 3, 0, n_layers=1)
+        assert got.shape == want.shape == (T, 512)
+        err = float(np.abs(got - want).max() / np.abs(want).max())
+        assert err < 1e-4, err          # same operators in the same order; the two differ only in how the f32 attention sums are blocked
