@@ -353,11 +353,12 @@ def test_frontend_vs_float64_restatement():
 
 
 def test_network_oracle_equals_composition_of_pinned_operators():
-    """oracle/sensevoice_ref.c (the whole-network CPU restatement the GPU runner is compared with) against the same first encoder
-    layer composed from the operator-level oracle functions, which are the ones pinned to the reference's KATs: prompt embedding +
-    sqrt(d) scaling + positions, LayerNorm, fused int8 QKV, FSMN memory (depthwise conv k=11 on V + V), 4-head softmax attention,
-    int8 out-projection + FSMN residual, LayerNorm, int8 FFN (ReLU) + residual.  Synthetic weights (no model file exists)."""
-    from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob
+    """oracle/sensevoice_ref.c (the whole-network CPU restatement the GPU runner is compared with) against the same network composed
+    in Python from the operator-level oracle functions, which are the ones pinned to the reference's KATs: prompt embedding +
+    sqrt(d) scaling + positions; per layer LayerNorm, fused int8 QKV, FSMN memory (depthwise conv k=11 on V, + V), 4-head softmax
+    attention, int8 out-projection + FSMN (+ input) residual, LayerNorm, int8 FFN (ReLU) + residual; after_norm at the stage
+    boundary; tp_norm + int8 CTC head; greedy arg-max with the last-max tie rule.  Synthetic weights (no model file exists)."""
+    from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob, synth_batch
     cfg = SenseVoiceConfig(n_layers=3, vocab=1000, n_stage1=2, max_t=128)
     blob = build_blob(cfg, seed=7)
     hdr = blob[:256].view(np.int32); nt = int(hdr[12])
@@ -367,26 +368,49 @@ def test_network_oracle_equals_composition_of_pinned_operators():
         o, n = int(table[i, 0]), int(table[i, 1])
         return blob[o:o + n].view(dt)
 
-    L = lambda w, dt=np.float32: T_(10 + w, dt)                      # layer 0 tensors
-    rng = np.random.default_rng(0)
-    t = 40; T = t + 4
-    for scale in (1.0, 2.5):
-        feats = (rng.standard_normal((t, 560)) * scale).astype(np.float32)
+    L = lambda l, w, dt=np.float32: T_(10 + l * 21 + w, dt)
+    qlin = lambda x, w, k, n, sc, zp, bi, relu=False: R.fused_quantized_linear(x[None], w.reshape(k, n), sc, int(zp[0]), bi, relu)[0]
+
+    def network(feats, lang, textnorm, n_layers):
+        T = feats.shape[0] + 4
         embed = T_(0).reshape(16, 560); pos = T_(1).reshape(-1, 560)
-        x0 = np.concatenate([embed[[3, 1, 2, 0]], feats], 0) * np.float32(np.sqrt(np.float32(512))) + pos[:T]
-        h = R.layer_norm(x0, L(0), L(1), -1, 1e-5)
-        qkv = R.fused_quantized_linear(h[None], L(2, np.uint8).reshape(560, 1536), L(3), int(L(5, np.uint8)[0]), L(4))[0]
-        q, k, v = qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]
-        fs = R.conv1d(v.T[None], L(6).reshape(512, 1, 11), None, (1,), 512, (5, 5), (1,))[0].T + v
-        qh = (q.reshape(T, 4, 128).transpose(1, 0, 2) * np.float32(1.0 / np.sqrt(np.float32(128)))).astype(np.float32)
-        kh = k.reshape(T, 4, 128).transpose(1, 2, 0); vh = v.reshape(T, 4, 128).transpose(1, 0, 2)
-        o = R.matmul(R.softmax(R.matmul(qh, kh)), vh).transpose(1, 0, 2).reshape(T, 512)
-        a = R.fused_quantized_linear(o[None], L(7, np.uint8).reshape(512, 512), L(8), int(L(10, np.uint8)[0]), L(9))[0] + fs
-        h2 = R.layer_norm(a, L(11), L(12), -1, 1e-5)
-        f1 = R.fused_quantized_linear(h2[None], L(13, np.uint8).reshape(512, 2048), L(14), int(L(16, np.uint8)[0]), L(15), True)[0]
-        f2 = R.fused_quantized_linear(f1[None], L(17, np.uint8).reshape(2048, 512), L(18), int(L(20, np.uint8)[0]), L(19))[0]
-        want = a + f2
-        got = R.SenseVoiceRef(blob).forward(feats, 3, 0, n_layers=1)
-        assert got.shape == want.shape == (T, 512)
-        err = float(np.abs(got - want).max() / np.abs(want).max())
-        assert err < 1e-4, err          # same operators in the same order; the two differ only in how the f32 attention sums are blocked
+        x = np.concatenate([embed[[lang, 1, 2, textnorm]], feats], 0) * np.float32(np.sqrt(np.float32(512))) + pos[:T]
+        for l in range(n_layers):
+            cur = x.shape[1]
+            h = R.layer_norm(x, L(l, 0), L(l, 1), -1, 1e-5)
+            qkv = qlin(h, L(l, 2, np.uint8), cur, 1536, L(l, 3), L(l, 5, np.uint8), L(l, 4))
+            q, k, v = qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]
+            fs = R.conv1d(v.T[None], L(l, 6).reshape(512, 1, 11), None, (1,), 512, (5, 5), (1,))[0].T + v
+            qh = (q.reshape(T, 4, 128).transpose(1, 0, 2) * np.float32(1.0 / np.sqrt(np.float32(128)))).astype(np.float32)
+            kh = k.reshape(T, 4, 128).transpose(1, 2, 0); vh = v.reshape(T, 4, 128).transpose(1, 0, 2)
+            o = R.matmul(R.softmax(R.matmul(qh, kh)), vh).transpose(1, 0, 2).reshape(T, 512)
+            att = qlin(o, L(l, 7, np.uint8), 512, 512, L(l, 8), L(l, 10, np.uint8), L(l, 9)) + fs
+            x = att + x if cur == 512 else att                          # the 560-wide first layer has no input residual
+            h2 = R.layer_norm(x, L(l, 11), L(l, 12), -1, 1e-5)
+            f1 = qlin(h2, L(l, 13, np.uint8), 512, 2048, L(l, 14), L(l, 16, np.uint8), L(l, 15), True)
+            x = x + qlin(f1, L(l, 17, np.uint8), 2048, 512, L(l, 18), L(l, 20, np.uint8), L(l, 19))
+            if l == cfg.n_stage1 - 1:
+                x = R.layer_norm(x, T_(2), T_(3), -1, 1e-5)
+        if n_layers < cfg.n_layers:
+            return x
+        h = R.layer_norm(x, T_(4), T_(5), -1, 1e-5)
+        return qlin(h, T_(6, np.uint8), 512, cfg.vocab, T_(7), T_(9, np.uint8), T_(8))
+
+    rng = np.random.default_rng(0)
+    ref = R.SenseVoiceRef(blob)
+    for scale, lang, tn in ((1.0, 3, 0), (2.5, 0, 15)):
+        feats = (rng.standard_normal((40, 560)) * scale).astype(np.float32)
+        for n_layers in (1, 2, 3):
+            got, want = ref.forward(feats, lang, tn, n_layers=n_layers), network(feats, lang, tn, n_layers)
+            assert got.shape == want.shape == (44, 1000 if n_layers == 3 else 512)
+            err = float(np.abs(got - want).max() / np.abs(want).max())
+            assert err < 2e-4 * n_layers, (n_layers, err)   # same operators in the same order; int8 re-quantisation may move a code by one step
+    # raw audio -> ids: front-end + CMVN + network + arg-max keeping the LAST maximum (tokenizer.rs:55-59)
+    pcm = synth_batch(1, 1, 16000)[0]
+    ids, logits = ref.pcm_to_ids(pcm, 3, 0, want_logits=True)
+    lfr = R.frontend(pcm)
+    want_logits = network(R.cmvn(lfr), 3, 0, 3)
+    assert logits.shape == want_logits.shape
+    assert float(np.abs(logits - want_logits).max() / np.abs(want_logits).max()) < 1e-3
+    last_max = logits.shape[1] - 1 - np.argmax(logits[:, ::-1], axis=1)
+    np.testing.assert_array_equal(ids, last_max)
