@@ -32,6 +32,7 @@ extern "C" {
 typedef struct lele_b200_ctx lele_b200_ctx;
 typedef struct lele_b200_qweights lele_b200_qweights;
 typedef struct lele_b200_sensevoice lele_b200_sensevoice;
+typedef struct lele_b200_comm lele_b200_comm;
 
 enum { LELE_B200_OK = 0, LELE_B200_ERR_ARG = 1, LELE_B200_ERR_CUDA = 2, LELE_B200_ERR_UNSUPPORTED = 3 };
 
@@ -97,6 +98,11 @@ int lele_b200_dynamic_quantize_linear(lele_b200_ctx* ctx, const float* x, int n_
 int lele_b200_mat_mul_integer(lele_b200_ctx* ctx, const float* a, const float* b, int batch, int m,
                               int k, int n, float a_zp, float b_zp, const float* scale,
                               int scale_len, const float* bias, int relu, float* out);
+/* same with a batched b [batch_b, k, n] (quantization.rs:1157-1173): batch_a == batch_b, or the side with batch 1 is broadcast;
+ * out [max(batch_a, batch_b), m, n]. */
+int lele_b200_mat_mul_integer_batched(lele_b200_ctx* ctx, const float* a, const float* b, int batch_a, int batch_b,
+                                      int m, int k, int n, float a_zp, float b_zp, const float* scale, int scale_len,
+                                      const float* bias, int relu, float* out);
 /* prepare_weights (quantization.rs:221) / B_WEIGHT_CACHE (avx/quantization.rs:47-95): one-time
  * transpose of the u8 weight [k,n] to the K-major layout the tensor cores read + column sums.
  * w_scale_len 1 or n; bias NULL or [n]. */
@@ -128,6 +134,11 @@ int lele_b200_conv1d(lele_b200_ctx* ctx, const float* x, const float* w, const f
 int lele_b200_conv2d(lele_b200_ctx* ctx, const float* x, const float* w, const float* bias, int nb,
                      int ic, int h, int wd, int oc, int kh, int kw, int group, const int* pads_host,
                      const int* strides_host, const int* dilations_host, int act, float* out);
+/* conv_integer (conv2d.rs:2216, emitted by ops/nn.rs:328): (x - x_zp) (*) (w - w_zp); padded positions hold RAW zeros, i.e. contribute
+ * (0 - x_zp) (conv2d.rs:2025).  x, w hold integer values as f32; x_zp / w_zp = first element of the zero-point tensor or 0. */
+int lele_b200_conv_integer(lele_b200_ctx* ctx, const float* x, const float* w, float x_zp, float w_zp, int nb, int ic,
+                           int h, int wd, int oc, int kh, int kw, int group, const int* pads_host,
+                           const int* strides_host, const int* dilations_host, float* out);
 int lele_b200_conv_transpose(lele_b200_ctx* ctx, const float* x, const float* w, const float* bias,
                              int nb, int ic, int h, int wd, int oc, int kh, int kw,
                              const int* pads_host, const int* strides_host,
@@ -244,6 +255,21 @@ int lele_b200_sensevoice_workspace(lele_b200_sensevoice* m, const char* name, vo
                                    size_t* nbytes);
 int lele_b200_sensevoice_last_profile(lele_b200_sensevoice* m, const char** names_host,
                                       float* ms_host, int* calls_host, int cap, int* n_out);
+
+/* ---- multi-GPU: clips shard across one process per GPU; the only collectives of the path are one broadcast of the weights
+ *      blob and one gather of the greedy ids per batch, over NCCL / NVLink.  NCCL is bound at run time (dlopen; LELE_B200_NCCL_LIB
+ *      overrides the library path); a single-GPU host never needs it.  Rendez-vous: rank 0 creates the 128-byte id and the host hands it
+ *      to the other ranks by its own means.  Every call runs on the context stream. ---- */
+int lele_b200_comm_nccl_version(void);                                        /* 0 when NCCL cannot be loaded */
+int lele_b200_comm_unique_id(void* id128_host);
+int lele_b200_comm_create(lele_b200_ctx* ctx, const void* id128_host, int world, int rank, lele_b200_comm** out);
+int lele_b200_comm_destroy(lele_b200_comm* comm);
+int lele_b200_comm_rank(const lele_b200_comm* comm);
+int lele_b200_comm_world(const lele_b200_comm* comm);
+/* in place: dptr [nbytes] on every rank receives root's bytes (ncclBroadcast) */
+int lele_b200_comm_broadcast(lele_b200_ctx* ctx, lele_b200_comm* comm, void* dptr, size_t nbytes, int root);
+/* root's recv_dev [world][nbytes] receives every rank's send_dev [nbytes] in rank order (grouped ncclSend / ncclRecv) */
+int lele_b200_comm_gather(lele_b200_ctx* ctx, lele_b200_comm* comm, const void* send_dev, void* recv_dev, size_t nbytes, int root);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ def build(force: bool = False) -> str:
         objs = list(ex.map(lambda s: _compile(s, force, hdr_m), sources()))
     if force or not os.path.exists(SO) or any(os.path.getmtime(o) > os.path.getmtime(SO) for o in objs):
         subprocess.check_call([NVCC, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-                               "-cudart", "shared"])
+                               "-cudart", "shared", "-ldl"])
     return SO
 
 

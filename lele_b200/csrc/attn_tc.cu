@@ -562,27 +562,19 @@ int make_map_f32_4d_uncached(CUtensorMap* map, const void* ptr, const unsigned l
     if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(f32 4d) failed (%d)", (int)r); return LELE_B200_ERR_CUDA; }
     return LELE_B200_OK;
 }
-lele_b200_ctx* g_ctx_for_maps = nullptr;
-int make_map_f32_4d(CUtensorMap* map, const void* ptr, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+int make_map_f32_4d(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
                     const unsigned box[4]) {
-    lele_b200_ctx* ctx = g_ctx_for_maps;
-    unsigned long long h = lb_hash_mix(0x66333234ull, (unsigned long long)(uintptr_t)ptr);
-    for (int i = 0; i < 4; ++i) h = lb_hash_mix(lb_hash_mix(h, dims[i]), box[i]);
-    for (int i = 0; i < 3; ++i) h = lb_hash_mix(h, strides_bytes[i]);
-    auto it = ctx->tmaps.find(h);
-    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    const unsigned long long key[10] = {0x66333234ull, (unsigned long long)(uintptr_t)ptr, dims[0], dims[1], dims[2], dims[3], strides_bytes[0], strides_bytes[1],
+                                        strides_bytes[2], ((unsigned long long)box[0] << 48) | ((unsigned long long)box[1] << 32) | ((unsigned long long)box[2] << 16) | box[3]};
+    if (lb_tmap_lookup(ctx, key, map)) return LELE_B200_OK;
     int rc = make_map_f32_4d_uncached(map, ptr, dims, strides_bytes, box);
     if (rc) return rc;
-    std::vector<unsigned char> blob(sizeof(CUtensorMap));
-    memcpy(blob.data(), map, sizeof(CUtensorMap));
-    ctx->tmaps.emplace(h, std::move(blob));
+    lb_tmap_store(ctx, key, map);
     return LELE_B200_OK;
 }
-int make_map_f32_out3d(CUtensorMap* map, const void* ptr, unsigned long long cols, unsigned long long rows, unsigned long long clips) {
-    lele_b200_ctx* ctx = g_ctx_for_maps;
-    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(lb_hash_mix(0x6f337364ull, (unsigned long long)(uintptr_t)ptr), cols), rows), clips);
-    auto it = ctx->tmaps.find(h);
-    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+int make_map_f32_out3d(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, unsigned long long cols, unsigned long long rows, unsigned long long clips) {
+    const unsigned long long key[10] = {0x6f337364ull, (unsigned long long)(uintptr_t)ptr, cols, rows, clips};
+    if (lb_tmap_lookup(ctx, key, map)) return LELE_B200_OK;
     EncodeTiledFn fn = encode_fn();
     if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
     cuuint64_t d[3] = {cols, rows, clips};
@@ -592,9 +584,7 @@ int make_map_f32_out3d(CUtensorMap* map, const void* ptr, unsigned long long col
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(att out) failed (%d)", (int)r); return LELE_B200_ERR_CUDA; }
-    std::vector<unsigned char> blob(sizeof(CUtensorMap));
-    memcpy(blob.data(), map, sizeof(CUtensorMap));
-    ctx->tmaps.emplace(h, std::move(blob));
+    lb_tmap_store(ctx, key, map);
     return LELE_B200_OK;
 }
 }  // namespace
@@ -641,20 +631,18 @@ int lb_attention_tc(lele_b200_ctx* ctx, const float* qkv, int B, int T, int d, i
     const unsigned bv[4] = {KC, DK, 1, 1};
     CUtensorMap mqh, mkh, mvh;
     int rc;
-    g_ctx_for_maps = ctx;
-    if ((rc = make_map_f32_4d(&mqh, qkv, dqk, sqh, bq))) return rc;
-    if ((rc = make_map_f32_4d(&mkh, qkv + d, dqk, sqh, bk))) return rc;
-    if ((rc = make_map_f32_4d(&mvh, vt, dv, sv, bv))) return rc;
+    if ((rc = make_map_f32_4d(ctx, &mqh, qkv, dqk, sqh, bq))) return rc;
+    if ((rc = make_map_f32_4d(ctx, &mkh, qkv + d, dqk, sqh, bk))) return rc;
+    if ((rc = make_map_f32_4d(ctx, &mvh, vt, dv, sv, bv))) return rc;
     // att [B][T][H*DK] -> dims (H*DK, T, B), box 32 x 32 x 1 (one epilogue warp's sub-tile); rows >= T are clipped
     CUtensorMap mout;
-    if ((rc = make_map_f32_out3d(&mout, att, (unsigned long long)H * DK, (unsigned long long)T, (unsigned long long)B))) return rc;
+    if ((rc = make_map_f32_out3d(ctx, &mout, att, (unsigned long long)H * DK, (unsigned long long)T, (unsigned long long)B))) return rc;
     AttnArgs a;
     a.B = B; a.T = T; a.H = H; a.n_qtiles = lb_ceil_div(T, AQ); a.n_kchunks = lb_ceil_div(T, KC); a.rows_per_slice = T;
     a.out = att; a.minmax_keys = minmax_keys;
     a.scale_l2e = qscale * 1.4426950408889634f;
     a.dbg = getenv("LELE_B200_ATTN_DBG") ? 1 : 0;
-    static thread_local bool attr_done = false;
-    if (!attr_done) { LB_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); attr_done = true; }
+    if ((rc = lb_func_smem(ctx, (const void*)attn_tc_kernel, SMEM_BYTES))) return rc;
     const int n_items = B * H * a.n_qtiles;
     const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;     // persistent: one CTA per SM walks the items
     LB_CHECK_CUDA(lb_launch_pdl(attn_tc_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, mqh, mkh, mvh, mout, a));

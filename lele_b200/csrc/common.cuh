@@ -22,16 +22,41 @@ struct lele_b200_ctx {
     // grow-only scratch (the analogue of lele's thread_local SCRATCH_A/RS/CS, avx/quantization.rs:90-95)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // second grow-only buffer for entries that stage operands and then call another entry which uses `scratch` itself (conv_integer)
+    void* scratch2 = nullptr;
+    size_t scratch2_bytes = 0;
     // arena: host Vec base pointer -> device mirror (src/tensor.rs static buffer arena mapped to HBM)
     struct Mirror { void* dptr; size_t bytes; };
     std::unordered_map<const void*, Mirror> arena;
     unsigned long long launches = 0;   // kernels launched through this ctx (bench "gpu_launches")
     // cached device constants (FFT twiddles per n, Hann window, sparse mel bank ...)
     std::unordered_map<std::string, void*> tables;
-    // encoded TMA descriptors keyed by (pointer, geometry): workspace / weight pointers are stable
-    // across forwards, so cuTensorMapEncodeTiled runs once per tensor instead of once per launch
-    std::unordered_map<unsigned long long, std::vector<unsigned char>> tmaps;
+    // encoded TMA descriptors keyed by (kind, pointer, geometry): workspace / weight pointers are stable
+    // across forwards, so cuTensorMapEncodeTiled runs once per tensor instead of once per launch.  Each
+    // entry stores its full key tuple (a 64-bit hash collision must not hand back another tensor's
+    // descriptor); the cache is bounded (LB_TMAP_CACHE_MAX, oldest-half eviction) because the operator
+    // API sees fresh pointers on every call, and entries die with the allocation they describe
+    // (lele_b200_free / arena_release / scratch growth call lb_tmap_forget_range).
+    struct TmapEntry { unsigned long long key[10]; unsigned long long stamp; unsigned char blob[128]; };
+    std::unordered_map<unsigned long long, TmapEntry> tmaps;
+    unsigned long long tmap_clock = 0;
+    // dynamic shared-memory opt-in already applied on THIS device, per kernel function
+    std::unordered_map<const void*, size_t> func_smem;
+    // device-side precondition failures (the reference panics, e.g. a gather index out of range, manipulation.rs:589): kernels
+    // clamp the access and raise this word; lele_b200_sync() reads it back (only when a checking kernel ran since the last sync)
+    int* dev_err = nullptr;
+    bool dev_err_armed = false;
 };
+#define LB_TMAP_CACHE_MAX 4096
+// key = {kind tag, pointer, dim/stride/box words...}; returns true and fills `blob128` on a verified hit
+bool lb_tmap_lookup(lele_b200_ctx* ctx, const unsigned long long (&key)[10], void* blob128);
+void lb_tmap_store(lele_b200_ctx* ctx, const unsigned long long (&key)[10], const void* blob128);
+void lb_tmap_forget_range(lele_b200_ctx* ctx, const void* base, size_t bytes);   // bytes == 0: every entry whose pointer == base
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (context = device, kernel)
+int lb_func_smem(lele_b200_ctx* ctx, const void* func, size_t bytes);
+// makes the context's device current for the calling thread (every entry point starts with it)
+int lb_enter(lele_b200_ctx* ctx);
+#define LB_ENTER(ctx) do { int _rc_enter = lb_enter(ctx); if (_rc_enter) return _rc_enter; } while (0)
 static inline unsigned long long lb_hash_mix(unsigned long long h, unsigned long long v) {
     h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
     return h;
@@ -41,6 +66,7 @@ int lb_table(lele_b200_ctx* ctx, const std::string& key, const void* host, size_
 
 void lb_set_error(const char* fmt, ...);
 int lb_scratch(lele_b200_ctx* ctx, size_t bytes, void** out);
+int lb_scratch2(lele_b200_ctx* ctx, size_t bytes, void** out);
 
 #define LB_CHECK_CUDA(expr)                                                                  \
     do {                                                                                     \
@@ -157,6 +183,8 @@ __device__ __forceinline__ unsigned lb_fkey(float f) {
     unsigned b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+// arg-max keys: the reference compares with partial_cmp, for which -0.0 == +0.0 (ties -> last index), so both zeros share a key
+__device__ __forceinline__ unsigned lb_fkey_argmax(float f) { return lb_fkey(f == 0.0f ? 0.0f : f); }
 __device__ __forceinline__ float lb_fkey_inv(unsigned k) {
     unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
     return __uint_as_float(b);

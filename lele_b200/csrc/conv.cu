@@ -147,6 +147,7 @@ __global__ void conv_transpose_kernel(const float* __restrict__ x, const float* 
 extern "C" int lele_b200_conv1d(lele_b200_ctx* ctx, const float* x, const float* w, const float* bias, int nb, int ic, int l,
                                 int oc, int k, int group, int pad_l, int pad_r, int stride, int dilation, int relu, float* out) {
     LB_REQUIRE(ctx && x && w && out, "conv1d: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(group >= 1 && ic % group == 0 && oc % group == 0 && stride >= 1 && dilation >= 1 && k >= 1, "conv1d: bad attributes");
     int ol = (l + pad_l + pad_r - dilation * (k - 1) - 1) / stride + 1;
     LB_REQUIRE(ol >= 0, "conv1d: negative output length");
@@ -161,6 +162,7 @@ extern "C" int lele_b200_conv2d(lele_b200_ctx* ctx, const float* x, const float*
                                 int oc, int kh, int kw, int group, const int* pads, const int* strides, const int* dils, int act,
                                 float* out) {
     LB_REQUIRE(ctx && x && w && out && pads && strides && dils, "conv2d: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(group >= 1 && ic % group == 0 && oc % group == 0, "Conv2d: channels not divisible by group (conv2d.rs:196-205)");
     Conv2dGeom g;
     g.ic = ic; g.h = h; g.w = wd; g.oc = oc; g.kh = kh; g.kw = kw; g.group = group; g.pt = pads[0]; g.pl = pads[1];
@@ -216,10 +218,48 @@ extern "C" int lele_b200_conv2d(lele_b200_ctx* ctx, const float* x, const float*
     return LELE_B200_OK;
 }
 
+// ConvInteger (conv2d.rs:2216-2420 -> conv2d_with_zero_points :1507-2000): an f32 convolution of (x - x_zp) with (w - w_zp) whose im2col
+// pads with RAW zeros, so a padded position contributes (0 - x_zp) (conv2d.rs:2025).  Here: one staging kernel writes the zero-padded,
+// shifted input and the shifted weight, then the convolution runs un-padded on the same paths as conv2d (tcgen05 implicit GEMM when
+// the shape qualifies).
+namespace {
+__global__ void conv_integer_stage_kernel(const float* __restrict__ x, int nbc, int h, int w, int pt, int pl, int hp, int wp, float x_zp,
+                                          float* __restrict__ xs, const float* __restrict__ wgt, long long w_len, float w_zp, float* __restrict__ ws) {
+    const long long total = (long long)nbc * hp * wp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + w_len; i += (long long)gridDim.x * blockDim.x) {
+        if (i >= total) { ws[i - total] = __fsub_rn(wgt[i - total], w_zp); continue; }
+        const int c = (int)(i % wp), r = (int)((i / wp) % hp); const long long p = i / ((long long)wp * hp);
+        const int sr = r - pt, sc = c - pl;
+        const float v = (sr >= 0 && sr < h && sc >= 0 && sc < w) ? x[(p * h + sr) * w + sc] : 0.0f;
+        xs[i] = __fsub_rn(v, x_zp);
+    }
+}
+}  // namespace
+
+extern "C" int lele_b200_conv_integer(lele_b200_ctx* ctx, const float* x, const float* w, float x_zp, float w_zp, int nb, int ic, int h,
+                                      int wd, int oc, int kh, int kw, int group, const int* pads, const int* strides, const int* dils,
+                                      float* out) {
+    LB_REQUIRE(ctx && x && w && out && pads && strides && dils, "conv_integer: NULL argument");
+    LB_ENTER(ctx);
+    LB_REQUIRE(group >= 1 && ic % group == 0 && oc % group == 0, "ConvInteger: channels not divisible by group (conv2d.rs:196-205)");
+    LB_REQUIRE(pads[0] >= 0 && pads[1] >= 0 && pads[2] >= 0 && pads[3] >= 0, "conv_integer: negative pads");
+    if (nb == 0) return LELE_B200_OK;
+    const int hp = h + pads[0] + pads[2], wp = wd + pads[1] + pads[3];
+    const long long n_x = (long long)nb * ic * hp * wp, n_w = (long long)oc * (ic / group) * kh * kw;
+    void* sc; int rc;
+    if ((rc = lb_scratch2(ctx, sizeof(float) * (size_t)(n_x + n_w) + 512, &sc))) return rc;
+    float* xs = (float*)sc; float* ws = xs + (n_x + 63) / 64 * 64;
+    conv_integer_stage_kernel<<<grid_for(n_x + n_w), 256, 0, ctx->stream>>>(x, nb * ic, h, wd, pads[0], pads[1], hp, wp, x_zp, xs, w, n_w, w_zp, ws);
+    LB_LAUNCH_CHECK(ctx);
+    const int zero_pads[4] = {0, 0, 0, 0};
+    return lele_b200_conv2d(ctx, xs, ws, nullptr, nb, ic, hp, wp, oc, kh, kw, group, zero_pads, strides, dils, 0, out);
+}
+
 extern "C" int lele_b200_conv_transpose(lele_b200_ctx* ctx, const float* x, const float* w, const float* bias, int nb, int ic, int h,
                                         int wd, int oc, int kh, int kw, const int* pads, const int* strides, const int* dils,
                                         float* out) {
     LB_REQUIRE(ctx && x && w && out && pads && strides && dils, "conv_transpose: NULL argument");
+    LB_ENTER(ctx);
     int oh = (h - 1) * strides[0] - (pads[0] + pads[2]) + dils[0] * (kh - 1) + 1;
     int ow = (wd - 1) * strides[1] - (pads[1] + pads[3]) + dils[1] * (kw - 1) + 1;
     LB_REQUIRE(oh > 0 && ow > 0, "conv_transpose: output dimensions must be positive, got out_h=%d out_w=%d (conv2d.rs:3025)", oh, ow);

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <stdarg.h>
+#include <algorithm>
 
 static thread_local char g_err[1024] = "";
 
@@ -45,6 +46,13 @@ extern "C" int lele_b200_ctx_create(int device, void* stream, lele_b200_ctx** ou
         if (e != cudaSuccess) { delete c; lb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return LELE_B200_ERR_CUDA; }
         c->own_stream = true;
     }
+    if (cudaMalloc((void**)&c->dev_err, sizeof(int)) != cudaSuccess || cudaMemset(c->dev_err, 0, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        delete c;
+        lb_set_error("ctx_create: cannot allocate the device error word");
+        return LELE_B200_ERR_CUDA;
+    }
     *out = c;
     return LELE_B200_OK;
 }
@@ -56,6 +64,8 @@ extern "C" int lele_b200_ctx_destroy(lele_b200_ctx* ctx) {
     for (auto& kv : ctx->arena) cudaFree(kv.second.dptr);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
+    if (ctx->dev_err) cudaFree(ctx->dev_err);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return LELE_B200_OK;
@@ -63,6 +73,20 @@ extern "C" int lele_b200_ctx_destroy(lele_b200_ctx* ctx) {
 
 extern "C" int lele_b200_sync(lele_b200_ctx* ctx) {
     LB_REQUIRE(ctx, "sync: NULL ctx");
+    LB_ENTER(ctx);
+    if (ctx->dev_err_armed) {
+        int flag = 0;
+        LB_CHECK_CUDA(cudaMemcpyAsync(&flag, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->dev_err_armed = false;
+        if (flag) {
+            cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), ctx->stream);
+            lb_set_error("%s: index out of range for the gathered axis (the reference panics, manipulation.rs:589 / conv2d.rs:1438)",
+                         flag == 2 ? "gather_elements" : "gather");
+            return LELE_B200_ERR_ARG;
+        }
+        return LELE_B200_OK;
+    }
     LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return LELE_B200_OK;
 }
@@ -71,38 +95,49 @@ extern "C" unsigned long long lele_b200_launch_count(const lele_b200_ctx* ctx) {
 
 extern "C" int lele_b200_malloc(lele_b200_ctx* ctx, size_t nbytes, void** dptr) {
     LB_REQUIRE(ctx && dptr, "malloc: NULL argument");
+    LB_ENTER(ctx);
     LB_CHECK_CUDA(cudaSetDevice(ctx->device));
     LB_CHECK_CUDA(cudaMalloc(dptr, nbytes ? nbytes : 16));
     return LELE_B200_OK;
 }
 extern "C" int lele_b200_free(lele_b200_ctx* ctx, void* dptr) {
     LB_REQUIRE(ctx, "free: NULL ctx");
-    if (dptr) { LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream)); LB_CHECK_CUDA(cudaFree(dptr)); }
+    LB_ENTER(ctx);
+    if (dptr) {
+        LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        lb_tmap_forget_range(ctx, dptr, 0);          // descriptors of a freed tensor must not outlive it
+        LB_CHECK_CUDA(cudaFree(dptr));
+    }
     return LELE_B200_OK;
 }
 extern "C" int lele_b200_memset(lele_b200_ctx* ctx, void* dptr, int value, size_t nbytes) {
     LB_REQUIRE(ctx, "memset: NULL ctx");
+    LB_ENTER(ctx);
     LB_CHECK_CUDA(cudaMemsetAsync(dptr, value, nbytes, ctx->stream));
     return LELE_B200_OK;
 }
 extern "C" int lele_b200_h2d(lele_b200_ctx* ctx, void* dst, const void* src, size_t nbytes) {
     LB_REQUIRE(ctx, "h2d: NULL ctx");
+    LB_ENTER(ctx);
     if (nbytes) LB_CHECK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     return LELE_B200_OK;
 }
 extern "C" int lele_b200_d2h(lele_b200_ctx* ctx, void* dst, const void* src, size_t nbytes) {
     LB_REQUIRE(ctx, "d2h: NULL ctx");
+    LB_ENTER(ctx);
     if (nbytes) LB_CHECK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     return LELE_B200_OK;
 }
 extern "C" int lele_b200_d2d(lele_b200_ctx* ctx, void* dst, const void* src, size_t nbytes) {
     LB_REQUIRE(ctx, "d2d: NULL ctx");
+    LB_ENTER(ctx);
     if (nbytes) LB_CHECK_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return LELE_B200_OK;
 }
 
 extern "C" int lele_b200_arena_bind(lele_b200_ctx* ctx, const void* host_base, size_t nbytes, void** dptr) {
     LB_REQUIRE(ctx && host_base && dptr, "arena_bind: NULL argument");
+    LB_ENTER(ctx);
     auto it = ctx->arena.find(host_base);
     if (it != ctx->arena.end() && it->second.bytes >= nbytes) { *dptr = it->second.dptr; return LELE_B200_OK; }
     void* p = nullptr;
@@ -111,6 +146,7 @@ extern "C" int lele_b200_arena_bind(lele_b200_ctx* ctx, const void* host_base, s
     if (it != ctx->arena.end()) {  // grow: keep contents, like Vec::reserve
         LB_CHECK_CUDA(cudaMemcpyAsync(p, it->second.dptr, it->second.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        lb_tmap_forget_range(ctx, it->second.dptr, it->second.bytes);
         cudaFree(it->second.dptr);
         it->second = {p, nbytes};
     } else ctx->arena[host_base] = {p, nbytes};
@@ -119,9 +155,11 @@ extern "C" int lele_b200_arena_bind(lele_b200_ctx* ctx, const void* host_base, s
 }
 extern "C" int lele_b200_arena_release(lele_b200_ctx* ctx, const void* host_base) {
     LB_REQUIRE(ctx, "arena_release: NULL ctx");
+    LB_ENTER(ctx);
     auto it = ctx->arena.find(host_base);
     if (it != ctx->arena.end()) {
         LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        lb_tmap_forget_range(ctx, it->second.dptr, it->second.bytes);
         cudaFree(it->second.dptr);
         ctx->arena.erase(it);
     }
@@ -143,13 +181,26 @@ bool lb_pdl_enabled() {
 int lb_scratch(lele_b200_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->scratch_bytes) {
         LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->scratch) cudaFree(ctx->scratch);
+        if (ctx->scratch) { lb_tmap_forget_range(ctx, ctx->scratch, ctx->scratch_bytes); cudaFree(ctx->scratch); }
         ctx->scratch = nullptr; ctx->scratch_bytes = 0;
         size_t want = bytes + (bytes >> 2) + 4096;
         LB_CHECK_CUDA(cudaMalloc(&ctx->scratch, want));
         ctx->scratch_bytes = want;
     }
     *out = ctx->scratch;
+    return LELE_B200_OK;
+}
+
+int lb_scratch2(lele_b200_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch2_bytes) {
+        LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch2) { lb_tmap_forget_range(ctx, ctx->scratch2, ctx->scratch2_bytes); cudaFree(ctx->scratch2); }
+        ctx->scratch2 = nullptr; ctx->scratch2_bytes = 0;
+        size_t want = bytes + (bytes >> 2) + 4096;
+        LB_CHECK_CUDA(cudaMalloc(&ctx->scratch2, want));
+        ctx->scratch2_bytes = want;
+    }
+    *out = ctx->scratch2;
     return LELE_B200_OK;
 }
 
@@ -164,4 +215,54 @@ int lb_table(lele_b200_ctx* ctx, const std::string& key, const void* host, size_
     ctx->tables[key] = p;
     *out = p;
     return LELE_B200_OK;
+}
+
+
+int lb_enter(lele_b200_ctx* ctx) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) LB_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return LELE_B200_OK;
+}
+
+int lb_func_smem(lele_b200_ctx* ctx, const void* func, size_t bytes) {
+    auto it = ctx->func_smem.find(func);
+    if (it != ctx->func_smem.end() && it->second >= bytes) return LELE_B200_OK;
+    LB_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes ? bytes : 16)));
+    ctx->func_smem[func] = bytes;
+    return LELE_B200_OK;
+}
+
+static unsigned long long lb_tmap_hash(const unsigned long long (&key)[10]) {
+    unsigned long long h = 0x746d6170ull;
+    for (int i = 0; i < 10; ++i) h = lb_hash_mix(h, key[i]);
+    return h;
+}
+bool lb_tmap_lookup(lele_b200_ctx* ctx, const unsigned long long (&key)[10], void* blob128) {
+    auto it = ctx->tmaps.find(lb_tmap_hash(key));
+    if (it == ctx->tmaps.end() || memcmp(it->second.key, key, sizeof(key)) != 0) return false;   // a hash collision is a miss
+    it->second.stamp = ++ctx->tmap_clock;
+    memcpy(blob128, it->second.blob, 128);
+    return true;
+}
+void lb_tmap_store(lele_b200_ctx* ctx, const unsigned long long (&key)[10], const void* blob128) {
+    if (ctx->tmaps.size() >= LB_TMAP_CACHE_MAX) {        // drop the least recently used half
+        std::vector<unsigned long long> stamps;
+        stamps.reserve(ctx->tmaps.size());
+        for (auto& kv : ctx->tmaps) stamps.push_back(kv.second.stamp);
+        std::nth_element(stamps.begin(), stamps.begin() + stamps.size() / 2, stamps.end());
+        const unsigned long long cut = stamps[stamps.size() / 2];
+        for (auto it = ctx->tmaps.begin(); it != ctx->tmaps.end();) it = it->second.stamp < cut ? ctx->tmaps.erase(it) : ++it;
+    }
+    lele_b200_ctx::TmapEntry e;
+    memcpy(e.key, key, sizeof(key));
+    e.stamp = ++ctx->tmap_clock;
+    memcpy(e.blob, blob128, 128);
+    ctx->tmaps[lb_tmap_hash(key)] = e;                   // a colliding older entry is replaced
+}
+void lb_tmap_forget_range(lele_b200_ctx* ctx, const void* base, size_t bytes) {
+    const unsigned long long lo = (unsigned long long)(uintptr_t)base, hi = lo + (bytes ? bytes : 1);
+    for (auto it = ctx->tmaps.begin(); it != ctx->tmaps.end();) {
+        const unsigned long long p = it->second.key[1];
+        it = (p >= lo && p < hi) ? ctx->tmaps.erase(it) : ++it;
+    }
 }

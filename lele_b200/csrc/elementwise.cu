@@ -187,6 +187,7 @@ int grid_for(long long total, int per = 1) { long long g = (total / per + 255) /
 extern "C" int lele_b200_binary(lele_b200_ctx* ctx, int op, const float* a, const long long* a_shape, int a_rank, const float* b,
                                 const long long* b_shape, int b_rank, float* out) {
     LB_REQUIRE(ctx && a && b && out, "binary: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(op >= LELE_B200_ADD && op <= LELE_B200_LESS, "binary: unknown op %d", op);
     Bcast bc;
     int rc = make_bcast(bc, a_shape, a_rank, b_shape, b_rank);
@@ -226,6 +227,7 @@ extern "C" int lele_b200_where(lele_b200_ctx* ctx, const float* cond, const long
                                const long long* x_shape, int x_rank, const float* y, const long long* y_shape, int y_rank,
                                float* out) {
     LB_REQUIRE(ctx && cond && x && y && out, "where: NULL argument");
+    LB_ENTER(ctx);
     Bcast bc;
     int rc = make_bcast(bc, c_shape, c_rank, x_shape, x_rank, y_shape, y_rank);
     if (rc) return rc;
@@ -237,6 +239,7 @@ extern "C" int lele_b200_where(lele_b200_ctx* ctx, const float* cond, const long
 
 extern "C" int lele_b200_unary(lele_b200_ctx* ctx, int op, const float* x, long long len, float* out) {
     LB_REQUIRE(ctx && (len == 0 || (x && out)), "unary: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(op >= LELE_B200_RELU && op <= LELE_B200_FAST_GELU, "unary: unknown op %d", op);
     if (len == 0) return LELE_B200_OK;
     unary_kernel<<<grid_for(len), 256, 0, ctx->stream>>>(op, x, len, out);
@@ -246,6 +249,7 @@ extern "C" int lele_b200_unary(lele_b200_ctx* ctx, int op, const float* x, long 
 
 extern "C" int lele_b200_clip(lele_b200_ctx* ctx, const float* x, long long len, float lo, float hi, float* out) {
     LB_REQUIRE(ctx && (len == 0 || (x && out)), "clip: NULL argument");
+    LB_ENTER(ctx);
     if (len == 0) return LELE_B200_OK;
     clip_kernel<<<grid_for(len), 256, 0, ctx->stream>>>(x, len, lo, hi, out);
     LB_LAUNCH_CHECK(ctx);
@@ -255,6 +259,7 @@ extern "C" int lele_b200_clip(lele_b200_ctx* ctx, const float* x, long long len,
 extern "C" int lele_b200_reduce(lele_b200_ctx* ctx, int kind, const float* x, long long outer, int axis_len, long long inner,
                                 float* out) {
     LB_REQUIRE(ctx && x && out && kind >= 0 && kind <= 3 && axis_len > 0, "reduce: bad arguments");
+    LB_ENTER(ctx);
     if (outer * inner == 0) return LELE_B200_OK;
     reduce_kernel<<<grid_for(outer * inner), 256, 0, ctx->stream>>>(kind, x, outer, axis_len, inner, out);
     LB_LAUNCH_CHECK(ctx);

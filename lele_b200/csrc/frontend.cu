@@ -254,6 +254,7 @@ static int get_fbank_tables(lele_b200_ctx* ctx, FbankTables* tb) {
 extern "C" int lele_b200_frontend_compute(lele_b200_ctx* ctx, const float* pcm, int n_clips, int n_samples,
                                           long long clip_stride, float* mel_opt, float* lfr_out) {
     LB_REQUIRE(ctx && pcm && lfr_out, "frontend_compute: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(n_clips >= 0 && clip_stride >= n_samples, "frontend_compute: bad clip geometry");
     int frames = lele_b200_frontend_num_frames(n_samples);
     if (frames == 0 || n_clips == 0) return LELE_B200_OK;  // TensorView::empty() (pipeline.rs:70-72)
@@ -286,6 +287,7 @@ __global__ void lfr_kernel(const float* __restrict__ in, int t, int d, int m, in
 }
 extern "C" int lele_b200_lfr(lele_b200_ctx* ctx, const float* in, int n_clips, int t, int d, int m, int n, float* out) {
     LB_REQUIRE(ctx && m > 0 && n > 0 && d > 0, "lfr: bad arguments");
+    LB_ENTER(ctx);
     if (t == 0 || n_clips == 0) return LELE_B200_OK;
     int t_lfr = (t + n - 1) / n;
     long long total = (long long)t_lfr * m * d;
@@ -317,6 +319,7 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int t, int d, float ep
 }
 extern "C" int lele_b200_cmvn(lele_b200_ctx* ctx, const float* in, int n_clips, int t, int d, float eps, float* out) {
     LB_REQUIRE(ctx && d > 0, "cmvn: bad arguments");
+    LB_ENTER(ctx);
     if (t == 0 || n_clips == 0) return LELE_B200_OK;
     dim3 grid(lb_ceil_div(d, 64), n_clips);
     cmvn_kernel<<<grid, 64, 0, ctx->stream>>>(in, t, d, eps, out);
@@ -360,6 +363,7 @@ static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 extern "C" int lele_b200_rfft(lele_b200_ctx* ctx, const float* x, int n_rows, int n, float* out_re, float* out_im) {
     LB_REQUIRE(ctx && x && out_re && out_im, "rfft: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(is_pow2(n) && n >= 2 && n <= 4096, "rfft: n=%d must be a power of two in [2,4096] (kernels/fft.rs:4)", n);
     if (n_rows == 0) return LELE_B200_OK;
     const float *tr, *ti; const int* br;
@@ -373,6 +377,7 @@ extern "C" int lele_b200_rfft(lele_b200_ctx* ctx, const float* x, int n_rows, in
 extern "C" int lele_b200_stft(lele_b200_ctx* ctx, const float* signal, int signal_len, int n_fft, int hop, int win,
                               const float* window, int power, float* out, int* frames_out) {
     LB_REQUIRE(ctx, "stft: NULL ctx");
+    LB_ENTER(ctx);
     LB_REQUIRE(is_pow2(n_fft) && n_fft >= 2 && n_fft <= 4096, "stft: n_fft=%d must be a power of two <= 4096", n_fft);
     LB_REQUIRE(hop > 0 && win > 0 && win <= n_fft, "stft: bad hop/win");
     if (signal_len == 0) { if (frames_out) *frames_out = 0; return LELE_B200_OK; }

@@ -153,6 +153,7 @@ static int gemm_tc_or_simt(lele_b200_ctx* ctx, const float* a, bool a_kmajor, lo
 extern "C" int lele_b200_matmul(lele_b200_ctx* ctx, const float* a, const float* b, int batch_a, int batch_b, int m, int k,
                                 int n, float* out) {
     LB_REQUIRE(ctx && a && b && out, "matmul: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(batch_a >= 1 && batch_b >= 1 && (batch_a == batch_b || batch_a == 1 || batch_b == 1),
                "matmul: batch mismatch %d vs %d (gemm.rs:134)", batch_a, batch_b);
     int fb = batch_a > batch_b ? batch_a : batch_b;
@@ -162,6 +163,7 @@ extern "C" int lele_b200_matmul(lele_b200_ctx* ctx, const float* a, const float*
 extern "C" int lele_b200_matmul_fused_add(lele_b200_ctx* ctx, const float* a, const float* b, const float* bias, int bias_len,
                                           int batch_a, int batch_b, int m, int k, int n, float* out) {
     LB_REQUIRE(ctx && a && b && bias && out && bias_len > 0, "matmul_fused_add: bad arguments");
+    LB_ENTER(ctx);
     int fb = batch_a > batch_b ? batch_a : batch_b;
     long long total = (long long)fb * m * n;
     if (total == 0) return LELE_B200_OK;
@@ -180,6 +182,7 @@ extern "C" int lele_b200_matmul_fused_add(lele_b200_ctx* ctx, const float* a, co
 extern "C" int lele_b200_gemm(lele_b200_ctx* ctx, const float* a, const float* b, const float* c, int c_len, float alpha,
                               float beta, int trans_a, int trans_b, int m, int k, int n, float* out) {
     LB_REQUIRE(ctx && a && b && out, "gemm: NULL argument");
+    LB_ENTER(ctx);
     if ((long long)m * n == 0) return LELE_B200_OK;
     gemm_prefill_kernel<<<grid_for((long long)m * n), 256, 0, ctx->stream>>>(out, m, n, c, c_len, beta);
     LB_LAUNCH_CHECK(ctx);

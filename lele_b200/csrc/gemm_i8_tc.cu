@@ -489,13 +489,19 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.0f));
                 }
+                // QKV projection with skip_v_out: the v columns leave the SM only as V^T (below), not through the staging tile
+                const bool v_only_vt = MODE == EPI_QKV && ep.skip_v_out && gcol0 >= 2 * (N / 3);
+                if (!v_only_vt) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), __uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+                    for (int q = 0; q < 8; ++q)
+                        sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), __uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+                }
                 if (TMA_OUT) {
-                    fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
-                    __syncwarp();
-                    if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, first_row);
+                    if (!v_only_vt) {
+                        fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, first_row);
+                    }
                     if (MODE == EPI_QKV) {
                         // operand preparation for the attention kernel: the v columns are also written transposed (V^T, keys
                         // contiguous = the K-major B operand of P.V); r[] holds the 32 finished f32 values of this row.
@@ -598,7 +604,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     if (lane == 0 && mnB <= mxB) lb_mm_update_keys(ep.minmax_keys, slice_first + 1, mnB, mxB);
                 }
             }
-            if (MODE == EPI_ARGMAX && row_ok && best_c >= 0) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey(best_t) << 32) | (unsigned)best_c);
+            if (MODE == EPI_ARGMAX && row_ok && best_c >= 0) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey_argmax(best_t) << 32) | (unsigned)best_c);
             m_blk += step_m; n_blk += step_n;
             if (n_blk >= nnb) { n_blk -= nnb; ++m_blk; }
         }
@@ -654,45 +660,35 @@ int make_tmap_u8(CUtensorMap* map, const void* ptr, long long rows, long long co
 }
 
 int cached_tmap_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_rows) {
-    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(lb_hash_mix(0x75386d61ull, (unsigned long long)(uintptr_t)ptr), (unsigned long long)rows),
-                                                   (unsigned long long)cols), (unsigned long long)box_rows);
-    auto it = ctx->tmaps.find(h);
-    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    const unsigned long long key[10] = {0x75386d61ull, (unsigned long long)(uintptr_t)ptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)box_rows};
+    if (lb_tmap_lookup(ctx, key, map)) return LELE_B200_OK;
     int rc = make_tmap_u8(map, ptr, rows, cols, box_rows);
     if (rc) return rc;
-    std::vector<unsigned char> blob(sizeof(CUtensorMap));
-    memcpy(blob.data(), map, sizeof(CUtensorMap));
-    ctx->tmaps.emplace(h, std::move(blob));
+    lb_tmap_store(ctx, key, map);
     return LELE_B200_OK;
 }
 
 // f32 [rows, cols] row-major output, box = 32 x 32 (one epilogue warp's sub-tile), 128B swizzle
-int cached_tmap_out_f32(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols) {
-    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(0x6f757466ull, (unsigned long long)(uintptr_t)ptr), (unsigned long long)rows),
-                                       (unsigned long long)cols);
-    auto it = ctx->tmaps.find(h);
-    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+int cached_tmap_out_f32(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols, long long pitch_cols) {
+    const unsigned long long key[10] = {0x6f757466ull, (unsigned long long)(uintptr_t)ptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_cols};
+    if (lb_tmap_lookup(ctx, key, map)) return LELE_B200_OK;
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_cols * 4};
     cuuint32_t box[2] = {32, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(out) failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return LELE_B200_ERR_CUDA; }
-    std::vector<unsigned char> blob(sizeof(CUtensorMap));
-    memcpy(blob.data(), map, sizeof(CUtensorMap));
-    ctx->tmaps.emplace(h, std::move(blob));
+    lb_tmap_store(ctx, key, map);
     return LELE_B200_OK;
 }
 // u8 [rows, cols] row-major output, box = 32 x 32 (one epilogue warp's quantised sub-tile), no swizzle
 int cached_tmap_out_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols) {
-    unsigned long long h = lb_hash_mix(lb_hash_mix(lb_hash_mix(0x6f757538ull, (unsigned long long)(uintptr_t)ptr), (unsigned long long)rows),
-                                       (unsigned long long)cols);
-    auto it = ctx->tmaps.find(h);
-    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    const unsigned long long key[10] = {0x6f757538ull, (unsigned long long)(uintptr_t)ptr, (unsigned long long)rows, (unsigned long long)cols};
+    if (lb_tmap_lookup(ctx, key, map)) return LELE_B200_OK;
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -703,9 +699,7 @@ int cached_tmap_out_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, lo
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(u8 out) failed (%d) rows=%lld cols=%lld", (int)r, rows, cols); return LELE_B200_ERR_CUDA; }
-    std::vector<unsigned char> blob(sizeof(CUtensorMap));
-    memcpy(blob.data(), map, sizeof(CUtensorMap));
-    ctx->tmaps.emplace(h, std::move(blob));
+    lb_tmap_store(ctx, key, map);
     return LELE_B200_OK;
 }
 }  // namespace
@@ -764,7 +758,9 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
         if (rc) return rc;
     }
     if (tma_out) {
-        rc = cached_tmap_out_f32(ctx, &tout, ep.out, M, N);
+        // QKV projection: the v third of the row is consumed only through V^T (attention) -- the tensor map stops at 2d columns when
+        // the caller says nobody reads v from `out` (ep.skip_v_out), so those TMA stores are clipped by the hardware and never reach HBM
+        rc = cached_tmap_out_f32(ctx, &tout, ep.out, M, (mode == EPI_QKV && ep.skip_v_out) ? (N / 3) * 2 : N, N);
         if (rc) return rc;
     }
     if (mode == EPI_QKV) {
@@ -778,15 +774,11 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
         if (G > args.num_m_blocks) G = args.num_m_blocks;
         grid = G * args.num_n_blocks;
     }
-    static thread_local unsigned long long attr_done = 0;   // one process per GPU: the attribute is set once per instantiation
+    // the shared-memory opt-in is recorded per context (= per device), once per instantiation
 #define LB_LAUNCH_MODE4(MD, TM, RL, RB)                                                                                 \
     {                                                                                                                   \
-        const unsigned long long bit = 1ull << (MD * 8 + (RB ? 4 : 0) + (TM ? 2 : 0) + (RL ? 1 : 0));                   \
         const int smem_bytes = RB ? RES_SMEM_BYTES : SMEM_BYTES;                                                        \
-        if (!(attr_done & bit)) {                                                                                       \
-            LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<MD, TM, RL, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
-            attr_done |= bit;                                                                                           \
-        }                                                                                                               \
+        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_tc_kernel<MD, TM, RL, RB>, smem_bytes))) return rc;            \
         LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, ctx->stream, 1, ta, tb, tout, tlo, args)); \
     }
 #define LB_LAUNCH_MODE3(MD, TM, RL) LB_LAUNCH_MODE4(MD, TM, RL, false)

@@ -27,6 +27,7 @@ struct LbI8Epilogue {
     // B operand of P.V).  q / k are read straight from `out`; the tf32 lo residuals are computed on chip by attn_tc.cu.
     float* vt;
     int vt_tp;
+    int skip_v_out;            // the v third of `out` is not written (nobody reads it: attention and the FSMN block both take V^T)
     // fused output quantiser (two-pass linear -> dynamic quantiser, no f32 round trip): pass 1 = this GEMM with out == NULL,
     // minmax_keys set and q_rowsum set (max-only, zeroes q_rowsum); pass 2 = the same GEMM with q_out set: the epilogue
     // quantises with the per-slice (scale, zp) derived from q_keys (the keys pass 1 reduced) and emits the next GEMM's

@@ -346,10 +346,9 @@ EncodeTiledFn encode_fn() {
 }
 // f32 operand [batch][rows][K] (row pitch ld, batch stride bs; bs == 0 broadcasts one matrix) -> dims (K, rows, batch)
 int make_operand_map(lele_b200_ctx* ctx, CUtensorMap* map, const float* ptr, long long rows, long long K, long long ld, long long bs, int batch, int box_rows) {
-    unsigned long long h = lb_hash_mix(0x74663332ull, (unsigned long long)(uintptr_t)ptr);
-    h = lb_hash_mix(lb_hash_mix(lb_hash_mix(lb_hash_mix(lb_hash_mix(lb_hash_mix(h, rows), K), ld), bs), batch), box_rows);
-    auto it = ctx->tmaps.find(h);
-    if (it != ctx->tmaps.end()) { memcpy(map, it->second.data(), sizeof(CUtensorMap)); return LELE_B200_OK; }
+    const unsigned long long key[10] = {0x74663332ull, (unsigned long long)(uintptr_t)ptr, (unsigned long long)rows, (unsigned long long)K, (unsigned long long)ld,
+                                        (unsigned long long)bs, (unsigned long long)batch, (unsigned long long)box_rows};
+    if (lb_tmap_lookup(ctx, key, map)) return LELE_B200_OK;
     EncodeTiledFn fn = encode_fn();
     if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
     const bool bcast = (bs == 0 || batch == 1);
@@ -360,9 +359,7 @@ int make_operand_map(lele_b200_ctx* ctx, CUtensorMap* map, const float* ptr, lon
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { lb_set_error("cuTensorMapEncodeTiled(f32 operand) failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return LELE_B200_ERR_CUDA; }
-    std::vector<unsigned char> blob(sizeof(CUtensorMap));
-    memcpy(blob.data(), map, sizeof(CUtensorMap));
-    ctx->tmaps.emplace(h, std::move(blob));
+    lb_tmap_store(ctx, key, map);
     return LELE_B200_OK;
 }
 }  // namespace
@@ -390,12 +387,11 @@ static int launch_tc(lele_b200_ctx* ctx, const float* A, long long lda, long lon
     a.M = m; a.N = n; a.K = k; a.n_kchunks = lb_ceil_div(k, KC);
     a.a_bcast = (bsa == 0 || batch == 1) ? 1 : 0; a.b_bcast = (bsb == 0 || batch == 1) ? 1 : 0;
     a.C = C; a.ldc = ldc; a.bsc = bsc; a.alpha = ep.alpha; a.pre_mode = ep.pre_mode; a.bias_row = ep.bias_row; a.act = ep.act; a.simd_end = ep.simd_end;
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
-        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_nt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        LB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_done = true;
+    {
+        int rc_a = lb_func_smem(ctx, (const void*)gemm_tf32x3_nt_kernel<0>, SMEM_BYTES);
+        if (!rc_a) rc_a = lb_func_smem(ctx, (const void*)gemm_tf32x3_nt_kernel<1>, SMEM_BYTES);
+        if (!rc_a) rc_a = lb_func_smem(ctx, (const void*)gemm_tf32x3_nt_kernel<2>, SMEM_BYTES);
+        if (rc_a) return rc_a;
     }
     dim3 grid(lb_ceil_div(n, BN), lb_ceil_div(m, BM), batch);
     const int mode = gb ? gb->mode : 0;

@@ -35,7 +35,7 @@ strided_rows_kernel(const float* __restrict__ in, StridedArgs a, long long n_row
 // gather along axis 0-like layouts with a long contiguous inner run: one sub-warp per gathered row, float4 copies
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ data, long long outer, int axis_dim, int inner_v4, const float* __restrict__ indices, long long n_idx,
-                   float* __restrict__ out) {
+                   float* __restrict__ out, int* __restrict__ err) {
     const int lanes_per_row = inner_v4 >= 32 ? 32 : (inner_v4 >= 16 ? 16 : (inner_v4 >= 8 ? 8 : 4));
     const int rows_per_block = 256 / lanes_per_row;
     const int sub = threadIdx.x % lanes_per_row;
@@ -44,6 +44,7 @@ gather_rows_kernel(const float* __restrict__ data, long long outer, int axis_dim
         const long long o = row / n_idx, k = row - o * n_idx;
         long long idx = (long long)indices[k];
         if (idx < 0) idx += axis_dim;                             // negative index wrap (manipulation.rs:610)
+        if (idx < 0 || idx >= axis_dim) { if (sub == 0) *err = 1; idx = 0; }   // the reference panics (slice bounds check); reported at sync
         const float4* src = reinterpret_cast<const float4*>(data + (o * axis_dim + idx) * (long long)inner_v4 * 4);
         float4* dst = reinterpret_cast<float4*>(out + row * (long long)inner_v4 * 4);
         for (int q = sub; q < inner_v4; q += lanes_per_row) dst[q] = __ldg(src + q);
@@ -119,22 +120,24 @@ __global__ void pad_kernel(const float* __restrict__ in, PadArgs a, float* __res
 }
 
 __global__ void gather_kernel(const float* __restrict__ data, long long outer, int axis_dim, long long inner,
-                              const float* __restrict__ indices, long long n_idx, float* __restrict__ out) {
+                              const float* __restrict__ indices, long long n_idx, float* __restrict__ out, int* __restrict__ err) {
     const long long total = outer * n_idx * inner;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long k = i % inner, q = (i / inner) % n_idx, o = i / (inner * n_idx);
         long long idx = (long long)indices[q];
         if (idx < 0) idx += axis_dim;
+        if (idx < 0 || idx >= axis_dim) { *err = 1; idx = 0; }
         out[i] = data[(o * axis_dim + idx) * inner + k];
     }
 }
 __global__ void gather_elements_kernel(const float* __restrict__ data, const float* __restrict__ indices, long long outer,
-                                       int axis_dim, int idx_dim, long long inner, float* __restrict__ out) {
+                                       int axis_dim, int idx_dim, long long inner, float* __restrict__ out, int* __restrict__ err) {
     const long long total = outer * idx_dim * inner;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long k = i % inner, o = i / (inner * idx_dim);
         long long idx = (long long)indices[i];
         if (idx < 0) idx += axis_dim;
+        if (idx < 0 || idx >= axis_dim) { *err = 2; idx = 0; }
         out[i] = data[(o * axis_dim + idx) * inner + k];
     }
 }
@@ -185,7 +188,7 @@ argmax_last_kernel(const float* __restrict__ x, long long outer, int n, int32_t*
     const float* xr = x + row * n;
     unsigned long long best = 0ull;
     for (int j = lane; j < n; j += 32) {
-        unsigned long long key = ((unsigned long long)lb_fkey(xr[j]) << 32) | (unsigned)j;
+        unsigned long long key = ((unsigned long long)lb_fkey_argmax(xr[j]) << 32) | (unsigned)j;
         best = key > best ? key : best;
     }
 #pragma unroll
@@ -263,6 +266,7 @@ int lb_argmax_keys_to_ids(lele_b200_ctx* ctx, const unsigned long long* keys, lo
 extern "C" int lele_b200_strided_copy(lele_b200_ctx* ctx, const float* in, long long in_offset, const long long* out_shape,
                                       const long long* in_strides, int rank, float* out) {
     LB_REQUIRE(ctx && in && out && rank >= 0 && rank <= MAXR, "strided_copy: bad arguments");
+    LB_ENTER(ctx);
     StridedArgs a; a.rank = rank; a.total = 1; a.offset = in_offset;
     for (int i = 0; i < rank; ++i) { a.shape[i] = out_shape[i]; a.stride[i] = in_strides[i]; a.total *= out_shape[i]; }
     if (a.total == 0) return LELE_B200_OK;
@@ -306,6 +310,7 @@ extern "C" int lele_b200_strided_copy(lele_b200_ctx* ctx, const float* in, long 
 extern "C" int lele_b200_concat(lele_b200_ctx* ctx, const float* const* inputs, const long long* axis_lens, int n_inputs,
                                 long long outer, long long inner, float* out) {
     LB_REQUIRE(ctx && inputs && axis_lens && out, "concat: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(n_inputs >= 1 && n_inputs <= 16, "concat: %d inputs (supported: 1..16 per call)", n_inputs);
     ConcatArgs a; a.n = 0; long long off = 0;
     for (int i = 0; i < n_inputs; ++i) {
@@ -328,6 +333,7 @@ extern "C" int lele_b200_concat(lele_b200_ctx* ctx, const float* const* inputs, 
 extern "C" int lele_b200_pad(lele_b200_ctx* ctx, const float* in, const long long* shape, int rank, const long long* pads, int mode,
                              float value, float* out) {
     LB_REQUIRE(ctx && in && out && rank >= 1 && rank <= MAXR && mode >= 0 && mode <= 2, "pad: bad arguments");
+    LB_ENTER(ctx);
     PadArgs a; a.rank = rank; a.total = 1; a.mode = mode; a.value = value;
     for (int i = 0; i < rank; ++i) {
         long long b = pads[i] < 0 ? 0 : pads[i], e = pads[i + rank] < 0 ? 0 : pads[i + rank];   // negatives clamp to 0 (manipulation.rs:390)
@@ -342,29 +348,35 @@ extern "C" int lele_b200_pad(lele_b200_ctx* ctx, const float* in, const long lon
 extern "C" int lele_b200_gather(lele_b200_ctx* ctx, const float* data, long long outer, int axis_dim, long long inner,
                                 const float* indices, long long n_indices, float* out) {
     LB_REQUIRE(ctx && data && indices && out, "gather: NULL argument");
+    LB_ENTER(ctx);
     if (outer * n_indices * inner == 0) return LELE_B200_OK;
     if (inner % 4 == 0 && inner >= 16 && inner <= (1ll << 30) && ((((uintptr_t)data) | ((uintptr_t)out)) & 15) == 0) {
         const int inner_v4 = (int)(inner / 4);
         const int lanes = inner_v4 >= 32 ? 32 : (inner_v4 >= 16 ? 16 : (inner_v4 >= 8 ? 8 : 4));
-        gather_rows_kernel<<<grid_for(outer * n_indices * lanes), 256, 0, ctx->stream>>>(data, outer, axis_dim, inner_v4, indices, n_indices, out);
+        gather_rows_kernel<<<grid_for(outer * n_indices * lanes), 256, 0, ctx->stream>>>(data, outer, axis_dim, inner_v4, indices, n_indices, out, ctx->dev_err);
+        ctx->dev_err_armed = true;
         LB_LAUNCH_CHECK(ctx);
         return LELE_B200_OK;
     }
-    gather_kernel<<<grid_for(outer * n_indices * inner), 256, 0, ctx->stream>>>(data, outer, axis_dim, inner, indices, n_indices, out);
+    gather_kernel<<<grid_for(outer * n_indices * inner), 256, 0, ctx->stream>>>(data, outer, axis_dim, inner, indices, n_indices, out, ctx->dev_err);
+    ctx->dev_err_armed = true;
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }
 extern "C" int lele_b200_gather_elements(lele_b200_ctx* ctx, const float* data, const float* indices, long long outer, int axis_dim,
                                          int idx_dim, long long inner, float* out) {
     LB_REQUIRE(ctx && data && indices && out, "gather_elements: NULL argument");
+    LB_ENTER(ctx);
     if (outer * idx_dim * inner == 0) return LELE_B200_OK;
-    gather_elements_kernel<<<grid_for(outer * idx_dim * inner), 256, 0, ctx->stream>>>(data, indices, outer, axis_dim, idx_dim, inner, out);
+    gather_elements_kernel<<<grid_for(outer * idx_dim * inner), 256, 0, ctx->stream>>>(data, indices, outer, axis_dim, idx_dim, inner, out, ctx->dev_err);
+    ctx->dev_err_armed = true;
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }
 extern "C" int lele_b200_tile(lele_b200_ctx* ctx, const float* in, const long long* shape, const long long* repeats, int rank,
                               float* out) {
     LB_REQUIRE(ctx && in && out && rank >= 1 && rank <= MAXR, "tile: bad arguments");
+    LB_ENTER(ctx);
     TileArgs a; a.rank = rank; a.total = 1;
     for (int i = 0; i < rank; ++i) { a.in_shape[i] = shape[i]; a.out_shape[i] = shape[i] * repeats[i]; a.total *= a.out_shape[i]; }
     if (a.total == 0) return LELE_B200_OK;
@@ -374,6 +386,7 @@ extern "C" int lele_b200_tile(lele_b200_ctx* ctx, const float* in, const long lo
 }
 extern "C" int lele_b200_topk(lele_b200_ctx* ctx, const float* x, long long outer, int n, int k, float* values, float* indices) {
     LB_REQUIRE(ctx && x && values && indices && n > 0, "topk: bad arguments");
+    LB_ENTER(ctx);
     LB_REQUIRE(k >= 0 && k <= n, "topk: k=%d must be in [0, n=%d] (caller applies k=min(k,last), conv2d.rs:1396)", k, n);
     if (outer == 0 || k == 0) return LELE_B200_OK;
     topk_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, outer, n, k, values, indices);
@@ -404,6 +417,7 @@ greedy_filter_kernel(const int32_t* __restrict__ ids, int t, const uint8_t* __re
 extern "C" int lele_b200_greedy_filter(lele_b200_ctx* ctx, const int32_t* ids, int n_clips, int t, const uint8_t* skip_mask, int vocab,
                                        int32_t* out_ids, int32_t* out_len) {
     LB_REQUIRE(ctx && ids && out_ids && out_len && n_clips >= 0 && t >= 0 && vocab > 0, "greedy_filter: bad arguments");
+    LB_ENTER(ctx);
     if (n_clips == 0) return LELE_B200_OK;
     greedy_filter_kernel<<<n_clips, 32, 0, ctx->stream>>>(ids, t, skip_mask, vocab, out_ids, out_len);
     LB_LAUNCH_CHECK(ctx);
@@ -412,6 +426,7 @@ extern "C" int lele_b200_greedy_filter(lele_b200_ctx* ctx, const int32_t* ids, i
 
 extern "C" int lele_b200_argmax_last(lele_b200_ctx* ctx, const float* x, long long outer, int n, int32_t* out) {
     LB_REQUIRE(ctx && x && out && n > 0, "argmax_last: bad arguments");
+    LB_ENTER(ctx);
     if (outer == 0) return LELE_B200_OK;
     argmax_last_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, outer, n, out);
     LB_LAUNCH_CHECK(ctx);
@@ -420,6 +435,7 @@ extern "C" int lele_b200_argmax_last(lele_b200_ctx* ctx, const float* x, long lo
 extern "C" int lele_b200_resize_nearest(lele_b200_ctx* ctx, const float* x, int nb, int c, int h, int w, int oh, int ow, int mode,
                                         float* out) {
     LB_REQUIRE(ctx && x && out, "resize_nearest: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(oh > 0 && ow > 0, "Resize: output dimensions must be positive, got out_h=%d out_w=%d (conv2d.rs:1321)", oh, ow);
     long long total = (long long)nb * c * oh * ow;
     if (total == 0) return LELE_B200_OK;
@@ -430,6 +446,7 @@ extern "C" int lele_b200_resize_nearest(lele_b200_ctx* ctx, const float* x, int 
 extern "C" int lele_b200_max_pool2d(lele_b200_ctx* ctx, const float* x, int nb, int c, int h, int w, int kh, int kw, const int* pads,
                                     const int* strides, const int* dils, int ceil_mode, float* out) {
     LB_REQUIRE(ctx && x && out && pads && strides && dils, "max_pool2d: NULL argument");
+    LB_ENTER(ctx);
     PoolArgs a;
     a.h = h; a.w = w; a.kh = kh; a.kw = kw; a.pt = pads[0]; a.pl = pads[1]; a.sh = strides[0]; a.sw = strides[1]; a.dh = dils[0]; a.dw = dils[1];
     int nh = h + pads[0] + pads[2] - a.dh * (kh - 1) - 1, nw = w + pads[1] + pads[3] - a.dw * (kw - 1) - 1;

@@ -602,22 +602,16 @@ int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const flo
         const int R = (T + CS - 1) / CS;
         const size_t smem_r = (size_t)(R > 8 ? R - 8 : 0) * 512 * 4;
         if (smem_r <= 56 * 1024 && (R > 8 ? R - 8 : 0) <= LNQ_CHUNK * LNQ_MAX_CHUNKS) {
-            static thread_local size_t smem_r_set = 0;
-            if (smem_r > smem_r_set || smem_r_set == 0) {
-                LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_reg_kernel<8, 4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_r ? smem_r : 16)));
-                smem_r_set = smem_r ? smem_r : 16;
-            }
+            { int rc_a = lb_func_smem(ctx, (const void*)ln_quant_cluster_reg_kernel<8, 4, 4, 2>, smem_r ? smem_r : 16); if (rc_a) return rc_a; }
             LB_CHECK_CUDA(lb_launch_pdl(ln_quant_cluster_reg_kernel<8, 4, 4, 2>, dim3(CS, clips, 1), dim3(4 * 32), smem_r, ctx->stream, CS, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out));
             LB_LAUNCH_CHECK(ctx);
             return LELE_B200_OK;
         }
     }
     const size_t smem = (size_t)((T + CS - 1) / CS) * 512 * 4;
-    static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-        LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_kernel<4, 24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LB_CHECK_CUDA(cudaFuncSetAttribute(ln_quant_cluster_kernel<8, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    {
+        int rc_a = CS == 4 ? lb_func_smem(ctx, (const void*)ln_quant_cluster_kernel<4, 24, 1>, smem) : lb_func_smem(ctx, (const void*)ln_quant_cluster_kernel<8, 8, 3>, smem);
+        if (rc_a) return rc_a;
     }
     if (CS == 4) LB_CHECK_CUDA(lb_launch_pdl(ln_quant_cluster_kernel<4, 24, 1>, dim3(CS, clips, 1), dim3(24 * 32), smem, ctx->stream, CS, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
     else LB_CHECK_CUDA(lb_launch_pdl(ln_quant_cluster_kernel<8, 8, 3>, dim3(CS, clips, 1), dim3(8 * 32), smem, ctx->stream, CS, x, gamma, beta, T, eps, a_u8, rowsum, row_scale, row_zp, keys_out, dbg));
@@ -652,6 +646,7 @@ int lb_layer_norm_quantize(lele_b200_ctx* ctx, const float* x, const float* gamm
 extern "C" int lele_b200_layer_norm(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta,
                                     long long outer, int n, float eps, float* out) {
     LB_REQUIRE(ctx && x && out && n > 0 && outer >= 0, "layer_norm: bad arguments");
+    LB_ENTER(ctx);
     return lb_layer_norm_minmax(ctx, x, gamma, beta, outer, n, eps, out, nullptr, 1);
 }
 
@@ -683,6 +678,7 @@ softmax_kernel(const float* __restrict__ x, long long outer, int n, float* __res
 
 extern "C" int lele_b200_softmax(lele_b200_ctx* ctx, const float* x, long long outer, int n, float* out) {
     LB_REQUIRE(ctx && x && out && n > 0 && outer >= 0, "softmax: bad arguments");
+    LB_ENTER(ctx);
     if (outer == 0) return LELE_B200_OK;
     softmax_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, outer, n, out);
     LB_LAUNCH_CHECK(ctx);
@@ -705,6 +701,7 @@ extern "C" int lele_b200_batch_norm(lele_b200_ctx* ctx, const float* x, const fl
                                     const float* mean, const float* var, int nb, int c, long long inner, float eps,
                                     float* out) {
     LB_REQUIRE(ctx && x && scale && bias && mean && var && out, "batch_norm: NULL argument");
+    LB_ENTER(ctx);
     long long total = (long long)nb * c * inner;
     if (total == 0) return LELE_B200_OK;
     batch_norm_kernel<<<min(lb_ceil_div(total, 256), 148 * 16), 256, 0, ctx->stream>>>(x, scale, bias, mean, var, c, inner, eps, total, out);
@@ -729,6 +726,7 @@ rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, long l
 extern "C" int lele_b200_rms_norm(lele_b200_ctx* ctx, const float* x, const float* w, long long outer, int n, float eps,
                                   float* out) {
     LB_REQUIRE(ctx && x && out && n > 0, "rms_norm: bad arguments");
+    LB_ENTER(ctx);
     if (outer == 0) return LELE_B200_OK;
     rms_norm_kernel<<<lb_ceil_div(outer, 8), 256, 0, ctx->stream>>>(x, w, outer, n, eps, out);
     LB_LAUNCH_CHECK(ctx);

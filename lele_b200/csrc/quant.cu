@@ -192,6 +192,7 @@ __global__ void dql_empty_kernel(float* scale_out, float* zp_out, int n) {
 extern "C" int lele_b200_dynamic_quantize_linear(lele_b200_ctx* ctx, const float* x, int n_slices, long long slice_len,
                                                  float* q, float* scale, float* zp) {
     LB_REQUIRE(ctx && scale && zp && n_slices >= 0 && slice_len >= 0, "dynamic_quantize_linear: bad arguments");
+    LB_ENTER(ctx);
     if (n_slices == 0) return LELE_B200_OK;
     if (slice_len == 0) {
         dql_empty_kernel<<<lb_ceil_div(n_slices, 128), 128, 0, ctx->stream>>>(scale, zp, n_slices);
@@ -220,14 +221,15 @@ __device__ __forceinline__ int f32_as_u8(float v) {  // Rust `as u8`: saturating
     return (int)fminf(fmaxf(v, 0.0f), 255.0f);
 }
 __global__ void __launch_bounds__(256)
-mmi_kernel(const float* __restrict__ a, const float* __restrict__ b, int m, int k, int n, int zpa, int zpb,
+mmi_kernel(const float* __restrict__ a, const float* __restrict__ b_all, long long a_bs, long long b_bs, int m, int k, int n, int zpa, int zpb,
            const float* __restrict__ scale, int scale_len, const float* __restrict__ bias, int relu, float* __restrict__ out) {
     // 16x16 output tile per CTA, k staged through shared memory in chunks of 16
     __shared__ int sa[16][17], sb[16][17];
     const int bi = blockIdx.z;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
-    const float* ab = a + (long long)bi * m * k;
+    const float* ab = a + (long long)bi * a_bs;                   // a stride of 0 broadcasts the single matrix (quantization.rs:1172-1173)
+    const float* b = b_all + (long long)bi * b_bs;
     int acc = 0;
     for (int k0 = 0; k0 < k; k0 += 16) {
         sa[ty][tx] = (row < m && k0 + tx < k) ? f32_as_u8(ab[(long long)row * k + k0 + tx]) - zpa : 0;
@@ -245,17 +247,26 @@ mmi_kernel(const float* __restrict__ a, const float* __restrict__ b, int m, int 
         out[((long long)bi * m + row) * n + col] = v;
     }
 }
+extern "C" int lele_b200_mat_mul_integer_batched(lele_b200_ctx* ctx, const float* a, const float* b, int batch_a, int batch_b, int m, int k,
+                                                 int n, float a_zp, float b_zp, const float* scale, int scale_len, const float* bias,
+                                                 int relu, float* out) {
+    LB_REQUIRE(ctx && a && b && out, "mat_mul_integer: NULL argument");
+    LB_ENTER(ctx);
+    LB_REQUIRE(batch_a >= 0 && batch_b >= 0 && m >= 0 && k >= 0 && n >= 0, "mat_mul_integer: negative dims");
+    LB_REQUIRE(batch_a == batch_b || batch_a == 1 || batch_b == 1, "mat_mul_integer: batch %d vs %d (equal, or one side 1; quantization.rs:1157-1173)", batch_a, batch_b);
+    LB_REQUIRE(!scale || scale_len == 1 || scale_len == n, "mat_mul_integer: scale length %d is neither 1 nor n=%d", scale_len, n);
+    const int batch = batch_a > batch_b ? batch_a : batch_b;
+    if (batch == 0 || m == 0 || n == 0) return LELE_B200_OK;
+    dim3 grid(lb_ceil_div(n, 16), lb_ceil_div(m, 16), batch);
+    mmi_kernel<<<grid, 256, 0, ctx->stream>>>(a, b, batch_a == 1 ? 0ll : (long long)m * k, batch_b == 1 ? 0ll : (long long)k * n, m, k, n, (int)a_zp,
+                                              (int)b_zp, scale, scale_len, bias, relu, out);
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
 extern "C" int lele_b200_mat_mul_integer(lele_b200_ctx* ctx, const float* a, const float* b, int batch, int m, int k, int n,
                                          float a_zp, float b_zp, const float* scale, int scale_len, const float* bias,
                                          int relu, float* out) {
-    LB_REQUIRE(ctx && a && b && out, "mat_mul_integer: NULL argument");
-    LB_REQUIRE(batch >= 0 && m >= 0 && k >= 0 && n >= 0, "mat_mul_integer: negative dims");
-    LB_REQUIRE(!scale || scale_len == 1 || scale_len == n, "mat_mul_integer: scale length %d is neither 1 nor n=%d", scale_len, n);
-    if (batch == 0 || m == 0 || n == 0) return LELE_B200_OK;
-    dim3 grid(lb_ceil_div(n, 16), lb_ceil_div(m, 16), batch);
-    mmi_kernel<<<grid, 256, 0, ctx->stream>>>(a, b, m, k, n, (int)a_zp, (int)b_zp, scale, scale_len, bias, relu, out);
-    LB_LAUNCH_CHECK(ctx);
-    return LELE_B200_OK;
+    return lele_b200_mat_mul_integer_batched(ctx, a, b, batch, 1, m, k, n, a_zp, b_zp, scale, scale_len, bias, relu, out);
 }
 
 // ---------------------------------------------------------------------------
@@ -292,6 +303,7 @@ __global__ void prep_vectors_kernel(const float* __restrict__ w_scale, int w_sca
 extern "C" int lele_b200_prepare_weights(lele_b200_ctx* ctx, const uint8_t* w, int k, int n, const float* w_scale,
                                          int w_scale_len, int w_zp, const float* bias, lele_b200_qweights** out) {
     LB_REQUIRE(ctx && w && w_scale && out, "prepare_weights: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(k > 0 && n > 0, "prepare_weights: empty weight");
     LB_REQUIRE(w_scale_len == 1 || w_scale_len == n, "prepare_weights: weight_scale length %d is neither 1 nor n=%d", w_scale_len, n);
     LB_REQUIRE(w_zp >= 0 && w_zp <= 255, "prepare_weights: u8 zero point out of range (x86 handles u8 weights only, SURVEY appendix A)");
@@ -348,7 +360,7 @@ gemm_i8_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ W
         if (ep.minmax_keys) {
             lb_mm_update(ep.minmax_keys, row / ep.rows_per_slice, v, v);
         }
-        if (ep.argmax_keys) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey(v) << 32) | (unsigned)col);
+        if (ep.argmax_keys) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey_argmax(v) << 32) | (unsigned)col);
         if (ep.out) ep.out[o] = v;
     }
 }
@@ -396,6 +408,7 @@ static int lb_quantized_linear(lele_b200_ctx* ctx, const float* x, const unsigne
 extern "C" int lele_b200_fused_quantized_linear(lele_b200_ctx* ctx, const float* x, int n_slices, int m,
                                                 const lele_b200_qweights* w, int relu, float* out) {
     LB_REQUIRE(ctx && x && w && out, "fused_quantized_linear: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(n_slices >= 0 && m >= 0, "fused_quantized_linear: negative dims");
     const long long M = (long long)n_slices * m;
     if (M == 0) return LELE_B200_OK;

@@ -178,7 +178,7 @@ int run_rnn(lele_b200_ctx* ctx, const float* x, const float* w, const float* r, 
         constexpr int RREG = 64;
         const size_t smem_r = sizeof(float) * ((size_t)(2 * H + 2 * GH) + (size_t)(H > RREG ? H - RREG : 0) * GH);
         if (H >= RREG && H % 4 == 0 && GH <= 512 && GH % 32 == 0 && smem_r <= 200 * 1024 && !getenv("LELE_B200_RNN_STREAM_R")) {
-            LB_CHECK_CUDA(cudaFuncSetAttribute(rnn_seq_resident_kernel<G, RREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            if ((rc = lb_func_smem(ctx, (const void*)rnn_seq_resident_kernel<G, RREG>, smem_r))) return rc;
             rnn_seq_resident_kernel<G, RREG><<<n_seq, GH, smem_r, ctx->stream>>>(wx, rt, bias, h0, c0, seq, H, y, h, c);
             LB_LAUNCH_CHECK(ctx);
             return LELE_B200_OK;
@@ -187,7 +187,7 @@ int run_rnn(lele_b200_ctx* ctx, const float* x, const float* w, const float* r, 
     int threads = GH < 1024 ? ((GH + 31) / 32) * 32 : 1024;
     size_t smem = sizeof(float) * (size_t)(2 * H + 2 * GH);
     LB_REQUIRE(smem <= 200 * 1024, "rnn: hidden size %d too large", H);
-    if (smem > 48 * 1024) LB_CHECK_CUDA(cudaFuncSetAttribute(rnn_seq_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024 && (rc = lb_func_smem(ctx, (const void*)rnn_seq_kernel<G>, smem))) return rc;
     rnn_seq_kernel<G><<<n_seq, threads, smem, ctx->stream>>>(wx, rt, bias, h0, c0, seq, H, y, h, c);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
@@ -198,12 +198,14 @@ extern "C" int lele_b200_lstm(lele_b200_ctx* ctx, const float* x, const float* w
                               const float* h0, const float* c0, int n_seq, int seq, int in_size, int hidden, float* y, float* h,
                               float* c) {
     LB_REQUIRE(ctx && x && w && r && y && h && c, "lstm: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(hidden > 0 && in_size > 0 && seq >= 0 && n_seq >= 0, "lstm: bad dims");
     return run_rnn<4>(ctx, x, w, r, bias, h0, c0, n_seq, seq, in_size, hidden, y, h, c);
 }
 extern "C" int lele_b200_gru(lele_b200_ctx* ctx, const float* x, const float* w, const float* r, const float* bias,
                              const float* h0, int n_seq, int seq, int in_size, int hidden, float* y, float* h) {
     LB_REQUIRE(ctx && x && w && r && y && h, "gru: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(hidden > 0 && in_size > 0 && seq >= 0 && n_seq >= 0, "gru: bad dims");
     return run_rnn<3>(ctx, x, w, r, bias, h0, nullptr, n_seq, seq, in_size, hidden, y, h, nullptr);
 }

@@ -121,6 +121,37 @@ fsmn_window_kernel(const float* __restrict__ qkv, const float* __restrict__ w, i
     }
 }
 
+// The same block fed from V^T [B][H][128][Tp] (keys contiguous), the only copy of v the product path keeps: the QKV projection's
+// epilogue writes v transposed for the attention kernel and skips the row-major v columns (36 MB per layer less HBM traffic at
+// B = 64).  One CTA = (clip, 32 channels): the channel rows are staged in shared memory (coalesced along time), each warp then
+// walks time steps with lane = channel, so the [M, d] output rows are written 128 B at a time.  Tap order and the unfused
+// mul + add are those of fsmn_kernel (bit-identical results).
+template <int K>
+__global__ void __launch_bounds__(256)
+fsmn_vt_kernel(const float* __restrict__ vt, const float* __restrict__ w, int T, int Tp, int d, float* __restrict__ out) {
+    extern __shared__ float fs_tile[];                 // [32][Tp + 1]
+    constexpr int PAD = (K - 1) / 2;
+    const int b = blockIdx.y, c0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pitch = Tp + 1;
+    const float* src = vt + ((size_t)b * d + c0) * (size_t)Tp;     // channel c = h * 128 + dk -> row (b * d + c) of V^T
+    for (int i = threadIdx.x; i < 32 * Tp; i += 256) { const int ch = i / Tp, t = i - ch * Tp; fs_tile[ch * pitch + t] = src[i]; }
+    float wk[K];
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) wk[kk] = __ldg(w + (size_t)(c0 + lane) * K + kk);
+    __syncthreads();
+    const float* row = fs_tile + lane * pitch;
+    for (int tt = warp; tt < T; tt += 8) {
+        float s = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+            const int pos = tt + kk - PAD;
+            if (pos >= 0 && pos < T) s = __fadd_rn(s, __fmul_rn(wk[kk], row[pos]));
+        }
+        out[((size_t)b * T + tt) * d + c0 + lane] = __fadd_rn(s, row[tt]);
+    }
+}
+
 __global__ void scale_copy_q_kernel(const float* __restrict__ qkv, long long M, int d, float qscale, float* __restrict__ q) {
     const long long total = M * d;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -176,18 +207,24 @@ struct lele_b200_sensevoice {
     int ffn_twopass = 1;              // FFN1 as max-only pass + quantising pass (no f32 [M, ffn] round trip); LELE_B200_FFN_TWOPASS=0 disables
     int fuse_lnq = 1;                 // LayerNorm + quantiser fused for the encoder width (LELE_B200_FUSE_LNQ=0 disables)
     int attn_simt = 0;   // LELE_B200_ATTN_SIMT=1: CUDA-core attention (cross-check of the tcgen05 path)
+    int qkv_full = 0;    // LELE_B200_QKV_FULL=1: the QKV projection also writes the row-major v columns (default: v exists only as V^T)
     // profiling
     int profiling = 0;
     // CUDA-graph replay of the whole forward (the ~1000 launches of one step are CPU-bound otherwise)
     struct GraphKey { const float* pcm; int B, n_samples, lang, textnorm, n_layers; int32_t* ids; float* logits; };
     int use_graph = 1;              // LELE_B200_GRAPH=0 disables
+    // capture policy: library-owned staging buffers (pcm_stage, pcm_slot[]) are captured on first use; a caller-owned buffer set is
+    // captured the SECOND time the same (pointers, geometry) key is seen, so a host that passes fresh device buffers on every call
+    // (the numpy-form wrappers) never pays capture + instantiate and never evicts the graphs the serving entries replay
+    GraphKey seen_key[4] = {};
+    int seen_next = 0;
     bool warmed = false;            // one eager forward has run (lazy tables / attributes / scratch are in place)
     // small cache of captured forwards (the pipelined host entry alternates between two staging buffers)
     static constexpr int N_GRAPHS = 4;
     cudaGraphExec_t graph_exec[N_GRAPHS] = {nullptr, nullptr, nullptr, nullptr};
     GraphKey graph_key[N_GRAPHS] = {};
     unsigned long long graph_launches[N_GRAPHS] = {0, 0, 0, 0};
-    int graph_next = 0;             // round-robin replacement
+    unsigned long long graph_used[N_GRAPHS] = {0, 0, 0, 0}, graph_clock = 0;   // least-recently-used replacement
     // pipelined host entry (transcribe_host_async): 2 slots of staging, H2D / D2H on their own streams so the copy of
     // batch i+1 overlaps the forward of batch i
     static constexpr int N_SLOTS = 2;
@@ -279,10 +316,12 @@ int sv_alloc(void** p, size_t bytes) {
 extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* blob_dev, size_t nbytes, const uint8_t* hdr_host,
                                            size_t header_bytes, int max_clips, int max_samples, lele_b200_sensevoice** out) {
     LB_REQUIRE(ctx && blob_dev && hdr_host && out, "sensevoice_create: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(header_bytes >= 256, "sensevoice_create: header too short");
     const int32_t* hd = (const int32_t*)hdr_host;
     LB_REQUIRE(hd[0] == 0x454C454C && hd[1] == 1, "sensevoice_create: bad blob magic/version");
     lele_b200_sensevoice* m = new lele_b200_sensevoice();
+    struct Guard { lele_b200_sensevoice* p; lele_b200_ctx* c; ~Guard() { if (p) lele_b200_sensevoice_destroy(c, p); } } guard{m, ctx};   // LB_REQUIRE returns below must not leak m
     m->n_layers = hd[2]; m->d = hd[3]; m->d_in = hd[4]; m->ffn = hd[5]; m->heads = hd[6]; m->fsmn_k = hd[7]; m->vocab = hd[8];
     m->n_embed = hd[9]; m->max_t = hd[10]; m->n_stage1 = hd[11]; m->n_tensors = hd[12];
     LB_REQUIRE(header_bytes >= 256 + 16 * (size_t)m->n_tensors, "sensevoice_create: header does not contain the tensor table");
@@ -317,7 +356,7 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
         if (!rc) rc = prep(m->lt(l, SV_L_FFN2_W), m->ffn, m->d, m->lt(l, SV_L_FFN2_SCALE), m->lt(l, SV_L_FFN2_ZP), m->lt(l, SV_L_FFN2_BIAS), &m->lin[l * 4 + 3]);
     }
     if (!rc) rc = prep(m->tensor(SV_G_CTC_W), m->d, m->vocab, m->tensor(SV_G_CTC_SCALE), m->tensor(SV_G_CTC_ZP), m->tensor(SV_G_CTC_BIAS), &m->lin[(size_t)m->n_layers * 4]);
-    if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
+    if (rc) return rc;   // (guard frees m)
 
     const size_t B = max_clips, M = B * m->max_T;
     const int wide = m->d_in > m->d ? m->d_in : m->d;
@@ -341,12 +380,13 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("LELE_B200_GRAPH"); m->use_graph = (e && e[0] == '0') ? 0 : 1; }
+    m->qkv_full = lb_env_flag("LELE_B200_QKV_FULL", 0) ? 1 : 0;
     { const char* e = getenv("LELE_B200_FUSE_LNQ"); m->fuse_lnq = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }   // 0 unfused, 1 cluster, 2 two-pass
     if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); m->side = nullptr; }
     if (!rc) rc = sv_alloc((void**)&m->pcm_stage, sizeof(float) * B * (size_t)max_samples);
     if (!rc) rc = sv_alloc((void**)&m->ids_stage, sizeof(int32_t) * M);
-    if (rc) { lele_b200_sensevoice_destroy(ctx, m); return rc; }
+    if (rc) return rc;   // (guard frees m)
     {   // clip lanes (see the struct): views are shallow copies whose workspace pointers are re-based per call
         const char* e = getenv("LELE_B200_LANES");
         m->n_lanes = e ? atoi(e) : 1;
@@ -370,6 +410,7 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
             if (!ok) { cudaGetLastError(); m->n_lanes = 1; }
         }
     }
+    guard.p = nullptr;
     *out = m;
     return LELE_B200_OK;
 }
@@ -441,6 +482,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     int cur = din;
     const bool attn_tc = !m->attn_simt && lb_attention_tc_supported(T, d, H);
     int attn_ops_ready = 0;
+    bool fsmn_from_vt = false; const float* vt_ptr = nullptr; int vt_tp = 0;
     for (int l = 0; l < n_layers; ++l) {
         // ---- self-attention block ----
         {
@@ -450,7 +492,10 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             if (attn_tc && m->lin[l * 4 + 0]->k % 16 == 0 && !getenv("LELE_B200_FORCE_SIMT") && !getenv("LELE_B200_GEMM_NO_TMA_STORE")) {
                 lb_attention_tc_operands(m->attn_scratch, B, T, d, H, &ep.vt, &ep.vt_tp);
                 attn_ops_ready = 1;
+                ep.skip_v_out = (!m->qkv_full && m->fsmn_k == 11 && d % 32 == 0) ? 1 : 0;   // attention and the FSMN block both read V^T
             } else attn_ops_ready = 0;
+            fsmn_from_vt = attn_ops_ready && ep.skip_v_out;
+            vt_ptr = ep.vt; vt_tp = ep.vt_tp;
             int rc_ = sv_ln_linear(ctx, m, xin, (const float*)m->lt(l, SV_L_LN1_G), (const float*)m->lt(l, SV_L_LN1_B), cur, site(l * 4 + 0), M, T,
                                    m->lin[l * 4 + 0], qs, ep, P_G_QKV);
             if (rc_) return rc_;
@@ -463,7 +508,10 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         }
         {
             ProfScope ps(m, ctx, P_FSMN);
-            if (m->fsmn_k == 11)
+            if (fsmn_from_vt) {
+                const size_t sm = sizeof(float) * 32 * (size_t)(vt_tp + 1);
+                fsmn_vt_kernel<11><<<dim3(d / 32, B), 256, sm, fs>>>(vt_ptr, (const float*)m->lt(l, SV_L_FSMN_W), T, vt_tp, d, m->fsmn);
+            } else if (m->fsmn_k == 11)
                 fsmn_window_kernel<11><<<dim3(lb_ceil_div(d, 128), lb_ceil_div(T, FS_TCH), B), 128, 0, fs>>>(
                     m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), T, d, m->fsmn);
             else
@@ -629,6 +677,7 @@ extern "C" int lele_b200_sensevoice_forward_features(lele_b200_ctx* ctx, lele_b2
                                                      int t, int lang, int textnorm, int n_layers_limit, int32_t* ids_dev,
                                                      float* logits_dev_opt) {
     LB_REQUIRE(ctx && m && feats_dev, "sensevoice_forward_features: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && t >= 1 && t + 4 <= m->max_T, "sensevoice_forward_features: batch/length exceeds workspace");
     int rc = sv_encoder_lanes(ctx, m, feats_dev, n_clips, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
     if (rc) return rc;
@@ -645,6 +694,7 @@ static int sv_forward_eager(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const f
 extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_dev, int n_clips, int n_samples,
                                             int lang, int textnorm, int n_layers_limit, int32_t* ids_dev, float* logits_dev_opt) {
     LB_REQUIRE(ctx && m && pcm_dev, "sensevoice_forward: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && n_samples <= m->max_samples, "sensevoice_forward: batch/length exceeds workspace");
     int frames = lele_b200_frontend_num_frames(n_samples);
     LB_REQUIRE(frames > 0, "sensevoice_forward: clip shorter than one frame (400 samples)");
@@ -656,17 +706,35 @@ extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensev
         return sv_finish_profile(ctx, m);
     }
     const lele_b200_sensevoice::GraphKey key = {pcm_dev, n_clips, n_samples, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt};
+    auto same = [](const lele_b200_sensevoice::GraphKey& a, const lele_b200_sensevoice::GraphKey& b) {   // (not memcmp: the struct has padding)
+        return a.pcm == b.pcm && a.B == b.B && a.n_samples == b.n_samples && a.lang == b.lang && a.textnorm == b.textnorm &&
+               a.n_layers == b.n_layers && a.ids == b.ids && a.logits == b.logits;
+    };
     for (int g = 0; g < lele_b200_sensevoice::N_GRAPHS; ++g)
-        if (m->graph_exec[g] && memcmp(&key, &m->graph_key[g], sizeof(key)) == 0) {
+        if (m->graph_exec[g] && same(key, m->graph_key[g])) {
             LB_CHECK_CUDA(cudaGraphLaunch(m->graph_exec[g], ctx->stream));
             ctx->launches += m->graph_launches[g];
+            m->graph_used[g] = ++m->graph_clock;
             return LELE_B200_OK;
         }
+    // Caller-owned buffers (the numpy-form entry points allocate fresh ones per call) would miss on every call and evict the
+    // graphs of the library-owned staging slots the serving entries replay: those calls run eagerly and capture nothing.
+    bool capture_now = pcm_dev == m->pcm_stage || pcm_dev == m->pcm_slot[0] || pcm_dev == m->pcm_slot[1];
+    for (int i = 0; i < 4 && !capture_now; ++i) capture_now = m->seen_key[i].pcm != nullptr && same(key, m->seen_key[i]);
+    if (!capture_now) {
+        m->seen_key[m->seen_next] = key; m->seen_next = (m->seen_next + 1) % 4;
+        int rc = sv_forward_eager(ctx, m, pcm_dev, n_clips, n_samples, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
+        if (rc) return rc;
+        m->warmed = true;
+        return LELE_B200_OK;
+    }
     // new shape / pointers: one eager pass (also the warm-up that performs every lazy allocation), then capture
     int rc = sv_forward_eager(ctx, m, pcm_dev, n_clips, n_samples, t, lang, textnorm, n_layers_limit, ids_dev, logits_dev_opt);
     if (rc) return rc;
     m->warmed = true;
-    const int gi = m->graph_next; m->graph_next = (m->graph_next + 1) % lele_b200_sensevoice::N_GRAPHS;
+    int gi = 0;
+    for (int g = 1; g < lele_b200_sensevoice::N_GRAPHS; ++g)
+        if (!m->graph_exec[g] ? m->graph_exec[gi] != nullptr : (m->graph_exec[gi] && m->graph_used[g] < m->graph_used[gi])) gi = g;
     if (m->graph_exec[gi]) { cudaGraphExecDestroy(m->graph_exec[gi]); m->graph_exec[gi] = nullptr; }
     const unsigned long long l0 = ctx->launches;
     LB_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
@@ -681,6 +749,7 @@ extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensev
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { m->graph_exec[gi] = nullptr; lb_set_error("sensevoice_forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
     m->graph_key[gi] = key;
+    m->graph_used[gi] = ++m->graph_clock;
     cudaGraphUpload(m->graph_exec[gi], ctx->stream);   // pre-stage the executable graph on the device: the first replay then costs what every replay costs
     cudaGetLastError();
     return LELE_B200_OK;           // this call's result was produced by the eager pass above
@@ -689,6 +758,7 @@ extern "C" int lele_b200_sensevoice_forward(lele_b200_ctx* ctx, lele_b200_sensev
 extern "C" int lele_b200_sensevoice_transcribe_host(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_host, int n_clips,
                                                     int n_samples, int lang, int textnorm, int32_t* ids_host) {
     LB_REQUIRE(ctx && m && pcm_host && ids_host, "sensevoice_transcribe_host: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && n_samples <= m->max_samples, "sensevoice_transcribe_host: batch/length exceeds workspace");
     int T = lele_b200_sensevoice_rows(m, n_samples);
     LB_REQUIRE(T > 0, "sensevoice_transcribe_host: clip shorter than one frame");
@@ -722,6 +792,7 @@ static int sv_pipeline_init(lele_b200_sensevoice* m) {
 extern "C" int lele_b200_sensevoice_transcribe_host_async(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_host, int n_clips,
                                                           int n_samples, int lang, int textnorm, int32_t* ids_host, int slot) {
     LB_REQUIRE(ctx && m && pcm_host && ids_host, "sensevoice_transcribe_host_async: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(slot >= 0 && slot < lele_b200_sensevoice::N_SLOTS, "sensevoice_transcribe_host_async: slot %d out of range", slot);
     LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && n_samples <= m->max_samples, "sensevoice_transcribe_host_async: batch/length exceeds workspace");
     LB_REQUIRE(!m->slot_busy[slot], "sensevoice_transcribe_host_async: slot %d still in flight (call transcribe_wait first)", slot);
@@ -745,6 +816,7 @@ extern "C" int lele_b200_sensevoice_transcribe_host_async(lele_b200_ctx* ctx, le
 
 extern "C" int lele_b200_sensevoice_transcribe_wait(lele_b200_ctx* ctx, lele_b200_sensevoice* m, int slot) {
     LB_REQUIRE(ctx && m, "sensevoice_transcribe_wait: NULL argument");
+    LB_ENTER(ctx);
     LB_REQUIRE(slot >= 0 && slot < lele_b200_sensevoice::N_SLOTS, "sensevoice_transcribe_wait: slot %d out of range", slot);
     if (!m->slot_busy[slot]) return LELE_B200_OK;
     LB_CHECK_CUDA(cudaEventSynchronize(m->ev_d2h[slot]));
@@ -761,7 +833,7 @@ extern "C" int lele_b200_sensevoice_workspace(lele_b200_sensevoice* m, const cha
         {"lfr", m->lfr, sizeof(float) * B * t * m->d_in}, {"feats", m->feats, sizeof(float) * B * t * m->d_in},
         {"x0", m->x0, sizeof(float) * M * m->d_in}, {"x", m->x, sizeof(float) * M * m->d}, {"h", m->h, sizeof(float) * M * wide},
         {"qkv", m->qkv, sizeof(float) * M * 3 * m->d}, {"fsmn", m->fsmn, sizeof(float) * M * m->d}, {"att", m->att, sizeof(float) * M * m->d},
-        {"f1", m->f1, sizeof(float) * M * m->ffn}, {"keys", m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1)}};
+        {"f1", m->f1, sizeof(float) * M * m->ffn}, {"vt", m->attn_scratch, lb_attention_tc_scratch_bytes(m->max_clips, m->max_T, m->d, m->heads)}, {"keys", m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1)}};
     for (auto& e : tab)
         if (strcmp(e.n, name) == 0) { *dptr = e.p; *nbytes = e.b; return LELE_B200_OK; }
     lb_set_error("sensevoice_workspace: unknown buffer '%s'", name);

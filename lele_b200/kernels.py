@@ -198,11 +198,19 @@ def dynamic_quantize_linear(x, ctx=None):
 
 
 def mat_mul_integer(a, b, a_zero_point=0.0, b_zero_point=0.0, scale=None, bias=None, relu=False, ctx=None):
-    """mat_mul_integer / _with_scale_bias / _with_scale_bias_relu (quantization.rs:8-72)"""
+    """mat_mul_integer / _with_scale_bias / _with_scale_bias_relu (quantization.rs:8-72).  a [.., M, K], b [.., K, N]: equal batch, or
+    the side whose batch is 1 is broadcast (quantization.rs:1157-1173)."""
     a, b = _f(a), _f(b)
-    m, k = a.shape[-2:]; n = b.shape[-1]; batch = _prod(a.shape[:-2])
+    if a.ndim < 2 or b.ndim < 2:
+        raise LeleB200Error("MatMulInteger: both operands need rank >= 2")
+    m, k = a.shape[-2:]; n = b.shape[-1]; ba = _prod(a.shape[:-2]); bb = _prod(b.shape[:-2])
+    if b.shape[-2] != k:
+        raise LeleB200Error(f"MatMulInteger: K mismatch {k} vs {b.shape[-2]} (the reference panics on the slice bounds, quantization.rs:1176)")
+    if not (ba == bb or ba == 1 or bb == 1):
+        raise LeleB200Error(f"MatMulInteger: batch {ba} vs {bb} (equal, or one side 1; quantization.rs:1157-1173)")
+    lead = a.shape[:-2] if ba >= bb else b.shape[:-2]
     sc = None if scale is None else _f(scale).reshape(-1); bi = None if bias is None else _f(bias).reshape(-1)
-    return _run(a.shape[:-1] + (n,), lambda c, o, pa, pb, ps, pbi: call("lele_b200_mat_mul_integer", c.h, pa, pb, i32(batch), i32(m), i32(k), i32(n), f32(a_zero_point), f32(b_zero_point), ps, i32(0 if sc is None else sc.size), pbi, i32(int(relu)), o), a, b, sc, bi, ctx=ctx)
+    return _run(tuple(lead) + (m, n), lambda c, o, pa, pb, ps, pbi: call("lele_b200_mat_mul_integer_batched", c.h, pa, pb, i32(ba), i32(bb), i32(m), i32(k), i32(n), f32(a_zero_point), f32(b_zero_point), ps, i32(0 if sc is None else sc.size), pbi, i32(int(relu)), o), a, b, sc, bi, ctx=ctx)
 
 
 class PreparedWeights:
