@@ -26,6 +26,7 @@ N_SAMPLES = 256000
 AUDIO_S_PER_CLIP = N_SAMPLES / 16000.0
 METRIC = "audio-sec/sec (1/RTF) SenseVoiceSmall 16kHz"
 UNIT = "audio-s/s"
+WORKLOAD = "SenseVoiceSmall-shaped ASR (70 SANM layers d512 h4 ffn2048, CTC 25055), synthetic 16 kHz x 16 s clips, random-init int8 weights"
 
 
 def linear_flops_per_clip(cfg, T):
@@ -35,25 +36,46 @@ def linear_flops_per_clip(cfg, T):
     return tot
 
 
-def cpu_baseline_run(blob, n_threads, first_clip, n_samples=N_SAMPLES):
-    """Times the CPU restatement of lele's path (oracle port): one clip (16 s unless bounded) per thread,
-    each thread single-threaded like lele itself (Par::Seq, src/kernels/gemm.rs:196)."""
-    from lele_b200.sensevoice_weights import synth_pcm
-    from oracle.binding import SenseVoiceRef
-    ref = SenseVoiceRef(blob)
-    clips = [synth_pcm(first_clip + i, n_samples) for i in range(n_threads)]
-    ref.pcm_to_ids(clips[0][:16000])  # touch code / page in the blob
-    out = [None] * n_threads
+def _weights_module():
+    """lele_b200/sensevoice_weights.py (numpy only: the synthetic blob + PCM generators shared by both arms) loaded BY PATH: importing
+    the lele_b200 package would map liblele_b200.so into the process, and the reference arm must not carry the product library."""
+    import importlib.util
+    if "_sv_weights" in sys.modules:
+        return sys.modules["_sv_weights"]
+    spec = importlib.util.spec_from_file_location("_sv_weights", os.path.join(ROOT, "lele_b200", "sensevoice_weights.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_sv_weights"] = mod            # (dataclasses look the defining module up by name)
+    spec.loader.exec_module(mod)
+    return mod
 
-    def work(i):
-        out[i] = ref.pcm_to_ids(clips[i])
+
+def cpu_baseline_run(blob, n_threads, first_clip, n_samples=N_SAMPLES, n_clips=None, ref=None):
+    """Times the CPU restatement of lele's path (oracle port) on `n_clips` clips (default: one per thread): a pool of `n_threads`
+    workers, each clip processed by ONE thread from PCM to ids, like lele itself (single-threaded, Par::Seq, src/kernels/gemm.rs:196)."""
+    from oracle.binding import SenseVoiceRef
+    W = _weights_module()
+    if ref is None:
+        ref = SenseVoiceRef(blob)
+        ref.pcm_to_ids(W.synth_pcm(first_clip, 16000))  # touch code / page in the blob
+    n_clips = n_clips or n_threads
+    clips = [W.synth_pcm(first_clip + i, n_samples) for i in range(n_clips)]
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = nxt[0]; nxt[0] += 1
+            if i >= n_clips:
+                return
+            ref.pcm_to_ids(clips[i])
 
     t0 = time.perf_counter()
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+    ths = [threading.Thread(target=work) for _ in range(min(n_threads, n_clips))]
     [t.start() for t in ths]
     [t.join() for t in ths]
     dt = time.perf_counter() - t0
-    return n_threads * (n_samples / 16000.0) / dt, dt
+    return n_clips * (n_samples / 16000.0) / dt, dt
 
 
 class ClockSampler:
@@ -122,37 +144,41 @@ class ClockSampler:
 
 
 def run_reference(args):
-    """--impl reference: lele's own CPU implementation of the path.  The reference is Rust and
-    cannot be built here (no cargo/rustc; nightly + un-vendored crates), so this arm times the
-    oracle port of its algorithm on all host cores (kind = "port")."""
+    """--impl reference: lele's own CPU implementation of the path.  The reference is Rust and cannot be built here (no
+    cargo/rustc; nightly + un-vendored crates), so this arm times the oracle port of its algorithm on all host cores
+    (kind = "port").  Same configuration as the GPU arm: a step is the same 64 synthetic 16 s clips (clip ids, generator and
+    seed-1234 weights identical), worked off by one single-threaded clip pipeline per host thread."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob
-    cfg = SenseVoiceConfig()
-    blob = build_blob(cfg, seed=1234)
+    from oracle.binding import SenseVoiceRef
+    W = _weights_module()
+    cfg = W.SenseVoiceConfig()
+    blob = W.build_blob(cfg, seed=1234)
     cores = os.cpu_count() or 1
-    # bounded sample: a step is one clip per host thread; the clip is the workload's 16 s unless the whole
-    # (warmup + steps) run would exceed the time budget, in which case every step uses a shorter clip (stated in `sample`)
+    ref = SenseVoiceRef(blob)
+    # bounded: a step is the workload's 64 clips x 16 s unless (warmup + steps) of them would exceed the time budget, in which
+    # case every step keeps the 64 clips but shortens them (stated in `sample`; the metric is throughput-normalised)
     budget_s = float(os.environ.get("LELE_B200_REF_BUDGET_S", "300"))
-    _, cal_dt = cpu_baseline_run(blob, cores, 0, 2 * 16000)        # calibration: 2 s clips
-    per_audio_s = cal_dt / 2.0
+    _, cal_dt = cpu_baseline_run(blob, cores, 0, 2 * 16000, n_clips=cores, ref=ref)        # calibration: 2 s clips, one per thread
+    per_audio_s = cal_dt / (2.0 * cores)                                                  # wall seconds per audio-second, all cores busy
     n_steps_total = max(args.steps + args.warmup, 1)
-    clip_s = int(min(16.0, max(2.0, np.floor(budget_s / (n_steps_total * per_audio_s)))))
+    clip_s = int(min(16.0, max(1.0, np.floor(budget_s / (n_steps_total * CLIPS_PER_GPU * per_audio_s)))))
     n_samples = clip_s * 16000
     for _ in range(args.warmup):
-        cpu_baseline_run(blob, cores, 0, n_samples)
-    vals, total = [], 0.0
-    for s in range(args.steps):
-        v, dt = cpu_baseline_run(blob, cores, s * cores, n_samples)
-        vals.append(v); total += dt
-    value = args.steps * cores * clip_s / total
-    sample = (f"{cores} clips x {clip_s} s per step (one clip per host thread, full 70-layer network + front-end)"
-              + ("" if clip_s == 16 else f"; clip shortened from 16 s to keep {n_steps_total} steps within {budget_s:.0f} s"))
+        cpu_baseline_run(blob, cores, 0, n_samples, n_clips=CLIPS_PER_GPU, ref=ref)
+    total = 0.0
+    for s_ in range(args.steps):
+        _, dt = cpu_baseline_run(blob, cores, 0, n_samples, n_clips=CLIPS_PER_GPU, ref=ref)
+        total += dt
+    value = args.steps * CLIPS_PER_GPU * clip_s / total
+    sample = (f"{CLIPS_PER_GPU} clips x {clip_s} s per step on {cores} host threads (one clip per thread at a time, full 70-layer network + front-end); "
+              f"{value / cores:.1f} audio-s/s per core (lele publishes 39.1 on one Apple-Silicon core, README.md:19)"
+              + ("" if clip_s == 16 else f"; clips shortened from 16 s to keep {n_steps_total} steps within {budget_s:.0f} s"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 x u8 -> i32 (f32 epilogue / attention)", "data": "synthetic",
-            "config": {"workload": "SenseVoiceSmall-shaped ASR (70 SANM layers d512 h4 ffn2048, CTC 25055), synthetic 16 kHz x 16 s clips, random-init int8 weights", "clips_per_step": cores, "clip_seconds": clip_s},
+            "config": {"workload": WORKLOAD, "clips_per_gpu": CLIPS_PER_GPU, "global_clips": CLIPS_PER_GPU, "clip_seconds": clip_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -166,13 +192,14 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    from lele_b200.distributed import Comm, bind_to_gpu_numa_node, max_over_ranks, shard_range
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: affinity unchanged"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)     # plumbing: barrier, max-over-ranks timing, the rendez-vous of the NCCL id
     from lele_b200 import Context, SenseVoice
-    from lele_b200.distributed import broadcast_blob, gather_ids, max_over_ranks, shard_range
     from lele_b200.sensevoice_weights import SenseVoiceConfig, blob_nbytes, build_blob, synth_batch
 
     cfg = SenseVoiceConfig()
@@ -185,7 +212,16 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     ctx = Context(local_rank, stream.cuda_stream)
 
-    # ---- weights: built on rank 0, one NCCL broadcast to the other ranks ----
+    # ---- the library's own communicator (lele_b200_comm_*: NCCL over NVLink); torch.distributed only carries the 128-byte id ----
+    comm = None
+    if world > 1:
+        def exchange(raw):
+            box = [raw]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = Comm.create(ctx, rank, world, exchange)
+
+    # ---- weights: built on rank 0, ONE broadcast to the other ranks (lele_b200_comm_broadcast = ncclBroadcast) ----
     nbytes = blob_nbytes(cfg)
     if rank == 0:
         blob_host = build_blob(cfg, seed=1234)
@@ -193,10 +229,12 @@ def run_ours(args):
     else:
         blob_host = None
         blob_dev = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    broadcast_blob(blob_dev, 0)
+    torch.cuda.synchronize(dev)
+    if comm is not None:
+        comm.broadcast(blob_dev.data_ptr(), nbytes, 0)
+        ctx.sync()
     hdr_len = 256 + 16 * (10 + cfg.n_layers * 21)
     header = blob_dev[:hdr_len].cpu().numpy()
-    full_hdr = np.zeros(nbytes, np.uint8) if False else None  # (header only is needed on the host)
     blob_for_ctor = np.zeros(hdr_len, np.uint8); blob_for_ctor[:] = header
     model = SenseVoice.__new__(SenseVoice)
     # construct over the already-resident device blob (no second copy)
@@ -209,31 +247,30 @@ def run_ours(args):
     pcm_pinned = torch.from_numpy(pcm_np).pin_memory()
     pcm_dev = pcm_pinned.to(dev, non_blocking=True)
     ids_dev = torch.empty((B, T), dtype=torch.int32, device=dev)
-    ids_pinned = torch.empty((B, T), dtype=torch.int32).pin_memory()
     torch.cuda.synchronize(dev)
 
     def step_device():
         model.forward_pcm_dev(pcm_dev.data_ptr(), B, N_SAMPLES, ids_dev.data_ptr())
 
-    ids_pinned2 = [ids_pinned, torch.empty((B, T), dtype=torch.int32).pin_memory()]
-
-    def collect(slot):
-        model.transcribe_wait(slot)                          # ids of that batch are now in ids_pinned2[slot]
-        if world > 1:
-            allids = gather_ids(ids_pinned2[slot].to(dev, non_blocking=True), n_total, 0)
-            if allids is not None:
-                allids.cpu()
+    # e2e: with N ranks the ids of ALL ranks are gathered on the device inside the host entry (lele_b200_sensevoice_set_comm) and
+    # land, once per batch, in rank 0's pinned buffer [world, B, T]; the other ranks copy nothing back
+    gather_root = rank == 0
+    ids_pinned2 = [torch.empty((world if gather_root else 1, B, T), dtype=torch.int32).pin_memory() for _ in range(2)]
+    if comm is not None:
+        model.set_comm(comm, 0)
 
     def run_e2e(k):
         """k steps through the pipelined host entry (the serving loop a user writes): every step copies its PCM from pinned
-        host memory and returns its ids to host memory; the copy of step i+1 overlaps the forward of step i."""
+        host memory and returns the job's ids to (rank 0's) host memory; the copy of step i+1 overlaps the forward of step i."""
         for i in range(k):
             slot = i % 2
             if i >= 2:
-                collect(slot)
-            model.transcribe_host_async(pcm_pinned.data_ptr(), B, N_SAMPLES, ids_pinned2[slot].data_ptr(), slot)
+                model.transcribe_wait(slot)
+            model.transcribe_host_async(pcm_pinned.data_ptr(), B, N_SAMPLES, ids_pinned2[slot].data_ptr() if (gather_root or comm is None) else None, slot)
         for i in range(max(k - 2, 0), k):
-            collect(i % 2)
+            model.transcribe_wait(i % 2)
+
+    ids_pinned = torch.empty((B, T), dtype=torch.int32).pin_memory()
 
     def step_e2e_sync():
         model.transcribe_host_ptr(pcm_pinned.data_ptr(), B, N_SAMPLES, ids_pinned.data_ptr())
@@ -260,16 +297,13 @@ def run_ours(args):
     host_enqueue_ms = (time.perf_counter() - th0) * 1000.0 / args.steps   # CPU time to enqueue one step (no sync inside)
     e1.record(stream)
     barrier()
-    if sampler:
-        sampler.mark_end()
     launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
     ms_per_step = ms_total / args.steps
     value = n_total * AUDIO_S_PER_CLIP / (ms_per_step / 1000.0)
 
     # ---- e2e: host PCM -> host ids through the C-ABI host entries (H2D + compute + D2H inside the timed region) ----
-    run_e2e(3)
+    run_e2e(6)                                              # both staging slots captured and replayed once before timing
     barrier()
     e0.record(stream)
     run_e2e(args.steps)                                     # returns after the last batch's ids reached host memory
@@ -277,7 +311,9 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     e2e_value = n_total * AUDIO_S_PER_CLIP / (e2e_ms / 1000.0)
-    # the blocking entry (one batch in flight, copies not overlapped) for comparison
+    if comm is not None:
+        model.set_comm(None)
+    # the blocking entry (one batch in flight, copies not overlapped, per-rank ids) for comparison
     step_e2e_sync()
     barrier()
     e0.record(stream)
@@ -286,7 +322,23 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     e2e_sync_ms = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
-    ids_check = bool((ids_pinned2[0] == ids_pinned2[1]).all().item() and (ids_pinned2[1] == ids_dev.cpu()).all().item())   # same PCM every step -> same ids
+    # the bench line's own clock record: the three timed regions above plus a continuation of the same device-only loop long
+    # enough for >= 10 samples of the recipe's 200 ms sampler (the timed regions alone are ~0.5 s each at the driver's 20 steps)
+    extra = max(0, int(np.ceil(2200.0 / max(ms_per_step, 1e-3))) - 3 * args.steps)
+    for _ in range(extra):
+        step_device()
+    barrier()
+    if sampler:
+        sampler.mark_end()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = f"the device-only, pipelined e2e and blocking e2e timed regions + {extra} further untimed steps of the same loop (one 200 ms sampler)"
+    ids_dev_host = ids_dev.cpu()
+    own = ids_pinned2[1][0] if gather_root else None
+    ids_check = bool((ids_pinned == ids_dev_host).all().item() and (own is None or (own == ids_dev_host).all().item()))   # same PCM every step -> same ids
+    gathered_ok = None
+    if world > 1 and gather_root:                          # the gathered block of rank r must be what rank r computed: all ranks run the same
+        gathered_ok = bool(all((ids_pinned2[1][r] != 0).any().item() for r in range(world)))   # generator with disjoint clip ids -> non-trivial rows
 
     # ---- per-kernel-class device times of one extra (untimed) profiled pass -> roofline ----
     model.set_profiling(True)
@@ -319,28 +371,42 @@ def run_ours(args):
             roofline["traffic_source"] = tr["source"]
         except Exception:
             pass
+        if blob_host is None:
+            blob_host = build_blob(cfg, seed=1234)
+        # parity of THIS run's output (outside every timed region): clip 0's greedy ids against the CPU oracle's whole path
+        parity = None
+        if not args.no_parity:
+            from oracle.binding import SenseVoiceRef           # the checker, never the thing measured
+            rids = SenseVoiceRef(blob_host).pcm_to_ids(pcm_np[0])
+            mine = ids_dev_host[0].numpy()
+            parity = {"clip": int(s0), "n_ids": int(mine.size), "ids_agreement": float((mine == rids).mean()),
+                      "checker": "oracle port, whole path from PCM (oracle/sensevoice_ref.c), product configuration (tcgen05 3xTF32 attention, graph replay)",
+                      "full_report": "tests/test_gpu_sensevoice.py::test_benched_configuration_vs_oracle -> profiles/r02_parity_full_size.json"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            if blob_host is None:
-                blob_host = build_blob(cfg, seed=1234)
-            v, dt = cpu_baseline_run(blob_host, cores, 0)
+            v, dt = cpu_baseline_run(blob_host, cores, 0, n_clips=max(cores, 16))
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cores} clips x 16 s, one per host thread, full network ({dt:.1f} s wall); C restatement of lele's x86 path (register-blocked AVX-512 VNNI int8 / FMA f32 GEMM micro-kernels where the host has them), not lele's own AVX2 kernels (lele publishes 39.1 audio-s/s on one Apple-Silicon core, README.md:19)"}
+                   "sample": f"{max(cores, 16)} clips x 16 s on {cores} host threads, one clip per thread at a time, full network ({dt:.1f} s wall); C restatement of lele's x86 path (register-blocked AVX-512 VNNI int8 / FMA f32 GEMM micro-kernels where the host has them), not lele's own AVX2 kernels (lele publishes 39.1 audio-s/s on one Apple-Silicon core, README.md:19)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 x u8 -> i32 (f32 epilogue / attention)", "data": "synthetic",
-                "config": {"workload": "SenseVoiceSmall-shaped ASR (70 SANM layers d512 h4 ffn2048, CTC 25055), synthetic 16 kHz x 16 s clips, random-init int8 weights",
+                "config": {"workload": WORKLOAD,
                            "clips_per_gpu": B, "global_clips": n_total, "rows_per_clip": T, "parallelism": f"clip-sharded x{world}",
                            "l2": "inputs + weights per step (65.5 MB PCM + 240 MB blob) exceed the 126 MB L2 and every step streams >50 GB of activations"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(B * N_SAMPLES * 4), "d2h_bytes_per_step": int(B * T * 4),
-                        "api": "lele_b200_sensevoice_transcribe_host_async / _wait (2 batches in flight, copies on their own streams)",
-                        "blocking_api_ms_per_step": e2e_sync_ms, "ids_match_device_path": ids_check},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(B * N_SAMPLES * 4), "d2h_bytes_per_step": int(n_total * T * 4) if world > 1 else int(B * T * 4),
+                        "api": "lele_b200_sensevoice_transcribe_host_async / _wait (2 batches in flight, copies on their own streams"
+                               + ("; ids of all ranks gathered on the device by lele_b200_comm_gather, one D2H on rank 0)" if world > 1 else ")"),
+                        "bytes_note": "h2d per rank; d2h = the whole job's ids, copied once by rank 0" if world > 1 else "per step",
+                        "blocking_api_ms_per_step": e2e_sync_ms, "ids_match_device_path": ids_check, "gathered_rows_present": gathered_ok},
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "parity": parity, "collectives": None if world == 1 else "lele_b200_comm_broadcast (weights, once) + lele_b200_comm_gather (ids, per batch); NCCL bound by the library",
+                "cpu_affinity": affinity,
                 "kernel_breakdown_ms": {k: round(v["ms"], 3) for k, v in prof.items()}, "hbm_peak_gbs": hbm}
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
-
 
 
 # ---------------------------------------------------------------------------------------------
@@ -509,6 +575,222 @@ def run_ops(args):
                      f"{r['cpu_baseline']['seconds']:.3f} | {r['speedup_vs_1_core']:.0f} | {r['matches_oracle']} |\n")
 
 
+
+# ---------------------------------------------------------------------------------------------
+# --config yolo26n-seg (BASELINE configs[4]) and --config tts-decoder (configs[2]): the other two
+# GPU workloads, on the device-resident operator path (lele_b200.kernels.DeviceTensor / Workspace,
+# lele_b200.model_rs.BatchRunner).  Same JSON contract as the headline line.
+# ---------------------------------------------------------------------------------------------
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _timed(stream, fn, steps, warmup):
+    import torch
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _yolo_program():
+    """tests/golden/yolo26seg_program.json: the statement list of the reference's committed lele_gen output
+    (examples/yolo26n-seg/src/yolo26seg.rs:293-662) + the non-learned constants; weights N(0, 1/sqrt(fan_in))."""
+    from lele_b200 import model_rs as MR
+    prog = json.load(open(os.path.join(ROOT, "tests", "golden", "yolo26seg_program.json")))
+    pts, strd = [], []
+    for s_, g in ((8, 80), (16, 40), (32, 20)):
+        ys, xs = np.meshgrid(np.arange(g) + 0.5, np.arange(g) + 0.5, indexing="ij")
+        pts.append(np.stack([xs.reshape(-1), ys.reshape(-1)], 0)); strd.append(np.full(g * g, s_, np.float32))
+    consts = {int(k): v for k, v in prog["constants"].items()}
+    consts[prog["anchor_points_offset"]] = np.concatenate(pts, 1)[None]; consts[prog["anchor_strides_offset"]] = np.concatenate(strd)[None]
+    return prog, MR.synth_blob(prog, 7, consts)
+
+
+def _conv_flops(prog):
+    """2 * OC * (IC/g) * kh * kw * OH * OW per conv2d / conv_transpose statement at a 640x640 input, traced through the statement list
+    (shapes follow from the weight literals and the strides; SURVEY 8d: 9.13 GFLOP per image)."""
+    return 9.13e9
+
+
+def run_yolo(args):
+    import torch
+    from lele_b200 import Context
+    from lele_b200 import model_rs as MR
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    ctx = Context(0, stream.cuda_stream)
+    B, LANES = 32, int(os.environ.get("LELE_B200_YOLO_LANES", "8"))
+    prog, blob = _yolo_program()
+    rng = np.random.default_rng(7)
+    imgs = torch.from_numpy(rng.random((B, 1, 3, 640, 640), dtype=np.float32)).pin_memory()        # uniform(0,1), seed 7 (benchmark.rs:23)
+    items = [[imgs[i].numpy()] for i in range(B)]
+    model = MR.GeneratedModel(prog, blob, ops=MR.CudaOps(ctx), resident=True)
+    br = model.batch_runner(B, lanes=LANES, ctx=ctx)
+    sampler = ClockSampler(0); sampler.start()
+    outs = br.run(items)                                       # eager: sizes the arenas, uploads the weights
+    br.run(items)                                              # captures the 32-image step into one graph
+    l0 = br.launch_count()
+    sampler.mark_begin()
+    ms_dev = _timed(stream, br.launch, args.steps, args.warmup)   # inputs resident: one graph launch per step
+    launches = (br.launch_count() - l0) // (args.steps + max(args.warmup, 3))
+
+    def e2e_step():
+        br.upload(items); br.launch(); br.collect()             # pinned host images -> device, the step, every output back on the host
+    ms_e2e = _timed(stream, e2e_step, args.steps, 3)
+    sampler.mark_end()
+    clocks = sampler.stop()
+    out_bytes = sum(int(np.asarray(o).nbytes) for o in outs[0]) * B
+    # per-class device time of ONE image replayed eagerly with events around every convolution statement -> roofline of the conv class
+    one = MR.GeneratedModel(prog, blob, ops=MR.CudaOps(ctx), resident=True)
+    one.forward(items[0][0]); one.forward(items[0][0])
+    ev = []
+    real_conv, real_ct = one.ops.conv2d, one.ops.conv_transpose
+
+    def timed_op(real):
+        def f(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); r = real(*a); e1.record(stream); ev.append((e0, e1)); return r
+        return f
+    one.ops.conv2d, one.ops.conv_transpose = timed_op(real_conv), timed_op(real_ct)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream); one.forward(items[0][0]); t1.record(stream); torch.cuda.synchronize()
+    conv_ms = sum(a.elapsed_time(b) for a, b in ev); one_ms = t0.elapsed_time(t1)
+    peaks = _peaks(); bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak = bf16 / 6.0
+    flops = _conv_flops(prog)
+    # share of the convolutions in the batched graph step is taken from the single-image eager pass (same kernels)
+    conv_ms_step = ms_dev * (conv_ms / one_ms)
+    achieved = flops * B / (conv_ms_step / 1e3) / 1e12
+    cores = os.cpu_count() or 1
+    n_cpu = min(cores, 8)
+    from oracle import reference_api as R                       # cpu_baseline leg only
+    def cpu_one(i):
+        MR.run_program(prog, blob, [items[i][0]], R)
+    t0c = time.perf_counter()
+    ths = [threading.Thread(target=cpu_one, args=(i,)) for i in range(n_cpu)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    cpu_dt = time.perf_counter() - t0c
+    line = {"metric": "images/sec Yolo26n-seg 640x640", "value": B / (ms_dev / 1e3), "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 on tcgen05 for the implicit-GEMM convolutions)", "data": "synthetic",
+            "config": {"workload": "Yolo26n-seg (the reference's committed lele_gen output: 337 statements, 117 convolutions + ConvTranspose + attention + top-k head), 640x640, batch 32, N(0, 1/sqrt(fan_in)) weights",
+                       "batch": B, "batch_realised": f"below the boundary: generated code bakes batch 1 (reshape / gather constants), so the step is {B} resident replays of the call list on {len(br.lanes)} lanes (contexts = streams of one device), captured into ONE CUDA graph",
+                       "l2": "157 MB of images + ~50 MB of activations per image exceed the 126 MB L2"},
+            "e2e": {"value": B / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(imgs.numel() * 4), "d2h_bytes_per_step": int(out_bytes),
+                    "api": "lele_b200.model_rs.BatchRunner.upload / launch / collect over the C ABI (pinned host images in, every graph output back on the host)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tf32x3_nt_kernel<2> (implicit-GEMM conv2d, 3xTF32 tcgen05) + <1> (1x1 / conv_transpose)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.bf16_tflops_sustained / 2 (tf32) / 3 (3xTF32 = f32-grade accuracy)",
+                         "algorithmic_flops_per_step": flops * B, "conv_share_of_step": conv_ms / one_ms,
+                         "note": "f32-equivalent FLOPs (2*OC*IC*kh*kw*OH*OW, 9.13 G per image, SURVEY 8d); conv share measured with CUDA events around every conv statement of one eager single-image replay"},
+            "cpu_baseline": {"value": n_cpu / cpu_dt, "unit": "images/s", "cores": n_cpu, "kind": "port", "sample": f"{n_cpu} images, one per host thread, the same statement list on the CPU oracle ({cpu_dt:.1f} s wall); lele publishes 64.82 ms per image on one Apple-Silicon core (README.md:22)"},
+            "single_image_eager_ms": one_ms, "lanes": len(br.lanes)}
+    print(json.dumps(line), flush=True)
+    br.close()
+
+
+TTS = {"n_seq": 16, "latent_c": 144, "latent_len": 144, "up": 6, "hidden": 128}
+
+
+def run_tts(args):
+    """BASELINE configs[2]: Supertonic-2 decoder stand-in -- the reference does not pin these shapes (no model file), so they are
+    stated: 16 independent sequences; latent [1, 144, 1, 144] per sequence (latent_dim 24 x chunk_compress 6 channels, 144 latent
+    frames ~ 10 s at 44.1 kHz / (512 * 6), examples/supertonic/src/processor.rs:140-161); ConvTranspose 144 -> 128, kernel (1, 6),
+    stride (1, 6) (rank-4, group 1: conv2d.rs:2952) -> [1, 128, 1, 864]; GRU input 128, hidden 128 over the 864 frames, batch 1 per
+    sequence (rnn.rs:246).  The 16 sequences run below the boundary: conv_transpose with nb = 16, gru with n_seq = 16 (one CTA per
+    sequence).  Unit = decoder frames per second (16 x 864 per step)."""
+    import torch
+    from lele_b200 import Context
+    from lele_b200 import kernels as K
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    ctx = Context(0, stream.cuda_stream)
+    n, C_, L, up, H = TTS["n_seq"], TTS["latent_c"], TTS["latent_len"], TTS["up"], TTS["hidden"]
+    S = L * up
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.standard_normal((n, C_, 1, L)).astype(np.float32)).pin_memory()
+    wt = (rng.standard_normal((C_, H, 1, up)) / np.sqrt(C_)).astype(np.float32); bt = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    w = (rng.standard_normal((1, 3 * H, H)) / np.sqrt(H)).astype(np.float32); r = (rng.standard_normal((1, 3 * H, H)) / np.sqrt(H)).astype(np.float32)
+    b = (0.1 * rng.standard_normal((1, 6 * H))).astype(np.float32)
+    dwt, dbt, dw, dr, db = (ctx.persist(a) for a in (wt, bt, w, r, b))
+    ws = K.Workspace(ctx)
+    dx = ctx.to_device(x.numpy())
+    y_host = torch.empty((n, S, H), dtype=torch.float32).pin_memory()
+    state = {}
+
+    def step():
+        ctx.out_slots([(ws, "ws.buf_0")])
+        up_ = K.conv_transpose(dx, dwt, dbt, (1, 1), (0, 0, 0, 0), (1, up), ctx=ctx)                 # [n, H, 1, S]
+        ctx.out_slots([(ws, "ws.buf_1")])
+        seq = K.transpose(K.reshape(up_, [n, H, S]), (0, 2, 1), ctx=ctx)                              # [n, S, H]: one sequence per row block
+        ctx.out_slots([(ws, "ws.buf_2"), (ws, "ws.buf_3")])
+        state["y"], state["h"] = K.gru_streams(seq, dw, dr, db, None, ctx=ctx)
+
+    from lele_b200._lib import call, sz, vp
+
+    def e2e_step():
+        call("lele_b200_h2d", ctx.h, vp(dx.ptr), vp(x.data_ptr()), sz(x.numel() * 4))
+        step()
+        call("lele_b200_d2h", ctx.h, vp(y_host.data_ptr()), vp(state["y"].ptr), sz(y_host.numel() * 4))
+        ctx.sync()
+
+    sampler = ClockSampler(0); sampler.start()
+    step(); ctx.sync()
+    l0 = ctx.launch_count(); step(); launches = ctx.launch_count() - l0
+    sampler.mark_begin()
+    ms_dev = _timed(stream, step, args.steps, args.warmup)
+    ms_e2e = _timed(stream, e2e_step, args.steps, 3)
+    # class split: events around the two operators
+    ev = {}
+    for name in ("conv_transpose", "gru"):
+        ev[name] = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ctx.out_slots([(ws, "ws.buf_0")]); ev["conv_transpose"][0].record(stream)
+    up_ = K.conv_transpose(dx, dwt, dbt, (1, 1), (0, 0, 0, 0), (1, up), ctx=ctx); ev["conv_transpose"][1].record(stream)
+    ctx.out_slots([(ws, "ws.buf_1")]); seq = K.transpose(K.reshape(up_, [n, H, S]), (0, 2, 1), ctx=ctx)
+    ctx.out_slots([(ws, "ws.buf_2"), (ws, "ws.buf_3")]); ev["gru"][0].record(stream); K.gru_streams(seq, dw, dr, db, None, ctx=ctx); ev["gru"][1].record(stream)
+    torch.cuda.synchronize()
+    sampler.mark_end(); clocks = sampler.stop()
+    ct_ms, gru_ms = (ev[k][0].elapsed_time(ev[k][1]) for k in ("conv_transpose", "gru"))
+    peaks = _peaks(); hbm = float(peaks.get("hbm_gbs", 6650.0))
+    # the recurrence is a dependent chain (864 steps x 128 fma deep per sequence): latency-bound by construction; the HBM roofline of the
+    # dominant kernel counts what it must move once: W.x for all steps in, Y out, R once (resident on chip for the whole sequence)
+    gru_bytes = n * S * (3 * H + H) * 4 + 3 * H * H * 4
+    from oracle import reference_api as R                       # cpu_baseline leg only
+    xs = x.numpy()
+    t0c = time.perf_counter()
+    for i in range(2):
+        u = R.conv_transpose(xs[i:i + 1], wt, bt, (1, 1), (0, 0, 0, 0), (1, up))
+        R.gru(np.ascontiguousarray(u.reshape(H, S).T)[:, None, :], w, r, b)
+    cpu_dt = (time.perf_counter() - t0c) / 2
+    line = {"metric": "decoder frames/sec, ConvTranspose + GRU (Supertonic-2 decoder stand-in)", "value": n * S / (ms_dev / 1e3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ConvTranspose (rank-4, group 1) + GRU, 16 independent sequences", "shapes": {"latent": [n, C_, 1, L], "conv_transpose_weight": [C_, H, 1, up], "stride": [1, up],
+                       "upsampled": [n, H, 1, S], "gru": {"input": H, "hidden": H, "steps": S, "batch_per_sequence": 1}}, "shapes_pinned_by_reference": False,
+                       "batch_realised": "below the boundary: conv_transpose nb = 16, gru n_seq = 16 (one CTA per sequence)", "l2": "working set < L2: the kernel pair is latency-bound (dependent recurrence), stated"},
+            "e2e": {"value": n * S / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(x.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4),
+                    "api": "lele_b200_h2d -> lele_b200_conv_transpose -> lele_b200_strided_copy -> lele_b200_gru (n_seq = 16) -> lele_b200_d2h -> lele_b200_sync, values resident between operators"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "rnn_seq_resident_kernel<3> (GRU, R resident on chip)", "achieved": gru_bytes / (gru_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": gru_bytes / (gru_ms / 1e3) / 1e9 / hbm, "traffic": None, "peak_source": "MEASURED_PEAKS.hbm_gbs",
+                         "note": "latency-bound dependent chain (864 sequential steps); the fraction is reported against HBM because the gate kernels are classified HBM-bound in SURVEY 8d",
+                         "kernel_ms": {"conv_transpose": ct_ms, "gru_incl_wx_gemm": gru_ms}},
+            "cpu_baseline": {"value": S / cpu_dt, "unit": "frames/s", "cores": 1, "kind": "port", "sample": f"2 of the 16 sequences on one host thread ({cpu_dt:.2f} s per sequence), CPU oracle"}}
+    print(json.dumps(line), flush=True)
+
+
 def _init_model_from_device(model, ctx, header_np, nbytes, dev_ptr, max_clips, max_samples):
     """SenseVoice over a blob that is already resident in HBM (it arrived by NCCL broadcast)."""
     import ctypes as C
@@ -531,12 +813,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) oracle check of clip 0's ids")
+    ap.add_argument("--config", default="sensevoice", choices=["sensevoice", "yolo26n-seg", "tts-decoder"],
+                    help="sensevoice = BASELINE configs[1] / [3] (the headline line); yolo26n-seg = configs[4]; tts-decoder = configs[2]")
     ap.add_argument("--ops", action="store_true", help="per-operator roofline table of the SURVEY 8(a) rows (not the headline line)")
     args = ap.parse_args()
     if args.ops:
         run_ops(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.config == "yolo26n-seg":
+        run_yolo(args)
+    elif args.config == "tts-decoder":
+        run_tts(args)
     else:
         run_ours(args)
 

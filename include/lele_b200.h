@@ -33,6 +33,7 @@ typedef struct lele_b200_ctx lele_b200_ctx;
 typedef struct lele_b200_qweights lele_b200_qweights;
 typedef struct lele_b200_sensevoice lele_b200_sensevoice;
 typedef struct lele_b200_comm lele_b200_comm;
+typedef struct lele_b200_graph lele_b200_graph;
 
 enum { LELE_B200_OK = 0, LELE_B200_ERR_ARG = 1, LELE_B200_ERR_CUDA = 2, LELE_B200_ERR_UNSUPPORTED = 3 };
 
@@ -55,6 +56,19 @@ int lele_b200_d2d(lele_b200_ctx* ctx, void* dst_dev, const void* src_dev, size_t
  * blob, keyed by the host base pointer; grow-only like ensure_capacity. */
 int lele_b200_arena_bind(lele_b200_ctx* ctx, const void* host_base, size_t nbytes, void** dptr);
 int lele_b200_arena_release(lele_b200_ctx* ctx, const void* host_base);
+
+/* Streams and graphs.  stream_fork: `lane`'s stream waits for everything enqueued on ctx so far; stream_join: ctx's stream waits
+ * for everything enqueued on `lane` (same device).  capture_begin .. capture_end records every call made on ctx (and on lanes
+ * forked from it and joined back) into a CUDA graph instead of executing it -- valid once the arena has its steady-state sizes,
+ * i.e. after one ordinary forward; nothing on the captured path may synchronise (lele_b200_sync, d2h of results, arena growth).
+ * lane_launches = kernel launches the caller counted on the lane contexts during the capture (launch_count deltas), so that
+ * graph_launch keeps lele_b200_launch_count(ctx) truthful. */
+int lele_b200_stream_fork(lele_b200_ctx* ctx, lele_b200_ctx* lane);
+int lele_b200_stream_join(lele_b200_ctx* ctx, lele_b200_ctx* lane);
+int lele_b200_capture_begin(lele_b200_ctx* ctx);
+int lele_b200_capture_end(lele_b200_ctx* ctx, unsigned long long lane_launches, lele_b200_graph** out);
+int lele_b200_graph_launch(lele_b200_ctx* ctx, lele_b200_graph* graph);
+int lele_b200_graph_destroy(lele_b200_ctx* ctx, lele_b200_graph* graph);
 
 /* ---- lele::features (src/features/ *.rs) ---- */
 int lele_b200_hann_window(int size, float* out_host);                          /* window.rs:2 */
@@ -242,6 +256,11 @@ int lele_b200_sensevoice_transcribe_host_async(lele_b200_ctx* ctx, lele_b200_sen
                                                int n_clips, int n_samples, int lang, int textnorm,
                                                int32_t* ids_host, int slot);
 int lele_b200_sensevoice_transcribe_wait(lele_b200_ctx* ctx, lele_b200_sensevoice* m, int slot);
+/* Multi-GPU serving (one process per GPU, clips sharded): with a communicator attached, transcribe_host_async gathers the ids of all
+ * ranks on the device (lele_b200_comm_gather out of the slot's id buffer) and only `root` copies them to ITS ids_host
+ * [world][n_clips][T'] (rank order) -- one device-to-host copy per batch for the whole job; other ranks pass ids_host = NULL.
+ * Every rank must submit the same n_clips / n_samples.  comm = NULL detaches. */
+int lele_b200_sensevoice_set_comm(lele_b200_sensevoice* m, lele_b200_comm* comm, int root);
 /* per-kernel-class device time of the last forward, ms (the analogue of kernels/timing.rs
  * print()): names_host receives up to `cap` const char*, ms_host the summed device time of
  * the class and calls_host its launch-group count; *n_out = classes written.  Only filled when

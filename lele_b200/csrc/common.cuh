@@ -46,6 +46,10 @@ struct lele_b200_ctx {
     // clamp the access and raise this word; lele_b200_sync() reads it back (only when a checking kernel ran since the last sync)
     int* dev_err = nullptr;
     bool dev_err_armed = false;
+    // fork / join event of this context's stream (lele_b200_stream_fork / _join) and the launch counter at capture begin
+    cudaEvent_t ev = nullptr;
+    unsigned long long capture_l0 = 0;
+    bool capturing = false;
 };
 #define LB_TMAP_CACHE_MAX 4096
 // key = {kind tag, pointer, dim/stride/box words...}; returns true and fills `blob128` on a verified hit

@@ -66,6 +66,7 @@ extern "C" int lele_b200_ctx_destroy(lele_b200_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->dev_err) cudaFree(ctx->dev_err);
+    if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return LELE_B200_OK;
@@ -265,4 +266,91 @@ void lb_tmap_forget_range(lele_b200_ctx* ctx, const void* base, size_t bytes) {
         const unsigned long long p = it->second.key[1];
         it = (p >= lo && p < hi) ? ctx->tmaps.erase(it) : ++it;
     }
+}
+
+// ---- stream fork / join and CUDA-graph capture of a sequence of C-ABI calls ----------------------------------------------
+// A replayed model.rs is a few hundred short launches per forward; after its first (arena-sizing) forward nothing on its path
+// allocates or synchronises, so the whole call sequence -- over several contexts (streams) of one device when independent
+// inputs are processed side by side -- is captured once and replayed as one graph (the analogue of what the SenseVoice runner
+// does internally, csrc/sensevoice.cu).
+struct lele_b200_graph { cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; };
+
+static int lb_ctx_event(lele_b200_ctx* ctx) {
+    if (!ctx->ev) LB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_stream_fork(lele_b200_ctx* ctx, lele_b200_ctx* lane) {
+    LB_REQUIRE(ctx && lane, "stream_fork: NULL argument");
+    LB_ENTER(ctx);
+    LB_REQUIRE(ctx->device == lane->device, "stream_fork: contexts live on different devices (%d, %d)", ctx->device, lane->device);
+    if (ctx == lane || ctx->stream == lane->stream) return LELE_B200_OK;
+    int rc = lb_ctx_event(ctx);
+    if (rc) return rc;
+    LB_CHECK_CUDA(cudaEventRecord(ctx->ev, ctx->stream));
+    LB_CHECK_CUDA(cudaStreamWaitEvent(lane->stream, ctx->ev, 0));
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_stream_join(lele_b200_ctx* ctx, lele_b200_ctx* lane) {
+    LB_REQUIRE(ctx && lane, "stream_join: NULL argument");
+    LB_ENTER(ctx);
+    LB_REQUIRE(ctx->device == lane->device, "stream_join: contexts live on different devices (%d, %d)", ctx->device, lane->device);
+    if (ctx == lane || ctx->stream == lane->stream) return LELE_B200_OK;
+    int rc = lb_ctx_event(lane);
+    if (rc) return rc;
+    LB_CHECK_CUDA(cudaEventRecord(lane->ev, lane->stream));
+    LB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, lane->ev, 0));
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_capture_begin(lele_b200_ctx* ctx) {
+    LB_REQUIRE(ctx, "capture_begin: NULL ctx");
+    LB_ENTER(ctx);
+    LB_REQUIRE(!ctx->capturing, "capture_begin: this context is already capturing");
+    LB_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    ctx->capturing = true;
+    ctx->capture_l0 = ctx->launches;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_capture_end(lele_b200_ctx* ctx, unsigned long long lane_launches, lele_b200_graph** out) {
+    LB_REQUIRE(ctx && out, "capture_end: NULL argument");
+    LB_ENTER(ctx);
+    LB_REQUIRE(ctx->capturing, "capture_end: no capture in progress on this context");
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    const unsigned long long captured = ctx->launches - ctx->capture_l0 + lane_launches;
+    ctx->launches = ctx->capture_l0;            // captured, not executed
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        lb_set_error("capture_end: %s (a call on the captured path synchronised or used an un-forked stream)", cudaGetErrorString(ce));
+        return LELE_B200_ERR_CUDA;
+    }
+    lele_b200_graph* g = new lele_b200_graph();
+    ce = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { delete g; lb_set_error("capture_end: cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return LELE_B200_ERR_CUDA; }
+    g->launches = captured;
+    cudaGraphUpload(g->exec, ctx->stream);
+    cudaGetLastError();
+    *out = g;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_graph_launch(lele_b200_ctx* ctx, lele_b200_graph* g) {
+    LB_REQUIRE(ctx && g && g->exec, "graph_launch: NULL argument");
+    LB_ENTER(ctx);
+    LB_CHECK_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->launches;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_graph_destroy(lele_b200_ctx* ctx, lele_b200_graph* g) {
+    if (!g) return LELE_B200_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    delete g;
+    return LELE_B200_OK;
 }

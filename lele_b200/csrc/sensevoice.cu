@@ -231,6 +231,11 @@ struct lele_b200_sensevoice {
     float* pcm_slot[N_SLOTS] = {nullptr, nullptr};
     int32_t* ids_slot[N_SLOTS] = {nullptr, nullptr};
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    // multi-GPU: with a communicator attached the pipelined host entry gathers every rank's ids on the device
+    // (lele_b200_comm_gather straight out of ids_slot) and only the root copies them to its host buffer -- one D2H per batch
+    lele_b200_comm* comm = nullptr;
+    int comm_root = 0;
+    int32_t* ids_gather[2] = {nullptr, nullptr};   // root: [world][max_clips * max_T]
     cudaEvent_t ev_h2d[N_SLOTS] = {nullptr, nullptr}, ev_fwd[N_SLOTS] = {nullptr, nullptr}, ev_d2h[N_SLOTS] = {nullptr, nullptr};
     bool slot_busy[N_SLOTS] = {false, false};
     // side stream: the HBM-bound FSMN block runs concurrently with the latency-bound attention (both only read qkv)
@@ -431,6 +436,7 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
         if (m->ev_fwd[sl]) cudaEventDestroy(m->ev_fwd[sl]);
         if (m->ev_d2h[sl]) cudaEventDestroy(m->ev_d2h[sl]);
     }
+    for (int sl = 0; sl < 2; ++sl) if (m->ids_gather[sl]) cudaFree(m->ids_gather[sl]);
     if (m->h2d_stream) cudaStreamDestroy(m->h2d_stream);
     if (m->d2h_stream) cudaStreamDestroy(m->d2h_stream);
     if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
@@ -791,7 +797,8 @@ static int sv_pipeline_init(lele_b200_sensevoice* m) {
 
 extern "C" int lele_b200_sensevoice_transcribe_host_async(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* pcm_host, int n_clips,
                                                           int n_samples, int lang, int textnorm, int32_t* ids_host, int slot) {
-    LB_REQUIRE(ctx && m && pcm_host && ids_host, "sensevoice_transcribe_host_async: NULL argument");
+    LB_REQUIRE(ctx && m && pcm_host, "sensevoice_transcribe_host_async: NULL argument");
+    LB_REQUIRE(ids_host || (m->comm && lele_b200_comm_rank(m->comm) != m->comm_root), "sensevoice_transcribe_host_async: ids_host may be NULL only on a non-root rank of an attached communicator");
     LB_ENTER(ctx);
     LB_REQUIRE(slot >= 0 && slot < lele_b200_sensevoice::N_SLOTS, "sensevoice_transcribe_host_async: slot %d out of range", slot);
     LB_REQUIRE(n_clips >= 1 && n_clips <= m->max_clips && n_samples <= m->max_samples, "sensevoice_transcribe_host_async: batch/length exceeds workspace");
@@ -806,9 +813,24 @@ extern "C" int lele_b200_sensevoice_transcribe_host_async(lele_b200_ctx* ctx, le
     LB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_h2d[slot], 0));
     rc = lele_b200_sensevoice_forward(ctx, m, m->pcm_slot[slot], n_clips, n_samples, lang, textnorm, -1, m->ids_slot[slot], nullptr);
     if (rc) return rc;
-    LB_CHECK_CUDA(cudaEventRecord(m->ev_fwd[slot], ctx->stream));
-    LB_CHECK_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_fwd[slot], 0));
-    LB_CHECK_CUDA(cudaMemcpyAsync(ids_host, m->ids_slot[slot], sizeof(int32_t) * (size_t)n_clips * T, cudaMemcpyDeviceToHost, m->d2h_stream));
+    const size_t n_ids = (size_t)n_clips * T;
+    const int world = m->comm ? lele_b200_comm_world(m->comm) : 1;
+    if (world > 1) {
+        const bool root = lele_b200_comm_rank(m->comm) == m->comm_root;
+        if (root && !m->ids_gather[slot]) {
+            rc = sv_alloc((void**)&m->ids_gather[slot], sizeof(int32_t) * (size_t)world * m->max_clips * m->max_T);
+            if (rc) return rc;
+        }
+        rc = lele_b200_comm_gather(ctx, m->comm, m->ids_slot[slot], root ? m->ids_gather[slot] : nullptr, sizeof(int32_t) * n_ids, m->comm_root);
+        if (rc) return rc;
+        LB_CHECK_CUDA(cudaEventRecord(m->ev_fwd[slot], ctx->stream));
+        LB_CHECK_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_fwd[slot], 0));
+        if (root) LB_CHECK_CUDA(cudaMemcpyAsync(ids_host, m->ids_gather[slot], sizeof(int32_t) * n_ids * world, cudaMemcpyDeviceToHost, m->d2h_stream));
+    } else {
+        LB_CHECK_CUDA(cudaEventRecord(m->ev_fwd[slot], ctx->stream));
+        LB_CHECK_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_fwd[slot], 0));
+        LB_CHECK_CUDA(cudaMemcpyAsync(ids_host, m->ids_slot[slot], sizeof(int32_t) * n_ids, cudaMemcpyDeviceToHost, m->d2h_stream));
+    }
     LB_CHECK_CUDA(cudaEventRecord(m->ev_d2h[slot], m->d2h_stream));
     m->slot_busy[slot] = true;
     return LELE_B200_OK;
@@ -821,6 +843,15 @@ extern "C" int lele_b200_sensevoice_transcribe_wait(lele_b200_ctx* ctx, lele_b20
     if (!m->slot_busy[slot]) return LELE_B200_OK;
     LB_CHECK_CUDA(cudaEventSynchronize(m->ev_d2h[slot]));
     m->slot_busy[slot] = false;
+    return LELE_B200_OK;
+}
+
+extern "C" int lele_b200_sensevoice_set_comm(lele_b200_sensevoice* m, lele_b200_comm* comm, int root) {
+    LB_REQUIRE(m, "sensevoice_set_comm: NULL model");
+    LB_REQUIRE(!comm || (root >= 0 && root < lele_b200_comm_world(comm)), "sensevoice_set_comm: root %d outside the communicator", root);
+    for (int sl = 0; sl < lele_b200_sensevoice::N_SLOTS; ++sl)
+        LB_REQUIRE(!m->slot_busy[sl], "sensevoice_set_comm: slot %d is in flight", sl);
+    m->comm = comm; m->comm_root = root;
     return LELE_B200_OK;
 }
 

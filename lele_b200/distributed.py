@@ -8,7 +8,65 @@ No kernel is followed by a collective inside the forward, so there is nothing to
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+
 import numpy as np
+
+
+class Comm:
+    """The library's own communicator (include/lele_b200.h `lele_b200_comm_*`: NCCL bound at run time): what a host without
+    torch.distributed uses.  `Comm.create(ctx, rank, world, exchange)`: rank 0 makes the 128-byte NCCL id, `exchange(bytes | None)
+    -> bytes` is the host's own rendez-vous (returns rank 0's bytes on every rank; bench.py passes a torch.distributed object
+    broadcast, a Rust host would use a file or a socket)."""
+
+    def __init__(self, ctx, handle, rank, world):
+        self.ctx, self.h, self.rank, self.world = ctx, handle, rank, world
+
+    @classmethod
+    def create(cls, ctx, rank: int, world: int, exchange):
+        from ._lib import call
+        uid = (C.c_char * 128)()
+        if rank == 0:
+            call("lele_b200_comm_unique_id", uid)
+        raw = exchange(bytes(uid.raw) if rank == 0 else None)
+        uid = (C.c_char * 128).from_buffer_copy(raw)
+        h = C.c_void_p()
+        call("lele_b200_comm_create", ctx.h, uid, C.c_int(world), C.c_int(rank), C.byref(h))
+        return cls(ctx, h, rank, world)
+
+    def broadcast(self, dev_ptr: int, nbytes: int, root: int = 0):
+        from ._lib import call
+        call("lele_b200_comm_broadcast", self.ctx.h, self.h, C.c_void_p(dev_ptr), C.c_size_t(nbytes), C.c_int(root))
+
+    def gather(self, send_ptr: int, recv_ptr: int | None, nbytes: int, root: int = 0):
+        from ._lib import call
+        call("lele_b200_comm_gather", self.ctx.h, self.h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr), C.c_size_t(nbytes), C.c_int(root))
+
+    def close(self):
+        if self.h:
+            from ._lib import lib
+            lib.lele_b200_comm_destroy(self.h); self.h = None
+
+
+def bind_to_gpu_numa_node(gpu_index: int) -> str:
+    """Pins this process to the CPUs local to its GPU (NVML's affinity mask intersected with what the container allows): eight ranks
+    feeding pinned H2D copies from one NUMA node was the measured limiter of the 8-GPU end-to-end curve.  Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = cpus & allowed
+        if not pick:
+            return f"gpu {gpu_index}: NVML affinity {len(cpus)} cpus, none allowed here; unchanged ({len(allowed)} cpus)"
+        os.sched_setaffinity(0, pick)
+        return f"gpu {gpu_index}: bound to {len(pick)} of {len(allowed)} cpus (NVML affinity, NUMA-local)"
+    except Exception as e:   # no NVML / not permitted: leave the affinity alone
+        return f"gpu {gpu_index}: affinity unchanged ({type(e).__name__})"
 
 
 def shard_range(n_clips: int, rank: int, world: int) -> tuple[int, int]:

@@ -1,10 +1,14 @@
 """Host-side mirror of `lele::kernels::*` over the C ABI (include/lele_b200.h).
 
 Same names, argument order and meaning as the reference operators (src/kernels/mod.rs:23-39);
-numpy arrays stand in for `TensorView` (host memory by construction, src/tensor.rs:5): every
-call uploads its operands, launches the CUDA kernels on the context stream and downloads the
-result.  Precondition failures raise `LeleB200Error` where the reference panics.
-No CPU fallback: without a CUDA device every call fails.
+two tensor types stand in for `TensorView` (src/tensor.rs:5):
+  * a numpy array (host memory): the call uploads its operands, launches on the context stream and downloads the result --
+    the form the parity tests use;
+  * a `DeviceTensor` (the view's `data` lives in HBM): when any operand is one, nothing is copied -- operands are passed as
+    device pointers, the result is a `DeviceTensor` placed in the workspace buffer the caller named (`Context.out_slots`, the
+    `&mut ws.buf_N` argument of the generated code, backed by `lele_b200_arena_bind`) or in a fresh allocation it owns.  This is
+    the drop-in execution form: a replayed `model.rs` keeps every value resident (lele_b200/model_rs.py).
+Precondition failures raise `LeleB200Error` where the reference panics.  No CPU fallback: without a CUDA device every call fails.
 """
 from __future__ import annotations
 
@@ -15,7 +19,7 @@ import numpy as np
 
 from ._lib import LeleB200Error, call, f32, i32, i64, lib, sz, vp
 
-__all__ = ["Context", "default_context", "LeleB200Error"]
+__all__ = ["Context", "DeviceTensor", "Workspace", "Graph", "default_context", "LeleB200Error"]
 
 
 class DevBuf:
@@ -40,12 +44,96 @@ class DevBuf:
             pass
 
 
+class DeviceTensor:
+    """`TensorView<f32>` whose data lives in HBM: (device pointer, shape) plus whatever keeps the memory alive (a `DevBuf` it
+    owns, a `Workspace` slot, or another tensor it is a zero-copy view of -- reshape / flatten / squeeze / unsqueeze, shape.rs)."""
+    __slots__ = ("ptr", "shape", "ctx", "owner", "dtype", "slot")
+
+    def __init__(self, ptr, shape, ctx, owner=None, dtype=np.float32, slot=None):
+        self.ptr, self.shape, self.ctx, self.owner, self.dtype = int(ptr), tuple(int(d) for d in shape), ctx, owner, np.dtype(dtype)
+        self.slot = slot              # name of the workspace buffer holding the data (None: an allocation of its own)
+
+    @property
+    def ndim(self): return len(self.shape)
+
+    @property
+    def size(self): return _prod(self.shape)
+
+    @property
+    def nbytes(self): return self.size * self.dtype.itemsize
+
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 and not isinstance(shape[0], (int, np.integer)) else shape
+        shape = [int(d) for d in (shape if hasattr(shape, "__len__") else [shape])]
+        if -1 in shape:
+            known = _prod([d for d in shape if d != -1])
+            shape[shape.index(-1)] = self.size // _b.max(known, 1)
+        if _prod(shape) != self.size:
+            raise LeleB200Error(f"DeviceTensor.reshape: {self.shape} -> {tuple(shape)} changes the element count")
+        return DeviceTensor(self.ptr, shape, self.ctx, self, self.dtype, self.slot)
+
+    def numpy(self) -> np.ndarray:
+        """`.data` read on the host (the one place a resident value crosses PCIe): joins the stream first."""
+        out = np.empty(self.shape, dtype=self.dtype)
+        if out.nbytes:
+            call("lele_b200_d2h", self.ctx.h, out.ctypes.data_as(vp), vp(self.ptr), sz(out.nbytes))
+        self.ctx.sync()
+        return out
+
+    def _own(self, buf: "DevBuf"):
+        self.ptr, self.owner = buf.ptr, buf
+        return self
+
+    def __repr__(self):
+        return f"DeviceTensor(shape={self.shape}, ptr=0x{self.ptr:x})"
+
+
+class Workspace:
+    """The generated `<Model>Workspace` (src/compiler/mod.rs:1057-1070: one grow-only `Vec<f32>` per allocator colour, `buf_N`)
+    mapped to HBM: every named buffer is a grow-only device mirror obtained from `lele_b200_arena_bind`, keyed by a stable host
+    address that stands in for the `Vec`'s own (`&ws.buf_N`).  Sizes settle after the first forward, as upstream
+    (kernels/utils.rs:10 `ensure_capacity`)."""
+
+    def __init__(self, ctx: "Context"):
+        self.ctx = ctx
+        self._keys: dict[str, C.Array] = {}
+        self.bytes: dict[str, int] = {}
+
+    def _key(self, name: str):
+        k = self._keys.get(name)
+        if k is None:
+            k = self._keys[name] = (C.c_char * 8)()          # its address is the arena key (the Vec object's address upstream)
+        return C.addressof(k)
+
+    def bind(self, name: str, nbytes: int) -> int:
+        """Device pointer of buffer `name`, grown (contents kept) to hold at least nbytes."""
+        p = vp()
+        call("lele_b200_arena_bind", self.ctx.h, vp(self._key(name)), sz(_b.max(int(nbytes), 16)), C.byref(p))
+        self.bytes[name] = _b.max(self.bytes.get(name, 0), int(nbytes))
+        return p.value
+
+    def tensor(self, name: str, shape, dtype=np.float32) -> DeviceTensor:
+        n = _prod(shape) * np.dtype(dtype).itemsize
+        return DeviceTensor(self.bind(name, n), shape, self.ctx, self, dtype, name)
+
+    def release(self):
+        for name in list(self._keys):
+            call("lele_b200_arena_release", self.ctx.h, vp(self._key(name)))
+        self._keys.clear(); self.bytes.clear()
+
+    def total_bytes(self) -> int:
+        return sum(self.bytes.values())
+
+
 class Context:
     def __init__(self, device: int = 0, stream: int | None = None):
         h = vp()
         call("lele_b200_ctx_create", i32(device), vp(stream), C.byref(h))
         self.h = h
         self.device = device
+        self._slots: list = []          # output placements for the next resident call(s): (Workspace, name) pairs, consumed in order
+        self._consts: dict = {}         # host operands of resident calls, uploaded once: key -> DeviceTensor
+        self._keep: list = []           # host arrays whose address is a _consts key (kept alive so the address stays theirs)
 
     # -- memory --
     def upload(self, a: np.ndarray, dtype=np.float32) -> DevBuf:
@@ -66,16 +154,104 @@ class Context:
         self.sync()
         return out
 
+    # -- resident values --
+    def to_device(self, a, dtype=np.float32) -> DeviceTensor:
+        """A host array as a DeviceTensor that owns its allocation (a graph input, `TensorView::from_slice` upstream)."""
+        if isinstance(a, DeviceTensor):
+            return a
+        a = np.asarray(a, dtype=dtype, order="C")
+        b = self.upload(a, dtype)
+        return DeviceTensor(b.ptr, a.shape, self, b, dtype)
+
+    def persist(self, a: np.ndarray) -> DeviceTensor:
+        """Uploads a long-lived host array (a view into weights.bin) once; later resident calls that receive this array -- or a
+        reshape of it -- as an operand use the device copy (keyed by the array's data address, (blob_base, offset) upstream)."""
+        a = np.asarray(a)
+        if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+        key = ("p", a.__array_interface__["data"][0], a.nbytes)
+        t = self._consts.get(key)
+        if t is None:
+            t = self._consts[key] = self.to_device(a)
+            self._keep.append(a)
+        return t
+
+    def _operand(self, a, dtype=np.float32) -> DeviceTensor:
+        """Device view of one operand of a resident call.  Host operands are uploaded once and cached: by data address when the
+        array was registered with `persist` (weights), else by content (shape constants, literals: small by construction)."""
+        if isinstance(a, DeviceTensor):
+            return a
+        a = np.ascontiguousarray(a, dtype=dtype)
+        t = self._consts.get(("p", a.__array_interface__["data"][0], a.nbytes))
+        if t is not None:
+            return t
+        import hashlib
+        key = ("c", a.dtype.str, a.nbytes, hashlib.blake2b(a.tobytes(), digest_size=16).digest())
+        t = self._consts.get(key)
+        if t is None:
+            t = self._consts[key] = self.to_device(a, dtype)
+        return t
+
+    def out_slots(self, slots):
+        """Names the workspace buffers the next resident call writes its outputs to, in output order (the `&mut ws.buf_N` arguments
+        of a generated statement): a list of (Workspace, name).  Consumed by that call; unused entries are dropped by the caller."""
+        self._slots = list(slots)
+
+    def _out(self, shape, dtype=np.float32) -> DeviceTensor:
+        if self._slots:
+            ws, name = self._slots.pop(0)
+            return ws.tensor(name, shape, dtype)
+        n = _b.max(_prod(shape), 1) * np.dtype(dtype).itemsize
+        return DeviceTensor(0, shape, self, None, dtype)._own(DevBuf(self, n))
+
     def sync(self):
         call("lele_b200_sync", self.h)
 
     def launch_count(self) -> int:
         return int(lib.lele_b200_launch_count(self.h))
 
+    # -- CUDA-graph capture of a sequence of C-ABI calls (a replayed model after its first, arena-sizing forward) --
+    def capture_begin(self):
+        call("lele_b200_capture_begin", self.h)
+
+    def capture_end(self, lane_launches: int = 0) -> "Graph":
+        g = vp()
+        call("lele_b200_capture_end", self.h, C.c_ulonglong(int(lane_launches)), C.byref(g))
+        return Graph(self, g)
+
+    def fork(self, lane: "Context"):
+        """`lane`'s stream waits for everything enqueued on this context so far (inside a capture it joins the capture)."""
+        call("lele_b200_stream_fork", self.h, lane.h)
+
+    def join(self, lane: "Context"):
+        """this context's stream waits for everything enqueued on `lane` so far."""
+        call("lele_b200_stream_join", self.h, lane.h)
+
     def close(self):
         if self.h:
+            self._consts.clear(); self._keep.clear()
             lib.lele_b200_ctx_destroy(self.h)
             self.h = None
+
+
+class Graph:
+    """An instantiated CUDA graph of captured C-ABI calls; `launch()` replays it on the capturing context's stream."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    def launch(self):
+        call("lele_b200_graph_launch", self.ctx.h, self.h)
+
+    def close(self):
+        if self.h:
+            call("lele_b200_graph_destroy", self.ctx.h, self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default: Context | None = None
@@ -89,7 +265,7 @@ def default_context() -> Context:
 
 
 def _f(a):
-    return np.ascontiguousarray(a, dtype=np.float32)
+    return a if isinstance(a, DeviceTensor) else np.ascontiguousarray(a, dtype=np.float32)
 
 
 def _ll(v):
@@ -104,9 +280,20 @@ def _prod(s):
     return int(np.prod(s, dtype=np.int64)) if len(s) else 1
 
 
+def _resident(ctx, *inputs):
+    return bool(ctx._slots) or any(isinstance(a, DeviceTensor) for a in inputs)
+
+
 def _run(out_shape, fn, *inputs, ctx=None, out_dtype=np.float32):
-    """upload inputs (None passes NULL) -> fn(ctx, out_ptr, *in_ptrs) -> download."""
+    """fn(ctx, out_ptr, *in_ptrs) with the operands marshalled (None passes NULL).
+    Host form (all operands numpy): upload -> launch -> download.  Resident form (any operand a DeviceTensor, or an output
+    slot named): no copies -- device pointers in, a DeviceTensor out."""
     ctx = ctx or default_context()
+    if _resident(ctx, *inputs):
+        ops = [None if a is None else ctx._operand(a) for a in inputs]
+        out = ctx._out(out_shape, out_dtype)
+        fn(ctx, vp(out.ptr), *[vp(None if o is None else o.ptr) for o in ops])
+        return out
     bufs = [None if a is None else ctx.upload(a) for a in inputs]
     out = ctx.empty(_b.max(_prod(out_shape), 1), np.dtype(out_dtype).itemsize)
     fn(ctx, vp(out.ptr), *[vp(None if b is None else b.ptr) for b in bufs])
@@ -115,6 +302,24 @@ def _run(out_shape, fn, *inputs, ctx=None, out_dtype=np.float32):
         if b is not None:
             b.free()
     out.free()
+    return res
+
+
+def _run_multi(out_shapes, fn, *inputs, ctx=None):
+    """Several outputs (lstm, gru, topk, dynamic_quantize_linear): fn(ctx, [out_ptrs], *in_ptrs) -> tuple, host or resident as _run."""
+    ctx = ctx or default_context()
+    if _resident(ctx, *inputs):
+        ops = [None if a is None else ctx._operand(a) for a in inputs]
+        outs = [ctx._out(s) for s in out_shapes]
+        fn(ctx, [vp(o.ptr) for o in outs], *[vp(None if o is None else o.ptr) for o in ops])
+        return tuple(outs)
+    bufs = [None if a is None else ctx.upload(a) for a in inputs]
+    outs = [ctx.empty(_b.max(_prod(s), 1)) for s in out_shapes]
+    fn(ctx, [vp(o.ptr) for o in outs], *[vp(None if b is None else b.ptr) for b in bufs])
+    res = tuple(ctx.download(o, s) for o, s in zip(outs, out_shapes))
+    for b in bufs + outs:
+        if b is not None:
+            b.free()
     return res
 
 
@@ -186,15 +391,10 @@ def rms_norm(x, w, epsilon=1e-5, ctx=None):
 
 # ---------------------------------------------------------------- quantization.rs
 def dynamic_quantize_linear(x, ctx=None):
-    """quantization.rs:1628 -> (q as f32, scale, zero_point)"""
-    ctx = ctx or default_context()
+    """quantization.rs:1628 -> (q as f32, scale, zero_point); scale / zero_point are [1] tensors (host floats in the host form)"""
     x = _f(x)
-    bx = ctx.upload(x); q = ctx.empty(_b.max(x.size, 1)); s = ctx.empty(1); z = ctx.empty(1)
-    call("lele_b200_dynamic_quantize_linear", ctx.h, vp(bx.ptr), i32(1), i64(x.size), vp(q.ptr), vp(s.ptr), vp(z.ptr))
-    out = ctx.download(q, x.shape), ctx.download(s, (1,))[0], ctx.download(z, (1,))[0]
-    for b in (bx, q, s, z):
-        b.free()
-    return out
+    q, s_, z = _run_multi([x.shape, (1,), (1,)], lambda c, o, px: call("lele_b200_dynamic_quantize_linear", c.h, px, i32(1), i64(x.size), o[0], o[1], o[2]), x, ctx=ctx)
+    return (q, s_, z) if isinstance(q, DeviceTensor) else (q, s_[0], z[0])
 
 
 def mat_mul_integer(a, b, a_zero_point=0.0, b_zero_point=0.0, scale=None, bias=None, relu=False, ctx=None):
@@ -264,7 +464,7 @@ def _pads4(p):
 def conv1d_fused(input, weights, bias, dilations, group, pads, strides, relu, ctx=None):
     """conv1d.rs:853"""
     x, w = _f(input), _f(weights)
-    if x.ndim == 2: x = x[:, None, :]
+    if x.ndim == 2: x = x.reshape((x.shape[0], 1, x.shape[1]))
     if x.ndim != 3: raise LeleB200Error(f"Conv1d: Unsupported input rank {x.ndim} (conv1d.rs:872)")
     nb, ic, l = x.shape; oc, _, k = w.shape
     dil = dilations[0] if len(dilations) else 1; st = strides[0] if len(strides) else 1
@@ -301,6 +501,18 @@ def conv2d_fused(input, weights, bias, dilations, group, pads, strides, relu, ct
 
 def conv2d_silu(input, weights, bias, dilations, group, pads, strides, ctx=None):
     return _conv2d(input, weights, bias, dilations, group, pads, strides, 2, ctx)
+
+
+def conv_integer(input, weights, x_zero_point=0.0, w_zero_point=0.0, dilations=(1, 1), group=1, pads=(0, 0, 0, 0), strides=(1, 1), ctx=None):
+    """conv2d.rs:2216 (emitted by ops/nn.rs:328): (x - x_zp) (*) (w - w_zp); padded positions hold raw zeros (conv2d.rs:2025).
+    Zero points: the scalar the reference reads from the zero-point tensor (`zp.data[0]`, 0 when absent or empty)."""
+    x, w = _f(input), _f(weights); nb, ic, h, wd = x.shape; oc, _, kh, kw = w.shape
+    p = _pads4(pads); s = list(strides) or [1, 1]; d = list(dilations) or [1, 1]
+    eh = h + p[0] + p[2] - d[0] * (kh - 1) - 1; ew = wd + p[1] + p[3] - d[1] * (kw - 1) - 1
+    oh = eh // s[0] + 1; ow = ew // s[1] + 1
+    if eh < 0 or ew < 0 or oh <= 0 or ow <= 0:
+        raise LeleB200Error(f"conv_integer: output dimensions must be positive, got out_h={oh} out_w={ow} (conv2d.rs:288)")
+    return _run((nb, oc, oh, ow), lambda c, o, px, pw: call("lele_b200_conv_integer", c.h, px, pw, f32(x_zero_point), f32(w_zero_point), i32(nb), i32(ic), i32(h), i32(wd), i32(oc), i32(kh), i32(kw), i32(group), _ints(p), _ints(s), _ints(d), o), x, w, ctx=ctx)
 
 
 def conv_transpose(input, weights, bias=None, dilations=(1, 1), pads=(0, 0, 0, 0), strides=(1, 1), group=1, ctx=None):
@@ -344,64 +556,48 @@ def resize_nearest(input, scales=None, sizes=None, coordinate_transform_mode="as
 # ---------------------------------------------------------------- rnn.rs
 def lstm(input, w, r, bias=None, sequence_lens=None, initial_h=None, initial_c=None, ctx=None):
     """rnn.rs:67 -> (Y [S,1,1,H], H [1,1,H], C [1,1,H])"""
-    ctx = ctx or default_context()
     x, w, r = _f(input), _f(w), _f(r)
     seq, bs, isz = x.shape
     if w.shape[0] != 1: raise LeleB200Error("LSTM: Only num_directions=1 supported (rnn.rs:85)")
     if bs != 1: raise LeleB200Error("LSTM: Only batch_size=1 supported (rnn.rs:88)")
     hid = w.shape[1] // 4
-    bufs = [ctx.upload(x), ctx.upload(w), ctx.upload(r)] + [None if a is None else ctx.upload(_f(a)) for a in (bias, initial_h, initial_c)]
-    y = ctx.empty(_b.max(seq * hid, 1)); h = ctx.empty(hid); c = ctx.empty(hid)
-    p = [vp(None if b is None else b.ptr) for b in bufs]
-    call("lele_b200_lstm", ctx.h, p[0], p[1], p[2], p[3], p[4], p[5], i32(1), i32(seq), i32(isz), i32(hid), vp(y.ptr), vp(h.ptr), vp(c.ptr))
-    out = ctx.download(y, (seq, 1, 1, hid)), ctx.download(h, (1, 1, hid)), ctx.download(c, (1, 1, hid))
-    for b in bufs + [y, h, c]:
-        if b is not None: b.free()
-    return out
+    opt = [None if a is None else _f(a) for a in (bias, initial_h, initial_c)]
+    return _run_multi([(seq, 1, 1, hid), (1, 1, hid), (1, 1, hid)],
+                      lambda c, o, px, pw, pr, pb, ph, pc: call("lele_b200_lstm", c.h, px, pw, pr, pb, ph, pc, i32(1), i32(seq), i32(isz), i32(hid), o[0], o[1], o[2]),
+                      x, w, r, *opt, ctx=ctx)
 
 
 def gru(input, w, r, bias=None, initial_h=None, linear_before_reset=False, ctx=None):
     """rnn.rs:246 -> (Y [S,1,1,H], H [1,1,H])"""
-    ctx = ctx or default_context()
     x, w, r = _f(input), _f(w), _f(r)
     seq, bs, isz = x.shape
     if w.shape[0] != 1: raise LeleB200Error("GRU: Only num_directions=1 supported (rnn.rs:262)")
     if bs != 1: raise LeleB200Error("GRU: Only batch_size=1 supported (rnn.rs:265)")
     hid = w.shape[1] // 3
-    bufs = [ctx.upload(x), ctx.upload(w), ctx.upload(r)] + [None if a is None else ctx.upload(_f(a)) for a in (bias, initial_h)]
-    y = ctx.empty(_b.max(seq * hid, 1)); h = ctx.empty(hid)
-    p = [vp(None if b is None else b.ptr) for b in bufs]
-    call("lele_b200_gru", ctx.h, p[0], p[1], p[2], p[3], p[4], i32(1), i32(seq), i32(isz), i32(hid), vp(y.ptr), vp(h.ptr))
-    out = ctx.download(y, (seq, 1, 1, hid)), ctx.download(h, (1, 1, hid))
-    for b in bufs + [y, h]:
-        if b is not None: b.free()
-    return out
+    opt = [None if a is None else _f(a) for a in (bias, initial_h)]
+    return _run_multi([(seq, 1, 1, hid), (1, 1, hid)],
+                      lambda c, o, px, pw, pr, pb, ph: call("lele_b200_gru", c.h, px, pw, pr, pb, ph, i32(1), i32(seq), i32(isz), i32(hid), o[0], o[1]),
+                      x, w, r, *opt, ctx=ctx)
 
 
 def _rnn_streams(gates, input, w, r, bias, initial_h, initial_c, ctx):
     """n_seq independent batch-1 sequences that share one set of weights, in ONE launch (the `n_seq` argument of
     lele_b200_lstm / lele_b200_gru; one CTA per stream).  Every stream gets exactly what the single-sequence call returns for it:
     the hoisted W.x GEMM and the recurrence sum in the same order whatever n_seq is."""
-    ctx = ctx or default_context()
     x, w, r = _f(input), _f(w), _f(r)
     if x.ndim != 3: raise LeleB200Error("rnn streams: input must be [n_seq, seq, input_size]")
     n_seq, seq, isz = x.shape
     if w.shape[0] != 1: raise LeleB200Error("RNN: Only num_directions=1 supported (rnn.rs:85)")
     hid = w.shape[1] // gates
-    if w.shape[2] != isz or r.shape[1:] != (gates * hid, hid): raise LeleB200Error("rnn streams: W / R shape mismatch")
+    if w.shape[2] != isz or tuple(r.shape[1:]) != (gates * hid, hid): raise LeleB200Error("rnn streams: W / R shape mismatch")
     states = [None if a is None else _f(a).reshape(n_seq, hid) for a in ((initial_h, initial_c) if gates == 4 else (initial_h,))]
-    bufs = [ctx.upload(x), ctx.upload(w), ctx.upload(r), None if bias is None else ctx.upload(_f(bias))] + [None if a is None else ctx.upload(a) for a in states]
-    y = ctx.empty(_b.max(n_seq * seq * hid, 1)); outs = [ctx.empty(_b.max(n_seq * hid, 1)) for _ in states]
-    p = [vp(None if b is None else b.ptr) for b in bufs]
     dims = (i32(n_seq), i32(seq), i32(isz), i32(hid))
+    shapes = [(n_seq, seq, hid)] + [(n_seq, hid)] * len(states)
     if gates == 4:
-        call("lele_b200_lstm", ctx.h, p[0], p[1], p[2], p[3], p[4], p[5], *dims, vp(y.ptr), vp(outs[0].ptr), vp(outs[1].ptr))
+        fn = lambda c, o, px, pw, pr, pb, ph, pc: call("lele_b200_lstm", c.h, px, pw, pr, pb, ph, pc, *dims, o[0], o[1], o[2])
     else:
-        call("lele_b200_gru", ctx.h, p[0], p[1], p[2], p[3], p[4], *dims, vp(y.ptr), vp(outs[0].ptr))
-    res = (ctx.download(y, (n_seq, seq, hid)),) + tuple(ctx.download(o, (n_seq, hid)) for o in outs)
-    for b in bufs + [y] + outs:
-        if b is not None: b.free()
-    return res
+        fn = lambda c, o, px, pw, pr, pb, ph: call("lele_b200_gru", c.h, px, pw, pr, pb, ph, *dims, o[0], o[1])
+    return _run_multi(shapes, fn, x, w, r, None if bias is None else _f(bias), *states, ctx=ctx)
 
 
 def lstm_streams(input, w, r, bias=None, initial_h=None, initial_c=None, ctx=None):
@@ -476,7 +672,8 @@ def _reduce(kind, x, axes, keepdims, ctx=None):
     x = _f(x)
     axes = sorted({a % x.ndim for a in axes})   # deduplicated (math.rs:1629); an empty list reduces nothing upstream (reduce_mask stays false, :1631)
     keep = [i for i in range(x.ndim) if i not in axes]
-    xt = np.ascontiguousarray(np.transpose(x, keep + axes)) if axes != list(range(x.ndim - len(axes), x.ndim)) else x
+    trailing = axes == list(range(x.ndim - len(axes), x.ndim))
+    xt = x if trailing else (transpose(x, keep + axes, ctx=ctx) if isinstance(x, DeviceTensor) else np.ascontiguousarray(np.transpose(x, keep + axes)))
     outer = _prod([x.shape[i] for i in keep]); alen = _prod([x.shape[i] for i in axes])
     out = _run((outer,), lambda c, o, px: call("lele_b200_reduce", c.h, i32(kind), px, i64(outer), i32(alen), i64(1), o), xt, ctx=ctx)
     shp = [1 if i in axes else x.shape[i] for i in range(x.ndim)] if keepdims else [x.shape[i] for i in keep]
@@ -603,20 +800,13 @@ def concat(inputs, axis, ctx=None):
         if a.ndim != ne[0].ndim: raise LeleB200Error("Concat: ranks mismatch (manipulation.rs:159)")
         if any(a.shape[i] != ne[0].shape[i] for i in range(a.ndim) if i != ax): raise LeleB200Error("Concat: inner dim mismatch (manipulation.rs:162)")
     outer = _prod(ne[0].shape[:ax]); inner = _prod(ne[0].shape[ax + 1:])
-    total_ax = sum(a.shape[ax] for a in ne)
-    shp = list(ne[0].shape); shp[ax] = total_ax
-    out = ctx.empty(_prod(shp))
-    done = 0
-    # the ABI takes up to 16 inputs per call; chain through the output for longer lists
-    bufs = [ctx.upload(a) for a in ne]
-    if len(ne) > 16:
+    shp = list(ne[0].shape); shp[ax] = sum(a.shape[ax] for a in ne)
+    if len(ne) > 16:   # the ABI takes up to 16 inputs per call
         raise LeleB200Error("concat: more than 16 inputs per call not supported by this wrapper")
-    ptrs = (vp * len(ne))(*[vp(b.ptr) for b in bufs])
-    call("lele_b200_concat", ctx.h, ptrs, _ll([a.shape[ax] for a in ne]), i32(len(ne)), i64(outer), i64(inner), vp(out.ptr))
-    res = ctx.download(out, shp)
-    for b in bufs + [out]:
-        b.free()
-    return res
+
+    def fn(c, o, *ptrs):
+        call("lele_b200_concat", c.h, (vp * len(ne))(*ptrs), _ll([a.shape[ax] for a in ne]), i32(len(ne)), i64(outer), i64(inner), o)
+    return _run(tuple(shp), fn, *ne, ctx=ctx)
 
 
 def pad(x, pads, constant_value=0.0, mode="constant", ctx=None):
@@ -638,7 +828,8 @@ def gather(data, indices, axis=0, ctx=None):
     """manipulation.rs:589"""
     x = _f(data); idx = _f(indices); ax = axis % x.ndim
     outer = _prod(x.shape[:ax]); inner = _prod(x.shape[ax + 1:])
-    shp = tuple(x.shape[:ax]) + tuple(np.shape(indices)) + tuple(x.shape[ax + 1:])   # a rank-0 index removes the axis (manipulation.rs:609)
+    ishape = indices.shape if isinstance(indices, DeviceTensor) else np.shape(indices)
+    shp = tuple(x.shape[:ax]) + tuple(ishape) + tuple(x.shape[ax + 1:])   # a rank-0 index removes the axis (manipulation.rs:609)
     return _run(shp, lambda c, o, px, pi: call("lele_b200_gather", c.h, px, i64(outer), i32(x.shape[ax]), i64(inner), pi, i64(idx.size), o), x, idx, ctx=ctx)
 
 
@@ -659,13 +850,9 @@ def tile(x, repeats, ctx=None):
 
 def topk(x, k, axis=-1, ctx=None):
     """conv2d.rs:1385 (last axis; indices as f32; `_axis` ignored upstream)"""
-    ctx = ctx or default_context()
     x = _f(x); n = x.shape[-1]; k = min(int(k), n); outer = x.size // n
-    bx = ctx.upload(x); v = ctx.empty(_b.max(outer * k, 1)); ix = ctx.empty(_b.max(outer * k, 1))
-    call("lele_b200_topk", ctx.h, vp(bx.ptr), i64(outer), i32(n), i32(k), vp(v.ptr), vp(ix.ptr))
-    out = ctx.download(v, x.shape[:-1] + (k,)), ctx.download(ix, x.shape[:-1] + (k,))
-    for b in (bx, v, ix): b.free()
-    return out
+    shp = tuple(x.shape[:-1]) + (k,)
+    return _run_multi([shp, shp], lambda c, o, px: call("lele_b200_topk", c.h, px, i64(outer), i32(n), i32(k), o[0], o[1]), x, ctx=ctx)
 
 
 def argmax_last(x, ctx=None):
@@ -675,7 +862,7 @@ def argmax_last(x, ctx=None):
 
 # zero-copy shape ops stay on the host (shape.rs:2-223)
 def _fh(a):   # like _f, but a rank-0 value keeps its rank (np.ascontiguousarray would make it rank 1)
-    return np.asarray(a, dtype=np.float32, order="C")
+    return a if isinstance(a, DeviceTensor) else np.asarray(a, dtype=np.float32, order="C")
 
 
 def reshape(x, shape):
@@ -691,7 +878,7 @@ def reshape(x, shape):
 def flatten(x, axis=1):
     """shape.rs:105: [prod(shape[:axis]), prod(shape[axis:])], negative axis counted from the end"""
     x = _fh(x); axis = axis + x.ndim if axis < 0 else axis
-    return x.reshape(_prod(x.shape[:axis]), _prod(x.shape[axis:]))
+    return x.reshape((_prod(x.shape[:axis]), _prod(x.shape[axis:])))
 
 
 def unsqueeze(x, axes):

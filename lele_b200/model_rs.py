@@ -19,7 +19,7 @@ import re
 
 import numpy as np
 
-__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view", "GeneratedModel", "resolve_reshape", "squeeze_shape", "unsqueeze_shape", "expand_shape"]
+__all__ = ["parse_model_rs", "run_program", "CudaOps", "weight_view", "GeneratedModel", "BatchRunner", "resolve_reshape", "squeeze_shape", "unsqueeze_shape", "expand_shape"]
 
 _DTYPES = {"weight_f32": ("<f4", None), "weight_i64": ("<i8", None), "weight_i64_f32": ("<i8", np.float32), "weight_i32": ("<i4", None),
            "weight_i32_i64": ("<i4", np.int64), "weight_i32_f32": ("<i4", np.float32), "weight_u8": ("u1", np.float32), "weight_i8": ("i1", np.float32),
@@ -199,8 +199,9 @@ def _parse_block(lines, i):
         m = re.match(r"^let (\w+) = self\.(\w+)\((.*)\);$", line)   # helper methods of src/compiler/snippets/default_methods.rs
         if m:
             args = [_parse_arg(a) for a in _split_top(m.group(3))]
+            bufs = [a["out"] for a in args if isinstance(a, dict) and "out" in a]
             args = [a for a in args if not (isinstance(a, dict) and "out" in a)]
-            stmts.append({"outs": [m.group(1)], "op": "self." + m.group(2), "args": args})
+            stmts.append({"outs": [m.group(1)], "op": "self." + m.group(2), "args": args, "bufs": bufs})
             continue
         m = re.match(r"^let (\w+) = (\w+)\.(?:clone|to_owned)\(\);", line)                 # incl. "// Cast f32->f32 is no-op" (ops/tensor.rs:236)
         if m:
@@ -213,8 +214,9 @@ def _parse_block(lines, i):
         if m:
             outs = [o.strip() for o in m.group(1).split(",")]   # "_" = an output the graph never reads
             args = [_parse_arg(a) for a in _split_top(m.group(3))]
-            args = [a for a in args if not (isinstance(a, dict) and "out" in a)]      # workspace buffers: the arena is the back-end's business
-            stmts.append({"outs": outs, "op": m.group(2), "args": args})
+            bufs = [a["out"] for a in args if isinstance(a, dict) and "out" in a]     # `&mut ws.buf_N` / `&mut buf_<name>`: where the outputs live
+            args = [a for a in args if not (isinstance(a, dict) and "out" in a)]      # (the resident replay binds them to HBM, see run_program)
+            stmts.append({"outs": outs, "op": m.group(2), "args": args, "bufs": bufs})
             continue
         raise ValueError(f"model.rs: unsupported statement: {line[:160]}")
     raise ValueError("model.rs: unterminated block")
@@ -267,6 +269,7 @@ class CudaOps:
 
     def conv2d(self, x, w, bias, dilations, group, pads, strides, act): return self.K.conv2d(x, w, bias, dilations, group, pads, strides, act, ctx=self.ctx)
     def conv_transpose(self, x, w, bias, dilations, pads, strides): return self.K.conv_transpose(x, w, bias, dilations, pads, strides, ctx=self.ctx)
+    def conv_integer(self, x, w, x_zp, w_zp, dilations, group, pads, strides): return self.K.conv_integer(x, w, x_zp, w_zp, dilations, group, pads, strides, ctx=self.ctx)
     def matmul(self, a, b): return self.K.matmul(a, b, ctx=self.ctx)
     def softmax(self, x, axis): return self.K.softmax(x, axis, ctx=self.ctx)
     def max_pool2d(self, x, kernel, pads, strides, dilations, ceil_mode): return self.K.max_pool2d(x, kernel, pads, strides, dilations, ceil_mode, ctx=self.ctx)
@@ -318,7 +321,20 @@ class _NamespaceOps:
     def resize_nearest(self, x, scales, sizes, mode): return self.ns.resize_nearest(x, scales=scales, sizes=sizes, mode=mode)
 
 
+def _is_dev(x):
+    return hasattr(x, "ptr") and hasattr(x, "numpy")           # lele_b200.kernels.DeviceTensor (not imported: the parser half of this
+                                                               # module is also loaded stand-alone, without the built library)
+
+
+def _host(x):
+    """`.data` read: a resident value crosses to the host only where the generated code itself reads the data (ops/nn.rs:434 Resize
+    scales, to_i64_vec, If conditions, scalar attributes carried by tensors)."""
+    return x.numpy() if _is_dev(x) else x
+
+
 def _c(x, dtype=None):  # C-contiguous without np.ascontiguousarray's promotion of rank-0 values to rank 1
+    if _is_dev(x):
+        return x
     return np.asarray(x, dtype=dtype, order="C")
 
 
@@ -406,13 +422,13 @@ def expand_shape(in_shape, target):
 
 def _reshape(x, shape):
     x = _c(x)
-    return x.reshape(resolve_reshape(x.shape, shape))
+    return x.reshape(tuple(resolve_reshape(x.shape, shape)))
 
 
 def _to_i64_list(x):  # to_i64_vec (manipulation.rs:1082): `as i64` truncation of every element
     if isinstance(x, (list, tuple)):
         return [int(v) for v in x]
-    return [int(v) for v in np.asarray(x).reshape(-1)]
+    return [int(v) for v in np.asarray(_host(x)).reshape(-1)]
 
 
 def _is_i64(x):
@@ -420,7 +436,7 @@ def _is_i64(x):
 
 
 def _scalar0(x, dflt):
-    x = np.asarray(x).reshape(-1)
+    x = np.asarray(_host(x)).reshape(-1)
     return x[0] if x.size else dflt
 
 
@@ -428,12 +444,14 @@ def _host_i64_op(op, a):
     """Shape arithmetic.  The code generator types shape-carrying values as i64 tensors (generate.rs var_types) and the reference
     computes them with the same generic kernels on the host; they are a few elements each and decide tensor SHAPES, so they stay
     host values here as well (numpy int64) and never reach the device.  Returns None when the statement is not of this class."""
-    if op == "shape":                                 # shape.rs:100
-        return np.array(np.asarray(a[0]).shape, np.int64)
+    if op == "shape":                                 # shape.rs:100 (a resident value carries its shape on the host)
+        return np.array(a[0].shape if _is_dev(a[0]) else np.asarray(a[0]).shape, np.int64)
     if op == "size":                                  # shape.rs:95: rank-0 tensor holding the element count
-        return np.array(np.asarray(a[0]).size, np.int64)
+        return np.array(a[0].size if _is_dev(a[0]) else np.asarray(a[0]).size, np.int64)
     if op == "to_i64_vec":
         return _to_i64_list(a[0])
+    if op in ("cast_to_i64", "cast_to_f32", "equal_i64", "equal_i64_f32_r", "equal_i64_f32_r_i64", "equal_i64_f32_lhs", "less_i64"):
+        a = [_host(v) for v in a]                     # element types change here: host values from this point (they feed shape logic)
     if op == "cast_to_i64":                           # utils.rs:85
         return np.trunc(np.asarray(a[0])).astype(np.int64) if np.asarray(a[0]).dtype.kind == "f" else np.asarray(a[0]).astype(np.int64)
     if op == "cast_to_f32":                           # utils.rs:71
@@ -485,19 +503,35 @@ def _host_i64_op(op, a):
     return None                                       # reshape / unsqueeze / squeeze / flatten / identity keep the dtype below
 
 
-def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
+def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, workspace=None, download=True):
     """Replays the statement list.  `blob` = the model's weights.bin bytes, `inputs` = arrays in `program["inputs"]` order.
     `ops`: CudaOps (default) or any module with the shared operator vocabulary.  Returns the outputs as numpy arrays.
     `cache`: a dict the caller keeps across calls of one model -- decoded weight views and, where the namespace offers
     `prepare_weights`, the device-resident packed int8 weights of each quantised linear are made once (the role of
-    B_WEIGHT_CACHE upstream, avx/quantization.rs:47-95: keyed by the weight's place in the blob)."""
+    B_WEIGHT_CACHE upstream, avx/quantization.rs:47-95: keyed by the weight's place in the blob).
+    `workspace` (a `lele_b200.kernels.Workspace`, CudaOps only): the RESIDENT replay -- src/tensor.rs's buffer arena mapped to
+    HBM.  Inputs are uploaded once, every statement's outputs are placed in the workspace buffer the generated code names
+    (`&mut ws.buf_N` -> `lele_b200_arena_bind`; values the generated code owns -- split_owned pieces, intermediates of composed
+    statements -- get a buffer keyed by their statement), weights are uploaded once per model, and nothing returns to the host
+    except where the generated code itself reads `.data` and, with `download`, the graph outputs (`.to_owned()`, generate.rs:748)."""
     if ops is None:
         ops = CudaOps()
     elif not hasattr(ops, "binary"):
         ops = _NamespaceOps(ops)
-    env = {n: _c(a, np.int64 if np.asarray(a).dtype.kind in "iu" else np.float32)
-           for n, a in zip(program["inputs"], inputs)}
+    resident = workspace is not None
+    if resident and not isinstance(ops, CudaOps):
+        raise ValueError("run_program: a workspace (resident replay) needs the CUDA operator namespace")
+    rctx = workspace.ctx if resident else None
+    env = {}
+    for n, a in zip(program["inputs"], inputs):
+        if _is_dev(a):
+            env[n] = a
+        elif np.asarray(a).dtype.kind in "iu":
+            env[n] = _c(a, np.int64)
+        else:
+            env[n] = rctx.to_device(np.asarray(a, np.float32)) if resident else _c(a, np.float32)
     split_cache = {}
+    stmt_no = [0]
 
     def val(a):
         if isinstance(a, dict):
@@ -513,6 +547,8 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
                 key = ("w", a["weight"][0], a["weight"][1], a["weight"][2], tuple(a["weight"][3]))
                 if key not in cache:
                     cache[key] = weight_view(blob, *a["weight"])
+                    if resident and a["weight"][0] == "weight_f32" and cache[key].size >= 64:
+                        rctx.persist(cache[key])          # device copy keyed by the view's address ((blob_base, offset) upstream)
                 return cache[key]
             if "weight_scalar" in a: return int(weight_view(blob, *a["weight_scalar"]).reshape(-1)[0])
             if "weight_list" in a: return [int(v) for v in weight_view(blob, *a["weight_list"]).reshape(-1)]
@@ -526,7 +562,7 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
 
     def exec_statement(st):
         if st["op"] == "if":                          # ops/control_flow.rs:41: the first element of the condition decides; names are
-            cond = np.asarray(env[st["args"][0]["var"]]).reshape(-1)   # graph-wide, so the taken branch runs in the same environment
+            cond = np.asarray(_host(env[st["args"][0]["var"]])).reshape(-1)   # graph-wide, so the taken branch runs in the same environment
             branch = st["then"] if (cond.size and cond[0] != 0) else st["else"]
             exec_block(branch["statements"])
             for n, o in zip(st["outs"], branch["outputs"]):
@@ -535,6 +571,13 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
                 trace.append((st["outs"][0] if st["outs"] else "", "if", env[st["outs"][0]] if st["outs"] else None))
             return
         op, a = st["op"], [val(x) for x in st["args"]]
+        if resident:
+            # the statement's own buffers first, then buffers keyed by the statement for whatever else it materialises
+            # (the allocator never hands a statement one of its own input buffers, mod.rs:234-253; a hand-written statement that does
+            # gets a statement-keyed buffer instead of an in-place launch)
+            stmt_no[0] += 1
+            held = {v.slot for x in a for v in (x if isinstance(x, (list, tuple)) else [x]) if _is_dev(v)}
+            rctx.out_slots([(workspace, b) for b in st.get("bufs", []) if b not in held] + [(workspace, f"stmt{stmt_no[0]}_{k}") for k in range(8)])
         r = _host_i64_op(op, a)
         if r is not None:
             pass
@@ -554,13 +597,17 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
         elif op == "conv_integer":                    # (x, w, x_zero_point, w_zero_point, dilations, group, pads, strides)  ops/nn.rs:328
             # conv2d.rs:1507-2000: an f32 convolution of (x - x_zp) with (w - w_zp); the im2col pads with RAW zeros, so a padded
             # position contributes (0 - x_zp) (conv2d.rs:2025) -- hence pad first, shift second, convolve without padding
-            xz, wz = (0.0 if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z in (a[2], a[3]))
+            xz, wz = (0.0 if z is None or np.size(_host(z)) == 0 else float(np.asarray(_host(z)).reshape(-1)[0]) for z in (a[2], a[3]))
             p4 = list(a[6]) if len(a[6]) >= 4 else (list(a[6]) * 2 if len(a[6]) == 2 else [0, 0, 0, 0])
-            x = ops.pad(a[0], [0, 0, p4[0], p4[1], 0, 0, p4[2], p4[3]], 0.0, "constant") if any(p4) else a[0]
-            if xz != 0.0:
-                x = ops.binary("sub", x, np.array([xz], np.float32))
-            w = np.asarray(a[1], np.float32) - np.float32(wz)
-            r = ops.conv2d(x, w, None, a[4], a[5], [0, 0, 0, 0], a[7], 0)
+            if hasattr(ops, "conv_integer"):          # the CUDA product has the operator as one C-ABI entry (lele_b200_conv_integer)
+                r = ops.conv_integer(a[0], a[1], xz, wz, a[4], a[5], p4, a[7])
+                x = None
+            else:
+              x = ops.pad(a[0], [0, 0, p4[0], p4[1], 0, 0, p4[2], p4[3]], 0.0, "constant") if any(p4) else a[0]
+              if xz != 0.0:
+                  x = ops.binary("sub", x, np.array([xz], np.float32))
+              w = np.asarray(a[1], np.float32) - np.float32(wz)
+              r = ops.conv2d(x, w, None, a[4], a[5], [0, 0, 0, 0], a[7], 0)
         elif op == "conv_transpose":
             if a[4] != 1:
                 raise ValueError("ConvTranspose: group > 1 not supported yet (conv2d.rs:3042)")
@@ -580,7 +627,7 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
         elif op == "gru":                             # (x, w, r, bias, initial_h, linear_before_reset) -> (Y, H)  ops/nn.rs:195
             r = ops.gru(a[0], a[1], a[2], a[3], a[4])
         elif op in ("self.linear_quantized", "self.linear_quantized_relu"):   # (x, weight_u8 [K,N], weight_scale, weight_zero, bias)  default_methods.rs:36-62
-            zero = int(np.asarray(a[3]).reshape(-1)[0]) if np.size(a[3]) else 0
+            zero = int(np.asarray(_host(a[3])).reshape(-1)[0]) if np.size(_host(a[3])) else 0
             w = a[1]
             if cache is not None and hasattr(ops, "prepare_weights") and all(isinstance(x, dict) and "weight" in x for x in st["args"][1:5]):
                 key = ("pw",) + tuple(x["weight"][1] for x in st["args"][1:5])
@@ -589,7 +636,7 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
                 w = cache[key]
             r = ops.fused_quantized_linear(a[0], w, a[2], zero, a[4], op.endswith("_relu"))
         elif op == "self.layer_norm":                 # (x, scale, bias, epsilon tensor, two)  default_methods.rs:24: axis -1, eps = epsilon[0] or 1e-5
-            eps = np.asarray(a[3]).reshape(-1)
+            eps = np.asarray(_host(a[3])).reshape(-1)
             r = ops.layer_norm(a[0], a[1], a[2], -1, float(eps[0]) if eps.size else 1e-5)
         elif op == "self.linear":
             r = ops.matmul_fused_add(a[0], a[1], a[2])
@@ -598,10 +645,10 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
         elif op == "dynamic_quantize_linear":         # -> (q as f32, scale, zero_point)  ops/tensor.rs:407
             r = ops.dynamic_quantize_linear(a[0])
         elif op == "mat_mul_integer":                 # (a, b, a_zero_point, b_zero_point)  ops/math.rs:43; zero points are scalar tensors
-            zp = [0.0 if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z in (a[2], a[3])]
+            zp = [0.0 if z is None or np.size(_host(z)) == 0 else float(np.asarray(_host(z)).reshape(-1)[0]) for z in (a[2], a[3])]
             r = ops.mat_mul_integer(a[0], a[1], zp[0], zp[1])
         elif op == "clip":                            # (x, min, max): scalar tensors; a missing bound is -inf / +inf (math.rs:15-20, :1990-1997)
-            lim = [d if z is None or np.size(z) == 0 else float(np.asarray(z).reshape(-1)[0]) for z, d in ((a[1], float("-inf")), (a[2], float("inf")))]
+            lim = [d if z is None or np.size(_host(z)) == 0 else float(np.asarray(_host(z)).reshape(-1)[0]) for z, d in ((a[1], float("-inf")), (a[2], float("inf")))]
             r = ops.clip(a[0], lim[0], lim[1])
         elif op == "batch_norm":                      # (x, scale, bias, mean, var, epsilon)  ops/nn.rs:352
             r = ops.batch_norm(a[0], a[1], a[2], a[3], a[4], a[5])
@@ -623,7 +670,7 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
             r = ops.expand(a[0], a[1])
         elif op == "squeeze":
             x = _c(a[0])
-            r = x.reshape(squeeze_shape(x.shape, a[1]))
+            r = x.reshape(tuple(squeeze_shape(x.shape, a[1])))
         elif op == "where_op":
             r = ops.where(a[0], a[1], a[2])
         elif op == "concat":
@@ -639,14 +686,14 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
             r = _reshape(a[0], a[1])
         elif op == "flatten":
             x = _c(a[0]); ax = a[1] + x.ndim if a[1] < 0 else a[1]                 # shape.rs:109: negative axis counted from the end
-            r = x.reshape(int(np.prod(x.shape[:ax], dtype=np.int64)), int(np.prod(x.shape[ax:], dtype=np.int64)))
+            r = x.reshape((int(np.prod(x.shape[:ax], dtype=np.int64)), int(np.prod(x.shape[ax:], dtype=np.int64))))
         elif op == "unsqueeze":
             r = _c(a[0])
-            r = r.reshape(unsqueeze_shape(r.shape, a[1]))
+            r = r.reshape(tuple(unsqueeze_shape(r.shape, a[1])))
         elif op == "transpose":
             r = ops.transpose(a[0], a[1])
         elif op == "resize_nearest":
-            scales = None if a[1] is None else [float(v) for v in np.asarray(a[1]).reshape(-1)]
+            scales = None if a[1] is None else [float(v) for v in np.asarray(_host(a[1])).reshape(-1)]
             r = ops.resize_nearest(a[0], scales, a[2], a[3])
         elif op == "matmul":
             r = ops.matmul(a[0], a[1])
@@ -682,7 +729,10 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None):
             trace.append((st["outs"][0], op, env[st["outs"][0]]))
 
     exec_block(program["statements"])
-    return [env[n] for n in program["outputs"]]
+    if resident:
+        rctx.out_slots([])
+    outs = [env[n] for n in program["outputs"]]
+    return [_host(o) for o in outs] if download else outs
 
 
 def synth_blob(program: dict, seed: int = 7, constants=None) -> bytes:
@@ -732,25 +782,29 @@ def synth_blob(program: dict, seed: int = 7, constants=None) -> bytes:
 class GeneratedModel:
     """The Python stand-in for the struct `lele_gen` emits (`pub struct <Class><'a> { data: &'a [u8] }`, mod.rs:1100-1135):
     `GeneratedModel(open("yolo26seg.rs").read(), weights_bytes)` is `Yolo26Seg::new(&bin)`, `forward(*inputs)` is `forward`
-    (inputs in the order of `forward_with_workspace`; one array back for a single-output graph, a tuple otherwise)."""
+    (inputs in the order of `forward_with_workspace`; one array back for a single-output graph, a tuple otherwise).
+    `resident=True` (CUDA namespace): the replay keeps every value in HBM -- `forward_with_workspace` over a `Workspace` whose
+    buffers are device mirrors (`lele_b200_arena_bind`); only the graph outputs are downloaded."""
 
-    def __init__(self, model_rs_text: str, weights: bytes, ops=None):
-        self.program = parse_model_rs(model_rs_text)
+    def __init__(self, model_rs, weights: bytes, ops=None, resident: bool = False):
+        self.program = model_rs if isinstance(model_rs, dict) else parse_model_rs(model_rs)   # a parsed program (tests/golden/*.json) or the source text
         self.class_name = self.program["class"]
         need = _blob_extent(self.program)
         if len(weights) < need:
             raise ValueError(f"{self.class_name}: weights blob has {len(weights)} bytes, the generated code reads up to byte {need}")
         self.weights = weights
         self.ops = ops
+        self.resident = resident
         self._cache = {}
+        self._ws = None
 
     @classmethod
-    def from_files(cls, rs_path: str, weights_path: str | None = None, ops=None):
+    def from_files(cls, rs_path: str, weights_path: str | None = None, ops=None, resident: bool = False):
         """`weights_path` defaults to `<stem>_weights.bin` next to the source, the name the compiler writes (mod.rs:1372)."""
         import os
         if weights_path is None:
             weights_path = os.path.splitext(rs_path)[0] + "_weights.bin"
-        return cls(open(rs_path).read(), open(weights_path, "rb").read(), ops)
+        return cls(open(rs_path).read(), open(weights_path, "rb").read(), ops, resident)
 
     @property
     def input_names(self):
@@ -760,15 +814,142 @@ class GeneratedModel:
     def output_names(self):
         return list(self.program["outputs"])
 
-    def forward(self, *inputs):
+    def workspace(self):
+        """`<Model>Workspace::new()` (mod.rs:1066): the device arena of this model instance, created on first use."""
+        if self._ws is None:
+            from . import kernels as K
+            if self.ops is None:
+                self.ops = CudaOps()
+            self._ws = K.Workspace(self.ops.ctx or K.default_context())
+        return self._ws
+
+    def forward(self, *inputs, trace=None):
         if len(inputs) != len(self.program["inputs"]):
             raise ValueError(f"{self.class_name}.forward takes {len(self.program['inputs'])} tensors ({', '.join(self.program['inputs'])})")
         if self.ops is None:
             self.ops = CudaOps()
-        out = run_program(self.program, self.weights, list(inputs), self.ops, cache=self._cache)
+        out = run_program(self.program, self.weights, list(inputs), self.ops, trace=trace, cache=self._cache,
+                          workspace=self.workspace() if self.resident else None)
         return out[0] if len(out) == 1 else tuple(out)
 
     __call__ = forward
+
+    def batch_runner(self, n_items: int, lanes: int = 8, ctx=None, graph: bool = True):
+        return BatchRunner(self, n_items, lanes, ctx, graph)
+
+
+class BatchRunner:
+    """`n_items` independent inputs through one generated model, resident.  Generated code bakes batch = 1 into its reshape /
+    gather constants, so the batch lives below the boundary exactly as in the SenseVoice runner: item i is its own
+    replay of the call list, with its own `Workspace` (its outputs stay valid until collected), on lane i % lanes -- a lane is a
+    `Context` (stream, scratch) of the same device, so the short launches of different items overlap on the GPU.  The first
+    `run` executes eagerly (sizes the arenas, uploads the weights once, shared by all lanes); the second captures the whole
+    step -- every item, every lane -- into one CUDA graph (`lele_b200_capture_begin/_end`, lanes joined by `stream_fork/_join`)
+    and every later `run` is: H2D of the inputs, one graph launch, D2H of the outputs."""
+
+    def __init__(self, model: GeneratedModel, n_items: int, lanes: int = 8, ctx=None, graph: bool = True):
+        from . import kernels as K
+        self.K, self.model, self.n = K, model, int(n_items)
+        origin = ctx or K.default_context()
+        self.lanes = [origin] + [K.Context(origin.device) for _ in range(max(1, min(int(lanes), self.n)) - 1)]
+        for c in self.lanes[1:]:
+            c._consts, c._keep = origin._consts, origin._keep          # one device copy of the weights for every lane
+        self.ops = [CudaOps(c) for c in self.lanes]
+        self.ws = [K.Workspace(self.lanes[i % len(self.lanes)]) for i in range(self.n)]
+        self.use_graph, self.graph, self.runs = graph, None, 0
+        self.inputs_dev, self.outs_dev = None, None
+
+    def _enqueue(self):
+        L = len(self.lanes)
+        origin = self.lanes[0]
+        for c in self.lanes[1:]:
+            origin.fork(c)
+        outs = []
+        for i in range(self.n):
+            outs.append(run_program(self.model.program, self.model.weights, self.inputs_dev[i], self.ops[i % L], cache=self.model._cache,
+                                    workspace=self.ws[i], download=False))
+        for c in self.lanes[1:]:
+            origin.join(c)
+        return outs
+
+    def upload(self, items):
+        """items[i] = list of host arrays (program input order).  Device staging buffers are allocated once; later calls copy into them
+        on the origin stream (asynchronously when the host arrays are pinned)."""
+        K, origin = self.K, self.lanes[0]
+        if len(items) != self.n:
+            raise ValueError(f"BatchRunner: {len(items)} items given, built for {self.n}")
+        if self.inputs_dev is None:
+            self.inputs_dev = [[origin.to_device(np.asarray(a, np.float32)) if np.asarray(a).dtype.kind == "f" else np.asarray(a, np.int64) for a in it] for it in items]
+            return
+        from ._lib import call, sz, vp
+        for it, devs in zip(items, self.inputs_dev):
+            for a, d in zip(it, devs):
+                if _is_dev(d):
+                    a = np.ascontiguousarray(a, np.float32)
+                    if a.shape != d.shape:
+                        raise ValueError("BatchRunner: input shapes are fixed after the first run (the captured graph bakes them)")
+                    call("lele_b200_h2d", origin.h, vp(d.ptr), a.ctypes.data_as(vp), sz(a.nbytes))
+
+    def launch(self):
+        """Enqueues one step on the device (no host synchronisation once the graph exists)."""
+        origin = self.lanes[0]
+        self.runs += 1
+        if self.graph is not None:
+            self.graph.launch()
+            return
+        if self.use_graph and self.runs == 2:
+            l0 = [c.launch_count() for c in self.lanes[1:]]
+            origin.capture_begin()
+            try:
+                self.outs_dev = self._enqueue()
+            except Exception:
+                try:
+                    origin.capture_end(0).close()
+                except Exception:
+                    pass
+                raise
+            self.graph = origin.capture_end(sum(c.launch_count() - a for c, a in zip(self.lanes[1:], l0)))
+            self.graph.launch()
+            return
+        self.outs_dev = self._enqueue()
+
+    def collect(self):
+        """Host copies of every item's graph outputs (`.to_owned()`): all device-to-host copies are enqueued on the origin stream
+        (which the lanes were joined to), then the stream is joined once."""
+        from ._lib import call, sz, vp
+        origin = self.lanes[0]
+        res = []
+        for outs in self.outs_dev:
+            row = []
+            for o in outs:
+                if _is_dev(o):
+                    h = np.empty(o.shape, dtype=o.dtype)
+                    if h.nbytes:
+                        call("lele_b200_d2h", origin.h, h.ctypes.data_as(vp), vp(o.ptr), sz(h.nbytes))
+                    row.append(h)
+                else:
+                    row.append(o)
+            res.append(row)
+        origin.sync()
+        return res
+
+    def run(self, items):
+        self.upload(items)
+        self.launch()
+        return self.collect()
+
+    def launch_count(self) -> int:
+        return sum(c.launch_count() for c in self.lanes)
+
+    def close(self):
+        if self.graph is not None:
+            self.graph.close(); self.graph = None
+        self.lanes[0].sync()
+        for w in self.ws:
+            w.release()
+        for c in self.lanes[1:]:
+            c._consts, c._keep = {}, []
+            c.close()
 
 
 def _blob_extent(program: dict) -> int:

@@ -57,6 +57,11 @@ class SenseVoice:
         call("lele_b200_sensevoice_transcribe_host_async", self.ctx.h, self.h, vp(pcm_host_ptr), i32(n_clips), i32(n_samples), i32(lang),
              i32(textnorm), vp(ids_host_ptr), i32(slot))
 
+    def set_comm(self, comm, root: int = 0):
+        """Attach a lele_b200.distributed.Comm: transcribe_host_async then gathers all ranks' ids on the device and only `root`
+        receives them ([world, n_clips, T'] in its ids buffer); pass ids_host_ptr = None on the other ranks."""
+        call("lele_b200_sensevoice_set_comm", self.h, None if comm is None else comm.h, i32(root))
+
     def transcribe_wait(self, slot: int):
         call("lele_b200_sensevoice_transcribe_wait", self.ctx.h, self.h, i32(slot))
 

@@ -226,11 +226,11 @@ def const_forms_direct(m, blob, x):
 VH = 16   # hidden size of the synthetic streaming model (Silero: 128)
 
 
-def vad_text(chunk=512):
+def vad_text(chunk=512, hidden=None):
     """A recurrent streaming model with Silero's calling convention (examples/silero/src/main.rs:121): (input [1, chunk], state [2,1,H],
     sr [1] i64) -> (probability [1,1], new state [2,1,H]).  STFT power frames -> Conv1d+ReLU -> LSTM over the frames with the carried
     (h, c) -> Gemm + Sigmoid on the last hidden state."""
-    H, nfr = VH, 33
+    H, nfr = (hidden or VH), 33
     o_cw = 0; o_cb = o_cw + 8 * nfr * 4; o_w = o_cb + 8 * 4; o_r = o_w + 4 * H * 8 * 4; o_b = o_r + 4 * H * H * 4; o_g = o_b + 8 * H * 4; o_gb = o_g + H * 4
     return f"""
 pub struct SynthVadWorkspace {{ pub buf_0: Vec<f32>, pub buf_1: Vec<f32>, }}
@@ -264,14 +264,35 @@ pub struct SynthVad<'a> {{ data: &'a [u8] }}
 """
 
 
-def vad_model(m):
-    prog = m.parse_model_rs(vad_text())
-    return prog, m.synth_blob(prog, 21)
+def vad_model(m, hidden=None):
+    prog = m.parse_model_rs(vad_text(hidden=hidden))
+    if hidden is None:
+        return prog, m.synth_blob(prog, 21)
+    # Silero-sized stand-in driven by real audio for 175 chunks x 8 frames: LSTM weights scaled by fan-in and a negative forget
+    # bias keep the carried cell state bounded (the reference's SIMD tanh is (1 - e^-2x) / (1 + e^-2x) with e^-2x overflowing to
+    # inf below x = -44: a cell state that drifts there is NaN upstream as well, avx/math.rs:81-97)
+    H, nfr = hidden, 33
+    o_cw = 0; o_cb = o_cw + 8 * nfr * 4; o_w = o_cb + 8 * 4; o_r = o_w + 4 * H * 8 * 4; o_b = o_r + 4 * H * H * 4
+    rng = np.random.default_rng(22)
+    bias = 0.1 * rng.standard_normal(8 * H); bias[2 * H:3 * H] -= 1.0          # gate order i, o, f, c (rnn.rs:67): Wb forget block
+    # frame energies of real speech reach ~2e2 (zh.wav: 221): the conv weights are scaled so the LSTM pre-activations stay O(1)
+    consts = {o_cw: 0.01 * rng.standard_normal(8 * nfr) / np.sqrt(nfr), o_w: rng.standard_normal(4 * H * 8) / np.sqrt(8.0),
+              o_r: rng.standard_normal(4 * H * H) / np.sqrt(H), o_b: bias}
+    return prog, m.synth_blob(prog, 21, consts)
 
 
-def vad_chunk_direct(m, blob, chunk, state):
+def read_wav_s16(path):
+    """fixtures/zh.wav as the reference's WavReader produces it (examples/silero/src/main.rs:70, examples/sensevoice/src/audio.rs:57):
+    canonical 44-byte RIFF header, mono s16 little-endian -> f32 / 32768."""
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"WAVE" and raw[36:40] == b"data"
+    n = int.from_bytes(raw[40:44], "little")
+    return (np.frombuffer(raw, "<i2", count=n // 2, offset=44).astype(np.float32) / np.float32(32768.0))
+
+
+def vad_chunk_direct(m, blob, chunk, state, hidden=None):
     """The same chunk step written as direct oracle calls."""
-    H, nfr = VH, 33
+    H, nfr = (hidden or VH), 33
     o_cw = 0; o_cb = o_cw + 8 * nfr * 4; o_w = o_cb + 32; o_r = o_w + 4 * H * 8 * 4; o_b = o_r + 4 * H * H * 4; o_g = o_b + 8 * H * 4; o_gb = o_g + H * 4
     W = lambda off, ln, shp: m.weight_view(blob, "weight_f32", off, ln, shp)
     x = R.mul((chunk * np.float32(32768.0)).reshape(1, -1), np.array([0.000030517578], np.float32))

@@ -44,6 +44,18 @@ def small_model_tc():
     m.close()
 
 
+def _qkv_with_v(m, B, T, H=4, dk=128):
+    """The projection's [q | k | v] rows of the last forward.  The product path keeps v only transposed (V^T [B][H][dk][Tp], the
+    attention kernel's P.V operand, which the FSMN block reads too) and never writes the row-major v columns, so they are rebuilt
+    from the "vt" workspace buffer here."""
+    d = H * dk
+    qkv = m.workspace("qkv", (B * T, 3 * d)).copy()
+    Tp = (T + 3) // 4 * 4
+    vt = m.workspace("vt", (B, H, dk, Tp))
+    qkv[:, 2 * d:] = vt[..., :T].transpose(0, 3, 1, 2).reshape(B * T, d)
+    return qkv
+
+
 def _oracle_attention(qkv, T, H=4, dk=128):
     d = H * dk
     q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
@@ -63,7 +75,7 @@ def test_tcgen05_attention_stage(small_model_tc, t):
     feats = (rng.standard_normal((B, t, 560)) * np.array([1.0, 2.5, 0.3])[:, None, None]).astype(np.float32)
     m.forward(feats, 3, 0, n_layers=1)
     T = t + 4
-    qkv = m.workspace("qkv", (B * T, 1536)); att = m.workspace("att", (B * T, 512))
+    qkv = _qkv_with_v(m, B, T); att = m.workspace("att", (B * T, 512))
     keys = m.workspace("keys", (SMALL.n_layers * 4 + 1, B, 8, 2), np.uint32)    # [site][clip][slot][min,max], sharded atomics
     for c in range(B):
         want = _oracle_attention(qkv[c * T:(c + 1) * T], T)
@@ -207,7 +219,7 @@ def test_full_size_first_layers_vs_oracle(full_model):
     assert got.shape == (271, 512)
     err = np.abs(got - want)
     assert err.max() / np.abs(want).max() < 0.1 and err.mean() / np.abs(want).mean() < 0.02   # normwise: tensor-core attention (see test_tc_network_close_to_oracle)
-    qkv = m.workspace("qkv", (271, 1536)); att = m.workspace("att", (271, 512))                  # layer-1 buffers of the last forward
+    qkv = _qkv_with_v(m, 1, 271); att = m.workspace("att", (271, 512))                            # layer-1 buffers of the last forward
     assert rel_err(att, _oracle_attention(qkv, 271)) < 1e-5                                       # the attention stage itself at T'=271
 
 
@@ -224,3 +236,87 @@ def test_full_size_batch_properties(full_model):
     np.testing.assert_array_equal(ids2[0], ids64[7]); np.testing.assert_array_equal(ids2[1], ids64[63])
     np.testing.assert_array_equal(ids2, logits2.shape[2] - 1 - np.argmax(logits2[:, :, ::-1], axis=2))
     assert np.isfinite(logits2).all() and len(np.unique(ids64)) > 10
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Parity of the BENCHED configuration (BASELINE configs[1]: 64 clips x 16 s, 70 layers, seed-1234 blob, product path =
+# tcgen05 3xTF32 attention + CUDA-graph replay) against the oracle.  The reference's own end-to-end bar for this model is
+# "logits MAE <= 1.0 and the arg-max sequences share tokens" (examples/sensevoice/tests/e2e_test.rs:125-185: lele vs ONNX
+# Runtime, i.e. two f32 implementations whose summation orders differ -- exactly the situation of a tensor-core attention
+# vs the CPU order).  The numbers are written to gpurun_out/parity_full_size.json; the asserted bounds are the measured
+# values of this test on B200 with margin (recorded beside the asserts).
+# ------------------------------------------------------------------------------------------------------------------
+PARITY_CLIPS = [0, 21, 42, 63]
+PARITY_DEPTHS = [1, 10, 35, 70]
+
+
+def _last_argmax(logits):
+    return logits.shape[-1] - 1 - np.argmax(logits[..., ::-1], axis=-1)
+
+
+def test_benched_configuration_vs_oracle(full_model):
+    import json
+    import os
+    blob, m = full_model
+    ref = R.SenseVoiceRef(blob)
+    pcm = synth_batch(0, 64, 256000)
+    for _ in range(3):                                             # eager pass, capture, replay: the ids compared are a graph replay's
+        ids64 = m.transcribe(pcm)
+    sub = pcm[PARITY_CLIPS]
+    ids4, logits4 = m.transcribe(sub, want_logits=True)
+    np.testing.assert_array_equal(ids4, ids64[PARITY_CLIPS])       # batch-invariant: the 4-clip logits are those of the benched batch
+    report = {"clips": PARITY_CLIPS, "rows_per_clip": int(ids64.shape[1]), "per_clip": [], "hidden_drift": []}
+    for j, c in enumerate(PARITY_CLIPS):
+        rids, rlog = ref.pcm_to_ids(pcm[c], want_logits=True)     # the whole path on the CPU: front-end, CMVN, 70 layers, CTC head
+        err = np.abs(logits4[j] - rlog)
+        report["per_clip"].append({"clip": c, "ids_agreement": float((ids64[c] == rids).mean()), "logits_mae": float(err.mean()),
+                                   "logits_max_abs": float(err.max()), "logits_ref_mean_abs": float(np.abs(rlog).mean()),
+                                   "logits_ref_max_abs": float(np.abs(rlog).max())})
+    # encoder only, identical (oracle-computed) features: hidden state after 1, 10, 35 layers and the logits after all 70
+    feats = np.stack([R.cmvn(R.frontend(pcm[c])) for c in PARITY_CLIPS])
+    for depth in PARITY_DEPTHS:
+        nl = -1 if depth == 70 else depth
+        got = m.forward(feats, 3, 0, n_layers=nl)
+        row = {"layers": depth, "rel_max": [], "rel_mean": [], "argmax_agreement": []}
+        for j in range(len(PARITY_CLIPS)):
+            want = ref.forward(feats[j], 3, 0, n_layers=nl)
+            e = np.abs(got[j] - want)
+            row["rel_max"].append(float(e.max() / np.abs(want).max())); row["rel_mean"].append(float(e.mean() / np.abs(want).mean()))
+            if depth == 70:
+                row["argmax_agreement"].append(float((_last_argmax(got[j]) == _last_argmax(want)).mean()))
+        report["hidden_drift"].append(row)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "parity_full_size.json"), "w") as fh:
+        json.dump(report, fh, indent=1)
+    print("PARITY", json.dumps(report))
+    for r in report["per_clip"]:
+        assert r["logits_mae"] <= 1.0, r                           # the reference's own bar (e2e_test.rs:143)
+        assert r["logits_mae"] <= FULL_MAE_BOUND * r["logits_ref_mean_abs"], r
+        assert r["ids_agreement"] >= FULL_IDS_BOUND, r
+    for row in report["hidden_drift"]:
+        assert max(row["rel_mean"]) <= FULL_DRIFT_BOUND[row["layers"]], row
+
+
+# measured on B200 (round 2, gpurun_out/parity_full_size.json -> profiles/r02_parity_full_size.json), asserted with margin
+FULL_MAE_BOUND = 0.05          # logits MAE relative to the mean |logit| of the oracle
+FULL_IDS_BOUND = 0.80          # share of the 271 greedy ids per clip equal to the oracle's
+FULL_DRIFT_BOUND = {1: 1e-3, 10: 2e-2, 35: 5e-2, 70: 5e-2}
+
+
+def test_full_size_simt_attention_bit_exact_vs_oracle():
+    """Same clips, same seed-1234 70-layer blob, CUDA-core attention in the oracle's summation order (LELE_B200_ATTN_SIMT=1): on
+    identical features the whole encoder + CTC head is the oracle's arithmetic (integer core exact, same f32 op order), so the
+    logits agree to f32 rounding of the last op and the ids are identical -- at full size, all 70 layers."""
+    blob = build_blob(SenseVoiceConfig(), seed=1234)
+    m = _make(blob, "simt", max_clips=2, max_samples=256000)
+    try:
+        ref = R.SenseVoiceRef(blob)
+        pcm = synth_batch(0, 64, 256000)[[0, 63]]
+        feats = np.stack([R.cmvn(R.frontend(p)) for p in pcm])
+        got, ids = m.forward(feats, 3, 0, want_ids=True)
+        for j in range(2):
+            want = ref.forward(feats[j], 3, 0)
+            assert rel_err(got[j], want) < 1e-5, j
+            np.testing.assert_array_equal(ids[j], _last_argmax(want))
+    finally:
+        m.close()
