@@ -3,9 +3,10 @@
 // host without torch.distributed (the Rust host of INTEGRATION.md, one process per GPU) can shard clips across the 8 GPUs of a box.
 // There is no collective inside the forward pass -- clips are independent end to end -- hence nothing to fuse with a kernel.
 //
-// NCCL is bound at run time (dlopen): the library links against nothing but the CUDA runtime, a single-GPU host never needs NCCL, and
-// inside a process that already carries an NCCL (torch's bundled one) the same loaded copy is reused (same soname).  Override the
-// path with LELE_B200_NCCL_LIB.  The 128-byte unique id is created on rank 0 (lele_b200_comm_unique_id) and handed to the other ranks
+// NCCL is bound at run time (dlopen, local scope): the library links against nothing but the CUDA runtime, a single-GPU host never
+// needs NCCL, and inside a process that already carries an NCCL (torch's bundled one) that loaded copy is reused (RTLD_NOLOAD probe
+// by soname first).  LELE_B200_NCCL_LIB names the file explicitly -- the Python package sets it to the pip-installed NCCL that torch
+// itself loads, so that importing torch AFTER the first collective still finds the NCCL it was built against.  The 128-byte unique id is created on rank 0 (lele_b200_comm_unique_id) and handed to the other ranks
 // by the host's own means (a file, a socket, MPI, torch.distributed's store ...) -- rendez-vous is host plumbing, not part of the path.
 #include "common.cuh"
 #include <dlfcn.h>
@@ -43,11 +44,12 @@ NcclApi* nccl_api() {
     static bool tried = false;
     if (tried) return api.handle ? &api : nullptr;
     tried = true;
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);      // an NCCL this process already runs
     const char* names[] = {getenv("LELE_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-        if (!n || !n[0]) continue;
-        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (api.handle) break;
+        if (!n || !n[0]) continue;
+        api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
     }
     if (!api.handle) { lb_set_error("comm: cannot load NCCL (%s); set LELE_B200_NCCL_LIB", dlerror()); return nullptr; }
     bool ok = true;

@@ -40,8 +40,6 @@ struct lele_b200_ctx {
     struct TmapEntry { unsigned long long key[10]; unsigned long long stamp; unsigned char blob[128]; };
     std::unordered_map<unsigned long long, TmapEntry> tmaps;
     unsigned long long tmap_clock = 0;
-    // dynamic shared-memory opt-in already applied on THIS device, per kernel function
-    std::unordered_map<const void*, size_t> func_smem;
     // device-side precondition failures (the reference panics, e.g. a gather index out of range, manipulation.rs:589): kernels
     // clamp the access and raise this word; lele_b200_sync() reads it back (only when a checking kernel ran since the last sync)
     int* dev_err = nullptr;
@@ -56,7 +54,7 @@ struct lele_b200_ctx {
 bool lb_tmap_lookup(lele_b200_ctx* ctx, const unsigned long long (&key)[10], void* blob128);
 void lb_tmap_store(lele_b200_ctx* ctx, const unsigned long long (&key)[10], const void* blob128);
 void lb_tmap_forget_range(lele_b200_ctx* ctx, const void* base, size_t bytes);   // bytes == 0: every entry whose pointer == base
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (context = device, kernel)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), raised (never lowered) per (device, kernel)
 int lb_func_smem(lele_b200_ctx* ctx, const void* func, size_t bytes);
 // makes the context's device current for the calling thread (every entry point starts with it)
 int lb_enter(lele_b200_ctx* ctx);
@@ -77,6 +75,7 @@ int lb_scratch2(lele_b200_ctx* ctx, size_t bytes, void** out);
         cudaError_t _e = (expr);                                                             \
         if (_e != cudaSuccess) {                                                             \
             lb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            cudaGetLastError(); /* reported here: must not resurface at the next launch check */ \
             return LELE_B200_ERR_CUDA;                                                       \
         }                                                                                    \
     } while (0)

@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <stdarg.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 static thread_local char g_err[1024] = "";
 
@@ -225,11 +227,17 @@ int lb_enter(lele_b200_ctx* ctx) {
     return LELE_B200_OK;
 }
 
+// The opt-in is a property of (device, kernel), shared by every context on that device, and must only ever be RAISED: a second
+// context asking for less would otherwise lower it under a context that already launches with more.  One process-wide table,
+// keyed by (device, function), guarded for hosts that drive several contexts from several threads.
 int lb_func_smem(lele_b200_ctx* ctx, const void* func, size_t bytes) {
-    auto it = ctx->func_smem.find(func);
-    if (it != ctx->func_smem.end() && it->second >= bytes) return LELE_B200_OK;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = granted[std::make_pair(ctx->device, func)];
+    if (cur >= bytes && cur != 0) return LELE_B200_OK;
     LB_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes ? bytes : 16)));
-    ctx->func_smem[func] = bytes;
+    cur = bytes ? bytes : 16;
     return LELE_B200_OK;
 }
 

@@ -14,6 +14,37 @@ import os
 import numpy as np
 
 
+def nccl_library_path() -> str | None:
+    """The NCCL a Python host should bind: the pip-installed one next to torch (nvidia/nccl/lib/libnccl.so.2) when it exists.  A
+    process has ONE libnccl.so.2 (the loader de-duplicates by soname): if the library bound the system NCCL first, a later
+    `import torch` would be handed that copy instead of the version it was built against."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    return None
+
+
+def ensure_nccl_env():
+    if not os.environ.get("LELE_B200_NCCL_LIB"):
+        p = nccl_library_path()
+        if p:
+            os.environ["LELE_B200_NCCL_LIB"] = p
+
+
+ensure_nccl_env()
+
+
+def nccl_version() -> int:
+    from ._lib import lib
+    return int(lib.lele_b200_comm_nccl_version())
+
+
 class Comm:
     """The library's own communicator (include/lele_b200.h `lele_b200_comm_*`: NCCL bound at run time): what a host without
     torch.distributed uses.  `Comm.create(ctx, rank, world, exchange)`: rank 0 makes the 128-byte NCCL id, `exchange(bytes | None)

@@ -599,15 +599,7 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, w
             # position contributes (0 - x_zp) (conv2d.rs:2025) -- hence pad first, shift second, convolve without padding
             xz, wz = (0.0 if z is None or np.size(_host(z)) == 0 else float(np.asarray(_host(z)).reshape(-1)[0]) for z in (a[2], a[3]))
             p4 = list(a[6]) if len(a[6]) >= 4 else (list(a[6]) * 2 if len(a[6]) == 2 else [0, 0, 0, 0])
-            if hasattr(ops, "conv_integer"):          # the CUDA product has the operator as one C-ABI entry (lele_b200_conv_integer)
-                r = ops.conv_integer(a[0], a[1], xz, wz, a[4], a[5], p4, a[7])
-                x = None
-            else:
-              x = ops.pad(a[0], [0, 0, p4[0], p4[1], 0, 0, p4[2], p4[3]], 0.0, "constant") if any(p4) else a[0]
-              if xz != 0.0:
-                  x = ops.binary("sub", x, np.array([xz], np.float32))
-              w = np.asarray(a[1], np.float32) - np.float32(wz)
-              r = ops.conv2d(x, w, None, a[4], a[5], [0, 0, 0, 0], a[7], 0)
+            r = ops.conv_integer(a[0], a[1], xz, wz, a[4], a[5], p4, a[7])   # one C-ABI entry on the device (lele_b200_conv_integer)
         elif op == "conv_transpose":
             if a[4] != 1:
                 raise ValueError("ConvTranspose: group > 1 not supported yet (conv2d.rs:3042)")

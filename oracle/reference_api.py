@@ -65,3 +65,16 @@ maximum, neg, sqrt, reciprocal, clip, mod_f32, prelu = N.maximum, N.neg, N.sqrt,
 pow, log, sin, cos, equal, less, not_ = N.pow, N.log, N.sin, N.cos, N.equal, N.less, N.not_  # noqa: A001
 reduce = N.reduce
 SenseVoiceRef = B.SenseVoiceRef
+
+
+def conv_integer(x, w, x_zp, w_zp, dilations, group, pads, strides):
+    """conv_integer (conv2d.rs:2216 -> conv2d_with_zero_points :1507-2000): an f32 convolution of (x - x_zp) with (w - w_zp); the
+    im2col pads with RAW zeros, so a padded position contributes (0 - x_zp) (conv2d.rs:2025): pad first, shift second, convolve
+    without padding."""
+    p = list(pads) if len(pads) >= 4 else (list(pads) * 2 if len(pads) == 2 else [0, 0, 0, 0])
+    x = np.asarray(x, np.float32)
+    if any(p):
+        x = N.pad(x, [0, 0, p[0], p[1], 0, 0, p[2], p[3]], 0.0, "constant")
+    if x_zp != 0.0:
+        x = N.sub(x, np.array([x_zp], np.float32))
+    return B.conv2d(x, np.asarray(w, np.float32) - np.float32(w_zp), None, dilations, group, [0, 0, 0, 0], strides, 0)

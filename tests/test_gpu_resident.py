@@ -217,8 +217,9 @@ def test_argmax_treats_both_zeros_as_equal():
 def test_comm_entries_single_rank():
     """lele_b200_comm_* with a world of one (the 2..8-rank form runs under torchrun in bench.py): NCCL loads, a communicator forms,
     broadcast is the identity and gather copies the rank's own contribution into slot 0."""
+    from lele_b200 import distributed as D                 # (sets LELE_B200_NCCL_LIB to the NCCL torch itself loads)
     ctx = K.default_context()
-    ver = _lib.lib.lele_b200_comm_nccl_version()
+    ver = D.nccl_version()
     assert ver >= 22000, ver
     uid = (C.c_char * 128)()
     _lib.call("lele_b200_comm_unique_id", uid)

@@ -414,3 +414,33 @@ def test_network_oracle_equals_composition_of_pinned_operators():
     assert float(np.abs(logits - want_logits).max() / np.abs(want_logits).max()) < 1e-3
     last_max = logits.shape[1] - 1 - np.argmax(logits[:, ::-1], axis=1)
     np.testing.assert_array_equal(ids, last_max)
+
+
+def test_network_sensitivity_floor_of_the_oracle_itself():
+    import os
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    """The end-to-end bar of tests/test_gpu_sensevoice.py::test_benched_configuration_vs_oracle, measured where it can be measured
+    without a GPU: the 70-layer seed-1234 network run twice ON THE ORACLE, the second time on features multiplied by
+    (1 + 1e-7 N(0,1)) (about one ulp).  281 dynamic quantisers turn that into flipped u8 codes and the two runs decorrelate to a
+    saturation level set by the quantisation step, not by the size of the perturbation: ~3 % of the mean |logit|, ~93 % shared
+    greedy ids.  Any implementation that differs from the reference by one rounding anywhere sits on this floor."""
+    import json
+    from lele_b200.sensevoice_weights import SenseVoiceConfig, build_blob, synth_batch
+    blob = build_blob(SenseVoiceConfig(), seed=1234)
+    ref = R.SenseVoiceRef(blob)
+    feats = R.cmvn(R.frontend(synth_batch(0, 1, 256000)[0]))
+    rng = np.random.default_rng(0)
+    last = lambda l: l.shape[-1] - 1 - np.argmax(l[..., ::-1], -1)
+    base10, base70 = ref.forward(feats, 3, 0, n_layers=10), ref.forward(feats, 3, 0)
+    report = []
+    for eps in (1e-7, 1e-5):
+        twin = (feats * (1 + eps * rng.standard_normal(feats.shape))).astype(np.float32)
+        t10, t70 = ref.forward(twin, 3, 0, n_layers=10), ref.forward(twin, 3, 0)
+        report.append({"relative_input_noise": eps, "rel_mean_layer10": float(np.abs(t10 - base10).mean() / np.abs(base10).mean()),
+                       "rel_mean_logits": float(np.abs(t70 - base70).mean() / np.abs(base70).mean()), "logits_mae": float(np.abs(t70 - base70).mean()),
+                       "ids_agreement": float((last(t70) == last(base70)).mean())})
+    with open(os.path.join(ROOT, "profiles", "r02_oracle_self_sensitivity.json"), "w") as fh:
+        json.dump({"what": "CPU oracle vs itself on ~1-ulp / 1e-5 perturbed features, clip 0, 70 layers, seed 1234", "rows": report}, fh, indent=1)
+    for r in report:
+        assert 0.005 < r["rel_mean_logits"] < 0.06 and 0.8 < r["ids_agreement"] < 0.995 and r["logits_mae"] < 0.06, r
+    assert report[1]["rel_mean_logits"] < 1.5 * report[0]["rel_mean_logits"]      # saturation: 100x the noise, the same floor
