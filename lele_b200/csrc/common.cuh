@@ -48,6 +48,9 @@ struct lele_b200_ctx {
     cudaEvent_t ev = nullptr;
     unsigned long long capture_l0 = 0;
     bool capturing = false;
+    // allocations released while the stream was being captured (a free must join the stream first, which a capture forbids):
+    // handed to cudaFree at the next point where joining is legal
+    std::vector<void*> deferred_free;
 };
 #define LB_TMAP_CACHE_MAX 4096
 // key = {kind tag, pointer, dim/stride/box words...}; returns true and fills `blob128` on a verified hit
@@ -58,6 +61,8 @@ void lb_tmap_forget_range(lele_b200_ctx* ctx, const void* base, size_t bytes);  
 int lb_func_smem(lele_b200_ctx* ctx, const void* func, size_t bytes);
 // makes the context's device current for the calling thread (every entry point starts with it)
 int lb_enter(lele_b200_ctx* ctx);
+bool lb_stream_capturing(lele_b200_ctx* ctx);
+void lb_flush_deferred_free(lele_b200_ctx* ctx);   // call only where the stream was just joined
 #define LB_ENTER(ctx) do { int _rc_enter = lb_enter(ctx); if (_rc_enter) return _rc_enter; } while (0)
 static inline unsigned long long lb_hash_mix(unsigned long long h, unsigned long long v) {
     h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
@@ -234,6 +239,12 @@ __device__ __forceinline__ float lb_cephes_expf(float x) {
     int e = ((int)fx + 127) << 23;
     return __fmul_rn(y, __int_as_float(e));
 }
+// The scalar tails of lele's SIMD row kernels call libm's expf (avx/norm.rs:196, glibc: correctly rounded in all but astronomically
+// rare cases); CUDA's expf carries up to 2 ulp.  exp in double, rounded once to float, reproduces the libm result, so the row
+// tails -- 7 of the 271 columns of a SenseVoice score row -- do not seed 1-ulp differences that a later quantiser turns into
+// flipped codes: with it the CUDA-core-attention path is bit-identical to the CPU restatement through all 70 layers at T' = 271
+// (tests/test_gpu_sensevoice.py::test_full_size_simt_attention_is_bit_identical).
+__device__ __forceinline__ float lb_libm_expf(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float lb_sigmoid_simd(float x) {  // avx/math.rs:69
     return __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_cephes_expf(-x)));
 }

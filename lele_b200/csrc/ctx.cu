@@ -63,6 +63,7 @@ extern "C" int lele_b200_ctx_destroy(lele_b200_ctx* ctx) {
     if (!ctx) return LELE_B200_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    lb_flush_deferred_free(ctx);
     for (auto& kv : ctx->arena) cudaFree(kv.second.dptr);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     if (ctx->scratch) cudaFree(ctx->scratch);
@@ -77,11 +78,13 @@ extern "C" int lele_b200_ctx_destroy(lele_b200_ctx* ctx) {
 extern "C" int lele_b200_sync(lele_b200_ctx* ctx) {
     LB_REQUIRE(ctx, "sync: NULL ctx");
     LB_ENTER(ctx);
+    LB_REQUIRE(!lb_stream_capturing(ctx), "sync: the context's stream is being captured into a graph (nothing on a captured path may join the stream)");
     if (ctx->dev_err_armed) {
         int flag = 0;
         LB_CHECK_CUDA(cudaMemcpyAsync(&flag, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->dev_err_armed = false;
+        lb_flush_deferred_free(ctx);
         if (flag) {
             cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), ctx->stream);
             lb_set_error("%s: index out of range for the gathered axis (the reference panics, manipulation.rs:589 / conv2d.rs:1438)",
@@ -91,6 +94,7 @@ extern "C" int lele_b200_sync(lele_b200_ctx* ctx) {
         return LELE_B200_OK;
     }
     LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    lb_flush_deferred_free(ctx);
     return LELE_B200_OK;
 }
 
@@ -107,8 +111,10 @@ extern "C" int lele_b200_free(lele_b200_ctx* ctx, void* dptr) {
     LB_REQUIRE(ctx, "free: NULL ctx");
     LB_ENTER(ctx);
     if (dptr) {
-        LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
         lb_tmap_forget_range(ctx, dptr, 0);          // descriptors of a freed tensor must not outlive it
+        if (lb_stream_capturing(ctx)) { ctx->deferred_free.push_back(dptr); return LELE_B200_OK; }   // (e.g. a host GC running during a capture)
+        LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        lb_flush_deferred_free(ctx);
         LB_CHECK_CUDA(cudaFree(dptr));
     }
     return LELE_B200_OK;
@@ -220,6 +226,17 @@ int lb_table(lele_b200_ctx* ctx, const std::string& key, const void* host, size_
     return LELE_B200_OK;
 }
 
+
+bool lb_stream_capturing(lele_b200_ctx* ctx) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess) { cudaGetLastError(); return ctx->capturing; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+void lb_flush_deferred_free(lele_b200_ctx* ctx) {
+    for (void* p : ctx->deferred_free) cudaFree(p);
+    ctx->deferred_free.clear();
+}
 
 int lb_enter(lele_b200_ctx* ctx) {
     int cur = -1;

@@ -117,9 +117,9 @@ __global__ void where_kernel(const float* __restrict__ c, const float* __restric
 __device__ __forceinline__ float un_op(int op, float v, bool simd) {
     switch (op) {
         case LELE_B200_RELU: return fmaxf(v, 0.0f);
-        case LELE_B200_SIGMOID: return simd ? lb_sigmoid_simd(v) : __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+        case LELE_B200_SIGMOID: return simd ? lb_sigmoid_simd(v) : __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_libm_expf(-v)));
         case LELE_B200_TANH: return simd ? lb_tanh_simd(v) : tanhf(v);
-        case LELE_B200_SILU: return simd ? __fmul_rn(v, lb_sigmoid_simd(v)) : __fdiv_rn(v, __fadd_rn(1.0f, expf(-v)));
+        case LELE_B200_SILU: return simd ? __fmul_rn(v, lb_sigmoid_simd(v)) : __fdiv_rn(v, __fadd_rn(1.0f, lb_libm_expf(-v)));
         case LELE_B200_ERF: return simd ? lb_erf_simd(v) : erff(v);
         case LELE_B200_GELU: {   // 0.5 x (1 + erf(x / sqrt2))  math.rs:906
             float t = __fmul_rn(v, 0.70710678f);
@@ -131,7 +131,7 @@ __device__ __forceinline__ float un_op(int op, float v, bool simd) {
             return __fmul_rn(__fmul_rn(0.5f, v), __fadd_rn(1.0f, tanhf(u)));
         }
         case LELE_B200_EXP: return simd ? lb_cephes_expf(v) : expf(v);
-        case LELE_B200_SOFTPLUS: return v > 20.0f ? v : logf(__fadd_rn(1.0f, expf(v)));   // math.rs:1046
+        case LELE_B200_SOFTPLUS: return v > 20.0f ? v : logf(__fadd_rn(1.0f, lb_libm_expf(v)));   // math.rs:1046
         case LELE_B200_LOG: return logf(v);
         case LELE_B200_SQRT: return __fsqrt_rn(v);
         case LELE_B200_NEG: return -v;

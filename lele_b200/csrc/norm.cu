@@ -666,7 +666,7 @@ softmax_kernel(const float* __restrict__ x, long long outer, int n, float* __res
     mx = lb_warp_max(mx);
     for (int j = lane; j < n; j += 32) {
         float d = __fsub_rn(xr[j], mx);
-        o[j] = j < simd_end ? lb_cephes_expf(d) : expf(d);
+        o[j] = j < simd_end ? lb_cephes_expf(d) : lb_libm_expf(d);
     }
     __syncwarp();
     // sum in the AVX2 accumulator order (avx/norm.rs:169-205)

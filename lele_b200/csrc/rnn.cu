@@ -35,9 +35,9 @@ __device__ __forceinline__ float rnn_gate_step(int k, int H, int GH, int simd_en
             float bw = bias ? bias[gi] : 0.0f, br = bias ? bias[GH + gi] : 0.0f;
             g4[q] = __fadd_rn(__fadd_rn(__fadd_rn(wc[gi], rc[gi]), bw), br);
         }
-        float ig = sd ? lb_sigmoid_simd(g4[0]) : __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g4[0])));
-        float og = sd ? lb_sigmoid_simd(g4[1]) : __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g4[1])));
-        float fg = sd ? lb_sigmoid_simd(g4[2]) : __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g4[2])));
+        float ig = sd ? lb_sigmoid_simd(g4[0]) : __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_libm_expf(-g4[0])));
+        float og = sd ? lb_sigmoid_simd(g4[1]) : __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_libm_expf(-g4[1])));
+        float fg = sd ? lb_sigmoid_simd(g4[2]) : __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_libm_expf(-g4[2])));
         float cg = sd ? lb_tanh_simd(g4[3]) : tanhf(g4[3]);
         float ct = sd ? __fmaf_rn(fg, c[k], __fmul_rn(ig, cg)) : __fadd_rn(__fmul_rn(fg, c[k]), __fmul_rn(ig, cg));
         ht = __fmul_rn(og, sd ? lb_tanh_simd(ct) : tanhf(ct));
@@ -54,8 +54,8 @@ __device__ __forceinline__ float rnn_gate_step(int k, int H, int GH, int simd_en
             zp = __fadd_rn(__fadd_rn(__fadd_rn(wc[k], rc[k]), bwz), brz);
             rp = __fadd_rn(__fadd_rn(__fadd_rn(wc[H + k], rc[H + k]), bwr), brr);
         }
-        float z = sd ? lb_sigmoid_simd(zp) : __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-zp)));
-        float rg = sd ? lb_sigmoid_simd(rp) : __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-rp)));
+        float z = sd ? lb_sigmoid_simd(zp) : __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_libm_expf(-zp)));
+        float rg = sd ? lb_sigmoid_simd(rp) : __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_libm_expf(-rp)));
         float hp = __fadd_rn(__fadd_rn(wc[2 * H + k], bwh), __fmul_rn(rg, __fadd_rn(rc[2 * H + k], brh)));
         float hg = sd ? lb_tanh_simd(hp) : tanhf(hp);
         ht = sd ? __fmaf_rn(__fsub_rn(1.0f, z), hg, __fmul_rn(z, h[k]))

@@ -173,7 +173,7 @@ softmax_rows_kernel(float* __restrict__ s, long long rows, int n) {
     mx = lb_warp_max(mx);
     for (int j = lane; j < n; j += 32) {
         float dlt = __fsub_rn(xr[j], mx);
-        xr[j] = j < simd_end ? lb_cephes_expf(dlt) : expf(dlt);
+        xr[j] = j < simd_end ? lb_cephes_expf(dlt) : lb_libm_expf(dlt);
     }
     __syncwarp();
     const float sum = lb_avx_order_reduce(n, lane, [&](float acc, int j) { return __fadd_rn(acc, xr[j]); },

@@ -890,7 +890,10 @@ class BatchRunner:
             self.graph.launch()
             return
         if self.use_graph and self.runs == 2:
+            import gc
             l0 = [c.launch_count() for c in self.lanes[1:]]
+            gc.collect()                                    # finalisers free device buffers, and a free joins the stream: none may run
+            gc_was = gc.isenabled(); gc.disable()           # inside the capture (the library also defers such frees, csrc/ctx.cu)
             origin.capture_begin()
             try:
                 self.outs_dev = self._enqueue()
@@ -900,6 +903,9 @@ class BatchRunner:
                 except Exception:
                     pass
                 raise
+            finally:
+                if gc_was:
+                    gc.enable()
             self.graph = origin.capture_end(sum(c.launch_count() - a for c, a in zip(self.lanes[1:], l0)))
             self.graph.launch()
             return

@@ -329,12 +329,13 @@ def test_benched_configuration_vs_oracle(full_model):
         assert r["ids_agreement"] >= 0.75, r                       # measured 0.83-0.93
 
 
-def test_full_size_simt_attention_vs_oracle():
-    """Same clips, same seed-1234 70-layer blob, CUDA-core attention in the oracle's summation order (LELE_B200_ATTN_SIMT=1).  Every
-    stage is then the oracle's arithmetic up to the last bit of a handful of transcendental / division results, and at T' = 271 x 70
-    layers those few ulps are enough to flip quantiser codes: the path lands on the same floor as the tensor-core one (the numbers
-    are recorded next to the product path's, gpurun_out/parity_full_size_simt.json), which is what shows that the tensor-core
-    attention is not what sets the end-to-end deviation."""
+def test_full_size_simt_attention_is_bit_identical():
+    """Same clips, same seed-1234 70-layer blob, CUDA-core attention in the oracle's summation order (LELE_B200_ATTN_SIMT=1): on
+    identical features the whole encoder + CTC head IS the oracle's arithmetic -- integer core exact, LayerNorm / softmax in the AVX2
+    accumulator order, the polynomial exp in the SIMD bodies and a correctly rounded exp in the scalar tails (lb_libm_expf) -- and the
+    result is bit-identical at full size: hidden state after 1, 10, 35 layers, the 271 x 25055 logits after 70, and the ids.  (Before
+    the scalar-tail exp was made libm-exact, 1-ulp differences in 7 of the 271 softmax columns were enough to flip quantiser codes
+    from layer ~20 on and put this path on the same floor as the tensor-core one -- which is what shows the floor is the network's.)"""
     import json
     import os
     blob = build_blob(SenseVoiceConfig(), seed=1234)
@@ -346,16 +347,16 @@ def test_full_size_simt_attention_vs_oracle():
         nl = lambda d: -1 if d == 70 else d
         gpu = {d: m.forward(feats, 3, 0, n_layers=nl(d)) for d in PARITY_DEPTHS}
         rows = _drift_rows(lambda d, j: gpu[d][j], lambda d, j: ref.forward(feats[j], 3, 0, n_layers=nl(d)), 2)
-        floor = {r["layers"]: r for r in _oracle_self_sensitivity(ref, feats)}
         os.makedirs("gpurun_out", exist_ok=True)
         with open(os.path.join("gpurun_out", "parity_full_size_simt.json"), "w") as fh:
-            json.dump({"gpu_simt_vs_oracle": rows, "oracle_vs_its_one_ulp_twin": list(floor.values())}, fh, indent=1)
+            json.dump({"gpu_simt_vs_oracle": rows}, fh, indent=1)
         print("PARITY_SIMT", json.dumps(rows))
-        for row in rows:
-            if row["layers"] >= 10:
-                assert max(row["rel_mean"]) <= 1.5 * max(floor[row["layers"]]["rel_mean"]), row
-        assert max(rows[0]["rel_mean"]) < 1e-3
+        for d in PARITY_DEPTHS:
+            for j in range(2):
+                np.testing.assert_array_equal(gpu[d][j], ref.forward(feats[j], 3, 0, n_layers=nl(d)), err_msg=f"depth {d} clip {j}")
         got, ids = m.forward(feats, 3, 0, want_ids=True)
         np.testing.assert_array_equal(ids, _last_argmax(got))       # the fused arg-max epilogue is the last-max arg-max of the logits it writes
+        for j in range(2):
+            np.testing.assert_array_equal(ids[j], _last_argmax(ref.forward(feats[j], 3, 0)))
     finally:
         m.close()

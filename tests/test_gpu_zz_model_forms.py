@@ -51,7 +51,7 @@ def test_statement_forms_lockstep(case):
     got = MR.run_program(prog, blob, x if isinstance(x, list) else [x], ops)
     for a, b in zip(got, direct(MR, blob, x)):
         np.testing.assert_array_equal(a, b)           # the carried values are the oracle's
-    assert len(ops.calls) >= {"math": 10, "recurrent": 3, "quant": 8, "shape": 6, "const": 10, "convint": 3}[case]
+    assert len(ops.calls) >= {"math": 10, "recurrent": 3, "quant": 8, "shape": 6, "const": 10, "convint": 1}[case]
 
 
 def test_streaming_vad_on_device():
