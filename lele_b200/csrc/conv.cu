@@ -144,6 +144,16 @@ __global__ void conv_transpose_kernel(const float* __restrict__ x, const float* 
 }
 }  // namespace
 
+namespace {
+__global__ void pad_rows_kernel(const float* __restrict__ w, int rows, int k, int kpad, float* __restrict__ out) {
+    const long long total = (long long)rows * kpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % kpad); const long long r = i / kpad;
+        out[i] = c < k ? w[r * k + c] : 0.0f;
+    }
+}
+}  // namespace
+
 extern "C" int lele_b200_conv1d(lele_b200_ctx* ctx, const float* x, const float* w, const float* bias, int nb, int ic, int l,
                                 int oc, int k, int group, int pad_l, int pad_r, int stride, int dilation, int relu, float* out) {
     LB_REQUIRE(ctx && x && w && out, "conv1d: NULL argument");
@@ -188,6 +198,25 @@ extern "C" int lele_b200_conv2d(lele_b200_ctx* ctx, const float* x, const float*
         } else {
             rc = lb_sgemm_strided(ctx, w, ic, 1, 0, x, hw, 1, (long long)ic * hw, out, nb, oc, ic, (int)hw, 1.0f, 0);
             if (rc) return rc;
+        }
+    } else if (!tc_ok && group == 1 && kdim % 4 != 0 && oc >= 16 && hw >= 64 && kdim >= 16 && hw * kdim * oc >= (1ll << 22)) {
+        // K = IC*kh*kw not a multiple of 4 (a 3-channel stem: 27): the weight rows are re-pitched to the next multiple of 4 (zeros) so TMA can
+        // address them; the im2col producers treat k >= K as padding (k_valid) -- the layer then runs on the tensor cores like the others
+        const int kpad = (int)((kdim + 3) / 4 * 4);
+        void* sc;
+        if ((rc = lb_scratch(ctx, sizeof(float) * (size_t)oc * kpad + 256, &sc))) return rc;   // (scratch2 may hold conv_integer's staged operands)
+        float* wp = (float*)sc;
+        pad_rows_kernel<<<grid_for((long long)oc * kpad), 256, 0, ctx->stream>>>(w, oc, (int)kdim, kpad, wp);
+        LB_LAUNCH_CHECK(ctx);
+        if (lb_gemm_tc_supported(wp, kpad, 0, wp, kpad, 0, oc, (int)hw, kpad)) {
+            LbGatherB gb; memset(&gb, 0, sizeof(gb));
+            gb.mode = 2; gb.ptr = x; gb.bs = (long long)ic * h * wd; gb.h = h; gb.w = wd; gb.kh = kh; gb.kw = kw; gb.pt = g.pt; gb.pl = g.pl;
+            gb.sh = g.sh; gb.sw = g.sw; gb.dh = g.dh; gb.dw = g.dw; gb.ow = g.ow; gb.k_valid = (int)kdim;
+            if ((rc = lb_gemm_tf32x3_gather(ctx, wp, kpad, 0, gb, out, hw, (long long)oc * hw, nb, oc, (int)hw, kpad, tep))) return rc;
+            fused_epilogue = true;
+        } else {
+            conv2d_direct_kernel<<<grid_for((long long)nb * oc * hw), 256, 0, ctx->stream>>>(x, w, nb, g, out);
+            LB_LAUNCH_CHECK(ctx);
         }
     } else if (tc_ok) {
         // implicit GEMM on the tensor cores: out[b] = W[OC,K] . im2col(x[b])[HW,K]^T with the im2col element computed on the

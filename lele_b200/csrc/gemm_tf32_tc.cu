@@ -210,29 +210,35 @@ gemm_tf32x3_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const float* gsrc = gb.ptr + (long long)b * gb.bs;
         int iy0 = 0, ix0 = 0;
         if (GATHER == 2) { const int oy = p / gb.ow, ox = p - oy * gb.ow; iy0 = oy * gb.sh - gb.pt; ix0 = ox * gb.sw - gb.pl; }
+        // The gathered operand is software-pipelined one k-chunk ahead: the 16 global loads of chunk kc+1 are issued before chunk kc
+        // is converted and handed to the MMA warp, so a load round trip (the im2col reads miss L1 on every new input row) is hidden
+        // behind one chunk of conversion + barrier traffic instead of being paid per chunk by the 8 converter warps.
+        auto gather = [&](int kc, float (&g)[16]) {
+            // the loads do not depend on the TMA: (the stage itself is written only after full[s], which the producer arms only
+            // once the MMAs that read the stage's previous contents have retired)
+            const int k0 = kc * KC + kg * 16;
+            if (GATHER == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) g[j] = (p_ok && k0 + j < args.K) ? __ldg(gsrc + (long long)(k0 + j) * gb.ldk + p) : 0.0f;
+            } else {
+                const int khw = gb.kh * gb.kw;
+                const int kmax = gb.k_valid > 0 ? gb.k_valid : args.K;      // (K padded to a multiple of 4 for the weight's TMA pitch: the pad reads nothing)
+                int c = k0 / khw; int rem = k0 - c * khw; int ky = rem / gb.kw; int kx = rem - ky * gb.kw;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int iy = iy0 + ky * gb.dh, ix = ix0 + kx * gb.dw;
+                    const bool ok = p_ok && k0 + j < kmax && iy >= 0 && iy < gb.h && ix >= 0 && ix < gb.w;
+                    g[j] = ok ? __ldg(gsrc + ((long long)c * gb.h + iy) * gb.w + ix) : 0.0f;
+                    if (++kx == gb.kw) { kx = 0; if (++ky == gb.kh) { ky = 0; ++c; } }
+                }
+            }
+        };
+        float g[16], gn[16];
+        if (GATHER) gather(0, g);
         for (int kc = 0; kc < NK; ++kc) {
             const int s = kc % NSTAGE; const uint32_t ph = (uint32_t)(kc / NSTAGE) & 1u;
             const uint32_t st = smem_u32(smem + s * STAGE);
-            float g[16];
-            if (GATHER) {
-                // the loads do not depend on the TMA: issue them first (the stage itself is written only after full[s], which
-                // the producer arms only once the MMAs that read the stage's previous contents have retired)
-                const int k0 = kc * KC + kg * 16;
-                if (GATHER == 1) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) g[j] = (p_ok && k0 + j < args.K) ? __ldg(gsrc + (long long)(k0 + j) * gb.ldk + p) : 0.0f;
-                } else {
-                    const int khw = gb.kh * gb.kw;
-                    int c = k0 / khw; int rem = k0 - c * khw; int ky = rem / gb.kw; int kx = rem - ky * gb.kw;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int iy = iy0 + ky * gb.dh, ix = ix0 + kx * gb.dw;
-                        const bool ok = p_ok && k0 + j < args.K && iy >= 0 && iy < gb.h && ix >= 0 && ix < gb.w;
-                        g[j] = ok ? __ldg(gsrc + ((long long)c * gb.h + iy) * gb.w + ix) : 0.0f;
-                        if (++kx == gb.kw) { kx = 0; if (++ky == gb.kh) { ky = 0; ++c; } }
-                    }
-                }
-            }
+            if (GATHER && kc + 1 < NK) gather(kc + 1, gn);
             mbar_wait(&full[s], ph);
 #pragma unroll
             for (int i = t256; i < TILE_A / 16; i += 256) lo_convert_16B(st + (uint32_t)i * 16u, st + (uint32_t)TILE_A + (uint32_t)i * 16u);
@@ -253,6 +259,10 @@ gemm_tf32x3_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&conv[s]);
+            if (GATHER) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) g[j] = gn[j];
+            }
         }
         if (warp < 8) {
             // ---- epilogue: warp = TMEM lane quadrant; thread = row, 4 chunks of 32 columns ----

@@ -15,6 +15,7 @@ struct LbGatherB {
     const float* ptr;
     long long ldk, bs;   // bs = batch stride in floats (0 = shared)
     int h, w, kh, kw, pt, pl, sh, sw, dh, dw, ow;   // mode 2: n = oy*ow + ox, k = (c*kh + ky)*kw + kx
+    int k_valid;         // mode 2: true IC*kh*kw when the GEMM's K was padded up to a multiple of 4 (0 = K is the true size)
 };
 // TMA-addressable operands: 16-byte aligned bases, pitches and batch strides multiples of 4 floats, k >= 4
 bool lb_gemm_tc_supported(const float* A, long long lda, long long bsa, const float* B, long long ldb, long long bsb, int m, int n, int k);

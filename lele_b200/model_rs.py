@@ -503,7 +503,95 @@ def _host_i64_op(op, a):
     return None                                       # reshape / unsqueeze / squeeze / flatten / identity keep the dtype below
 
 
-def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, workspace=None, download=True):
+def _item_view(t, i, B):
+    """Item i of a folded value: the i-th [1, ...] slice of a contiguous [B, ...] DeviceTensor (zero-copy)."""
+    from .kernels import DeviceTensor
+    per = t.size // B
+    return DeviceTensor(t.ptr + i * per * t.dtype.itemsize, (1,) + tuple(t.shape[1:]), t.ctx, t, t.dtype, t.slot)
+
+
+_LIFT_UNARY = {"sigmoid", "silu", "relu", "tanh_kernel", "erf", "exp", "sqrt", "neg", "reciprocal", "softplus", "log", "sin", "cos", "clip", "identity"}
+_LIFT_BINARY = {"add", "sub", "mul", "div", "max", "pow", "prelu", "mod_f32"}
+_LIFT_NCHW = {"conv2d", "conv2d_silu", "conv2d_fused", "conv_transpose", "max_pool2d", "resize_nearest", "batch_norm"}
+
+
+def _liftable(st, a, lifted, env, B):
+    """Can this statement run ONCE on folded operands ([B, ...] standing for B independent [1, ...] values)?
+    -> None: no (the folded replay stops here); False: it has no folded operand (run it as it is); else the statement to execute
+    (the original, or a copy whose reshape target has its leading 1 replaced by B).  Conservative: anything not listed stops."""
+    if st["op"] == "if":
+        return None
+    def names(x):
+        if isinstance(x, dict):
+            if "var" in x: return [x["var"]]
+            if "vars" in x: return list(x["vars"])
+            if "items" in x: return [n for it in x["items"] for n in names(it)]
+            if "i64vec" in x: return [x["i64vec"]]
+            if "i64vec_of" in x: return names(x["i64vec_of"])
+        return []
+    arg_names = [names(x) for x in st["args"]]
+    used = [n for ns in arg_names for n in ns]
+    if not any(n in lifted for n in used):
+        return False
+    op = st["op"]
+    folded = lambda k: any(n in lifted for n in arg_names[k])
+    rank = lambda k: len(a[k].shape)
+    norm = lambda ax, r: ax + r if ax < 0 else ax
+    try:
+        if op in _LIFT_NCHW:
+            return st if folded(0) and not any(folded(k) for k in range(1, len(a))) and rank(0) >= 3 else None
+        if op in _LIFT_UNARY:
+            return st if not any(folded(k) for k in range(1, len(a))) else None
+        if op in _LIFT_BINARY:
+            r = max(len(np.shape(v)) if not _is_dev(v) else len(v.shape) for v in a[:2])
+            for k in (0, 1):
+                if folded(k) and rank(k) != r: return None                      # a folded operand must carry the leading (batch) dim of the result
+                if not folded(k) and len(np.shape(a[k]) if not _is_dev(a[k]) else a[k].shape) == r and (np.shape(a[k]) if not _is_dev(a[k]) else a[k].shape)[0] != 1: return None
+            return st
+        if op == "concat":
+            if not all(n in lifted for n in arg_names[0]): return None
+            return st if norm(a[1], len(a[0][0].shape)) != 0 else None
+        if op == "split_take":
+            return st if folded(0) and norm(a[1], rank(0)) != 0 else None
+        if op == "reshape":
+            tgt = list(a[1])
+            if not folded(0) or not tgt or tgt[0] not in (0, 1) or a[0].shape[0] != B: return None
+            return dict(st, args=[st["args"][0], {"list": [B] + tgt[1:]}])
+        if op == "flatten":
+            return st if folded(0) and a[1] == 1 else None
+        if op == "unsqueeze":
+            r_out = rank(0) + len(a[1])
+            return st if folded(0) and all(norm(int(x), r_out) != 0 for x in a[1]) else None
+        if op == "squeeze":
+            return st if folded(0) and a[1] is not None and all(norm(int(x), rank(0)) != 0 for x in a[1]) else None
+        if op == "transpose":
+            perm = list(a[1]) if len(a[1]) else list(reversed(range(rank(0))))
+            return st if folded(0) and perm[0] == 0 else None
+        if op == "matmul":
+            if not folded(0) or rank(0) < 3: return None
+            if folded(1): return st if rank(1) == rank(0) else None
+            return st if len(np.shape(a[1])) == 2 else None
+        if op == "softmax":
+            return st if folded(0) and rank(0) >= 2 and norm(a[1], rank(0)) != 0 else None
+        if op == "layer_norm":
+            return st if folded(0) and not folded(1) and not folded(2) and norm(a[3], rank(0)) != 0 else None
+        if op == "slice":
+            axes = list(a[3]) if a[3] else list(range(len(a[1])))
+            return st if folded(0) and all(norm(int(x), rank(0)) != 0 for x in axes) else None
+        if op == "topk":
+            return st if folded(0) and rank(0) >= 2 else None
+        if op in ("reduce_max", "reduce_sum", "reduce_mean", "reduce_l2"):
+            return st if folded(0) and len(a[1]) > 0 and all(norm(int(x), rank(0)) != 0 for x in a[1]) else None
+        if op == "tile":
+            return st if folded(0) and len(a[1]) == rank(0) and int(a[1][0]) == 1 else None
+        if op == "gather_elements":
+            return st if folded(0) and folded(1) and norm(a[2], rank(0)) != 0 else None
+    except Exception:
+        return None
+    return None
+
+
+def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, workspace=None, download=True, env0=None, lift=None, items=None):
     """Replays the statement list.  `blob` = the model's weights.bin bytes, `inputs` = arrays in `program["inputs"]` order.
     `ops`: CudaOps (default) or any module with the shared operator vocabulary.  Returns the outputs as numpy arrays.
     `cache`: a dict the caller keeps across calls of one model -- decoded weight views and, where the namespace offers
@@ -513,7 +601,15 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, w
     HBM.  Inputs are uploaded once, every statement's outputs are placed in the workspace buffer the generated code names
     (`&mut ws.buf_N` -> `lele_b200_arena_bind`; values the generated code owns -- split_owned pieces, intermediates of composed
     statements -- get a buffer keyed by their statement), weights are uploaded once per model, and nothing returns to the host
-    except where the generated code itself reads `.data` and, with `download`, the graph outputs (`.to_owned()`, generate.rs:748)."""
+    except where the generated code itself reads `.data` and, with `download`, the graph outputs (`.to_owned()`, generate.rs:748).
+    `lift` = B (resident replay only): the BATCH-FOLDED replay.  Generated code bakes batch 1 into its shapes, but almost every
+    statement of a vision graph is independent along the leading dimension, so B inputs stacked as [B, ...] run through the SAME
+    statement as one launch (the convolutions see nb = B: one implicit GEMM over the whole batch) -- a value whose logical shape is
+    [1, ...] is carried as [B, ...].  A statement is folded only if `_liftable` can prove it independent per leading index (reshape
+    targets get their leading 1 replaced by B); at the first top-level statement that is not (the detection tail: flatten to a
+    row-major list, gather on axis 0 ...) the folded values are sliced per item (zero-copy views) and the remaining statements run
+    per item: `items` = [(ops_i, workspace_i)] -- item i's operator namespace (its lane) and its own workspace.  Returns one output
+    list per item.  `env0`: a ready environment (internal: the per-item tail)."""
     if ops is None:
         ops = CudaOps()
     elif not hasattr(ops, "binary"):
@@ -522,8 +618,11 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, w
     if resident and not isinstance(ops, CudaOps):
         raise ValueError("run_program: a workspace (resident replay) needs the CUDA operator namespace")
     rctx = workspace.ctx if resident else None
-    env = {}
-    for n, a in zip(program["inputs"], inputs):
+    if lift is not None and not resident:
+        raise ValueError("run_program: the batch-folded replay (lift) needs a workspace")
+    env = dict(env0) if env0 is not None else {}
+    lifted = set(program["inputs"]) if lift is not None else set()     # names of values carried as [B, ...] for logical [1, ...]
+    for n, a in zip(program["inputs"], inputs if env0 is None else []):
         if _is_dev(a):
             env[n] = a
         elif np.asarray(a).dtype.kind in "iu":
@@ -531,7 +630,7 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, w
         else:
             env[n] = rctx.to_device(np.asarray(a, np.float32)) if resident else _c(a, np.float32)
     split_cache = {}
-    stmt_no = [0]
+    stmt_no = [0 if env0 is None else 100000]         # (a per-item tail never shares statement-keyed buffer names with the folded prefix)
 
     def val(a):
         if isinstance(a, dict):
@@ -720,11 +819,49 @@ def run_program(program: dict, blob, inputs, ops=None, trace=None, cache=None, w
         if trace is not None:
             trace.append((st["outs"][0], op, env[st["outs"][0]]))
 
-    exec_block(program["statements"])
-    if resident:
-        rctx.out_slots([])
-    outs = [env[n] for n in program["outputs"]]
-    return [_host(o) for o in outs] if download else outs
+    if lift is None:
+        exec_block(program["statements"])
+        if resident:
+            rctx.out_slots([])
+        outs = [env[n] for n in program["outputs"]]
+        return [_host(o) for o in outs] if download else outs
+
+    # ---- batch-folded replay ----
+    B, stmts, cut = int(lift), program["statements"], None
+    folded_statements = 0
+    for idx, st in enumerate(stmts):
+        patched = _liftable(st, [val(x) for x in st["args"]] if st["op"] != "if" else None, lifted, env, B)
+        if patched is None:
+            cut = idx
+            break
+        if patched is False:                          # no folded operand: an ordinary (shared) statement
+            exec_statement(st)
+            continue
+        exec_statement(patched)
+        folded_statements += 1
+        lifted.update(n for n in st["outs"] if n != "_" and _is_dev(env.get(n)))
+    rctx.out_slots([])
+    per_item = []
+    if cut is None:
+        cut = len(stmts)
+    program.setdefault("_fold_report", {})[B] = {"folded_statements": folded_statements, "first_per_item_statement": cut, "statements": len(stmts),
+                                                 "stopped_at": None if cut == len(stmts) else stmts[cut]["op"]}
+    tail = dict(program, statements=stmts[cut:], inputs=[])
+    lanes = []
+    for ops_i, ws_i in (items or []):
+        if ws_i.ctx is not rctx and ws_i.ctx not in lanes:
+            lanes.append(ws_i.ctx)
+    for c in lanes:
+        rctx.fork(c)                                  # the per-item tails start when the folded prefix is done
+    for i in range(B):
+        ops_i, ws_i = items[i] if items else (ops, workspace)
+        env_i = {n: (_item_view(v, i, B) if n in lifted and _is_dev(v) else v) for n, v in env.items()}
+        per_item.append(run_program(tail, blob, [], ops_i, cache=cache, workspace=ws_i, download=False, env0=env_i))
+    for c in lanes:
+        rctx.join(c)
+    if download:
+        per_item = [[_host(o) for o in outs] for outs in per_item]
+    return per_item
 
 
 def synth_blob(program: dict, seed: int = 7, constants=None) -> bytes:
@@ -826,8 +963,8 @@ class GeneratedModel:
 
     __call__ = forward
 
-    def batch_runner(self, n_items: int, lanes: int = 8, ctx=None, graph: bool = True):
-        return BatchRunner(self, n_items, lanes, ctx, graph)
+    def batch_runner(self, n_items: int, lanes: int = 8, ctx=None, graph: bool = True, fold: bool = False):
+        return BatchRunner(self, n_items, lanes, ctx, graph, fold)
 
 
 class BatchRunner:
@@ -839,21 +976,27 @@ class BatchRunner:
     step -- every item, every lane -- into one CUDA graph (`lele_b200_capture_begin/_end`, lanes joined by `stream_fork/_join`)
     and every later `run` is: H2D of the inputs, one graph launch, D2H of the outputs."""
 
-    def __init__(self, model: GeneratedModel, n_items: int, lanes: int = 8, ctx=None, graph: bool = True):
+    def __init__(self, model: GeneratedModel, n_items: int, lanes: int = 8, ctx=None, graph: bool = True, fold: bool = False):
         from . import kernels as K
         self.K, self.model, self.n = K, model, int(n_items)
+        self.fold = bool(fold)      # batch-folded replay (run_program lift=): the statements that are independent along the leading dimension
+                                    # run ONCE on the stacked [n_items, ...] values; only the tail that is not runs per item on the lanes
         origin = ctx or K.default_context()
         self.lanes = [origin] + [K.Context(origin.device) for _ in range(max(1, min(int(lanes), self.n)) - 1)]
         for c in self.lanes[1:]:
             c._consts, c._keep = origin._consts, origin._keep          # one device copy of the weights for every lane
         self.ops = [CudaOps(c) for c in self.lanes]
         self.ws = [K.Workspace(self.lanes[i % len(self.lanes)]) for i in range(self.n)]
+        self.ws_folded = K.Workspace(origin) if self.fold else None
         self.use_graph, self.graph, self.runs = graph, None, 0
         self.inputs_dev, self.outs_dev = None, None
 
     def _enqueue(self):
         L = len(self.lanes)
         origin = self.lanes[0]
+        if self.fold:
+            return run_program(self.model.program, self.model.weights, self.inputs_dev, self.ops[0], cache=self.model._cache,
+                               workspace=self.ws_folded, download=False, lift=self.n, items=[(self.ops[i % L], self.ws[i]) for i in range(self.n)])
         for c in self.lanes[1:]:
             origin.fork(c)
         outs = []
@@ -870,10 +1013,30 @@ class BatchRunner:
         K, origin = self.K, self.lanes[0]
         if len(items) != self.n:
             raise ValueError(f"BatchRunner: {len(items)} items given, built for {self.n}")
+        from ._lib import call, sz, vp
+        if self.fold:                                                      # one stacked [n_items, ...] device tensor per program input
+            if self.inputs_dev is None:
+                self.inputs_dev = []
+                for k in range(len(items[0])):
+                    first = np.asarray(items[0][k])
+                    if first.dtype.kind != "f":
+                        self.inputs_dev.append(np.asarray(first, np.int64)); continue
+                    if first.shape[0] != 1:
+                        raise ValueError("BatchRunner(fold=True): every float input needs a leading dimension of 1 (the folded batch axis)")
+                    self.inputs_dev.append(origin.to_device(np.zeros((self.n,) + first.shape[1:], np.float32)))
+            for k, d in enumerate(self.inputs_dev):
+                if not _is_dev(d):
+                    continue
+                per = d.nbytes // self.n
+                for i, it in enumerate(items):
+                    a = np.ascontiguousarray(it[k], np.float32)
+                    if a.nbytes != per:
+                        raise ValueError("BatchRunner: input shapes are fixed after the first run (the captured graph bakes them)")
+                    call("lele_b200_h2d", origin.h, vp(d.ptr + i * per), a.ctypes.data_as(vp), sz(per))
+            return
         if self.inputs_dev is None:
             self.inputs_dev = [[origin.to_device(np.asarray(a, np.float32)) if np.asarray(a).dtype.kind == "f" else np.asarray(a, np.int64) for a in it] for it in items]
             return
-        from ._lib import call, sz, vp
         for it, devs in zip(items, self.inputs_dev):
             for a, d in zip(it, devs):
                 if _is_dev(d):
@@ -943,7 +1106,7 @@ class BatchRunner:
         if self.graph is not None:
             self.graph.close(); self.graph = None
         self.lanes[0].sync()
-        for w in self.ws:
+        for w in self.ws + ([self.ws_folded] if self.ws_folded is not None else []):
             w.release()
         for c in self.lanes[1:]:
             c._consts, c._keep = {}, []

@@ -1079,3 +1079,37 @@ def test_config1_silero_shaped_vad_on_the_reference_fixture():
     assert len(np.unique(probs)) > 10                                   # the recurrent state makes every chunk's answer its own
     segs = merge_segments(collect_segments(probs, audio.size))
     assert all(0 <= s < e <= audio.size for s, e in segs)
+
+
+def test_batch_folded_replay_runs_the_independent_prefix_once(fake_dev):
+    """run_program(lift=B) / BatchRunner(fold=True): statements that are independent along the leading dimension run ONCE on the
+    stacked [B, ...] values (reshape targets get their leading 1 replaced by B); the first statement that is not stops the folding
+    and the rest runs per item on zero-copy slices.  Same results as B separate replays."""
+    MR, prog, blob, xs, want = _resident_case()
+    dev = fake_dev
+    model = MR.GeneratedModel(prog, blob, resident=True)
+    br = model.batch_runner(3, lanes=2, fold=True)
+    for rnd in range(3):
+        dev.log.clear()
+        got = br.run([[x] for x in xs])
+        for it, w in zip(got, want):
+            for g, ww in zip(it, w):
+                np.testing.assert_allclose(g, ww, rtol=1e-6, atol=1e-6)
+        if rnd == 0:
+            assert dev.log.count("lele_b200_conv2d") == 1 and dev.log.count("lele_b200_max_pool2d") == 1      # one launch for the whole batch
+    rep = prog["_fold_report"][3]
+    assert rep["first_per_item_statement"] == rep["statements"] and rep["stopped_at"] is None              # this graph folds completely
+    br.close()
+    # a statement that is not independent along the leading dimension ends the folded prefix: flatten(axis=2) moves the batch inward
+    text = RESIDENT_TEXT.replace("let g = lele::kernels::transpose(&f, &[0, 2, 1], &mut ws.buf_0);",
+                                 "let f2 = lele::kernels::flatten(&f, 2);\n        let g = lele::kernels::transpose(&f2, &[1, 0], &mut ws.buf_0);")
+    prog2 = MR.parse_model_rs(text)
+    from oracle import reference_api as R
+    want2 = [MR.run_program(prog2, blob, [x], R) for x in xs]
+    br2 = MR.GeneratedModel(prog2, blob, resident=True).batch_runner(3, lanes=2, fold=True)
+    got2 = br2.run([[x] for x in xs])
+    for it, w in zip(got2, want2):
+        for g, ww in zip(it, w):
+            np.testing.assert_allclose(g, ww, rtol=1e-6, atol=1e-6)
+    assert prog2["_fold_report"][3]["stopped_at"] == "flatten" and prog2["_fold_report"][3]["folded_statements"] >= 8
+    br2.close()

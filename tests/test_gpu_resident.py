@@ -167,6 +167,31 @@ def test_batch_runner_graph_replay_matches_single_forwards():
         br.close()
 
 
+def test_batch_folded_yolo_replay_matches_single_forwards():
+    """Config 5's execution form: the 337-statement graph with the batch folded into the statements that allow it (every
+    convolution sees nb = B: one implicit GEMM per layer for the whole batch) and the detection tail per item.  3 images, 2 lanes,
+    eager / captured / replayed rounds: each image's outputs are those of its own single resident forward."""
+    prog, blob = _yolo_case()
+    rng = np.random.default_rng(10)
+    xs = [rng.random((1, 3, 640, 640), dtype=np.float32) for _ in range(3)]
+    single = MR.GeneratedModel(prog, blob, resident=True)
+    want = [single.forward(x) for x in xs]
+    br = MR.GeneratedModel(prog, blob, resident=True).batch_runner(3, lanes=2, fold=True)
+    try:
+        for rnd in range(3):
+            got = br.run([[x] for x in xs])
+            for it, w in zip(got, want):
+                close(it[1], w[1], rtol=1e-5, atol_frac=1e-6)                  # prototype masks [1, 32, 160, 160]
+                key = lambda r: (int(r[5]), tuple(np.round(r[:4], 1)))           # detections: same set (near-equal scores may reorder)
+                kg, kw = {key(r) for r in it[0][0]}, {key(r) for r in w[0][0]}
+                assert len(kg & kw) >= 0.97 * len(kw)
+        rep = prog["_fold_report"][3]
+        assert rep["folded_statements"] >= 300 and rep["stopped_at"] is not None, rep     # the backbone, neck and heads fold; the top-k tail does not
+        assert br.graph is not None
+    finally:
+        br.close()
+
+
 def test_conv_integer_entry_matches_the_pad_shift_convolve_composition():
     """lele_b200_conv_integer (conv2d.rs:2216): padded cells hold raw zeros, i.e. contribute (0 - x_zp)(w - w_zp)."""
     rng = np.random.default_rng(3)
@@ -248,3 +273,19 @@ def test_config1_vad_on_the_reference_fixture_on_device():
     np.testing.assert_allclose(gpu.state, cpu.state, rtol=2e-3, atol=2e-3)
     seg = lambda p: merge_segments(collect_segments(p, audio.size))
     assert seg(p_gpu) == seg(p_cpu)
+
+
+@pytest.mark.parametrize("outer,n,k", [(1, 24000, 300), (32, 8400, 300), (3, 1000, 1000), (2, 70000, 2048), (5, 300, 7)])
+def test_topk_long_rows_select_and_sort(outer, n, k):
+    """conv2d.rs:1385: stable descending sort, ties keep the lower index; the long-row kernel (radix select + ordered tie compaction +
+    bitonic sort) against the oracle, on rows full of ties (values drawn from 50 levels), with +-0.0 and -inf present."""
+    rng = np.random.default_rng(outer * 7 + k)
+    x = rng.integers(0, 50, (outer, n)).astype(np.float32) / np.float32(7.0) - np.float32(3.0)
+    x[0, ::97] = 0.0; x[0, 5::97] = -0.0; x[-1, 3] = -np.inf; x[-1, 11] = np.inf
+    v, i = K.topk(x, k)
+    rv, ri = R.topk(x, k)
+    np.testing.assert_array_equal(i, ri)
+    np.testing.assert_array_equal(v.view(np.uint32), rv.view(np.uint32))         # the original values, bit for bit (a -0.0 stays -0.0)
+    y = rng.standard_normal((outer, n)).astype(np.float32)                       # distinct values
+    v, i = K.topk(y, k); rv, ri = R.topk(y, k)
+    np.testing.assert_array_equal(i, ri); np.testing.assert_array_equal(v, rv)
