@@ -246,7 +246,9 @@ __device__ __forceinline__ float lb_cephes_expf(float x) {
 // (tests/test_gpu_sensevoice.py::test_full_size_simt_attention_is_bit_identical).
 __device__ __forceinline__ float lb_libm_expf(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float lb_sigmoid_simd(float x) {  // avx/math.rs:69
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, lb_cephes_expf(-x)));
+    // 1 / d with a correctly rounded reciprocal: by IEEE-754 the same bits as the division _mm256_div_ps(1, d) performs, at a
+    // third of the instructions of the general __fdiv_rn sequence (this sits in the conv / LSTM epilogues, once per element)
+    return __frcp_rn(__fadd_rn(1.0f, lb_cephes_expf(-x)));
 }
 __device__ __forceinline__ float lb_tanh_simd(float x) {  // avx/math.rs:81-97
     float e = lb_cephes_expf(__fmul_rn(-x, 2.0f));

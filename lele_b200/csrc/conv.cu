@@ -144,6 +144,11 @@ __global__ void conv_transpose_kernel(const float* __restrict__ x, const float* 
 }
 }  // namespace
 
+bool lb_conv2d_tc_pixel_supported(const float* w, long long w_pitch, int oc, long long kdim);
+int lb_conv_transpose_tc_scatter(lele_b200_ctx* ctx, const float* x, const float* wt, const float* bias, int nb, int ic, int h, int wd, int oc,
+                                 int kh, int kw, int sh, int sw, float* out);
+int lb_conv2d_tc_pixel(lele_b200_ctx* ctx, const float* x, const float* w, long long w_pitch, int k_valid, const float* bias, int nb, int ic, int h,
+                       int wd, int oc, int kh, int kw, int pt, int pl, int sh, int sw, int dh, int dw, int oh, int ow, int act, float* out);
 namespace {
 __global__ void pad_rows_kernel(const float* __restrict__ w, int rows, int k, int kpad, float* __restrict__ out) {
     const long long total = (long long)rows * kpad;
@@ -188,6 +193,22 @@ extern "C" int lele_b200_conv2d(lele_b200_ctx* ctx, const float* x, const float*
     const long long kdim = (long long)ic * kh * kw;
     const bool tc_ok = group == 1 && kdim % 4 == 0 && oc >= 16 && hw >= 64 && kdim >= 16 && hw * kdim * oc >= (1ll << 22) &&
                        lb_gemm_tc_supported(w, kdim, 0, w, kdim, 0, oc, (int)hw, (int)kdim);
+    // Pixel-major implicit GEMM (conv_tc.cu): pixels = the tensor core's M (full 128-row tiles whatever OC is), OC = its N; persistent,
+    // epilogue overlapped with the next tile.  Takes every group-1 layer with 8 <= OC <= 256 and enough work, 1x1 included.
+    if (group == 1 && oc >= 8 && oc <= 256 && kdim >= 8 && (long long)nb * hw >= 128 && (long long)nb * hw * kdim * oc >= (1ll << 22) &&
+        g.dh >= 1 && g.dw >= 1) {
+        const float* wp = w; long long pitch = kdim;
+        if (kdim % 4 != 0) {          // K = IC*kh*kw not a multiple of 4 (a 3-channel stem: 27): rows re-pitched (zeros) so TMA can address them
+            pitch = (kdim + 3) / 4 * 4;
+            void* sc;
+            if ((rc = lb_scratch(ctx, sizeof(float) * (size_t)oc * pitch + 256, &sc))) return rc;
+            pad_rows_kernel<<<grid_for((long long)oc * pitch), 256, 0, ctx->stream>>>(w, oc, (int)kdim, (int)pitch, (float*)sc);
+            LB_LAUNCH_CHECK(ctx);
+            wp = (const float*)sc;
+        }
+        if (lb_conv2d_tc_pixel_supported(wp, pitch, oc, kdim))
+            return lb_conv2d_tc_pixel(ctx, x, wp, pitch, (int)kdim, bias, nb, ic, h, wd, oc, kh, kw, g.pt, g.pl, g.sh, g.sw, g.dh, g.dw, g.oh, g.ow, act, out);
+    }
     if (group == 1 && kh == 1 && kw == 1 && g.sh == 1 && g.sw == 1 && pads[0] == 0 && pads[1] == 0 && pads[2] == 0 && pads[3] == 0) {
         // 1x1: out[b] = W[OC,IC] x X[b][IC,HW]
         if (tc_ok) {   // tensor cores: the kernel gathers X[b] [IC, HW] as its N-major B operand; bias + activation fused in the epilogue
@@ -295,6 +316,16 @@ extern "C" int lele_b200_conv_transpose(lele_b200_ctx* ctx, const float* x, cons
     long long total = (long long)nb * oc * oh * ow;
     if (total == 0) return LELE_B200_OK;
     const long long hw = (long long)h * wd; const int mk = oc * kh * kw;
+    if (kh == strides[0] && kw == strides[1] && pads[0] == 0 && pads[1] == 0 && pads[2] == 0 && pads[3] == 0 && dils[0] == 1 && dils[1] == 1 &&
+        ic % 4 == 0 && ic >= 8 && mk >= 8 && mk <= 256 && (long long)nb * hw >= 128 && (long long)nb * hw * ic * mk >= (1ll << 22)) {
+        // kernel == stride: non-overlapping taps, every output written once -> one pixel-major GEMM with the scatter in its epilogue
+        void* sc; int rc;
+        if ((rc = lb_scratch(ctx, sizeof(float) * (size_t)mk * ic + 256, &sc))) return rc;
+        float* wt = (float*)sc;
+        if ((rc = lb_transpose_f32(ctx, w, mk, 0, wt, ic, 0, 1, ic, mk))) return rc;       // W [ic, oc*kh*kw] -> [oc*kh*kw, ic]
+        if (lb_conv2d_tc_pixel_supported(wt, ic, mk, ic))
+            return lb_conv_transpose_tc_scatter(ctx, x, wt, bias, nb, ic, h, wd, oc, kh, kw, strides[0], strides[1], out);
+    }
     if (ic % 4 == 0 && ic >= 16 && mk >= 16 && hw >= 64 && hw * ic * mk >= (1ll << 22) && lb_gemm_tc_supported(x, ic, 0, x, ic, 0, mk, (int)hw, ic)) {
         // the reference's own structure (conv2d.rs:3069-3128): col = W^T X as a GEMM -- here on the tensor cores -- then the
         // scatter-add, done as a gather per output element in the same tap order
