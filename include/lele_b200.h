@@ -48,6 +48,9 @@ int lele_b200_sync(lele_b200_ctx* ctx);
 unsigned long long lele_b200_launch_count(const lele_b200_ctx* ctx);
 int lele_b200_malloc(lele_b200_ctx* ctx, size_t nbytes, void** dptr);
 int lele_b200_free(lele_b200_ctx* ctx, void* dptr);
+/* page-locked host buffers for asynchronous, full-rate h2d / d2h */
+int lele_b200_malloc_host(lele_b200_ctx* ctx, size_t nbytes, void** hptr);
+int lele_b200_free_host(lele_b200_ctx* ctx, void* hptr);
 int lele_b200_memset(lele_b200_ctx* ctx, void* dptr, int value, size_t nbytes);
 int lele_b200_h2d(lele_b200_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);
 int lele_b200_d2h(lele_b200_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes);

@@ -119,6 +119,24 @@ extern "C" int lele_b200_free(lele_b200_ctx* ctx, void* dptr) {
     }
     return LELE_B200_OK;
 }
+// page-locked host memory: what a host hands to h2d / d2h when the copies are to run asynchronously at PCIe rate (a pageable buffer is
+// staged by the driver at a fraction of it)
+extern "C" int lele_b200_malloc_host(lele_b200_ctx* ctx, size_t nbytes, void** hptr) {
+    LB_REQUIRE(ctx && hptr, "malloc_host: NULL argument");
+    LB_ENTER(ctx);
+    LB_CHECK_CUDA(cudaMallocHost(hptr, nbytes ? nbytes : 16));
+    return LELE_B200_OK;
+}
+extern "C" int lele_b200_free_host(lele_b200_ctx* ctx, void* hptr) {
+    LB_REQUIRE(ctx, "free_host: NULL ctx");
+    LB_ENTER(ctx);
+    if (hptr) {
+        if (lb_stream_capturing(ctx)) { lb_set_error("free_host: the context's stream is being captured"); return LELE_B200_ERR_ARG; }
+        LB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+        LB_CHECK_CUDA(cudaFreeHost(hptr));
+    }
+    return LELE_B200_OK;
+}
 extern "C" int lele_b200_memset(lele_b200_ctx* ctx, void* dptr, int value, size_t nbytes) {
     LB_REQUIRE(ctx, "memset: NULL ctx");
     LB_ENTER(ctx);

@@ -134,6 +134,7 @@ class Context:
         self._slots: list = []          # output placements for the next resident call(s): (Workspace, name) pairs, consumed in order
         self._consts: dict = {}         # host operands of resident calls, uploaded once: key -> DeviceTensor
         self._keep: list = []           # host arrays whose address is a _consts key (kept alive so the address stays theirs)
+        self._pinned: list = []         # page-locked host allocations handed out by pinned_empty
 
     # -- memory --
     def upload(self, a: np.ndarray, dtype=np.float32) -> DevBuf:
@@ -204,6 +205,16 @@ class Context:
         n = _b.max(_prod(shape), 1) * np.dtype(dtype).itemsize
         return DeviceTensor(0, shape, self, None, dtype)._own(DevBuf(self, n))
 
+    def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """A numpy array over page-locked host memory (lele_b200_malloc_host), freed with the context: the destination of d2h / source
+        of h2d copies that should run asynchronously at PCIe rate."""
+        n = _b.max(_prod(shape) * np.dtype(dtype).itemsize, 16)
+        p = vp()
+        call("lele_b200_malloc_host", self.h, sz(n), C.byref(p))
+        self._pinned.append(p.value)
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=_prod(shape)).reshape(shape)
+
     def sync(self):
         call("lele_b200_sync", self.h)
 
@@ -230,6 +241,9 @@ class Context:
     def close(self):
         if self.h:
             self._consts.clear(); self._keep.clear()
+            for p in self._pinned:
+                lib.lele_b200_free_host(self.h, vp(p))
+            self._pinned = []
             lib.lele_b200_ctx_destroy(self.h)
             self.h = None
 

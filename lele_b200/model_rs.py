@@ -988,6 +988,7 @@ class BatchRunner:
         self.ops = [CudaOps(c) for c in self.lanes]
         self.ws = [K.Workspace(self.lanes[i % len(self.lanes)]) for i in range(self.n)]
         self.ws_folded = K.Workspace(origin) if self.fold else None
+        self._host_out = {}
         self.use_graph, self.graph, self.runs = graph, None, 0
         self.inputs_dev, self.outs_dev = None, None
 
@@ -1080,11 +1081,13 @@ class BatchRunner:
         from ._lib import call, sz, vp
         origin = self.lanes[0]
         res = []
-        for outs in self.outs_dev:
+        for i, outs in enumerate(self.outs_dev):
             row = []
-            for o in outs:
+            for k, o in enumerate(outs):
                 if _is_dev(o):
-                    h = np.empty(o.shape, dtype=o.dtype)
+                    h = self._host_out.get((i, k))
+                    if h is None or h.shape != tuple(o.shape):          # page-locked, allocated once: the copies run at PCIe rate
+                        h = self._host_out[(i, k)] = origin.pinned_empty(o.shape, o.dtype)
                     if h.nbytes:
                         call("lele_b200_d2h", origin.h, h.ctypes.data_as(vp), vp(o.ptr), sz(h.nbytes))
                     row.append(h)
@@ -1092,7 +1095,7 @@ class BatchRunner:
                     row.append(o)
             res.append(row)
         origin.sync()
-        return res
+        return res                                                       # (views of the runner's page-locked buffers: valid until the next collect)
 
     def run(self, items):
         self.upload(items)

@@ -49,7 +49,7 @@ class FakeDevice:
         fn = getattr(self, "e_" + name[len("lele_b200_"):], None)
         if fn is None:
             raise NotImplementedError(f"fake device: {name} is not emulated")
-        if self.capturing and name not in ("lele_b200_capture_end", "lele_b200_arena_bind", "lele_b200_stream_fork", "lele_b200_stream_join"):
+        if self.capturing and name not in ("lele_b200_capture_end", "lele_b200_arena_bind", "lele_b200_stream_fork", "lele_b200_stream_join", "lele_b200_malloc_host"):
             if name in ("lele_b200_sync", "lele_b200_d2h", "lele_b200_free"):
                 raise RuntimeError(f"fake device: {name} during graph capture (would invalidate a real capture)")
             self.captured.append((fn, args))
@@ -67,6 +67,12 @@ class FakeDevice:
         out._obj.value = self._alloc(_v(nbytes))
 
     def e_free(self, ctx, p):
+        self.mem.pop(_v(p), None)
+
+    def e_malloc_host(self, ctx, nbytes, out):
+        out._obj.value = self._alloc(_v(nbytes))
+
+    def e_free_host(self, ctx, p):
         self.mem.pop(_v(p), None)
 
     def e_h2d(self, ctx, dst, src, n):
@@ -167,6 +173,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_lib, "call", call)
     monkeypatch.setattr(kernels, "call", call)
     monkeypatch.setattr(kernels, "_default", None)
-    fake_lib = type("FakeLib", (), {"lele_b200_launch_count": staticmethod(lambda h: 0), "lele_b200_ctx_destroy": staticmethod(lambda h: 0)})()
+    fake_lib = type("FakeLib", (), {"lele_b200_launch_count": staticmethod(lambda h: 0), "lele_b200_ctx_destroy": staticmethod(lambda h: 0),
+                                    "lele_b200_free_host": staticmethod(lambda h, p: 0)})()
     monkeypatch.setattr(kernels, "lib", fake_lib)
     return dev
