@@ -38,19 +38,8 @@ constexpr int EPI_TILE_BYTES = 32 * 128;                       // per-warp 32x32
 constexpr int EPI_META_BYTES = 3 * 64 * 4;                     // zp*colsum / scale / bias of the warp's 64 columns
 constexpr int EPI_BYTES = NUM_EPI_WARPS * (EPI_TILE_BYTES + EPI_META_BYTES);
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-// RESB ("resident B") variant, K <= 4 k-blocks (K <= 512) and an epilogue that needs <= 1 KB of staging per warp (the
-// fused output quantiser, the max-only pass): a CTA keeps ONE n-block for its whole life, loads that 256 x K weight
-// tile once (128 KB stays in shared memory) and streams only A (16 KB per k-block, 4-stage ring = one full tile of
-// look-ahead): 64 KB instead of 192 KB of operand traffic per tile.  MEASURED (B200, FFN1 passes, M=17600): no gain
-// (37.3 vs 35.6 us) -- these GEMMs are bound by the epilogue (per-tile ~5.3 k cycles vs ~3.4 k for the MMAs), not by
-// the L2 -> SM operand fabric.  Kept as an opt-in (LELE_B200_GEMM_RESB=1) since it is bit-identical and tested.
-constexpr int RES_KB = 4;                                      // resident k-blocks of B
-constexpr int RES_A_STAGES = 4;
-constexpr int RES_EPI_TILE_BYTES = 1024;
-constexpr int RES_EPI_BYTES = NUM_EPI_WARPS * (RES_EPI_TILE_BYTES + EPI_META_BYTES);
-constexpr int RES_SMEM_BYTES = RES_KB * B_STAGE_BYTES + RES_A_STAGES * A_STAGE_BYTES + RES_EPI_BYTES + 1024 + 256;
-static_assert(SMEM_BYTES <= 232448 && RES_SMEM_BYTES <= 232448, "shared memory budget");
-constexpr int MAX_STAGES = STAGES > RES_A_STAGES ? STAGES : RES_A_STAGES;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+constexpr int MAX_STAGES = STAGES;
 #ifdef LELE_B200_GEMM_TIMELINE
 constexpr bool GEMM_DBG = true;    // role wait counters (clock64) printed by CTAs 0 / 77 when LELE_B200_GEMM_DBG=1; costs ~12 registers
 #else
@@ -114,11 +103,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor: D=S32 (c_format 2 @4), A=U8 (0 @7), B=U8 (0 @10), K-major both,
-// N>>3 @17, M>>4 @24
-constexpr uint32_t IDESC = (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D=S32 (c_format 2 @4), A=U8 (0 @7), B=U8 (0 @10) or S8 (1 @10: the weight stored as w - 128),
+// K-major both, N>>3 @17, M>>4 @24
+constexpr uint32_t idesc_for(bool b_signed) {
+    return (2u << 4) | (0u << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t IDESC) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -188,7 +179,8 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // RELU (compile-time; PLAIN / MINMAX / QUANT only): the per-element epilogue is bound by the half-rate ALU pipe (IADD3,
 // I2FP, FMNMX ...), so a ReLU that is not asked for -- or is implied (QUANT: unsigned saturation; MINMAX: max(relu(t)) =
 // max(max t, 0), min(relu(t)) >= 0) -- must not cost an FMNMX per element.
-template <int MODE, bool TMA_OUT, bool RELU, bool RESB>
+// WSIGNED: the weight operand is s8 (w - 128, prepare_weights with w_zp == 128): no per-row zero-point term in the epilogue.
+template <int MODE, bool TMA_OUT, bool RELU, bool WSIGNED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_lo, const KernelArgs args) {
@@ -197,30 +189,26 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (GEMM_DBG && args.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;   // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem = smem_raw + pad;
-    constexpr int NST = RESB ? RES_A_STAGES : STAGES;                      // A (RESB) or A+B (ring) stages
-    constexpr int ETB = RESB ? RES_EPI_TILE_BYTES : EPI_TILE_BYTES;
+    constexpr int NST = STAGES;
+    constexpr int ETB = EPI_TILE_BYTES;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + NST * A_STAGE_BYTES;                          // RESB: the RES_KB resident k-block tiles of B
-    uint8_t* epi_base = smem_b + (RESB ? RES_KB : STAGES) * B_STAGE_BYTES; // per-warp staging tiles, then column metadata
-    uint64_t* bars = (uint64_t*)(epi_base + (RESB ? RES_EPI_BYTES : EPI_BYTES));
+    uint8_t* smem_b = smem + NST * A_STAGE_BYTES;
+    uint8_t* epi_base = smem_b + STAGES * B_STAGE_BYTES;                   // per-warp staging tiles, then column metadata
+    uint64_t* bars = (uint64_t*)(epi_base + EPI_BYTES);
     uint64_t* full_bar = bars;                     // [NST]  TMA -> MMA
     uint64_t* empty_bar = bars + MAX_STAGES;       // [NST]  MMA -> TMA
     uint64_t* tmem_full = bars + 2 * MAX_STAGES;   // [2]    MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;          // [2]    epilogue -> MMA
-    uint64_t* b_full = tmem_empty + 2;             // RESB: the resident weight tile landed
-    uint32_t* tmem_base_smem = (uint32_t*)(b_full + 1);
+    uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = args.num_m_blocks * args.num_n_blocks;
-    // tile walk (both variants): tile = blockIdx.x + i * gridDim.x -> (m_blk, n_blk) = (tile / nnb, tile % nnb).
-    // RESB: the host launches gridDim.x as a multiple of nnb, so n_blk = blockIdx.x % nnb is the same for every tile of
-    // the CTA (its resident weight tile) and the CTA walks m-blocks blockIdx.x / nnb + i * gridDim.x / nnb.
+    // tile walk: tile = blockIdx.x + i * gridDim.x -> (m_blk, n_blk) = (tile / nnb, tile % nnb)
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
-        mbar_init(b_full, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -241,20 +229,14 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             long long w_empty = 0; const long long t_begin = clock64();
-            if (RESB && (int)blockIdx.x < num_tiles) {             // the CTA's weight tile: loaded once, resident
-                const int n_blk = (int)blockIdx.x % args.num_n_blocks;
-                mbar_expect_tx(b_full, (uint32_t)args.num_k_blocks * B_STAGE_BYTES);
-                for (int kb = 0; kb < args.num_k_blocks; ++kb)
-                    tma_load_2d(smem_b + kb * B_STAGE_BYTES, &tmap_b, b_full, kb * BK, n_blk * BN);
-            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
                 for (int kb = 0; kb < args.num_k_blocks; ++kb) {
                     if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t0; }
                     else mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], RESB ? A_STAGE_BYTES : STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    if (!RESB) tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
@@ -267,7 +249,6 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             long long w_tmem = 0, w_full = 0; const long long t_begin = clock64();
-            if (RESB && (int)blockIdx.x < num_tiles) { mbar_wait(b_full, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t0; }
                 else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
@@ -278,12 +259,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     else mbar_wait(&full_bar[stage], phase);            // TMA bytes landed
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (RESB ? kb : stage) * B_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance along K inside the 128B swizzle atom: +32 B == +2 in the (>>4) address field
                         umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
-                                (kb > 0 || k > 0) ? 1u : 0u);
+                                (kb > 0 || k > 0) ? 1u : 0u, idesc_for(WSIGNED));
                     }
                     umma_commit(&empty_bar[stage]);                // frees the smem slot when the MMAs retire
                     if (kb == args.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
@@ -331,7 +312,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 pf_qkey = __ldg(ep.q_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
             }
             pf_rs = 0; pf_zpa = 0; pf_sa = 0.0f;
-            if (rw < M) { pf_rs = __ldg(ep.rowsum + rw); pf_zpa = __ldg(ep.row_zp + rw); pf_sa = __ldg(ep.row_scale + rw); }
+            if (rw < M) { if (!WSIGNED) pf_rs = __ldg(ep.rowsum + rw); pf_zpa = __ldg(ep.row_zp + rw); pf_sa = __ldg(ep.row_scale + rw); }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int cc = min(nb * BN + cgrp * 64 + hh * 32 + lane, N - 1);
@@ -347,7 +328,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // this tile's row / column metadata was fetched while the previous tile drained (pf_*), so no global-load
             // latency sits between two accumulators
             const int rs = pf_rs, zpa = pf_zpa; const float sa = pf_sa;
-            const int row_corr = args.K * zpa * ep.w_zp - ep.w_zp * rs;
+            const int row_corr = WSIGNED ? 0 : args.K * zpa * ep.w_zp - ep.w_zp * rs;   // s8 weights carry their zero point: no row term
             // Per-warp column metadata, pre-combined with the activation parameters of the clip that owns the warp's
             // first row ("A"): zcA[c] = zp_A * colsum[c], csA[c] = scale_A * w_scale[c].  A warp's 32 rows touch a
             // second clip only at clip boundaries (1 warp in ~8 for T' = 271); those rows take the uncombined path.
@@ -445,7 +426,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int idx = q * 4 + e;
-                            const int iv = (int)r[idx] + row_corr - (STRADDLE ? zpa * zc[e] : zc[e]);
+                            const int iv = (WSIGNED ? (int)r[idx] : (int)r[idx] + row_corr) - (STRADDLE ? zpa * zc[e] : zc[e]);
                             float t = __fmul_rn((float)iv, STRADDLE ? __fmul_rn(sa, cs[e]) : cs[e]);
                             t = ep.has_bias ? __fadd_rn(t, bi[e]) : t;
                             const bool col_ok = FULL || gcol0 + idx < N;
@@ -628,6 +609,346 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
 }
 
+
+// =====================================================================================================================
+// Fused "linear -> ReLU -> dynamic quantiser" (SenseVoice FFN1): ONE pass over the GEMM.
+//
+// The reference's dynamic quantiser needs the per-clip min / max of the whole [T, N] output before it can quantise the
+// first element (avx/quantization.rs:112-140), so round 1 ran this GEMM twice (a max-only pass, then a quantising pass:
+// 2.3 ms of every 23 ms step spent on MMAs whose results were thrown away).  Here the accumulators WAIT IN TMEM instead:
+//   * the rows are walked in GROUPS of G whole clips; a group is one wave of the persistent grid (CTA = one 128-row block
+//     x one 256-column block of the group, the same (m, n) block in every group), so a CTA's i-th tile belongs to group i;
+//   * max pass  me(g): tcgen05.ld the finished accumulator, dequantise (exact integer correction, scale, bias), reduce
+//     the per-clip min / max (warp REDUX -> shared-memory atomics -> one pair of global atomics per CTA and clip), write
+//     the dequantised f32 values BACK into the same TMEM columns (tcgen05.st), then arrive on the clip's counter;
+//   * quantising pass qe(g): once the counters of the warp's clips show every contributing CTA (acquire load), derive
+//     (scale, zp) from the keys, tcgen05.ld the f32 values, quantise, TMA-store the u8 tile (the next GEMM's A operand)
+//     and hand the accumulator stage back to the MMA warp.
+//   The 16 epilogue warps run  me(0) me(1) qe(0) qe(1) me(2) me(3) ...  over the two TMEM stages, so the wait for the other
+//   CTAs' maxima is covered by the next group's max pass and the MMAs of group g+2 run under qe(g+1) / me(g+2).
+// Requires every CTA of the grid to be co-resident (grid <= #SMs, 1 CTA per SM by shared memory): the host refuses shapes
+// that do not fit and the runner uses it only when nothing else shares the device (one lane).  Spins are bounded (trap).
+// =====================================================================================================================
+constexpr int FQ_TILE_BYTES = 1024;                            // per-warp 32 x 32 u8 staging tile
+constexpr int FQ_META_BYTES = 5 * 64 * 4;                      // zcA | csA | zcB | csB | bias of the warp's 64 columns
+constexpr int FQ_MAX_SLOTS = BM / 32 + 1;                      // clips a 128-row tile can touch (T >= 32)
+constexpr int FQ_EPI_BYTES = NUM_EPI_WARPS * (FQ_TILE_BYTES + FQ_META_BYTES);
+constexpr int FQ_SMEM_BYTES = STAGES * STAGE_BYTES + FQ_EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers, CTA key slots*/;
+static_assert(FQ_SMEM_BYTES <= 232448, "shared memory budget (fused quantiser)");
+
+struct FusedArgs {
+    int M, N, K;
+    int nnb, nkb;
+    int T; float inv_T;   // rows per clip
+    int GT;               // rows per group (G clips)
+    int n_groups, n_clips;
+    LbI8Epilogue ep;
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
+
+template <bool RELU>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const __grid_constant__ CUtensorMap tmap_out, const FusedArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* epi_base = smem_b + STAGES * B_STAGE_BYTES;           // 16 staging tiles, then 16 metadata blocks
+    uint64_t* bars = (uint64_t*)(epi_base + FQ_EPI_BYTES);
+    uint64_t* full_bar = bars;                     // [STAGES] TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;           // [STAGES] MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * STAGES;       // [2]      MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]      epilogue (quantising pass) -> MMA
+    uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+    unsigned* cta_keys = (unsigned*)(tmem_base_smem + 2);          // [2 parities][FQ_MAX_SLOTS][min, max]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nnb = args.nnb;
+    const int mb = (int)blockIdx.x / nnb, nb = (int)blockIdx.x % nnb;     // the CTA's block of every group
+    const int M = args.M, GT = args.GT;
+    // groups in which this CTA's m-block has rows: all but possibly the last (shorter) one
+    const int last_rows = M - (args.n_groups - 1) * GT;
+    const int n_act = (mb * BM < last_rows) ? args.n_groups : args.n_groups - 1;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
+        for (int i = 0; i < 2 * FQ_MAX_SLOTS; ++i) { cta_keys[2 * i] = LB_KEY_MIN_INIT; cta_keys[2 * i + 1] = LB_KEY_MAX_INIT; }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    lb_pdl_launch_dependents();
+    lb_pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int g = 0; g < n_act; ++g) {
+                const int row0 = g * GT + mb * BM;
+                for (int kb = 0; kb < args.nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, row0);
+                    tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, nb * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int g = 0; g < n_act; ++g) {
+                const int acc = g & 1; const uint32_t acc_phase = (uint32_t)(g >> 1) & 1u;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);            // the quantising pass of group g - 2 drained this stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < args.nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
+                                (kb > 0 || k > 0) ? 1u : 0u, idesc_for(true));
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == args.nkb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: 16 warps, each owns 32 rows x 64 columns of the CTA's block =====================
+        const int ew = warp - FIRST_EPI_WARP;
+        const int quad = warp & 3;
+        const int cgrp = ew >> 2;
+        const LbI8Epilogue& ep = args.ep;
+        const uint32_t tile_s = smem_u32(epi_base) + (uint32_t)ew * FQ_TILE_BYTES;
+        const uint32_t meta_s = smem_u32(epi_base) + NUM_EPI_WARPS * FQ_TILE_BYTES + (uint32_t)ew * FQ_META_BYTES;
+        const int T = args.T; const float inv_T = args.inv_T;
+        const int N = args.N;
+        const int gcol_w = nb * BN + cgrp * 64;
+        const bool cols_ok = gcol_w < N;                               // N % 64 == 0 (host): a warp's columns exist or not
+        const float FMAX = 3.402823466e+38f;
+        // column metadata: the CTA keeps its n-block, so the warp's 64 columns are the same in every group
+        int cs_raw[2]; float ws_raw[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int cc = min(gcol_w + hh * 32 + lane, N - 1);
+            cs_raw[hh] = __ldg(ep.colsum + cc); ws_raw[hh] = __ldg(ep.w_scale + cc);
+            sts_f32(meta_s + 1024 + 4 * (hh * 32 + lane), __ldg(ep.bias + cc));
+        }
+        struct Geo { int first_row, nrows, sl_a, clip0, gend, g0; bool row_ok, in_a, all_a; };
+        auto geometry = [&](int g) {
+            Geo q;
+            q.g0 = g * GT; q.gend = min(q.g0 + GT, M);
+            const int tile_r0 = q.g0 + mb * BM;
+            q.first_row = tile_r0 + quad * 32;
+            q.nrows = max(0, min(32, q.gend - q.first_row));
+            q.row_ok = lane < q.nrows;
+            q.clip0 = div_by_rps(tile_r0, T, inv_T);
+            q.sl_a = div_by_rps(min(q.first_row, q.gend - 1), T, inv_T);
+            q.in_a = q.first_row + lane < (q.sl_a + 1) * T;
+            q.all_a = __all_sync(0xffffffffu, !q.row_ok || q.in_a);
+            return q;
+        };
+
+        // ---- max pass of group g ----
+        auto max_pass = [&](int g) {
+            const int s = g & 1; const uint32_t ph = (uint32_t)(g >> 1) & 1u;
+            const Geo q = geometry(g);
+            int zpa = 0; float sa = 0.0f;
+            if (q.row_ok) { zpa = __ldg(ep.row_zp + q.first_row + lane); sa = __ldg(ep.row_scale + q.first_row + lane); }
+            const int lastl = max(q.nrows - 1, 0);
+            const int zpa_a = __shfl_sync(0xffffffffu, zpa, 0), zpa_b = __shfl_sync(0xffffffffu, zpa, lastl);
+            const float sa_a = __shfl_sync(0xffffffffu, sa, 0), sa_b = __shfl_sync(0xffffffffu, sa, lastl);
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {                       // tables combined with the clip's activation parameters
+                const int c = hh * 32 + lane;
+                sts_s32(meta_s + 4 * c, zpa_a * cs_raw[hh]);
+                sts_f32(meta_s + 256 + 4 * c, __fmul_rn(sa_a, ws_raw[hh]));
+                sts_s32(meta_s + 512 + 4 * c, zpa_b * cs_raw[hh]);   // rows past a clip boundary read the second table
+                sts_f32(meta_s + 768 + 4 * c, __fmul_rn(sa_b, ws_raw[hh]));
+            }
+            __syncwarp();
+            const uint32_t my_meta = meta_s + (q.in_a ? 0u : 512u);
+            float vmax = -FMAX, vmin = FMAX;
+            if (q.nrows > 0 && cols_ok) {
+                mbar_wait(&tmem_full[s], ph);
+                tc_fence_after();
+#pragma unroll 1
+                for (int chunk = 0; chunk < 2; ++chunk) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * BN + cgrp * 64 + chunk * 32);
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr, r);
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        const int4 zc4 = lds_v4(my_meta + 16 * (chunk * 8 + qq));
+                        const int4 cs4 = lds_v4(my_meta + 256 + 16 * (chunk * 8 + qq));
+                        const int4 bi4 = lds_v4(meta_s + 1024 + 16 * (chunk * 8 + qq));
+                        const int zc[4] = {zc4.x, zc4.y, zc4.z, zc4.w};
+                        const float cs[4] = {__int_as_float(cs4.x), __int_as_float(cs4.y), __int_as_float(cs4.z), __int_as_float(cs4.w)};
+                        const float bi[4] = {__int_as_float(bi4.x), __int_as_float(bi4.y), __int_as_float(bi4.z), __int_as_float(bi4.w)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int idx = qq * 4 + e;
+                            float t = __fmul_rn((float)((int)r[idx] - zc[e]), cs[e]);
+                            t = ep.has_bias ? __fadd_rn(t, bi[e]) : t;
+                            vmax = fmaxf(vmax, t);
+                            if (!RELU) vmin = fminf(vmin, t);
+                            r[idx] = __float_as_uint(t);
+                        }
+                    }
+                    tmem_st_32x32b_x32(taddr, r);                  // the dequantised values wait in TMEM for the clip's scale
+                }
+                tmem_st_wait();
+                if (RELU) { vmin = 0.0f; vmax = fmaxf(vmax, 0.0f); }     // min / max of the ReLU output
+                const unsigned kmin = lb_fkey(vmin), kmax = lb_fkey(vmax);
+                unsigned* slot = cta_keys + ((size_t)(g & 1) * FQ_MAX_SLOTS + (q.sl_a - q.clip0)) * 2;
+                const bool a_ok = q.row_ok && q.in_a;
+                const unsigned mnA = __reduce_min_sync(0xffffffffu, a_ok ? kmin : LB_KEY_MIN_INIT), mxA = __reduce_max_sync(0xffffffffu, a_ok ? kmax : LB_KEY_MAX_INIT);
+                if (lane == 0) { atomicMin(slot, mnA); atomicMax(slot + 1, mxA); }
+                if (!q.all_a) {
+                    const bool b_ok = q.row_ok && !q.in_a;
+                    const unsigned mnB = __reduce_min_sync(0xffffffffu, b_ok ? kmin : LB_KEY_MIN_INIT), mxB = __reduce_max_sync(0xffffffffu, b_ok ? kmax : LB_KEY_MAX_INIT);
+                    if (lane == 0) { atomicMin(slot + 2, mnB); atomicMax(slot + 3, mxB); }
+                }
+            }
+            epi_bar_sync();                                        // every warp's keys are in the CTA slots
+            if (ew == 0 && lane < FQ_MAX_SLOTS) {
+                const int tile_r0 = q.g0 + mb * BM, tile_end = min(tile_r0 + BM, q.gend);
+                const int clip = q.clip0 + lane;
+                if (tile_r0 < tile_end && clip * T < tile_end) {   // the block has rows of this clip: publish, then arrive
+                    unsigned* slot = cta_keys + ((size_t)(g & 1) * FQ_MAX_SLOTS + lane) * 2;
+                    const unsigned mn = slot[0], mx = slot[1];
+                    slot[0] = LB_KEY_MIN_INIT; slot[1] = LB_KEY_MAX_INIT;
+                    lb_mm_update_keys(ep.fq_keys, clip, mn, mx);
+                    __threadfence();
+                    atomicAdd(ep.fq_counters + clip, 1);
+                }
+            }
+        };
+
+        // ---- quantising pass of group g ----
+        auto quant_pass = [&](int g) {
+            const int s = g & 1;
+            const Geo q = geometry(g);
+            float q_inv = 0.0f, q_zp = 0.0f, q_scale = 0.0f;
+            if (q.nrows > 0 && cols_ok) {
+                if (lane == 0) {
+                    // every CTA whose block has rows of the clip arrives once: nnb column blocks x the m-blocks the clip spans
+                    for (int cl = q.sl_a; cl <= q.sl_a + (q.all_a ? 0 : 1); ++cl) {
+                        const int a = max(cl * T, q.g0) - q.g0, b = min((cl + 1) * T, q.gend) - q.g0;
+                        const int expect = (((b - 1) >> 7) - (a >> 7) + 1) * nnb;
+                        if (ld_acquire_gpu(ep.fq_counters + cl) < expect) {
+                            const long long t0 = clock64();
+                            while (ld_acquire_gpu(ep.fq_counters + cl) < expect) {
+                                __nanosleep(64);
+                                if (clock64() - t0 > 4000000000ll) { printf("lele_b200 gemm_i8 fused quantiser: clip %d never completed (block %d)\n", cl, blockIdx.x); __trap(); }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                // lanes 0-15 hold the 8 (min, max) key slots of clip A, lanes 16-31 those of clip A+1
+                const int sl = min(q.sl_a + (lane >> 4), args.n_clips - 1);
+                unsigned k = __ldcg(ep.fq_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
+#pragma unroll
+                for (int of = 2; of <= 8; of <<= 1) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, k, of);
+                    k = (lane & 1) ? max(k, o) : min(k, o);
+                }
+                const int src = q.in_a ? 0 : 16;
+                const float mn = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src)), mx = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src + 1));
+                const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);          // dq_params (quant.cu)
+                q_scale = __fdiv_rn(fmaxf(__fsub_rn(amax, amin), 1e-5f), 255.0f);
+                q_zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, q_scale)), 0.0f), 255.0f);
+                q_inv = __fdiv_rn(1.0f, q_scale);
+#pragma unroll 1
+                for (int chunk = 0; chunk < 2; ++chunk) {
+                    const int gcol0 = gcol_w + chunk * 32;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * BN + cgrp * 64 + chunk * 32);
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr, r);
+                    unsigned pk[8];
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        const unsigned u0 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[qq * 4 + 0]), q_inv, q_zp));
+                        const unsigned u1 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[qq * 4 + 1]), q_inv, q_zp));
+                        const unsigned u2 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[qq * 4 + 2]), q_inv, q_zp));
+                        const unsigned u3 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[qq * 4 + 3]), q_inv, q_zp));
+                        pk[qq] = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
+                    }
+                    if (q.nrows == 32) {
+                        if (lane == 0) tma_store_wait_read();      // the previous store has read the staging tile
+                        __syncwarp();
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, q.first_row);
+                    } else if (q.row_ok) {                         // last rows of a group: the rows below belong to the next group
+                        uint4* dst = reinterpret_cast<uint4*>(ep.q_out + (size_t)(q.first_row + lane) * N + gcol0);
+                        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[s]);            // the MMA warp may overwrite this accumulator stage
+            if (q.row_ok && nb == 0 && cgrp == 0) { ep.q_row_scale[q.first_row + lane] = q_scale; ep.q_row_zp[q.first_row + lane] = (int)q_zp; }
+        };
+
+        for (int p = 0; p < n_act; p += 2) {                       // me(p) me(p+1) qe(p) qe(p+1): one copy of each pass in the instruction cache
+            const int pe = min(p + 2, n_act);
+#pragma unroll 1
+            for (int g = p; g < pe; ++g) max_pass(g);
+#pragma unroll 1
+            for (int g = p; g < pe; ++g) quant_pass(g);
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -710,6 +1031,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     LB_REQUIRE((((uintptr_t)A | (uintptr_t)Wt) & 15) == 0, "gemm_i8_tc: operands must be 16-byte aligned");
     LB_REQUIRE(!ep.minmax_keys || ep.rows_per_slice >= 32, "gemm_i8_tc: fused min/max needs rows_per_slice >= 32 (a warp's 32 rows may span at most two slices)");
     LB_REQUIRE(!ep.argmax_keys || (!ep.add1 && !ep.add2), "gemm_i8_tc: fused arg-max cannot be combined with residual adds");
+    LB_REQUIRE(!ep.w_signed || ep.w_zp == 128, "gemm_i8_tc: a signed weight operand implies zero point 128");
     CUtensorMap ta, tb;
     int rc = cached_tmap_u8(ctx, &ta, A, M, K, BM);
     if (rc) return rc;
@@ -766,40 +1088,71 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     if (mode == EPI_QKV) {
         LB_REQUIRE(tma_out, "gemm_i8_tc: fused attention-operand epilogue needs a 16-byte aligned output");
     }
-    // resident-B variant (see RES_* above): small-K GEMMs whose epilogue needs no f32 staging tile
-    const bool resb = (mode == EPI_QUANT || (mode == EPI_MINMAX && !ep.out)) && args.num_k_blocks <= RES_KB &&
-                      args.num_n_blocks <= ctx->num_sms && lb_env_flag("LELE_B200_GEMM_RESB", 0);
-    if (resb) {   // grid = G * nnb: every CTA keeps one n-block (tile walk in the kernel)
-        int G = ctx->num_sms / args.num_n_blocks;
-        if (G > args.num_m_blocks) G = args.num_m_blocks;
-        grid = G * args.num_n_blocks;
-    }
     // the shared-memory opt-in is recorded per context (= per device), once per instantiation
-#define LB_LAUNCH_MODE4(MD, TM, RL, RB)                                                                                 \
+#define LB_LAUNCH_MODE4(MD, TM, RL, WS)                                                                                 \
     {                                                                                                                   \
-        const int smem_bytes = RB ? RES_SMEM_BYTES : SMEM_BYTES;                                                        \
-        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_tc_kernel<MD, TM, RL, RB>, smem_bytes))) return rc;            \
-        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, ctx->stream, 1, ta, tb, tout, tlo, args)); \
+        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_tc_kernel<MD, TM, RL, WS>, SMEM_BYTES))) return rc;            \
+        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL, WS>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, ta, tb, tout, tlo, args)); \
     }
-#define LB_LAUNCH_MODE3(MD, TM, RL) LB_LAUNCH_MODE4(MD, TM, RL, false)
-#define LB_LAUNCH_RESB(MD, TM) { if (ep.relu) LB_LAUNCH_MODE4(MD, TM, true, true) else LB_LAUNCH_MODE4(MD, TM, false, true) }
+#define LB_LAUNCH_MODE3(MD, TM, RL) { if (ep.w_signed) LB_LAUNCH_MODE4(MD, TM, RL, true) else LB_LAUNCH_MODE4(MD, TM, RL, false) }
 #define LB_LAUNCH_MODE(MD, TM) LB_LAUNCH_MODE3(MD, TM, false)
 #define LB_LAUNCH_RELU(MD, TM) { if (ep.relu) LB_LAUNCH_MODE3(MD, TM, true) else LB_LAUNCH_MODE3(MD, TM, false) }
     switch (mode) {
         case EPI_PLAIN: if (tma_out) LB_LAUNCH_RELU(EPI_PLAIN, true) else LB_LAUNCH_RELU(EPI_PLAIN, false) break;
-        case EPI_MINMAX: if (resb) LB_LAUNCH_RESB(EPI_MINMAX, false) else if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
+        case EPI_MINMAX: if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
         case EPI_ARGMAX: LB_LAUNCH_MODE(EPI_ARGMAX, false) break;
         case EPI_R1: LB_LAUNCH_MODE(EPI_R1, false) break;
         case EPI_R2: LB_LAUNCH_MODE(EPI_R2, false) break;
         case EPI_R12: LB_LAUNCH_MODE(EPI_R12, false) break;
         case EPI_QKV: LB_LAUNCH_MODE(EPI_QKV, true) break;
-        case EPI_QUANT: if (resb) LB_LAUNCH_RESB(EPI_QUANT, true) else LB_LAUNCH_RELU(EPI_QUANT, true) break;
+        case EPI_QUANT: LB_LAUNCH_RELU(EPI_QUANT, true) break;
     }
 #undef LB_LAUNCH_MODE
 #undef LB_LAUNCH_MODE3
 #undef LB_LAUNCH_MODE4
-#undef LB_LAUNCH_RESB
 #undef LB_LAUNCH_RELU
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
+// The fused linear -> (ReLU) -> dynamic quantiser GEMM (gemm_i8_fused_q_kernel).  Needs the s8 weight operand, whole clips
+// of T >= 32 rows, N % 64 == 0 and a grid (one group of clips per wave) that fits the device.
+bool lb_gemm_i8_fused_q_supported(lele_b200_ctx* ctx, long long M, int N, int K, int T, int w_signed) {
+    if (!w_signed || T < 32 || M <= 0 || M % T != 0 || N % 64 != 0 || K % 16 != 0 || M >= (1 << 22)) return false;
+    const int nnb = lb_ceil_div(N, BN);
+    const int mb_fit = ctx->num_sms / nnb;                 // m-blocks of one group that fit the grid
+    return mb_fit >= 1 && (long long)mb_fit * BM >= T;     // at least one whole clip per group
+}
+int lb_gemm_i8_tc_fused_q(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep) {
+    const int T = ep.rows_per_slice;
+    LB_REQUIRE(lb_gemm_i8_fused_q_supported(ctx, M, N, K, T, ep.w_signed), "gemm_i8 fused quantiser: unsupported shape M=%d N=%d K=%d T=%d", M, N, K, T);
+    LB_REQUIRE(ep.q_out && ep.q_row_scale && ep.q_row_zp && ep.fq_keys && ep.fq_counters && (((uintptr_t)ep.q_out) & 15) == 0,
+               "gemm_i8 fused quantiser: q_out / q_row_scale / q_row_zp / fq_keys / fq_counters are required");
+    LB_REQUIRE((((uintptr_t)A | (uintptr_t)Wt) & 15) == 0, "gemm_i8 fused quantiser: operands must be 16-byte aligned");
+    CUtensorMap ta, tb, tout;
+    int rc = cached_tmap_u8(ctx, &ta, A, M, K, BM);
+    if (rc) return rc;
+    if ((rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN))) return rc;
+    if ((rc = cached_tmap_out_u8(ctx, &tout, ep.q_out, M, N))) return rc;
+    FusedArgs args;
+    args.M = M; args.N = N; args.K = K;
+    args.nnb = lb_ceil_div(N, BN); args.nkb = lb_ceil_div(K, BK);
+    args.T = T; args.inv_T = 1.0f / (float)T;
+    args.n_clips = M / T;
+    int G = (int)(((long long)(ctx->num_sms / args.nnb) * BM) / T);     // whole clips per group (= per wave of the grid)
+    if (G > args.n_clips) G = args.n_clips;
+    args.GT = G * T;
+    args.n_groups = lb_ceil_div(args.n_clips, G);
+    args.ep = ep;
+    const int grid = lb_ceil_div(args.GT, BM) * args.nnb;
+    LB_REQUIRE(grid <= ctx->num_sms, "gemm_i8 fused quantiser: grid %d exceeds the %d SMs (every CTA must be resident)", grid, ctx->num_sms);
+    if (ep.relu) {
+        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_fused_q_kernel<true>, FQ_SMEM_BYTES))) return rc;
+        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_fused_q_kernel<true>, dim3(grid), dim3(NUM_THREADS), FQ_SMEM_BYTES, ctx->stream, 1, ta, tb, tout, args));
+    } else {
+        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_fused_q_kernel<false>, FQ_SMEM_BYTES))) return rc;
+        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_fused_q_kernel<false>, dim3(grid), dim3(NUM_THREADS), FQ_SMEM_BYTES, ctx->stream, 1, ta, tb, tout, args));
+    }
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

@@ -13,6 +13,8 @@ struct LbI8Epilogue {
     const float* w_scale;      // per-channel weight scale (scalar scales are expanded)
     const float* bias;         // zeros when absent
     int w_zp;
+    int w_signed;              // Wt holds (w - 128) as s8 (prepare_weights does this when w_zp == 128): the tensor core multiplies u8 x s8,
+                               // colsum = sum_k (w - 128), and the row term w_zp * rowsum of the zero-point correction vanishes
     int has_bias;
     int relu;
     // optional fusions used by the SenseVoice runner (all NULL for the plain operator)
@@ -37,19 +39,27 @@ struct LbI8Epilogue {
     float* q_row_scale;
     int32_t* q_row_zp;
     const unsigned* q_keys;
+    // single-pass variant (lb_gemm_i8_tc_fused_q): the accumulators wait in TMEM for the clip's min / max instead of being
+    // recomputed; fq_keys = the output's per-clip key slots (initialised), fq_counters = [n_clips] zeroed arrival counters
+    unsigned* fq_keys;
+    int* fq_counters;
 };
 
 // A: u8 [M, K] row-major (K-major); Wt: u8 [N, K] row-major (K-major).  K % 16 == 0.
 int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K,
                   const LbI8Epilogue& ep);
 
+// one-pass linear -> (ReLU) -> dynamic quantiser: q_out / q_row_scale / q_row_zp + fq_keys / fq_counters; s8 weights only
+bool lb_gemm_i8_fused_q_supported(lele_b200_ctx* ctx, long long M, int N, int K, int T, int w_signed);
+int lb_gemm_i8_tc_fused_q(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep);
+
 // ---- shared between quant.cu and the graph runner (sensevoice.cu) ----
 struct lele_b200_qweights {
-    uint8_t* wt = nullptr;      // [n, k]  K-major copy of the u8 weight (lele's b_t, quantization.rs:206)
-    int32_t* colsum = nullptr;  // [n_pad]
+    uint8_t* wt = nullptr;      // [n, k]  K-major copy of the u8 weight (lele's b_t, quantization.rs:206); w ^ 0x80 (= s8 w - 128) when w_signed
+    int32_t* colsum = nullptr;  // [n_pad] sum_k w, or sum_k (w - 128) when w_signed
     float* w_scale = nullptr;   // [n_pad] (scalar scales expanded)
     float* bias = nullptr;      // [n_pad] zeros when absent
-    int k = 0, n = 0, n_pad = 0, w_zp = 0, has_bias = 0;
+    int k = 0, n = 0, n_pad = 0, w_zp = 0, has_bias = 0, w_signed = 0;
 };
 struct LbQuantScratch { uint8_t* a_u8; int32_t* rowsum; float* row_scale; int32_t* row_zp; };
 size_t lb_quant_scratch_bytes(long long M, int K);

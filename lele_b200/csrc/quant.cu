@@ -272,7 +272,8 @@ extern "C" int lele_b200_mat_mul_integer(lele_b200_ctx* ctx, const float* a, con
 // ---------------------------------------------------------------------------
 // prepare_weights: u8 [k,n] -> K-major [n,k] + column sums (+ padded per-column vectors)
 // ---------------------------------------------------------------------------
-__global__ void prep_weights_kernel(const uint8_t* __restrict__ w, int k, int n, uint8_t* __restrict__ wt, int32_t* __restrict__ colsum) {
+// `flip` = 0x80 stores w ^ 0x80, i.e. the s8 value w - 128 (the zero point 128 folded into the operand), and sums that
+__global__ void prep_weights_kernel(const uint8_t* __restrict__ w, int k, int n, uint8_t* __restrict__ wt, int32_t* __restrict__ colsum, int flip) {
     // 32x32 tile transpose through shared memory; column sums accumulated with atomics per tile
     __shared__ uint8_t tile[32][33];
     const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -284,11 +285,12 @@ __global__ void prep_weights_kernel(const uint8_t* __restrict__ w, int k, int n,
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         int j = n0 + r, kk = k0 + tx;
-        if (j < n && kk < k) wt[(long long)j * k + kk] = tile[tx][r];
+        if (j < n && kk < k) wt[(long long)j * k + kk] = (uint8_t)(tile[tx][r] ^ flip);
     }
     if (ty == 0) {
         int s = 0;
         for (int r = 0; r < 32; ++r) s += tile[r][tx];
+        if (flip) s -= 128 * min(32, k - k0);
         if (n0 + tx < n) atomicAdd(colsum + n0 + tx, s);
     }
 }
@@ -309,12 +311,15 @@ extern "C" int lele_b200_prepare_weights(lele_b200_ctx* ctx, const uint8_t* w, i
     LB_REQUIRE(w_zp >= 0 && w_zp <= 255, "prepare_weights: u8 zero point out of range (x86 handles u8 weights only, SURVEY appendix A)");
     lele_b200_qweights* q = new lele_b200_qweights();
     q->k = k; q->n = n; q->n_pad = (n + 255) / 256 * 256; q->w_zp = w_zp; q->has_bias = bias ? 1 : 0;
+    // zero point 128 (lele's u8 weights): keep w - 128 as s8 -- the tensor core takes u8 x s8, so the
+    // epilogue's zero-point correction loses its per-row term (w_zp * rowsum) and one integer add per output element
+    q->w_signed = (w_zp == 128 && !lb_env_flag("LELE_B200_W_UNSIGNED", 0)) ? 1 : 0;
     LB_CHECK_CUDA(cudaMalloc(&q->wt, (size_t)n * k));
     LB_CHECK_CUDA(cudaMalloc(&q->colsum, sizeof(int32_t) * q->n_pad));
     LB_CHECK_CUDA(cudaMalloc(&q->w_scale, sizeof(float) * q->n_pad));
     LB_CHECK_CUDA(cudaMalloc(&q->bias, sizeof(float) * q->n_pad));
     LB_CHECK_CUDA(cudaMemsetAsync(q->colsum, 0, sizeof(int32_t) * q->n_pad, ctx->stream));
-    prep_weights_kernel<<<dim3(lb_ceil_div(n, 32), lb_ceil_div(k, 32)), 256, 0, ctx->stream>>>(w, k, n, q->wt, q->colsum);
+    prep_weights_kernel<<<dim3(lb_ceil_div(n, 32), lb_ceil_div(k, 32)), 256, 0, ctx->stream>>>(w, k, n, q->wt, q->colsum, q->w_signed ? 0x80 : 0);
     LB_LAUNCH_CHECK(ctx);
     prep_vectors_kernel<<<lb_ceil_div(q->n_pad, 256), 256, 0, ctx->stream>>>(w_scale, w_scale_len, bias, n, q->n_pad, q->w_scale, q->bias);
     LB_LAUNCH_CHECK(ctx);
@@ -342,7 +347,8 @@ gemm_i8_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ W
     for (int k0 = 0; k0 < K; k0 += 16) {
         sa[ty][tx] = (row < M && k0 + tx < K) ? A[(long long)row * K + k0 + tx] : 0;
         int wc = blockIdx.x * 16 + ty;
-        sb[tx][ty] = (wc < N && k0 + tx < K) ? Wt[(long long)wc * K + k0 + tx] : 0;   // sb[kk][col]
+        const int wraw = (wc < N && k0 + tx < K) ? Wt[(long long)wc * K + k0 + tx] : 0;
+        sb[tx][ty] = ep.w_signed ? (int)(int8_t)wraw : wraw;   // sb[kk][col]; signed storage: the byte w ^ 0x80 read as s8 is w - 128
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) acc += sa[ty][kk] * sb[kk][tx];
@@ -350,7 +356,8 @@ gemm_i8_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ W
     }
     if (row < M && col < N) {
         int zpa = ep.row_zp[row];
-        int acci = acc + K * zpa * ep.w_zp - ep.w_zp * ep.rowsum[row] - zpa * ep.colsum[col];
+        const int wz = ep.w_signed ? ep.w_zp - 128 : ep.w_zp;
+        int acci = acc + K * zpa * wz - wz * ep.rowsum[row] - zpa * ep.colsum[col];
         float v = __fmul_rn((float)acci, __fmul_rn(ep.row_scale[row], ep.w_scale[col]));
         if (ep.has_bias) v = __fadd_rn(v, ep.bias[col]);
         if (ep.relu) v = fmaxf(v, 0.0f);
@@ -395,7 +402,7 @@ LbQuantScratch lb_quant_scratch_carve(void* base, long long M, int K) {
 }
 void lb_fill_weight_fields(LbI8Epilogue& ep, const lele_b200_qweights* w, const LbQuantScratch& s) {
     ep.rowsum = s.rowsum; ep.row_scale = s.row_scale; ep.row_zp = s.row_zp;
-    ep.colsum = w->colsum; ep.w_scale = w->w_scale; ep.bias = w->bias; ep.w_zp = w->w_zp; ep.has_bias = w->has_bias;
+    ep.colsum = w->colsum; ep.w_scale = w->w_scale; ep.bias = w->bias; ep.w_zp = w->w_zp; ep.w_signed = w->w_signed; ep.has_bias = w->has_bias;
 }
 static int lb_quantized_linear(lele_b200_ctx* ctx, const float* x, const unsigned* keys, long long M, int rows_per_slice,
                                const lele_b200_qweights* w, const LbQuantScratch& s, LbI8Epilogue ep) {

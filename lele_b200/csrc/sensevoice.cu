@@ -201,9 +201,11 @@ struct lele_b200_sensevoice {
     int32_t* ids_stage = nullptr;
     unsigned* keys = nullptr;
     unsigned long long* amax_keys = nullptr;
+    int* fq_counters = nullptr;       // [n_layers][clips] arrival counters of the one-pass FFN1 (gemm_i8_fused_q_kernel), zeroed per forward
     void* qscratch = nullptr;
     void* qscratch2 = nullptr;        // second quantised-operand set: FFN1's fused output quantiser writes it while reading the first
     void* attn_scratch = nullptr;
+    int ffn_onepass = 1;              // FFN1 in ONE pass (dequantised tile parked in TMEM until the clip's max is known); LELE_B200_FFN_FUSED=0 -> two passes
     int ffn_twopass = 1;              // FFN1 as max-only pass + quantising pass (no f32 [M, ffn] round trip); LELE_B200_FFN_TWOPASS=0 disables
     int fuse_lnq = 1;                 // LayerNorm + quantiser fused for the encoder width (LELE_B200_FUSE_LNQ=0 disables)
     int attn_simt = 0;   // LELE_B200_ATTN_SIMT=1: CUDA-core attention (cross-check of the tcgen05 path)
@@ -279,13 +281,19 @@ struct ProfScope {
 
 #define SV_LINEAR(...) do { int _rc = sv_linear(__VA_ARGS__); if (_rc) return _rc; } while (0)
 
+// the quantised GEMM; an epilogue that carries fq_keys asks for the one-pass linear -> ReLU -> quantiser kernel
+static int sv_gemm(lele_b200_ctx* ctx, const LbQuantScratch& qs, const lele_b200_qweights* w, long long M, const LbI8Epilogue& ep) {
+    if (ep.fq_keys) return lb_gemm_i8_tc_fused_q(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep);
+    return lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep);
+}
+
 // quantise the activation rows (per-clip keys already hold min/max) then the tcgen05 GEMM;
 // profiled as two classes so the GEMM's own duration feeds the roofline.
 int sv_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const unsigned* keys, long long M, int T,
               const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep, int gcls) {
     SV_RUN(P_QUANTIZE, lb_quantize_rows(ctx, x, keys, M, T, w->k, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp));
     lb_fill_weight_fields(ep, w, qs);
-    SV_RUN(gcls, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+    SV_RUN(gcls, sv_gemm(ctx, qs, w, M, ep));
     return LELE_B200_OK;
 }
 
@@ -297,14 +305,14 @@ int sv_ln_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, co
         // one cluster per clip: x read once, normalised rows live in shared memory until the clip's min/max is known
         SV_RUN(P_LAYERNORM, lb_layer_norm_quantize_cluster(ctx, x, gamma, beta, (int)(M / T), T, 1e-5f, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp, keys));
         lb_fill_weight_fields(ep, w, qs);
-        SV_RUN(gcls, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+        SV_RUN(gcls, sv_gemm(ctx, qs, w, M, ep));
         return LELE_B200_OK;
     }
     if (m->fuse_lnq && lb_layer_norm_quantize_supported(n, T)) {
         SV_RUN(P_LAYERNORM, lb_layer_norm_stats(ctx, x, gamma, beta, M, n, 1e-5f, m->h, keys, T));
         SV_RUN(P_QUANTIZE, lb_layer_norm_quantize(ctx, x, gamma, beta, M, n, m->h, keys, T, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp));
         lb_fill_weight_fields(ep, w, qs);
-        SV_RUN(gcls, lb_gemm_i8(ctx, qs.a_u8, w->wt, (int)M, w->n, w->k, ep));
+        SV_RUN(gcls, sv_gemm(ctx, qs, w, M, ep));
         return LELE_B200_OK;
     }
     SV_RUN(P_LAYERNORM, lb_layer_norm_minmax(ctx, x, gamma, beta, M, n, 1e-5f, m->h, keys, T));
@@ -379,9 +387,11 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc((void**)&m->scores, sizeof(float) * B * m->heads * m->max_T * m->max_T);
     if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1));
     if (!rc) rc = sv_alloc((void**)&m->amax_keys, sizeof(unsigned long long) * M);
+    if (!rc) rc = sv_alloc((void**)&m->fq_counters, sizeof(int) * (size_t)m->n_layers * B);
     if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax) + 4096 * lele_b200_sensevoice::MAX_LANES);   // + per-lane carve alignment
     if (!rc) rc = sv_alloc(&m->qscratch2, lb_quant_scratch_bytes((long long)M, kmax) + 4096 * lele_b200_sensevoice::MAX_LANES);
     { const char* e = getenv("LELE_B200_FFN_TWOPASS"); m->ffn_twopass = (e && e[0] == '0') ? 0 : 1; }
+    m->ffn_onepass = lb_env_flag("LELE_B200_FFN_FUSED", 1) ? 1 : 0;
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("LELE_B200_GRAPH"); m->use_graph = (e && e[0] == '0') ? 0 : 1; }
@@ -424,7 +434,7 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
     if (!m) return LELE_B200_OK;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (auto* q : m->lin) lele_b200_qweights_destroy(nullptr, q);
-    void* bufs[] = {m->lfr, m->feats, m->x0, m->x, m->h, m->qkv, m->qs, m->fsmn, m->att, m->f1, m->scores, m->keys, m->amax_keys,
+    void* bufs[] = {m->lfr, m->feats, m->x0, m->x, m->h, m->qkv, m->qs, m->fsmn, m->att, m->f1, m->scores, m->keys, m->amax_keys, m->fq_counters,
                     m->qscratch, m->qscratch2, m->pcm_stage, m->ids_stage, m->attn_scratch};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : m->ev_pool) cudaEventDestroy(e);
@@ -473,6 +483,10 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     LB_REQUIRE(lang >= 0 && lang < m->n_embed && textnorm >= 0 && textnorm < m->n_embed, "sensevoice: prompt id out of range");
     const int n_sites = m->n_layers * 4 + 1;
     SV_RUN(P_MISC, lb_minmax_init(ctx, m->keys, n_sites * B));
+    // one-pass FFN1 (accumulators wait in TMEM for the clip's max): its CTAs spin on each other, so it runs only when this forward owns the
+    // device's SMs -- not inside a clip lane (lanes are concurrent forwards)
+    const bool fq_allowed = !m->is_view && m->fq_counters && m->ffn_onepass;
+    if (fq_allowed) LB_CHECK_CUDA(cudaMemsetAsync(m->fq_counters, 0, sizeof(int) * (size_t)m->n_layers * B, ctx->stream));
     auto site = [&](int s) { return m->keys + (size_t)2 * LB_MM_SLOTS * B * s; };
     const LbQuantScratch qs = lb_quant_scratch_carve(m->qscratch, M, ffn > din ? ffn : din);
     const LbQuantScratch qs2 = lb_quant_scratch_carve(m->qscratch2, M, ffn > din ? ffn : din);
@@ -561,7 +575,21 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         // ---- feed-forward block ----
         const lele_b200_qweights* w1 = m->lin[l * 4 + 2];
         const bool twopass = m->ffn_twopass && T >= 32 && w1->n % 32 == 0 && w1->k % 16 == 0 && !getenv("LELE_B200_FORCE_SIMT");
-        if (twopass) {
+        const lele_b200_qweights* w2f = m->lin[l * 4 + 3];
+        const bool onepass = twopass && fq_allowed && w2f->w_signed && lb_gemm_i8_fused_q_supported(ctx, M, w1->n, w1->k, T, w1->w_signed);
+        if (onepass) {
+            // FFN1 once: LayerNorm + quantiser, then the GEMM whose epilogue reduces the per-clip max, parks the dequantised tile in TMEM
+            // until every CTA has contributed, and quantises it -> FFN2 consumes the u8 operand; no max-only pass, no f32 [M, ffn] tensor
+            LbI8Epilogue e2; memset(&e2, 0, sizeof(e2));
+            e2.rows_per_slice = T; e2.relu = 1; e2.q_out = qs2.a_u8; e2.q_row_scale = qs2.row_scale; e2.q_row_zp = qs2.row_zp;
+            e2.fq_keys = site(l * 4 + 3); e2.fq_counters = m->fq_counters + (size_t)l * B;
+            int rc_ = sv_ln_linear(ctx, m, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), d, site(l * 4 + 2), M, T, w1, qs, e2, P_G_FFN1);
+            if (rc_) return rc_;
+            LbI8Epilogue e3; memset(&e3, 0, sizeof(e3));
+            e3.out = m->x; e3.rows_per_slice = T; e3.add2 = m->x;                                          // x = x + ffn
+            lb_fill_weight_fields(e3, w2f, qs2);                                                           // s8 weights: FFN2 needs no row sums
+            SV_RUN(P_G_FFN2, lb_gemm_i8(ctx, qs2.a_u8, w2f->wt, (int)M, w2f->n, w2f->k, e3));
+        } else if (twopass) {
             // FFN1 twice over the same quantised LN output: pass 1 reduces only the per-clip max of the ReLU output (nothing is
             // written), pass 2 recomputes the tile and quantises it in the epilogue -> the [M, ffn] f32 tensor of the reference
             // (and its quantiser pass) never exists; FFN2 consumes the u8 operand directly.

@@ -106,6 +106,28 @@ def test_clip_lanes_bit_identical(lanes, monkeypatch):
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("switch", ["LELE_B200_FFN_FUSED", "LELE_B200_W_UNSIGNED"])
+def test_one_pass_ffn1_and_s8_weights_bit_identical(switch, monkeypatch):
+    """Round-2 GEMM changes are pure re-schedulings of exact arithmetic: (a) FFN1 as ONE pass (the dequantised tile waits in TMEM for
+    the clip's max, gemm_i8_fused_q_kernel) vs the max-only + quantising passes; (b) the weight operand as s8 (w - 128, no per-row
+    zero-point term) vs u8.  Logits and ids must be bit-identical either way -- uneven batch (7 clips of 3 s: groups of clips, a partial
+    last m-block per group, warps that straddle two clips), eager + capture + replay."""
+    blob = build_blob(SMALL, seed=12)
+    pcm = synth_batch(5, 7, 16000 * 3)
+    outs = []
+    for v in ("default", "switched"):
+        if v == "switched":
+            monkeypatch.setenv(switch, "0" if switch == "LELE_B200_FFN_FUSED" else "1")
+        m = SenseVoice(blob, max_clips=7, max_samples=pcm.shape[1])
+        ids, logits = m.transcribe(pcm, want_logits=True)
+        for _ in range(2):
+            np.testing.assert_array_equal(ids, m.transcribe(pcm))
+        outs.append((ids, logits))
+        m.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
 def test_pipelined_host_entry_matches_blocking(small_model_tc):
     """transcribe_host_async / transcribe_wait (two batches in flight, copies on their own streams) returns exactly the ids
     of the blocking entry for every batch, in submission order; a busy slot is refused."""
