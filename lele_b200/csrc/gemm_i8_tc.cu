@@ -629,12 +629,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // Requires every CTA of the grid to be co-resident (grid <= #SMs, 1 CTA per SM by shared memory): the host refuses shapes
 // that do not fit and the runner uses it only when nothing else shares the device (one lane).  Spins are bounded (trap).
 // =====================================================================================================================
-constexpr int FQ_TILE_BYTES = 1024;                            // per-warp 32 x 32 u8 staging tile
-constexpr int FQ_META_BYTES = 5 * 64 * 4;                      // zcA | csA | zcB | csB | bias of the warp's 64 columns
+constexpr int FQ_TILE_BYTES = 2048;                            // per-warp 32 rows x 64 u8 staging tile (one TMA store per tile)
+constexpr int FQ_META_BYTES = 64 * 4;                          // bias of the warp's 64 columns; the per-pass tables zcA | csA | zcB | csB (1 KB) live in the
+                                                               // staging tile, which is idle during a max pass (its last TMA store is waited for first)
 constexpr int FQ_MAX_SLOTS = BM / 32 + 1;                      // clips a 128-row tile can touch (T >= 32)
 constexpr int FQ_EPI_BYTES = NUM_EPI_WARPS * (FQ_TILE_BYTES + FQ_META_BYTES);
 constexpr int FQ_SMEM_BYTES = STAGES * STAGE_BYTES + FQ_EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers, CTA key slots*/;
-static_assert(FQ_SMEM_BYTES <= 232448, "shared memory budget (fused quantiser)");
+// K <= 512: the CTA's 256 x K weight block (the same in every group) is loaded ONCE and stays in shared memory; only the
+// 16 KB activation tiles stream (64 KB instead of 192 KB of L2 -> SM traffic per tile, which is what paces the MMAs)
+constexpr int FQ_RES_KB = 4;
+constexpr int FQ_RES_SMEM_BYTES = FQ_RES_KB * B_STAGE_BYTES + STAGES * A_STAGE_BYTES + FQ_EPI_BYTES + 1024 + 512;
+static_assert(FQ_SMEM_BYTES <= 232448 && FQ_RES_SMEM_BYTES <= 232448, "shared memory budget (fused quantiser)");
 
 struct FusedArgs {
     int M, N, K;
@@ -642,6 +647,7 @@ struct FusedArgs {
     int T; float inv_T;   // rows per clip
     int GT;               // rows per group (G clips)
     int n_groups, n_clips;
+    int dbg;              // LELE_B200_GEMM_DBG=1 in a -DLELE_B200_GEMM_TIMELINE build: CTAs 0 / 77 print where their epilogue waited
     LbI8Epilogue ep;
 };
 
@@ -662,7 +668,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
 
-template <bool RELU>
+template <bool RELU, bool RESB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_out, const FusedArgs args) {
@@ -670,14 +676,15 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* epi_base = smem_b + STAGES * B_STAGE_BYTES;           // 16 staging tiles, then 16 metadata blocks
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;               // RESB: the FQ_RES_KB resident k-blocks of the weight block
+    uint8_t* epi_base = smem_b + (RESB ? FQ_RES_KB : STAGES) * B_STAGE_BYTES;   // 16 staging tiles, then 16 metadata blocks
     uint64_t* bars = (uint64_t*)(epi_base + FQ_EPI_BYTES);
     uint64_t* full_bar = bars;                     // [STAGES] TMA -> MMA
     uint64_t* empty_bar = bars + STAGES;           // [STAGES] MMA -> TMA
     uint64_t* tmem_full = bars + 2 * STAGES;       // [2]      MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;          // [2]      epilogue (quantising pass) -> MMA
-    uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+    uint64_t* b_full = tmem_empty + 2;             // RESB: the resident weight block landed
+    uint32_t* tmem_base_smem = (uint32_t*)(b_full + 1);
     unsigned* cta_keys = (unsigned*)(tmem_base_smem + 2);          // [2 parities][FQ_MAX_SLOTS][min, max]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -693,6 +700,7 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
         for (int i = 0; i < 2 * FQ_MAX_SLOTS; ++i) { cta_keys[2 * i] = LB_KEY_MIN_INIT; cta_keys[2 * i + 1] = LB_KEY_MAX_INIT; }
+        mbar_init(b_full, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -711,13 +719,17 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            if (RESB && n_act > 0) {                               // weights do not depend on the previous kernel, but the wait above is cheap
+                mbar_expect_tx(b_full, (uint32_t)args.nkb * B_STAGE_BYTES);
+                for (int kb = 0; kb < args.nkb; ++kb) tma_load_2d(smem_b + kb * B_STAGE_BYTES, &tmap_b, b_full, kb * BK, nb * BN);
+            }
             for (int g = 0; g < n_act; ++g) {
                 const int row0 = g * GT + mb * BM;
                 for (int kb = 0; kb < args.nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    mbar_expect_tx(&full_bar[stage], RESB ? A_STAGE_BYTES : STAGE_BYTES);
                     tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, row0);
-                    tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, nb * BN);
+                    if (!RESB) tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, nb * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -726,6 +738,7 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         // ===================== MMA issuer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            if (RESB && n_act > 0) { mbar_wait(b_full, 0); tc_fence_after(); }
             for (int g = 0; g < n_act; ++g) {
                 const int acc = g & 1; const uint32_t acc_phase = (uint32_t)(g >> 1) & 1u;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);            // the quantising pass of group g - 2 drained this stage
@@ -735,7 +748,7 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (RESB ? kb : stage) * B_STAGE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
@@ -753,7 +766,8 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int cgrp = ew >> 2;
         const LbI8Epilogue& ep = args.ep;
         const uint32_t tile_s = smem_u32(epi_base) + (uint32_t)ew * FQ_TILE_BYTES;
-        const uint32_t meta_s = smem_u32(epi_base) + NUM_EPI_WARPS * FQ_TILE_BYTES + (uint32_t)ew * FQ_META_BYTES;
+        const uint32_t meta_s = tile_s;                                // zcA | csA | zcB | csB during a max pass
+        const uint32_t bias_s = smem_u32(epi_base) + NUM_EPI_WARPS * FQ_TILE_BYTES + (uint32_t)ew * FQ_META_BYTES;
         const int T = args.T; const float inv_T = args.inv_T;
         const int N = args.N;
         const int gcol_w = nb * BN + cgrp * 64;
@@ -765,8 +779,9 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int hh = 0; hh < 2; ++hh) {
             const int cc = min(gcol_w + hh * 32 + lane, N - 1);
             cs_raw[hh] = __ldg(ep.colsum + cc); ws_raw[hh] = __ldg(ep.w_scale + cc);
-            sts_f32(meta_s + 1024 + 4 * (hh * 32 + lane), __ldg(ep.bias + cc));
+            sts_f32(bias_s + 4 * (hh * 32 + lane), __ldg(ep.bias + cc));
         }
+        long long w_mma = 0, w_cnt = 0, w_bar = 0, t_me = 0, t_qe = 0; const long long t_begin = clock64();
         struct Geo { int first_row, nrows, sl_a, clip0, gend, g0; bool row_ok, in_a, all_a; };
         auto geometry = [&](int g) {
             Geo q;
@@ -782,15 +797,27 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             return q;
         };
 
+        // the row's activation parameters are fetched one group ahead (no global-load latency between two passes)
+        int pf_zpa = 0; float pf_sa = 0.0f;
+        auto fetch_rows = [&](int g) {
+            pf_zpa = 0; pf_sa = 0.0f;
+            if (g >= n_act) return;
+            const int row = g * GT + mb * BM + quad * 32 + lane;
+            if (row < min(g * GT + GT, M)) { pf_zpa = __ldg(ep.row_zp + row); pf_sa = __ldg(ep.row_scale + row); }
+        };
+        fetch_rows(0);
+
         // ---- max pass of group g ----
         auto max_pass = [&](int g) {
+            const long long t_me0 = GEMM_DBG ? clock64() : 0;
             const int s = g & 1; const uint32_t ph = (uint32_t)(g >> 1) & 1u;
             const Geo q = geometry(g);
-            int zpa = 0; float sa = 0.0f;
-            if (q.row_ok) { zpa = __ldg(ep.row_zp + q.first_row + lane); sa = __ldg(ep.row_scale + q.first_row + lane); }
+            const int zpa = pf_zpa; const float sa = pf_sa;
+            fetch_rows(g + 1);
             const int lastl = max(q.nrows - 1, 0);
             const int zpa_a = __shfl_sync(0xffffffffu, zpa, 0), zpa_b = __shfl_sync(0xffffffffu, zpa, lastl);
             const float sa_a = __shfl_sync(0xffffffffu, sa, 0), sa_b = __shfl_sync(0xffffffffu, sa, lastl);
+            if (lane == 0) tma_store_wait_read();                  // the tables share the staging tile: its last store must have read it
             __syncwarp();
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {                       // tables combined with the clip's activation parameters
@@ -804,7 +831,9 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const uint32_t my_meta = meta_s + (q.in_a ? 0u : 512u);
             float vmax = -FMAX, vmin = FMAX;
             if (q.nrows > 0 && cols_ok) {
+                const long long t_w0 = GEMM_DBG ? clock64() : 0;
                 mbar_wait(&tmem_full[s], ph);
+                if (GEMM_DBG) w_mma += clock64() - t_w0;
                 tc_fence_after();
 #pragma unroll 1
                 for (int chunk = 0; chunk < 2; ++chunk) {
@@ -815,7 +844,7 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     for (int qq = 0; qq < 8; ++qq) {
                         const int4 zc4 = lds_v4(my_meta + 16 * (chunk * 8 + qq));
                         const int4 cs4 = lds_v4(my_meta + 256 + 16 * (chunk * 8 + qq));
-                        const int4 bi4 = lds_v4(meta_s + 1024 + 16 * (chunk * 8 + qq));
+                        const int4 bi4 = lds_v4(bias_s + 16 * (chunk * 8 + qq));
                         const int zc[4] = {zc4.x, zc4.y, zc4.z, zc4.w};
                         const float cs[4] = {__int_as_float(cs4.x), __int_as_float(cs4.y), __int_as_float(cs4.z), __int_as_float(cs4.w)};
                         const float bi[4] = {__int_as_float(bi4.x), __int_as_float(bi4.y), __int_as_float(bi4.z), __int_as_float(bi4.w)};
@@ -844,7 +873,9 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     if (lane == 0) { atomicMin(slot + 2, mnB); atomicMax(slot + 3, mxB); }
                 }
             }
+            const long long t_b0 = GEMM_DBG ? clock64() : 0;
             epi_bar_sync();                                        // every warp's keys are in the CTA slots
+            if (GEMM_DBG) { w_bar += clock64() - t_b0; t_me += clock64() - t_me0; }
             if (ew == 0 && lane < FQ_MAX_SLOTS) {
                 const int tile_r0 = q.g0 + mb * BM, tile_end = min(tile_r0 + BM, q.gend);
                 const int clip = q.clip0 + lane;
@@ -864,6 +895,7 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const int s = g & 1;
             const Geo q = geometry(g);
             float q_inv = 0.0f, q_zp = 0.0f, q_scale = 0.0f;
+            const long long t_qe0 = GEMM_DBG ? clock64() : 0;
             if (q.nrows > 0 && cols_ok) {
                 if (lane == 0) {
                     // every CTA whose block has rows of the clip arrives once: nnb column blocks x the m-blocks the clip spans
@@ -880,6 +912,7 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                 }
                 __syncwarp();
+                if (GEMM_DBG) w_cnt += clock64() - t_qe0;
                 // lanes 0-15 hold the 8 (min, max) key slots of clip A, lanes 16-31 those of clip A+1
                 const int sl = min(q.sl_a + (lane >> 4), args.n_clips - 1);
                 unsigned k = __ldcg(ep.fq_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
@@ -894,9 +927,12 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 q_scale = __fdiv_rn(fmaxf(__fsub_rn(amax, amin), 1e-5f), 255.0f);
                 q_zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, q_scale)), 0.0f), 255.0f);
                 q_inv = __fdiv_rn(1.0f, q_scale);
+                if (q.nrows == 32) {                               // the previous tile's store has read the staging tile (long ago)
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
 #pragma unroll 1
                 for (int chunk = 0; chunk < 2; ++chunk) {
-                    const int gcol0 = gcol_w + chunk * 32;
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * BN + cgrp * 64 + chunk * 32);
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr, r);
@@ -909,25 +945,27 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         const unsigned u3 = cvt_sat_u8(__fmaf_rn(__uint_as_float(r[qq * 4 + 3]), q_inv, q_zp));
                         pk[qq] = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
                     }
-                    if (q.nrows == 32) {
-                        if (lane == 0) tma_store_wait_read();      // the previous store has read the staging tile
-                        __syncwarp();
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, q.first_row);
+                    if (q.nrows == 32) {                           // staging: row = lane, 64 B per row
+                        const uint32_t dst = tile_s + (uint32_t)lane * 64u + (uint32_t)chunk * 32u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
                     } else if (q.row_ok) {                         // last rows of a group: the rows below belong to the next group
-                        uint4* dst = reinterpret_cast<uint4*>(ep.q_out + (size_t)(q.first_row + lane) * N + gcol0);
+                        uint4* dst = reinterpret_cast<uint4*>(ep.q_out + (size_t)(q.first_row + lane) * N + gcol_w + chunk * 32);
                         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
+                }
+                if (q.nrows == 32) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol_w, q.first_row);     // 32 rows x 64 columns
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[s]);            // the MMA warp may overwrite this accumulator stage
             if (q.row_ok && nb == 0 && cgrp == 0) { ep.q_row_scale[q.first_row + lane] = q_scale; ep.q_row_zp[q.first_row + lane] = (int)q_zp; }
+            if (GEMM_DBG) t_qe += clock64() - t_qe0;
         };
 
         for (int p = 0; p < n_act; p += 2) {                       // me(p) me(p+1) qe(p) qe(p+1): one copy of each pass in the instruction cache
@@ -938,6 +976,9 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             for (int g = p; g < pe; ++g) quant_pass(g);
         }
         if (lane == 0) tma_store_wait_all();
+        if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (ew == 0 || ew == 15))
+            printf("FQDBG blk %d warp %d: total %lld | max passes %lld (wait MMA %lld, CTA barrier %lld) | quant passes %lld (wait clips %lld) | groups %d\n",
+                   blockIdx.x, ew, clock64() - t_begin, t_me, w_mma, w_bar, t_qe, w_cnt, n_act);
     }
 
     tc_fence_before();
@@ -1007,14 +1048,14 @@ int cached_tmap_out_f32(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, l
     return LELE_B200_OK;
 }
 // u8 [rows, cols] row-major output, box = 32 x 32 (one epilogue warp's quantised sub-tile), no swizzle
-int cached_tmap_out_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols) {
-    const unsigned long long key[10] = {0x6f757538ull, (unsigned long long)(uintptr_t)ptr, (unsigned long long)rows, (unsigned long long)cols};
+int cached_tmap_out_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, long long rows, long long cols, int box_cols = 32) {
+    const unsigned long long key[10] = {0x6f757538ull, (unsigned long long)(uintptr_t)ptr, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)box_cols};
     if (lb_tmap_lookup(ctx, key, map)) return LELE_B200_OK;
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { lb_set_error("cuTensorMapEncodeTiled entry point unavailable"); return LELE_B200_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -1133,7 +1174,7 @@ int lb_gemm_i8_tc_fused_q(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* W
     int rc = cached_tmap_u8(ctx, &ta, A, M, K, BM);
     if (rc) return rc;
     if ((rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN))) return rc;
-    if ((rc = cached_tmap_out_u8(ctx, &tout, ep.q_out, M, N))) return rc;
+    if ((rc = cached_tmap_out_u8(ctx, &tout, ep.q_out, M, N, 64))) return rc;
     FusedArgs args;
     args.M = M; args.N = N; args.K = K;
     args.nnb = lb_ceil_div(N, BN); args.nkb = lb_ceil_div(K, BK);
@@ -1144,15 +1185,19 @@ int lb_gemm_i8_tc_fused_q(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* W
     args.GT = G * T;
     args.n_groups = lb_ceil_div(args.n_clips, G);
     args.ep = ep;
+    args.dbg = getenv("LELE_B200_GEMM_DBG") ? 1 : 0;
     const int grid = lb_ceil_div(args.GT, BM) * args.nnb;
     LB_REQUIRE(grid <= ctx->num_sms, "gemm_i8 fused quantiser: grid %d exceeds the %d SMs (every CTA must be resident)", grid, ctx->num_sms);
-    if (ep.relu) {
-        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_fused_q_kernel<true>, FQ_SMEM_BYTES))) return rc;
-        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_fused_q_kernel<true>, dim3(grid), dim3(NUM_THREADS), FQ_SMEM_BYTES, ctx->stream, 1, ta, tb, tout, args));
-    } else {
-        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_fused_q_kernel<false>, FQ_SMEM_BYTES))) return rc;
-        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_fused_q_kernel<false>, dim3(grid), dim3(NUM_THREADS), FQ_SMEM_BYTES, ctx->stream, 1, ta, tb, tout, args));
+    const bool resb = args.nkb <= FQ_RES_KB && lb_env_flag("LELE_B200_FFN_RESB", 1);
+#define LB_LAUNCH_FQ(RL, RB)                                                                                                  \
+    {                                                                                                                         \
+        const int smem_bytes = RB ? FQ_RES_SMEM_BYTES : FQ_SMEM_BYTES;                                                        \
+        if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_fused_q_kernel<RL, RB>, smem_bytes))) return rc;                     \
+        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_fused_q_kernel<RL, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, ctx->stream, 1, ta, tb, tout, args)); \
     }
+    if (ep.relu) { if (resb) LB_LAUNCH_FQ(true, true) else LB_LAUNCH_FQ(true, false) }
+    else         { if (resb) LB_LAUNCH_FQ(false, true) else LB_LAUNCH_FQ(false, false) }
+#undef LB_LAUNCH_FQ
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }

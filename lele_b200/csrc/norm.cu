@@ -619,6 +619,260 @@ int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const flo
     return LELE_B200_OK;
 }
 
+
+// ---- streaming variant (round 2): ONE persistent CTA per SM, no clusters, no wave quantisation --------------------------------
+// The cluster kernel above holds a clip's rows on chip until the clip's min / max is known, which costs a second (almost empty) wave
+// and lock-step load -> normalise -> exchange -> quantise phases (22 us for 45 MB).  Here the rows STREAM: a CTA walks 16-row units
+// (unit u -> CTA u % grid, 4 bulk-copy buffers in flight), and each round runs
+//     A(i):   normalise unit i in place in shared memory (one row per warp, the reference's accumulator order), reduce the unit's
+//             per-clip min / max (warp -> shared-memory atomics -> one pair of global atomics per CTA and clip) and ARRIVE on the clip;
+//     B(i-1): once the counters of the row's clip show every unit that holds rows of it (acquire load; the other CTAs finished their
+//             A(i-1) a whole round ago), derive (scale, zp) and quantise unit i-1 out of shared memory.
+// Same arithmetic, operation for operation, as ln_quant_cluster_kernel (bit-identical outputs).  Every CTA must be resident (grid <=
+// #SMs; one CTA per SM by shared memory), so the runner uses it only when the forward owns the device (not inside a clip lane).
+constexpr int LQS_U = 16;                 // rows per unit == warps per CTA
+constexpr int LQS_NBUF = 6;               // 192 KB: units i-2, i-1 (normalised, waiting for their clips), i (being normalised), i+1 .. i+3 (in flight)
+constexpr int LQS_LAG = 2;                // a unit is quantised LQS_LAG rounds after it was normalised: the clip's parameters have long arrived
+constexpr int LQS_SMEM = LQS_NBUF * LQS_U * 512 * 4;
+
+__global__ void __launch_bounds__(LQS_U * 32 + 64, 1)
+ln_quant_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int T, float eps,
+                       uint8_t* __restrict__ a_u8, int32_t* __restrict__ rowsum, float* __restrict__ row_scale, int32_t* __restrict__ row_zp,
+                       uint4* __restrict__ records, int rec_stride, int dbg) {
+    constexpr int N = 512, NB = 16, U = LQS_U;
+    long long w_full = 0, t_a = 0, w_cnt = 0, t_b = 0, w_free = 0; const long long t_begin = clock64();
+    extern __shared__ __align__(128) float lqs_rows[];           // [NBUF][U][512]
+    __shared__ __align__(8) unsigned long long full_bar[LQS_NBUF];
+    __shared__ unsigned slot_keys[2][2][2];                      // [round parity][clip slot of the unit][min, max]
+    // warp 17 is the bulk-copy PRODUCER, warp 16 the PUBLISHER: the global atomics + fence + arrival of a round cost ~1-2 us of latency, which must not sit in a
+    // compute warp between two block barriers.  slots_full[p]: 16 compute warps -> publisher; slots_free[p]: publisher -> compute warps.
+    __shared__ __align__(8) unsigned long long slots_full[2], slots_free[2], buf_empty[LQS_NBUF];   // buf_empty[b]: 16 compute warps quantised the unit in buffer b
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_units = (M + U - 1) / U;
+    const int n_my = (int)((n_units - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x);   // units blockIdx.x + i * gridDim.x
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < LQS_NBUF; ++b)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full_bar[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 4; ++i) { slot_keys[i >> 1][i & 1][0] = LB_KEY_MIN_INIT; slot_keys[i >> 1][i & 1][1] = LB_KEY_MAX_INIT; }
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&slots_full[b])), "r"(LQS_U));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&slots_free[b])));
+        }
+        for (int b = 0; b < LQS_NBUF; ++b)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&buf_empty[b])), "r"(LQS_U));
+    }
+    __syncthreads();
+    lb_pdl_launch_dependents();
+    lb_pdl_wait();                 // PDL: x is the previous kernel's output
+    auto mbar_wait_par = [&](unsigned long long* b, uint32_t par) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(b);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(bar), "r"(par) : "memory");
+    };
+    auto mbar_arrive1 = [&](unsigned long long* b) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+    };
+    auto issue = [&](int i) {      // producer lane: bulk copy of the CTA's i-th unit into buffer i % NBUF
+        if (i >= n_my) return;
+        const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * U;
+        const uint32_t bytes = (uint32_t)min((long long)U, M - r0) * N * 4;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[i % LQS_NBUF]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the buffer's last generic-proxy accesses precede this copy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(lqs_rows + (size_t)(i % LQS_NBUF) * U * N)), "l"(x + r0 * N), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (warp == LQS_U + 1) {
+        // ===================== producer warp: keeps LQS_NBUF units in flight =====================
+        if (lane == 0) {
+            for (int i = 0; i < LQS_NBUF; ++i) issue(i);
+            for (int i = LQS_NBUF; i < n_my; ++i) {              // unit i - NBUF has been quantised by every warp: refill its buffer
+                mbar_wait_par(&buf_empty[i % LQS_NBUF], (uint32_t)(i / LQS_NBUF - 1) & 1u);
+                issue(i);
+            }
+        }
+        return;
+    }
+    if (warp == LQS_U) {
+        // ===================== publisher warp =====================
+        for (int i = 0; i < n_my; ++i) {
+            const int p = i & 1;
+            mbar_wait_par(&slots_full[p], (uint32_t)(i >> 1) & 1u);          // every compute warp's keys of round i are in the slots
+            if (lane < 2) {
+                const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * U;
+                const long long r_end = min(r0 + U, M);
+                const int clip = (int)(r0 / T) + lane;
+                unsigned* sk = slot_keys[p][lane];
+                const unsigned mn = sk[0], mx = sk[1];
+                sk[0] = LB_KEY_MIN_INIT; sk[1] = LB_KEY_MAX_INIT;
+                if ((long long)clip * T < r_end) {
+                    // the unit holds rows of this clip: publish its (min, max) as ONE self-validating 16-byte record {min key, 1, max key, 1}
+                    // in the clip's record row -- no atomics, no fence, no counter: the flag travels with the data (each 8-byte half
+                    // carries its own flag), and a quantising warp polls the whole row with a single load per lane
+                    const long long unit = (long long)blockIdx.x + (long long)i * gridDim.x;
+                    const int j = (int)(unit - ((long long)clip * T) / U);
+                    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(records + (size_t)clip * rec_stride + j), "r"(mn), "r"(1u), "r"(mx), "r"(1u) : "memory");
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&slots_free[p]);                     // the slots may take round i + 2
+        }
+        return;
+    }
+    float g[NB], bt[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { g[i] = __ldg(gamma + 32 * i + lane); bt[i] = __ldg(beta + 32 * i + lane); }
+    const float inv_n = __fdiv_rn(1.0f, (float)N);
+
+    // records of the clip of the warp's row in unit i, requested early (consumed by quantise_unit(i) after the next normalisation)
+    uint4 pf_rec = make_uint4(LB_KEY_MIN_INIT, 1u, LB_KEY_MAX_INIT, 1u); bool pf_valid = false;
+    auto prefetch_records = [&](int i) {
+        pf_valid = false;
+        const long long row = ((long long)blockIdx.x + (long long)i * gridDim.x) * U + warp;
+        if (i < 0 || i >= n_my || row >= M) return;
+        const int clip = (int)(row / T);
+        const long long c0 = (long long)clip * T;
+        const int n_rec = (int)((c0 + T - 1) / U - c0 / U + 1);
+        pf_rec = make_uint4(LB_KEY_MIN_INIT, 1u, LB_KEY_MAX_INIT, 1u);
+        if (lane < n_rec) asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pf_rec.x), "=r"(pf_rec.y), "=r"(pf_rec.z), "=r"(pf_rec.w)
+                                       : "l"(records + (size_t)clip * rec_stride + lane) : "memory");
+        pf_valid = true;
+    };
+    // B(i): quantise the warp's row of the CTA's i-th unit out of shared memory
+    auto quantise_unit = [&](int i) {
+        const long long row = ((long long)blockIdx.x + (long long)i * gridDim.x) * U + warp;
+        if (row >= M) return;
+        const int clip = (int)(row / T);
+        const long long t_b0 = dbg ? clock64() : 0;
+        // the clip's min / max = reduction over the records of every unit that holds rows of it (lane = record); the first 32 records
+        // were requested before this round's normalisation (pf_rec), so their L2 round trip is already behind us
+        const long long c0 = (long long)clip * T;
+        const int n_rec = (int)((c0 + T - 1) / U - c0 / U + 1);
+        unsigned kmn = LB_KEY_MIN_INIT, kmx = LB_KEY_MAX_INIT;
+        for (int jb = 0; jb < n_rec; jb += 32) {
+            const uint4* rp = records + (size_t)clip * rec_stride + jb + lane;
+            const bool mine = jb + lane < n_rec;
+            uint4 rc = make_uint4(LB_KEY_MIN_INIT, 1u, LB_KEY_MAX_INIT, 1u);
+            if (jb == 0 && pf_valid) rc = pf_rec;
+            else if (mine) asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rc.x), "=r"(rc.y), "=r"(rc.z), "=r"(rc.w) : "l"(rp) : "memory");
+            if (!__all_sync(0xffffffffu, rc.y == 1u && rc.w == 1u)) {
+                const long long t0 = clock64();
+                do {
+                    __nanosleep(32);
+                    if (mine) asm volatile("ld.volatile.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rc.x), "=r"(rc.y), "=r"(rc.z), "=r"(rc.w) : "l"(rp) : "memory");
+                    if (clock64() - t0 > 4000000000ll) { if (lane == 0) printf("lele_b200 ln_quant_stream: clip %d never completed (block %d)\n", clip, blockIdx.x); __trap(); }
+                } while (!__all_sync(0xffffffffu, rc.y == 1u && rc.w == 1u));
+            }
+            kmn = min(kmn, __reduce_min_sync(0xffffffffu, rc.x)); kmx = max(kmx, __reduce_max_sync(0xffffffffu, rc.z));
+        }
+        if (dbg) w_cnt += clock64() - t_b0;
+        const float mn = lb_fkey_inv(kmn), mx = lb_fkey_inv(kmx);
+        const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);
+        const float range = fmaxf(__fsub_rn(amax, amin), 1e-5f);
+        const float scale = __fdiv_rn(range, 255.0f);
+        const float zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, scale)), 0.0f), 255.0f);
+        const float inv = __fdiv_rn(1.0f, scale);
+        const float4* y4 = reinterpret_cast<const float4*>(lqs_rows + ((size_t)(i % LQS_NBUF) * U + warp) * N);
+        unsigned* a4 = reinterpret_cast<unsigned*>(a_u8 + row * N);
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < N / 128; ++j) {
+            const float4 y = y4[lane + 32 * j];
+            const unsigned q0 = min(__float2uint_rn(__fmaf_rn(y.x, inv, zp)), 255u), q1 = min(__float2uint_rn(__fmaf_rn(y.y, inv, zp)), 255u);
+            const unsigned q2 = min(__float2uint_rn(__fmaf_rn(y.z, inv, zp)), 255u), q3 = min(__float2uint_rn(__fmaf_rn(y.w, inv, zp)), 255u);
+            sum += (int)(q0 + q1 + q2 + q3);
+            a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+        }
+        if (rowsum) sum = lb_warp_sum_i(sum);
+        if (lane == 0) { if (rowsum) rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
+        if (dbg) t_b += clock64() - t_b0;
+    };
+
+    for (int i = 0; i < n_my; ++i) {
+        // ---- A(i): normalise the unit in place, reduce its per-clip min / max ----
+        const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * U;
+        const long long row = r0 + warp;
+        const int clip0 = (int)(r0 / T);
+        prefetch_records(i - LQS_LAG);
+        const long long t_a0 = dbg ? clock64() : 0;
+        {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&full_bar[i % LQS_NBUF]);
+            const uint32_t par = (uint32_t)(i / LQS_NBUF) & 1u;
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar), "r"(par) : "memory");
+        }
+        if (dbg) w_full += clock64() - t_a0;
+        if (row < M) {
+            float* o = lqs_rows + ((size_t)(i % LQS_NBUF) * U + warp) * N;
+            float v[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) v[j] = o[32 * j + lane];
+            float ps = 0.0f, pq = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) { ps = __fadd_rn(ps, v[j]); pq = __fmaf_rn(v[j], v[j], pq); }
+#pragma unroll
+            for (int of = 8; of <= 16; of <<= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, of)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, of)); }
+#pragma unroll
+            for (int of = 4; of >= 1; of >>= 1) { ps = __fadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, of)); pq = __fadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, of)); }
+            ps = __shfl_sync(0xffffffffu, ps, 0); pq = __shfl_sync(0xffffffffu, pq, 0);
+            const float mean = __fmul_rn(ps, inv_n);
+            const float var = __fsub_rn(__fmul_rn(pq, inv_n), __fmul_rn(mean, mean));
+            const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+            float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const float y = __fmaf_rn(__fmul_rn(__fsub_rn(v[j], mean), inv), g[j], bt[j]);
+                vmin = fminf(vmin, y); vmax = fmaxf(vmax, y);
+                o[32 * j + lane] = y;
+            }
+            const unsigned kvmin = __reduce_min_sync(0xffffffffu, lb_fkey(vmin)), kvmax = __reduce_max_sync(0xffffffffu, lb_fkey(vmax));
+            if (lane == 0) {
+                const long long t_f0 = dbg ? clock64() : 0;
+                if (i >= 2) mbar_wait_par(&slots_free[i & 1], (uint32_t)((i >> 1) - 1) & 1u);   // the publisher has drained round i - 2
+                if (dbg) w_free += clock64() - t_f0;
+                unsigned* sk = slot_keys[i & 1][(int)(row / T) - clip0];
+                atomicMin(sk, kvmin); atomicMax(sk + 1, kvmax);
+            }
+        }
+        __syncwarp();                                            // the row is normalised in place (the same warp quantises it next round)
+        if (lane == 0) mbar_arrive1(&slots_full[i & 1]);         // release: this warp's keys (if any) are in the slots
+        if (dbg) t_a += clock64() - t_a0;
+        // ---- B(i-LAG): row `warp` of an earlier unit (no block barrier anywhere: a row belongs to one warp from copy to store) ----
+        if (i >= LQS_LAG) {
+            quantise_unit(i - LQS_LAG);
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&buf_empty[(i - LQS_LAG) % LQS_NBUF]);   // release: this warp is done with the buffer
+        }
+    }
+    for (int i = max(n_my - LQS_LAG, 0); i < n_my; ++i) { pf_valid = false; quantise_unit(i); }
+    if (dbg && lane == 0 && (warp == 0 || warp == 15) && (blockIdx.x == 0 || blockIdx.x == 77))
+        printf("LQSDBG blk %d warp %d: total %lld | A %lld (wait copy %lld, wait publisher %lld) | B %lld (wait clip %lld) | units %d\n", blockIdx.x, warp, clock64() - t_begin,
+               t_a, w_full, w_free, t_b, w_cnt, n_my);
+}
+
+bool lb_layer_norm_quantize_stream_supported(lele_b200_ctx* ctx, int n, int T) { return n == 512 && T >= LQS_U && ctx->num_sms >= 1; }
+int lb_layer_norm_quantize_stream_records(int T) { return (T + LQS_U - 1) / LQS_U + 1; }   // 16-byte records per clip (units that can hold rows of one clip)
+// x [clips*T, 512] -> u8 rows (+ row sums when rowsum != NULL) + per-row (scale, zp); records = [clips][rec_stride] ZEROED 16-byte records
+// (rec_stride >= lb_layer_norm_quantize_stream_records(T)) through which the CTAs exchange the per-clip min / max
+int lb_layer_norm_quantize_stream(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, int clips, int T, float eps,
+                                  uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp, void* records, int rec_stride) {
+    LB_REQUIRE(lb_layer_norm_quantize_stream_supported(ctx, 512, T) && gamma && beta && records && (((uintptr_t)records) & 15) == 0 && rec_stride >= lb_layer_norm_quantize_stream_records(T), "layer_norm_quantize_stream: unsupported shape");
+    if (clips == 0) return LELE_B200_OK;
+    const long long M = (long long)clips * T;
+    const long long n_units = (M + LQS_U - 1) / LQS_U;
+    const int grid = (int)(n_units < ctx->num_sms ? n_units : ctx->num_sms);
+    { int rc_a = lb_func_smem(ctx, (const void*)ln_quant_stream_kernel, LQS_SMEM); if (rc_a) return rc_a; }
+    LB_CHECK_CUDA(lb_launch_pdl(ln_quant_stream_kernel, dim3(grid), dim3(LQS_U * 32 + 64), (size_t)LQS_SMEM, ctx->stream, 1, x, gamma, beta, M, T, eps, a_u8, rowsum, row_scale,
+                                row_zp, reinterpret_cast<uint4*>(records), rec_stride, (int)(getenv("LELE_B200_LNQ_DBG") ? 1 : 0)));
+    LB_LAUNCH_CHECK(ctx);
+    return LELE_B200_OK;
+}
+
 bool lb_layer_norm_quantize_supported(int n, int rows_per_slice) { return n == 512 && rows_per_slice >= 4; }
 
 // pass 1: statistics + min/max keys (keys must be initialised by the caller)

@@ -357,7 +357,7 @@ gemm_i8_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ W
     if (row < M && col < N) {
         int zpa = ep.row_zp[row];
         const int wz = ep.w_signed ? ep.w_zp - 128 : ep.w_zp;
-        int acci = acc + K * zpa * wz - wz * ep.rowsum[row] - zpa * ep.colsum[col];
+        int acci = acc + (wz ? K * zpa * wz - wz * ep.rowsum[row] : 0) - zpa * ep.colsum[col];   // s8 weights: no row term (rowsum may be NULL)
         float v = __fmul_rn((float)acci, __fmul_rn(ep.row_scale[row], ep.w_scale[col]));
         if (ep.has_bias) v = __fadd_rn(v, ep.bias[col]);
         if (ep.relu) v = fmaxf(v, 0.0f);

@@ -17,6 +17,10 @@
 // ---- internal entry points from the other translation units ----
 bool lb_layer_norm_quantize_supported(int n, int rows_per_slice);
 bool lb_layer_norm_quantize_cluster_supported(int n, int T);
+bool lb_layer_norm_quantize_stream_supported(lele_b200_ctx* ctx, int n, int T);
+int lb_layer_norm_quantize_stream(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, int clips, int T, float eps,
+                                  uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp, void* records, int rec_stride);
+int lb_layer_norm_quantize_stream_records(int T);
 int lb_layer_norm_quantize_cluster(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, int clips, int T, float eps,
                                    uint8_t* a_u8, int32_t* rowsum, float* row_scale, int32_t* row_zp, unsigned* keys_out);
 int lb_layer_norm_stats(lele_b200_ctx* ctx, const float* x, const float* gamma, const float* beta, long long outer, int n, float eps,
@@ -201,7 +205,13 @@ struct lele_b200_sensevoice {
     int32_t* ids_stage = nullptr;
     unsigned* keys = nullptr;
     unsigned long long* amax_keys = nullptr;
-    int* fq_counters = nullptr;       // [n_layers][clips] arrival counters of the one-pass FFN1 (gemm_i8_fused_q_kernel), zeroed per forward
+    int* fq_counters = nullptr;       // [sites][clips] arrival counters of the kernels whose CTAs meet through global memory (one-pass FFN1,
+                                      // streaming LayerNorm + quantiser), zeroed per forward; same site index as `keys`
+    void* ln_records = nullptr;       // [sites][clips][rec_stride] 16-byte {min key, 1, max key, 1} records of the streaming LayerNorm + quantiser, zeroed per forward
+    int rec_stride = 0; size_t rec_bytes = 0;
+    int lane_split = 0;               // clip lanes size their persistent grids to #SMs / lanes (each lane owns a share of the device): LELE_B200_LANE_SPLIT=0 -> full grids
+    int lane_sms = 0;                 // (views) the SM share of this lane, 0 = the whole device
+    int ln_stream = 0;                // LayerNorm + quantiser as the streaming persistent kernel (LELE_B200_LNQ_STREAM=0 -> cluster kernel)
     void* qscratch = nullptr;
     void* qscratch2 = nullptr;        // second quantised-operand set: FFN1's fused output quantiser writes it while reading the first
     void* attn_scratch = nullptr;
@@ -301,6 +311,15 @@ int sv_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const
 // materialised (norm.cu: statistics + min/max pass, then a re-deriving quantise pass); m->h holds the row statistics.
 int sv_ln_linear(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* x, const float* gamma, const float* beta, int n, unsigned* keys,
                  long long M, int T, const lele_b200_qweights* w, const LbQuantScratch& qs, LbI8Epilogue ep, int gcls) {
+    if (m->fuse_lnq == 1 && m->ln_stream && !m->is_view && m->ln_records && M % T == 0 && lb_layer_norm_quantize_stream_supported(ctx, n, T)) {
+        // streaming persistent kernel: x read once, rows quantised one round after their clip's min / max met in global memory
+        const size_t site_idx = (size_t)(keys - m->keys) / ((size_t)2 * LB_MM_SLOTS * (size_t)(M / T));
+        SV_RUN(P_LAYERNORM, lb_layer_norm_quantize_stream(ctx, x, gamma, beta, (int)(M / T), T, 1e-5f, qs.a_u8, w->w_signed ? nullptr : qs.rowsum, qs.row_scale, qs.row_zp,
+                                                          (uint8_t*)m->ln_records + (size_t)16 * m->rec_stride * (size_t)(M / T) * site_idx, m->rec_stride));
+        lb_fill_weight_fields(ep, w, qs);
+        SV_RUN(gcls, sv_gemm(ctx, qs, w, M, ep));
+        return LELE_B200_OK;
+    }
     if (m->fuse_lnq == 1 && lb_layer_norm_quantize_cluster_supported(n, T) && M % T == 0) {
         // one cluster per clip: x read once, normalised rows live in shared memory until the clip's min/max is known
         SV_RUN(P_LAYERNORM, lb_layer_norm_quantize_cluster(ctx, x, gamma, beta, (int)(M / T), T, 1e-5f, qs.a_u8, qs.rowsum, qs.row_scale, qs.row_zp, keys));
@@ -387,11 +406,16 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc((void**)&m->scores, sizeof(float) * B * m->heads * m->max_T * m->max_T);
     if (!rc) rc = sv_alloc((void**)&m->keys, sizeof(unsigned) * 2 * LB_MM_SLOTS * B * ((size_t)m->n_layers * 4 + 1));
     if (!rc) rc = sv_alloc((void**)&m->amax_keys, sizeof(unsigned long long) * M);
-    if (!rc) rc = sv_alloc((void**)&m->fq_counters, sizeof(int) * (size_t)m->n_layers * B);
+    if (!rc) rc = sv_alloc((void**)&m->fq_counters, sizeof(int) * ((size_t)m->n_layers * 4 + 1) * B);
+    m->rec_stride = lb_layer_norm_quantize_stream_records(m->max_T);
+    m->rec_bytes = (size_t)16 * m->rec_stride * B * ((size_t)m->n_layers * 4 + 1);
+    if (!rc) rc = sv_alloc(&m->ln_records, m->rec_bytes);
     if (!rc) rc = sv_alloc(&m->qscratch, lb_quant_scratch_bytes((long long)M, kmax) + 4096 * lele_b200_sensevoice::MAX_LANES);   // + per-lane carve alignment
     if (!rc) rc = sv_alloc(&m->qscratch2, lb_quant_scratch_bytes((long long)M, kmax) + 4096 * lele_b200_sensevoice::MAX_LANES);
     { const char* e = getenv("LELE_B200_FFN_TWOPASS"); m->ffn_twopass = (e && e[0] == '0') ? 0 : 1; }
     m->ffn_onepass = lb_env_flag("LELE_B200_FFN_FUSED", 1) ? 1 : 0;
+    m->ln_stream = lb_env_flag("LELE_B200_LNQ_STREAM", 0) ? 1 : 0;   // measured: 12 us in-kernel but 26 us in the replayed step (a 192 KB persistent CTA cannot start under its predecessor's tail; the 70 KB cluster CTAs can) -> opt-in
+    m->lane_split = lb_env_flag("LELE_B200_LANE_SPLIT", 0) ? 1 : 0;     // measured (2 lanes x 74 SMs): 3.54 vs 3.22 ms on the 8-layer stack -> opt-in
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
     { const char* e = getenv("LELE_B200_ATTN_SIMT"); m->attn_simt = (e && e[0] == '1') ? 1 : 0; }
     { const char* e = getenv("LELE_B200_GRAPH"); m->use_graph = (e && e[0] == '0') ? 0 : 1; }
@@ -434,7 +458,7 @@ extern "C" int lele_b200_sensevoice_destroy(lele_b200_ctx* ctx, lele_b200_sensev
     if (!m) return LELE_B200_OK;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (auto* q : m->lin) lele_b200_qweights_destroy(nullptr, q);
-    void* bufs[] = {m->lfr, m->feats, m->x0, m->x, m->h, m->qkv, m->qs, m->fsmn, m->att, m->f1, m->scores, m->keys, m->amax_keys, m->fq_counters,
+    void* bufs[] = {m->lfr, m->feats, m->x0, m->x, m->h, m->qkv, m->qs, m->fsmn, m->att, m->f1, m->scores, m->keys, m->amax_keys, m->fq_counters, m->ln_records,
                     m->qscratch, m->qscratch2, m->pcm_stage, m->ids_stage, m->attn_scratch};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : m->ev_pool) cudaEventDestroy(e);
@@ -485,8 +509,12 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
     SV_RUN(P_MISC, lb_minmax_init(ctx, m->keys, n_sites * B));
     // one-pass FFN1 (accumulators wait in TMEM for the clip's max): its CTAs spin on each other, so it runs only when this forward owns the
     // device's SMs -- not inside a clip lane (lanes are concurrent forwards)
-    const bool fq_allowed = !m->is_view && m->fq_counters && m->ffn_onepass;
-    if (fq_allowed) LB_CHECK_CUDA(cudaMemsetAsync(m->fq_counters, 0, sizeof(int) * (size_t)m->n_layers * B, ctx->stream));
+    // kernels whose CTAs wait for each other need every CTA resident: the forward owns the device, or it is a clip lane whose grids are
+    // sized to its share of the SMs (then the concurrent lanes' persistent grids fit side by side)
+    const bool meet_ok = (!m->is_view || m->lane_sms > 0) && m->fq_counters;
+    const bool fq_allowed = meet_ok && m->ffn_onepass;
+    if (meet_ok) LB_CHECK_CUDA(cudaMemsetAsync(m->fq_counters, 0, sizeof(int) * (size_t)n_sites * B, ctx->stream));
+    if (meet_ok && m->ln_stream && m->ln_records) LB_CHECK_CUDA(cudaMemsetAsync(m->ln_records, 0, (size_t)16 * m->rec_stride * B * n_sites, ctx->stream));
     auto site = [&](int s) { return m->keys + (size_t)2 * LB_MM_SLOTS * B * s; };
     const LbQuantScratch qs = lb_quant_scratch_carve(m->qscratch, M, ffn > din ? ffn : din);
     const LbQuantScratch qs2 = lb_quant_scratch_carve(m->qscratch2, M, ffn > din ? ffn : din);
@@ -582,7 +610,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             // until every CTA has contributed, and quantises it -> FFN2 consumes the u8 operand; no max-only pass, no f32 [M, ffn] tensor
             LbI8Epilogue e2; memset(&e2, 0, sizeof(e2));
             e2.rows_per_slice = T; e2.relu = 1; e2.q_out = qs2.a_u8; e2.q_row_scale = qs2.row_scale; e2.q_row_zp = qs2.row_zp;
-            e2.fq_keys = site(l * 4 + 3); e2.fq_counters = m->fq_counters + (size_t)l * B;
+            e2.fq_keys = site(l * 4 + 3); e2.fq_counters = m->fq_counters + (size_t)(l * 4 + 3) * B;
             int rc_ = sv_ln_linear(ctx, m, m->x, (const float*)m->lt(l, SV_L_LN2_G), (const float*)m->lt(l, SV_L_LN2_B), d, site(l * 4 + 2), M, T, w1, qs, e2, P_G_FFN1);
             if (rc_) return rc_;
             LbI8Epilogue e3; memset(&e3, 0, sizeof(e3));
@@ -666,6 +694,7 @@ static int sv_encoder_lanes(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const f
     const long long out_w = n_layers < m->n_layers ? (n_layers == 0 ? din : d) : m->vocab;
     const size_t Tp = (size_t)((T + 3) / 4 * 4);
     LB_CHECK_CUDA(cudaEventRecord(m->ev_lane_fork, ctx->stream));
+    const int lane_sms = ctx->num_sms / nl;   // each lane's persistent kernels take their share of the SMs, so the lanes run side by side
     int c0 = 0, rc = 0;
     size_t q_off = 0;
     for (int i = 0; i < nl; ++i) {
@@ -677,6 +706,10 @@ static int sv_encoder_lanes(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const f
         v->fsmn = m->fsmn + r0 * d; v->att = m->att + r0 * d; v->f1 = m->f1 + r0 * ffn;
         v->scores = m->scores + (long long)c0 * H * T * T;
         v->keys = m->keys + 2 * LB_MM_SLOTS * n_sites * (size_t)c0;
+        v->fq_counters = m->fq_counters + n_sites * (size_t)c0;
+        v->lane_sms = m->lane_split ? lane_sms : 0;
+        const int sms_saved = lctx->num_sms;
+        if (m->lane_split) lctx->num_sms = lane_sms;
         v->amax_keys = m->amax_keys + r0;
         v->qscratch = (uint8_t*)m->qscratch + q_off; v->qscratch2 = (uint8_t*)m->qscratch2 + q_off;
         v->attn_scratch = (float*)m->attn_scratch + (size_t)c0 * H * dk * Tp;
@@ -684,6 +717,7 @@ static int sv_encoder_lanes(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const f
         if (i > 0) LB_CHECK_CUDA(cudaStreamWaitEvent(lctx->stream, m->ev_lane_fork, 0));
         if (!rc) rc = sv_encoder(lctx, v, feats + (long long)c0 * t * din, nb, t, lang, textnorm, n_layers_limit, ids_dev ? ids_dev + r0 : nullptr,
                                  logits_opt ? logits_opt + r0 * out_w : nullptr);
+        lctx->num_sms = sms_saved;
         if (i > 0) {   // join even after an error so that an enclosing stream capture stays well formed
             LB_CHECK_CUDA(cudaEventRecord(m->ev_lane_join[i], lctx->stream));
             LB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_lane_join[i], 0));
