@@ -135,6 +135,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 struct KernelArgs {
     int M, N, K;
     int vec_io;
+    int red;            // TMA_OUT epilogues: the tile is ADDED to `out` (cp.reduce ... .add) -- the in-place residual x = x + (...)
     int dbg;            // LELE_B200_GEMM_DBG=1: CTAs 0 and 77 print where their producer / MMA / epilogue roles waited (clock64)
     int num_m_blocks, num_n_blocks, num_k_blocks;
     int rps;            // rows per slice (0x7fffffff when the epilogue has no slices)
@@ -166,6 +167,14 @@ __device__ __forceinline__ void sts_v4f(uint32_t addr, float a, float b, float c
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// out[tile] += staging tile, the f32 addition done by the L2 (cp.reduce.async.bulk.tensor .add): an in-place residual
+// (x = x + linear(..)) never enters the SM.  One IEEE round-to-nearest addition per element, operands commute, so the
+// result is bit-identical to __fadd_rn(x, v) in the epilogue (checked by the bit-exact network tests).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -395,7 +404,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const bool vcol_ok = gcol0 + vq * 4 < N;               // N % 4 == 0 on this path: a float4 is all-in or all-out
                 const long long vbase = (long long)(first_row + vr) * N + gcol0 + vq * 4;
                 float4 res1[8], res2[8];
-                if ((HAS_R1 || HAS_R2) && vec_io) {
+                if ((HAS_R1 || HAS_R2) && (vec_io || TMA_OUT)) {     // (TMA_OUT: the host has checked the 16-byte alignment)
                     if (MODE == EPI_R1) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it)
@@ -478,10 +487,28 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), __uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
                 }
                 if (TMA_OUT) {
+                    if (MODE == EPI_R1) {
+                        // + add1 in the staging tile: lane = (row % 4, 16-byte column chunk) as the residual registers were loaded;
+                        // every lane rewrites exactly the 16 bytes it read (rows >= nrows / columns >= N are clipped by the store)
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + vr;
+                            if (vcol_ok && rr < nrows) {
+                                const uint32_t ad = tile_s + (uint32_t)rr * 128u + (((uint32_t)vq ^ (uint32_t)(rr & 7)) << 4);
+                                const int4 raw = lds_v4(ad);
+                                sts_v4f(ad, __fadd_rn(__int_as_float(raw.x), res1[it].x), __fadd_rn(__int_as_float(raw.y), res1[it].y),
+                                        __fadd_rn(__int_as_float(raw.z), res1[it].z), __fadd_rn(__int_as_float(raw.w), res1[it].w));
+                            }
+                        }
+                    }
                     if (!v_only_vt) {
                         fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
                         __syncwarp();
-                        if (lane == 0) tma_store_2d(&tmap_out, tile_s, gcol0, first_row);
+                        if (lane == 0) {
+                            if ((MODE == EPI_R1 || MODE == EPI_PLAIN) && args.red) tma_reduce_add_2d(&tmap_out, tile_s, gcol0, first_row);
+                            else tma_store_2d(&tmap_out, tile_s, gcol0, first_row);
+                        }
                     }
                     if (MODE == EPI_QKV) {
                         // operand preparation for the attention kernel: the v columns are also written transposed (V^T, keys
@@ -1091,14 +1118,22 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     args.vec_io = (N % 4 == 0) && ((((uintptr_t)ep.out | (uintptr_t)ep.add1 | (uintptr_t)ep.add2) & 15) == 0) && !getenv("LELE_B200_GEMM_NO_VEC_IO");
     int tiles = args.num_m_blocks * args.num_n_blocks;
     int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    // In-place residual (x = x + (linear [+ add1]): add2 == out): the tile is reduce-added into `out` by the TMA engine / L2, so the
+    // residual stream is neither loaded into nor stored from registers; what is left is the plain (or + add1) epilogue with a TMA store.
+    const bool tma_ok = N % 4 == 0 && (((uintptr_t)ep.out | (uintptr_t)ep.add1) & 15) == 0 && !getenv("LELE_B200_GEMM_NO_TMA_STORE");
+    const bool r1_flag = lb_env_flag("LELE_B200_GEMM_R1_TMA", 1);
+    const bool red = ep.out && ep.add2 == ep.out && tma_ok && !ep.relu && !ep.minmax_keys && !ep.argmax_keys && !ep.q_out && !ep.vt &&
+                     (!ep.add1 || r1_flag) && lb_env_flag("LELE_B200_GEMM_RED", 1);
+    const bool r1_tma = ep.out && ep.add1 && (!ep.add2 || red) && tma_ok && r1_flag;
+    args.red = red ? 1 : 0;
     int mode = EPI_PLAIN;
     if (ep.q_out) mode = EPI_QUANT;
     else if (ep.vt) mode = EPI_QKV;
     else if (ep.argmax_keys) mode = EPI_ARGMAX;
     else if (ep.minmax_keys) mode = EPI_MINMAX;
-    else if (ep.add1 && ep.add2) mode = EPI_R12;
+    else if (ep.add1 && ep.add2 && !red) mode = EPI_R12;
     else if (ep.add1) mode = EPI_R1;
-    else if (ep.add2) mode = EPI_R2;
+    else if (ep.add2 && !red) mode = EPI_R2;
     LB_REQUIRE(!(ep.minmax_keys && (ep.add1 || ep.add2)), "gemm_i8_tc: fused min/max with residual adds is not instantiated");
     LB_REQUIRE(ep.out || mode == EPI_ARGMAX || mode == EPI_MINMAX || mode == EPI_QUANT, "gemm_i8_tc: no output requested");
     LB_REQUIRE(!ep.relu || mode == EPI_PLAIN || mode == EPI_MINMAX || mode == EPI_QUANT, "gemm_i8_tc: ReLU is only instantiated for the plain / min-max / quantising epilogues");
@@ -1113,8 +1148,9 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
                    !ep.minmax_keys && !ep.argmax_keys && !getenv("LELE_B200_GEMM_NO_TMA_STORE"),
                    "gemm_i8_tc: fused attention-operand epilogue needs N = 3 * heads * 128 and the V^T buffers");
     }
-    const bool tma_out = (mode == EPI_PLAIN || mode == EPI_MINMAX || mode == EPI_QKV) && ep.out && N % 4 == 0 && (((uintptr_t)ep.out) & 15) == 0 &&
-                         !getenv("LELE_B200_GEMM_NO_TMA_STORE");
+    const bool tma_out = ((mode == EPI_PLAIN || mode == EPI_MINMAX || mode == EPI_QKV) && ep.out && N % 4 == 0 && (((uintptr_t)ep.out) & 15) == 0 &&
+                          !getenv("LELE_B200_GEMM_NO_TMA_STORE")) || (mode == EPI_R1 && r1_tma);
+    LB_REQUIRE(!red || tma_out, "gemm_i8_tc: the in-place residual epilogue needs the TMA store path");
     CUtensorMap tout = ta, tlo = ta;
     if (mode == EPI_QUANT) {
         rc = cached_tmap_out_u8(ctx, &tout, ep.q_out, M, N);
@@ -1142,7 +1178,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
         case EPI_PLAIN: if (tma_out) LB_LAUNCH_RELU(EPI_PLAIN, true) else LB_LAUNCH_RELU(EPI_PLAIN, false) break;
         case EPI_MINMAX: if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
         case EPI_ARGMAX: LB_LAUNCH_MODE(EPI_ARGMAX, false) break;
-        case EPI_R1: LB_LAUNCH_MODE(EPI_R1, false) break;
+        case EPI_R1: if (tma_out) LB_LAUNCH_MODE(EPI_R1, true) else LB_LAUNCH_MODE(EPI_R1, false) break;
         case EPI_R2: LB_LAUNCH_MODE(EPI_R2, false) break;
         case EPI_R12: LB_LAUNCH_MODE(EPI_R12, false) break;
         case EPI_QKV: LB_LAUNCH_MODE(EPI_QKV, true) break;

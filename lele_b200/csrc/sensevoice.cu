@@ -156,6 +156,49 @@ fsmn_vt_kernel(const float* __restrict__ vt, const float* __restrict__ w, int T,
     }
 }
 
+// v2 of the block above: division-free staging (a warp copies whole channel rows), and each warp walks ONE contiguous time segment with
+// the K-tap window in registers (one shared-memory read per output instead of K; the taps that fall outside [0, T) read 0.0f: adding
+// w * 0 = +-0 to a sum that started at +0 never changes it, so the result equals the tap-skipping loop bit for bit).
+template <int K>
+__global__ void __launch_bounds__(256)
+fsmn_vt_win_kernel(const float* __restrict__ vt, const float* __restrict__ w, int T, int Tp, int d, float* __restrict__ out) {
+    extern __shared__ float fs_tile[];                 // [32][Tp + 1]
+    constexpr int PAD = (K - 1) / 2;
+    const int b = blockIdx.y, c0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pitch = Tp + 1;
+    const float* src = vt + ((size_t)b * d + c0) * (size_t)Tp;
+    for (int ch = warp; ch < 32; ch += 8)
+        for (int t = lane; t < Tp; t += 32) fs_tile[ch * pitch + t] = __ldg(src + (size_t)ch * Tp + t);
+    float wk[K];
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) wk[kk] = __ldg(w + (size_t)(c0 + lane) * K + kk);
+    __syncthreads();
+    const float* row = fs_tile + lane * pitch;
+    const int seg = (T + 7) >> 3;
+    const int t0 = warp * seg, t1 = min(t0 + seg, T);
+    if (t0 >= t1) return;
+    float win[K];                                      // win[(tt + kk) % K] = v[tt + kk - PAD] while step tt is computed
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) { const int pos = t0 + kk - PAD; win[kk] = (pos >= 0 && pos < T) ? row[pos] : 0.0f; }
+    float* op = out + ((size_t)b * T + t0) * d + c0 + lane;
+    for (int base = t0; base < t1; base += K) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {                  // compile-time rotation of the window registers
+            const int tt = base + j;
+            if (tt < t1) {
+                float s = 0.0f;
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) s = __fadd_rn(s, __fmul_rn(wk[kk], win[(j + kk) % K]));
+                *op = __fadd_rn(s, win[(j + PAD) % K]);
+                op += d;
+                const int nx = tt + K - PAD;           // the element that enters the window for step tt + 1
+                win[j % K] = nx < T ? row[nx] : 0.0f;
+            }
+        }
+    }
+}
+
 __global__ void scale_copy_q_kernel(const float* __restrict__ qkv, long long M, int d, float qscale, float* __restrict__ q) {
     const long long total = M * d;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -215,6 +258,8 @@ struct lele_b200_sensevoice {
     void* qscratch = nullptr;
     void* qscratch2 = nullptr;        // second quantised-operand set: FFN1's fused output quantiser writes it while reading the first
     void* attn_scratch = nullptr;
+    int fsmn_v2 = 1;                  // FSMN block: register-window kernel (LELE_B200_FSMN_V2=0 -> the tap-gathering kernel)
+    int fsmn_fork = 1;                // FSMN block on the side stream (LELE_B200_FSMN_FORK=0: in line, before attention)
     int ffn_onepass = 1;              // FFN1 in ONE pass (dequantised tile parked in TMEM until the clip's max is known); LELE_B200_FFN_FUSED=0 -> two passes
     int ffn_twopass = 1;              // FFN1 as max-only pass + quantising pass (no f32 [M, ffn] round trip); LELE_B200_FFN_TWOPASS=0 disables
     int fuse_lnq = 1;                 // LayerNorm + quantiser fused for the encoder width (LELE_B200_FUSE_LNQ=0 disables)
@@ -414,6 +459,8 @@ extern "C" int lele_b200_sensevoice_create(lele_b200_ctx* ctx, const uint8_t* bl
     if (!rc) rc = sv_alloc(&m->qscratch2, lb_quant_scratch_bytes((long long)M, kmax) + 4096 * lele_b200_sensevoice::MAX_LANES);
     { const char* e = getenv("LELE_B200_FFN_TWOPASS"); m->ffn_twopass = (e && e[0] == '0') ? 0 : 1; }
     m->ffn_onepass = lb_env_flag("LELE_B200_FFN_FUSED", 1) ? 1 : 0;
+    m->fsmn_fork = lb_env_flag("LELE_B200_FSMN_FORK", 1) ? 1 : 0;
+    m->fsmn_v2 = lb_env_flag("LELE_B200_FSMN_V2", 1) ? 1 : 0;
     m->ln_stream = lb_env_flag("LELE_B200_LNQ_STREAM", 0) ? 1 : 0;   // measured: 12 us in-kernel but 26 us in the replayed step (a 192 KB persistent CTA cannot start under its predecessor's tail; the 70 KB cluster CTAs can) -> opt-in
     m->lane_split = lb_env_flag("LELE_B200_LANE_SPLIT", 0) ? 1 : 0;     // measured (2 lanes x 74 SMs): 3.54 vs 3.22 ms on the 8-layer stack -> opt-in
     if (!rc) rc = sv_alloc(&m->attn_scratch, lb_attention_tc_scratch_bytes(max_clips, m->max_T, m->d, m->heads));
@@ -548,7 +595,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
                                    m->lin[l * 4 + 0], qs, ep, P_G_QKV);
             if (rc_) return rc_;
         }
-        const bool fork = !m->profiling && m->side != nullptr;
+        const bool fork = !m->profiling && m->side != nullptr && m->fsmn_fork;
         cudaStream_t fs = fork ? m->side : ctx->stream;
         if (fork) {
             LB_CHECK_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
@@ -558,7 +605,8 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
             ProfScope ps(m, ctx, P_FSMN);
             if (fsmn_from_vt) {
                 const size_t sm = sizeof(float) * 32 * (size_t)(vt_tp + 1);
-                fsmn_vt_kernel<11><<<dim3(d / 32, B), 256, sm, fs>>>(vt_ptr, (const float*)m->lt(l, SV_L_FSMN_W), T, vt_tp, d, m->fsmn);
+                if (m->fsmn_v2) fsmn_vt_win_kernel<11><<<dim3(d / 32, B), 256, sm, fs>>>(vt_ptr, (const float*)m->lt(l, SV_L_FSMN_W), T, vt_tp, d, m->fsmn);
+                else fsmn_vt_kernel<11><<<dim3(d / 32, B), 256, sm, fs>>>(vt_ptr, (const float*)m->lt(l, SV_L_FSMN_W), T, vt_tp, d, m->fsmn);
             } else if (m->fsmn_k == 11)
                 fsmn_window_kernel<11><<<dim3(lb_ceil_div(d, 128), lb_ceil_div(T, FS_TCH), B), 128, 0, fs>>>(
                     m->qkv, (const float*)m->lt(l, SV_L_FSMN_W), T, d, m->fsmn);
