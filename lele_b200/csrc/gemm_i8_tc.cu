@@ -87,6 +87,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_s(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -209,15 +214,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint64_t* tmem_full = bars + 2 * MAX_STAGES;   // [2]    MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;          // [2]    epilogue -> MMA
     uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+    uint64_t* res_bar = bars + 16;                 // [NUM_EPI_WARPS] EPI_R1 + TMA_OUT: the warp's residual sub-tile landed (TMA load into its staging tile)
+    constexpr bool R1T = (MODE == EPI_R1) && TMA_OUT;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = args.num_m_blocks * args.num_n_blocks;
     // tile walk: tile = blockIdx.x + i * gridDim.x -> (m_blk, n_blk) = (tile / nnb, tile % nnb)
 
-    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); }
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); if (R1T) prefetch_tmap(&tmap_lo); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
+        if (R1T) for (int s = 0; s < NUM_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -304,6 +312,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const float FMAX = 3.402823466e+38f;
         const bool vec_io = !TMA_OUT && args.vec_io;       // rows 16-byte aligned: float4 residual loads / output stores
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t res_phase = 0;
         long long w_acc = 0, t_busy0 = 0, busy = 0, d_ld = 0, d_math = 0; const long long t_begin = clock64();
         int pf_rs = 0, pf_zpa = 0, pf_cs[2] = {0, 0}; float pf_sa = 0.0f, pf_ws[2] = {0.0f, 0.0f}, pf_bi[2] = {0.0f, 0.0f};
         unsigned pf_qkey = 0;                                          // EPI_QUANT: one min/max key slot of the warp's clip A (lanes 0-15) / A+1 (16-31)
@@ -388,14 +397,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const int gcol0 = n_blk * BN + col0;                   // global column
                 uint32_t r[32];
                 long long t_c0 = 0;
+                const bool skip_chunk = gcol0 >= N || nrows <= 0;      // warp-uniform
+                if (R1T && !skip_chunk && lane == 0) {
+                    // the residual sub-tile (add1) is fetched by TMA into the warp's staging tile -- in the layout the output
+                    // leaves it in -- while the accumulator is loaded and dequantised: no residual registers, no exposed latency
+                    tma_store_wait_read();                             // the previous store has read the staging tile
+                    mbar_expect_tx(&res_bar[ew], EPI_TILE_BYTES);
+                    tma_load_2d_s(tile_s, &tmap_lo, &res_bar[ew], gcol0, first_row);
+                }
                 if (GEMM_DBG && args.dbg) t_c0 = clock64();
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0), r);
                 if (GEMM_DBG && args.dbg) { const long long t1 = clock64(); d_ld += t1 - t_c0; t_c0 = t1; }
-                if (gcol0 >= N || nrows <= 0) continue;                // warp-uniform
-                if (TMA_OUT) {                                         // the previous store must have read the staging tile
-                    if (lane == 0) tma_store_wait_read();
-                    __syncwarp();
-                }
+                if (skip_chunk) continue;
                 // Residual epilogues: 128-bit accesses, lane = (row % 4, 16-byte column chunk), 4 rows x 128 B per warp
                 // instruction, and every residual load of the sub-tile is issued before the accumulator math so that
                 // 4 KB (8 KB for two residuals) per warp is in flight while phase 1 runs.
@@ -404,7 +417,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const bool vcol_ok = gcol0 + vq * 4 < N;               // N % 4 == 0 on this path: a float4 is all-in or all-out
                 const long long vbase = (long long)(first_row + vr) * N + gcol0 + vq * 4;
                 float4 res1[8], res2[8];
-                if ((HAS_R1 || HAS_R2) && (vec_io || TMA_OUT)) {     // (TMA_OUT: the host has checked the 16-byte alignment)
+                if ((HAS_R1 || HAS_R2) && vec_io) {
                     if (MODE == EPI_R1) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it)
@@ -467,6 +480,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         pk[q] = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
                         q_sum = (int)__dp4a(pk[q], 0x01010101u, (unsigned)q_sum);
                     }
+                    if (lane == 0) tma_store_wait_read();              // the previous store has read the staging tile (waited for after the
+                    __syncwarp();                                      // math, so that the read overlaps it)
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_s + (uint32_t)lane * 32u + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
                     fence_proxy_async();
@@ -481,27 +496,26 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 // QKV projection with skip_v_out: the v columns leave the SM only as V^T (below), not through the staging tile
                 const bool v_only_vt = MODE == EPI_QKV && ep.skip_v_out && gcol0 >= 2 * (N / 3);
-                if (!v_only_vt) {
+                if (R1T) {
+                    mbar_wait(&res_bar[ew], res_phase);                // add1's sub-tile is in the staging tile: add it row-wise, in place
+                    res_phase ^= 1;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t ad = my_row_s + (((uint32_t)q ^ sw) << 4);
+                        const int4 raw = lds_v4(ad);
+                        sts_v4f(ad, __fadd_rn(__uint_as_float(r[q * 4 + 0]), __int_as_float(raw.x)), __fadd_rn(__uint_as_float(r[q * 4 + 1]), __int_as_float(raw.y)),
+                                __fadd_rn(__uint_as_float(r[q * 4 + 2]), __int_as_float(raw.z)), __fadd_rn(__uint_as_float(r[q * 4 + 3]), __int_as_float(raw.w)));
+                    }
+                } else if (!v_only_vt) {
+                    if (TMA_OUT) {                                     // the previous store must have read the staging tile (waited for
+                        if (lane == 0) tma_store_wait_read();          // after the math, so that the read overlaps it)
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         sts_v4f(my_row_s + (((uint32_t)q ^ sw) << 4), __uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
                 }
                 if (TMA_OUT) {
-                    if (MODE == EPI_R1) {
-                        // + add1 in the staging tile: lane = (row % 4, 16-byte column chunk) as the residual registers were loaded;
-                        // every lane rewrites exactly the 16 bytes it read (rows >= nrows / columns >= N are clipped by the store)
-                        __syncwarp();
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int rr = it * 4 + vr;
-                            if (vcol_ok && rr < nrows) {
-                                const uint32_t ad = tile_s + (uint32_t)rr * 128u + (((uint32_t)vq ^ (uint32_t)(rr & 7)) << 4);
-                                const int4 raw = lds_v4(ad);
-                                sts_v4f(ad, __fadd_rn(__int_as_float(raw.x), res1[it].x), __fadd_rn(__int_as_float(raw.y), res1[it].y),
-                                        __fadd_rn(__int_as_float(raw.z), res1[it].z), __fadd_rn(__int_as_float(raw.w), res1[it].w));
-                            }
-                        }
-                    }
                     if (!v_only_vt) {
                         fence_proxy_async();                           // generic-proxy smem writes -> visible to the TMA engine
                         __syncwarp();
@@ -1164,6 +1178,10 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     }
     if (mode == EPI_QKV) {
         LB_REQUIRE(tma_out, "gemm_i8_tc: fused attention-operand epilogue needs a 16-byte aligned output");
+    }
+    if (mode == EPI_R1 && tma_out) {          // add1's sub-tiles are fetched by TMA into the epilogue warps' staging tiles
+        rc = cached_tmap_out_f32(ctx, &tlo, ep.add1, M, N, N);
+        if (rc) return rc;
     }
     // the shared-memory opt-in is recorded per context (= per device), once per instantiation
 #define LB_LAUNCH_MODE4(MD, TM, RL, WS)                                                                                 \
