@@ -200,6 +200,202 @@ fbank_lfr_kernel(const float* __restrict__ pcm, long long clip_stride, int n_cli
     }
 }
 
+// ---------------------------------------------------------------------------
+// fused fbank + LFR, register-blocked FFT (round 2): one warp per frame, the 512-point transform as three radix-8 passes
+// (512 = 8 x 8 x 8, n = 64 n1 + 8 n2 + n3, k = k1 + 8 k2 + 64 k3) with 16 points per lane in registers and two
+// conflict-free exchanges through shared memory -- 128 shared-memory accesses per lane instead of the radix-2 network's
+// ~600, no bit-reversal scatter, pre-emphasis neighbours by shuffle.  Pass 1 is a real-input butterfly (the frame is real),
+// pass 3 only produces bins 0..256.  Twiddles W64^(n2 k1), W512^(n3 (k1 + 8 k2)) come from tables computed in double.
+// Same frame arithmetic as fbank_lfr_kernel up to the FFT's summation order (|dX| ~ 1e-7 of the spectrum's maximum;
+// the reference's own AVX2 / scalar FFT paths differ from each other at that level, kernels/fft.rs:208).
+// ---------------------------------------------------------------------------
+constexpr int FX_P = 72;                                  // row pitch of the exchange buffers (8 rows x 64 points + padding)
+constexpr float FX_R = 0.70710678118654752440f;           // sqrt(1/2)
+
+// 8-point forward DFT of a real sequence: X[k] = sum_n x[n] W8^(n k)
+__device__ __forceinline__ void fx_dft8_real(const float (&x)[8], float (&yr)[8], float (&yi)[8]) {
+    const float b0 = x[0] + x[4], b1 = x[1] + x[5], b2 = x[2] + x[6], b3 = x[3] + x[7];
+    const float d0 = x[0] - x[4], d1 = x[1] - x[5], d2 = x[2] - x[6], d3 = x[3] - x[7];
+    const float s0 = b0 + b2, s1 = b0 - b2, s2 = b1 + b3, t = b1 - b3;
+    yr[0] = s0 + s2; yi[0] = 0.0f;
+    yr[4] = s0 - s2; yi[4] = 0.0f;
+    yr[2] = s1; yi[2] = -t;
+    yr[6] = s1; yi[6] = t;
+    const float p = (d1 - d3) * FX_R, q = (d1 + d3) * FX_R;
+    yr[1] = d0 + p; yi[1] = -d2 - q;
+    yr[7] = d0 + p; yi[7] = d2 + q;
+    yr[3] = d0 - p; yi[3] = d2 - q;
+    yr[5] = d0 - p; yi[5] = q - d2;
+}
+// 4-point forward DFT (decimation in frequency), outputs in natural order
+__device__ __forceinline__ void fx_dft4(const float (&ar)[4], const float (&ai)[4], float (&yr)[4], float (&yi)[4]) {
+    const float s0r = ar[0] + ar[2], s0i = ai[0] + ai[2], s1r = ar[0] - ar[2], s1i = ai[0] - ai[2];
+    const float s2r = ar[1] + ar[3], s2i = ai[1] + ai[3], ur = ar[1] - ar[3], ui = ai[1] - ai[3];
+    yr[0] = s0r + s2r; yi[0] = s0i + s2i;
+    yr[2] = s0r - s2r; yi[2] = s0i - s2i;
+    yr[1] = s1r + ui;  yi[1] = s1i - ur;                  // s1 + (-i) u
+    yr[3] = s1r - ui;  yi[3] = s1i + ur;
+}
+// 8-point forward DFT of a complex sequence
+__device__ __forceinline__ void fx_dft8(const float (&xr)[8], const float (&xi)[8], float (&yr)[8], float (&yi)[8]) {
+    float br[4], bi[4], cr[4], ci[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { br[n] = xr[n] + xr[n + 4]; bi[n] = xi[n] + xi[n + 4]; }
+    const float d0r = xr[0] - xr[4], d0i = xi[0] - xi[4], d1r = xr[1] - xr[5], d1i = xi[1] - xi[5];
+    const float d2r = xr[2] - xr[6], d2i = xi[2] - xi[6], d3r = xr[3] - xr[7], d3i = xi[3] - xi[7];
+    cr[0] = d0r;                 ci[0] = d0i;             // c_n = d_n W8^n
+    cr[1] = (d1r + d1i) * FX_R;  ci[1] = (d1i - d1r) * FX_R;
+    cr[2] = d2i;                 ci[2] = -d2r;
+    cr[3] = (d3i - d3r) * FX_R;  ci[3] = (-d3r - d3i) * FX_R;
+    float er[4], ei[4], orr[4], oi[4];
+    fx_dft4(br, bi, er, ei);
+    fx_dft4(cr, ci, orr, oi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { yr[2 * j] = er[j]; yi[2 * j] = ei[j]; yr[2 * j + 1] = orr[j]; yi[2 * j + 1] = oi[j]; }
+}
+
+__global__ void __launch_bounds__(FB_WARPS * 32)
+fbank_lfr_r8_kernel(const float* __restrict__ pcm, long long clip_stride, int n_clips, int frames, int t_lfr,
+                    FbankTables tb, const float2* __restrict__ tw64, const float2* __restrict__ tw512,
+                    float* __restrict__ mel_opt, float* __restrict__ lfr_out) {
+    __shared__ float s_re[FB_WARPS][8 * FX_P];
+    __shared__ float s_im[FB_WARPS][8 * FX_P];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gframe = (long long)blockIdx.x * FB_WARPS + warp;
+    if (gframe >= (long long)n_clips * frames) return;   // whole warp exits together
+    const int clip = (int)(gframe / frames), f = (int)(gframe % frames);
+    float* re = s_re[warp];
+    float* im = s_im[warp];
+    const float* p = pcm + (long long)clip * clip_stride + (long long)f * FB_HOP;
+
+    // 1. scale (x32768) and frame mean; 2. mean subtraction (same operation order as fbank_lfr_kernel)
+    float x[13];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        const int j = lane + 32 * i;
+        x[i] = j < FB_FL ? __fmul_rn(__ldg(p + j), 32768.0f) : 0.0f;
+        sum += x[i];
+    }
+    sum = lb_warp_sum(sum);
+    const float mean = __fdiv_rn(sum, (float)FB_FL);
+#pragma unroll
+    for (int i = 0; i < 13; ++i) x[i] = __fsub_rn(x[i], mean);
+    // 3. pre-emphasis against the un-emphasised neighbour (sample j - 1 lives in the lane below, or in lane 31 of the
+    //    previous register), 4. Hann window; samples 400..511 are the zero padding
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        const int j = lane + 32 * i;
+        const float up = __shfl_up_sync(0xffffffffu, x[i], 1);
+        const float wrap = i > 0 ? __shfl_sync(0xffffffffu, x[i - 1], 31) : 0.0f;
+        const float prev = lane == 0 ? wrap : up;
+        float cur = x[i];
+        if (j >= 1) cur = __fsub_rn(cur, __fmul_rn(0.97f, prev));
+        v[i] = j < FB_FL ? __fmul_rn(cur, __ldg(tb.window + j)) : 0.0f;
+    }
+    v[13] = 0.0f; v[14] = 0.0f; v[15] = 0.0f;
+
+    // 5a. pass 1: point j = lane + 32 i = 64 n1 + m with m = lane + 32 (i & 1), n1 = i >> 1: two real 8-point transforms over n1,
+    //     times W64^(n2 k1) (n2 = m >> 3), stored as A[k1][m]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float in[8], yr[8], yi[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) in[n1] = v[2 * n1 + h];
+        fx_dft8_real(in, yr, yi);
+        const int m = lane + 32 * h, n2 = m >> 3;
+        re[m] = yr[0]; im[m] = yi[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) {
+            const float2 w = __ldg(tw64 + ((n2 * k1) & 63));
+            re[k1 * FX_P + m] = yr[k1] * w.x - yi[k1] * w.y;
+            im[k1 * FX_P + m] = yr[k1] * w.y + yi[k1] * w.x;
+        }
+    }
+    __syncwarp();
+    // 5b. pass 2: the lane owns (k1, n3) = (lane / 8 + 4 h, lane % 8): 8-point transforms over n2, times W512^(n3 (k1 + 8 k2)),
+    //     stored as B[k1][k2 + 9 n3] (both passes read every input before the buffer is rewritten)
+    {
+        const int n3 = lane & 7;
+        float ar[2][8], ai[2][8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k1 = (lane >> 3) + 4 * h;
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) { ar[h][n2] = re[k1 * FX_P + n2 * 8 + n3]; ai[h][n2] = im[k1 * FX_P + n2 * 8 + n3]; }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k1 = (lane >> 3) + 4 * h;
+            float yr[8], yi[8];
+            fx_dft8(ar[h], ai[h], yr, yi);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const float2 w = __ldg(tw512 + ((n3 * (k1 + 8 * k2)) & 511));
+                re[k1 * FX_P + k2 + 9 * n3] = yr[k2] * w.x - yi[k2] * w.y;
+                im[k1 * FX_P + k2 + 9 * n3] = yr[k2] * w.y + yi[k2] * w.x;
+            }
+        }
+    }
+    __syncwarp();
+    // 5c. pass 3: the lane owns (k1, k2) = (lane / 8 + 4 h, lane % 8): 8-point transforms over n3 give X[k1 + 8 k2 + 64 k3];
+    // 6.  power spectrum of bins 0..256 (Im(0) = Im(256) = 0 as in kernels/fft.rs:124-128) into re[0..256]
+    {
+        const int k2 = lane & 7;
+        float ar[2][8], ai[2][8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k1 = (lane >> 3) + 4 * h;
+#pragma unroll
+            for (int n3 = 0; n3 < 8; ++n3) { ar[h][n3] = re[k1 * FX_P + k2 + 9 * n3]; ai[h][n3] = im[k1 * FX_P + k2 + 9 * n3]; }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k1 = (lane >> 3) + 4 * h;
+            float yr[8], yi[8];
+            fx_dft8(ar[h], ai[h], yr, yi);
+            const int k0 = k1 + 8 * k2;
+#pragma unroll
+            for (int k3 = 0; k3 < 4; ++k3) {
+                const float r = yr[k3], q = (k0 == 0 && k3 == 0) ? 0.0f : yi[k3];
+                re[k0 + 64 * k3] = __fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q));
+            }
+            if (k0 == 0) re[256] = __fmul_rn(yr[4], yr[4]);
+        }
+    }
+    __syncwarp();
+    // 7. sparse mel (sequential tap order, mel.rs:92-104) + log(max(x, 1e-5))
+    for (int mI = lane; mI < FB_NM; mI += 32) {
+        int s = __ldg(tb.mel_start + mI), len = __ldg(tb.mel_len + mI), off = __ldg(tb.mel_off + mI);
+        float acc = 0.0f;
+        for (int t = 0; t < len; ++t) acc = __fadd_rn(acc, __fmul_rn(__ldg(tb.mel_w + off + t), re[s + t]));
+        im[mI] = logf(fmaxf(acc, 1e-5f));
+    }
+    __syncwarp();
+    // 8. outputs: raw mel frame (optional) and every LFR slot that clamps onto this frame
+    if (mel_opt) {
+        float* mo = mel_opt + ((long long)clip * frames + f) * FB_NM;
+        for (int c = lane; c < FB_NM; c += 32) mo[c] = im[c];
+    }
+    int i_lo = (f - 3 + 5) / 6 - 1; if (i_lo < 0) i_lo = 0;          // rows i with 6i-3 <= f
+    int i_hi = (f == frames - 1) ? t_lfr - 1 : (f + 3) / 6;           // last frame absorbs the clamp
+    if (i_hi > t_lfr - 1) i_hi = t_lfr - 1;
+    for (int i = i_lo; i <= i_hi; ++i) {
+#pragma unroll
+        for (int b = 0; b < 7; ++b) {
+            int raw = i * 6 + b - 3;
+            int c = raw < 0 ? 0 : (raw > frames - 1 ? frames - 1 : raw);
+            if (c == f) {
+                float* dst = lfr_out + ((long long)clip * t_lfr + i) * (7 * FB_NM) + b * FB_NM;
+                for (int q = lane; q < FB_NM; q += 32) dst[q] = im[q];
+            }
+        }
+    }
+}
+
 static int get_fft_tables(lele_b200_ctx* ctx, int n, const float** tw_re, const float** tw_im, const int** br) {
     std::string key = "fft" + std::to_string(n);
     void* p = nullptr;
@@ -263,8 +459,21 @@ extern "C" int lele_b200_frontend_compute(lele_b200_ctx* ctx, const float* pcm, 
     int rc = get_fbank_tables(ctx, &tb);
     if (rc) return rc;
     long long total = (long long)n_clips * frames;
-    fbank_lfr_kernel<<<lb_ceil_div(total, FB_WARPS), FB_WARPS * 32, 0, ctx->stream>>>(
-        pcm, clip_stride, n_clips, frames, t_lfr, tb, mel_opt, lfr_out);
+    if (lb_env_flag("LELE_B200_FBANK_R8", 1)) {
+        void* tw = nullptr;                                     // W64^k | W512^k as float2, computed in double
+        auto it = ctx->tables.find("fft512r8");
+        if (it == ctx->tables.end()) {
+            std::vector<float> h(2 * (64 + 512));
+            for (int k = 0; k < 64; ++k) { h[2 * k] = (float)cos(-2.0 * M_PI * k / 64.0); h[2 * k + 1] = (float)sin(-2.0 * M_PI * k / 64.0); }
+            for (int k = 0; k < 512; ++k) { h[128 + 2 * k] = (float)cos(-2.0 * M_PI * k / 512.0); h[128 + 2 * k + 1] = (float)sin(-2.0 * M_PI * k / 512.0); }
+            rc = lb_table(ctx, "fft512r8", h.data(), h.size() * sizeof(float), &tw);
+            if (rc) return rc;
+        } else tw = it->second;
+        fbank_lfr_r8_kernel<<<lb_ceil_div(total, FB_WARPS), FB_WARPS * 32, 0, ctx->stream>>>(
+            pcm, clip_stride, n_clips, frames, t_lfr, tb, (const float2*)tw, (const float2*)tw + 64, mel_opt, lfr_out);
+    } else
+        fbank_lfr_kernel<<<lb_ceil_div(total, FB_WARPS), FB_WARPS * 32, 0, ctx->stream>>>(
+            pcm, clip_stride, n_clips, frames, t_lfr, tb, mel_opt, lfr_out);
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
 }
