@@ -92,6 +92,17 @@ __device__ __forceinline__ void tma_load_2d_s(uint32_t smem_dst, const CUtensorM
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// B operand shared by a 2-CTA cluster: each CTA fetches half of the tile and the TMA unit delivers it to BOTH CTAs' shared memory
+// (same CTA-relative offset), signalling each CTA's own mbarrier -- the weight tile crosses the L2 -> SM fabric once per pair.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -124,6 +135,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the same arrival delivered to the barrier at this offset in every CTA of the mask (a shared-memory slot that a peer's multicast
+// load refills may only be released when both CTAs' MMAs have consumed it)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -140,6 +157,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 struct KernelArgs {
     int M, N, K;
     int vec_io;
+    int mc;             // 2-CTA clusters along M share each B tile by TMA multicast (grid = 2 x resident clusters); 0 = independent CTAs
     int red;            // TMA_OUT epilogues: the tile is ADDED to `out` (cp.reduce ... .add) -- the in-place residual x = x + (...)
     int dbg;            // LELE_B200_GEMM_DBG=1: CTAs 0 and 77 print where their producer / MMA / epilogue roles waited (clock64)
     int num_m_blocks, num_n_blocks, num_k_blocks;
@@ -218,12 +236,16 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr bool R1T = (MODE == EPI_R1) && TMA_OUT;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = args.num_m_blocks * args.num_n_blocks;
-    // tile walk: tile = blockIdx.x + i * gridDim.x -> (m_blk, n_blk) = (tile / nnb, tile % nnb)
+    // tile walk: tile = first + i * stride -> (m, n_blk) = (tile / nnb, tile % nnb); m is the m-block, or with multicast clusters the
+    // PAIR of m-blocks the cluster works on (the CTA's own m-block is 2 m + its rank: both CTAs walk the same n-blocks in step)
+    const int mc = args.mc;
+    const int crank = mc ? (int)(blockIdx.x & 1) : 0;
+    const int tile_first = mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_stride = mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int num_tiles = (mc ? (args.num_m_blocks + 1) / 2 : args.num_m_blocks) * args.num_n_blocks;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); if (R1T) prefetch_tmap(&tmap_lo); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], mc ? 2 : 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
         if (R1T) for (int s = 0; s < NUM_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
@@ -234,7 +256,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
-    __syncthreads();
+    if (mc) cluster_sync_all();          // the peer's barriers are initialised before any multicast load / remote arrival can reach them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     // PDL: everything above is independent of the previous kernel's output; everything below reads it
@@ -246,14 +269,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             long long w_empty = 0; const long long t_begin = clock64();
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / args.num_n_blocks, n_blk = tile % args.num_n_blocks;
+            for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
+                const int m_blk = (tile / args.num_n_blocks) * (mc ? 2 : 1) + crank, n_blk = tile % args.num_n_blocks;
                 for (int kb = 0; kb < args.num_k_blocks; ++kb) {
                     if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t0; }
                     else mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (mc)   // tmap_b's box is half a tile here: rows [rank * 128, +128) of the n-block, delivered to both CTAs
+                        tma_load_2d_mc(smem_b + stage * B_STAGE_BYTES + crank * (B_STAGE_BYTES / 2), &tmap_b, &full_bar[stage], kb * BK,
+                                       n_blk * BN + crank * (BN / 2), (uint16_t)3);
+                    else tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
@@ -266,7 +292,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             long long w_tmem = 0, w_full = 0; const long long t_begin = clock64();
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
                 if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t0; }
                 else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
                 tc_fence_after();
@@ -283,7 +309,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
                                 (kb > 0 || k > 0) ? 1u : 0u, idesc_for(WSIGNED));
                     }
-                    umma_commit(&empty_bar[stage]);                // frees the smem slot when the MMAs retire
+                    if (mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs (the peer refills half of it)
+                    else umma_commit(&empty_bar[stage]);           // frees the smem slot when the MMAs retire
                     if (kb == args.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
@@ -291,7 +318,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
             if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77))
                 printf("GEMMDBG blk %d MMA: total %lld wait_operands %lld wait_epilogue %lld (tiles %d, k-blocks %d)\n", blockIdx.x, clock64() - t_begin, w_full, w_tmem,
-                       (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, args.num_k_blocks);
+                       (num_tiles - tile_first + tile_stride - 1) / tile_stride, args.num_k_blocks);
         }
     } else if (warp >= FIRST_EPI_WARP) {
         // ===================== epilogue: 16 warps, each owns 32 rows x 64 columns of every tile =====================
@@ -320,8 +347,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int rps = args.rps; const float inv_rps = args.inv_rps;
         const int last_slice = div_by_rps(M - 1, rps, inv_rps);
         // tile coordinates advance incrementally (tile += gridDim.x): no per-tile integer divisions
-        const int step_m = (int)gridDim.x / nnb, step_n = (int)gridDim.x % nnb;
-        int m_blk = (int)blockIdx.x / nnb, n_blk = (int)blockIdx.x % nnb;
+        // (m_idx = the m-block, or the cluster's pair of m-blocks; the CTA's own m-block follows from it)
+        const int step_m = tile_stride / nnb, step_n = tile_stride % nnb;
+        int m_idx = tile_first / nnb, n_blk = tile_first % nnb;
+        const int mmul = mc ? 2 : 1;
+        int m_blk = m_idx * mmul + crank;
         auto fetch_meta = [&](int t, int mb, int nb) {
             if (t >= num_tiles) return;
             const int rw = mb * BM + quad * 32 + lane;
@@ -337,8 +367,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 pf_cs[hh] = __ldg(ep.colsum + cc); pf_ws[hh] = __ldg(ep.w_scale + cc); pf_bi[hh] = __ldg(ep.bias + cc);
             }
         };
-        fetch_meta(blockIdx.x, m_blk, n_blk);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        fetch_meta(tile_first, m_blk, n_blk);
+        for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
             const int first_row = m_blk * BM + quad * 32;
             const int row = first_row + lane;
             const bool row_ok = row < M;
@@ -380,9 +410,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 q_inv = __fdiv_rn(1.0f, q_scale);
             }
             {   // next tile's coordinates and metadata (consumed one iteration later)
-                int mb_n = m_blk + step_m, nb_n = n_blk + step_n;
-                if (nb_n >= nnb) { nb_n -= nnb; ++mb_n; }
-                fetch_meta(tile + (int)gridDim.x, mb_n, nb_n);
+                int mi_n = m_idx + step_m, nb_n = n_blk + step_n;
+                if (nb_n >= nnb) { nb_n -= nnb; ++mi_n; }
+                fetch_meta(tile + tile_stride, mi_n * mmul + crank, nb_n);
             }
             float best_t = -3.402823466e+38f; int best_c = -1;
             float vmin = FMAX, vmax = -FMAX;                           // this row's min / max over the warp's 64 columns
@@ -627,8 +657,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
             }
             if (MODE == EPI_ARGMAX && row_ok && best_c >= 0) atomicMax(ep.argmax_keys + row, ((unsigned long long)lb_fkey_argmax(best_t) << 32) | (unsigned)best_c);
-            m_blk += step_m; n_blk += step_n;
-            if (n_blk >= nnb) { n_blk -= nnb; ++m_blk; }
+            m_idx += step_m; n_blk += step_n;
+            if (n_blk >= nnb) { n_blk -= nnb; ++m_idx; }
+            m_blk = m_idx * mmul + crank;
         }
         if (TMA_OUT && lane == 0) tma_store_wait_all();                // staging smem must outlive the bulk stores
         if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (ew == 0 || ew == 15))
@@ -636,7 +667,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (mc) cluster_sync_all();          // no CTA leaves while its peer can still signal its barriers
+    else __syncthreads();
     if (GEMM_DBG && args.dbg && threadIdx.x == 0) {
         unsigned long long t1; unsigned smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -689,6 +721,7 @@ struct FusedArgs {
     int GT;               // rows per group (G clips)
     int n_groups, n_clips;
     int dbg;              // LELE_B200_GEMM_DBG=1 in a -DLELE_B200_GEMM_TIMELINE build: CTAs 0 / 77 print where their epilogue waited
+    int prefetch;         // early look-up of the quantiser parameters (LELE_B200_FFN_PREFETCH=0: always the blocking wait)
     LbI8Epilogue ep;
 };
 
@@ -848,8 +881,47 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         };
         fetch_rows(0);
 
+        // The quantising pass of a group needs its clips' arrival counters (an acquire load) and then their key slots: two dependent
+        // L2 round trips in front of every tile.  They are issued EARLY instead -- at the end of the pass that runs before it, when the
+        // warp would otherwise sit at the CTA barrier and the group's last arrivals are a whole pass old -- and kept in registers
+        // (pre_*); if the clips were not complete yet, the quantising pass falls back to the blocking wait.
+        int pre_g = -1; float pre_scale = 0.0f, pre_zp = 0.0f, pre_inv = 0.0f;
+        auto clip_expect = [&](const Geo& q, int cl) {         // CTAs that arrive for clip cl: nnb column blocks x the m-blocks the clip spans
+            const int a = max(cl * T, q.g0) - q.g0, b = min((cl + 1) * T, q.gend) - q.g0;
+            return (((b - 1) >> 7) - (a >> 7) + 1) * nnb;
+        };
+        auto clip_params = [&](const Geo& q, float& q_scale, float& q_zp, float& q_inv) {
+            // lanes 0-15 hold the 8 (min, max) key slots of clip A, lanes 16-31 those of clip A+1
+            const int sl = min(q.sl_a + (lane >> 4), args.n_clips - 1);
+            unsigned k = __ldcg(ep.fq_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
+#pragma unroll
+            for (int of = 2; of <= 8; of <<= 1) {
+                const unsigned o = __shfl_xor_sync(0xffffffffu, k, of);
+                k = (lane & 1) ? max(k, o) : min(k, o);
+            }
+            const int src = q.in_a ? 0 : 16;
+            const float mn = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src)), mx = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src + 1));
+            const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);          // dq_params (quant.cu)
+            q_scale = __fdiv_rn(fmaxf(__fsub_rn(amax, amin), 1e-5f), 255.0f);
+            q_zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, q_scale)), 0.0f), 255.0f);
+            q_inv = __fdiv_rn(1.0f, q_scale);
+        };
+        auto prefetch_params = [&](int g) {
+            pre_g = -1;
+            if (g < 0 || g >= n_act || !args.prefetch) return;
+            const Geo q = geometry(g);
+            if (!(q.nrows > 0 && cols_ok)) return;
+            int done = 1;
+            if (lane == 0)
+                for (int cl = q.sl_a; cl <= q.sl_a + (q.all_a ? 0 : 1); ++cl)
+                    if (ld_acquire_gpu(ep.fq_counters + cl) < clip_expect(q, cl)) done = 0;
+            if (!__shfl_sync(0xffffffffu, done, 0)) return;
+            clip_params(q, pre_scale, pre_zp, pre_inv);
+            pre_g = g;
+        };
+
         // ---- max pass of group g ----
-        auto max_pass = [&](int g) {
+        auto max_pass = [&](int g, int prefetch_g) {
             const long long t_me0 = GEMM_DBG ? clock64() : 0;
             const int s = g & 1; const uint32_t ph = (uint32_t)(g >> 1) & 1u;
             const Geo q = geometry(g);
@@ -914,6 +986,7 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     if (lane == 0) { atomicMin(slot + 2, mnB); atomicMax(slot + 3, mxB); }
                 }
             }
+            prefetch_params(prefetch_g);                           // (the previous group's quantiser parameters, see above)
             const long long t_b0 = GEMM_DBG ? clock64() : 0;
             epi_bar_sync();                                        // every warp's keys are in the CTA slots
             if (GEMM_DBG) { w_bar += clock64() - t_b0; t_me += clock64() - t_me0; }
@@ -932,42 +1005,30 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         };
 
         // ---- quantising pass of group g ----
-        auto quant_pass = [&](int g) {
+        auto quant_pass = [&](int g, int prefetch_g) {
             const int s = g & 1;
             const Geo q = geometry(g);
             float q_inv = 0.0f, q_zp = 0.0f, q_scale = 0.0f;
             const long long t_qe0 = GEMM_DBG ? clock64() : 0;
             if (q.nrows > 0 && cols_ok) {
-                if (lane == 0) {
-                    // every CTA whose block has rows of the clip arrives once: nnb column blocks x the m-blocks the clip spans
-                    for (int cl = q.sl_a; cl <= q.sl_a + (q.all_a ? 0 : 1); ++cl) {
-                        const int a = max(cl * T, q.g0) - q.g0, b = min((cl + 1) * T, q.gend) - q.g0;
-                        const int expect = (((b - 1) >> 7) - (a >> 7) + 1) * nnb;
-                        if (ld_acquire_gpu(ep.fq_counters + cl) < expect) {
-                            const long long t0 = clock64();
-                            while (ld_acquire_gpu(ep.fq_counters + cl) < expect) {
-                                __nanosleep(64);
-                                if (clock64() - t0 > 4000000000ll) { printf("lele_b200 gemm_i8 fused quantiser: clip %d never completed (block %d)\n", cl, blockIdx.x); __trap(); }
+                if (pre_g == g) { q_scale = pre_scale; q_zp = pre_zp; q_inv = pre_inv; }
+                else {
+                    if (lane == 0) {
+                        for (int cl = q.sl_a; cl <= q.sl_a + (q.all_a ? 0 : 1); ++cl) {
+                            const int expect = clip_expect(q, cl);
+                            if (ld_acquire_gpu(ep.fq_counters + cl) < expect) {
+                                const long long t0 = clock64();
+                                while (ld_acquire_gpu(ep.fq_counters + cl) < expect) {
+                                    __nanosleep(64);
+                                    if (clock64() - t0 > 4000000000ll) { printf("lele_b200 gemm_i8 fused quantiser: clip %d never completed (block %d)\n", cl, blockIdx.x); __trap(); }
+                                }
                             }
                         }
                     }
+                    __syncwarp();
+                    clip_params(q, q_scale, q_zp, q_inv);
                 }
-                __syncwarp();
                 if (GEMM_DBG) w_cnt += clock64() - t_qe0;
-                // lanes 0-15 hold the 8 (min, max) key slots of clip A, lanes 16-31 those of clip A+1
-                const int sl = min(q.sl_a + (lane >> 4), args.n_clips - 1);
-                unsigned k = __ldcg(ep.fq_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
-#pragma unroll
-                for (int of = 2; of <= 8; of <<= 1) {
-                    const unsigned o = __shfl_xor_sync(0xffffffffu, k, of);
-                    k = (lane & 1) ? max(k, o) : min(k, o);
-                }
-                const int src = q.in_a ? 0 : 16;
-                const float mn = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src)), mx = lb_fkey_inv(__shfl_sync(0xffffffffu, k, src + 1));
-                const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);          // dq_params (quant.cu)
-                q_scale = __fdiv_rn(fmaxf(__fsub_rn(amax, amin), 1e-5f), 255.0f);
-                q_zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, q_scale)), 0.0f), 255.0f);
-                q_inv = __fdiv_rn(1.0f, q_scale);
                 if (q.nrows == 32) {                               // the previous tile's store has read the staging tile (long ago)
                     if (lane == 0) tma_store_wait_read();
                     __syncwarp();
@@ -1006,15 +1067,16 @@ gemm_i8_fused_q_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[s]);            // the MMA warp may overwrite this accumulator stage
             if (q.row_ok && nb == 0 && cgrp == 0) { ep.q_row_scale[q.first_row + lane] = q_scale; ep.q_row_zp[q.first_row + lane] = (int)q_zp; }
+            prefetch_params(prefetch_g);
             if (GEMM_DBG) t_qe += clock64() - t_qe0;
         };
 
         for (int p = 0; p < n_act; p += 2) {                       // me(p) me(p+1) qe(p) qe(p+1): one copy of each pass in the instruction cache
             const int pe = min(p + 2, n_act);
 #pragma unroll 1
-            for (int g = p; g < pe; ++g) max_pass(g);
+            for (int g = p; g < pe; ++g) max_pass(g, g > p ? g - 1 : -1);        // me(p+1) ends with the look-up for qe(p)
 #pragma unroll 1
-            for (int g = p; g < pe; ++g) quant_pass(g);
+            for (int g = p; g < pe; ++g) quant_pass(g, g + 1 < pe ? g + 1 : -1);  // qe(p) ends with the look-up for qe(p+1)
         }
         if (lane == 0) tma_store_wait_all();
         if (GEMM_DBG && args.dbg && (blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (ew == 0 || ew == 15))
@@ -1105,6 +1167,27 @@ int cached_tmap_out_u8(lele_b200_ctx* ctx, CUtensorMap* map, const void* ptr, lo
     lb_tmap_store(ctx, key, map);
     return LELE_B200_OK;
 }
+// how many 2-CTA clusters of the GEMM kernel (one CTA per SM) the device keeps resident at once: GPCs with an odd number of SMs
+// leave one SM without a partner, and a persistent grid must not exceed what is co-resident
+int mc_resident_clusters(lele_b200_ctx* ctx) {
+    static int cached[64] = {0};                      // per device; -1 = unavailable
+    const int dev = ctx->device;
+    if (dev < 0 || dev >= 64) return 0;
+    if (cached[dev] != 0) return cached[dev] > 0 ? cached[dev] : 0;
+    const void* fn = (const void*)gemm_i8_tc_kernel<EPI_PLAIN, true, false, true>;
+    if (lb_func_smem(ctx, fn, SMEM_BYTES)) { cached[dev] = -1; return 0; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * ctx->num_sms); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); cached[dev] = -1; return 0; }
+    if (n > ctx->num_sms / 2) n = ctx->num_sms / 2;
+    cached[dev] = n;
+    return n;
+}
 }  // namespace
 
 int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep) {
@@ -1132,6 +1215,25 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     args.vec_io = (N % 4 == 0) && ((((uintptr_t)ep.out | (uintptr_t)ep.add1 | (uintptr_t)ep.add2) & 15) == 0) && !getenv("LELE_B200_GEMM_NO_VEC_IO");
     int tiles = args.num_m_blocks * args.num_n_blocks;
     int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    // 2-CTA clusters along M that share each weight tile by TMA multicast (32 instead of 48 KB per CTA and k-block over the L2 -> SM
+    // fabric).  Built for FFN2 (K = 2048), whose MMA thread waits for operands 40 % of the time -- measured: no gain (30.2 vs 31.4 us per
+    // launch), because the limiter is the SM's own shared-memory bandwidth, not the fabric: an SS-mode 128 x 256 x 32 int8 MMA reads 12 KB
+    // of operands per 128 cycles (96 B/clk) while TMA writes another 96 B/clk, against 128 B/clk per SM.  Multicast does not change either
+    // figure (cta_group::2 would: half of B per CTA).  Opt-in: LELE_B200_GEMM_MC=1 (every shape), results are bit-identical.
+    args.mc = 0;
+    {
+        const char* e = getenv("LELE_B200_GEMM_MC");
+        const bool want = e && e[0] != '0';
+        const int pair_tiles = ((args.num_m_blocks + 1) / 2) * args.num_n_blocks;
+        if (want && args.num_m_blocks >= 2) {
+            const int ncl = mc_resident_clusters(ctx);
+            if (ncl >= 1) {
+                args.mc = 1;
+                grid = 2 * (pair_tiles < ncl ? pair_tiles : ncl);
+                if ((rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN / 2))) return rc;      // half-tile boxes: each CTA of a pair fetches one
+            }
+        }
+    }
     // In-place residual (x = x + (linear [+ add1]): add2 == out): the tile is reduce-added into `out` by the TMA engine / L2, so the
     // residual stream is neither loaded into nor stored from registers; what is left is the plain (or + add1) epilogue with a TMA store.
     const bool tma_ok = N % 4 == 0 && (((uintptr_t)ep.out | (uintptr_t)ep.add1) & 15) == 0 && !getenv("LELE_B200_GEMM_NO_TMA_STORE");
@@ -1187,7 +1289,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
 #define LB_LAUNCH_MODE4(MD, TM, RL, WS)                                                                                 \
     {                                                                                                                   \
         if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_tc_kernel<MD, TM, RL, WS>, SMEM_BYTES))) return rc;            \
-        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL, WS>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, ta, tb, tout, tlo, args)); \
+        LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<MD, TM, RL, WS>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, args.mc ? 2 : 1, ta, tb, tout, tlo, args)); \
     }
 #define LB_LAUNCH_MODE3(MD, TM, RL) { if (ep.w_signed) LB_LAUNCH_MODE4(MD, TM, RL, true) else LB_LAUNCH_MODE4(MD, TM, RL, false) }
 #define LB_LAUNCH_MODE(MD, TM) LB_LAUNCH_MODE3(MD, TM, false)
@@ -1240,6 +1342,7 @@ int lb_gemm_i8_tc_fused_q(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* W
     args.n_groups = lb_ceil_div(args.n_clips, G);
     args.ep = ep;
     args.dbg = getenv("LELE_B200_GEMM_DBG") ? 1 : 0;
+    args.prefetch = lb_env_flag("LELE_B200_FFN_PREFETCH", 0) ? 1 : 0;   // measured: 49.5 -> 51.1 us per launch (the extra acquire loads cost more than the hidden latency): opt-in
     const int grid = lb_ceil_div(args.GT, BM) * args.nnb;
     LB_REQUIRE(grid <= ctx->num_sms, "gemm_i8 fused quantiser: grid %d exceeds the %d SMs (every CTA must be resident)", grid, ctx->num_sms);
     const bool resb = args.nkb <= FQ_RES_KB && lb_env_flag("LELE_B200_FFN_RESB", 1);

@@ -106,7 +106,15 @@ def test_clip_lanes_bit_identical(lanes, monkeypatch):
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
 
 
-@pytest.mark.parametrize("switch", ["LELE_B200_FFN_FUSED", "LELE_B200_W_UNSIGNED", "LELE_B200_LNQ_STREAM"])
+_SWITCHED = {"LELE_B200_FFN_FUSED": "0", "LELE_B200_W_UNSIGNED": "1", "LELE_B200_LNQ_STREAM": "1",
+             # round 2c: in-place residual added by the L2 (TMA reduce-add) vs added in registers; the FSMN residual tile fetched by TMA vs
+             # per-thread loads; the register-window FSMN kernel vs the tap-gathering one; B tiles multicast over 2-CTA clusters; the early
+             # look-up of the fused quantiser's parameters -- all re-schedulings of the same IEEE operations
+             "LELE_B200_GEMM_RED": "0", "LELE_B200_GEMM_R1_TMA": "0", "LELE_B200_FSMN_V2": "0", "LELE_B200_GEMM_MC": "1",
+             "LELE_B200_FFN_PREFETCH": "1"}
+
+
+@pytest.mark.parametrize("switch", sorted(_SWITCHED))
 def test_one_pass_ffn1_and_s8_weights_bit_identical(switch, monkeypatch):
     """Round-2 GEMM changes are pure re-schedulings of exact arithmetic: (a) FFN1 as ONE pass (the dequantised tile waits in TMEM for
     the clip's max, gemm_i8_fused_q_kernel) vs the max-only + quantising passes; (b) the weight operand as s8 (w - 128, no per-row
@@ -117,7 +125,7 @@ def test_one_pass_ffn1_and_s8_weights_bit_identical(switch, monkeypatch):
     outs = []
     for v in ("default", "switched"):
         if v == "switched":
-            monkeypatch.setenv(switch, {"LELE_B200_FFN_FUSED": "0", "LELE_B200_W_UNSIGNED": "1", "LELE_B200_LNQ_STREAM": "1"}[switch])
+            monkeypatch.setenv(switch, _SWITCHED[switch])
         m = SenseVoice(blob, max_clips=7, max_samples=pcm.shape[1])
         ids, logits = m.transcribe(pcm, want_logits=True)
         for _ in range(2):
