@@ -39,7 +39,8 @@ constexpr int EPI_META_BYTES = 3 * 64 * 4;                     // zp*colsum / sc
 constexpr int EPI_BYTES = NUM_EPI_WARPS * (EPI_TILE_BYTES + EPI_META_BYTES);
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-constexpr int MAX_STAGES = STAGES;
+constexpr int STAGES_CG2 = 4;                        // cta_group::2: 32 KB per stage (A 16 KB + this CTA's half of B 16 KB)
+constexpr int MAX_STAGES = 4;
 #ifdef LELE_B200_GEMM_TIMELINE
 constexpr bool GEMM_DBG = true;    // role wait counters (clock64) printed by CTAs 0 / 77 when LELE_B200_GEMM_DBG=1; costs ~12 registers
 #else
@@ -99,6 +100,30 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
+// ---- cta_group::2: the two CTAs of a cluster (two SMs of one TPC) execute ONE 256 x 256 MMA; each holds its own 128 rows of A and
+// half of B (128 of the 256 columns) in shared memory, so the operand bytes an SM reads and TMA writes per MMA are 2/3 of the 1-CTA case.
+// TMA loads of either CTA signal the LEADER's (rank 0) barrier: the barrier address with the CTA-rank bit cleared (cute Sm100MmaPeerBitMask)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t IDESC) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {   // arrives on the barrier at this offset in every CTA of the mask
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {                // arrive on the leader CTA's copy of a barrier
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(0));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -121,8 +146,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // instruction descriptor: D=S32 (c_format 2 @4), A=U8 (0 @7), B=U8 (0 @10) or S8 (1 @10: the weight stored as w - 128),
 // K-major both, N>>3 @17, M>>4 @24
-constexpr uint32_t idesc_for(bool b_signed) {
-    return (2u << 4) | (0u << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t idesc_for(bool b_signed, int m = BM) {
+    return (2u << 4) | (0u << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t IDESC) {
@@ -157,7 +182,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 struct KernelArgs {
     int M, N, K;
     int vec_io;
-    int mc;             // 2-CTA clusters along M share each B tile by TMA multicast (grid = 2 x resident clusters); 0 = independent CTAs
+    int mc;             // 0 = independent CTAs; 1 = 2-CTA clusters along M share each B tile by TMA multicast; 2 = cta_group::2: the
+                        // cluster's two CTAs run one 256 x 256 MMA (grid = 2 x resident clusters in both cluster modes)
     int red;            // TMA_OUT epilogues: the tile is ADDED to `out` (cp.reduce ... .add) -- the in-place residual x = x + (...)
     int dbg;            // LELE_B200_GEMM_DBG=1: CTAs 0 and 77 print where their producer / MMA / epilogue roles waited (clock64)
     int num_m_blocks, num_n_blocks, num_k_blocks;
@@ -212,7 +238,9 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // I2FP, FMNMX ...), so a ReLU that is not asked for -- or is implied (QUANT: unsigned saturation; MINMAX: max(relu(t)) =
 // max(max t, 0), min(relu(t)) >= 0) -- must not cost an FMNMX per element.
 // WSIGNED: the weight operand is s8 (w - 128, prepare_weights with w_zp == 128): no per-row zero-point term in the epilogue.
-template <int MODE, bool TMA_OUT, bool RELU, bool WSIGNED>
+// CG2 (compile-time: a kernel that contains cta_group::2 instructions can only be launched as a cluster): the two CTAs of a cluster run
+// one 256 x 256 MMA per k-step (see umma_i8_2sm); instantiated for the plain / TMA-store epilogue (FFN2).
+template <int MODE, bool TMA_OUT, bool RELU, bool WSIGNED, bool CG2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_lo, const KernelArgs args) {
@@ -221,11 +249,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (GEMM_DBG && args.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;   // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem = smem_raw + pad;
-    constexpr int NST = STAGES;
+    constexpr int NST = CG2 ? STAGES_CG2 : STAGES;
     constexpr int ETB = EPI_TILE_BYTES;
+    constexpr int B_STRIDE = CG2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;      // bytes between two stages of the B ring
+    static_assert(STAGES_CG2 * (A_STAGE_BYTES + B_STAGE_BYTES / 2) <= STAGES * STAGE_BYTES, "the cta_group::2 ring fits the operand area");
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + NST * A_STAGE_BYTES;
-    uint8_t* epi_base = smem_b + STAGES * B_STAGE_BYTES;                   // per-warp staging tiles, then column metadata
+    uint8_t* epi_base = smem + STAGES * STAGE_BYTES;                   // per-warp staging tiles, then column metadata
     uint64_t* bars = (uint64_t*)(epi_base + EPI_BYTES);
     uint64_t* full_bar = bars;                     // [NST]  TMA -> MMA
     uint64_t* empty_bar = bars + MAX_STAGES;       // [NST]  MMA -> TMA
@@ -238,22 +268,28 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile walk: tile = first + i * stride -> (m, n_blk) = (tile / nnb, tile % nnb); m is the m-block, or with multicast clusters the
     // PAIR of m-blocks the cluster works on (the CTA's own m-block is 2 m + its rank: both CTAs walk the same n-blocks in step)
-    const int mc = args.mc;
+    const int mc = CG2 ? 2 : (args.mc == 1 ? 1 : 0);
     const int crank = mc ? (int)(blockIdx.x & 1) : 0;
     const int tile_first = mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_stride = mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int num_tiles = (mc ? (args.num_m_blocks + 1) / 2 : args.num_m_blocks) * args.num_n_blocks;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); if (R1T) prefetch_tmap(&tmap_lo); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], mc ? 2 : 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], NUM_EPI_WARPS); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], mc == 1 ? 2 : 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], mc == 2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
         if (R1T) for (int s = 0; s < NUM_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
         fence_barrier_init();
         fence_proxy_async();
     }
+    if (CG2) cluster_sync_all();   // both CTAs of the pair are running before the paired allocation
     if (warp == 0) {   // whole warp: allocate all 512 TMEM columns (1 CTA/SM by construction)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (CG2) { // (the same warp of both CTAs, same destination offset)
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     if (mc) cluster_sync_all();          // the peer's barriers are initialised before any multicast load / remote arrival can reach them
@@ -274,12 +310,21 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int kb = 0; kb < args.num_k_blocks; ++kb) {
                     if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t0; }
                     else mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (CG2) {
+                        // each CTA fetches its own A rows and its half of B into its own shared memory; both signal the leader's barrier,
+                        // which the leader arms for the pair's 64 KB
+                        if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES / 2));
+                        tma_load_2d_2sm(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                        tma_load_2d_2sm(smem_b + stage * B_STRIDE, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN + crank * (BN / 2));
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                     tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
                     if (mc)   // tmap_b's box is half a tile here: rows [rank * 128, +128) of the n-block, delivered to both CTAs
-                        tma_load_2d_mc(smem_b + stage * B_STAGE_BYTES + crank * (B_STAGE_BYTES / 2), &tmap_b, &full_bar[stage], kb * BK,
+                        tma_load_2d_mc(smem_b + stage * B_STRIDE + crank * (B_STAGE_BYTES / 2), &tmap_b, &full_bar[stage], kb * BK,
                                        n_blk * BN + crank * (BN / 2), (uint16_t)3);
-                    else tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    else tma_load_2d(smem_b + stage * B_STRIDE, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
@@ -287,8 +332,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 printf("GEMMDBG blk %d TMA: total %lld wait_empty %lld\n", blockIdx.x, clock64() - t_begin, w_empty);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (single thread; with cta_group::2 the leader CTA's, for the pair) =====================
+        if (lane == 0 && !(CG2 && crank != 0)) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             long long w_tmem = 0, w_full = 0; const long long t_begin = clock64();
@@ -302,16 +347,21 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     else mbar_wait(&full_bar[stage], phase);            // TMA bytes landed
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STRIDE));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance along K inside the 128B swizzle atom: +32 B == +2 in the (>>4) address field
-                        umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
-                                (kb > 0 || k > 0) ? 1u : 0u, idesc_for(WSIGNED));
+                        if (CG2)
+                            umma_i8_2sm(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
+                                        (kb > 0 || k > 0) ? 1u : 0u, idesc_for(WSIGNED, 2 * BM));
+                        else
+                            umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)),
+                                    (kb > 0 || k > 0) ? 1u : 0u, idesc_for(WSIGNED));
                     }
-                    if (mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs (the peer refills half of it)
+                    if (CG2) umma_commit_2sm(&empty_bar[stage], (uint16_t)3);    // both CTAs' slots are free when the pair's MMAs retire
+                    else if (mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3);     // ... in both CTAs (the peer refills half of it)
                     else umma_commit(&empty_bar[stage]);           // frees the smem slot when the MMAs retire
-                    if (kb == args.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    if (kb == args.num_k_blocks - 1) { if (CG2) umma_commit_2sm(&tmem_full[acc], (uint16_t)3); else umma_commit(&tmem_full[acc]); }
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -634,8 +684,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (lane == 0) { if (CG2) mbar_arrive_rank0(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }   // (cta_group::2: the leader's
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }                                                                // MMA thread waits for both CTAs' epilogues)
             if (GEMM_DBG && args.dbg) busy += clock64() - t_busy0;
 
             if (MODE == EPI_QUANT && row_ok) {
@@ -678,7 +728,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (warp == 0) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
 
@@ -1215,25 +1266,6 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     args.vec_io = (N % 4 == 0) && ((((uintptr_t)ep.out | (uintptr_t)ep.add1 | (uintptr_t)ep.add2) & 15) == 0) && !getenv("LELE_B200_GEMM_NO_VEC_IO");
     int tiles = args.num_m_blocks * args.num_n_blocks;
     int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-    // 2-CTA clusters along M that share each weight tile by TMA multicast (32 instead of 48 KB per CTA and k-block over the L2 -> SM
-    // fabric).  Built for FFN2 (K = 2048), whose MMA thread waits for operands 40 % of the time -- measured: no gain (30.2 vs 31.4 us per
-    // launch), because the limiter is the SM's own shared-memory bandwidth, not the fabric: an SS-mode 128 x 256 x 32 int8 MMA reads 12 KB
-    // of operands per 128 cycles (96 B/clk) while TMA writes another 96 B/clk, against 128 B/clk per SM.  Multicast does not change either
-    // figure (cta_group::2 would: half of B per CTA).  Opt-in: LELE_B200_GEMM_MC=1 (every shape), results are bit-identical.
-    args.mc = 0;
-    {
-        const char* e = getenv("LELE_B200_GEMM_MC");
-        const bool want = e && e[0] != '0';
-        const int pair_tiles = ((args.num_m_blocks + 1) / 2) * args.num_n_blocks;
-        if (want && args.num_m_blocks >= 2) {
-            const int ncl = mc_resident_clusters(ctx);
-            if (ncl >= 1) {
-                args.mc = 1;
-                grid = 2 * (pair_tiles < ncl ? pair_tiles : ncl);
-                if ((rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN / 2))) return rc;      // half-tile boxes: each CTA of a pair fetches one
-            }
-        }
-    }
     // In-place residual (x = x + (linear [+ add1]): add2 == out): the tile is reduce-added into `out` by the TMA engine / L2, so the
     // residual stream is neither loaded into nor stored from registers; what is left is the plain (or + add1) epilogue with a TMA store.
     const bool tma_ok = N % 4 == 0 && (((uintptr_t)ep.out | (uintptr_t)ep.add1) & 15) == 0 && !getenv("LELE_B200_GEMM_NO_TMA_STORE");
@@ -1285,6 +1317,33 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
         rc = cached_tmap_out_f32(ctx, &tlo, ep.add1, M, N, N);
         if (rc) return rc;
     }
+    // 2-CTA clusters along M that share each weight tile by TMA multicast (32 instead of 48 KB per CTA and k-block over the L2 -> SM
+    // fabric).  Built for FFN2 (K = 2048), whose MMA thread waits for operands 40 % of the time -- measured: no gain (30.2 vs 31.4 us per
+    // launch), because the limiter is the SM's own shared-memory bandwidth, not the fabric: an SS-mode 128 x 256 x 32 int8 MMA reads 12 KB
+    // of operands per 128 cycles (96 B/clk) while TMA writes another 96 B/clk, against 128 B/clk per SM.  Multicast does not change either
+    // figure (cta_group::2 would: half of B per CTA).  Opt-in: LELE_B200_GEMM_MC=1 (every shape), results are bit-identical.
+    args.mc = 0;
+    {
+        const char* e = getenv("LELE_B200_GEMM_MC");
+        // cta_group::2 pair MMA (256 x 256 per cluster, 4-stage ring of 32 KB): LELE_B200_GEMM_CG2=1, plain / TMA-store epilogue only.
+        // Measured on FFN2 (K = 2048): 31.1 us per launch with and without, step 19.30 vs 19.37 ms -- like the multicast variant it
+        // changes nothing, so neither the L2 -> SM fabric nor shared-memory bandwidth paces that mainloop (both variants cut them by a
+        // third); what remains is per-k-block latency of the single producer thread (2 TMA issues + barrier round trip ~ 560 cycles,
+        // role timeline in profiles/r02c_gemm_role_timelines.log).  Opt-in; bit-identical (switch test).
+        const char* e2 = getenv("LELE_B200_GEMM_CG2");
+        const bool cg2_inst = mode == EPI_PLAIN && tma_out && ep.w_signed && !ep.relu;   // = the cta_group::2 instantiation below
+        const bool want2 = cg2_inst && e2 && e2[0] != '0';
+        const bool want = (e && e[0] != '0') || want2;
+        const int pair_tiles = ((args.num_m_blocks + 1) / 2) * args.num_n_blocks;
+        if (want && args.num_m_blocks >= 2) {
+            const int ncl = mc_resident_clusters(ctx);
+            if (ncl >= 1) {
+                args.mc = want2 ? 2 : 1;
+                grid = 2 * (pair_tiles < ncl ? pair_tiles : ncl);
+                if ((rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN / 2))) return rc;      // half-tile boxes: each CTA of a pair fetches one
+            }
+        }
+    }
     // the shared-memory opt-in is recorded per context (= per device), once per instantiation
 #define LB_LAUNCH_MODE4(MD, TM, RL, WS)                                                                                 \
     {                                                                                                                   \
@@ -1295,7 +1354,12 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
 #define LB_LAUNCH_MODE(MD, TM) LB_LAUNCH_MODE3(MD, TM, false)
 #define LB_LAUNCH_RELU(MD, TM) { if (ep.relu) LB_LAUNCH_MODE3(MD, TM, true) else LB_LAUNCH_MODE3(MD, TM, false) }
     switch (mode) {
-        case EPI_PLAIN: if (tma_out) LB_LAUNCH_RELU(EPI_PLAIN, true) else LB_LAUNCH_RELU(EPI_PLAIN, false) break;
+        case EPI_PLAIN:
+            if (args.mc == 2) {
+                if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_tc_kernel<EPI_PLAIN, true, false, true, true>, SMEM_BYTES))) return rc;
+                LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<EPI_PLAIN, true, false, true, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 2, ta, tb, tout, tlo, args));
+            } else if (tma_out) LB_LAUNCH_RELU(EPI_PLAIN, true) else LB_LAUNCH_RELU(EPI_PLAIN, false)
+            break;
         case EPI_MINMAX: if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
         case EPI_ARGMAX: LB_LAUNCH_MODE(EPI_ARGMAX, false) break;
         case EPI_R1: if (tma_out) LB_LAUNCH_MODE(EPI_R1, true) else LB_LAUNCH_MODE(EPI_R1, false) break;
