@@ -246,7 +246,15 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // WSIGNED: the weight operand is s8 (w - 128, prepare_weights with w_zp == 128): no per-row zero-point term in the epilogue.
 // CG2 (compile-time: a kernel that contains cta_group::2 instructions can only be launched as a cluster): the two CTAs of a cluster run
 // one 256 x 256 MMA per k-step (see umma_i8_2sm); instantiated for the plain / TMA-store epilogue (FFN2).
-template <int MODE, bool TMA_OUT, bool RELU, bool WSIGNED, bool CG2 = false>
+// AF (compile-time; K <= 512, one m-block per CTA): the A operand is produced IN the kernel from the f32 activation and its per-clip
+// min / max keys -- the reference's dynamic quantiser (dq_to_u8_rowsums_avx2) fused into the GEMM that consumes it.  The 16 epilogue
+// warps, idle until the first accumulator is ready, quantise the CTA's 128 x K block straight into the 128B-swizzled K-major layout TMA
+// would have produced; it stays resident while the CTA walks the n-blocks (only weight tiles stream).  No u8 tensor, no row-parameter
+// arrays, no separate quantiser launch.  Instantiated for the out-projection (EPI_R1, TMA store, s8 weights).
+constexpr int AF_KB = 4;                              // resident k-blocks of the A block (K <= 512)
+constexpr int AF_STAGES = 2;                          // B ring of the AF variant
+static_assert(AF_KB * A_STAGE_BYTES + AF_STAGES * B_STAGE_BYTES <= STAGES * STAGE_BYTES, "the AF layout fits the operand area");
+template <int MODE, bool TMA_OUT, bool RELU, bool WSIGNED, bool CG2 = false, bool AF = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_lo, const KernelArgs args) {
@@ -255,12 +263,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (GEMM_DBG && args.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_t0));
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;   // SWIZZLE_128B needs 1024 B alignment
     uint8_t* smem = smem_raw + pad;
-    constexpr int NST = CG2 ? STAGES_CG2 : STAGES;
+    constexpr int NST = AF ? AF_STAGES : (CG2 ? STAGES_CG2 : STAGES);
+    static_assert(!(AF && CG2), "AF and CG2 are separate variants");
     constexpr int ETB = EPI_TILE_BYTES;
     constexpr int B_STRIDE = CG2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;      // bytes between two stages of the B ring
     static_assert(STAGES_CG2 * (A_STAGE_BYTES + B_STAGE_BYTES / 2) <= STAGES * STAGE_BYTES, "the cta_group::2 ring fits the operand area");
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + NST * A_STAGE_BYTES;
+    uint8_t* smem_b = smem + (AF ? AF_KB : NST) * A_STAGE_BYTES;
     uint8_t* epi_base = smem + STAGES * STAGE_BYTES;                   // per-warp staging tiles, then column metadata
     uint64_t* bars = (uint64_t*)(epi_base + EPI_BYTES);
     uint64_t* full_bar = bars;                     // [NST]  TMA -> MMA
@@ -268,6 +277,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint64_t* tmem_full = bars + 2 * MAX_STAGES;   // [2]    MMA -> epilogue
     uint64_t* tmem_empty = tmem_full + 2;          // [2]    epilogue -> MMA
     uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+    uint64_t* a_ready = bars + 14;                 // AF: the CTA's quantised A block is in shared memory (16 epilogue warps arrive)
     uint64_t* res_bar = bars + 16;                 // [NUM_EPI_WARPS] EPI_R1 + TMA_OUT: the warp's residual sub-tile landed (TMA load into its staging tile)
     constexpr bool R1T = (MODE == EPI_R1) && TMA_OUT;
 
@@ -280,14 +290,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // PAIR of m-blocks the cluster works on (the CTA's own m-block is 2 m + its rank: both CTAs walk the same n-blocks in step)
     const int mc = CG2 ? 2 : (args.mc == 1 ? 1 : 0);
     const int crank = mc ? (int)(blockIdx.x & 1) : 0;
-    const int tile_first = mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_stride = mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int num_tiles = (mc ? (args.num_m_blocks + 1) / 2 : args.num_m_blocks) * args.num_n_blocks;
+    // (AF: CTA = one m-block, its tiles are that m-block's n-blocks in order)
+    const int tile_first = AF ? (int)blockIdx.x * args.num_n_blocks : (mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+    const int tile_stride = AF ? 1 : (mc ? (int)(gridDim.x >> 1) : (int)gridDim.x);
+    const int num_tiles_all = (mc ? (args.num_m_blocks + 1) / 2 : args.num_m_blocks) * args.num_n_blocks;
+    const int num_tiles = AF ? min(num_tiles_all, tile_first + args.num_n_blocks) : num_tiles_all;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); if (TMA_OUT) prefetch_tmap(&tmap_out); if (R1T) prefetch_tmap(&tmap_lo); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], mc == 1 ? 2 : 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], mc == 2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS); }
         if (R1T) for (int s = 0; s < NUM_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+        if (AF) mbar_init(a_ready, NUM_EPI_WARPS);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -320,6 +334,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 for (int kb = 0; kb < args.num_k_blocks; ++kb) {
                     if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t0; }
                     else mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (AF) {                                      // the A block is resident: only the weight tile streams
+                        mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
+                        tma_load_2d(smem_b + stage * B_STRIDE, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (CG2) {
                         // each CTA fetches its own A rows and its half of B into its own shared memory; both signal the leader's barrier,
                         // which the leader arms for the pair's 64 KB
@@ -347,6 +367,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             long long w_tmem = 0, w_full = 0; const long long t_begin = clock64();
+            if (AF && tile_first < num_tiles) { mbar_wait(a_ready, 0); tc_fence_after(); }   // the quantised A block is in place
             for (int tile = tile_first; tile < num_tiles; tile += tile_stride) {
                 if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t0; }
                 else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
@@ -356,7 +377,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     if (GEMM_DBG && args.dbg) { const long long t0 = clock64(); mbar_wait(&full_bar[stage], phase); w_full += clock64() - t0; }
                     else mbar_wait(&full_bar[stage], phase);            // TMA bytes landed
                     tc_fence_after();
-                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + (AF ? kb : stage) * A_STAGE_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STRIDE));
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -412,6 +433,64 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         int m_idx = tile_first / nnb, n_blk = tile_first % nnb;
         const int mmul = mc ? 2 : 1;
         int m_blk = m_idx * mmul + crank;
+        int af_zpa = 0; float af_sa = 0.0f;                            // AF: the row's activation zero point / scale, derived from the keys
+        if (AF && tile_first < num_tiles) {
+            // (scale, zp, 1 / scale) of one clip from its 8 (min, max) key slots: lanes 0-15 load the 16 keys, xor-shuffles reduce them
+            auto clip_params = [&](int clip, float& scale, float& zp, float& inv) {
+                unsigned k = __ldg(ep.a_keys + (size_t)clip * LB_MM_SLOTS * 2 + (lane & 15));
+#pragma unroll
+                for (int of = 2; of <= 8; of <<= 1) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, k, of);
+                    k = (lane & 1) ? max(k, o) : min(k, o);
+                }
+                const float mn = lb_fkey_inv(__shfl_sync(0xffffffffu, k, 0)), mx = lb_fkey_inv(__shfl_sync(0xffffffffu, k, 1));
+                const float amax = fmaxf(mx, 0.0f), amin = fminf(mn, 0.0f);          // dq_params (quant.cu)
+                scale = __fdiv_rn(fmaxf(__fsub_rn(amax, amin), 1e-5f), 255.0f);
+                zp = fminf(fmaxf(roundf(__fdiv_rn(-amin, scale)), 0.0f), 255.0f);
+                inv = __fdiv_rn(1.0f, scale);
+            };
+            // ---- the quantiser: warp ew takes rows ew, ew + 16, ... of the block; a lane takes 16 consecutive k (64 B of f32 -> one
+            //      16-byte chunk of the swizzled K-major tile of its k-block) ----
+            const int m0 = (int)blockIdx.x * BM;
+            const int kch = args.K >> 4;                               // 16-element chunks per row (K % 128 == 0, K <= 512)
+            int cur_clip = -1; float c_scale = 0.0f, c_zp = 0.0f, c_inv = 0.0f;
+#pragma unroll 1
+            for (int r = ew; r < BM; r += NUM_EPI_WARPS) {
+                const int grow = m0 + r;
+                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                if (grow < M) {                                        // warp-uniform
+                    const int clip = div_by_rps(grow, rps, inv_rps);
+                    if (clip != cur_clip) { clip_params(clip, c_scale, c_zp, c_inv); cur_clip = clip; }
+                    if (lane < kch) {
+                        const float4* src = reinterpret_cast<const float4*>(ep.a_f32 + (size_t)grow * args.K + lane * 16);
+                        const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
+                        auto q4 = [&](const float4& v) {               // clamp(rint(fma(x, 1 / scale, zp)), 0, 255), packed little-endian
+                            const unsigned a = cvt_sat_u8(__fmaf_rn(v.x, c_inv, c_zp)), b = cvt_sat_u8(__fmaf_rn(v.y, c_inv, c_zp));
+                            const unsigned c = cvt_sat_u8(__fmaf_rn(v.z, c_inv, c_zp)), d = cvt_sat_u8(__fmaf_rn(v.w, c_inv, c_zp));
+                            return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+                        };
+                        pk = make_uint4(q4(v0), q4(v1), q4(v2), q4(v3));
+                    }
+                }
+                if (lane < kch) {
+                    const uint32_t dst = smem_u32(smem_a) + (uint32_t)(lane >> 3) * A_STAGE_BYTES + (uint32_t)r * 128u + ((((uint32_t)lane & 7u) ^ ((uint32_t)r & 7u)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+                }
+            }
+            fence_proxy_async();                                       // generic-proxy writes -> visible to the tensor core's operand fetch
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+            // ---- the epilogue's per-row activation parameters: the warp's 32 rows lie in clip A (that of its first row) or A + 1 ----
+            {
+                const int fr = m0 + quad * 32;
+                const int clip_a = min(div_by_rps(min(fr, M - 1), rps, inv_rps), last_slice);
+                float sA, zA, iA, sB, zB, iB;
+                clip_params(clip_a, sA, zA, iA);
+                clip_params(min(clip_a + 1, last_slice), sB, zB, iB);
+                const bool in_a_row = fr + lane < (clip_a + 1) * rps;
+                af_sa = in_a_row ? sA : sB; af_zpa = (int)(in_a_row ? zA : zB);
+            }
+        }
         auto fetch_meta = [&](int t, int mb, int nb) {
             if (t >= num_tiles) return;
             const int rw = mb * BM + quad * 32 + lane;
@@ -420,7 +499,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 pf_qkey = __ldg(ep.q_keys + (size_t)sl * LB_MM_SLOTS * 2 + (lane & 15));
             }
             pf_rs = 0; pf_zpa = 0; pf_sa = 0.0f;
-            if (rw < M) { if (!WSIGNED) pf_rs = __ldg(ep.rowsum + rw); pf_zpa = __ldg(ep.row_zp + rw); pf_sa = __ldg(ep.row_scale + rw); }
+            if (AF) { if (rw < M) { pf_zpa = af_zpa; pf_sa = af_sa; } }
+            else if (rw < M) { if (!WSIGNED) pf_rs = __ldg(ep.rowsum + rw); pf_zpa = __ldg(ep.row_zp + rw); pf_sa = __ldg(ep.row_scale + rw); }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int cc = min(nb * BN + cgrp * 64 + hh * 32 + lane, N - 1);
@@ -1259,14 +1339,17 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
     LB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_i8_tc: empty problem");
     LB_REQUIRE(K % 16 == 0, "gemm_i8_tc: K=%d must be a multiple of 16 (TMA row pitch)", K);
     LB_REQUIRE((((uintptr_t)A | (uintptr_t)Wt) & 15) == 0, "gemm_i8_tc: operands must be 16-byte aligned");
+    const bool af = ep.a_f32 != nullptr;               // fused input quantiser: A is produced in the kernel
+    LB_REQUIRE(af || A, "gemm_i8_tc: no A operand");
+    LB_REQUIRE(!af || lb_gemm_i8_afuse_supported(ctx, M, N, K, ep), "gemm_i8_tc: fused input quantiser not available for M=%d N=%d K=%d", M, N, K);
     LB_REQUIRE(!ep.minmax_keys || ep.rows_per_slice >= 32, "gemm_i8_tc: fused min/max needs rows_per_slice >= 32 (a warp's 32 rows may span at most two slices)");
     LB_REQUIRE(!ep.argmax_keys || (!ep.add1 && !ep.add2), "gemm_i8_tc: fused arg-max cannot be combined with residual adds");
     LB_REQUIRE(!ep.w_signed || ep.w_zp == 128, "gemm_i8_tc: a signed weight operand implies zero point 128");
     CUtensorMap ta, tb;
-    int rc = cached_tmap_u8(ctx, &ta, A, M, K, BM);
+    int rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN);
     if (rc) return rc;
-    rc = cached_tmap_u8(ctx, &tb, Wt, N, K, BN);
-    if (rc) return rc;
+    if (af) ta = tb;                                   // (unused by that variant)
+    else if ((rc = cached_tmap_u8(ctx, &ta, A, M, K, BM))) return rc;
     KernelArgs args;
     args.M = M; args.N = N; args.K = K;
     args.num_m_blocks = lb_ceil_div(M, BM);
@@ -1349,7 +1432,7 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
         const bool want2 = cg2_inst && e2 && e2[0] != '0';
         const bool want = (e && e[0] != '0') || want2;
         const int pair_tiles = ((args.num_m_blocks + 1) / 2) * args.num_n_blocks;
-        if (want && args.num_m_blocks >= 2) {
+        if (want && !af && args.num_m_blocks >= 2) {
             const int ncl = mc_resident_clusters(ctx);
             if (ncl >= 1) {
                 args.mc = want2 ? 2 : 1;
@@ -1376,7 +1459,14 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
             break;
         case EPI_MINMAX: if (tma_out) LB_LAUNCH_RELU(EPI_MINMAX, true) else LB_LAUNCH_RELU(EPI_MINMAX, false) break;
         case EPI_ARGMAX: LB_LAUNCH_MODE(EPI_ARGMAX, false) break;
-        case EPI_R1: if (tma_out) LB_LAUNCH_MODE(EPI_R1, true) else LB_LAUNCH_MODE(EPI_R1, false) break;
+        case EPI_R1:
+            if (af) {
+                LB_REQUIRE(tma_out && args.mc == 0, "gemm_i8_tc: the fused input quantiser needs the TMA-store epilogue");
+                grid = args.num_m_blocks;              // one m-block per CTA, its A block resident
+                if ((rc = lb_func_smem(ctx, (const void*)gemm_i8_tc_kernel<EPI_R1, true, false, true, false, true>, SMEM_BYTES))) return rc;
+                LB_CHECK_CUDA(lb_launch_pdl(gemm_i8_tc_kernel<EPI_R1, true, false, true, false, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, ctx->stream, 1, ta, tb, tout, tlo, args));
+            } else if (tma_out) LB_LAUNCH_MODE(EPI_R1, true) else LB_LAUNCH_MODE(EPI_R1, false)
+            break;
         case EPI_R2: LB_LAUNCH_MODE(EPI_R2, false) break;
         case EPI_R12: LB_LAUNCH_MODE(EPI_R12, false) break;
         case EPI_QKV: LB_LAUNCH_MODE(EPI_QKV, true) break;
@@ -1388,6 +1478,16 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
 #undef LB_LAUNCH_RELU
     LB_LAUNCH_CHECK(ctx);
     return LELE_B200_OK;
+}
+
+bool lb_gemm_i8_afuse_supported(lele_b200_ctx* ctx, long long M, int N, int K, const LbI8Epilogue& ep) {
+    if (!lb_env_flag("LELE_B200_GEMM_AFUSE", 1) || getenv("LELE_B200_FORCE_SIMT") || getenv("LELE_B200_GEMM_NO_TMA_STORE")) return false;
+    if (!ep.a_f32 || !ep.a_keys || !ep.w_signed || ep.relu || !ep.out || !ep.add1 || (ep.add2 && ep.add2 != ep.out)) return false;
+    if (ep.minmax_keys || ep.argmax_keys || ep.q_out || ep.vt || ep.fq_keys || ep.rows_per_slice < 32) return false;
+    if (K % BK != 0 || K > AF_KB * BK || N % 4 != 0 || M <= 0 || M > (long long)ctx->num_sms * BM || M >= (1 << 22)) return false;
+    if ((((uintptr_t)ep.a_f32 | (uintptr_t)ep.out | (uintptr_t)ep.add1) & 15) != 0) return false;
+    if (ep.add2 && !lb_env_flag("LELE_B200_GEMM_RED", 1)) return false;
+    return lb_env_flag("LELE_B200_GEMM_R1_TMA", 1);
 }
 
 // The fused linear -> (ReLU) -> dynamic quantiser GEMM (gemm_i8_fused_q_kernel).  Needs the s8 weight operand, whole clips

@@ -39,6 +39,11 @@ struct LbI8Epilogue {
     float* q_row_scale;
     int32_t* q_row_zp;
     const unsigned* q_keys;
+    // fused INPUT quantiser (lb_gemm_i8_tc with a_f32 set, A == NULL): the A operand is quantised in the kernel from the f32 activation
+    // a_f32 [M, K] with the per-slice (scale, zp) derived from a_keys; rowsum / row_scale / row_zp are not read.  K % 128 == 0, K <= 512,
+    // M <= #SMs * 128, s8 weights, add1-only (+ in-place add2) epilogue.
+    const float* a_f32;
+    const unsigned* a_keys;
     // single-pass variant (lb_gemm_i8_tc_fused_q): the accumulators wait in TMEM for the clip's min / max instead of being
     // recomputed; fq_keys = the output's per-clip key slots (initialised), fq_counters = [n_clips] zeroed arrival counters
     unsigned* fq_keys;
@@ -50,6 +55,8 @@ int lb_gemm_i8_tc(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M
                   const LbI8Epilogue& ep);
 
 // one-pass linear -> (ReLU) -> dynamic quantiser: q_out / q_row_scale / q_row_zp + fq_keys / fq_counters; s8 weights only
+// the fused input quantiser above is available for this problem (the caller then skips its quantiser launch)
+bool lb_gemm_i8_afuse_supported(lele_b200_ctx* ctx, long long M, int N, int K, const LbI8Epilogue& ep);
 bool lb_gemm_i8_fused_q_supported(lele_b200_ctx* ctx, long long M, int N, int K, int T, int w_signed);
 int lb_gemm_i8_tc_fused_q(lele_b200_ctx* ctx, const uint8_t* A, const uint8_t* Wt, int M, int N, int K, const LbI8Epilogue& ep);
 

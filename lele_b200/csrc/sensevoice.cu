@@ -57,17 +57,18 @@ const char* kProfNames[P_NUM] = {"frontend_fbank_lfr", "cmvn", "prompt_scale_pos
                                  "gemm_i8:qkv", "gemm_i8:out_proj", "gemm_i8:ffn1_max_pass", "gemm_i8:ffn1", "gemm_i8:ffn2", "gemm_i8:ctc"};
 
 // x0[b, r, :] = (r < 4 ? embed[id_r] : feats[b, r-4]) * sqrt(d) + pos[r]
-__global__ void prompt_scale_pos_kernel(const float* __restrict__ feats, const float* __restrict__ embed, const float* __restrict__ pos,
-                                        int4 ids, int n_clips, int t, int din, float sq, float* __restrict__ x0) {
+__global__ void __launch_bounds__(128)
+prompt_scale_pos_kernel(const float* __restrict__ feats, const float* __restrict__ embed, const float* __restrict__ pos,
+                        int4 ids, int n_clips, int t, int din, float sq, float* __restrict__ x0) {
+    // one CTA per output row: the row's source (a prompt embedding or a feature row) is decided once, no per-element index divisions
     const int T = t + 4;
-    const long long total = (long long)n_clips * T * din;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % din), r = (int)((i / din) % T), b = (int)(i / ((long long)din * T));
-        float v;
-        if (r < 4) { int id = r == 0 ? ids.x : (r == 1 ? ids.y : (r == 2 ? ids.z : ids.w)); v = embed[(long long)id * din + c]; }
-        else v = feats[((long long)b * t + (r - 4)) * din + c];
-        x0[i] = __fadd_rn(__fmul_rn(v, sq), pos[(long long)r * din + c]);
-    }
+    const int row = blockIdx.x, b = row / T, r = row - b * T;
+    const float* src;
+    if (r < 4) { const int id = r == 0 ? ids.x : (r == 1 ? ids.y : (r == 2 ? ids.z : ids.w)); src = embed + (long long)id * din; }
+    else src = feats + ((long long)b * t + (r - 4)) * din;
+    const float* pr = pos + (long long)r * din;
+    float* dst = x0 + (long long)row * din;
+    for (int c = threadIdx.x; c < din; c += 128) dst[c] = __fadd_rn(__fmul_rn(__ldg(src + c), sq), __ldg(pr + c));
 }
 
 // FSMN memory block: depthwise conv1d over time (k taps, zero pad, no bias) on V + V.
@@ -568,7 +569,7 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
 
     {   // gather(embed, prompt ids) ++ concat ++ mul sqrt(d) ++ add pos
         ProfScope ps(m, ctx, P_PREP);
-        prompt_scale_pos_kernel<<<grid_for(M * din), 256, 0, ctx->stream>>>(feats, (const float*)m->tensor(SV_G_EMBED),
+        prompt_scale_pos_kernel<<<(unsigned)M, 128, 0, ctx->stream>>>(feats, (const float*)m->tensor(SV_G_EMBED),
             (const float*)m->tensor(SV_G_POS), make_int4(lang, 1, 2, textnorm), B, t, din, sqrtf((float)d), m->x0);
         LB_LAUNCH_CHECK(ctx);
     }
@@ -645,7 +646,16 @@ static int sv_encoder(lele_b200_ctx* ctx, lele_b200_sensevoice* m, const float* 
         {
             LbI8Epilogue ep; memset(&ep, 0, sizeof(ep));
             ep.out = m->x; ep.rows_per_slice = T; ep.add1 = m->fsmn; ep.add2 = (cur == d) ? xin : nullptr;   // x = x + (lin + fsmn)
-            SV_LINEAR(ctx, m,m->att, site(l * 4 + 1), M, T, m->lin[l * 4 + 1], qs, ep, P_G_OUT);
+            const lele_b200_qweights* wo = m->lin[l * 4 + 1];
+            LbI8Epilogue epf = ep;
+            epf.a_f32 = m->att; epf.a_keys = site(l * 4 + 1);
+            lb_fill_weight_fields(epf, wo, qs);
+            if (lb_gemm_i8_afuse_supported(ctx, M, wo->n, wo->k, epf)) {
+                // the attention output is quantised INSIDE the projection (its per-clip min / max came out of the attention epilogue):
+                // no quantiser launch, no u8 copy of the tensor
+                SV_RUN(P_G_OUT, lb_gemm_i8(ctx, nullptr, wo->wt, (int)M, wo->n, wo->k, epf));
+            } else
+                SV_LINEAR(ctx, m,m->att, site(l * 4 + 1), M, T, wo, qs, ep, P_G_OUT);
         }
         xin = m->x; cur = d;
         // ---- feed-forward block ----
