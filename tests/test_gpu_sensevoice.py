@@ -112,7 +112,7 @@ _SWITCHED = {"LELE_B200_FFN_FUSED": "0", "LELE_B200_W_UNSIGNED": "1", "LELE_B200
              # look-up of the fused quantiser's parameters -- all re-schedulings of the same IEEE operations
              "LELE_B200_GEMM_RED": "0", "LELE_B200_GEMM_R1_TMA": "0", "LELE_B200_FSMN_V2": "0", "LELE_B200_GEMM_MC": "1",
              "LELE_B200_FFN_PREFETCH": "1", "LELE_B200_GEMM_CG2": "1",      # + FFN2 as cta_group::2 pair MMAs (256 x 256 per cluster)
-             "LELE_B200_GEMM_AFUSE": "0"}    # the attention output quantised by its own kernel instead of inside the out-projection
+             "LELE_B200_GEMM_AFUSE": "1"}    # the attention output quantised inside the out-projection instead of by its own kernel
 
 
 @pytest.mark.parametrize("switch", sorted(_SWITCHED))

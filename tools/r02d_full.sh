@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 tag=${1:-r02d}
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/${tag}_pytest.log
 grep -E "passed|failed|rror" gpurun_out/${tag}_pytest.log | tail -5
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 timeout 400 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
 timeout 600 python bench.py --config yolo26n-seg --steps 10 --warmup 3 > gpurun_out/${tag}_yolo.json 2> gpurun_out/${tag}_yolo.err
