@@ -36,6 +36,18 @@ def linear_flops_per_clip(cfg, T):
     return tot
 
 
+def linear_bytes_per_step(cfg, M):
+    """Algorithmic HBM bytes of the int8 linears of one step (M K s_a + K N s_w + M N s_out, each tensor once, plus the residual /
+    FSMN operands the epilogues fuse): u8 operand in, weights once, f32 (or u8, FFN1) result out; x = x + ... reads and writes the residual."""
+    d, din, ffn, v = cfg.d_model, cfg.d_in, cfg.ffn, cfg.vocab
+    qkv = lambda k: M * k + 3 * d * k + M * 3 * d * 4                       # q, k f32 + V^T f32
+    out = M * d + d * d + M * d * 4 + 2 * M * d * 4                          # + FSMN memory read, residual read + write
+    ffn1 = M * d + ffn * d + M * ffn                                          # quantised hidden tensor out (u8)
+    ffn2 = M * ffn + d * ffn + 2 * M * d * 4                                  # residual read + write
+    ctc = M * d + v * d                                                       # ids only: the logits are not written
+    return float(qkv(din) + (cfg.n_layers - 1) * qkv(d) + cfg.n_layers * (out + ffn1 + ffn2) + ctc)
+
+
 def _weights_module():
     """lele_b200/sensevoice_weights.py (numpy only: the synthetic blob + PCM generators shared by both arms) loaded BY PATH: importing
     the lele_b200 package would map liblele_b200.so into the process, and the reference arm must not carry the product library."""
@@ -390,6 +402,12 @@ def run_ours(args):
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                     "launches_per_step": g["calls"], "avg_launch_ms": (g["ms"] / g["calls"]) if g["calls"] else None,
                     "algorithmic_flops_per_step": flops_step, "share_of_step": (g["ms"] / sum(v["ms"] for k, v in prof.items() if not k.startswith("gemm_i8:"))) if prof else None}
+        # the same launches seen as HBM kernels: at M = 17 600 their f32 activations make QKV / out-projection / FFN2 traffic-bound
+        gbytes = linear_bytes_per_step(cfg, B * T)
+        if g["ms"] > 0:
+            roofline["hbm_view"] = {"bound": "hbm", "achieved": gbytes / (g["ms"] / 1000.0) / 1e9, "peak": hbm, "unit": "GB/s",
+                                    "frac": gbytes / (g["ms"] / 1000.0) / 1e9 / hbm, "algorithmic_bytes_per_step": gbytes,
+                                    "note": "algorithmic bytes of the int8 linears (operands, weights once, results, fused residual / FSMN operands) over the same summed launch time"}
         try:   # DRAM bytes per launch of the same kernel from the committed ncu capture (tools/summarize_ncu.py traffic)
             tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
             roofline["traffic"] = tr["dram_bytes_per_launch"]
