@@ -136,6 +136,32 @@ __device__ __forceinline__ void lb_pdl_launch_dependents() { asm volatile("gridd
 // device helpers
 // ----------------------------------------------------------------------------
 #ifdef __CUDACC__
+// clamp(rint(y), 0, 255) with round-half-even, NaN -> 0 -- the quantisers' inner operation -- without a float -> integer conversion (F2I
+// issues on the quarter-rate special-function pipe): clamp first (min / max on the ALU pipe; clamping before or after the rounding is the
+// same, 0 and 255 are integers), then add 1.5 * 2^23: at that magnitude one ulp is 1, so the addition itself rounds to the nearest-even
+// integer and the sum's low mantissa byte is the result.  Bit-identical to the conversion (parity tests); measured on the LayerNorm +
+// quantiser kernel's quantising phase: 4.3 k -> 3.8 k cycles (the rest of that phase is the burst of u8 stores).  LB_Q8_CVT: the conversion.
+__device__ __forceinline__ unsigned lb_q8(float y) {
+#ifdef LB_Q8_CVT
+    return min(__float2uint_rn(y), 255u);
+#else
+    return __float_as_uint(__fadd_rn(fminf(fmaxf(y, 0.0f), 255.0f), 12582912.0f)) & 0xffu;
+#endif
+}
+// four of them packed little-endian (the byte selects take the low byte of each sum: no mask needed)
+__device__ __forceinline__ unsigned lb_q8x4(float y0, float y1, float y2, float y3, int& sum) {
+#ifdef LB_Q8_CVT
+    const unsigned q0 = lb_q8(y0), q1 = lb_q8(y1), q2 = lb_q8(y2), q3 = lb_q8(y3);
+    sum += (int)(q0 + q1 + q2 + q3);
+    return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+#else
+    const unsigned b0 = __float_as_uint(__fadd_rn(fminf(fmaxf(y0, 0.0f), 255.0f), 12582912.0f)), b1 = __float_as_uint(__fadd_rn(fminf(fmaxf(y1, 0.0f), 255.0f), 12582912.0f));
+    const unsigned b2 = __float_as_uint(__fadd_rn(fminf(fmaxf(y2, 0.0f), 255.0f), 12582912.0f)), b3 = __float_as_uint(__fadd_rn(fminf(fmaxf(y3, 0.0f), 255.0f), 12582912.0f));
+    const unsigned pk = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+    sum = (int)__dp4a(pk, 0x01010101u, (unsigned)sum);
+    return pk;
+#endif
+}
 __device__ __forceinline__ float lb_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -233,7 +233,7 @@ __device__ __forceinline__ void lnq_params(const unsigned* keys, long long slice
 }
 __device__ __forceinline__ unsigned lnq_one(float x, float mean, float rstd, float g, float b, float inv, float zp) {
     const float r = __fmaf_rn(__fmul_rn(__fsub_rn(x, mean), rstd), g, b);
-    return min(__float2uint_rn(__fmaf_rn(r, inv, zp)), 255u);   // == clamp(rint(.), 0, 255): the conversion saturates at 0
+    return lb_q8(__fmaf_rn(r, inv, zp));   // == clamp(rint(.), 0, 255)
 }
 template <int N, int RPW>
 __global__ void __launch_bounds__(256)
@@ -409,10 +409,7 @@ ln_quant_cluster_kernel(const float* __restrict__ x, const float* __restrict__ g
 #pragma unroll
         for (int j = 0; j < N / 128; ++j) {
             const float4 y = y4[lane + 32 * j];
-            const unsigned q0 = min(__float2uint_rn(__fmaf_rn(y.x, inv, zp)), 255u), q1 = min(__float2uint_rn(__fmaf_rn(y.y, inv, zp)), 255u);
-            const unsigned q2 = min(__float2uint_rn(__fmaf_rn(y.z, inv, zp)), 255u), q3 = min(__float2uint_rn(__fmaf_rn(y.w, inv, zp)), 255u);
-            sum += (int)(q0 + q1 + q2 + q3);
-            a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            a4[lane + 32 * j] = lb_q8x4(__fmaf_rn(y.x, inv, zp), __fmaf_rn(y.y, inv, zp), __fmaf_rn(y.z, inv, zp), __fmaf_rn(y.w, inv, zp), sum);
         }
         sum = lb_warp_sum_i(sum);
         if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
@@ -556,7 +553,7 @@ ln_quant_cluster_reg_kernel(const float* __restrict__ x, const float* __restrict
             int sum = 0;
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
-                const unsigned q = min(__float2uint_rn(__fmaf_rn(yr[i][j], inv, zp)), 255u);
+                const unsigned q = lb_q8(__fmaf_rn(yr[i][j], inv, zp));
                 sum += (int)q;
                 dst[32 * j] = (uint8_t)q;
             }
@@ -572,10 +569,7 @@ ln_quant_cluster_reg_kernel(const float* __restrict__ x, const float* __restrict
 #pragma unroll
         for (int j = 0; j < N / 128; ++j) {
             const float4 y = y4[lane + 32 * j];
-            const unsigned q0 = min(__float2uint_rn(__fmaf_rn(y.x, inv, zp)), 255u), q1 = min(__float2uint_rn(__fmaf_rn(y.y, inv, zp)), 255u);
-            const unsigned q2 = min(__float2uint_rn(__fmaf_rn(y.z, inv, zp)), 255u), q3 = min(__float2uint_rn(__fmaf_rn(y.w, inv, zp)), 255u);
-            sum += (int)(q0 + q1 + q2 + q3);
-            a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            a4[lane + 32 * j] = lb_q8x4(__fmaf_rn(y.x, inv, zp), __fmaf_rn(y.y, inv, zp), __fmaf_rn(y.z, inv, zp), __fmaf_rn(y.w, inv, zp), sum);
         }
         sum = lb_warp_sum_i(sum);
         if (lane == 0) { rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }
@@ -781,10 +775,7 @@ ln_quant_stream_kernel(const float* __restrict__ x, const float* __restrict__ ga
 #pragma unroll
         for (int j = 0; j < N / 128; ++j) {
             const float4 y = y4[lane + 32 * j];
-            const unsigned q0 = min(__float2uint_rn(__fmaf_rn(y.x, inv, zp)), 255u), q1 = min(__float2uint_rn(__fmaf_rn(y.y, inv, zp)), 255u);
-            const unsigned q2 = min(__float2uint_rn(__fmaf_rn(y.z, inv, zp)), 255u), q3 = min(__float2uint_rn(__fmaf_rn(y.w, inv, zp)), 255u);
-            sum += (int)(q0 + q1 + q2 + q3);
-            a4[lane + 32 * j] = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+            a4[lane + 32 * j] = lb_q8x4(__fmaf_rn(y.x, inv, zp), __fmaf_rn(y.y, inv, zp), __fmaf_rn(y.z, inv, zp), __fmaf_rn(y.w, inv, zp), sum);
         }
         if (rowsum) sum = lb_warp_sum_i(sum);
         if (lane == 0) { if (rowsum) rowsum[row] = sum; row_scale[row] = scale; row_zp[row] = (int)zp; }

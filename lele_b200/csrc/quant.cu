@@ -69,7 +69,7 @@ __device__ __forceinline__ float dq_one(float v, float inv, float zp, bool simd)
 __device__ __forceinline__ unsigned dq_body(float v, float inv, float zp) {
     // round-half-even + clamp to [0, 255]: cvt.rni.u32.f32 saturates negatives (and NaN) to 0, so one conversion and
     // one integer min give exactly clamp(rint(fma(v, inv, zp)), 0, 255)
-    return min(__float2uint_rn(__fmaf_rn(v, inv, zp)), 255u);
+    return lb_q8(__fmaf_rn(v, inv, zp));
 }
 template <bool kAligned>
 __global__ void __launch_bounds__(256)
