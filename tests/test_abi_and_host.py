@@ -1113,3 +1113,24 @@ def test_batch_folded_replay_runs_the_independent_prefix_once(fake_dev):
             np.testing.assert_allclose(g, ww, rtol=1e-6, atol=1e-6)
     assert prog2["_fold_report"][3]["stopped_at"] == "flatten" and prog2["_fold_report"][3]["folded_statements"] >= 8
     br2.close()
+
+
+def test_quantiser_rounding_without_a_conversion_is_exact():
+    """csrc/common.cuh lb_q8: clamp(rint(y), 0, 255) (round-half-even, the reference's `_mm256_cvtps_epi32` after the clamp-free fma,
+    avx/quantization.rs:158-161, then the saturating pack) computed as  low byte of  f32(clamp(y, 0, 255) + 1.5 * 2^23).  The identity is
+    checked here in numpy float32 on every half-way point, the neighbours of every integer, out-of-range / infinite / NaN inputs and a
+    random sweep (the GPU kernels are compared bit for bit with the oracle's quantiser in test_gpu_parity.py)."""
+    f32 = np.float32
+    ks = np.arange(-3, 260, dtype=np.float64)
+    pts = [ks, ks + 0.5, ks - 0.5]
+    for d in (1e-3, 2.0 ** -16, 2.0 ** -20):
+        pts += [ks + d, ks - d, ks + 0.5 + d, ks + 0.5 - d]
+    rng = np.random.default_rng(5)
+    pts.append(rng.uniform(-10.0, 270.0, 200000))
+    pts.append(np.array([0.0, -0.0, 255.0, 255.49999, 255.5, 256.0, 1e9, -1e9, np.inf, -np.inf, np.nan, 1e-45, -1e-45]))
+    y = np.concatenate(pts).astype(f32)
+    with np.errstate(invalid="ignore"):
+        want = np.clip(np.rint(np.nan_to_num(y.astype(np.float64), nan=0.0, posinf=1e30, neginf=-1e30)), 0, 255).astype(np.uint32)
+        c = np.minimum(np.fmax(y, f32(0.0)), f32(255.0)).astype(f32)         # fmaxf(NaN, 0) = 0, as CUDA's fmaxf
+        got = (c + f32(12582912.0)).astype(f32).view(np.uint32) & np.uint32(0xFF)
+    np.testing.assert_array_equal(got, want)
