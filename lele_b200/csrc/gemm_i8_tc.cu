@@ -11,10 +11,17 @@
 //    int      = acc - w_zp*rowsum[i] - a_zp[i]*colsum[j] + K*a_zp[i]*w_zp
 //    y        = f32(int) * (a_scale[i] * w_scale[j]) + bias[j]   (separate mul / add, :1417-1423)
 //
-// Tiling: CTA tile 128 x 256 x 128B-K, 4 smem stages (48 KB each), 2 TMEM accumulator stages
-// (2 x 256 columns = all 512), 384 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM
-// allocator, warps 4-11 epilogue (TMEM lane quadrant = warp%4, column half = (warp-4)/4).
-// Persistent: grid = #SMs, tiles walked n-fastest so concurrently running CTAs share A rows in L2.
+// Tiling: CTA tile 128 x 256 x 128B-K, 3 shared-memory stages (48 KB each), 2 TMEM accumulator stages (2 x 256 columns = all 512),
+// 576 threads: 16 epilogue warps (TMEM lane quadrant = warp % 4, 64-column group = warp / 4), then the two single-thread control
+// roles -- TMA producer (+ TMEM allocation) and MMA issuer -- in the CTA's LAST two warps (the issue arbiter serves the highest warp
+// id first).  Persistent: grid = #SMs, tiles walked n-fastest so concurrently running CTAs share A rows in L2.
+//
+// Epilogue variants (compile-time MODE): plain / min-max / arg-max / residual adds / QKV (+ V^T) / fused output quantiser.  Outputs
+// leave through a swizzled per-warp staging tile and TMA tensor stores; an in-place residual (x = x + ...) is a TMA REDUCE-ADD
+// store (the L2 adds), the FSMN residual tile is fetched by TMA into the staging tile.  Further variants, all bit-identical:
+//   gemm_i8_fused_q_kernel  FFN1 in one pass: the dequantised tile waits in TMEM for the clip's max, then is quantised (below)
+//   AF                      the A operand quantised in the kernel from f32 + per-clip keys, resident across the n-blocks (opt-in)
+//   mc = 1 / CG2            2-CTA clusters: weight tile by TMA multicast / cta_group::2 pair MMAs 256 x 256 (opt-ins, measured equal)
 #include "gemm_i8_tc.cuh"
 #include <cuda.h>
 #include <stdlib.h>
