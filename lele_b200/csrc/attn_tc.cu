@@ -6,8 +6,8 @@
 //
 //   S = Q K^T          tcgen05.mma kind::tf32, 3xTF32 split (hi*hi + hi*lo + lo*hi: ~2^-21 relative,
 //                      i.e. f32-grade; plain TF32 would be 2^-11 and miss the 1e-4 bar)
-//   P = exp(S - max)   8 softmax warps read S from TMEM (two threads per query row, even / odd 32-key
-//                      chunks), same polynomial exp / libm tail split as the CPU reference
+//   P = exp(S - max)   16 softmax warps read S from TMEM (four threads per query row: group g owns the 32-key chunks g, g + 4,
+//                      g + 8), exp as one FFMA + MUFU.EX2 per element with the query scale folded into the exponent
 //   O = P V            P goes back into TENSOR MEMORY as the tf32 hi/lo A operand (hi in place of its S chunk,
 //                      lo in a 3-slot ring), 32 keys at a time, while the MMA warp consumes the previous chunks
 //                      (tcgen05.mma with A in TMEM); O accumulates in TMEM
