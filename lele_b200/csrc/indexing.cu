@@ -323,6 +323,46 @@ max_pool2d_plane_kernel(const float* __restrict__ x, PoolArgs a, float* __restri
     }
     out[((long long)blockIdx.z * a.oh + oy) * a.ow + ox] = m;
 }
+// stride 1, dilation 1 (the SPPF pools of the detection models: 5 x 5, pad 2): separable in shared memory.  A block owns a 64 x 16 output
+// tile of one plane: the input tile (+ halo, -inf outside the image: padded cells never win, conv2d.rs:1230) is staged once, a row pass
+// takes the kw-wide maxima, a column pass the kh-high ones -- kw + kh shared-memory reads per output instead of kw * kh cached global
+// loads.  max is order-independent, so the result is bit-identical to the window walk.
+constexpr int MP_TW = 64, MP_TH = 16, MP_KMAX = 7;
+__global__ void __launch_bounds__(256)
+max_pool2d_sep_kernel(const float* __restrict__ x, PoolArgs a, float* __restrict__ out) {
+    __shared__ float s_in[(MP_TH + MP_KMAX - 1) * (MP_TW + MP_KMAX - 1)];
+    __shared__ float s_h[(MP_TH + MP_KMAX - 1) * MP_TW];
+    const int ox0 = blockIdx.x * MP_TW, oy0 = blockIdx.y * MP_TH;
+    const int iw_t = MP_TW + a.kw - 1, ih_t = MP_TH + a.kh - 1;
+    const float* xp = x + (long long)blockIdx.z * a.h * a.w;
+    const int tx = threadIdx.x & (MP_TW - 1), ty0 = threadIdx.x >> 6;        // 64 columns x 4 rows of threads: no index divisions
+    for (int ty = ty0; ty < ih_t; ty += 4) {
+        const int iy = oy0 - a.pt + ty;
+        const bool row_in = iy >= 0 && iy < a.h;
+        for (int cx = tx; cx < iw_t; cx += MP_TW) {
+            const int ix = ox0 - a.pl + cx;
+            s_in[ty * iw_t + cx] = (row_in && ix >= 0 && ix < a.w) ? __ldg(xp + iy * a.w + ix) : -INFINITY;
+        }
+    }
+    __syncthreads();
+    for (int ty = ty0; ty < ih_t; ty += 4) {
+        const float* r = s_in + ty * iw_t + tx;
+        float m = r[0];
+        for (int kx = 1; kx < a.kw; ++kx) m = fmaxf(m, r[kx]);
+        s_h[ty * MP_TW + tx] = m;
+    }
+    __syncthreads();
+    const int ox = ox0 + tx;
+    if (ox < a.ow) {
+        for (int ty = ty0; ty < MP_TH; ty += 4) {
+            const int oy = oy0 + ty;
+            if (oy >= a.oh) break;
+            float m = s_h[ty * MP_TW + tx];
+            for (int ky = 1; ky < a.kh; ++ky) m = fmaxf(m, s_h[(ty + ky) * MP_TW + tx]);
+            out[((long long)blockIdx.z * a.oh + oy) * a.ow + ox] = m;
+        }
+    }
+}
 __global__ void max_pool2d_kernel(const float* __restrict__ x, long long nc, PoolArgs a, float* __restrict__ out) {
     const long long total = nc * a.oh * a.ow;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -548,6 +588,12 @@ extern "C" int lele_b200_max_pool2d(lele_b200_ctx* ctx, const float* x, int nb, 
     a.ow = (ceil_mode ? (nw + a.sw - 1) / a.sw : nw / a.sw) + 1;
     long long total = (long long)nb * c * a.oh * a.ow;
     if (total <= 0) return LELE_B200_OK;
+    if (a.sh == 1 && a.sw == 1 && a.dh == 1 && a.dw == 1 && kh <= MP_KMAX && kw <= MP_KMAX && a.ow >= 32 && a.oh >= 8 &&
+        (long long)nb * c <= 65535 && lb_ceil_div(a.oh, MP_TH) <= 65535 && lb_env_flag("LELE_B200_POOL_SEP", 1)) {
+        max_pool2d_sep_kernel<<<dim3(lb_ceil_div(a.ow, MP_TW), lb_ceil_div(a.oh, MP_TH), nb * c), 256, 0, ctx->stream>>>(x, a, out);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
+    }
     if ((long long)nb * c <= 65535 && lb_ceil_div(a.oh, 8) <= 65535) {
         max_pool2d_plane_kernel<<<dim3(lb_ceil_div(a.ow, 32), lb_ceil_div(a.oh, 8), nb * c), 256, 0, ctx->stream>>>(x, a, out);
         LB_LAUNCH_CHECK(ctx);

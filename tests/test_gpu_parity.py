@@ -234,6 +234,10 @@ def test_convs():
     x = rng.standard_normal((2, 3, 10, 11)).astype(np.float32)
     np.testing.assert_array_equal(G.max_pool2d(x, (5, 5), (2, 2, 2, 2), (1, 1)), R.max_pool2d(x, (5, 5), (2, 2, 2, 2), (1, 1)))
     np.testing.assert_array_equal(G.max_pool2d(x, (3, 3), (0, 0, 0, 0), (2, 2), (1, 1), True), R.max_pool2d(x, (3, 3), (0, 0, 0, 0), (2, 2), (1, 1), True))
+    # planes wide enough for the separable shared-memory kernel (stride 1): ragged tiles, asymmetric pads, a window that hangs over every edge
+    xl = rng.standard_normal((2, 3, 45, 83)).astype(np.float32)
+    for k, pads in (((5, 5), (2, 2, 2, 2)), ((3, 7), (1, 3, 1, 3)), ((5, 3), (0, 1, 4, 1)), ((7, 7), (3, 3, 3, 3))):
+        np.testing.assert_array_equal(G.max_pool2d(xl, k, pads, (1, 1)), R.max_pool2d(xl, k, pads, (1, 1)))
     for mode in ("asymmetric", "half_pixel"):
         np.testing.assert_array_equal(G.resize_nearest(x, scales=[1, 1, 2, 2], mode=mode), R.resize_nearest(x, scales=[1, 1, 2, 2], mode=mode))
         np.testing.assert_array_equal(G.resize_nearest(x, sizes=[2, 3, 7, 5], mode=mode), R.resize_nearest(x, sizes=[2, 3, 7, 5], mode=mode))
