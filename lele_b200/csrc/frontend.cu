@@ -254,48 +254,10 @@ __device__ __forceinline__ void fx_dft8(const float (&xr)[8], const float (&xi)[
     for (int j = 0; j < 4; ++j) { yr[2 * j] = er[j]; yi[2 * j] = ei[j]; yr[2 * j + 1] = orr[j]; yi[2 * j + 1] = oi[j]; }
 }
 
-__global__ void __launch_bounds__(FB_WARPS * 32)
-fbank_lfr_r8_kernel(const float* __restrict__ pcm, long long clip_stride, int n_clips, int frames, int t_lfr,
-                    FbankTables tb, const float2* __restrict__ tw64, const float2* __restrict__ tw512,
-                    float* __restrict__ mel_opt, float* __restrict__ lfr_out) {
-    __shared__ float s_re[FB_WARPS][8 * FX_P];
-    __shared__ float s_im[FB_WARPS][8 * FX_P];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gframe = (long long)blockIdx.x * FB_WARPS + warp;
-    if (gframe >= (long long)n_clips * frames) return;   // whole warp exits together
-    const int clip = (int)(gframe / frames), f = (int)(gframe % frames);
-    float* re = s_re[warp];
-    float* im = s_im[warp];
-    const float* p = pcm + (long long)clip * clip_stride + (long long)f * FB_HOP;
-
-    // 1. scale (x32768) and frame mean; 2. mean subtraction (same operation order as fbank_lfr_kernel)
-    float x[13];
-    float sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 13; ++i) {
-        const int j = lane + 32 * i;
-        x[i] = j < FB_FL ? __fmul_rn(__ldg(p + j), 32768.0f) : 0.0f;
-        sum += x[i];
-    }
-    sum = lb_warp_sum(sum);
-    const float mean = __fdiv_rn(sum, (float)FB_FL);
-#pragma unroll
-    for (int i = 0; i < 13; ++i) x[i] = __fsub_rn(x[i], mean);
-    // 3. pre-emphasis against the un-emphasised neighbour (sample j - 1 lives in the lane below, or in lane 31 of the
-    //    previous register), 4. Hann window; samples 400..511 are the zero padding
-    float v[16];
-#pragma unroll
-    for (int i = 0; i < 13; ++i) {
-        const int j = lane + 32 * i;
-        const float up = __shfl_up_sync(0xffffffffu, x[i], 1);
-        const float wrap = i > 0 ? __shfl_sync(0xffffffffu, x[i - 1], 31) : 0.0f;
-        const float prev = lane == 0 ? wrap : up;
-        float cur = x[i];
-        if (j >= 1) cur = __fsub_rn(cur, __fmul_rn(0.97f, prev));
-        v[i] = j < FB_FL ? __fmul_rn(cur, __ldg(tb.window + j)) : 0.0f;
-    }
-    v[13] = 0.0f; v[14] = 0.0f; v[15] = 0.0f;
-
+// The 512-point real-input transform of one warp: v[i] = x[lane + 32 i]; re / im = the warp's two 8 x FX_P exchange buffers.
+template <class Emit>
+__device__ __forceinline__ void fx_fft512(const float (&v)[16], float* re, float* im, const float2* __restrict__ tw64,
+                                          const float2* __restrict__ tw512, int lane, Emit emit) {
     // 5a. pass 1: point j = lane + 32 i = 64 n1 + m with m = lane + 32 (i & 1), n1 = i >> 1: two real 8-point transforms over n1,
     //     times W64^(n2 k1) (n2 = m >> 3), stored as A[k1][m]
 #pragma unroll
@@ -341,7 +303,8 @@ fbank_lfr_r8_kernel(const float* __restrict__ pcm, long long clip_stride, int n_
     }
     __syncwarp();
     // 5c. pass 3: the lane owns (k1, k2) = (lane / 8 + 4 h, lane % 8): 8-point transforms over n3 give X[k1 + 8 k2 + 64 k3];
-    // 6.  power spectrum of bins 0..256 (Im(0) = Im(256) = 0 as in kernels/fft.rs:124-128) into re[0..256]
+    //     bins 0..256 are handed to emit(k, re, im) with Im(0) = Im(256) = 0 (kernels/fft.rs:124-128); emit may overwrite re[] / im[]
+    //     (every input of the pass has been read)
     {
         const int k2 = lane & 7;
         float ar[2][8], ai[2][8];
@@ -359,14 +322,57 @@ fbank_lfr_r8_kernel(const float* __restrict__ pcm, long long clip_stride, int n_
             fx_dft8(ar[h], ai[h], yr, yi);
             const int k0 = k1 + 8 * k2;
 #pragma unroll
-            for (int k3 = 0; k3 < 4; ++k3) {
-                const float r = yr[k3], q = (k0 == 0 && k3 == 0) ? 0.0f : yi[k3];
-                re[k0 + 64 * k3] = __fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q));
-            }
-            if (k0 == 0) re[256] = __fmul_rn(yr[4], yr[4]);
+            for (int k3 = 0; k3 < 4; ++k3) emit(k0 + 64 * k3, yr[k3], (k0 == 0 && k3 == 0) ? 0.0f : yi[k3]);
+            if (k0 == 0) emit(256, yr[4], 0.0f);
         }
     }
     __syncwarp();
+}
+
+__global__ void __launch_bounds__(FB_WARPS * 32)
+fbank_lfr_r8_kernel(const float* __restrict__ pcm, long long clip_stride, int n_clips, int frames, int t_lfr,
+                    FbankTables tb, const float2* __restrict__ tw64, const float2* __restrict__ tw512,
+                    float* __restrict__ mel_opt, float* __restrict__ lfr_out) {
+    __shared__ float s_re[FB_WARPS][8 * FX_P];
+    __shared__ float s_im[FB_WARPS][8 * FX_P];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gframe = (long long)blockIdx.x * FB_WARPS + warp;
+    if (gframe >= (long long)n_clips * frames) return;   // whole warp exits together
+    const int clip = (int)(gframe / frames), f = (int)(gframe % frames);
+    float* re = s_re[warp];
+    float* im = s_im[warp];
+    const float* p = pcm + (long long)clip * clip_stride + (long long)f * FB_HOP;
+
+    // 1. scale (x32768) and frame mean; 2. mean subtraction (same operation order as fbank_lfr_kernel)
+    float x[13];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        const int j = lane + 32 * i;
+        x[i] = j < FB_FL ? __fmul_rn(__ldg(p + j), 32768.0f) : 0.0f;
+        sum += x[i];
+    }
+    sum = lb_warp_sum(sum);
+    const float mean = __fdiv_rn(sum, (float)FB_FL);
+#pragma unroll
+    for (int i = 0; i < 13; ++i) x[i] = __fsub_rn(x[i], mean);
+    // 3. pre-emphasis against the un-emphasised neighbour (sample j - 1 lives in the lane below, or in lane 31 of the
+    //    previous register), 4. Hann window; samples 400..511 are the zero padding
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        const int j = lane + 32 * i;
+        const float up = __shfl_up_sync(0xffffffffu, x[i], 1);
+        const float wrap = i > 0 ? __shfl_sync(0xffffffffu, x[i - 1], 31) : 0.0f;
+        const float prev = lane == 0 ? wrap : up;
+        float cur = x[i];
+        if (j >= 1) cur = __fsub_rn(cur, __fmul_rn(0.97f, prev));
+        v[i] = j < FB_FL ? __fmul_rn(cur, __ldg(tb.window + j)) : 0.0f;
+    }
+    v[13] = 0.0f; v[14] = 0.0f; v[15] = 0.0f;
+
+    // 5. FFT-512 (three radix-8 passes); 6. power spectrum of bins 0..256 into re[0..256]
+    fx_fft512(v, re, im, tw64, tw512, lane, [&](int k, float r, float q) { re[k] = __fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q)); });
     // 7. sparse mel (sequential tap order, mel.rs:92-104) + log(max(x, 1e-5))
     for (int mI = lane; mI < FB_NM; mI += 32) {
         int s = __ldg(tb.mel_start + mI), len = __ldg(tb.mel_len + mI), off = __ldg(tb.mel_off + mI);
@@ -393,6 +399,56 @@ fbank_lfr_r8_kernel(const float* __restrict__ pcm, long long clip_stride, int n_
                 for (int q = lane; q < FB_NM; q += 32) dst[q] = im[q];
             }
         }
+    }
+}
+
+// W64^k | W512^k as float2, computed in double (the radix-8 transform's twiddles)
+static int get_fft512r8_tables(lele_b200_ctx* ctx, const float2** tw64, const float2** tw512) {
+    void* tw = nullptr;
+    auto it = ctx->tables.find("fft512r8");
+    if (it == ctx->tables.end()) {
+        std::vector<float> h(2 * (64 + 512));
+        for (int k = 0; k < 64; ++k) { h[2 * k] = (float)cos(-2.0 * M_PI * k / 64.0); h[2 * k + 1] = (float)sin(-2.0 * M_PI * k / 64.0); }
+        for (int k = 0; k < 512; ++k) { h[128 + 2 * k] = (float)cos(-2.0 * M_PI * k / 512.0); h[128 + 2 * k + 1] = (float)sin(-2.0 * M_PI * k / 512.0); }
+        int rc = lb_table(ctx, "fft512r8", h.data(), h.size() * sizeof(float), &tw);
+        if (rc) return rc;
+    } else tw = it->second;
+    *tw64 = (const float2*)tw; *tw512 = (const float2*)tw + 64;
+    return LELE_B200_OK;
+}
+
+// rFFT rows / STFT frames of n_fft = 512 on the same register-blocked transform: one warp per frame (the generic kernel below spends a
+// CTA and a radix-2 shared-memory network per frame).  mode: 0 re | im planes, 1 interleaved, 2 power.
+__global__ void __launch_bounds__(FB_WARPS * 32)
+stft512_r8_kernel(const float* __restrict__ sig, int signal_len, int hop, int win, const float* __restrict__ window,
+                  const float2* __restrict__ tw64, const float2* __restrict__ tw512, int mode, int frames,
+                  float* __restrict__ out0, float* __restrict__ out1) {
+    __shared__ float s_re[FB_WARPS][8 * FX_P];
+    __shared__ float s_im[FB_WARPS][8 * FX_P];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * FB_WARPS + warp;
+    if (row >= frames) return;                           // whole warp exits together
+    float* re = s_re[warp];
+    float* im = s_im[warp];
+    const long long start = (long long)row * hop;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = lane + 32 * i;
+        float x = 0.0f;
+        if (j < win && start + j < signal_len) {
+            x = __ldg(sig + start + j);
+            if (window) x = __fmul_rn(x, __ldg(window + j));
+        }
+        v[i] = x;
+    }
+    fx_fft512(v, re, im, tw64, tw512, lane, [&](int k, float r, float q) { re[k] = r; im[k] = q; });
+    constexpr int NFR = FB_NF / 2 + 1;
+    for (int k = lane; k < NFR; k += 32) {
+        const float r = re[k], q = im[k];
+        if (mode == 0) { out0[(long long)row * NFR + k] = r; out1[(long long)row * NFR + k] = q; }
+        else if (mode == 1) { out0[((long long)row * NFR + k) * 2] = r; out0[((long long)row * NFR + k) * 2 + 1] = q; }
+        else out0[(long long)row * NFR + k] = __fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q));
     }
 }
 
@@ -460,17 +516,10 @@ extern "C" int lele_b200_frontend_compute(lele_b200_ctx* ctx, const float* pcm, 
     if (rc) return rc;
     long long total = (long long)n_clips * frames;
     if (lb_env_flag("LELE_B200_FBANK_R8", 1)) {
-        void* tw = nullptr;                                     // W64^k | W512^k as float2, computed in double
-        auto it = ctx->tables.find("fft512r8");
-        if (it == ctx->tables.end()) {
-            std::vector<float> h(2 * (64 + 512));
-            for (int k = 0; k < 64; ++k) { h[2 * k] = (float)cos(-2.0 * M_PI * k / 64.0); h[2 * k + 1] = (float)sin(-2.0 * M_PI * k / 64.0); }
-            for (int k = 0; k < 512; ++k) { h[128 + 2 * k] = (float)cos(-2.0 * M_PI * k / 512.0); h[128 + 2 * k + 1] = (float)sin(-2.0 * M_PI * k / 512.0); }
-            rc = lb_table(ctx, "fft512r8", h.data(), h.size() * sizeof(float), &tw);
-            if (rc) return rc;
-        } else tw = it->second;
+        const float2 *tw64, *tw512;
+        if ((rc = get_fft512r8_tables(ctx, &tw64, &tw512))) return rc;
         fbank_lfr_r8_kernel<<<lb_ceil_div(total, FB_WARPS), FB_WARPS * 32, 0, ctx->stream>>>(
-            pcm, clip_stride, n_clips, frames, t_lfr, tb, (const float2*)tw, (const float2*)tw + 64, mel_opt, lfr_out);
+            pcm, clip_stride, n_clips, frames, t_lfr, tb, tw64, tw512, mel_opt, lfr_out);
     } else
         fbank_lfr_kernel<<<lb_ceil_div(total, FB_WARPS), FB_WARPS * 32, 0, ctx->stream>>>(
             pcm, clip_stride, n_clips, frames, t_lfr, tb, mel_opt, lfr_out);
@@ -588,6 +637,14 @@ extern "C" int lele_b200_rfft(lele_b200_ctx* ctx, const float* x, int n_rows, in
     LB_ENTER(ctx);
     LB_REQUIRE(is_pow2(n) && n >= 2 && n <= 4096, "rfft: n=%d must be a power of two in [2,4096] (kernels/fft.rs:4)", n);
     if (n_rows == 0) return LELE_B200_OK;
+    if (n == FB_NF && lb_env_flag("LELE_B200_FFT_R8", 1)) {
+        const float2 *tw64, *tw512;
+        int rc8 = get_fft512r8_tables(ctx, &tw64, &tw512);
+        if (rc8) return rc8;
+        stft512_r8_kernel<<<lb_ceil_div(n_rows, FB_WARPS), FB_WARPS * 32, 0, ctx->stream>>>(x, n_rows * n, n, n, nullptr, tw64, tw512, 0, n_rows, out_re, out_im);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
+    }
     const float *tr, *ti; const int* br;
     int rc = get_fft_tables(ctx, n, &tr, &ti, &br);
     if (rc) return rc;
@@ -620,6 +677,13 @@ extern "C" int lele_b200_stft(lele_b200_ctx* ctx, const float* signal, int signa
             if (rc) return rc;
         } else p = it->second;
         wdev = (const float*)p;
+    }
+    if (n_fft == FB_NF && lb_env_flag("LELE_B200_FFT_R8", 1)) {
+        const float2 *tw64, *tw512;
+        if ((rc = get_fft512r8_tables(ctx, &tw64, &tw512))) return rc;
+        stft512_r8_kernel<<<lb_ceil_div(frames, FB_WARPS), FB_WARPS * 32, 0, ctx->stream>>>(signal, signal_len, hop, win, wdev, tw64, tw512, power ? 2 : 1, frames, out, nullptr);
+        LB_LAUNCH_CHECK(ctx);
+        return LELE_B200_OK;
     }
     rfft_rows_kernel<<<frames, 256, 2 * n_fft * sizeof(float), ctx->stream>>>(signal, signal_len, n_fft, hop, win, wdev, tr, ti, br,
                                                                                 power ? 2 : 1, out, nullptr);

@@ -57,6 +57,14 @@ def test_cmvn_lfr_stft_rfft():
     close(G.stft(sig, 256, 128, 256), R.stft(sig, 256, 128, 256), atol_frac=1e-5)
     close(G.stft(sig, 256, 128, 256, power=True), R.stft(sig, 256, 128, 256, power=True), atol_frac=1e-5)
     close(G.stft(sig[:100], 256, 64, 256, power=True), R.stft(sig[:100], 256, 64, 256, power=True), atol_frac=1e-5)  # shorter than a window
+    # n_fft = 512 takes the register-blocked radix-8 transform (one warp per frame): the front-end's geometry (win 400, hop 160, explicit
+    # window), the default periodic Hann, a signal that ends inside the last frame's window, several rows of rfft
+    sig5 = (np.sin(np.arange(4000, dtype=np.float32) * np.float32(0.05)) + 0.1 * rng.standard_normal(4000)).astype(np.float32)
+    w400 = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(400) / 399)).astype(np.float32)
+    close(G.stft(sig5, 512, 160, 400, window=w400), R.stft(sig5, 512, 160, 400, window=w400), atol_frac=1e-5)
+    close(G.stft(sig5, 512, 160, 400, window=w400, power=True), R.stft(sig5, 512, 160, 400, window=w400, power=True), atol_frac=1e-5)
+    close(G.stft(sig5, 512, 128, 512), R.stft(sig5, 512, 128, 512), atol_frac=1e-5)
+    close(G.stft(sig5[:300], 512, 64, 512, power=True), R.stft(sig5[:300], 512, 64, 512, power=True), atol_frac=1e-5)
     for n in (8, 64, 512, 1024):
         v = rng.standard_normal(n).astype(np.float32)
         re, im = G.rfft(v); rr, ri = R.rfft(v)
